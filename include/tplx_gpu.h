@@ -1,0 +1,165 @@
+/*
+ * tplx_gpu.h — C ABI of libtplx_gpu.so, the B200 executor for Tuplex's normal-case
+ * TransformStage row pipeline.
+ *
+ * What this boundary replaces in the reference (paths relative to /root/reference/tuplex/):
+ *   - IBackend::execute(PhysicalStage*)            core/include/ee/IBackend.h:29-46
+ *   - LocalBackend::executeTransformStage          core/src/ee/local/LocalBackend.cc:815-1252
+ *   - the JIT'd stage function read_block_f + its per-row callbacks
+ *                                                  core/include/physical/CodeDefs.h:43-116
+ *   - TransformTask (per-partition hot loop)       core/src/physical/TransformTask.cc:382-513,682-722
+ * The deliberate departure from the inner ABI: no per-row callbacks cross the boundary;
+ * blocks of rows go in, blocks of rows (+ exception records) come out.
+ *
+ * Conventions: extern "C", plain pointers and sizes, int32 status codes
+ * (0 = OK, negative = tplx_status, message via tplx_gpu_last_error()). Row-level errors never
+ * fail a call — they become exception records (IExceptionableTask.h:22-36). Buffers passed in
+ * are borrowed for the duration of the call unless stated; buffers handed out are caller-owned
+ * (caller allocates, library fills). All entry points are thread-safe per handle.
+ * There is NO CPU fallback: every compute entry point fails with TPLX_E_NODEVICE when no
+ * CUDA device is usable.
+ */
+#ifndef TPLX_GPU_H
+#define TPLX_GPU_H
+
+#include <stdint.h>
+#include "tplx_ir.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum tplx_status {
+    TPLX_OK = 0,
+    TPLX_E_NODEVICE = -1,
+    TPLX_E_CUDA = -2,
+    TPLX_E_BADDESC = -3,
+    TPLX_E_BADARG = -4,
+    TPLX_E_NOMEM = -5,
+    TPLX_E_UNSUPPORTED = -6,
+    TPLX_E_OVERFLOW = -7,
+};
+
+typedef struct tplx_stage tplx_stage;   /* replaces TransformStage + compiled functor */
+typedef struct tplx_block tplx_block;   /* a device-resident column block (input) */
+typedef struct tplx_result tplx_result; /* outputs of one block through a stage */
+
+/* One input column of a column block. Fixed-width types: `data` = n_rows 8-byte values.
+ * TPLX_T_STR: `data` = concatenated bytes (no terminators), `offsets` = n_rows+1 uint32. */
+typedef struct tplx_column {
+    uint8_t type; /* tplx_type */
+    uint8_t pad[7];
+    const void *data;
+    const uint32_t *offsets;
+    uint64_t data_bytes;
+} tplx_column;
+
+/* Exception record as produced by the device (fixed width); tplx_gpu_result_exception_partition
+ * expands it to the reference layout [rowNo, ecCode, opID, size, row bytes]. */
+typedef struct tplx_exception_rec {
+    int64_t row;    /* input row index inside the submitted block */
+    int64_t row_no; /* TransformTask::_outputRowCounter semantics (TransformTask.cc:764,885) */
+    int64_t code;   /* tplx_exception_code / ExceptionCodes.h */
+    int64_t op_id;  /* reference operator id */
+} tplx_exception_rec;
+
+typedef struct tplx_result_info {
+    uint64_t n_in_rows;
+    uint64_t n_out_rows;
+    uint64_t n_exceptions;
+    uint64_t out_str_bytes[TPLX_MAX_COLS]; /* per output column; 0 for fixed-width */
+    double kernel_ms;    /* CUDA-event time of the stage kernel(s) on the device stream */
+    double total_ms;     /* CUDA-event time submit→results ready (incl. H2D when input was on host) */
+    uint32_t kernel_launches;
+    uint32_t pad;
+} tplx_result_info;
+
+/* ---- process / devices ------------------------------------------------------------------ */
+/* Select devices (NULL,0 = device 0 only). Mirrors LocalBackend's executor start-up
+ * (LocalEngine.cc:41-115). */
+int32_t tplx_gpu_init(const int32_t *devices, int32_t n);
+int32_t tplx_gpu_device_count(void);
+int32_t tplx_gpu_shutdown(void);
+const char *tplx_gpu_last_error(void);
+/* name + SM count + memory of a selected device; buf may be NULL */
+int32_t tplx_gpu_device_info(int32_t device, char *name_buf, int32_t buf_len, int32_t *sm_count,
+                             uint64_t *mem_bytes);
+
+/* ---- stage ------------------------------------------------------------------------------ */
+/* desc = serialized tplx_stage_header + sections (tplx_ir.h). Replaces TransformStage::compile
+ * (TransformStage.cc:763-914): validates the program and sizes launch configuration. */
+int32_t tplx_gpu_stage_create(const void *desc, uint64_t desc_bytes, tplx_stage **out);
+int32_t tplx_gpu_stage_destroy(tplx_stage *stage);
+
+/* ---- input blocks ----------------------------------------------------------------------- */
+/* Upload a host column block to `device` (pinned or pageable host memory). */
+int32_t tplx_gpu_block_upload(int32_t device, const tplx_column *cols, uint32_t n_cols, uint64_t n_rows,
+                              tplx_block **out);
+/* Wrap columns that already live in device memory on `device` (no copy, caller keeps ownership). */
+int32_t tplx_gpu_block_wrap_device(int32_t device, const tplx_column *cols, uint32_t n_cols,
+                                   uint64_t n_rows, tplx_block **out);
+/* K5: build a column block from reference-format partitions (Partition.h:130-139: int64 numRows then
+ * rows in Serializer row format, Serializer.cc:1016-1117) that lie in host memory. */
+int32_t tplx_gpu_block_from_partitions(int32_t device, const uint8_t *const *partitions,
+                                       const uint64_t *partition_bytes, uint32_t n_partitions,
+                                       const uint8_t *col_types, uint32_t n_cols, tplx_block **out);
+int32_t tplx_gpu_block_rows(const tplx_block *block, uint64_t *n_rows);
+int32_t tplx_gpu_block_free(tplx_block *block);
+
+/* ---- execution -------------------------------------------------------------------------- */
+/* Run the stage over one block (asynchronously on the device's stream; results are complete
+ * when tplx_gpu_result_info returns). first_row_no seeds the exception row counter so that
+ * several blocks of one task number their rows like TransformTask does (not reset between
+ * input partitions of a task, TransformTask.cc:885). Replaces the functor call at
+ * TransformTask.cc:702. */
+int32_t tplx_gpu_stage_run(tplx_stage *stage, const tplx_block *block, int64_t first_row_no,
+                           tplx_result **out);
+/* Convenience for host callers: upload + run + free the device block (timed as one unit). */
+int32_t tplx_gpu_stage_run_host(tplx_stage *stage, int32_t device, const tplx_column *cols,
+                                uint32_t n_cols, uint64_t n_rows, int64_t first_row_no,
+                                tplx_result **out);
+
+int32_t tplx_gpu_result_info(tplx_result *res, tplx_result_info *info); /* synchronises */
+/* Copy output column `col` to host: fixed-width -> data (n_out_rows*8 bytes);
+ * TPLX_T_STR -> data (out_str_bytes[col]) and offsets (n_out_rows+1 uint32). */
+int32_t tplx_gpu_result_fetch_column(tplx_result *res, uint32_t col, void *data, uint32_t *offsets);
+/* Device pointers of an output column (valid until tplx_gpu_result_free). */
+int32_t tplx_gpu_result_device_column(tplx_result *res, uint32_t col, const void **data,
+                                      const uint32_t **offsets);
+int32_t tplx_gpu_result_fetch_exceptions(tplx_result *res, tplx_exception_rec *recs /* n_exceptions */);
+/* AGGREGATE endpoint: the block's partial aggregate, one 8-byte value per accumulator, already
+ * combined with the accumulator's init (per-task intermediate, BlockBasedTaskBuilder.cc:185-224). */
+int32_t tplx_gpu_result_fetch_aggregate(tplx_result *res, int64_t *acc_bits /* n_accs */);
+/* Output rows in the reference's Partition byte format (int64 numRows + Serializer rows),
+ * split into partitions of at most partition_bytes like rowToMemorySink (TransformTask.h:47-92).
+ * Call with buf == NULL to get the required size and partition count. */
+int32_t tplx_gpu_result_partitions(tplx_result *res, uint64_t partition_bytes, uint8_t *buf,
+                                   uint64_t buf_bytes, uint64_t *bytes_needed, uint64_t *part_offsets,
+                                   uint32_t max_parts, uint32_t *n_parts);
+/* Exception rows in the reference's exception-partition format: int64 numRows, then per record
+ * int64 rowNo, ecCode, opID, size, followed by the ORIGINAL input row in normal-case input row
+ * format (IExceptionableTask.h:22-36, TuplexSourceTaskBuilder.cc:79,186-193). */
+int32_t tplx_gpu_result_exception_partition(tplx_result *res, uint8_t *buf, uint64_t buf_bytes,
+                                            uint64_t *bytes_needed);
+int32_t tplx_gpu_result_free(tplx_result *res);
+
+/* ---- hash endpoint (aggregateByKey / unique) ---------------------------------------------- */
+/* The per-stage, per-device hash table accumulates over every tplx_gpu_stage_run of the stage
+ * (TransformTask.cc:791-866 per-task tables + LocalBackend.cc:2219-2376 merge, done in one
+ * table here). hash_finish materialises it as a result whose output columns are
+ * key columns followed by one column per accumulator (TransformStage.cc:473-528,568-608). */
+int32_t tplx_gpu_stage_hash_reserve(tplx_stage *stage, int32_t device, uint64_t expected_keys);
+int32_t tplx_gpu_stage_hash_finish(tplx_stage *stage, int32_t device, tplx_result **out);
+/* Merge packed (key columns, accumulator columns) rows — e.g. received from another GPU over
+ * NCCL — into this device's table using the accumulators' combine operation. */
+int32_t tplx_gpu_stage_hash_merge(tplx_stage *stage, const tplx_block *packed);
+/* Like hash_finish but the accumulator columns hold raw partials (initial value not applied): the form
+ * that is exchanged between GPUs before the owner of a key range merges and finishes. */
+int32_t tplx_gpu_stage_hash_export_raw(tplx_stage *stage, int32_t device, tplx_result **out);
+/* Drop the device's table (start a new job on the same stage). */
+int32_t tplx_gpu_stage_hash_reset(tplx_stage *stage, int32_t device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TPLX_GPU_H */

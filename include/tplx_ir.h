@@ -1,0 +1,228 @@
+/*
+ * tplx_ir.h — the stage descriptor ("op program") that replaces the LLVM bitcode a
+ * reference TransformStage carries (tuplex/core/include/physical/TransformStage.h:67-514,
+ * tuplex/core/src/physical/StageBuilder.cc:1499-1535). A reference stage holds bitcode +
+ * symbol names; a non-LLVM backend needs the operator list in a form it can execute, so the
+ * planner side (tuplex_b200/frontend.py, or a C++ planner) lowers every UDF of the stage to
+ * this flat, typed, predicated register program. The same bytes are consumed by
+ *   - the CUDA VM (tuplex_b200/csrc/vm.cuh),
+ *   - the CPU oracle (oracle/tplx_oracle.c: tplx_oracle_run_program).
+ *
+ * Semantics of every op follow the reference codegen/runtime; the file:line each op restates
+ * is cited beside it (paths relative to /root/reference/tuplex/).
+ *
+ * This header is also parsed by tuplex_b200/ir.py (regex over the enum bodies) so that the
+ * Python side cannot drift from the C side. Keep one enumerator per line: `NAME = value,`.
+ */
+#ifndef TPLX_IR_H
+#define TPLX_IR_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TPLX_IR_MAGIC 0x58504C54u /* "TPLX" */
+#define TPLX_IR_VERSION 3u
+#define TPLX_NOSLOT 0xFFFFu
+#define TPLX_MAX_COLS 64
+#define TPLX_MAX_ACCS 16
+#define TPLX_MAX_KEYS 8
+
+/* column / value types (python::Type subset on the normal-case path, utils/include/TypeSystem.h) */
+enum tplx_type {
+    TPLX_T_I64 = 0,
+    TPLX_T_F64 = 1,
+    TPLX_T_BOOL = 2, /* stored as i64 0/1 in row format (Serializer.cc:1069) and as 8-byte column */
+    TPLX_T_STR = 3,  /* column block: uint32 offsets[n+1] + bytes (no NUL); row format: NUL-terminated */
+};
+
+/* stage endpoints (TransformStage::outputMode, EndPointMode in core/include/physical/PhysicalStage.h) */
+enum tplx_endpoint {
+    TPLX_EP_MEMORY = 0,    /* rows out, input order preserved (LocalBackend.cc:1104-1152) */
+    TPLX_EP_AGGREGATE = 1, /* AGG_GENERAL: one row out (PipelineBuilder.cc:2525-2608) */
+    TPLX_EP_HASH = 2,      /* AGG_BY_KEY / AGG_UNIQUE (PipelineBuilder.cc:1108-1400) */
+};
+
+/* accumulator kinds recognised in aggregate UDFs `lambda a, x: a (+) g(x)` (AggregateFunctions.cc:152-243) */
+enum tplx_acc_kind {
+    TPLX_ACC_SUM_I64 = 0, /* wrapping add (BlockGeneratorVisitor.cc:372-456) */
+    TPLX_ACC_SUM_F64 = 1, /* IEEE add, fixed documented tree (DESIGN.md "reduction tree") */
+    TPLX_ACC_MIN_I64 = 2,
+    TPLX_ACC_MAX_I64 = 3,
+    TPLX_ACC_MIN_F64 = 4,
+    TPLX_ACC_MAX_F64 = 5,
+};
+
+/* compare predicates: signed integer / ordered float (BlockGeneratorVisitor.cc:776-836) */
+enum tplx_cmp {
+    TPLX_CMP_EQ = 0,
+    TPLX_CMP_NE = 1, /* float: FCMP_ONE — false when either side is NaN (reference quirk) */
+    TPLX_CMP_LT = 2,
+    TPLX_CMP_LE = 3,
+    TPLX_CMP_GT = 4,
+    TPLX_CMP_GE = 5,
+};
+
+/* lazy ASCII case transform carried by a string value (StringFunctions.cc:71-110) */
+enum tplx_strflag {
+    TPLX_SF_NONE = 0,
+    TPLX_SF_LOWER = 1,
+    TPLX_SF_UPPER = 2,
+};
+
+/* slice flags (BlockGeneratorVisitor.cc:4469-4690; stride is always 1 on this path) */
+enum tplx_sliceflag {
+    TPLX_SL_HAS_START = 1,
+    TPLX_SL_HAS_END = 2,
+};
+
+/* exception codes used on this path (utils/include/ExceptionCodes.h:24-120) */
+enum tplx_exception_code {
+    TPLX_EC_SUCCESS = 0,
+    TPLX_EC_NORMALCASEVIOLATION = 7,
+    TPLX_EC_NULLERROR = 50,
+    TPLX_EC_PYTHON_PARALLELIZE = 80,
+    TPLX_EC_INDEXERROR = 111,
+    TPLX_EC_TYPEERROR = 129,
+    TPLX_EC_VALUEERROR = 135,
+    TPLX_EC_ZERODIVISIONERROR = 136,
+};
+
+/*
+ * Opcodes. A value lives in 8-byte slots: scalars (i64 / f64 bits / bool 0-1) take one slot,
+ * strings take two consecutive slots: [s] = byte address (generic pointer), [s+1] = len | flags<<32.
+ * Every instruction is predicated: it executes for a row iff the row is alive and
+ * (guard == TPLX_NOSLOT or slot[guard] != 0). Python if/elif/else and early returns are
+ * if-converted by the frontend into guards + TPLX_OP_SEL, so untaken branches can never raise.
+ */
+enum tplx_op {
+    TPLX_OP_NOP = 0,
+    /* loads */
+    TPLX_OP_LDCOL = 1,  /* dst <- input column imm at this row; flags = tplx_type */
+    TPLX_OP_LDI = 2,    /* dst <- imm (i64, f64 bits or bool) */
+    TPLX_OP_LDS = 3,    /* dst <- view of constant pool bytes [imm, imm+imm2) */
+    TPLX_OP_MOV = 4,    /* dst <- a ; flags = slot count (1|2) */
+    TPLX_OP_SEL = 5,    /* dst <- c ? a : b ; flags = slot count (1|2) */
+    TPLX_OP_LDROW = 6,  /* dst <- index of this row inside the block (used to merge CPython-resolved rows in order) */
+    /* i64 arithmetic: wrapping, no overflow detection (BlockGeneratorVisitor.cc:152-313,372-495) */
+    TPLX_OP_IADD = 10,
+    TPLX_OP_ISUB = 11,
+    TPLX_OP_IMUL = 12,
+    TPLX_OP_IFLOORDIV = 13, /* ZeroDivisionError; floor fix-up (LLVMEnvironment.cc:1377-1399) */
+    TPLX_OP_IMOD = 14,      /* ZeroDivisionError; floor fix-up (LLVMEnvironment.cc:1402-1430) */
+    TPLX_OP_INEG = 15,
+    TPLX_OP_IAND = 16,
+    TPLX_OP_IOR = 17,
+    TPLX_OP_IXOR = 18,
+    TPLX_OP_ISHL = 19, /* BlockGeneratorVisitor.cc:612-670 */
+    TPLX_OP_ISHR = 20,
+    TPLX_OP_IABS = 21,
+    /* f64 arithmetic: single IEEE-754 ops, no contraction (BlockGeneratorVisitor.cc:152-584) */
+    TPLX_OP_FADD = 30,
+    TPLX_OP_FSUB = 31,
+    TPLX_OP_FMUL = 32,
+    TPLX_OP_FDIV = 33,      /* ZeroDivisionError when divisor == 0.0 (divisionInst :497-530) */
+    TPLX_OP_FMOD = 34,      /* frem + sign fix (LLVMEnvironment.cc:1415-1422); ZeroDivisionError */
+    TPLX_OP_FNEG = 35,
+    TPLX_OP_FFLOORDIV = 36, /* both sides fptosi, floor-div, sitofp (integerDivisionInst :360-365) */
+    TPLX_OP_FABS = 37,
+    /* conversions (FunctionRegistry.cc:83-148, upCast) */
+    TPLX_OP_I2F = 40, /* sitofp */
+    TPLX_OP_F2I = 41, /* fptosi (trunc) — int(f64) */
+    /* comparisons -> bool; flags = tplx_cmp */
+    TPLX_OP_ICMP = 50,
+    TPLX_OP_FCMP = 51,
+    /* logical on 0/1 values */
+    TPLX_OP_BAND = 55,
+    TPLX_OP_BOR = 56,
+    TPLX_OP_BNOT = 57,
+    /* strings (ASCII bytes; FunctionRegistry.cc / runtime/src/Runtime.cc / StringFunctions.cc) */
+    TPLX_OP_SLEN = 60,     /* len(s) */
+    TPLX_OP_SFIND = 61,    /* s.find(b): strstr (FunctionRegistry.cc:2165-2188); -1 if absent */
+    TPLX_OP_SRFIND = 62,   /* s.rfind(b): std::string::rfind (Runtime.cc:387-397) */
+    TPLX_OP_SIN = 63,      /* a in b -> strstr(b, a) != NULL (BlockGeneratorVisitor.cc:838-880) */
+    TPLX_OP_SEQ = 64,      /* strcmp == 0 ; flags bit0 = negate (!=) */
+    TPLX_OP_SSLICE = 65,   /* a[b:c], flags = tplx_sliceflag (processSliceIndex :4618-4690) */
+    TPLX_OP_SINDEX = 66,   /* a[b] one-char string; IndexError (BlockGeneratorVisitor.cc:3869-3903) */
+    TPLX_OP_SLOWER = 67,   /* lazy flag (StringFunctions.cc:71-89) */
+    TPLX_OP_SUPPER = 68,   /* lazy flag (StringFunctions.cc:91-108) */
+    TPLX_OP_SREPLACE = 69, /* a.replace(b, c), materialises (Runtime.cc:401-540) */
+    TPLX_OP_SCONCAT = 70,  /* a + b, materialises (BlockGeneratorVisitor.cc:381-436) */
+    TPLX_OP_SFMTD = 71,    /* '%[0][w]d' % a : snprintf %d of (int)a, imm=width, flags bit0=zero pad,
+                              constant prefix/suffix via b/c string slots (BlockGeneratorVisitor.cc:675-775) */
+    TPLX_OP_S2I = 72,      /* int(s): fast_atoi64 (Runtime.cc:319-341, StringUtils.cc:22-63); ValueError */
+    TPLX_OP_STRUTH = 73,   /* bool(s): len > 0 */
+    TPLX_OP_SSTARTS = 74,  /* a.startswith(b) */
+    TPLX_OP_SENDS = 75,    /* a.endswith(b) */
+    TPLX_OP_I2S = 76,      /* str(i64), materialises */
+    TPLX_OP_SSTRIP = 77,   /* a.strip() whitespace view; flags bit0 = left, bit1 = right */
+    /* row control */
+    TPLX_OP_FILTER = 90, /* alive &= slot[a] != 0 (PipelineBuilder.cc:615-700) */
+    TPLX_OP_RAISE = 91,  /* unconditional (guarded) exception imm = code */
+};
+
+/* 32-byte instruction */
+typedef struct tplx_instr {
+    uint8_t op;     /* tplx_op */
+    uint8_t flags;  /* op specific */
+    uint16_t dst;   /* destination slot or TPLX_NOSLOT */
+    uint16_t a;     /* source slots */
+    uint16_t b;
+    uint16_t c;
+    uint16_t guard; /* bool slot or TPLX_NOSLOT */
+    uint16_t opidx; /* index into the stage's operator-id table (exception attribution) */
+    uint16_t pad;
+    int64_t imm;
+    int64_t imm2;
+} tplx_instr;
+
+typedef struct tplx_outcol {
+    uint16_t slot; /* value slot at program end */
+    uint8_t type;  /* tplx_type */
+    uint8_t pad;
+} tplx_outcol;
+
+typedef struct tplx_acc {
+    uint8_t kind;  /* tplx_acc_kind */
+    uint8_t pad;
+    uint16_t slot; /* per-row value g(x) */
+    uint32_t pad2;
+    int64_t init;  /* initial value bits (i64 or f64) — applied once per block, like the per-task
+                      intermediate in BlockBasedTaskBuilder.cc:185-206 */
+} tplx_acc;
+
+/*
+ * Serialized stage descriptor layout (little endian, 8-byte aligned sections):
+ *   tplx_stage_header
+ *   uint8_t  in_types[n_in_cols]      (padded to 8)
+ *   tplx_outcol out_cols[n_out_cols]  (padded to 8)   -- MEMORY: output row; HASH: key columns first
+ *   tplx_acc accs[n_accs]
+ *   int64_t  opids[n_ops]             -- reference operator ids (LogicalOperator.h:52-59, start 100000)
+ *   tplx_instr instrs[n_instr]
+ *   uint8_t  const_pool[const_bytes]  (padded to 8)
+ */
+typedef struct tplx_stage_header {
+    uint32_t magic;
+    uint32_t version;
+    uint32_t total_bytes;
+    uint16_t n_in_cols;
+    uint16_t n_out_cols;
+    uint16_t n_accs;
+    uint16_t n_keys;      /* HASH endpoint: first n_keys out_cols are the key */
+    uint16_t n_ops;
+    uint16_t n_slots;     /* register file size in 8-byte slots */
+    uint32_t n_instr;
+    uint32_t const_bytes;
+    uint8_t endpoint;     /* tplx_endpoint */
+    uint8_t pad0;
+    uint16_t split_pc;    /* 0 = none; else: run [0,split_pc) on all rows, compact survivors, then run
+                             the whole program densely on survivors (selective-filter split) */
+    uint32_t scratch_bytes; /* per-row scratch for materialised strings */
+} tplx_stage_header;
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TPLX_IR_H */

@@ -1,0 +1,214 @@
+"""CPU ORACLE — Python side. TEST INFRASTRUCTURE ONLY.
+
+ctypes wrapper over oracle/liboracle.so (tplx_oracle.c / workloads.c) plus a tiny pure-CPython
+row evaluator used to cross-check the UDF front end on inputs where Tuplex and CPython agree.
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module; nothing under tuplex_b200/ does.
+
+Reference citations live in tplx_oracle.c. Parity pinning: oracle/README.md.
+"""
+from __future__ import annotations
+
+import ctypes as ct
+import os
+import struct
+import subprocess
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "liboracle.so")
+MAX_COLS, MAX_ACCS = 64, 16
+T_I64, T_F64, T_BOOL, T_STR = 0, 1, 2, 3
+
+
+class OCol(ct.Structure):
+    _fields_ = [("type", ct.c_uint8), ("pad", ct.c_uint8 * 7), ("data", ct.c_void_p), ("offsets", ct.c_void_p),
+                ("data_bytes", ct.c_uint64)]
+
+
+class OExc(ct.Structure):
+    _fields_ = [("row", ct.c_int64), ("row_no", ct.c_int64), ("code", ct.c_int64), ("op_id", ct.c_int64)]
+
+
+class OResult(ct.Structure):
+    _fields_ = [("n_out", ct.c_uint64), ("n_exc", ct.c_uint64), ("n_accs", ct.c_uint64), ("n_cols", ct.c_uint64),
+                ("col_types", ct.c_uint8 * MAX_COLS),
+                ("fixed", ct.c_void_p * MAX_COLS), ("offsets", ct.c_void_p * MAX_COLS), ("bytes", ct.c_void_p * MAX_COLS),
+                ("bytes_len", ct.c_uint64 * MAX_COLS), ("bytes_cap", ct.c_uint64 * MAX_COLS),
+                ("exc", ct.c_void_p), ("exc_cap", ct.c_uint64), ("out_cap", ct.c_uint64),
+                ("acc_seq", ct.c_int64 * MAX_ACCS), ("acc_tree", ct.c_int64 * MAX_ACCS)]
+
+
+_lib = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE], stdout=subprocess.DEVNULL)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB):
+            build()
+        L = ct.CDLL(_LIB)
+        L.tplx_oracle_run.argtypes = [ct.c_void_p, ct.c_uint64, ct.POINTER(OCol), ct.c_uint64, ct.c_int64, ct.c_uint32,
+                                      ct.c_uint32, ct.c_uint32, ct.POINTER(OResult)]
+        L.tplx_oracle_run.restype = ct.c_int
+        L.tplx_oracle_free.argtypes = [ct.POINTER(OResult)]
+        L.tplx_oracle_to_partitions.argtypes = [ct.POINTER(OCol), ct.c_uint32, ct.c_uint64, ct.c_uint64, ct.c_void_p,
+                                                ct.POINTER(ct.c_uint64), ct.c_uint32, ct.POINTER(ct.c_uint32)]
+        L.tplx_oracle_to_partitions.restype = ct.c_uint64
+        L.tplx_oracle_exception_partition.argtypes = [ct.POINTER(OCol), ct.c_uint32, ct.c_void_p, ct.c_uint64, ct.c_void_p]
+        L.tplx_oracle_exception_partition.restype = ct.c_uint64
+        L.tplx_oracle_q6.argtypes = [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_uint64, ct.c_uint64, ct.c_int]
+        L.tplx_oracle_q6.restype = ct.c_double
+        L.tplx_oracle_c1.argtypes = [ct.c_void_p, ct.c_uint64, ct.c_void_p, ct.c_uint64, ct.c_int]
+        L.tplx_oracle_c1.restype = ct.c_uint64
+        L.tplx_o_atoi64.argtypes = [ct.c_char_p, ct.c_int64, ct.POINTER(ct.c_int64)]
+        L.tplx_o_atoi64.restype = ct.c_int32
+        L.tplx_o_floordiv.argtypes = [ct.c_int64, ct.c_int64]
+        L.tplx_o_floordiv.restype = ct.c_int64
+        L.tplx_o_floormod.argtypes = [ct.c_int64, ct.c_int64]
+        L.tplx_o_floormod.restype = ct.c_int64
+        _lib = L
+    return _lib
+
+
+def _ocols(cols):
+    """cols: sequence of objects with .type, .data (np array), .offsets (np array or None)."""
+    arr = (OCol * max(len(cols), 1))()
+    keep = []
+    for i, c in enumerate(cols):
+        d = np.ascontiguousarray(c.data)
+        keep.append(d)
+        arr[i].type = c.type
+        arr[i].data = d.ctypes.data
+        if c.type == T_STR:
+            o = np.ascontiguousarray(c.offsets, dtype=np.uint32)
+            keep.append(o)
+            arr[i].offsets = o.ctypes.data
+            arr[i].data_bytes = int(o[-1]) if len(o) else 0
+        else:
+            arr[i].data_bytes = d.nbytes
+    return arr, keep
+
+
+class OracleResult:
+    def __init__(self):
+        self.n_out = 0
+        self.columns: List[Tuple[int, np.ndarray, Optional[np.ndarray]]] = []  # (type, data, offsets)
+        self.exceptions = np.zeros(0, dtype=[("row", "<i8"), ("row_no", "<i8"), ("code", "<i8"), ("op_id", "<i8")])
+        self.acc_seq: List[int] = []
+        self.acc_tree: List[int] = []
+
+    def values(self, c: int) -> list:
+        t, data, offs = self.columns[c]
+        if t == T_STR:
+            raw = data.tobytes()
+            return [raw[offs[i]:offs[i + 1]].decode("utf-8") for i in range(self.n_out)]
+        if t == T_F64:
+            return data.view(np.float64).tolist()
+        if t == T_BOOL:
+            return [bool(v) for v in data.tolist()]
+        return data.tolist()
+
+
+def run_program(program, cols, n_rows: int, first_row_no: int = 0, tile_R: int = 16, tile_NT: int = 256,
+                fin_NT: int = 1024) -> OracleResult:
+    """Run a stage descriptor (tuplex_b200.ir.Program or its serialized bytes) over host columns."""
+    blob = program if isinstance(program, (bytes, bytearray)) else program.serialize()
+    buf = ct.create_string_buffer(bytes(blob), len(blob))
+    arr, keep = _ocols(cols)
+    res = OResult()
+    rc = lib().tplx_oracle_run(buf, len(blob), arr, n_rows, first_row_no, tile_R, tile_NT, fin_NT, ct.byref(res))
+    if rc != 0:
+        raise RuntimeError("oracle rejected the stage descriptor")
+    out = OracleResult()
+    out.n_out = int(res.n_out)
+    n = out.n_out
+    is_agg = res.n_accs > 0 and res.n_cols == 0
+    if not is_agg:
+        for c in range(res.n_cols):
+            t = res.col_types[c]
+            if t == T_STR:
+                offs = np.ctypeslib.as_array(ct.cast(res.offsets[c], ct.POINTER(ct.c_uint32)), shape=(n + 1,)).copy()
+                nb = int(res.bytes_len[c])
+                data = np.ctypeslib.as_array(ct.cast(res.bytes[c], ct.POINTER(ct.c_uint8)), shape=(nb,)).copy() if nb else np.zeros(0, np.uint8)
+                out.columns.append((t, data, offs))
+            else:
+                data = np.ctypeslib.as_array(ct.cast(res.fixed[c], ct.POINTER(ct.c_int64)), shape=(n,)).copy() if n else np.zeros(0, np.int64)
+                out.columns.append((t, data, None))
+    ne = int(res.n_exc)
+    if ne:
+        raw = ct.string_at(res.exc, ne * 32)
+        out.exceptions = np.frombuffer(raw, dtype=out.exceptions.dtype).copy()
+    out.acc_seq = [res.acc_seq[k] & ((1 << 64) - 1) for k in range(res.n_accs)]
+    out.acc_tree = [res.acc_tree[k] & ((1 << 64) - 1) for k in range(res.n_accs)]
+    lib().tplx_oracle_free(ct.byref(res))
+    return out
+
+
+def to_partitions(cols, n_rows: int, partition_bytes: int = 32 << 20) -> List[bytes]:
+    arr, keep = _ocols(cols)
+    np_ = ct.c_uint32()
+    total = lib().tplx_oracle_to_partitions(arr, len(cols), n_rows, partition_bytes, None, None, 0, ct.byref(np_))
+    buf = np.zeros(max(total, 8), dtype=np.uint8)
+    offs = (ct.c_uint64 * (np_.value + 1))()
+    lib().tplx_oracle_to_partitions(arr, len(cols), n_rows, partition_bytes, buf.ctypes.data, offs, np_.value, ct.byref(np_))
+    raw = buf.tobytes()
+    return [raw[offs[p]:offs[p + 1]] for p in range(np_.value)]
+
+
+def exception_partition(in_cols, exc: np.ndarray) -> bytes:
+    arr, keep = _ocols(in_cols)
+    e = np.ascontiguousarray(exc)
+    total = lib().tplx_oracle_exception_partition(arr, len(in_cols), e.ctypes.data, len(e), None)
+    buf = np.zeros(total, dtype=np.uint8)
+    lib().tplx_oracle_exception_partition(arr, len(in_cols), e.ctypes.data, len(e), buf.ctypes.data)
+    return buf.tobytes()
+
+
+def q6(qty: np.ndarray, price: np.ndarray, disc: np.ndarray, ship: np.ndarray, part_rows: int = 0, threads: int = 1) -> float:
+    qty, price, disc, ship = (np.ascontiguousarray(a) for a in (qty, price, disc, ship))
+    return lib().tplx_oracle_q6(qty.ctypes.data, price.ctypes.data, disc.ctypes.data, ship.ctypes.data, len(qty), part_rows, threads)
+
+
+def c1(x: np.ndarray, part_rows: int = 0, threads: int = 1) -> np.ndarray:
+    x = np.ascontiguousarray(x, dtype=np.int64)
+    out = np.empty(len(x), dtype=np.int64)
+    n = lib().tplx_oracle_c1(x.ctypes.data, len(x), out.ctypes.data, part_rows, threads)
+    return out[:n]
+
+
+def atoi64(s: str):
+    """int(str) exactly as the reference parses it; returns (ok, value)."""
+    b = s.encode()
+    v = ct.c_int64()
+    rc = lib().tplx_o_atoi64(b, len(b), ct.byref(v))
+    return rc == 0, v.value
+
+
+# ---- pure CPython evaluation of a pipeline (small cases only) -----------------------------------------
+def cpython_pipeline(rows: Sequence, ops: Sequence[Tuple[str, object]]):
+    """Evaluate [('map', f), ('filter', f), ...] row by row in CPython. Rows whose UDF raises are
+    returned separately as (index, exception type name). Used to cross-check the front end on inputs
+    where the reference's semantics and CPython's coincide."""
+    out, bad = [], []
+    for i, r in enumerate(rows):
+        try:
+            keep = True
+            for kind, f in ops:
+                if kind == "map":
+                    r = f(r)
+                elif kind == "filter":
+                    if not f(r):
+                        keep = False
+                        break
+            if keep:
+                out.append(r)
+        except Exception as e:  # noqa: BLE001
+            bad.append((i, type(e).__name__))
+    return out, bad

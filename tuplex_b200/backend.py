@@ -1,0 +1,390 @@
+"""ctypes binding of libtplx_gpu.so (include/tplx_gpu.h) + host column blocks.
+
+This is the host-side mirror of the reference's backend plug-in point
+(IBackend::execute, tuplex/core/include/ee/IBackend.h:29-46; selected by `tuplex.backend`,
+tuplex/core/src/Context.cc:56-83). There is deliberately no CPU implementation behind it: if the CUDA
+library is missing or no device is visible every call raises GpuBackendError.
+"""
+from __future__ import annotations
+
+import ctypes as ct
+import os
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import ir
+from .ir import T_BOOL, T_F64, T_I64, T_STR
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libtplx_gpu.so")
+MAX_COLS = ir.C["TPLX_MAX_COLS"]
+
+
+class GpuBackendError(RuntimeError):
+    pass
+
+
+class CColumn(ct.Structure):
+    _fields_ = [("type", ct.c_uint8), ("pad", ct.c_uint8 * 7), ("data", ct.c_void_p), ("offsets", ct.c_void_p),
+                ("data_bytes", ct.c_uint64)]
+
+
+class CExceptionRec(ct.Structure):
+    _fields_ = [("row", ct.c_int64), ("row_no", ct.c_int64), ("code", ct.c_int64), ("op_id", ct.c_int64)]
+
+
+class CResultInfo(ct.Structure):
+    _fields_ = [("n_in_rows", ct.c_uint64), ("n_out_rows", ct.c_uint64), ("n_exceptions", ct.c_uint64),
+                ("out_str_bytes", ct.c_uint64 * MAX_COLS), ("kernel_ms", ct.c_double), ("total_ms", ct.c_double),
+                ("kernel_launches", ct.c_uint32), ("pad", ct.c_uint32)]
+
+
+EXC_DTYPE = np.dtype([("row", "<i8"), ("row_no", "<i8"), ("code", "<i8"), ("op_id", "<i8")])
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library; fails loudly (no fallback) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise GpuBackendError(f"{_LIB_PATH} not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                              "the GPU backend has no CPU fallback")
+    L = ct.CDLL(_LIB_PATH)
+    vp, i32, u32, u64, i64 = ct.c_void_p, ct.c_int32, ct.c_uint32, ct.c_uint64, ct.c_int64
+    P = ct.POINTER
+    sig = {
+        "tplx_gpu_init": ([P(i32), i32], i32),
+        "tplx_gpu_device_count": ([], i32),
+        "tplx_gpu_shutdown": ([], i32),
+        "tplx_gpu_last_error": ([], ct.c_char_p),
+        "tplx_gpu_device_info": ([i32, ct.c_char_p, i32, P(i32), P(u64)], i32),
+        "tplx_gpu_stage_create": ([vp, u64, P(vp)], i32),
+        "tplx_gpu_stage_destroy": ([vp], i32),
+        "tplx_gpu_block_upload": ([i32, P(CColumn), u32, u64, P(vp)], i32),
+        "tplx_gpu_block_wrap_device": ([i32, P(CColumn), u32, u64, P(vp)], i32),
+        "tplx_gpu_block_from_partitions": ([i32, P(vp), P(u64), u32, P(ct.c_uint8), u32, P(vp)], i32),
+        "tplx_gpu_block_rows": ([vp, P(u64)], i32),
+        "tplx_gpu_block_free": ([vp], i32),
+        "tplx_gpu_stage_run": ([vp, vp, i64, P(vp)], i32),
+        "tplx_gpu_stage_run_host": ([vp, i32, P(CColumn), u32, u64, i64, P(vp)], i32),
+        "tplx_gpu_result_info": ([vp, P(CResultInfo)], i32),
+        "tplx_gpu_result_fetch_column": ([vp, u32, vp, vp], i32),
+        "tplx_gpu_result_device_column": ([vp, u32, P(vp), P(vp)], i32),
+        "tplx_gpu_result_fetch_exceptions": ([vp, vp], i32),
+        "tplx_gpu_result_fetch_aggregate": ([vp, P(i64)], i32),
+        "tplx_gpu_result_partitions": ([vp, u64, vp, u64, P(u64), P(u64), u32, P(u32)], i32),
+        "tplx_gpu_result_exception_partition": ([vp, vp, u64, P(u64)], i32),
+        "tplx_gpu_result_free": ([vp], i32),
+        "tplx_gpu_stage_hash_reserve": ([vp, i32, u64], i32),
+        "tplx_gpu_stage_hash_finish": ([vp, i32, P(vp)], i32),
+        "tplx_gpu_stage_hash_export_raw": ([vp, i32, P(vp)], i32),
+        "tplx_gpu_stage_hash_merge": ([vp, vp], i32),
+        "tplx_gpu_stage_hash_reset": ([vp, i32], i32),
+    }
+    for name, (argtypes, restype) in sig.items():
+        fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
+        fn.argtypes = argtypes
+        fn.restype = restype
+    L._declared = sorted(sig)
+    _lib = L
+    return L
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().tplx_gpu_last_error().decode("utf-8", "replace")
+        raise GpuBackendError(f"{what} failed ({rc}): {msg}")
+
+
+_initialised: set = set()
+
+
+def init(devices: Optional[Sequence[int]] = None):
+    L = lib()
+    devs = list(devices) if devices else [0]
+    if set(devs) <= _initialised:
+        return
+    arr = (ct.c_int32 * len(devs))(*devs)
+    _check(L.tplx_gpu_init(arr, len(devs)), "tplx_gpu_init")
+    _initialised.update(devs)
+
+
+def device_count() -> int:
+    return lib().tplx_gpu_device_count()
+
+
+# ------------------------------------------------------------------------------------------------
+# host column blocks
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class Column:
+    """One column of a column block on the host. Fixed width: `data` is an 8-byte numpy array
+    (int64 / float64; bool stored as int64 0/1). Strings: `data` = uint8 bytes, `offsets` = uint32[n+1]."""
+    type: int
+    data: np.ndarray
+    offsets: Optional[np.ndarray] = None
+
+    def __len__(self):
+        return len(self.offsets) - 1 if self.type == T_STR else len(self.data)
+
+    @staticmethod
+    def from_values(values: Sequence, t: int) -> "Column":
+        if t == T_STR:
+            enc = [v.encode("utf-8") for v in values]
+            lens = np.fromiter((len(b) for b in enc), dtype=np.int64, count=len(enc))
+            offsets = np.zeros(len(enc) + 1, dtype=np.uint32)
+            np.cumsum(lens, out=offsets[1:])
+            if lens.sum() > 0xFFFFFFFF:
+                raise GpuBackendError("string column exceeds 4 GiB; use smaller blocks")
+            data = np.frombuffer(b"".join(enc), dtype=np.uint8).copy() if enc else np.zeros(0, np.uint8)
+            return Column(T_STR, data, offsets)
+        if t == T_F64:
+            return Column(T_F64, np.asarray(values, dtype=np.float64))
+        return Column(t, np.asarray(values, dtype=np.int64))
+
+    def to_values(self) -> list:
+        if self.type == T_STR:
+            raw = self.data.tobytes()
+            o = self.offsets
+            return [raw[o[i]:o[i + 1]].decode("utf-8") for i in range(len(o) - 1)]
+        if self.type == T_BOOL:
+            return [bool(v) for v in self.data.tolist()]
+        return self.data.tolist()
+
+    def slice(self, lo: int, hi: int) -> "Column":
+        if self.type == T_STR:
+            o = self.offsets[lo:hi + 1]
+            return Column(T_STR, self.data[int(o[0]):int(o[-1])], (o - o[0]).astype(np.uint32))
+        return Column(self.type, self.data[lo:hi])
+
+    def take(self, idx: np.ndarray) -> "Column":
+        if self.type == T_STR:
+            vals = self.to_values()
+            return Column.from_values([vals[i] for i in idx.tolist()], T_STR)
+        return Column(self.type, self.data[idx])
+
+    def nbytes(self) -> int:
+        return int(self.data.nbytes + (self.offsets.nbytes if self.offsets is not None else 0))
+
+
+def _ccols(cols: Sequence[Column]):
+    arr = (CColumn * max(len(cols), 1))()
+    keep = []
+    for i, c in enumerate(cols):
+        d = np.ascontiguousarray(c.data)
+        keep.append(d)
+        arr[i].type = c.type
+        arr[i].data = d.ctypes.data
+        if c.type == T_STR:
+            o = np.ascontiguousarray(c.offsets, dtype=np.uint32)
+            keep.append(o)
+            arr[i].offsets = o.ctypes.data
+            arr[i].data_bytes = int(o[-1]) if len(o) else 0
+        else:
+            arr[i].offsets = None
+            arr[i].data_bytes = d.nbytes
+    return arr, keep
+
+
+class Stage:
+    """Device-side stage handle (replaces TransformStage + its JIT-compiled functor)."""
+
+    def __init__(self, program: ir.Program):
+        self.program = program
+        blob = program.serialize()
+        self._h = ct.c_void_p()
+        buf = ct.create_string_buffer(blob, len(blob))
+        _check(lib().tplx_gpu_stage_create(buf, len(blob), ct.byref(self._h)), "tplx_gpu_stage_create")
+
+    def close(self):
+        if self._h:
+            lib().tplx_gpu_stage_destroy(self._h)
+            self._h = ct.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- blocks --
+    def upload(self, device: int, cols: Sequence[Column], n_rows: int) -> "Block":
+        return Block.upload(device, cols, n_rows)
+
+    def run(self, block: "Block", first_row_no: int = 0) -> "Result":
+        h = ct.c_void_p()
+        _check(lib().tplx_gpu_stage_run(self._h, block._h, first_row_no, ct.byref(h)), "tplx_gpu_stage_run")
+        return Result(h, self, block)
+
+    def run_host(self, device: int, cols: Sequence[Column], n_rows: int, first_row_no: int = 0) -> "Result":
+        arr, keep = _ccols(cols)
+        h = ct.c_void_p()
+        _check(lib().tplx_gpu_stage_run_host(self._h, device, arr, len(cols), n_rows, first_row_no, ct.byref(h)),
+               "tplx_gpu_stage_run_host")
+        r = Result(h, self, None)
+        r._keep = keep
+        return r
+
+    def hash_reserve(self, device: int, expected_keys: int):
+        _check(lib().tplx_gpu_stage_hash_reserve(self._h, device, expected_keys), "tplx_gpu_stage_hash_reserve")
+
+    def hash_finish(self, device: int, raw: bool = False) -> "Result":
+        h = ct.c_void_p()
+        fn = lib().tplx_gpu_stage_hash_export_raw if raw else lib().tplx_gpu_stage_hash_finish
+        _check(fn(self._h, device, ct.byref(h)), "tplx_gpu_stage_hash_finish")
+        return Result(h, self, None, hash_result=True)
+
+    def hash_merge(self, packed: "Block"):
+        _check(lib().tplx_gpu_stage_hash_merge(self._h, packed._h), "tplx_gpu_stage_hash_merge")
+
+    def hash_reset(self, device: int):
+        _check(lib().tplx_gpu_stage_hash_reset(self._h, device), "tplx_gpu_stage_hash_reset")
+
+
+class Block:
+    def __init__(self, h, n_rows, device, keep=None):
+        self._h = h
+        self.n_rows = n_rows
+        self.device = device
+        self._keep = keep
+
+    @staticmethod
+    def upload(device: int, cols: Sequence[Column], n_rows: int) -> "Block":
+        init([device])
+        arr, keep = _ccols(cols)
+        h = ct.c_void_p()
+        _check(lib().tplx_gpu_block_upload(device, arr, len(cols), n_rows, ct.byref(h)), "tplx_gpu_block_upload")
+        return Block(h, n_rows, device, keep)
+
+    @staticmethod
+    def wrap_device(device: int, ptr_cols: Sequence[tuple], n_rows: int) -> "Block":
+        """ptr_cols: (type, data_ptr, offsets_ptr or 0, data_bytes) with device addresses."""
+        init([device])
+        arr = (CColumn * max(len(ptr_cols), 1))()
+        for i, (t, dp, op, nb) in enumerate(ptr_cols):
+            arr[i].type = t
+            arr[i].data = dp
+            arr[i].offsets = op or None
+            arr[i].data_bytes = nb
+        h = ct.c_void_p()
+        _check(lib().tplx_gpu_block_wrap_device(device, arr, len(ptr_cols), n_rows, ct.byref(h)), "tplx_gpu_block_wrap_device")
+        return Block(h, n_rows, device)
+
+    @staticmethod
+    def from_partitions(device: int, partitions: Sequence[bytes], col_types: Sequence[int]) -> "Block":
+        init([device])
+        n = len(partitions)
+        bufs = [np.frombuffer(p, dtype=np.uint8) for p in partitions]
+        ptrs = (ct.c_void_p * max(n, 1))(*[b.ctypes.data for b in bufs])
+        sizes = (ct.c_uint64 * max(n, 1))(*[len(p) for p in partitions])
+        types = (ct.c_uint8 * len(col_types))(*col_types)
+        h = ct.c_void_p()
+        _check(lib().tplx_gpu_block_from_partitions(device, ptrs, sizes, n, types, len(col_types), ct.byref(h)),
+               "tplx_gpu_block_from_partitions")
+        nr = ct.c_uint64()
+        _check(lib().tplx_gpu_block_rows(h, ct.byref(nr)), "tplx_gpu_block_rows")
+        return Block(h, nr.value, device)
+
+    def free(self):
+        if self._h:
+            lib().tplx_gpu_block_free(self._h)
+            self._h = ct.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Result:
+    def __init__(self, h, stage: Stage, block: Optional[Block], hash_result: bool = False):
+        self._h = h
+        self.stage = stage
+        self.block = block  # keep the input alive for exception gather
+        self._info = None
+        self.hash_result = hash_result
+
+    @property
+    def info(self) -> CResultInfo:
+        if self._info is None:
+            inf = CResultInfo()
+            _check(lib().tplx_gpu_result_info(self._h, ct.byref(inf)), "tplx_gpu_result_info")
+            self._info = inf
+        return self._info
+
+    def out_types(self) -> List[int]:
+        p = self.stage.program
+        if self.hash_result:
+            f = {ir.C["TPLX_ACC_SUM_F64"], ir.C["TPLX_ACC_MIN_F64"], ir.C["TPLX_ACC_MAX_F64"]}
+            return [t for _, t in p.out_cols] + [T_F64 if a.kind in f else T_I64 for a in p.accs]
+        return [t for _, t in p.out_cols]
+
+    def column(self, c: int) -> Column:
+        t = self.out_types()[c]
+        n = int(self.info.n_out_rows)
+        if t == T_STR:
+            nb = int(self.info.out_str_bytes[c])
+            data = np.empty(max(nb, 1), dtype=np.uint8)
+            offsets = np.empty(n + 1, dtype=np.uint32)
+            _check(lib().tplx_gpu_result_fetch_column(self._h, c, data.ctypes.data, offsets.ctypes.data), "result_fetch_column")
+            return Column(T_STR, data[:nb], offsets)
+        data = np.empty(n, dtype=np.float64 if t == T_F64 else np.int64)
+        if n:
+            _check(lib().tplx_gpu_result_fetch_column(self._h, c, data.ctypes.data, None), "result_fetch_column")
+        return Column(t, data)
+
+    def columns(self) -> List[Column]:
+        return [self.column(c) for c in range(len(self.out_types()))]
+
+    def device_column(self, c: int):
+        d, o = ct.c_void_p(), ct.c_void_p()
+        _check(lib().tplx_gpu_result_device_column(self._h, c, ct.byref(d), ct.byref(o)), "result_device_column")
+        return d.value or 0, o.value or 0
+
+    def exceptions(self) -> np.ndarray:
+        n = int(self.info.n_exceptions)
+        recs = np.zeros(n, dtype=EXC_DTYPE)
+        if n:
+            _check(lib().tplx_gpu_result_fetch_exceptions(self._h, recs.ctypes.data), "result_fetch_exceptions")
+        return recs
+
+    def aggregate_bits(self) -> List[int]:
+        n = len(self.stage.program.accs)
+        arr = (ct.c_int64 * n)()
+        _check(lib().tplx_gpu_result_fetch_aggregate(self._h, arr), "result_fetch_aggregate")
+        return [v & ((1 << 64) - 1) for v in arr]
+
+    def partitions(self, partition_bytes: int = 32 << 20) -> List[bytes]:
+        need, nparts = ct.c_uint64(), ct.c_uint32()
+        _check(lib().tplx_gpu_result_partitions(self._h, partition_bytes, None, 0, ct.byref(need), None, 0, ct.byref(nparts)),
+               "result_partitions(size)")
+        buf = np.empty(max(need.value, 8), dtype=np.uint8)
+        offs = (ct.c_uint64 * (nparts.value + 1))()
+        _check(lib().tplx_gpu_result_partitions(self._h, partition_bytes, buf.ctypes.data, buf.nbytes, ct.byref(need), offs,
+                                                nparts.value, ct.byref(nparts)), "result_partitions")
+        raw = buf.tobytes()
+        return [raw[offs[p]:offs[p + 1]] for p in range(nparts.value)]
+
+    def exception_partition(self) -> bytes:
+        need = ct.c_uint64()
+        _check(lib().tplx_gpu_result_exception_partition(self._h, None, 0, ct.byref(need)), "result_exception_partition(size)")
+        buf = np.empty(need.value, dtype=np.uint8)
+        _check(lib().tplx_gpu_result_exception_partition(self._h, buf.ctypes.data, buf.nbytes, ct.byref(need)),
+               "result_exception_partition")
+        return buf.tobytes()
+
+    def free(self):
+        if self._h:
+            lib().tplx_gpu_result_free(self._h)
+            self._h = ct.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

@@ -1,0 +1,241 @@
+"""Context — mirror of tuplex.Context for the hot path
+(tuplex/python/tuplex/context.py:50-365; C++ side tuplex/python/src/PythonContext.cc:126-209,823-1023).
+
+parallelize(): majority-type inference per column, rows that do not fit become fallback rows that run on
+the CPython path (PythonContext::parallelize / inferType, PythonContext.cc:823,1023; fallback rows :178-204).
+csv(): host-side parse into column blocks (CSV parsing stays on the host).
+"""
+from __future__ import annotations
+
+import csv as _csv
+import glob
+from collections import Counter
+from typing import Any, Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import backend
+from .backend import Column
+from .dataset import DataSet, Source
+from .ir import T_BOOL, T_F64, T_I64, T_STR
+
+_DEFAULTS = {
+    # key names follow tuplex/core/src/ContextOptions.cc:182-300
+    "tuplex.backend": "gpu",
+    "tuplex.partitionSize": "32MB",
+    "tuplex.executorCount": "0",
+    "tuplex.normalcaseThreshold": "0.9",
+    "tuplex.optimizer.mergeExceptionsInOrder": "true",
+    "tuplex.gpu.devices": "0",
+    "tuplex.gpu.blockRows": str(16 << 20),
+    "tuplex.webui.enable": "false",
+}
+
+
+def _kind(v) -> Optional[int]:
+    if isinstance(v, bool):
+        return T_BOOL
+    if isinstance(v, int):
+        return T_I64 if -(1 << 63) <= v < (1 << 63) else None
+    if isinstance(v, float):
+        return T_F64
+    if isinstance(v, str):
+        return T_STR
+    return None
+
+
+class Metrics:
+    """ctx.metrics (tuplex/python/tuplex/metrics.py; JobMetrics.h): counters of the GPU path."""
+
+    def __init__(self):
+        self.rows_in = self.rows_out = self.exceptions = 0
+        self.kernel_ms = self.total_ms = 0.0
+        self.kernel_launches = 0
+
+    def _add(self, info):
+        self.rows_in += int(info.n_in_rows)
+        self.rows_out += int(info.n_out_rows)
+        self.exceptions += int(info.n_exceptions)
+        self.kernel_ms += float(info.kernel_ms)
+        self.total_ms += float(info.total_ms)
+        self.kernel_launches += int(info.kernel_launches)
+
+    def as_dict(self):
+        return dict(self.__dict__)
+
+    def as_json(self):
+        import json
+        return json.dumps(self.as_dict())
+
+
+class Context:
+    def __init__(self, conf: Optional[Dict[str, Any]] = None, **kwargs):
+        self._options: Dict[str, str] = dict(_DEFAULTS)
+        for src in (conf or {}), kwargs:
+            for k, v in src.items():
+                k = k if k.startswith("tuplex.") else "tuplex." + k
+                self._options[k] = str(v).lower() if isinstance(v, bool) else str(v)
+        if self._options["tuplex.backend"] not in ("gpu",):
+            raise ValueError("this build provides the gpu backend only")
+        devs = [int(d) for d in str(self._options["tuplex.gpu.devices"]).replace(";", ",").split(",") if d != ""]
+        self._device = devs[0] if devs else 0
+        self._block_rows = int(self._options["tuplex.gpu.blockRows"])
+        self.metrics = Metrics()
+        self._messages: List[str] = []
+
+    def _log(self, msg: str):
+        self._messages.append(msg)
+
+    def options(self, nested=False):
+        return dict(self._options)
+
+    # ---- sources -----------------------------------------------------------------------------------
+    def parallelize(self, value_list, columns=None, schema=None) -> DataSet:
+        if not isinstance(value_list, (list, tuple, range)):
+            raise TypeError("data must be given as a list of objects")
+        value_list = list(value_list)
+        src = self._source_from_rows(value_list, list(columns) if columns else None, infer=True)
+        return DataSet(self, src)
+
+    def _dataset_from_rows(self, rows, names) -> DataSet:
+        return DataSet(self, self._source_from_rows(rows, names))
+
+    def _source_from_rows(self, rows: Sequence, names: Optional[List[Optional[str]]], infer: bool = True) -> Source:
+        n = len(rows)
+        # row shape: majority of (is tuple, arity)
+        shapes = Counter((len(r) if isinstance(r, tuple) else -1) for r in rows)
+        arity = shapes.most_common(1)[0][0] if shapes else -1
+        ncols = 1 if arity == -1 else arity
+        if names is not None and len(names) != ncols:
+            if ncols == 1 and len(names) > 1:
+                raise ValueError("number of column names does not match the data")
+            names = (list(names) + [None] * ncols)[:ncols]
+        names = list(names) if names is not None else [None] * ncols
+        # majority type per column (PythonContext::inferType)
+        col_types = []
+        for c in range(ncols):
+            cnt = Counter()
+            for r in rows:
+                if (len(r) if isinstance(r, tuple) else -1) != arity:
+                    continue
+                v = r[c] if arity != -1 else r
+                cnt[_kind(v)] += 1
+            t = next((k for k, _ in cnt.most_common() if k is not None), None)
+            if t is None:
+                t = T_I64
+            # ints and bools mixed with floats: keep the majority, the others become fallback rows
+            col_types.append(t)
+        normal_vals: List[list] = [[] for _ in range(ncols)]
+        orig: List[int] = []
+        fallback = []
+        for i, r in enumerate(rows):
+            ok = (len(r) if isinstance(r, tuple) else -1) == arity
+            if ok:
+                vals = r if arity != -1 else (r,)
+                ok = all(_kind(v) == t for v, t in zip(vals, col_types))
+            if ok:
+                for c, v in enumerate(vals):
+                    normal_vals[c].append(v)
+                orig.append(i)
+            else:
+                fallback.append((i, r))
+        cols = [Column.from_values(normal_vals[c], col_types[c]) for c in range(ncols)]
+        oi = None if not fallback else np.asarray(orig, dtype=np.int64)
+        return Source(cols, names, len(orig), oi, fallback, n)
+
+    def csv(self, pattern, columns=None, header=None, delimiter=None, quotechar='"', null_values=[''], type_hints={}) -> DataSet:
+        files = sorted(f for p in pattern.split(",") for f in (glob.glob(p) or [p]))
+        rows: List[List[str]] = []
+        names = None
+        for fn in files:
+            with open(fn, newline="") as fp:
+                sample = fp.read(65536)
+                fp.seek(0)
+                delim = delimiter or (_csv.Sniffer().sniff(sample, delimiters=",;|\t").delimiter if sample else ",")
+                rd = _csv.reader(fp, delimiter=delim, quotechar=quotechar)
+                data = list(rd)
+            if not data:
+                continue
+            if delim == "|" and data and data[0] and data[0][-1] == "":
+                data = [r[:-1] if r and r[-1] == "" else r for r in data]  # dbgen trailing delimiter
+            has_header = header if header is not None else (columns is None and not _looks_numeric(data[0]))
+            if has_header:
+                if names is None:
+                    names = data[0]
+                data = data[1:]
+            rows.extend(data)
+        if columns is not None:
+            names = list(columns)
+        ncols = len(names) if names is not None else (len(rows[0]) if rows else 0)
+        names = names if names is not None else [None] * ncols
+        nulls = set(null_values or [])
+        # per-column normal-case type: majority over cells (CSVStatistic), hints win
+        types = []
+        for c in range(ncols):
+            if c in type_hints or (names[c] in type_hints):
+                h = type_hints.get(c, type_hints.get(names[c]))
+                types.append({int: T_I64, float: T_F64, str: T_STR, bool: T_BOOL}[h])
+                continue
+            cnt = Counter(_cell_kind(r[c]) for r in rows[:10000] if len(r) == ncols and r[c] not in nulls)
+            if not cnt:
+                types.append(T_STR)
+            elif cnt.get(T_STR, 0) > 0.1 * sum(cnt.values()):
+                types.append(T_STR)
+            elif cnt.get(T_F64, 0):
+                types.append(T_F64)
+            else:
+                types.append(T_I64)
+        normal: List[list] = [[] for _ in range(ncols)]
+        orig, fallback = [], []
+        for i, r in enumerate(rows):
+            vals = _parse_row(r, types, nulls) if len(r) == ncols else None
+            if vals is None:
+                fallback.append((i, tuple(_parse_cell_general(x, nulls) for x in r) if len(r) != 1 else _parse_cell_general(r[0], nulls)))
+            else:
+                for c, v in enumerate(vals):
+                    normal[c].append(v)
+                orig.append(i)
+        cols = [Column.from_values(normal[c], types[c]) for c in range(ncols)]
+        oi = None if not fallback else np.asarray(orig, dtype=np.int64)
+        return DataSet(self, Source(cols, list(names), len(orig), oi, fallback, len(rows)))
+
+
+def _looks_numeric(cells) -> bool:
+    return any(_cell_kind(c) in (T_I64, T_F64) for c in cells)
+
+
+def _cell_kind(s: str) -> int:
+    try:
+        int(s)
+        return T_I64
+    except ValueError:
+        pass
+    try:
+        float(s)
+        return T_F64
+    except ValueError:
+        return T_STR
+
+
+def _parse_row(r, types, nulls):
+    out = []
+    for s, t in zip(r, types):
+        if t == T_STR:
+            if s in nulls and s != "":
+                return None
+            out.append(s)
+            continue
+        if s in nulls:
+            return None
+        try:
+            out.append(int(s) if t == T_I64 else float(s) if t == T_F64 else {"true": True, "false": False}[s.lower()])
+        except (ValueError, KeyError):
+            return None
+    return out
+
+
+def _parse_cell_general(s, nulls):
+    if s in nulls:
+        return None
+    k = _cell_kind(s)
+    return int(s) if k == T_I64 else float(s) if k == T_F64 else s

@@ -1,0 +1,511 @@
+// kernels.cuh — stage kernels for sm_100a.
+//
+// K1  stage_rows_kernel   : fused map/filter/withColumn/project over a column block, stable
+//                           compaction (warp ballot bitmaps) + single-pass decoupled look-back scan
+//                           for output row / string byte / exception offsets. Replaces the JIT'd
+//                           block loop + processRow + writeRowToMemory
+//                           (reference tuplex/core/src/physical/TuplexSourceTaskBuilder.cc:104-215,
+//                            PipelineBuilder.cc:565-1025, core/include/physical/TransformTask.h:47-92).
+// K2  exception records are emitted by K1 itself (row, rowNo, code, opID); the original row bytes are
+//     gathered by rowfmt.cuh (IExceptionableTask.h:22-36).
+// K3  stage_agg_kernel + agg_finalize_kernel : fused filter -> g(x) -> fixed-tree reduction.
+//     Replaces addAggregate/combineAggregate/fetchAggregate
+//     (PipelineBuilder.cc:2525-2608, TransformTask.cc:218-299).
+#pragma once
+#include <stdint.h>
+#include "vm.cuh"
+#include "../../include/tplx_gpu.h"
+
+namespace tplx {
+
+constexpr int NT = 256;           // threads per CTA
+constexpr int MAX_SCAN = 32;      // look-back vector width: keep, exc, + string output columns
+constexpr int FIN_NT = 1024;      // finalize CTA width
+
+struct OutCol {
+    uint64_t *data;      // fixed-width values
+    uint32_t *offsets;   // string: n_out+1 offsets
+    uint8_t *bytes;      // string bytes
+    uint64_t cap_bytes;  // capacity of bytes
+    uint32_t slot;
+    uint32_t type;
+    int32_t strk;        // index among string output columns, -1 for fixed width
+    uint32_t stage_off;  // byte offset of this column's staging area in shared memory
+};
+
+struct AccP {
+    uint32_t kind;
+    uint32_t slot;
+    int64_t init;
+};
+
+struct KParams {
+    uint64_t n_rows;
+    int64_t first_row_no;
+    uint32_t n_instr, split_pc, n_slots, n_in, n_out, n_str_out, n_accs, R, n_tiles, scratch_per_thread;
+    uint32_t K;            // scan vector width = 2 + n_str_out
+    uint32_t smem_regs_off, smem_stage_off, smem_misc_off, smem_cols_off;
+    uint64_t cap_rows, cap_exc;
+    const tplx_instr *prog;
+    const uint8_t *cpool;
+    const int64_t *opids;
+    uint64_t *tile_state;   // n_tiles * (1 + 2K)
+    uint32_t *counters;     // [0] ticket, [1] overflow flags, [2] exception append counter (agg)
+    uint64_t *totals;       // K totals
+    tplx_exception_rec *exc;
+    uint8_t *scratch;
+    uint64_t *tile_partials;  // aggregate: n_tiles * n_accs
+    uint64_t *agg_out;        // aggregate: n_accs
+    ColIn in[TPLX_MAX_COLS];
+    OutCol out[TPLX_MAX_COLS];
+    AccP accs[TPLX_MAX_ACCS];
+};
+
+// ---- small helpers --------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_cg_u64(const uint64_t *p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_cg_u64(uint64_t *p, uint64_t v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
+// accumulate one value into an accumulator (identity handling by kind)
+__device__ __forceinline__ uint64_t acc_identity(uint32_t kind) {
+    switch (kind) {
+        case TPLX_ACC_SUM_I64: return 0;
+        case TPLX_ACC_SUM_F64: return 0;  // +0.0
+        case TPLX_ACC_MIN_I64: return 0x7FFFFFFFFFFFFFFFull;
+        case TPLX_ACC_MAX_I64: return 0x8000000000000000ull;
+        case TPLX_ACC_MIN_F64: return 0x7FF0000000000000ull;  // +inf
+        default: return 0xFFF0000000000000ull;               // -inf
+    }
+}
+__device__ __forceinline__ uint64_t acc_combine(uint32_t kind, uint64_t a, uint64_t b) {
+    switch (kind) {
+        case TPLX_ACC_SUM_I64: return a + b;
+        case TPLX_ACC_SUM_F64:
+            return (uint64_t)__double_as_longlong(
+                __dadd_rn(__longlong_as_double((long long)a), __longlong_as_double((long long)b)));
+        case TPLX_ACC_MIN_I64: return (int64_t)b < (int64_t)a ? b : a;
+        case TPLX_ACC_MAX_I64: return (int64_t)b > (int64_t)a ? b : a;
+        case TPLX_ACC_MIN_F64:
+            return __longlong_as_double((long long)b) < __longlong_as_double((long long)a) ? b : a;
+        default: return __longlong_as_double((long long)b) > __longlong_as_double((long long)a) ? b : a;
+    }
+}
+
+// rank of local row lr among set bits (exclusive)
+__device__ __forceinline__ uint32_t bit_rank(const uint32_t *bits, const uint32_t *wpre, uint32_t lr) {
+    return wpre[lr >> 5] + __popc(bits[lr >> 5] & ((1u << (lr & 31)) - 1u));
+}
+__device__ __forceinline__ bool bit_test(const uint32_t *bits, uint32_t lr) {
+    return (bits[lr >> 5] >> (lr & 31)) & 1u;
+}
+
+// =============================================================================================
+// K1: rows in -> rows out
+// =============================================================================================
+// Shared memory map (byte offsets from KParams): prog | cols | regs | staging | misc
+// misc: keep_bits[W] exc_bits[W] keep_pre[W+1] exc_pre[W+1] exc_stage[T] surv[T] (u16) scan scratch
+__global__ void __launch_bounds__(NT) stage_rows_kernel(const KParams *__restrict__ Pg) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const KParams &P = *Pg;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t R = P.R, T = R * NT, W = T / 32, K = P.K;
+
+    tplx_instr *s_prog = reinterpret_cast<tplx_instr *>(smem);
+    ColIn *s_cols = reinterpret_cast<ColIn *>(smem + P.smem_cols_off);
+    uint64_t *s_regs = reinterpret_cast<uint64_t *>(smem + P.smem_regs_off) + tid;
+    uint8_t *s_stage = smem + P.smem_stage_off;
+    uint32_t *keep_bits = reinterpret_cast<uint32_t *>(smem + P.smem_misc_off);
+    uint32_t *exc_bits = keep_bits + W;
+    uint32_t *keep_pre = exc_bits + W;
+    uint32_t *exc_pre = keep_pre + W + 1;
+    uint32_t *exc_stage = exc_pre + W + 1;
+    uint16_t *surv = reinterpret_cast<uint16_t *>(exc_stage + T);
+    uint64_t *s_vals = reinterpret_cast<uint64_t *>(surv + T + ((T & 3) ? 4 - (T & 3) : 0));  // K tile values
+    uint64_t *s_excl = s_vals + MAX_SCAN;                                                    // K exclusive prefixes
+    uint64_t *s_warp = s_excl + MAX_SCAN;                                                    // NT/32 scan scratch
+    uint32_t *s_ctl = reinterpret_cast<uint32_t *>(s_warp + NT / 32 + 1);                     // [0] tile, [1] n_surv
+
+    // one-time: program + column table into shared memory
+    for (uint32_t i = tid; i < P.n_instr * (sizeof(tplx_instr) / 16); i += NT)
+        reinterpret_cast<uint4 *>(s_prog)[i] = reinterpret_cast<const uint4 *>(P.prog)[i];
+    for (uint32_t i = tid; i < P.n_in * (sizeof(ColIn) / 8); i += NT)
+        reinterpret_cast<uint64_t *>(s_cols)[i] = reinterpret_cast<const uint64_t *>(P.in)[i];
+
+    VMThread t;
+    t.scr_cap = P.scratch_per_thread;
+    t.scratch = P.scratch + ((size_t)blockIdx.x * NT + tid) * (size_t)P.scratch_per_thread;
+
+    const uint32_t state_stride = 1 + 2 * K;
+
+    while (true) {
+        __syncthreads();
+        if (tid == 0) {
+            s_ctl[0] = atomicAdd(&P.counters[0], 1u);
+            s_ctl[1] = 0;
+        }
+        for (uint32_t i = tid; i < 2 * W; i += NT) keep_bits[i] = 0;  // keep_bits and exc_bits
+        __syncthreads();
+        const uint32_t tile = s_ctl[0];
+        if (tile >= P.n_tiles) break;
+        const uint64_t base = (uint64_t)tile * T;
+        t.scr_used = 0;
+
+        // ---- evaluate -----------------------------------------------------------------------
+        auto stage_row = [&](uint32_t lr) {
+            for (uint32_t c = 0; c < P.n_out; ++c) {
+                const OutCol &oc = P.out[c];
+                if (oc.strk >= 0) {
+                    uint64_t *st = reinterpret_cast<uint64_t *>(s_stage + oc.stage_off) + 2 * (size_t)lr;
+                    st[0] = s_regs[oc.slot * NT];
+                    st[1] = s_regs[(oc.slot + 1) * NT];
+                } else {
+                    reinterpret_cast<uint64_t *>(s_stage + oc.stage_off)[lr] = s_regs[oc.slot * NT];
+                }
+            }
+        };
+
+        if (P.split_pc == 0) {
+            for (uint32_t s = 0; s < R; ++s) {
+                const uint32_t lr = s * NT + tid;
+                const uint64_t row = base + lr;
+                t.alive = row < P.n_rows;
+                t.exc_code = 0;
+                VM<NT>::run(s_prog, 0, P.n_instr, s_regs, s_cols, row, P.cpool, t);
+                const bool exc = t.exc_code != 0;
+                const uint32_t kb = __ballot_sync(0xFFFFFFFFu, t.alive);
+                const uint32_t eb = __ballot_sync(0xFFFFFFFFu, exc);
+                if (lane == 0) { keep_bits[lr >> 5] = kb; exc_bits[lr >> 5] = eb; }
+                if (t.alive) stage_row(lr);
+                if (exc) exc_stage[lr] = t.exc_code | (t.exc_op << 16);
+            }
+        } else {
+            // phase 1: selective prefix on every row, collect survivors
+            for (uint32_t s = 0; s < R; ++s) {
+                const uint32_t lr = s * NT + tid;
+                const uint64_t row = base + lr;
+                t.alive = row < P.n_rows;
+                t.exc_code = 0;
+                VM<NT>::run(s_prog, 0, P.split_pc, s_regs, s_cols, row, P.cpool, t);
+                const bool exc = t.exc_code != 0;
+                const uint32_t sb = __ballot_sync(0xFFFFFFFFu, t.alive);
+                const uint32_t eb = __ballot_sync(0xFFFFFFFFu, exc);
+                uint32_t wbase = 0;
+                if (lane == 0) {
+                    exc_bits[lr >> 5] = eb;
+                    if (sb) wbase = atomicAdd(&s_ctl[1], (uint32_t)__popc(sb));
+                }
+                wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+                if (t.alive) surv[wbase + __popc(sb & ((1u << lane) - 1u))] = (uint16_t)lr;
+                if (exc) exc_stage[lr] = t.exc_code | (t.exc_op << 16);
+            }
+            __syncthreads();
+            // phase 2: whole program, densely, on survivors
+            const uint32_t n_surv = s_ctl[1];
+            t.scr_used = 0;
+            for (uint32_t i0 = 0; i0 < n_surv; i0 += NT) {
+                const uint32_t i = i0 + tid;
+                const bool valid = i < n_surv;
+                const uint32_t lr = valid ? surv[i] : 0;
+                t.alive = valid;
+                t.exc_code = 0;
+                VM<NT>::run(s_prog, 0, P.n_instr, s_regs, s_cols, base + lr, P.cpool, t);
+                if (t.alive) {
+                    atomicOr(&keep_bits[lr >> 5], 1u << (lr & 31));
+                    stage_row(lr);
+                }
+                if (t.exc_code != 0) {
+                    atomicOr(&exc_bits[lr >> 5], 1u << (lr & 31));
+                    exc_stage[lr] = t.exc_code | (t.exc_op << 16);
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- per-tile counts: word prefixes (warp 0), string byte totals ----------------------
+        if (warp == 0) {
+            uint32_t ck = 0, ce = 0;
+            for (uint32_t w0 = 0; w0 < W; w0 += 32) {
+                uint32_t w = w0 + lane;
+                uint32_t pk = w < W ? __popc(keep_bits[w]) : 0, pe = w < W ? __popc(exc_bits[w]) : 0;
+                uint32_t ik = pk, ie = pe;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    uint32_t a = __shfl_up_sync(0xFFFFFFFFu, ik, o), b = __shfl_up_sync(0xFFFFFFFFu, ie, o);
+                    if (lane >= (uint32_t)o) { ik += a; ie += b; }
+                }
+                if (w < W) { keep_pre[w] = ck + ik - pk; exc_pre[w] = ce + ie - pe; }
+                ck += __shfl_sync(0xFFFFFFFFu, ik, 31);
+                ce += __shfl_sync(0xFFFFFFFFu, ie, 31);
+            }
+            if (lane == 0) {
+                keep_pre[W] = ck;
+                exc_pre[W] = ce;
+                s_vals[0] = ck;
+                s_vals[1] = ce;
+            }
+        }
+        // string bytes per output column: thread owns local rows [tid*R, tid*R+R)
+        // (consecutive rows per thread so that one block scan yields in-order byte offsets)
+        for (uint32_t c = 0; c < P.n_out; ++c) {
+            const OutCol &oc = P.out[c];
+            if (oc.strk < 0) continue;
+            const uint64_t *st = reinterpret_cast<const uint64_t *>(s_stage + oc.stage_off);
+            uint32_t mine = 0;
+            for (uint32_t j = 0; j < R; ++j) {
+                uint32_t lr = tid * R + j;
+                if (bit_test(keep_bits, lr)) mine += (uint32_t)st[2 * (size_t)lr + 1];
+            }
+            uint32_t inc = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t a = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                if (lane >= (uint32_t)o) inc += a;
+            }
+            __syncthreads();  // s_warp reuse
+            if (lane == 31) s_warp[warp] = inc;
+            __syncthreads();
+            uint32_t wofs = 0, tot = 0;
+            for (uint32_t w = 0; w < NT / 32; ++w) {
+                uint32_t v = (uint32_t)s_warp[w];
+                if (w < warp) wofs += v;
+                tot += v;
+            }
+            // stash this thread's exclusive byte offset in the (now free) register file slot area:
+            // regs are dead after evaluation, reuse slot 0..n_str_out-1 of this thread
+            s_regs[(uint32_t)oc.strk * NT] = (uint64_t)(wofs + inc - mine);
+            if (tid == 0) s_vals[2 + oc.strk] = tot;
+        }
+        __syncthreads();
+
+        // ---- decoupled look-back over the K-vector (warp 0) -----------------------------------
+        if (warp == 0) {
+            uint64_t *my = P.tile_state + (size_t)tile * state_stride;
+            uint64_t myval = lane < K ? s_vals[lane] : 0;
+            if (lane < K) {
+                st_cg_u64(my + 1 + lane, myval);
+                if (tile == 0) st_cg_u64(my + 1 + K + lane, myval);
+            }
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) st_release_u32(reinterpret_cast<uint32_t *>(my), tile == 0 ? 2u : 1u);
+            uint64_t excl = 0;
+            if (tile > 0) {
+                int64_t p = (int64_t)tile - 1;
+                while (true) {
+                    const int64_t q = p - lane;
+                    uint32_t st = 2;
+                    const uint64_t *qs = nullptr;
+                    if (q >= 0) {
+                        qs = P.tile_state + (size_t)q * state_stride;
+                        do { st = ld_acquire_u32(reinterpret_cast<const uint32_t *>(qs)); } while (st == 0);
+                    }
+                    const uint32_t pm = __ballot_sync(0xFFFFFFFFu, st == 2);
+                    const uint32_t first = pm ? (uint32_t)(__ffs(pm) - 1) : 31u;
+                    const bool use = (lane <= first) && q >= 0;
+                    for (uint32_t k = 0; k < K; ++k) {
+                        uint64_t v = use ? ld_cg_u64(qs + 1 + (st == 2 ? K : 0) + k) : 0;
+                        v = warp_sum_u64(v);
+                        if (lane == k) excl += v;
+                    }
+                    if (pm) break;
+                    p -= 32;
+                }
+                if (lane < K) st_cg_u64(my + 1 + K + lane, excl + myval);
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) st_release_u32(reinterpret_cast<uint32_t *>(my), 2u);
+            }
+            if (lane < K) {
+                s_excl[lane] = excl;
+                if (tile == P.n_tiles - 1) P.totals[lane] = excl + myval;
+            }
+        }
+        __syncthreads();
+
+        // ---- write ----------------------------------------------------------------------------
+        const uint64_t pre_keep = s_excl[0], pre_exc = s_excl[1];
+        const uint32_t n_keep = (uint32_t)s_vals[0], n_exc = (uint32_t)s_vals[1];
+        const bool rows_fit = pre_keep + n_keep <= P.cap_rows;
+        if (!rows_fit && tid == 0) atomicOr(&P.counters[1], 1u);
+        if (n_keep && rows_fit) {
+            for (uint32_t c = 0; c < P.n_out; ++c) {
+                const OutCol &oc = P.out[c];
+                if (oc.strk < 0) {
+                    const uint64_t *st = reinterpret_cast<const uint64_t *>(s_stage + oc.stage_off);
+                    for (uint32_t lr = tid; lr < T; lr += NT)
+                        if (bit_test(keep_bits, lr)) oc.data[pre_keep + bit_rank(keep_bits, keep_pre, lr)] = st[lr];
+                } else {
+                    const uint64_t *st = reinterpret_cast<const uint64_t *>(s_stage + oc.stage_off);
+                    const uint64_t pre_b = s_excl[2 + oc.strk];
+                    const uint64_t tile_b = s_vals[2 + oc.strk];
+                    const bool fit = pre_b + tile_b <= oc.cap_bytes && pre_b + tile_b <= 0xFFFFFFFFull;
+                    if (!fit) {
+                        if (tid == 0) atomicOr(&P.counters[1], 2u);
+                        continue;
+                    }
+                    uint64_t off = pre_b + s_regs[(uint32_t)oc.strk * NT];
+                    for (uint32_t j = 0; j < R; ++j) {
+                        const uint32_t lr = tid * R + j;
+                        if (!bit_test(keep_bits, lr)) continue;
+                        StrV sv;
+                        sv.p = reinterpret_cast<const uint8_t *>(st[2 * (size_t)lr]);
+                        const uint64_t m = st[2 * (size_t)lr + 1];
+                        sv.len = (uint32_t)m;
+                        sv.flags = (uint32_t)(m >> 32);
+                        oc.offsets[pre_keep + bit_rank(keep_bits, keep_pre, lr)] = (uint32_t)off;
+                        uint8_t *o = oc.bytes + off;
+                        for (uint32_t i = 0; i < sv.len; ++i) o[i] = sch(sv, i);
+                        off += sv.len;
+                    }
+                    if (tile == P.n_tiles - 1 && tid == 0) oc.offsets[pre_keep + n_keep] = (uint32_t)(pre_b + tile_b);
+                }
+            }
+        } else if (tile == P.n_tiles - 1 && rows_fit && tid == 0) {
+            for (uint32_t c = 0; c < P.n_out; ++c)
+                if (P.out[c].strk >= 0) P.out[c].offsets[pre_keep] = (uint32_t)s_excl[2 + P.out[c].strk];
+        }
+        if (n_exc) {
+            if (pre_exc + n_exc <= P.cap_exc) {
+                for (uint32_t lr = tid; lr < T; lr += NT) {
+                    if (!bit_test(exc_bits, lr)) continue;
+                    const uint32_t ke = bit_rank(exc_bits, exc_pre, lr);
+                    const uint32_t kk = bit_rank(keep_bits, keep_pre, lr);
+                    tplx_exception_rec rec;
+                    rec.row = (int64_t)(base + lr);
+                    // _outputRowCounter semantics: rows written + exceptions so far (TransformTask.cc:764,885)
+                    rec.row_no = P.first_row_no + (int64_t)(pre_keep + pre_exc + kk + ke);
+                    const uint32_t es = exc_stage[lr];
+                    rec.code = es & 0xFFFF;
+                    rec.op_id = P.opids[es >> 16];
+                    P.exc[pre_exc + ke] = rec;
+                }
+            } else if (tid == 0) atomicOr(&P.counters[1], 4u);
+        }
+    }
+}
+
+// =============================================================================================
+// K3: rows in -> aggregate (fixed reduction tree; see DESIGN.md "reduction tree")
+//   thread t of a tile folds local rows t, t+NT, ... in order from the identity,
+//   warp tree via shfl_down 16,8,4,2,1, warps combined sequentially -> tile partial.
+// =============================================================================================
+__global__ void __launch_bounds__(NT) stage_agg_kernel(const KParams *__restrict__ Pg) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const KParams &P = *Pg;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t R = P.R, T = R * NT;
+
+    tplx_instr *s_prog = reinterpret_cast<tplx_instr *>(smem);
+    ColIn *s_cols = reinterpret_cast<ColIn *>(smem + P.smem_cols_off);
+    uint64_t *s_regs = reinterpret_cast<uint64_t *>(smem + P.smem_regs_off) + tid;
+    uint64_t *s_wacc = reinterpret_cast<uint64_t *>(smem + P.smem_misc_off);  // [NT/32][n_accs]
+
+    for (uint32_t i = tid; i < P.n_instr * (sizeof(tplx_instr) / 16); i += NT)
+        reinterpret_cast<uint4 *>(s_prog)[i] = reinterpret_cast<const uint4 *>(P.prog)[i];
+    for (uint32_t i = tid; i < P.n_in * (sizeof(ColIn) / 8); i += NT)
+        reinterpret_cast<uint64_t *>(s_cols)[i] = reinterpret_cast<const uint64_t *>(P.in)[i];
+    __syncthreads();
+
+    VMThread t;
+    t.scr_cap = P.scratch_per_thread;
+    t.scratch = P.scratch + ((size_t)blockIdx.x * NT + tid) * (size_t)P.scratch_per_thread;
+    const uint32_t na = P.n_accs;
+
+    for (uint32_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+        const uint64_t base = (uint64_t)tile * T;
+        uint64_t acc[TPLX_MAX_ACCS];
+#pragma unroll
+        for (uint32_t k = 0; k < TPLX_MAX_ACCS; ++k) acc[k] = k < na ? acc_identity(P.accs[k].kind) : 0;
+        for (uint32_t s = 0; s < R; ++s) {
+            const uint64_t row = base + (uint64_t)s * NT + tid;
+            t.alive = row < P.n_rows;
+            t.exc_code = 0;
+            t.scr_used = 0;
+            VM<NT>::run(s_prog, 0, P.n_instr, s_regs, s_cols, row, P.cpool, t);
+            if (t.alive) {
+#pragma unroll
+                for (uint32_t k = 0; k < TPLX_MAX_ACCS; ++k)
+                    if (k < na) acc[k] = acc_combine(P.accs[k].kind, acc[k], s_regs[P.accs[k].slot * NT]);
+            }
+            if (t.exc_code) {
+                uint32_t pos = atomicAdd(&P.counters[2], 1u);
+                if (pos < P.cap_exc) {
+                    tplx_exception_rec rec;
+                    rec.row = (int64_t)row;
+                    rec.row_no = 0;  // assigned on the host after sorting by row
+                    rec.code = t.exc_code;
+                    rec.op_id = P.opids[t.exc_op];
+                    P.exc[pos] = rec;
+                } else atomicOr(&P.counters[1], 4u);
+            }
+        }
+        // warp tree: shfl_down 16,8,4,2,1 (lane 0 holds the warp partial)
+#pragma unroll
+        for (uint32_t k = 0; k < TPLX_MAX_ACCS; ++k) {
+            if (k < na) {
+                uint64_t v = acc[k];
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                    uint64_t other = __shfl_down_sync(0xFFFFFFFFu, v, o);
+                    v = acc_combine(P.accs[k].kind, v, other);
+                }
+                if (lane == 0) s_wacc[warp * na + k] = v;
+            }
+        }
+        __syncthreads();
+        if (tid < na) {
+            uint64_t v = s_wacc[tid];
+            for (uint32_t w = 1; w < NT / 32; ++w) v = acc_combine(P.accs[tid].kind, v, s_wacc[w * na + tid]);
+            P.tile_partials[(size_t)tile * na + tid] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// thread t folds tile partials t, t+FIN_NT, ... in order; warp tree; warps sequential; then init (+) total
+__global__ void __launch_bounds__(FIN_NT) agg_finalize_kernel(const KParams *__restrict__ Pg) {
+    __shared__ uint64_t s_w[FIN_NT / 32];
+    const KParams &P = *Pg;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint32_t k = 0; k < P.n_accs; ++k) {
+        const uint32_t kind = P.accs[k].kind;
+        uint64_t v = acc_identity(kind);
+        for (uint32_t tile = tid; tile < P.n_tiles; tile += FIN_NT)
+            v = acc_combine(kind, v, P.tile_partials[(size_t)tile * P.n_accs + k]);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            uint64_t other = __shfl_down_sync(0xFFFFFFFFu, v, o);
+            v = acc_combine(kind, v, other);
+        }
+        if (lane == 0) s_w[warp] = v;
+        __syncthreads();
+        if (tid == 0) {
+            uint64_t tot = s_w[0];
+            for (uint32_t w = 1; w < FIN_NT / 32; ++w) tot = acc_combine(kind, tot, s_w[w]);
+            // per-task intermediate starts from the initial value (BlockBasedTaskBuilder.cc:185-206)
+            P.agg_out[k] = acc_combine(kind, (uint64_t)P.accs[k].init, tot);
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace tplx

@@ -1,0 +1,806 @@
+// tplx_gpu.cu — C-ABI implementation (host side of libtplx_gpu.so).
+//
+// Plays the role of LocalBackend::executeTransformStage + TransformTask for the GPU:
+// (reference tuplex/core/src/ee/local/LocalBackend.cc:815-1252, core/src/physical/TransformTask.cc:382-513)
+// validates a stage descriptor, keeps device copies of the program, sizes tiles/shared memory,
+// launches the stage kernels on a per-device stream, and hands back results in column form, in the
+// reference's Partition byte format, and as exception records.
+//
+// No CPU fallback exists in this file by design: every compute entry point requires a CUDA device.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/tplx_gpu.h"
+#include "kernels.cuh"
+#include "rowfmt.cuh"
+#include "hashagg.cuh"
+
+using namespace tplx;
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static int32_t fail(int32_t code, const std::string &msg) {
+    g_last_error = msg;
+    return code;
+}
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t _e = (call);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            return fail(TPLX_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));     \
+        }                                                                                     \
+    } while (0)
+
+extern "C" const char *tplx_gpu_last_error(void) { return g_last_error.c_str(); }
+
+// ---------------------------------------------------------------------------------------------
+// devices
+// ---------------------------------------------------------------------------------------------
+struct Device {
+    int id = -1;
+    cudaStream_t stream = nullptr;
+    cudaDeviceProp prop{};
+    int smem_optin = 0;
+    uint8_t *scratch = nullptr;
+    size_t scratch_bytes = 0;
+    std::mutex mu;
+};
+static std::vector<Device *> g_devices;
+static std::mutex g_mu;
+
+static Device *get_device(int32_t device) {
+    for (auto *d : g_devices)
+        if (d->id == device) return d;
+    return nullptr;
+}
+
+extern "C" int32_t tplx_gpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" int32_t tplx_gpu_init(const int32_t *devices, int32_t n) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int count = tplx_gpu_device_count();
+    if (count <= 0) return fail(TPLX_E_NODEVICE, "no CUDA device visible; the GPU backend has no CPU fallback");
+    std::vector<int32_t> want;
+    if (!devices || n <= 0) want.push_back(0);
+    else want.assign(devices, devices + n);
+    for (int32_t id : want) {
+        if (id < 0 || id >= count) return fail(TPLX_E_BADARG, "device index out of range");
+        if (get_device(id)) continue;
+        Device *d = new Device();
+        d->id = id;
+        CU(cudaSetDevice(id));
+        CU(cudaGetDeviceProperties(&d->prop, id));
+        CU(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+        CU(cudaDeviceGetAttribute(&d->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, id));
+        cudaMemPool_t pool;
+        CU(cudaDeviceGetDefaultMemPool(&pool, id));
+        uint64_t thr = UINT64_MAX;
+        CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        CU(cudaFuncSetAttribute(stage_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d->smem_optin));
+        CU(cudaFuncSetAttribute(stage_agg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d->smem_optin));
+        CU(cudaFuncSetAttribute(stage_hash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d->smem_optin));
+        g_devices.push_back(d);
+    }
+    return TPLX_OK;
+}
+
+extern "C" int32_t tplx_gpu_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto *d : g_devices) {
+        cudaSetDevice(d->id);
+        cudaStreamSynchronize(d->stream);
+        if (d->scratch) cudaFree(d->scratch);
+        cudaStreamDestroy(d->stream);
+        delete d;
+    }
+    g_devices.clear();
+    return TPLX_OK;
+}
+
+extern "C" int32_t tplx_gpu_device_info(int32_t device, char *name_buf, int32_t buf_len, int32_t *sm_count,
+                                        uint64_t *mem_bytes) {
+    Device *d = get_device(device);
+    if (!d) return fail(TPLX_E_BADARG, "device not initialised (call tplx_gpu_init)");
+    if (name_buf && buf_len > 0) {
+        strncpy(name_buf, d->prop.name, buf_len - 1);
+        name_buf[buf_len - 1] = 0;
+    }
+    if (sm_count) *sm_count = d->prop.multiProcessorCount;
+    if (mem_bytes) *mem_bytes = d->prop.totalGlobalMem;
+    return TPLX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage
+// ---------------------------------------------------------------------------------------------
+struct StageDev {
+    Device *dev = nullptr;
+    tplx_instr *prog = nullptr;
+    uint8_t *cpool = nullptr;
+    int64_t *opids = nullptr;
+    HashTable *ht = nullptr;  // HASH endpoint
+};
+
+struct tplx_stage {
+    tplx_stage_header hdr{};
+    std::vector<uint8_t> in_types;
+    std::vector<tplx_outcol> out_cols;
+    std::vector<tplx_acc> accs;
+    std::vector<int64_t> opids;
+    std::vector<tplx_instr> instrs;
+    std::vector<uint8_t> cpool;
+    bool has_str = false;
+    bool materialises = false;
+    uint32_t n_str_out = 0;
+    std::vector<StageDev> devs;
+    // adaptive output capacities learnt from earlier blocks (bytes per input row per str out col)
+    std::vector<double> est_bytes_per_row;
+    double est_exc_per_row = 0.0;
+    std::mutex mu;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+extern "C" int32_t tplx_gpu_stage_create(const void *desc, uint64_t desc_bytes, tplx_stage **out) {
+    if (!desc || !out || desc_bytes < sizeof(tplx_stage_header)) return fail(TPLX_E_BADARG, "stage_create: bad arguments");
+    const uint8_t *p = static_cast<const uint8_t *>(desc);
+    tplx_stage_header h;
+    memcpy(&h, p, sizeof(h));
+    if (h.magic != TPLX_IR_MAGIC) return fail(TPLX_E_BADDESC, "stage descriptor: bad magic");
+    if (h.version != TPLX_IR_VERSION) return fail(TPLX_E_BADDESC, "stage descriptor: version mismatch");
+    if (h.total_bytes != desc_bytes) return fail(TPLX_E_BADDESC, "stage descriptor: size mismatch");
+    if (h.n_in_cols > TPLX_MAX_COLS || h.n_out_cols > TPLX_MAX_COLS || h.n_accs > TPLX_MAX_ACCS || h.n_keys > TPLX_MAX_KEYS)
+        return fail(TPLX_E_BADDESC, "stage descriptor: too many columns/accumulators");
+    size_t off = sizeof(h);
+    auto need = [&](size_t n) { return off + n <= desc_bytes; };
+    tplx_stage *s = new tplx_stage();
+    s->hdr = h;
+    auto bad = [&](const char *m) {
+        delete s;
+        return fail(TPLX_E_BADDESC, m);
+    };
+    size_t n = align_up(h.n_in_cols, 8);
+    if (!need(n)) return bad("stage descriptor truncated (in_types)");
+    s->in_types.assign(p + off, p + off + h.n_in_cols);
+    off += n;
+    n = align_up(h.n_out_cols * sizeof(tplx_outcol), 8);
+    if (!need(n)) return bad("stage descriptor truncated (out_cols)");
+    s->out_cols.resize(h.n_out_cols);
+    memcpy(s->out_cols.data(), p + off, h.n_out_cols * sizeof(tplx_outcol));
+    off += n;
+    n = h.n_accs * sizeof(tplx_acc);
+    if (!need(n)) return bad("stage descriptor truncated (accs)");
+    s->accs.resize(h.n_accs);
+    memcpy(s->accs.data(), p + off, n);
+    off += n;
+    n = h.n_ops * sizeof(int64_t);
+    if (!need(n)) return bad("stage descriptor truncated (opids)");
+    s->opids.resize(h.n_ops);
+    memcpy(s->opids.data(), p + off, n);
+    off += n;
+    n = (size_t)h.n_instr * sizeof(tplx_instr);
+    if (!need(n)) return bad("stage descriptor truncated (instrs)");
+    s->instrs.resize(h.n_instr);
+    memcpy(s->instrs.data(), p + off, n);
+    off += n;
+    n = align_up(h.const_bytes, 8);
+    if (!need(n)) return bad("stage descriptor truncated (const pool)");
+    s->cpool.assign(p + off, p + off + h.const_bytes);
+    off += n;
+
+    // ---- validate the program (what TransformStage::compile would reject) ----
+    const uint32_t ns = h.n_slots;
+    auto slot_ok = [&](uint16_t v, uint32_t width) { return v == TPLX_NOSLOT || (uint32_t)v + width <= ns; };
+    for (uint32_t i = 0; i < h.n_instr; ++i) {
+        const tplx_instr &in = s->instrs[i];
+        if (!slot_ok(in.dst, 1) || !slot_ok(in.a, 1) || !slot_ok(in.b, 1) || !slot_ok(in.c, 1) || !slot_ok(in.guard, 1))
+            return bad("program: slot out of range");
+        if (h.n_ops && in.opidx >= h.n_ops) return bad("program: operator index out of range");
+        switch (in.op) {
+            case TPLX_OP_LDCOL:
+                if (in.imm < 0 || in.imm >= h.n_in_cols) return bad("program: LDCOL column out of range");
+                if (in.flags != s->in_types[in.imm]) return bad("program: LDCOL type mismatch");
+                break;
+            case TPLX_OP_LDS:
+                if (in.imm < 0 || in.imm2 < 0 || (uint64_t)in.imm + (uint64_t)in.imm2 > h.const_bytes)
+                    return bad("program: LDS constant out of range");
+                break;
+            case TPLX_OP_SREPLACE: case TPLX_OP_SCONCAT: case TPLX_OP_SFMTD: case TPLX_OP_I2S:
+                s->materialises = true;
+                break;
+            default: break;
+        }
+        if (in.op >= TPLX_OP_SLEN && in.op <= TPLX_OP_SSTRIP) s->has_str = true;
+        if (in.op == TPLX_OP_LDS) s->has_str = true;
+    }
+    if (h.split_pc > h.n_instr) return bad("program: split_pc out of range");
+    for (auto t : s->in_types) {
+        if (t > TPLX_T_STR) return bad("stage descriptor: unknown input type");
+        if (t == TPLX_T_STR) s->has_str = true;
+    }
+    for (auto &oc : s->out_cols) {
+        if (oc.type > TPLX_T_STR) return bad("stage descriptor: unknown output type");
+        if (!slot_ok(oc.slot, oc.type == TPLX_T_STR ? 2 : 1) || oc.slot == TPLX_NOSLOT) return bad("stage descriptor: output slot out of range");
+        if (oc.type == TPLX_T_STR) { s->n_str_out++; s->has_str = true; }
+    }
+    if (s->n_str_out + 2 > MAX_SCAN) return bad("stage descriptor: too many string output columns");
+    for (auto &a : s->accs)
+        if (a.kind > TPLX_ACC_MAX_F64 || a.slot >= ns) return bad("stage descriptor: bad accumulator");
+    if (h.endpoint > TPLX_EP_HASH) return bad("stage descriptor: unknown endpoint");
+    if (h.endpoint == TPLX_EP_AGGREGATE && h.n_accs == 0) return bad("aggregate endpoint without accumulators");
+    if (h.endpoint == TPLX_EP_HASH && (h.n_keys == 0 || h.n_keys > h.n_out_cols)) return bad("hash endpoint without key columns");
+    s->est_bytes_per_row.assign(h.n_out_cols, -1.0);
+    *out = s;
+    return TPLX_OK;
+}
+
+static int32_t stage_dev(tplx_stage *s, Device *d, StageDev **out) {
+    std::lock_guard<std::mutex> lk(s->mu);
+    for (auto &sd : s->devs)
+        if (sd.dev == d) { *out = &sd; return TPLX_OK; }
+    s->devs.reserve(16);
+    StageDev sd;
+    sd.dev = d;
+    CU(cudaSetDevice(d->id));
+    size_t nb = std::max<size_t>(s->instrs.size() * sizeof(tplx_instr), 16);
+    CU(cudaMalloc(&sd.prog, nb));
+    CU(cudaMemcpy(sd.prog, s->instrs.data(), s->instrs.size() * sizeof(tplx_instr), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&sd.cpool, std::max<size_t>(s->cpool.size(), 16)));
+    CU(cudaMemcpy(sd.cpool, s->cpool.data(), s->cpool.size(), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&sd.opids, std::max<size_t>(s->opids.size() * 8, 16)));
+    CU(cudaMemcpy(sd.opids, s->opids.data(), s->opids.size() * 8, cudaMemcpyHostToDevice));
+    s->devs.push_back(sd);
+    *out = &s->devs.back();
+    return TPLX_OK;
+}
+
+extern "C" int32_t tplx_gpu_stage_destroy(tplx_stage *s) {
+    if (!s) return TPLX_OK;
+    for (auto &sd : s->devs) {
+        cudaSetDevice(sd.dev->id);
+        cudaStreamSynchronize(sd.dev->stream);
+        cudaFree(sd.prog);
+        cudaFree(sd.cpool);
+        cudaFree(sd.opids);
+        if (sd.ht) hash_table_destroy(sd.ht);
+    }
+    delete s;
+    return TPLX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// blocks
+// ---------------------------------------------------------------------------------------------
+struct tplx_block {
+    Device *dev = nullptr;
+    uint64_t n_rows = 0;
+    std::vector<ColIn> cols;           // device pointers
+    std::vector<uint64_t> data_bytes;  // per column
+    std::vector<void *> owned;         // allocations to free
+};
+
+extern "C" int32_t tplx_gpu_block_upload(int32_t device, const tplx_column *cols, uint32_t n_cols, uint64_t n_rows,
+                                         tplx_block **out) {
+    Device *d = get_device(device);
+    if (!d) return fail(TPLX_E_NODEVICE, "block_upload: device not initialised (no CPU fallback)");
+    if (!cols || !out || n_cols > TPLX_MAX_COLS) return fail(TPLX_E_BADARG, "block_upload: bad arguments");
+    CU(cudaSetDevice(d->id));
+    tplx_block *b = new tplx_block();
+    b->dev = d;
+    b->n_rows = n_rows;
+    for (uint32_t c = 0; c < n_cols; ++c) {
+        ColIn ci{};
+        ci.type = cols[c].type;
+        uint64_t nb = cols[c].type == TPLX_T_STR ? cols[c].data_bytes : n_rows * 8;
+        void *dd = nullptr;
+        CU(cudaMallocAsync(&dd, std::max<uint64_t>(nb, 16), d->stream));
+        b->owned.push_back(dd);
+        if (nb) CU(cudaMemcpyAsync(dd, cols[c].data, nb, cudaMemcpyHostToDevice, d->stream));
+        ci.data = dd;
+        if (cols[c].type == TPLX_T_STR) {
+            void *od = nullptr;
+            CU(cudaMallocAsync(&od, (n_rows + 1) * 4, d->stream));
+            b->owned.push_back(od);
+            CU(cudaMemcpyAsync(od, cols[c].offsets, (n_rows + 1) * 4, cudaMemcpyHostToDevice, d->stream));
+            ci.offsets = static_cast<const uint32_t *>(od);
+        }
+        b->cols.push_back(ci);
+        b->data_bytes.push_back(nb);
+    }
+    *out = b;
+    return TPLX_OK;
+}
+
+extern "C" int32_t tplx_gpu_block_wrap_device(int32_t device, const tplx_column *cols, uint32_t n_cols,
+                                              uint64_t n_rows, tplx_block **out) {
+    Device *d = get_device(device);
+    if (!d) return fail(TPLX_E_NODEVICE, "block_wrap_device: device not initialised");
+    if (!cols || !out || n_cols > TPLX_MAX_COLS) return fail(TPLX_E_BADARG, "block_wrap_device: bad arguments");
+    tplx_block *b = new tplx_block();
+    b->dev = d;
+    b->n_rows = n_rows;
+    for (uint32_t c = 0; c < n_cols; ++c) {
+        ColIn ci{};
+        ci.type = cols[c].type;
+        ci.data = cols[c].data;
+        ci.offsets = cols[c].offsets;
+        b->cols.push_back(ci);
+        b->data_bytes.push_back(cols[c].type == TPLX_T_STR ? cols[c].data_bytes : n_rows * 8);
+    }
+    *out = b;
+    return TPLX_OK;
+}
+
+extern "C" int32_t tplx_gpu_block_rows(const tplx_block *b, uint64_t *n_rows) {
+    if (!b || !n_rows) return fail(TPLX_E_BADARG, "block_rows: bad arguments");
+    *n_rows = b->n_rows;
+    return TPLX_OK;
+}
+
+extern "C" int32_t tplx_gpu_block_free(tplx_block *b) {
+    if (!b) return TPLX_OK;
+    cudaSetDevice(b->dev->id);
+    for (void *p : b->owned) cudaFreeAsync(p, b->dev->stream);
+    delete b;
+    return TPLX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// results
+// ---------------------------------------------------------------------------------------------
+struct tplx_result {
+    Device *dev = nullptr;
+    tplx_stage *stage = nullptr;
+    const tplx_block *block = nullptr;  // borrowed, needed for exception row gather
+    uint64_t n_in = 0, n_out = 0, n_exc = 0;
+    std::vector<OutCol> out;
+    std::vector<uint8_t> out_types;
+    std::vector<uint64_t> str_bytes;
+    tplx_exception_rec *exc = nullptr;
+    uint64_t *agg_out = nullptr;
+    uint32_t n_accs = 0;
+    std::vector<void *> owned;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+    double kernel_ms = 0, total_ms = 0;
+    uint32_t launches = 0;
+    bool owns_block = false;
+    tplx_block *owned_block = nullptr;
+};
+
+extern "C" int32_t tplx_gpu_result_free(tplx_result *r) {
+    if (!r) return TPLX_OK;
+    cudaSetDevice(r->dev->id);
+    for (void *p : r->owned) cudaFreeAsync(p, r->dev->stream);
+    if (r->ev0) cudaEventDestroy(r->ev0);
+    if (r->ev1) cudaEventDestroy(r->ev1);
+    if (r->evk0) cudaEventDestroy(r->evk0);
+    if (r->evk1) cudaEventDestroy(r->evk1);
+    if (r->owned_block) tplx_gpu_block_free(r->owned_block);
+    delete r;
+    return TPLX_OK;
+}
+
+// shared-memory layout; must mirror stage_rows_kernel / stage_agg_kernel
+struct Layout {
+    uint32_t cols_off, regs_off, stage_off, misc_off, total;
+    std::vector<uint32_t> col_stage_off;
+};
+static Layout make_layout(const tplx_stage *s, uint32_t R, bool rows_ep) {
+    Layout L;
+    const uint32_t T = R * NT, W = T / 32;
+    size_t off = align_up(std::max<size_t>(s->instrs.size(), 1) * sizeof(tplx_instr), 16);
+    L.cols_off = (uint32_t)off;
+    off = align_up(off + std::max<size_t>(s->in_types.size(), 1) * sizeof(ColIn), 16);
+    L.regs_off = (uint32_t)off;
+    uint32_t nslots = std::max<uint32_t>(std::max<uint32_t>(s->hdr.n_slots, s->n_str_out), 1);
+    off = align_up(off + (size_t)nslots * NT * 8, 16);
+    L.stage_off = (uint32_t)off;
+    if (rows_ep) {
+        size_t so = 0;
+        for (auto &oc : s->out_cols) {
+            L.col_stage_off.push_back((uint32_t)so);
+            so += (size_t)T * (oc.type == TPLX_T_STR ? 16 : 8);
+        }
+        off = align_up(off + so, 16);
+        L.misc_off = (uint32_t)off;
+        off += (size_t)(4 * W + 2 + T) * 4 + (size_t)T * 2 + (size_t)(2 * MAX_SCAN + NT / 32 + 1) * 8 + 16;
+    } else {
+        L.misc_off = (uint32_t)off;
+        off += (size_t)(NT / 32) * std::max<size_t>(s->accs.size(), 1) * 8;
+    }
+    L.total = (uint32_t)align_up(off, 16);
+    return L;
+}
+
+static int32_t ensure_scratch(Device *d, size_t bytes) {
+    if (bytes <= d->scratch_bytes) return TPLX_OK;
+    CU(cudaStreamSynchronize(d->stream));
+    if (d->scratch) CU(cudaFree(d->scratch));
+    d->scratch = nullptr;
+    d->scratch_bytes = 0;
+    CU(cudaMalloc(&d->scratch, bytes));
+    d->scratch_bytes = bytes;
+    return TPLX_OK;
+}
+
+static int32_t run_rows(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_t first_row_no, tplx_result *r);
+static int32_t run_agg(tplx_stage *s, StageDev *sd, const tplx_block *b, tplx_result *r);
+static int32_t run_hash(tplx_stage *s, StageDev *sd, const tplx_block *b, tplx_result *r);
+
+extern "C" int32_t tplx_gpu_stage_run(tplx_stage *s, const tplx_block *b, int64_t first_row_no, tplx_result **out) {
+    if (!s || !b || !out) return fail(TPLX_E_BADARG, "stage_run: bad arguments");
+    if (b->cols.size() != s->in_types.size()) return fail(TPLX_E_BADARG, "stage_run: block column count != stage input schema");
+    for (size_t c = 0; c < b->cols.size(); ++c)
+        if ((uint8_t)b->cols[c].type != s->in_types[c]) return fail(TPLX_E_BADARG, "stage_run: block column type != stage input schema");
+    Device *d = b->dev;
+    std::lock_guard<std::mutex> lk(d->mu);
+    CU(cudaSetDevice(d->id));
+    StageDev *sd = nullptr;
+    int32_t rc = stage_dev(s, d, &sd);
+    if (rc) return rc;
+    tplx_result *r = new tplx_result();
+    r->dev = d;
+    r->stage = s;
+    r->block = b;
+    r->n_in = b->n_rows;
+    CU(cudaEventCreate(&r->ev0));
+    CU(cudaEventCreate(&r->ev1));
+    CU(cudaEventCreate(&r->evk0));
+    CU(cudaEventCreate(&r->evk1));
+    CU(cudaEventRecord(r->ev0, d->stream));
+    switch (s->hdr.endpoint) {
+        case TPLX_EP_MEMORY: rc = run_rows(s, sd, b, first_row_no, r); break;
+        case TPLX_EP_AGGREGATE: rc = run_agg(s, sd, b, r); break;
+        default: rc = run_hash(s, sd, b, r); break;
+    }
+    if (rc) {
+        tplx_gpu_result_free(r);
+        return rc;
+    }
+    CU(cudaEventRecord(r->ev1, d->stream));
+    *out = r;
+    return TPLX_OK;
+}
+
+extern "C" int32_t tplx_gpu_stage_run_host(tplx_stage *s, int32_t device, const tplx_column *cols, uint32_t n_cols,
+                                           uint64_t n_rows, int64_t first_row_no, tplx_result **out) {
+    Device *d = get_device(device);
+    if (!d) return fail(TPLX_E_NODEVICE, "stage_run_host: device not initialised (no CPU fallback)");
+    CU(cudaSetDevice(d->id));
+    cudaEvent_t e0;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventRecord(e0, d->stream));
+    tplx_block *b = nullptr;
+    int32_t rc = tplx_gpu_block_upload(device, cols, n_cols, n_rows, &b);
+    if (rc) { cudaEventDestroy(e0); return rc; }
+    rc = tplx_gpu_stage_run(s, b, first_row_no, out);
+    if (rc) {
+        tplx_gpu_block_free(b);
+        cudaEventDestroy(e0);
+        return rc;
+    }
+    cudaEventDestroy((*out)->ev0);
+    (*out)->ev0 = e0;  // total time includes the H2D copies
+    (*out)->owned_block = b;
+    return TPLX_OK;
+}
+
+static int32_t fill_common(KParams &P, tplx_stage *s, StageDev *sd, const tplx_block *b, const Layout &L, uint32_t R) {
+    memset(&P, 0, sizeof(P));
+    P.n_rows = b->n_rows;
+    P.n_instr = (uint32_t)s->instrs.size();
+    P.split_pc = s->hdr.split_pc;
+    P.n_slots = s->hdr.n_slots;
+    P.n_in = (uint32_t)s->in_types.size();
+    P.n_out = (uint32_t)s->out_cols.size();
+    P.n_str_out = s->n_str_out;
+    P.n_accs = (uint32_t)s->accs.size();
+    P.R = R;
+    P.n_tiles = (uint32_t)((b->n_rows + (uint64_t)R * NT - 1) / ((uint64_t)R * NT));
+    P.K = 2 + s->n_str_out;
+    P.smem_cols_off = L.cols_off;
+    P.smem_regs_off = L.regs_off;
+    P.smem_stage_off = L.stage_off;
+    P.smem_misc_off = L.misc_off;
+    P.prog = sd->prog;
+    P.cpool = sd->cpool;
+    P.opids = sd->opids;
+    for (size_t c = 0; c < b->cols.size(); ++c) P.in[c] = b->cols[c];
+    for (size_t k = 0; k < s->accs.size(); ++k) {
+        P.accs[k].kind = s->accs[k].kind;
+        P.accs[k].slot = s->accs[k].slot;
+        P.accs[k].init = s->accs[k].init;
+    }
+    return TPLX_OK;
+}
+
+template <typename T>
+static int32_t dalloc(tplx_result *r, T **p, size_t count) {
+    void *q = nullptr;
+    CU(cudaMallocAsync(&q, std::max<size_t>(count * sizeof(T), 16), r->dev->stream));
+    r->owned.push_back(q);
+    *p = static_cast<T *>(q);
+    return TPLX_OK;
+}
+
+static int32_t run_rows(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_t first_row_no, tplx_result *r) {
+    Device *d = sd->dev;
+    const uint64_t n = b->n_rows;
+    r->out_types.clear();
+    for (auto &oc : s->out_cols) r->out_types.push_back(oc.type);
+    r->str_bytes.assign(s->out_cols.size(), 0);
+    r->out.assign(s->out_cols.size(), OutCol{});
+    if (n == 0) {
+        for (size_t c = 0; c < s->out_cols.size(); ++c)
+            if (s->out_cols[c].type == TPLX_T_STR) {
+                int32_t rc = dalloc(r, &r->out[c].offsets, 1);
+                if (rc) return rc;
+                CU(cudaMemsetAsync(r->out[c].offsets, 0, 4, d->stream));
+            }
+        return TPLX_OK;
+    }
+    // tile shape: strings are compute heavy -> small tiles; fixed width -> as large as shared memory allows
+    const uint32_t smem_budget = (uint32_t)std::min<int>(d->smem_optin, 113 * 1024);
+    uint32_t R = s->has_str ? 4 : 16;
+    Layout L = make_layout(s, R, true);
+    while (R > 1 && L.total > smem_budget) {
+        R /= 2;
+        L = make_layout(s, R, true);
+    }
+    if (L.total > (uint32_t)d->smem_optin) return fail(TPLX_E_UNSUPPORTED, "stage needs more shared memory than one SM has");
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stage_rows_kernel, NT, L.total));
+    if (occ < 1) return fail(TPLX_E_UNSUPPORTED, "stage kernel cannot be resident");
+    KParams P;
+    fill_common(P, s, sd, b, L, R);
+    const uint32_t grid = std::min<uint32_t>(P.n_tiles, (uint32_t)(occ * d->prop.multiProcessorCount));
+    P.first_row_no = first_row_no;
+    P.scratch_per_thread = s->materialises ? std::max<uint32_t>(s->hdr.scratch_bytes, 64) * R : 0;
+    int32_t rc = ensure_scratch(d, (size_t)grid * NT * P.scratch_per_thread);
+    if (rc) return rc;
+    P.scratch = d->scratch;
+
+    // capacities: rows worst case; string bytes + exceptions adaptive with exact retry
+    uint64_t in_str_bytes = 0;
+    for (size_t c = 0; c < b->cols.size(); ++c)
+        if (s->in_types[c] == TPLX_T_STR) in_str_bytes += b->data_bytes[c];
+    std::vector<uint64_t> cap_bytes(s->out_cols.size(), 0);
+    for (size_t c = 0; c < s->out_cols.size(); ++c) {
+        if (s->out_cols[c].type != TPLX_T_STR) continue;
+        double est = s->est_bytes_per_row[c];
+        uint64_t cap = est >= 0 ? (uint64_t)(est * 1.25 * (double)n) + (1u << 16) : in_str_bytes / 8 + n + (1u << 20);
+        cap_bytes[c] = std::min<uint64_t>(cap, 0xFFFFFFFFull);
+    }
+    uint64_t cap_exc = std::max<uint64_t>(4096, (uint64_t)(s->est_exc_per_row * 1.5 * (double)n) + n / 64);
+    uint64_t cap_rows = n;
+
+    uint64_t *tile_state = nullptr, *totals = nullptr;
+    uint32_t *counters = nullptr;
+    KParams *dP = nullptr;
+    const size_t state_words = (size_t)P.n_tiles * (1 + 2 * P.K);
+    rc = dalloc(r, &tile_state, state_words);
+    if (rc) return rc;
+    rc = dalloc(r, &totals, MAX_SCAN);
+    if (rc) return rc;
+    rc = dalloc(r, &counters, 4);
+    if (rc) return rc;
+    rc = dalloc(r, &dP, 1);
+    if (rc) return rc;
+    P.tile_state = tile_state;
+    P.totals = totals;
+    P.counters = counters;
+
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        int si = 0;
+        for (size_t c = 0; c < s->out_cols.size(); ++c) {
+            OutCol &oc = P.out[c];
+            oc.slot = s->out_cols[c].slot;
+            oc.type = s->out_cols[c].type;
+            oc.stage_off = L.col_stage_off[c];
+            if (oc.type == TPLX_T_STR) {
+                oc.strk = si++;
+                oc.cap_bytes = cap_bytes[c];
+                rc = dalloc(r, &oc.offsets, cap_rows + 1);
+                if (rc) return rc;
+                rc = dalloc(r, &oc.bytes, cap_bytes[c]);
+                if (rc) return rc;
+                oc.data = nullptr;
+            } else {
+                oc.strk = -1;
+                rc = dalloc(r, &oc.data, cap_rows);
+                if (rc) return rc;
+            }
+        }
+        P.cap_rows = cap_rows;
+        P.cap_exc = cap_exc;
+        rc = dalloc(r, &P.exc, cap_exc);
+        if (rc) return rc;
+        CU(cudaMemsetAsync(tile_state, 0, state_words * 8, d->stream));
+        CU(cudaMemsetAsync(counters, 0, 16, d->stream));
+        CU(cudaMemsetAsync(totals, 0, MAX_SCAN * 8, d->stream));
+        CU(cudaMemcpyAsync(dP, &P, sizeof(P), cudaMemcpyHostToDevice, d->stream));
+        CU(cudaEventRecord(r->evk0, d->stream));
+        stage_rows_kernel<<<grid, NT, L.total, d->stream>>>(dP);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(r->evk1, d->stream));
+        r->launches += 1;
+        uint64_t h_tot[MAX_SCAN];
+        uint32_t h_cnt[4];
+        CU(cudaMemcpyAsync(h_tot, totals, MAX_SCAN * 8, cudaMemcpyDeviceToHost, d->stream));
+        CU(cudaMemcpyAsync(h_cnt, counters, 16, cudaMemcpyDeviceToHost, d->stream));
+        CU(cudaStreamSynchronize(d->stream));
+        r->n_out = h_tot[0];
+        r->n_exc = h_tot[1];
+        si = 0;
+        for (size_t c = 0; c < s->out_cols.size(); ++c)
+            if (s->out_cols[c].type == TPLX_T_STR) {
+                r->str_bytes[c] = h_tot[2 + si++];
+                s->est_bytes_per_row[c] = (double)r->str_bytes[c] / (double)n;
+            }
+        s->est_exc_per_row = (double)r->n_exc / (double)n;
+        if (h_cnt[1] == 0) break;
+        if (attempt == 2) return fail(TPLX_E_OVERFLOW, "output capacity retry failed");
+        for (size_t c = 0; c < s->out_cols.size(); ++c)
+            if (s->out_cols[c].type == TPLX_T_STR) {
+                if (r->str_bytes[c] > 0xFFFFFFFFull)
+                    return fail(TPLX_E_OVERFLOW, "string output column exceeds 4 GiB in one block; use smaller blocks");
+                cap_bytes[c] = r->str_bytes[c] + 16;
+            }
+        cap_exc = r->n_exc + 16;
+    }
+    for (size_t c = 0; c < s->out_cols.size(); ++c) r->out[c] = P.out[c];
+    r->exc = P.exc;
+    return TPLX_OK;
+}
+
+static int32_t run_agg(tplx_stage *s, StageDev *sd, const tplx_block *b, tplx_result *r) {
+    Device *d = sd->dev;
+    const uint64_t n = b->n_rows;
+    const uint32_t R = 16;
+    Layout L = make_layout(s, R, false);
+    if (L.total > (uint32_t)d->smem_optin) return fail(TPLX_E_UNSUPPORTED, "stage needs more shared memory than one SM has");
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stage_agg_kernel, NT, L.total));
+    if (occ < 1) return fail(TPLX_E_UNSUPPORTED, "stage kernel cannot be resident");
+    KParams P;
+    fill_common(P, s, sd, b, L, R);
+    const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(P.n_tiles, (uint32_t)(occ * d->prop.multiProcessorCount)));
+    P.scratch_per_thread = s->materialises ? std::max<uint32_t>(s->hdr.scratch_bytes, 64) : 0;
+    int32_t rc = ensure_scratch(d, (size_t)grid * NT * P.scratch_per_thread);
+    if (rc) return rc;
+    P.scratch = d->scratch;
+    uint64_t cap_exc = std::max<uint64_t>(4096, (uint64_t)(s->est_exc_per_row * 1.5 * (double)n) + n / 64);
+    KParams *dP = nullptr;
+    uint32_t *counters = nullptr;
+    rc = dalloc(r, &P.tile_partials, (size_t)std::max<uint32_t>(P.n_tiles, 1) * P.n_accs);
+    if (rc) return rc;
+    rc = dalloc(r, &P.agg_out, TPLX_MAX_ACCS);
+    if (rc) return rc;
+    rc = dalloc(r, &counters, 4);
+    if (rc) return rc;
+    rc = dalloc(r, &dP, 1);
+    if (rc) return rc;
+    P.counters = counters;
+    r->n_accs = P.n_accs;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        P.cap_exc = cap_exc;
+        rc = dalloc(r, &P.exc, cap_exc);
+        if (rc) return rc;
+        CU(cudaMemsetAsync(counters, 0, 16, d->stream));
+        CU(cudaMemcpyAsync(dP, &P, sizeof(P), cudaMemcpyHostToDevice, d->stream));
+        CU(cudaEventRecord(r->evk0, d->stream));
+        if (P.n_tiles) {
+            stage_agg_kernel<<<grid, NT, L.total, d->stream>>>(dP);
+            CU(cudaGetLastError());
+            r->launches += 1;
+        }
+        agg_finalize_kernel<<<1, FIN_NT, 0, d->stream>>>(dP);
+        CU(cudaGetLastError());
+        r->launches += 1;
+        CU(cudaEventRecord(r->evk1, d->stream));
+        uint32_t h_cnt[4];
+        CU(cudaMemcpyAsync(h_cnt, counters, 16, cudaMemcpyDeviceToHost, d->stream));
+        CU(cudaStreamSynchronize(d->stream));
+        r->n_exc = h_cnt[2];
+        if (n) s->est_exc_per_row = (double)r->n_exc / (double)n;
+        if (!(h_cnt[1] & 4u)) break;
+        cap_exc = r->n_exc + 16;
+        if (attempt == 1) return fail(TPLX_E_OVERFLOW, "exception capacity retry failed");
+    }
+    r->agg_out = P.agg_out;
+    r->exc = P.exc;
+    r->n_out = 1;
+    // exception records of an aggregate stage are appended in arbitrary order: sort by input row and
+    // number them like TransformTask::_outputRowCounter would (no normal rows are written)
+    if (r->n_exc) {
+        std::vector<tplx_exception_rec> recs(r->n_exc);
+        CU(cudaMemcpy(recs.data(), r->exc, r->n_exc * sizeof(tplx_exception_rec), cudaMemcpyDeviceToHost));
+        std::sort(recs.begin(), recs.end(), [](const tplx_exception_rec &a, const tplx_exception_rec &b) { return a.row < b.row; });
+        for (size_t i = 0; i < recs.size(); ++i) recs[i].row_no = (int64_t)i;
+        CU(cudaMemcpy(r->exc, recs.data(), r->n_exc * sizeof(tplx_exception_rec), cudaMemcpyHostToDevice));
+    }
+    return TPLX_OK;
+}
+
+extern "C" int32_t tplx_gpu_result_info(tplx_result *r, tplx_result_info *info) {
+    if (!r || !info) return fail(TPLX_E_BADARG, "result_info: bad arguments");
+    CU(cudaSetDevice(r->dev->id));
+    CU(cudaEventSynchronize(r->ev1));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, r->evk0, r->evk1));
+    r->kernel_ms = ms;
+    CU(cudaEventElapsedTime(&ms, r->ev0, r->ev1));
+    r->total_ms = ms;
+    memset(info, 0, sizeof(*info));
+    info->n_in_rows = r->n_in;
+    info->n_out_rows = r->n_out;
+    info->n_exceptions = r->n_exc;
+    for (size_t c = 0; c < r->str_bytes.size() && c < TPLX_MAX_COLS; ++c) info->out_str_bytes[c] = r->str_bytes[c];
+    info->kernel_ms = r->kernel_ms;
+    info->total_ms = r->total_ms;
+    info->kernel_launches = r->launches;
+    return TPLX_OK;
+}
+
+extern "C" int32_t tplx_gpu_result_fetch_column(tplx_result *r, uint32_t col, void *data, uint32_t *offsets) {
+    if (!r || col >= r->out.size()) return fail(TPLX_E_BADARG, "result_fetch_column: bad arguments");
+    CU(cudaSetDevice(r->dev->id));
+    const OutCol &oc = r->out[col];
+    if (r->out_types[col] == TPLX_T_STR) {
+        if (offsets) CU(cudaMemcpyAsync(offsets, oc.offsets, (r->n_out + 1) * 4, cudaMemcpyDeviceToHost, r->dev->stream));
+        if (data && r->str_bytes[col]) CU(cudaMemcpyAsync(data, oc.bytes, r->str_bytes[col], cudaMemcpyDeviceToHost, r->dev->stream));
+    } else if (data && r->n_out) {
+        CU(cudaMemcpyAsync(data, oc.data, r->n_out * 8, cudaMemcpyDeviceToHost, r->dev->stream));
+    }
+    CU(cudaStreamSynchronize(r->dev->stream));
+    return TPLX_OK;
+}
+
+extern "C" int32_t tplx_gpu_result_device_column(tplx_result *r, uint32_t col, const void **data, const uint32_t **offsets) {
+    if (!r || col >= r->out.size()) return fail(TPLX_E_BADARG, "result_device_column: bad arguments");
+    const OutCol &oc = r->out[col];
+    if (r->out_types[col] == TPLX_T_STR) {
+        if (data) *data = oc.bytes;
+        if (offsets) *offsets = oc.offsets;
+    } else {
+        if (data) *data = oc.data;
+        if (offsets) *offsets = nullptr;
+    }
+    return TPLX_OK;
+}
+
+extern "C" int32_t tplx_gpu_result_fetch_exceptions(tplx_result *r, tplx_exception_rec *recs) {
+    if (!r || (!recs && r->n_exc)) return fail(TPLX_E_BADARG, "result_fetch_exceptions: bad arguments");
+    if (!r->n_exc) return TPLX_OK;
+    CU(cudaSetDevice(r->dev->id));
+    CU(cudaMemcpyAsync(recs, r->exc, r->n_exc * sizeof(tplx_exception_rec), cudaMemcpyDeviceToHost, r->dev->stream));
+    CU(cudaStreamSynchronize(r->dev->stream));
+    return TPLX_OK;
+}
+
+extern "C" int32_t tplx_gpu_result_fetch_aggregate(tplx_result *r, int64_t *acc_bits) {
+    if (!r || !acc_bits || !r->agg_out) return fail(TPLX_E_BADARG, "result_fetch_aggregate: not an aggregate result");
+    CU(cudaSetDevice(r->dev->id));
+    CU(cudaMemcpyAsync(acc_bits, r->agg_out, r->n_accs * 8, cudaMemcpyDeviceToHost, r->dev->stream));
+    CU(cudaStreamSynchronize(r->dev->stream));
+    return TPLX_OK;
+}
+
+#include "tplx_gpu_rowfmt.inl"
+#include "tplx_gpu_hash.inl"

@@ -1,0 +1,465 @@
+"""DataSet — mirror of the reference's python API for the hot path
+(tuplex/python/tuplex/dataset.py: map/filter/collect :49-123, withColumn/mapColumn/selectColumns :201-290,
+aggregate/aggregateByKey :593-705) executed by the GPU backend.
+
+Planning is the small plan->stage-descriptor lowering SURVEY.md §2 row 3 calls for: consecutive
+map/filter/withColumn/mapColumn/selectColumns/renameColumn operators fuse into one stage (the reference
+fuses the same operators into one TransformStage, tuplex/core/src/physical/PhysicalPlan.cc:60-420); an
+aggregate ends a stage. Execution = LocalBackend::executeTransformStage's job
+(tuplex/core/src/ee/local/LocalBackend.cc:815-1252): run the normal case, collect exception rows, resolve
+them on the CPython path, merge in order.
+"""
+from __future__ import annotations
+
+import struct
+from collections import Counter
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import backend, ir, pyexec
+from .backend import Column
+from .frontend import StageCompiler, UnsupportedUDF
+from .ir import C, T_BOOL, T_F64, T_I64, T_STR
+from .pyexec import Dropped, Op
+
+
+class Source:
+    """Input of a plan: normal-case column block + rows that did not fit the normal-case schema
+    (PythonContext::parallelize fallback rows, tuplex/python/src/PythonContext.cc:178-204)."""
+
+    def __init__(self, cols: List[Column], names: List[Optional[str]], n_rows: int, orig_index: Optional[np.ndarray],
+                 fallback: List[Tuple[int, Any]], total_rows: int):
+        self.cols = cols
+        self.names = names
+        self.n_rows = n_rows
+        self.orig_index = orig_index  # original list position of each normal row (None = identity)
+        self.fallback = fallback      # (original position, python object)
+        self.total_rows = total_rows
+
+
+class DataSet:
+    def __init__(self, ctx, source: Optional[Source], ops: Sequence[Op] = (), parent: Optional["DataSet"] = None):
+        self._ctx = ctx
+        self._source = source
+        self._ops: List[Op] = list(ops)
+        self._parent = parent  # upstream DataSet whose result is this one's source (after an aggregate)
+        self._last_exceptions: Counter = Counter()
+
+    # ---- lazy operators ---------------------------------------------------------------------------
+    def _with(self, op: Op) -> "DataSet":
+        return DataSet(self._ctx, self._source, self._ops + [op], self._parent)
+
+    def map(self, ftor):
+        return self._with(Op("map", ftor))
+
+    def filter(self, ftor):
+        return self._with(Op("filter", ftor))
+
+    def withColumn(self, column, ftor):
+        return self._with(Op("withColumn", ftor, column=column))
+
+    def mapColumn(self, column, ftor):
+        return self._with(Op("mapColumn", ftor, column=column))
+
+    def selectColumns(self, columns):
+        if not isinstance(columns, (list, tuple)):
+            columns = [columns]
+        return self._with(Op("selectColumns", columns=list(columns)))
+
+    def renameColumn(self, key, newColumnName):
+        return self._with(Op("renameColumn", column=key, extra=newColumnName))
+
+    def resolve(self, eclass, ftor):
+        if not self._ops:
+            raise ValueError("resolve() needs a preceding operator")
+        ds = DataSet(self._ctx, self._source, self._ops, self._parent)
+        ds._ops[-1].resolvers.append((eclass, ftor))
+        return ds
+
+    def ignore(self, eclass):
+        if not self._ops:
+            raise ValueError("ignore() needs a preceding operator")
+        ds = DataSet(self._ctx, self._source, self._ops, self._parent)
+        ds._ops[-1].ignores.append(eclass)
+        return ds
+
+    def aggregate(self, combine, aggregate, initial_value):
+        return self._with(Op("aggregate", udf=aggregate, extra=(combine, initial_value)))
+
+    def aggregateByKey(self, combine, aggregate, initial_value, key_columns):
+        if not isinstance(key_columns, (list, tuple)):
+            key_columns = [key_columns]
+        return self._with(Op("aggregateByKey", udf=aggregate, columns=list(key_columns), extra=(combine, initial_value)))
+
+    def unique(self):
+        return self._with(Op("unique"))
+
+    def cache(self, store_specialized=True):
+        rows, names = self._execute()
+        return self._ctx._dataset_from_rows(rows, names)
+
+    # ---- actions ------------------------------------------------------------------------------------
+    def collect(self):
+        rows, _ = self._execute()
+        return rows
+
+    def take(self, nrows=5):
+        rows, _ = self._execute()
+        return rows[:nrows] if nrows >= 0 else rows
+
+    def show(self, nrows=None):
+        rows, names = self._execute()
+        if any(names):
+            print(" | ".join(str(n) for n in names))
+        for r in rows[: (nrows if nrows is not None else len(rows))]:
+            print(r)
+
+    def tocsv(self, path, part_size=0, num_rows=None, num_parts=0, part_name_generator=None, null_value=None, header=True):
+        import os
+        rows, names = self._execute()
+        os.makedirs(path, exist_ok=True) if not path.endswith(".csv") else None
+        fn = path if path.endswith(".csv") else os.path.join(path, "part0.csv")
+        with open(fn, "w", newline="") as fp:
+            if header and any(names):
+                fp.write(",".join(str(n) for n in names) + "\n")
+            for r in rows:
+                vals = r if isinstance(r, tuple) else (r,)
+                fp.write(",".join(_csv_cell(v) for v in vals) + "\n")
+
+    @property
+    def columns(self):
+        _, names = self._plan_names()
+        return names
+
+    @property
+    def exception_counts(self):
+        return dict(self._last_exceptions)
+
+    # ---- planning + execution -------------------------------------------------------------------------
+    def _plan_names(self):
+        return None, self._execute(dry=True)[1]
+
+    def _execute(self, dry: bool = False):
+        """Split the operator chain into stages and run them. Returns (python rows, column names)."""
+        src = self._source
+        if self._parent is not None:
+            rows, names = self._parent._execute()
+            src = self._ctx._source_from_rows(rows, names)
+        stages: List[List[Op]] = [[]]
+        for op in self._ops:
+            stages[-1].append(op)
+            if op.kind in ("aggregate", "aggregateByKey", "unique"):
+                stages.append([])
+        if not stages[-1] and len(stages) > 1:
+            stages.pop()
+        rows = names = None
+        self._last_exceptions = Counter()
+        for si, ops in enumerate(stages):
+            if si > 0:
+                src = self._ctx._source_from_rows(rows, names)
+            rows, names = _run_stage(self._ctx, src, ops, self._last_exceptions)
+        return rows, names
+
+
+def _csv_cell(v) -> str:
+    if isinstance(v, str):
+        if any(ch in v for ch in ',"\n'):
+            return '"' + v.replace('"', '""') + '"'
+        return v
+    if isinstance(v, bool):
+        return "True" if v else "False"
+    return repr(v) if isinstance(v, float) else str(v)
+
+
+def _row_of(cols: List[Column], values_cache: List[list], i: int):
+    vals = tuple(values_cache[c][i] for c in range(len(cols)))
+    return vals if len(vals) != 1 else vals[0]
+
+
+def _run_stage(ctx, src: Source, ops: List[Op], exc_counter: Counter):
+    """One TransformStage on the GPU + CPython resolve of its exception rows."""
+    end = ops[-1] if ops and ops[-1].kind in ("aggregate", "aggregateByKey", "unique") else None
+    row_ops = ops[:-1] if end else ops
+    in_types = [c.type for c in src.cols]
+    prog = None
+    try:
+        sc = StageCompiler(in_types, src.names)
+        for op in row_ops:
+            if op.resolvers or op.ignores:
+                pass  # resolvers only act on the slow path
+            if op.kind == "map":
+                sc.add_map(op.udf, op.id)
+            elif op.kind == "filter":
+                sc.add_filter(op.udf, op.id)
+            elif op.kind == "withColumn":
+                sc.add_with_column(op.column, op.udf, op.id)
+            elif op.kind == "mapColumn":
+                sc.add_map_column(op.column, op.udf, op.id)
+            elif op.kind == "selectColumns":
+                sc.add_select(op.columns, op.id)
+            elif op.kind == "renameColumn":
+                sc.add_rename(op.column, op.extra, op.id)
+        out_names = list(sc.names)
+        need_rowidx = end is None and bool(src.fallback)
+        if end is None:
+            if need_rowidx:
+                sc.begin_op(row_ops[-1].id if row_ops else 0)
+                d = sc.new_vreg(T_I64)
+                sc.emit(C["TPLX_OP_LDROW"], d)
+                from .frontend import Val
+                sc.row.append(Val(T_I64, d))
+                sc.names.append("__rowidx")
+            prog = sc.finish_memory()
+        elif end.kind == "aggregate":
+            prog = sc.finish_aggregate(end.udf, end.extra[0], end.extra[1], end.id)
+        elif end.kind == "aggregateByKey":
+            prog = sc.finish_hash(end.columns, end.udf, end.extra[0], end.extra[1], end.id)
+        else:
+            prog = sc.finish_hash(list(range(len(sc.row))), None, None, None, end.id)
+    except UnsupportedUDF as e:
+        ctx._log(f"stage falls back to the CPython path: {e}")
+        return _run_stage_python(ctx, src, ops, exc_counter)
+
+    dev = ctx._device
+    backend.init([dev])
+    stage = backend.Stage(prog)
+    block_rows = ctx._block_rows
+    in_values: Optional[List[list]] = None  # python values of input columns, built lazily for resolve
+
+    def input_row(i: int):
+        nonlocal in_values
+        if in_values is None:
+            in_values = [c.to_values() for c in src.cols]
+        return _row_of(src.cols, in_values, i)
+
+    out_cols_all: List[List[Column]] = []
+    exc_all: List[np.ndarray] = []
+    agg_partials: List[List[int]] = []
+    first_row_no = 0
+    base = 0
+    n = src.n_rows
+    starts = list(range(0, n, block_rows)) or [0]
+    for lo in starts:
+        hi = min(n, lo + block_rows)
+        cols = [c.slice(lo, hi) for c in src.cols] if (lo, hi) != (0, n) else src.cols
+        res = stage.run_host(dev, cols, hi - lo, first_row_no)
+        info = res.info
+        ctx.metrics._add(info)
+        exc = res.exceptions()
+        if len(exc):
+            exc = exc.copy()
+            exc["row"] += lo
+            exc_all.append(exc)
+        if prog.endpoint == C["TPLX_EP_MEMORY"]:
+            oc = res.columns()
+            if need_rowidx:
+                oc[-1].data += lo
+            out_cols_all.append(oc)
+            first_row_no += int(info.n_out_rows) + int(info.n_exceptions)
+        elif prog.endpoint == C["TPLX_EP_AGGREGATE"]:
+            agg_partials.append(res.aggregate_bits())
+        res.free()
+    excs = np.concatenate(exc_all) if exc_all else np.zeros(0, dtype=backend.EXC_DTYPE)
+
+    # ---- endpoints --------------------------------------------------------------------------------
+    if prog.endpoint == C["TPLX_EP_MEMORY"]:
+        ncols = len(prog.out_cols)
+        merged_vals = [sum((oc[c].to_values() for oc in out_cols_all), []) for c in range(ncols)]
+        n_out = len(merged_vals[0]) if ncols else 0
+        user_cols = ncols - (1 if need_rowidx else 0)
+        normal_rows = [tuple(merged_vals[c][i] for c in range(user_cols)) if user_cols != 1 else merged_vals[0][i] for i in range(n_out)]
+        # resolve exception rows in CPython, merge by row number (ResolveTask::executeInOrder)
+        resolved: List[Tuple[int, int, Any]] = []  # (input row, row_no, value) for rows that produced output
+        for e in excs:
+            i = int(e["row"])
+            try:
+                val, _ = pyexec.run_row(row_ops, input_row(i), src.names)
+                resolved.append((i, int(e["row_no"]), val))
+            except Dropped:
+                pass
+            except Exception as ex:  # noqa: BLE001 — stays an exception, counted like the reference's exception_counts
+                exc_counter[(getattr(ex, "tplx_op", int(e["op_id"])), type(ex).__name__)] += 1
+        if not src.fallback:
+            rows = _merge_by_rowno(normal_rows, excs, resolved)
+        else:
+            # rows outside the normal-case schema run entirely on the CPython path; merge by original position
+            idx_normal = merged_vals[-1]
+            orig = src.orig_index
+            keyed = [(int(orig[j]) if orig is not None else int(j), r) for j, r in zip(idx_normal, normal_rows)]
+            keyed += [(int(orig[i]) if orig is not None else i, v) for i, _, v in resolved]
+            for pos, obj in src.fallback:
+                try:
+                    val, _ = pyexec.run_row(row_ops, obj, src.names)
+                    keyed.append((pos, val))
+                except Dropped:
+                    pass
+                except Exception as ex:  # noqa: BLE001
+                    exc_counter[(getattr(ex, "tplx_op", 0), type(ex).__name__)] += 1
+            keyed.sort(key=lambda t: t[0])
+            rows = [r for _, r in keyed]
+        stage.close()
+        return rows, out_names
+
+    if prog.endpoint == C["TPLX_EP_AGGREGATE"]:
+        combine, init = end.extra
+        inits = list(init) if isinstance(init, (tuple, list)) else [init]
+        # thread slot starts from the initial value; partials combined in block (partition) order
+        # (TransformTask.cc:218-230,278-299)
+        accs = list(inits)
+        for part in agg_partials:
+            vals = [_acc_value(a.kind, b) for a, b in zip(prog.accs, part)]
+            accs = [_acc_combine(a.kind, x, y) for a, x, y in zip(prog.accs, accs, vals)]
+        value = tuple(accs) if isinstance(init, (tuple, list)) else accs[0]
+        # exception rows + fallback rows: fold on the CPython path with the user's own aggregate UDF
+        for i in [int(e["row"]) for e in excs]:
+            value = _py_fold(row_ops, end, value, input_row(i), src.names, exc_counter)
+        for _, obj in src.fallback:
+            value = _py_fold(row_ops, end, value, obj, src.names, exc_counter)
+        stage.close()
+        return [value], [None] * (len(value) if isinstance(value, tuple) else 1)
+
+    # hash endpoint
+    res = stage.hash_finish(dev)
+    cols = res.columns()
+    res.free()
+    nk = prog.n_keys
+    vals = [c.to_values() for c in cols]
+    n_out = len(vals[0]) if vals else 0
+    table: Dict[Any, list] = {}
+    order: List[Any] = []
+    for i in range(n_out):
+        key = tuple(vals[c][i] for c in range(nk))
+        table[key] = [vals[nk + k][i] for k in range(len(prog.accs))]
+        order.append(key)
+    if end.kind == "aggregateByKey" and (len(excs) or src.fallback):
+        combine, init = end.extra
+        pending = [input_row(int(e["row"])) for e in excs] + [obj for _, obj in src.fallback]
+        for obj in pending:
+            try:
+                val, names2 = pyexec.run_row(row_ops, obj, src.names)
+            except Dropped:
+                continue
+            except Exception as ex:  # noqa: BLE001
+                exc_counter[(getattr(ex, "tplx_op", 0), type(ex).__name__)] += 1
+                continue
+            r = pyexec.Row(val if isinstance(val, tuple) else (val,), names2)
+            key = tuple(r[k] for k in end.columns)
+            cur = table.get(key)
+            cur_v = (tuple(cur) if isinstance(init, (tuple, list)) else cur[0]) if cur is not None else init
+            try:
+                nv = end.udf(cur_v, r if len(r) != 1 else r[0])
+            except Exception as ex:  # noqa: BLE001
+                exc_counter[(end.id, type(ex).__name__)] += 1
+                continue
+            if cur is None:
+                order.append(key)
+            table[key] = list(nv) if isinstance(nv, tuple) else [nv]
+    order.sort(key=lambda k: tuple((0, x) if not isinstance(x, str) else (1, x) for x in k))
+    rows = [tuple(list(k) + table[k]) if (len(k) + len(table[k])) != 1 else k[0] for k in order]
+    names = list(prog.out_names) + [None] * len(prog.accs)
+    stage.close()
+    return rows, names
+
+
+def _acc_value(kind: int, bits: int):
+    if kind in (C["TPLX_ACC_SUM_F64"], C["TPLX_ACC_MIN_F64"], C["TPLX_ACC_MAX_F64"]):
+        return ir.bits_f64(bits)
+    return bits - (1 << 64) if bits >= 1 << 63 else bits
+
+
+def _acc_combine(kind: int, a, b):
+    if kind in (C["TPLX_ACC_SUM_I64"],):
+        s = (int(a) + int(b)) & ((1 << 64) - 1)
+        return s - (1 << 64) if s >= 1 << 63 else s
+    if kind == C["TPLX_ACC_SUM_F64"]:
+        return float(a) + float(b)
+    if kind in (C["TPLX_ACC_MIN_I64"], C["TPLX_ACC_MIN_F64"]):
+        return min(a, b)
+    return max(a, b)
+
+
+def _py_fold(row_ops, end: Op, value, obj, names, exc_counter):
+    try:
+        val, _ = pyexec.run_row(row_ops, obj, names)
+        return end.udf(value, val)
+    except Dropped:
+        return value
+    except Exception as ex:  # noqa: BLE001
+        exc_counter[(getattr(ex, "tplx_op", end.id), type(ex).__name__)] += 1
+        return value
+
+
+def _merge_by_rowno(normal_rows: list, excs: np.ndarray, resolved: List[Tuple[int, int, Any]]) -> list:
+    """Exception k occupied slot row_no_k of the task's output stream (TransformTask.cc:885); a resolved row
+    goes back to exactly that slot, an unresolved one leaves it empty."""
+    if not len(excs):
+        return normal_rows
+    res_by_no = {no: v for _, no, v in resolved}
+    out = []
+    ni = 0
+    pos = 0
+    for no in sorted(int(x) for x in excs["row_no"]):
+        while pos < no and ni < len(normal_rows):
+            out.append(normal_rows[ni])
+            ni += 1
+            pos += 1
+        if no in res_by_no:
+            out.append(res_by_no[no])
+        pos += 1
+    out.extend(normal_rows[ni:])
+    return out
+
+
+def _run_stage_python(ctx, src: Source, ops: List[Op], exc_counter: Counter):
+    """Whole stage on the CPython path (UDF outside the GPU op set)."""
+    end = ops[-1] if ops and ops[-1].kind in ("aggregate", "aggregateByKey", "unique") else None
+    row_ops = ops[:-1] if end else ops
+    vals = [c.to_values() for c in src.cols]
+    items: List[Tuple[int, Any]] = []
+    for i in range(src.n_rows):
+        pos = int(src.orig_index[i]) if src.orig_index is not None else i
+        items.append((pos, _row_of(src.cols, vals, i)))
+    items += list(src.fallback)
+    items.sort(key=lambda t: t[0])
+    out = []
+    names = list(src.names)
+    for _, obj in items:
+        try:
+            v, names = pyexec.run_row(row_ops, obj, src.names)
+            out.append(v)
+        except Dropped:
+            pass
+        except Exception as ex:  # noqa: BLE001
+            exc_counter[(getattr(ex, "tplx_op", 0), type(ex).__name__)] += 1
+    if end is None:
+        return out, names
+    if end.kind == "aggregate":
+        combine, init = end.extra
+        agg = end.udf if not isinstance(end.udf, str) else eval(end.udf)
+        value = init
+        for v in out:
+            try:
+                value = agg(value, v)
+            except Exception as ex:  # noqa: BLE001
+                exc_counter[(end.id, type(ex).__name__)] += 1
+        comb = combine if not isinstance(combine, str) else eval(combine)
+        value = comb(init, value)  # thread slot (initial value) combined with the task partial
+        return [value], [None]
+    if end.kind == "unique":
+        seen = dict.fromkeys(out)
+        return list(seen), names
+    combine, init = end.extra
+    agg = end.udf if not isinstance(end.udf, str) else eval(end.udf)
+    comb = combine if not isinstance(combine, str) else eval(combine)
+    table: Dict[Any, Any] = {}
+    for v in out:
+        r = pyexec.Row(v if isinstance(v, tuple) else (v,), names)
+        key = tuple(r[k] for k in end.columns)
+        table[key] = agg(table.get(key, init), r if len(r) != 1 else r[0])
+    rows = []
+    for key in sorted(table, key=lambda k: tuple((0, x) if not isinstance(x, str) else (1, x) for x in k)):
+        v = comb(init, table[key])  # combine at least once per group (LocalBackend.cc:2148-2217)
+        rows.append(tuple(list(key) + (list(v) if isinstance(v, tuple) else [v])))
+    knames = [k if isinstance(k, str) else names[k] for k in end.columns]
+    return rows, knames + [None] * (len(rows[0]) - len(knames) if rows else 1)

@@ -1,0 +1,1067 @@
+"""UDF front end: Python lambdas/defs -> tplx op program (include/tplx_ir.h).
+
+Stands where the reference's codegen stands (tuplex/codegen: ASTBuilderVisitor, TypeAnnotatorVisitor,
+BlockGeneratorVisitor, FunctionRegistry; driven by StageBuilder::generateFastCodePath,
+tuplex/core/src/physical/StageBuilder.cc:602-1143) but emits a flat predicated register program
+instead of LLVM IR. Typing is static from the normal-case input schema, like the reference's
+TypeAnnotatorVisitor. Anything outside the supported op set raises UnsupportedUDF; the caller then
+routes the operator's rows to the CPython path (the reference does the same when a UDF cannot be
+compiled: it falls back to the interpreter, tuplex/python/tuplex/dataset.py:49-80).
+
+Python control flow is if-converted: every instruction carries a guard, `if/elif/else` and early
+`return` become guards + SEL, so instructions of untaken branches can never raise
+(reference semantics: an exception is only raised on the executed path, PipelineBuilder.cc:949).
+"""
+from __future__ import annotations
+
+import ast
+import inspect
+import linecache
+import re
+import types
+from dataclasses import dataclass
+from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
+
+from . import ir
+from .ir import C, Instr, NOSLOT, Program, T_BOOL, T_F64, T_I64, T_STR
+
+
+class UnsupportedUDF(Exception):
+    """The UDF uses something outside the GPU op set -> CPython path."""
+
+
+# ------------------------------------------------------------------------------------------------
+# locating the AST of a function object
+# ------------------------------------------------------------------------------------------------
+_file_ast_cache: Dict[str, Tuple[int, ast.AST]] = {}
+
+
+def _file_ast(filename: str) -> Optional[ast.AST]:
+    lines = linecache.getlines(filename)
+    if not lines:
+        return None
+    key = hash(tuple(lines))
+    hit = _file_ast_cache.get(filename)
+    if hit and hit[0] == key:
+        return hit[1]
+    try:
+        tree = ast.parse("".join(lines), filename)
+    except SyntaxError:
+        return None
+    _file_ast_cache[filename] = (key, tree)
+    return tree
+
+
+def _code_signature(code: types.CodeType):
+    consts = tuple(c for c in code.co_consts if not isinstance(c, types.CodeType))
+    return (code.co_code, consts, code.co_names, code.co_varnames[: code.co_argcount])
+
+
+def get_udf_ast(func) -> Tuple[List[str], Union[ast.expr, List[ast.stmt]], Dict[str, Any]]:
+    """Return (argument names, body, resolvable globals/closure) for a lambda or def."""
+    if isinstance(func, str):  # source string, like the reference's UDF("lambda x: ...") in C++ tests
+        node = ast.parse(func.strip(), mode="eval").body
+        if not isinstance(node, ast.Lambda):
+            raise UnsupportedUDF("UDF string must be a lambda")
+        return [a.arg for a in node.args.args], node.body, {}
+    if not isinstance(func, types.FunctionType):
+        raise UnsupportedUDF(f"not a plain Python function: {func!r}")
+    code = func.__code__
+    env: Dict[str, Any] = dict(func.__globals__)
+    if func.__closure__:
+        for name, cell in zip(code.co_freevars, func.__closure__):
+            try:
+                env[name] = cell.cell_contents
+            except ValueError:
+                pass
+    tree = _file_ast(code.co_filename)
+    if tree is None:
+        raise UnsupportedUDF("source of UDF not available")
+    if code.co_name == "<lambda>":
+        cands = [n for n in ast.walk(tree) if isinstance(n, ast.Lambda) and n.lineno <= code.co_firstlineno <= (n.end_lineno or n.lineno)]
+        cands = [n for n in cands if n.lineno == code.co_firstlineno] or cands
+        if len(cands) > 1:
+            sig = _code_signature(code)
+            matched = []
+            for n in cands:
+                try:
+                    mod = compile(ast.Expression(body=n), code.co_filename, "eval")
+                    inner = [c for c in mod.co_consts if isinstance(c, types.CodeType)]
+                    if inner and _code_signature(inner[0]) == sig:
+                        matched.append(n)
+                except Exception:
+                    continue
+            if matched:
+                cands = matched[:1]
+        if len(cands) != 1:
+            raise UnsupportedUDF("cannot locate lambda source unambiguously")
+        node = cands[0]
+        _check_args(node.args)
+        return [a.arg for a in node.args.args], node.body, env
+    for n in ast.walk(tree):
+        if isinstance(n, ast.FunctionDef) and n.name == code.co_name and n.lineno <= code.co_firstlineno + len(n.decorator_list) + 1 \
+                and (n.end_lineno or n.lineno) >= code.co_firstlineno:
+            _check_args(n.args)
+            return [a.arg for a in n.args.args], n.body, env
+    raise UnsupportedUDF("cannot locate function source")
+
+
+def _check_args(a: ast.arguments):
+    if a.vararg or a.kwarg or a.kwonlyargs or a.defaults or a.posonlyargs:
+        raise UnsupportedUDF("only plain positional parameters are supported")
+
+
+# ------------------------------------------------------------------------------------------------
+# compile-time values
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class Val:
+    """A typed scalar/string value: either a compile-time constant or a virtual register."""
+    type: int
+    vreg: Optional[int] = None
+    const: Any = None
+
+    @property
+    def is_const(self):
+        return self.vreg is None
+
+
+@dataclass
+class TupleVal:
+    elems: List[Any]  # Val | TupleVal
+    names: Optional[List[Optional[str]]] = None
+
+
+def _py_type_of(v) -> int:
+    if isinstance(v, bool):
+        return T_BOOL
+    if isinstance(v, int):
+        return T_I64
+    if isinstance(v, float):
+        return T_F64
+    if isinstance(v, str):
+        return T_STR
+    raise UnsupportedUDF(f"unsupported constant {v!r}")
+
+
+def const_val(v) -> Val:
+    return Val(_py_type_of(v), None, v)
+
+
+# ------------------------------------------------------------------------------------------------
+# the stage compiler
+# ------------------------------------------------------------------------------------------------
+class StageCompiler:
+    """Accumulates the operators of one stage and emits a Program.
+
+    Mirrors PipelineBuilder's per-operator API (tuplex/core/src/physical/PipelineBuilder.cc:
+    mapOperation :565, filterOperation :615, mapColumnOperation :706, withColumnOperation :808,
+    addAggregate :2525, buildWithHashmapWriter :1108).
+    """
+
+    def __init__(self, in_types: Sequence[int], in_names: Sequence[Optional[str]]):
+        self.prog = Program(list(in_types), list(in_names))
+        self.vreg_width: List[int] = []
+        self.row: List[Val] = []
+        self.names: List[Optional[str]] = list(in_names)
+        self._col_cache: Dict[int, Val] = {}
+        self.cur_op = 0
+        self.guard: Optional[int] = None  # vreg of current guard
+        self.filters: List[int] = []      # pcs of FILTER instructions
+        for c, t in enumerate(in_types):
+            self.row.append(Val(t, None, ("col", c)))  # lazily loaded column reference
+
+    # ---- emission helpers ----------------------------------------------------------------------
+    def new_vreg(self, t: int) -> int:
+        self.vreg_width.append(2 if t == T_STR else 1)
+        return len(self.vreg_width) - 1
+
+    def emit(self, op, dst=None, a=None, b=None, c=None, flags=0, imm=0, imm2=0) -> None:
+        def r(x):
+            return NOSLOT if x is None else x
+        self.prog.instrs.append(Instr(op, r(dst), r(a), r(b), r(c), r(self.guard), self.cur_op, flags, imm, imm2))
+
+    def reg(self, v: Val) -> int:
+        """Materialise a value into a vreg (loads constants / columns on demand)."""
+        if v.vreg is not None:
+            return v.vreg
+        if isinstance(v.const, tuple) and v.const and v.const[0] == "col":
+            col = v.const[1]
+            hit = self._col_cache.get(col)
+            if hit is not None:
+                v.vreg = hit.vreg
+                return v.vreg
+            # column loads are hoisted out of any guard: they cannot raise and must dominate all uses
+            g, self.guard = self.guard, None
+            d = self.new_vreg(v.type)
+            self.emit(C["TPLX_OP_LDCOL"], d, flags=v.type, imm=col)
+            self.guard = g
+            v.vreg = d
+            self._col_cache[col] = v
+            return d
+        d = self.new_vreg(v.type)
+        g, self.guard = self.guard, None  # constants are unconditional
+        if v.type == T_STR:
+            off, ln = self.prog.const_bytes(v.const.encode("utf-8"))
+            self.emit(C["TPLX_OP_LDS"], d, imm=off, imm2=ln)
+        elif v.type == T_F64:
+            self.emit(C["TPLX_OP_LDI"], d, imm=ir.f64_bits(float(v.const)))
+        else:
+            self.emit(C["TPLX_OP_LDI"], d, imm=int(v.const) & ((1 << 64) - 1))
+        self.guard = g
+        return d
+
+    def _is_colref(self, v: Val) -> bool:
+        return v.vreg is None and isinstance(v.const, tuple) and bool(v.const) and v.const[0] == "col"
+
+    def is_const(self, v) -> bool:
+        return isinstance(v, Val) and v.vreg is None and not self._is_colref(v)
+
+    def op2(self, op, t, a: Val, b: Val, flags=0) -> Val:
+        d = self.new_vreg(t)
+        self.emit(op, d, self.reg(a), self.reg(b), flags=flags)
+        return Val(t, d)
+
+    def op1(self, op, t, a: Val, flags=0, imm=0) -> Val:
+        d = self.new_vreg(t)
+        self.emit(op, d, self.reg(a), flags=flags, imm=imm)
+        return Val(t, d)
+
+    # ---- type coercions (BlockGeneratorVisitor upCast) -----------------------------------------
+    def to_f64(self, v: Val) -> Val:
+        if v.type == T_F64:
+            return v
+        if v.type in (T_I64, T_BOOL):
+            if self.is_const(v):
+                return const_val(float(int(v.const)))
+            return self.op1(C["TPLX_OP_I2F"], T_F64, v)
+        raise UnsupportedUDF("cannot convert str to float implicitly")
+
+    def to_i64(self, v: Val) -> Val:
+        if v.type == T_I64:
+            return v
+        if v.type == T_BOOL:
+            if self.is_const(v):
+                return const_val(int(v.const))
+            return Val(T_I64, self.reg(v))  # bool is stored as 0/1
+        raise UnsupportedUDF("expected integer")
+
+    def truth(self, v) -> Val:
+        """Python truth value test (LLVMEnvironment::truthValueTest; filter: PipelineBuilder.cc:671-686)."""
+        if isinstance(v, TupleVal):
+            return const_val(len(v.elems) > 0)
+        if self.is_const(v):
+            return const_val(bool(v.const))
+        if v.type == T_BOOL:
+            return v
+        if v.type == T_I64:
+            return self.op2(C["TPLX_OP_ICMP"], T_BOOL, v, const_val(0), flags=C["TPLX_CMP_NE"])
+        if v.type == T_F64:
+            return self.op2(C["TPLX_OP_FCMP"], T_BOOL, v, const_val(0.0), flags=C["TPLX_CMP_NE"])
+        return self.op1(C["TPLX_OP_STRUTH"], T_BOOL, v)
+
+    def b_and(self, a: Optional[Val], b: Val) -> Val:
+        if a is None:
+            return b
+        if self.is_const(a):
+            return b if a.const else const_val(False)
+        if self.is_const(b):
+            return a if b.const else const_val(False)
+        return self.op2(C["TPLX_OP_BAND"], T_BOOL, a, b)
+
+    def b_or(self, a: Val, b: Val) -> Val:
+        if self.is_const(a):
+            return const_val(True) if a.const else b
+        if self.is_const(b):
+            return const_val(True) if b.const else a
+        return self.op2(C["TPLX_OP_BOR"], T_BOOL, a, b)
+
+    def b_not(self, a: Val) -> Val:
+        if self.is_const(a):
+            return const_val(not a.const)
+        return self.op1(C["TPLX_OP_BNOT"], T_BOOL, a)
+
+    def select(self, cond: Val, a, b):
+        """cond ? a : b over scalars and tuples."""
+        if isinstance(a, TupleVal) or isinstance(b, TupleVal):
+            if not (isinstance(a, TupleVal) and isinstance(b, TupleVal) and len(a.elems) == len(b.elems)):
+                raise UnsupportedUDF("branches return different shapes")
+            return TupleVal([self.select(cond, x, y) for x, y in zip(a.elems, b.elems)], a.names or b.names)
+        if self.is_const(cond):
+            return a if cond.const else b
+        a, b = self.unify(a, b)
+        d = self.new_vreg(a.type)
+        # SEL itself must run wherever either side may be needed later: emit under the current guard
+        self.emit(C["TPLX_OP_SEL"], d, self.reg(a), self.reg(b), self.reg(cond), flags=2 if a.type == T_STR else 1)
+        return Val(a.type, d)
+
+    def unify(self, a: Val, b: Val) -> Tuple[Val, Val]:
+        if a.type == b.type:
+            return a, b
+        nums = (T_I64, T_BOOL)
+        if a.type in nums and b.type in nums:
+            return self.to_i64(a), self.to_i64(b)
+        raise UnsupportedUDF("branches produce different types (normal case must be uniformly typed)")
+
+    # ---- pipeline operators ----------------------------------------------------------------------
+    def begin_op(self, op_id: int):
+        self.prog.opids.append(int(op_id))
+        self.cur_op = len(self.prog.opids) - 1
+        self.guard = None
+
+    def row_value(self):
+        if len(self.row) == 1:
+            return self.row[0]
+        return TupleVal(list(self.row), list(self.names))
+
+    def _call_udf(self, func, args_vals: List[Any]):
+        argnames, body, env = get_udf_ast(func)
+        if len(argnames) != len(args_vals):
+            # Tuplex unpacks a tuple row over multiple lambda parameters
+            if len(args_vals) == 1 and isinstance(args_vals[0], TupleVal) and len(args_vals[0].elems) == len(argnames):
+                args_vals = list(args_vals[0].elems)
+            else:
+                raise UnsupportedUDF("UDF arity does not match row")
+        fc = _FuncCompiler(self, env)
+        return fc.run(argnames, args_vals, body)
+
+    def add_map(self, func, op_id: int):
+        self.begin_op(op_id)
+        res = self._call_udf(func, [self.row_value()])
+        if isinstance(res, TupleVal):
+            flat, names = [], []
+            for i, e in enumerate(res.elems):
+                if isinstance(e, TupleVal):
+                    raise UnsupportedUDF("nested tuples in map output")
+                flat.append(e)
+                names.append(res.names[i] if res.names else None)
+            self.row, self.names = flat, names
+        else:
+            self.row, self.names = [res], [None]
+
+    def add_filter(self, func, op_id: int):
+        self.begin_op(op_id)
+        res = self.truth(self._call_udf(func, [self.row_value()]))
+        self.guard = None
+        self.emit(C["TPLX_OP_FILTER"], a=self.reg(res))
+        self.filters.append(len(self.prog.instrs))
+
+    def col_index(self, key) -> int:
+        if isinstance(key, int):
+            if not -len(self.row) <= key < len(self.row):
+                raise UnsupportedUDF("column index out of range")
+            return key % len(self.row)
+        if key not in self.names:
+            raise UnsupportedUDF(f"unknown column {key!r}")
+        return self.names.index(key)
+
+    def add_with_column(self, name: str, func, op_id: int):
+        self.begin_op(op_id)
+        res = self._call_udf(func, [self.row_value()])
+        if isinstance(res, TupleVal):
+            raise UnsupportedUDF("withColumn UDF must return a scalar")
+        if name in self.names:
+            self.row[self.names.index(name)] = res
+        else:
+            self.row.append(res)
+            self.names.append(name)
+
+    def add_map_column(self, name, func, op_id: int):
+        self.begin_op(op_id)
+        i = self.col_index(name)
+        res = self._call_udf(func, [self.row[i]])
+        if isinstance(res, TupleVal):
+            raise UnsupportedUDF("mapColumn UDF must return a scalar")
+        self.row[i] = res
+
+    def add_select(self, cols: Sequence[Union[int, str]], op_id: int):
+        self.begin_op(op_id)
+        idx = [self.col_index(c) for c in cols]
+        self.row = [self.row[i] for i in idx]
+        self.names = [self.names[i] for i in idx]
+
+    def add_rename(self, old, new: str, op_id: int):
+        self.begin_op(op_id)
+        self.names[self.col_index(old)] = new
+
+    # ---- endpoints ---------------------------------------------------------------------------------
+    def _finish(self, used_vals: List[Val]) -> List[int]:
+        self.guard = None
+        regs = [self.reg(v) for v in used_vals]
+        slots = self._regalloc(regs)
+        return slots
+
+    def finish_memory(self, selective_hint: Optional[float] = None) -> Program:
+        self.prog.endpoint = C["TPLX_EP_MEMORY"]
+        slots = self._finish(self.row)
+        self.prog.out_cols = [(s, v.type) for s, v in zip(slots, self.row)]
+        self.prog.out_names = list(self.names)
+        self._choose_split()
+        return self.prog
+
+    def _choose_split(self):
+        """Split after the last filter when later work is heavy: rows are evaluated up to the split,
+        survivors are compacted inside the tile, and only they run the rest densely."""
+        if not self.filters:
+            return
+        pc = self.filters[-1]
+        heavy = {C[k] for k in ("TPLX_OP_SREPLACE", "TPLX_OP_SCONCAT", "TPLX_OP_SFMTD", "TPLX_OP_SFIND", "TPLX_OP_SRFIND",
+                                "TPLX_OP_S2I", "TPLX_OP_SIN", "TPLX_OP_I2S")}
+        # candidate split points: after each filter; pick the last one that still has heavy work behind it
+        best = 0
+        for f in self.filters:
+            rest = self.prog.instrs[f:]
+            if sum(1 for i in rest if i.op in heavy) >= 2 or len(rest) >= 24:
+                best = f
+        if best and best < len(self.prog.instrs):
+            self.prog.split_pc = best
+
+    def finish_aggregate(self, agg_func, combine_func, init, op_id: int) -> Program:
+        """aggregate(combine, agg, init) -> AGG_GENERAL endpoint (AggregateFunctions.cc:16-243)."""
+        self.begin_op(op_id)
+        accs = self._lower_aggregate(agg_func, combine_func, init)
+        self.prog.endpoint = C["TPLX_EP_AGGREGATE"]
+        slots = self._finish([v for _, v, _ in accs])
+        self.prog.accs = [ir.Acc(kind, s, bits) for (kind, _, bits), s in zip(accs, slots)]
+        self.prog.out_cols = []
+        return self.prog
+
+    def finish_hash(self, key_cols: Sequence[Union[int, str]], agg_func, combine_func, init, op_id: int) -> Program:
+        """aggregateByKey / unique (PipelineBuilder.cc:1108-1400)."""
+        self.begin_op(op_id)
+        kidx = [self.col_index(k) for k in key_cols]
+        for i in kidx:
+            if self.row[i].type not in (T_I64, T_STR, T_BOOL):
+                raise UnsupportedUDF("f64 keys are not supported (reference: PipelineBuilder.cc:1175-1177)")
+        accs = self._lower_aggregate(agg_func, combine_func, init) if agg_func is not None else []
+        self.prog.endpoint = C["TPLX_EP_HASH"]
+        keys = [self.row[i] for i in kidx]
+        slots = self._finish(keys + [v for _, v, _ in accs])
+        self.prog.n_keys = len(keys)
+        self.prog.out_cols = [(s, v.type) for s, v in zip(slots[: len(keys)], keys)]
+        self.prog.out_names = [self.names[i] for i in kidx]
+        self.prog.accs = [ir.Acc(kind, s, bits) for (kind, _, bits), s in zip(accs, slots[len(keys):])]
+        return self.prog
+
+    def _lower_aggregate(self, agg_func, combine_func, init):
+        """Recognise component-wise `a (+) g(x)` aggregators with a matching associative combiner."""
+        inits = list(init) if isinstance(init, (tuple, list)) else [init]
+        n = len(inits)
+        an, abody, aenv = get_udf_ast(agg_func)
+        cn, cbody, _ = get_udf_ast(combine_func)
+        if len(an) != 2 or len(cn) != 2:
+            raise UnsupportedUDF("aggregate UDFs take (aggregate, row) and (a, b)")
+        abody = _single_return(abody)
+        cbody = _single_return(cbody)
+        aparts = abody.elts if isinstance(abody, ast.Tuple) else [abody]
+        cparts = cbody.elts if isinstance(cbody, ast.Tuple) else [cbody]
+        if len(aparts) != n or len(cparts) != n:
+            raise UnsupportedUDF("aggregate shape does not match initial value")
+
+        def is_acc_ref(node, name, i):
+            if n == 1 and isinstance(node, ast.Name) and node.id == name:
+                return True
+            return (isinstance(node, ast.Subscript) and isinstance(node.value, ast.Name) and node.value.id == name
+                    and isinstance(node.slice, ast.Constant) and node.slice.value == i)
+
+        out = []
+        fc = _FuncCompiler(self, aenv)
+        fc.env[an[1]] = self.row_value()
+        for i, (ap, cp, iv) in enumerate(zip(aparts, cparts, inits)):
+            kind = None
+            g_node = None
+            if isinstance(ap, ast.BinOp) and isinstance(ap.op, ast.Add):
+                if is_acc_ref(ap.left, an[0], i):
+                    g_node, kind = ap.right, "sum"
+                elif is_acc_ref(ap.right, an[0], i):
+                    g_node, kind = ap.left, "sum"
+            elif isinstance(ap, ast.Call) and isinstance(ap.func, ast.Name) and ap.func.id in ("min", "max") and len(ap.args) == 2:
+                if is_acc_ref(ap.args[0], an[0], i):
+                    g_node, kind = ap.args[1], ap.func.id
+                elif is_acc_ref(ap.args[1], an[0], i):
+                    g_node, kind = ap.args[0], ap.func.id
+            if kind is None or _mentions(g_node, an[0]):
+                raise UnsupportedUDF("aggregate component is not of the form a (+) g(x)")
+            # combiner must be the same associative operation on component i
+            ok = False
+            if kind == "sum" and isinstance(cp, ast.BinOp) and isinstance(cp.op, ast.Add):
+                ok = (is_acc_ref(cp.left, cn[0], i) and is_acc_ref(cp.right, cn[1], i)) or \
+                     (is_acc_ref(cp.left, cn[1], i) and is_acc_ref(cp.right, cn[0], i))
+            elif kind in ("min", "max") and isinstance(cp, ast.Call) and isinstance(cp.func, ast.Name) and cp.func.id == kind and len(cp.args) == 2:
+                ok = {0, 1} == {j for j in (0, 1) for a_ in cp.args if is_acc_ref(a_, cn[j], i)}
+            if not ok:
+                raise UnsupportedUDF("combine UDF does not match the aggregate operation")
+            g = fc.expr(g_node)
+            if isinstance(g, TupleVal) or g.type == T_STR:
+                raise UnsupportedUDF("aggregate term must be numeric")
+            if isinstance(iv, bool) or not isinstance(iv, (int, float)):
+                raise UnsupportedUDF("initial aggregate value must be int or float")
+            is_f = g.type == T_F64 or isinstance(iv, float)
+            if is_f:
+                g = self.to_f64(g)
+                bits = ir.f64_bits(float(iv))
+                k = {"sum": "TPLX_ACC_SUM_F64", "min": "TPLX_ACC_MIN_F64", "max": "TPLX_ACC_MAX_F64"}[kind]
+            else:
+                g = self.to_i64(g)
+                bits = int(iv) & ((1 << 64) - 1)
+                k = {"sum": "TPLX_ACC_SUM_I64", "min": "TPLX_ACC_MIN_I64", "max": "TPLX_ACC_MAX_I64"}[kind]
+            out.append((C[k], g, bits))
+        return out
+
+    # ---- register allocation -----------------------------------------------------------------------
+    def _regalloc(self, live_out: List[int]) -> List[int]:
+        """Linear-scan assignment of vregs to 8-byte slots (strings take two consecutive slots).
+        The program is straight-line (predicated), so a vreg's live range is [first def, last use]."""
+        ins = self.prog.instrs
+        n = len(self.vreg_width)
+        first = [None] * n
+        last = [-1] * n
+        for pc, i in enumerate(ins):
+            for r in (i.a, i.b, i.c, i.guard):
+                if r != NOSLOT:
+                    last[r] = max(last[r], pc)
+                    if first[r] is None:
+                        first[r] = pc  # used before def can only be a guarded phi input; treat as live from here
+            if i.dst != NOSLOT:
+                if first[i.dst] is None:
+                    first[i.dst] = pc
+                last[i.dst] = max(last[i.dst], pc)
+        for r in live_out:
+            last[r] = len(ins)
+        # a vreg that is redefined under guards (phi via repeated MOV) stays live across all its defs: covered by min/max
+        order = sorted((r for r in range(n) if first[r] is not None), key=lambda r: first[r])
+        free1: List[int] = []
+        free2: List[int] = []
+        active: List[Tuple[int, int]] = []  # (end, vreg)
+        assign: Dict[int, int] = {}
+        top = 0
+        for r in order:
+            start = first[r]
+            still = []
+            for end, v in active:
+                if end < start:
+                    (free2 if self.vreg_width[v] == 2 else free1).append(assign[v])
+                else:
+                    still.append((end, v))
+            active = still
+            w = self.vreg_width[r]
+            if w == 2:
+                if free2:
+                    s = free2.pop()
+                else:
+                    s = top
+                    top += 2
+            else:
+                if free1:
+                    s = free1.pop()
+                elif free2:
+                    s = free2.pop()
+                    free1.append(s + 1)
+                else:
+                    s = top
+                    top += 1
+            assign[r] = s
+            active.append((last[r], r))
+        for i in ins:
+            for f in ("dst", "a", "b", "c", "guard"):
+                v = getattr(i, f)
+                if v != NOSLOT:
+                    setattr(i, f, assign[v])
+        self.prog.n_slots = max(top, 1)
+        if self.prog.n_slots >= NOSLOT:
+            raise UnsupportedUDF("program too large")
+        return [assign[r] for r in live_out]
+
+
+def _single_return(body):
+    if isinstance(body, list):
+        stmts = [s for s in body if not (isinstance(s, ast.Expr) and isinstance(s.value, ast.Constant))]
+        if len(stmts) == 1 and isinstance(stmts[0], ast.Return) and stmts[0].value is not None:
+            return stmts[0].value
+        raise UnsupportedUDF("aggregate UDF must be a single expression")
+    return body
+
+
+def _mentions(node, name) -> bool:
+    return any(isinstance(n, ast.Name) and n.id == name for n in ast.walk(node))
+
+
+# ------------------------------------------------------------------------------------------------
+# per-function lowering
+# ------------------------------------------------------------------------------------------------
+_CMP = {ast.Eq: "EQ", ast.NotEq: "NE", ast.Lt: "LT", ast.LtE: "LE", ast.Gt: "GT", ast.GtE: "GE"}
+_FMT_RE = re.compile(r"%(?:(?P<flags>[0 \-+#]*)(?P<width>\d*)(?:\.(?P<prec>\d+))?(?P<conv>[dsif%]))")
+
+
+class _FuncCompiler:
+    def __init__(self, sc: StageCompiler, genv: Dict[str, Any]):
+        self.sc = sc
+        self.genv = genv
+        self.env: Dict[str, Any] = {}
+        self.ret_val = None
+        self.ret_done: Val = const_val(False)  # "row has already returned"
+        self.path: Optional[Val] = None         # conjunction of enclosing if-conditions
+
+    # guard management -------------------------------------------------------------------------------
+    def _set_guard(self):
+        g = self.path
+        if not (self.sc.is_const(self.ret_done) and not self.ret_done.const):
+            g = self.sc.b_and(g, self.sc.b_not(self.ret_done)) if g is not None else self.sc.b_not(self.ret_done)
+        if g is None:
+            self.sc.guard = None
+        elif self.sc.is_const(g):
+            self.sc.guard = None if g.const else self.sc.reg(g)
+        else:
+            self.sc.guard = self.sc.reg(g)
+
+    def _with_unguarded(self, fn):
+        g = self.sc.guard
+        self.sc.guard = None
+        try:
+            return fn()
+        finally:
+            self.sc.guard = g
+
+    def run(self, argnames, args_vals, body):
+        outer_guard = self.sc.guard
+        for n, v in zip(argnames, args_vals):
+            self.env[n] = v
+        if isinstance(body, list):
+            self.block(body)
+            if self.ret_val is None:
+                raise UnsupportedUDF("function does not return a value")
+            res = self.ret_val
+        else:
+            self._set_guard()
+            res = self.expr(body)
+        self.sc.guard = outer_guard
+        return res
+
+    # statements -------------------------------------------------------------------------------------
+    def block(self, stmts):
+        for s in stmts:
+            self._set_guard()
+            self.stmt(s)
+
+    def stmt(self, s):
+        sc = self.sc
+        if isinstance(s, ast.Return):
+            if s.value is None:
+                raise UnsupportedUDF("return without value")
+            v = self.expr(s.value)
+            here = self.path if self.path is not None else const_val(True)
+            active = self._with_unguarded(lambda: sc.b_and(here, sc.b_not(self.ret_done)))
+            if self.ret_val is None:
+                self.ret_val = v
+            else:
+                self.ret_val = self._with_unguarded(lambda: sc.select(active, v, self.ret_val))
+            self.ret_done = self._with_unguarded(lambda: sc.b_or(self.ret_done, here))
+            return
+        if isinstance(s, ast.Assign):
+            if len(s.targets) != 1:
+                raise UnsupportedUDF("chained assignment")
+            v = self.expr(s.value)
+            self._assign(s.targets[0], v)
+            return
+        if isinstance(s, ast.AugAssign):
+            if not isinstance(s.target, ast.Name):
+                raise UnsupportedUDF("augmented assignment target")
+            cur = self.expr(ast.Name(id=s.target.id, ctx=ast.Load()))
+            v = self.binop(s.op, cur, self.expr(s.value))
+            self._assign(s.target, v)
+            return
+        if isinstance(s, ast.If):
+            cond = sc.truth(self.expr(s.test))
+            outer_path, outer_env = self.path, dict(self.env)
+            # then-branch
+            self.path = self._with_unguarded(lambda: sc.b_and(outer_path, cond) if outer_path is not None else cond)
+            self.block(s.body)
+            env_then = self.env
+            # else-branch
+            self.env = dict(outer_env)
+            ncond = self._with_unguarded(lambda: sc.b_not(cond))
+            self.path = self._with_unguarded(lambda: sc.b_and(outer_path, ncond) if outer_path is not None else ncond)
+            self.block(s.orelse)
+            env_else = self.env
+            self.path = outer_path
+            # merge variables
+            merged = dict(outer_env)
+            for name in set(env_then) | set(env_else):
+                a, b = env_then.get(name), env_else.get(name)
+                if a is b:
+                    merged[name] = a
+                elif a is None:
+                    merged[name] = b
+                elif b is None:
+                    merged[name] = a
+                else:
+                    merged[name] = self._with_unguarded(lambda a=a, b=b: sc.select(cond, a, b))
+            self.env = merged
+            return
+        if isinstance(s, ast.Expr):
+            if isinstance(s.value, ast.Constant):
+                return  # docstring
+            self.expr(s.value)
+            return
+        if isinstance(s, ast.Pass):
+            return
+        raise UnsupportedUDF(f"statement {type(s).__name__} not supported")
+
+    def _assign(self, target, v):
+        if isinstance(target, ast.Name):
+            self.env[target.id] = v
+            return
+        if isinstance(target, ast.Tuple) and isinstance(v, TupleVal) and len(target.elts) == len(v.elems):
+            for t, e in zip(target.elts, v.elems):
+                self._assign(t, e)
+            return
+        raise UnsupportedUDF("assignment target not supported")
+
+    # expressions ------------------------------------------------------------------------------------
+    def expr(self, e):
+        sc = self.sc
+        if isinstance(e, ast.Constant):
+            if e.value is None:
+                raise UnsupportedUDF("None in normal-case code")
+            return const_val(e.value)
+        if isinstance(e, ast.Name):
+            if e.id in self.env:
+                return self.env[e.id]
+            if e.id in ("True", "False"):
+                return const_val(e.id == "True")
+            if e.id in self.genv and isinstance(self.genv[e.id], (bool, int, float, str)):
+                return const_val(self.genv[e.id])
+            raise UnsupportedUDF(f"name {e.id!r} is not a parameter, local or constant global")
+        if isinstance(e, ast.Tuple):
+            return TupleVal([self.expr(x) for x in e.elts])
+        if isinstance(e, ast.BinOp):
+            return self.binop(e.op, self.expr(e.left), self.expr(e.right))
+        if isinstance(e, ast.UnaryOp):
+            v = self.expr(e.operand)
+            if isinstance(e.op, ast.Not):
+                return sc.b_not(sc.truth(v))
+            if isinstance(v, TupleVal) or v.type == T_STR:
+                raise UnsupportedUDF("unary operator on non-number")
+            if isinstance(e.op, ast.USub):
+                if sc.is_const(v):
+                    return const_val(-v.const if not isinstance(v.const, bool) else -int(v.const))
+                return sc.op1(C["TPLX_OP_FNEG"], T_F64, v) if v.type == T_F64 else sc.op1(C["TPLX_OP_INEG"], T_I64, sc.to_i64(v))
+            if isinstance(e.op, ast.UAdd):
+                return v if v.type == T_F64 else sc.to_i64(v)
+            if isinstance(e.op, ast.Invert):
+                return sc.op2(C["TPLX_OP_IXOR"], T_I64, sc.to_i64(v), const_val(-1))
+        if isinstance(e, ast.BoolOp):
+            # short-circuit: later operands are only evaluated (and may only raise) when needed
+            vals = None
+            outer_path = self.path
+            acc = None
+            for i, sub in enumerate(e.values):
+                v = sc.truth(self.expr(sub))
+                if acc is None:
+                    acc = v
+                else:
+                    acc = self._with_unguarded(lambda: sc.b_and(acc, v)) if isinstance(e.op, ast.And) else \
+                        self._with_unguarded(lambda: sc.b_or(acc, v))
+                if i + 1 < len(e.values):
+                    need = acc if isinstance(e.op, ast.And) else self._with_unguarded(lambda: sc.b_not(acc))
+                    self.path = self._with_unguarded(lambda: sc.b_and(outer_path, need) if outer_path is not None else need)
+                    self._set_guard()
+            self.path = outer_path
+            self._set_guard()
+            return acc
+        if isinstance(e, ast.Compare):
+            return self.compare(e)
+        if isinstance(e, ast.IfExp):
+            cond = sc.truth(self.expr(e.test))
+            outer_path = self.path
+            self.path = self._with_unguarded(lambda: sc.b_and(outer_path, cond) if outer_path is not None else cond)
+            self._set_guard()
+            a = self.expr(e.body)
+            ncond = self._with_unguarded(lambda: sc.b_not(cond))
+            self.path = self._with_unguarded(lambda: sc.b_and(outer_path, ncond) if outer_path is not None else ncond)
+            self._set_guard()
+            b = self.expr(e.orelse)
+            self.path = outer_path
+            self._set_guard()
+            return sc.select(cond, a, b)
+        if isinstance(e, ast.Subscript):
+            return self.subscript(e)
+        if isinstance(e, ast.Call):
+            return self.call(e)
+        raise UnsupportedUDF(f"expression {type(e).__name__} not supported")
+
+    # ---- arithmetic (BlockGeneratorVisitor.cc:152-584) ------------------------------------------------
+    def binop(self, op, l, r):
+        sc = self.sc
+        if isinstance(l, TupleVal) or isinstance(r, TupleVal):
+            raise UnsupportedUDF("tuple arithmetic")
+        if l.type == T_STR or r.type == T_STR:
+            if isinstance(op, ast.Add) and l.type == T_STR and r.type == T_STR:
+                if sc.is_const(l) and sc.is_const(r):
+                    return const_val(l.const + r.const)
+                return sc.op2(C["TPLX_OP_SCONCAT"], T_STR, l, r)
+            if isinstance(op, ast.Mod) and l.type == T_STR:
+                return self.format_percent(l, r)
+            raise UnsupportedUDF("string operator not supported")
+        if sc.is_const(l) and sc.is_const(r):
+            return self.fold(op, l.const, r.const)
+        is_f = l.type == T_F64 or r.type == T_F64
+        if isinstance(op, ast.Div):
+            return sc.op2(C["TPLX_OP_FDIV"], T_F64, sc.to_f64(l), sc.to_f64(r))
+        if is_f:
+            table = {ast.Add: "FADD", ast.Sub: "FSUB", ast.Mult: "FMUL", ast.Mod: "FMOD", ast.FloorDiv: "FFLOORDIV"}
+            if type(op) not in table:
+                raise UnsupportedUDF(f"float operator {type(op).__name__}")
+            return sc.op2(C["TPLX_OP_" + table[type(op)]], T_F64, sc.to_f64(l), sc.to_f64(r))
+        table = {ast.Add: "IADD", ast.Sub: "ISUB", ast.Mult: "IMUL", ast.Mod: "IMOD", ast.FloorDiv: "IFLOORDIV",
+                 ast.BitAnd: "IAND", ast.BitOr: "IOR", ast.BitXor: "IXOR", ast.LShift: "ISHL", ast.RShift: "ISHR"}
+        if type(op) not in table:
+            raise UnsupportedUDF(f"integer operator {type(op).__name__}")
+        if type(op) in (ast.BitAnd, ast.BitOr, ast.BitXor) and l.type == T_BOOL and r.type == T_BOOL:
+            return sc.op2(C["TPLX_OP_" + table[type(op)]], T_BOOL, l, r)
+        return sc.op2(C["TPLX_OP_" + table[type(op)]], T_I64, sc.to_i64(l), sc.to_i64(r))
+
+    def fold(self, op, a, b):
+        """Literal folding with the reference's quirk: folded floats are re-parsed from their
+        6-significant-digit text (ReduceExpressionsVisitor.cc:257-263,300-306,328-334)."""
+        try:
+            if isinstance(op, ast.Add):
+                x = a + b
+            elif isinstance(op, ast.Sub):
+                x = a - b
+            elif isinstance(op, ast.Mult):
+                x = a * b
+            elif isinstance(op, ast.Div):
+                x = a / b
+            else:
+                # not folded by the reference: evaluate at run time so that errors surface per row
+                return self.binop(op, self._force(const_val(a)), self._force(const_val(b)))
+        except ZeroDivisionError:
+            return self.binop(op, self._force(const_val(a)), self._force(const_val(b)))
+        if isinstance(x, float):
+            x = float("%g" % x)
+        elif isinstance(x, bool):
+            x = int(x)
+        return const_val(x)
+
+    def _force(self, v: Val) -> Val:
+        return Val(v.type, self.sc.reg(v))
+
+    def format_percent(self, fmt: Val, arg):
+        """'%05d' % v via snprintf semantics (BlockGeneratorVisitor::formatStr :675-775)."""
+        sc = self.sc
+        if not sc.is_const(fmt):
+            raise UnsupportedUDF("format string must be a literal")
+        args = arg.elems if isinstance(arg, TupleVal) else [arg]
+        pieces: List[Val] = []
+        pos = 0
+        ai = 0
+        s = fmt.const
+        for m in _FMT_RE.finditer(s):
+            if m.start() > pos:
+                pieces.append(const_val(s[pos:m.start()]))
+            pos = m.end()
+            conv = m.group("conv")
+            if conv == "%":
+                pieces.append(const_val("%"))
+                continue
+            if ai >= len(args):
+                raise UnsupportedUDF("not enough arguments for format string")
+            a = args[ai]
+            ai += 1
+            flags, width = m.group("flags") or "", int(m.group("width") or 0)
+            if m.group("prec") or any(f in flags for f in " -+#"):
+                raise UnsupportedUDF("format flags/precision not supported")
+            if conv in "di":
+                if isinstance(a, TupleVal) or a.type not in (T_I64, T_BOOL):
+                    raise UnsupportedUDF("%d needs an integer")
+                pieces.append(sc.op1(C["TPLX_OP_SFMTD"], T_STR, sc.to_i64(a), flags=1 if "0" in flags else 0, imm=width))
+            elif conv == "s":
+                if isinstance(a, TupleVal) or a.type != T_STR or width:
+                    raise UnsupportedUDF("%s supports plain strings only")
+                pieces.append(a)
+            else:
+                raise UnsupportedUDF("%f formatting not supported")
+        if ai != len(args):
+            raise UnsupportedUDF("too many arguments for format string")
+        if pos < len(s):
+            pieces.append(const_val(s[pos:]))
+        if not pieces:
+            return const_val("")
+        out = pieces[0]
+        for p in pieces[1:]:
+            out = self.binop(ast.Add(), out, p)
+        return out
+
+    # ---- comparisons (BlockGeneratorVisitor.cc:776-880) -------------------------------------------------
+    def compare(self, e: ast.Compare):
+        sc = self.sc
+        left = self.expr(e.left)
+        acc = None
+        outer_path = self.path
+        for k, (op, rn) in enumerate(zip(e.ops, e.comparators)):
+            right = self.expr(rn)
+            c = self.compare1(op, left, right)
+            acc = c if acc is None else self._with_unguarded(lambda: sc.b_and(acc, c))
+            left = right
+            if k + 1 < len(e.ops):  # chained comparison short-circuits like `and`
+                self.path = self._with_unguarded(lambda: sc.b_and(outer_path, acc) if outer_path is not None else acc)
+                self._set_guard()
+        self.path = outer_path
+        self._set_guard()
+        return acc
+
+    def compare1(self, op, l, r):
+        sc = self.sc
+        if isinstance(l, TupleVal) or isinstance(r, TupleVal):
+            raise UnsupportedUDF("tuple comparison")
+        if isinstance(op, (ast.In, ast.NotIn)):
+            if l.type != T_STR or r.type != T_STR:
+                raise UnsupportedUDF("`in` is supported for str in str")
+            if sc.is_const(l) and sc.is_const(r):
+                res = const_val(l.const in r.const)
+            else:
+                res = sc.op2(C["TPLX_OP_SIN"], T_BOOL, l, r)
+            return sc.b_not(res) if isinstance(op, ast.NotIn) else res
+        if type(op) not in _CMP:
+            raise UnsupportedUDF(f"comparison {type(op).__name__}")
+        if l.type == T_STR or r.type == T_STR:
+            if l.type != r.type:
+                # str == number is False in Python; the reference rejects it at compile time
+                raise UnsupportedUDF("comparison between str and number")
+            if not isinstance(op, (ast.Eq, ast.NotEq)):
+                raise UnsupportedUDF("ordering comparison of strings")
+            if sc.is_const(l) and sc.is_const(r):
+                return const_val((l.const == r.const) == isinstance(op, ast.Eq))
+            return sc.op2(C["TPLX_OP_SEQ"], T_BOOL, l, r, flags=0 if isinstance(op, ast.Eq) else 1)
+        pred = C["TPLX_CMP_" + _CMP[type(op)]]
+        if sc.is_const(l) and sc.is_const(r):
+            a, b = l.const, r.const
+            return const_val({"EQ": a == b, "NE": a != b, "LT": a < b, "LE": a <= b, "GT": a > b, "GE": a >= b}[_CMP[type(op)]])
+        if l.type == T_F64 or r.type == T_F64:
+            return sc.op2(C["TPLX_OP_FCMP"], T_BOOL, sc.to_f64(l), sc.to_f64(r), flags=pred)
+        return sc.op2(C["TPLX_OP_ICMP"], T_BOOL, sc.to_i64(l), sc.to_i64(r), flags=pred)
+
+    # ---- subscripts -------------------------------------------------------------------------------------
+    def subscript(self, e: ast.Subscript):
+        sc = self.sc
+        base = self.expr(e.value)
+        if isinstance(base, TupleVal):
+            if isinstance(e.slice, ast.Slice):
+                raise UnsupportedUDF("tuple slices")
+            idx = self.expr(e.slice)
+            if not sc.is_const(idx):
+                raise UnsupportedUDF("tuple index must be a compile-time constant")
+            k = idx.const
+            if isinstance(k, str):
+                if not base.names or k not in base.names:
+                    raise UnsupportedUDF(f"unknown column {k!r}")
+                return base.elems[base.names.index(k)]
+            if isinstance(k, bool) or not isinstance(k, int) or not -len(base.elems) <= k < len(base.elems):
+                raise UnsupportedUDF("tuple index out of range")
+            return base.elems[k]
+        if base.type != T_STR:
+            # single-column rows: x[0] / x['col'] address the only column (python/tuplex/dataset.py semantics)
+            if isinstance(e.slice, ast.Constant) and (e.slice.value == 0 or (isinstance(e.slice.value, str) and e.slice.value in sc.names)):
+                return base
+            raise UnsupportedUDF("subscript on a number")
+        if isinstance(e.slice, ast.Slice):
+            sl = e.slice
+            if sl.step is not None:
+                st = self.expr(sl.step)
+                if not (sc.is_const(st) and st.const == 1):
+                    raise UnsupportedUDF("slice stride other than 1")
+            lo = self.expr(sl.lower) if sl.lower is not None else None
+            hi = self.expr(sl.upper) if sl.upper is not None else None
+            for v in (lo, hi):
+                if v is not None and (isinstance(v, TupleVal) or v.type not in (T_I64, T_BOOL)):
+                    raise UnsupportedUDF("slice bounds must be integers")
+            if sc.is_const(base) and (lo is None or sc.is_const(lo)) and (hi is None or sc.is_const(hi)):
+                return const_val(base.const[(lo.const if lo else None):(hi.const if hi else None)])
+            flags = (C["TPLX_SL_HAS_START"] if lo is not None else 0) | (C["TPLX_SL_HAS_END"] if hi is not None else 0)
+            d = sc.new_vreg(T_STR)
+            sc.emit(C["TPLX_OP_SSLICE"], d, sc.reg(base), sc.reg(sc.to_i64(lo)) if lo is not None else None,
+                    sc.reg(sc.to_i64(hi)) if hi is not None else None, flags=flags)
+            return Val(T_STR, d)
+        idx = self.expr(e.slice)
+        if isinstance(idx, TupleVal) or idx.type not in (T_I64, T_BOOL):
+            # single string column addressed by name
+            if sc.is_const(idx) and isinstance(idx.const, str) and idx.const in sc.names and len(sc.row) == 1:
+                return base
+            raise UnsupportedUDF("string index must be an integer")
+        return sc.op2(C["TPLX_OP_SINDEX"], T_STR, base, sc.to_i64(idx))
+
+    # ---- calls (FunctionRegistry.cc) --------------------------------------------------------------------
+    def call(self, e: ast.Call):
+        sc = self.sc
+        if e.keywords:
+            raise UnsupportedUDF("keyword arguments")
+        if isinstance(e.func, ast.Name):
+            name = e.func.id
+            args = [self.expr(a) for a in e.args]
+            if any(isinstance(a, TupleVal) for a in args):
+                if name == "len" and len(args) == 1:
+                    return const_val(len(args[0].elems))
+                raise UnsupportedUDF("tuple argument")
+            if name == "int":
+                if not args:
+                    return const_val(0)
+                (a,) = args
+                if a.type in (T_I64, T_BOOL):
+                    return sc.to_i64(a)
+                if a.type == T_F64:
+                    return const_val(int(a.const)) if sc.is_const(a) else sc.op1(C["TPLX_OP_F2I"], T_I64, a)
+                return sc.op1(C["TPLX_OP_S2I"], T_I64, a)
+            if name == "float" and len(args) == 1 and args[0].type != T_STR:
+                return sc.to_f64(args[0])
+            if name == "bool" and len(args) == 1:
+                return sc.truth(args[0])
+            if name == "len" and len(args) == 1 and args[0].type == T_STR:
+                return const_val(len(args[0].const)) if sc.is_const(args[0]) else sc.op1(C["TPLX_OP_SLEN"], T_I64, args[0])
+            if name == "str" and len(args) == 1:
+                a = args[0]
+                if a.type == T_STR:
+                    return a
+                if a.type == T_I64:
+                    return sc.op1(C["TPLX_OP_I2S"], T_STR, a)
+                raise UnsupportedUDF("str() of this type")
+            if name == "abs" and len(args) == 1 and args[0].type != T_STR:
+                a = args[0]
+                return sc.op1(C["TPLX_OP_FABS"], T_F64, a) if a.type == T_F64 else sc.op1(C["TPLX_OP_IABS"], T_I64, sc.to_i64(a))
+            raise UnsupportedUDF(f"call to {name}()")
+        if isinstance(e.func, ast.Attribute):
+            obj = self.expr(e.func.value)
+            if isinstance(obj, TupleVal) or obj.type != T_STR:
+                raise UnsupportedUDF("method call on non-string")
+            m = e.func.attr
+            args = [self.expr(a) for a in e.args]
+            if any(isinstance(a, TupleVal) for a in args):
+                raise UnsupportedUDF("tuple argument")
+
+            def want_str(n):
+                if len(args) != n or any(a.type != T_STR for a in args):
+                    raise UnsupportedUDF(f"str.{m} expects {n} string argument(s)")
+            if m in ("find", "rfind", "index"):
+                want_str(1)
+                if m == "index":
+                    raise UnsupportedUDF("str.index")
+                return sc.op2(C["TPLX_OP_SFIND" if m == "find" else "TPLX_OP_SRFIND"], T_I64, obj, args[0])
+            if m in ("lower", "upper"):
+                want_str(0)
+                if sc.is_const(obj):
+                    return const_val(obj.const.lower() if m == "lower" else obj.const.upper())
+                return sc.op1(C["TPLX_OP_SLOWER" if m == "lower" else "TPLX_OP_SUPPER"], T_STR, obj)
+            if m == "replace":
+                want_str(2)
+                d = sc.new_vreg(T_STR)
+                sc.emit(C["TPLX_OP_SREPLACE"], d, sc.reg(obj), sc.reg(args[0]), sc.reg(args[1]))
+                return Val(T_STR, d)
+            if m in ("startswith", "endswith"):
+                want_str(1)
+                return sc.op2(C["TPLX_OP_SSTARTS" if m == "startswith" else "TPLX_OP_SENDS"], T_BOOL, obj, args[0])
+            if m in ("strip", "lstrip", "rstrip"):
+                want_str(0)
+                fl = {"strip": 3, "lstrip": 1, "rstrip": 2}[m]
+                return sc.op1(C["TPLX_OP_SSTRIP"], T_STR, obj, flags=fl)
+            raise UnsupportedUDF(f"str.{m}()")
+        raise UnsupportedUDF("call expression")

@@ -1,0 +1,138 @@
+"""Stage descriptor ("op program") builder — Python mirror of include/tplx_ir.h.
+
+The enumerators are parsed out of the C header at import time so the two sides cannot drift.
+A reference TransformStage carries LLVM bitcode (tuplex/core/src/physical/StageBuilder.cc:1499-1535);
+ours carries this flat predicated register program instead.
+"""
+from __future__ import annotations
+
+import os
+import re
+import struct
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+_HDR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "include", "tplx_ir.h")
+
+
+def _parse_header(path: str) -> Dict[str, int]:
+    txt = open(path).read()
+    consts: Dict[str, int] = {}
+    for m in re.finditer(r"^\s*(TPLX_[A-Z0-9_]+)\s*=\s*(-?\d+)\s*,", txt, re.M):
+        consts[m.group(1)] = int(m.group(2))
+    for m in re.finditer(r"^#define\s+(TPLX_[A-Z0-9_]+)\s+(0x[0-9A-Fa-f]+|\d+)u?\s*(?:/\*.*)?$", txt, re.M):
+        consts[m.group(1)] = int(m.group(2), 0)
+    return consts
+
+
+C = _parse_header(_HDR)
+globals().update(C)  # TPLX_OP_*, TPLX_T_*, ... become module attributes
+
+T_I64, T_F64, T_BOOL, T_STR = C["TPLX_T_I64"], C["TPLX_T_F64"], C["TPLX_T_BOOL"], C["TPLX_T_STR"]
+TYPE_NAMES = {T_I64: "i64", T_F64: "f64", T_BOOL: "bool", T_STR: "str"}
+NOSLOT = C["TPLX_NOSLOT"]
+OP_NAMES = {v: k[len("TPLX_OP_"):] for k, v in C.items() if k.startswith("TPLX_OP_")}
+
+INSTR_FMT = "<BBHHHHHHHqq"  # 32 bytes
+assert struct.calcsize(INSTR_FMT) == 32
+HEADER_FMT = "<IIIHHHHHHIIBBHI"
+assert struct.calcsize(HEADER_FMT) == 40
+
+
+@dataclass
+class Instr:
+    op: int
+    dst: int = NOSLOT
+    a: int = NOSLOT
+    b: int = NOSLOT
+    c: int = NOSLOT
+    guard: int = NOSLOT
+    opidx: int = 0
+    flags: int = 0
+    imm: int = 0
+    imm2: int = 0
+
+    def pack(self) -> bytes:
+        imm = self.imm
+        if imm >= 1 << 63:
+            imm -= 1 << 64
+        return struct.pack(INSTR_FMT, self.op, self.flags, self.dst, self.a, self.b, self.c, self.guard,
+                           self.opidx, 0, imm, self.imm2)
+
+    def __repr__(self):
+        return (f"{OP_NAMES.get(self.op, self.op)} dst={self.dst} a={self.a} b={self.b} c={self.c} "
+                f"g={self.guard} fl={self.flags} imm={self.imm} imm2={self.imm2} op#{self.opidx}")
+
+
+@dataclass
+class Acc:
+    kind: int
+    slot: int
+    init_bits: int  # raw 64-bit pattern (i64 value or f64 bits)
+
+
+@dataclass
+class Program:
+    """A complete stage: input schema, instructions, output row / accumulators / keys."""
+    in_types: List[int]
+    in_names: List[Optional[str]]
+    instrs: List[Instr] = field(default_factory=list)
+    cpool: bytearray = field(default_factory=bytearray)
+    out_cols: List[Tuple[int, int]] = field(default_factory=list)  # (slot, type)
+    out_names: List[Optional[str]] = field(default_factory=list)
+    accs: List[Acc] = field(default_factory=list)
+    n_keys: int = 0
+    opids: List[int] = field(default_factory=list)
+    n_slots: int = 0
+    endpoint: int = 0
+    split_pc: int = 0
+    scratch_bytes: int = 256
+    _cpool_index: Dict[bytes, int] = field(default_factory=dict)
+
+    def const_bytes(self, b: bytes) -> Tuple[int, int]:
+        if b in self._cpool_index:
+            return self._cpool_index[b], len(b)
+        off = len(self.cpool)
+        self.cpool += b
+        # keep constants 8-byte separated so that views never alias by accident
+        while len(self.cpool) % 8:
+            self.cpool.append(0)
+        self._cpool_index[b] = off
+        return off, len(b)
+
+    def serialize(self) -> bytes:
+        def pad8(b: bytes) -> bytes:
+            return b + b"\0" * ((-len(b)) % 8)
+
+        body = b""
+        body += pad8(bytes(self.in_types))
+        body += pad8(b"".join(struct.pack("<HBB", s, t, 0) for s, t in self.out_cols))
+        body += b"".join(struct.pack("<BBHIq", a.kind, 0, a.slot, 0, _as_i64(a.init_bits)) for a in self.accs)
+        body += b"".join(struct.pack("<q", o) for o in self.opids)
+        body += b"".join(i.pack() for i in self.instrs)
+        body += pad8(bytes(self.cpool))
+        total = struct.calcsize(HEADER_FMT) + len(body)
+        hdr = struct.pack(HEADER_FMT, C["TPLX_IR_MAGIC"], C["TPLX_IR_VERSION"], total, len(self.in_types),
+                          len(self.out_cols), len(self.accs), self.n_keys, len(self.opids), self.n_slots,
+                          len(self.instrs), len(self.cpool), self.endpoint, 0, self.split_pc, self.scratch_bytes)
+        return hdr + body
+
+    def dump(self) -> str:
+        lines = [f"in: {[TYPE_NAMES[t] for t in self.in_types]} slots={self.n_slots} split_pc={self.split_pc}"]
+        for i, ins in enumerate(self.instrs):
+            lines.append(f"{i:4d}: {ins!r}")
+        lines.append(f"out: {[(s, TYPE_NAMES[t]) for s, t in self.out_cols]} accs={self.accs} keys={self.n_keys}")
+        return "\n".join(lines)
+
+
+def _as_i64(bits: int) -> int:
+    bits &= (1 << 64) - 1
+    return bits - (1 << 64) if bits >= 1 << 63 else bits
+
+
+def f64_bits(x: float) -> int:
+    return struct.unpack("<Q", struct.pack("<d", x))[0]
+
+
+def bits_f64(b: int) -> float:
+    return struct.unpack("<d", struct.pack("<Q", b & ((1 << 64) - 1)))[0]
