@@ -1,0 +1,457 @@
+#!/usr/bin/env python
+"""bench.py — rows/s of the hot path on B200, next to the HBM roofline and the reference's CPU path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload zillow|q6|c1] [--rows R] [--impl reference]
+
+A "step" is one pass of the stage over the whole synthetic workload. Default workload = BASELINE.json
+configs[1]: the Zillow Z1 pipeline over 100M synthetic rows (cyclic replication of the reference's 32,661-row
+fixture, the reference's own generator benchmarks/zillow/Z1/sample_zillow.py:20-45), column-blocked, one GPU.
+Prints ONE JSON line (rank 0). See the prompt contract in DESIGN.md §Measurement for every key.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="zillow", choices=["zillow", "q6", "c1", "aggbykey"])
+    ap.add_argument("--rows", type=int, default=0, help="rows per GPU (default: 100M zillow / 600M q6 / 1e6*100 c1)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) >= 8:
+                self.samples.append(f)
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        mx = [float(s[2]) for s in self.samples if s[2].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(self.samples)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------------
+# workloads
+# ------------------------------------------------------------------------------------------------------
+def pinned(arr: np.ndarray):
+    """Copy a numpy array into page-locked host memory (torch is plumbing here: allocator only)."""
+    import torch
+    t = torch.empty(arr.shape, dtype=torch.from_numpy(arr[:0]).dtype, pin_memory=True)
+    out = t.numpy()
+    out[...] = arr
+    out_flags_keep = t  # keep the tensor alive through the numpy view's base
+    return out, out_flags_keep
+
+
+def build_workload(args):
+    from tuplex_b200 import workloads as W
+    from tuplex_b200.backend import Column
+    keep = []
+
+    def pin_cols(cols):
+        out = []
+        for c in cols:
+            d, k1 = pinned(c.data)
+            keep.append(k1)
+            o = None
+            if c.offsets is not None:
+                o, k2 = pinned(c.offsets)
+                keep.append(k2)
+            out.append(Column(c.type, d, o))
+        return out
+
+    if args.workload == "zillow":
+        total = args.rows or 100_000_000
+        src, n0 = W.load_zillow_fixture()
+        cycles_per_block = 500
+        bn = cycles_per_block * n0
+        blocks = []
+        full = W.replicate(src, n0, min(bn, total))
+        full = pin_cols(full)
+        done = 0
+        while done < total:
+            m = min(bn, total - done)
+            if m == len(full[0]):
+                blocks.append((full, m))
+            else:
+                blocks.append((pin_cols(W.replicate(src, n0, m)), m))
+            done += m
+        prog = W.zillow_program()
+        in_bytes = sum(sum(c.nbytes() for c in cols) for cols, _ in blocks)
+        return dict(name="zillow_z1", prog=prog, blocks=blocks, rows=total, in_bytes=in_bytes, keep=keep,
+                    desc=f"Zillow Z1 map/withColumn/filter pipeline, {total} synthetic rows (cyclic replication of the 32,661-row "
+                         f"zillow_noexc fixture), 8 column-blocked inputs, {len(blocks)} blocks of <= {bn} rows")
+    if args.workload == "q6":
+        total = args.rows or 600_000_000
+        bn = 100_000_000
+        blocks = []
+        done = 0
+        base = pin_cols(W.gen_lineitem(min(bn, total), seed=42))
+        while done < total:
+            m = min(bn, total - done)
+            blocks.append((base if m == len(base[0].data) else [c.slice(0, m) for c in base], m))
+            done += m
+        prog = W.q6_program()
+        return dict(name="tpch_q6", prog=prog, blocks=blocks, rows=total, in_bytes=total * 32, keep=keep,
+                    desc=f"TPC-H Q6 filter+aggregate, {total} synthetic lineitem rows (SF100 ~ 600M), 4 columns i64,f64,f64,i64")
+    if args.workload == "c1":
+        total = args.rows or 100_000_000
+        x = np.arange(1, total + 1, dtype=np.int64)
+        blocks = [(pin_cols([Column(0, x)]), total)]
+        return dict(name="c1_map_filter", prog=W.c1_program(), blocks=blocks, rows=total, in_bytes=total * 8, keep=keep,
+                    desc=f"parallelize([1..{total}]).map(x*x).filter(x%2==0)")
+    total = args.rows or 100_000_000
+    nkeys = max(1000, total // 100)
+    blocks = [(pin_cols(W.gen_keyed(total, nkeys, seed=42)), total)]
+    return dict(name="aggbykey_str", prog=W.keyed_program(), blocks=blocks, rows=total, in_bytes=total * 20, keep=keep, nkeys=nkeys,
+                desc=f"aggregateByKey string key, {total} rows, {nkeys} distinct keys")
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arms
+# ------------------------------------------------------------------------------------------------------
+def cpu_zillow_reference(sample_rows: int, procs: int):
+    """The reference's own hand-written C++ Z1 pipeline (benchmarks/zillow/Z1/baseline/zillow.cpp, built unmodified
+    into oracle/_ref/zillow_ref), --preload compute stage, `procs` processes in parallel over the host cores."""
+    import gzip
+    exe = os.path.join(ROOT, "oracle", "_ref", "zillow_ref")
+    if not os.path.exists(exe):
+        return None
+    with gzip.open(os.path.join(ROOT, "tests", "golden", "zillow_noexc_cols.csv.gz"), "rb") as fp:
+        raw = fp.read()
+    header, body = raw.split(b"\n", 1)
+    n0 = body.count(b"\n")
+    reps = max(1, sample_rows // n0)
+    rows = reps * n0
+    td = tempfile.mkdtemp(prefix="tplx_cpu_")
+    path = os.path.join(td, "sample.csv")
+    with open(path, "wb") as fp:
+        fp.write(header + b"\n")
+        for _ in range(reps):
+            fp.write(body)
+    ps = [subprocess.Popen([exe, "--path", path, "--output_path", os.path.join(td, f"out{i}"), "--preload"], stdout=subprocess.PIPE,
+                           stderr=subprocess.DEVNULL, text=True) for i in range(procs)]
+    ns = []
+    for p in ps:
+        out, _ = p.communicate()
+        for line in out.splitlines():
+            if line.startswith("compute stage:"):
+                ns.append(float(line.split()[2]))
+    subprocess.call(["rm", "-rf", td])
+    if len(ns) != procs:
+        return None
+    return dict(value=procs * rows / (max(ns) * 1e-9), unit="rows/s", cores=procs, kind="reference",
+                sample=f"{procs} processes x {rows} rows (cyclic replication of the fixture, CSV preloaded), compute stage of "
+                       f"oracle/_ref/zillow_ref = reference benchmarks/zillow/Z1/baseline/zillow.cpp; slowest process {max(ns) * 1e-6:.1f} ms")
+
+
+def cpu_port(wl, sample_rows: int, threads: int):
+    """oracle port (kind 'port') on a bounded sample."""
+    from oracle import pyoracle
+    if wl["name"] == "tpch_q6":
+        cols = wl["blocks"][0][0]
+        m = min(len(cols[0].data), max(sample_rows, 50_000_000))
+        a = [c.data[:m] for c in cols]
+        t0 = time.perf_counter()
+        pyoracle.q6(*a, part_rows=1 << 20, threads=threads)
+        dt = time.perf_counter() - t0
+        return dict(value=m / dt, unit="rows/s", cores=threads, kind="port",
+                    sample=f"{m} rows, oracle/workloads.c Q6 loop, {threads} threads over 1Mi-row partitions, inputs in memory")
+    if wl["name"] == "c1_map_filter":
+        x = wl["blocks"][0][0][0].data
+        m = min(len(x), max(sample_rows, 50_000_000))
+        t0 = time.perf_counter()
+        pyoracle.c1(x[:m], part_rows=1 << 20, threads=threads)
+        dt = time.perf_counter() - t0
+        return dict(value=m / dt, unit="rows/s", cores=threads, kind="port",
+                    sample=f"{m} rows, oracle/workloads.c C1 loop, {threads} threads")
+    cols, n = wl["blocks"][0]
+    m = min(n, sample_rows)
+    t0 = time.perf_counter()
+    pyoracle.run_program(wl["prog"], [c.slice(0, m) for c in cols], m)
+    dt = time.perf_counter() - t0
+    return dict(value=m / dt, unit="rows/s", cores=1, kind="port", sample=f"{m} rows through oracle/tplx_oracle.c (scalar interpreter)")
+
+
+def cpu_baseline(args, wl):
+    cores = os.cpu_count() or 1
+    if wl["name"] == "zillow_z1":
+        r = cpu_zillow_reference(args.cpu_sample_rows, cores)
+        if r:
+            return r
+    return cpu_port(wl, args.cpu_sample_rows, cores)
+
+
+# ------------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        import types
+        wl_args = types.SimpleNamespace(**vars(args))
+        wl_args.rows = min(args.rows or 10**9, 2_000_000) if args.workload != "q6" else min(args.rows or 10**9, 100_000_000)
+        wl = None
+        if args.workload != "zillow":
+            os.environ.setdefault("CUDA_VISIBLE_DEVICES", "")
+            wl = build_workload_nopin(wl_args)
+        vals = []
+        last = None
+        for i in range(args.warmup + args.steps):
+            last = cpu_zillow_reference(args.cpu_sample_rows, os.cpu_count() or 1) if args.workload == "zillow" else \
+                cpu_port(wl, args.cpu_sample_rows, os.cpu_count() or 1)
+            if last is None:
+                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/zillow_ref missing and no port for this workload"}))
+                return 0
+            if i >= args.warmup:
+                vals.append(last["value"])
+        v = float(np.mean(vals))
+        names = {"zillow": "zillow_z1", "q6": "tpch_q6", "c1": "c1_map_filter", "aggbykey": "aggbykey_str"}
+        line = {"metric": "rows/sec on Zillow pipeline + TPC-H Q6" if args.workload in ("zillow", "q6") else "rows/sec",
+                "impl": "reference", "value": v, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i64/f64",
+                "data": "synthetic", "config": {"workload": names[args.workload]},
+                "cpu_baseline": dict(last, value=v),
+                "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from tuplex_b200 import backend, ir
+    backend.init([local])
+    wl = build_workload(args)
+    prog = wl["prog"]
+    st = backend.Stage(prog)
+    ep = prog.endpoint
+    if ep == ir.C["TPLX_EP_HASH"]:
+        st.hash_reserve(local, wl.get("nkeys", 1 << 20))
+
+    # device-resident copies of every block (distinct HBM: the working set is far larger than the 126 MB L2)
+    dev_blocks = [backend.Block.upload(local, cols, n) for cols, n in wl["blocks"]]
+    torch.cuda.synchronize()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    stats = {}
+
+    def step_resident():
+        first = 0
+        kms = 0.0
+        launches = 0
+        n_out = 0
+        partials = []
+        if ep == ir.C["TPLX_EP_HASH"]:
+            st.hash_reset(local)
+            st.hash_reserve(local, wl.get("nkeys", 1 << 20))
+        for b in dev_blocks:
+            r = st.run(b, first)
+            inf = r.info
+            kms += inf.kernel_ms
+            launches += inf.kernel_launches
+            n_out += int(inf.n_out_rows)
+            first += int(inf.n_out_rows) + int(inf.n_exceptions)
+            if ep == ir.C["TPLX_EP_AGGREGATE"]:
+                partials.append(ir.bits_f64(r.aggregate_bits()[0]))
+            r.free()
+        if ep == ir.C["TPLX_EP_AGGREGATE"]:
+            tot = 0.0
+            for p in partials:
+                tot = tot + p
+            if dist is not None:  # the one collective of the path: combine per-GPU partials, fixed rank order
+                t = torch.tensor([tot], dtype=torch.float64, device="cuda")
+                g = [torch.empty_like(t) for _ in range(world)]
+                dist.all_gather(g, t)
+                tot = 0.0
+                for x in g:
+                    tot = tot + float(x.item())
+            stats["result"] = tot
+        if ep == ir.C["TPLX_EP_HASH"]:
+            fin = st.hash_finish(local)
+            n_out = int(fin.info.n_out_rows)
+            kms += fin.info.kernel_ms
+            launches += fin.info.kernel_launches
+            fin.free()
+        stats.update(kernel_ms=kms, launches=launches, n_out=n_out)
+
+    def step_e2e():
+        first = 0
+        d2h = 0
+        if ep == ir.C["TPLX_EP_HASH"]:
+            st.hash_reset(local)
+            st.hash_reserve(local, wl.get("nkeys", 1 << 20))
+        for cols, n in wl["blocks"]:
+            r = st.run_host(local, cols, n, first)
+            inf = r.info
+            first += int(inf.n_out_rows) + int(inf.n_exceptions)
+            if ep == ir.C["TPLX_EP_MEMORY"]:
+                for c in r.columns():
+                    d2h += c.nbytes()
+                d2h += r.exceptions().nbytes
+            elif ep == ir.C["TPLX_EP_AGGREGATE"]:
+                r.aggregate_bits()
+                d2h += 8 * len(prog.accs)
+            r.free()
+        if ep == ir.C["TPLX_EP_HASH"]:
+            fin = st.hash_finish(local)
+            for c in fin.columns():
+                d2h += c.nbytes()
+            fin.free()
+        stats["d2h"] = d2h
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    clocks = Clocks(local)
+    sync_all()
+    clocks.start()
+    t0 = time.perf_counter()
+    kms = 0.0
+    launches = 0
+    for _ in range(args.steps):
+        step_resident()
+        kms += stats["kernel_ms"]
+        launches += stats["launches"]
+    sync_all()
+    dt = time.perf_counter() - t0
+    clk = clocks.stop()
+
+    # end-to-end through the C ABI with host buffers (H2D of inputs + D2H of results inside the timed region)
+    e2e_steps = max(1, min(args.steps, 3))
+    step_e2e()
+    sync_all()
+    t1 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    sync_all()
+    dt_e2e = time.perf_counter() - t1
+
+    times = torch.tensor([dt, dt_e2e], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dt, dt_e2e = float(times[0]), float(times[1])
+
+    if rank == 0:
+        rows_all = wl["rows"] * world
+        ms_step = dt / args.steps * 1e3
+        peak, peak_src = peaks()
+        # algorithmic bytes: every input byte read once + output bytes written once
+        out_bytes = 0
+        if ep == ir.C["TPLX_EP_MEMORY"]:
+            out_bytes = stats.get("d2h", 0)
+        alg_bytes = wl["in_bytes"] + out_bytes
+        n_launch = max(1, len(dev_blocks))
+        k_ms_per_launch = kms / args.steps / n_launch
+        achieved = (alg_bytes / n_launch) / (k_ms_per_launch * 1e-3) / 1e9 if k_ms_per_launch > 0 else 0.0
+        line = {
+            "metric": "rows/sec on Zillow pipeline + TPC-H Q6" if args.workload in ("zillow", "q6") else "rows/sec",
+            "value": rows_all / (dt / args.steps), "unit": "rows/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8/i64/f64", "data": "synthetic",
+            "config": {"workload": wl["name"], "rows_per_gpu": wl["rows"], "blocks": len(dev_blocks), "description": wl["desc"],
+                       "l2": "inputs larger than L2 (every block >> 126 MB, distinct HBM buffers per block)",
+                       "out_rows_per_gpu": stats.get("n_out")},
+            "clocks": clk,
+            "e2e": {"value": rows_all / (dt_e2e / e2e_steps), "unit": "rows/s", "h2d_bytes_per_step": wl["in_bytes"],
+                    "d2h_bytes_per_step": stats.get("d2h", 0), "steps": e2e_steps},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": {0: "stage_rows_kernel", 1: "stage_agg_kernel", 2: "stage_hash_kernel"}[ep],
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_row": alg_bytes / wl["rows"],
+                         "kernel_ms_per_launch": k_ms_per_launch, "kernel_share_of_step": (kms / args.steps) / ms_step},
+        }
+        if "result" in stats:
+            line["config"]["result"] = repr(stats["result"])
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args, wl)
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def build_workload_nopin(args):
+    """CPU arm: same generators, no pinned memory / no CUDA."""
+    from tuplex_b200 import workloads as W
+    from tuplex_b200.backend import Column
+    if args.workload == "q6":
+        n = args.rows
+        return dict(name="tpch_q6", prog=W.q6_program(), blocks=[(W.gen_lineitem(n, 42), n)], rows=n)
+    if args.workload == "c1":
+        n = args.rows
+        return dict(name="c1_map_filter", prog=W.c1_program(), blocks=[([Column(0, np.arange(1, n + 1, dtype=np.int64))], n)], rows=n)
+    n = args.rows
+    return dict(name="aggbykey_str", prog=W.keyed_program(), blocks=[(W.gen_keyed(n, max(1000, n // 100), 42), n)], rows=n)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -24,7 +24,7 @@ extern "C" {
 #endif
 
 #define TPLX_IR_MAGIC 0x58504C54u /* "TPLX" */
-#define TPLX_IR_VERSION 3u
+#define TPLX_IR_VERSION 4u
 #define TPLX_NOSLOT 0xFFFFu
 #define TPLX_MAX_COLS 64
 #define TPLX_MAX_ACCS 16
@@ -202,6 +202,13 @@ typedef struct tplx_acc {
  *   int64_t  opids[n_ops]             -- reference operator ids (LogicalOperator.h:52-59, start 100000)
  *   tplx_instr instrs[n_instr]
  *   uint8_t  const_pool[const_bytes]  (padded to 8)
+ *   uint8_t  prefilter[prefilter_bytes]  -- optional nested stage descriptor (same layout), see below
+ *
+ * Prefilter (selective pipelines): a MEMORY stage whose single output column is the row index
+ * (TPLX_OP_LDROW) of the rows that survive the leading, selective part of the pipeline. The executor runs
+ * it first and then runs THIS stage densely over the surviving row list only (late materialisation: the
+ * columns that only survivors need are never read for the other rows). It is an execution hint: running
+ * this stage over all rows gives the same result, which is what the oracle does.
  */
 typedef struct tplx_stage_header {
     uint32_t magic;
@@ -217,9 +224,11 @@ typedef struct tplx_stage_header {
     uint32_t const_bytes;
     uint8_t endpoint;     /* tplx_endpoint */
     uint8_t pad0;
-    uint16_t split_pc;    /* 0 = none; else: run [0,split_pc) on all rows, compact survivors, then run
-                             the whole program densely on survivors (selective-filter split) */
-    uint32_t scratch_bytes; /* per-row scratch for materialised strings */
+    uint16_t hidden_out_cols; /* trailing output columns that are executor-internal (row index of each output
+                                 row, used to number exception rows when a prefilter ran); never handed out */
+    uint32_t scratch_bytes;   /* per-row scratch for materialised strings */
+    uint32_t prefilter_bytes; /* size of the nested prefilter stage descriptor, 0 = none */
+    uint32_t pad1;
 } tplx_stage_header;
 
 #ifdef __cplusplus

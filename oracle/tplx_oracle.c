@@ -251,7 +251,8 @@ static int parse_stage(const void *desc, uint64_t bytes, ostage *s) {
     s->instrs = (const tplx_instr *)(p + off);
     off += (size_t)s->h.n_instr * sizeof(tplx_instr);
     s->cpool = p + off;
-    return off + pad8(s->h.const_bytes) == bytes ? 0 : -1;
+    /* a nested prefilter stage is an execution hint only: the oracle runs the full stage over every row */
+    return off + pad8(s->h.const_bytes) + s->h.prefilter_bytes == bytes ? 0 : -1;
 }
 
 static double as_f(int64_t bits) {
@@ -564,7 +565,7 @@ int tplx_oracle_run(const void *desc, uint64_t desc_bytes, const tplx_ocol *cols
     const uint32_t na = S.h.n_accs;
     res->n_accs = na;
     const int is_hash = S.h.endpoint == TPLX_EP_HASH;
-    res->n_cols = is_hash ? S.h.n_keys + na : S.h.n_out_cols;
+    res->n_cols = is_hash ? S.h.n_keys + na : (uint64_t)(S.h.n_out_cols - S.h.hidden_out_cols);
     for (uint64_t c = 0; c < S.h.n_out_cols && c < res->n_cols; ++c) res->col_types[c] = S.out_cols[c].type;
     if (is_hash)
         for (uint32_t k = 0; k < na; ++k) {

@@ -213,3 +213,33 @@ def test_hash_table_growth(gpu):
     k, v = fin.column(0).data, fin.column(1).data
     assert len(k) == n and set(v.tolist()) == {2}
     assert np.array_equal(np.sort(k), keys)
+
+
+def test_prefilter_exception_numbering(gpu):
+    """Selective pipeline -> prefilter launch + dense launch; exceptions raised in either launch must be
+    numbered exactly like one TransformTask numbers them (rows written + exceptions so far)."""
+    rng = np.random.default_rng(21)
+    words = ["7", "12", "x", "30", "", "9", "21", "70", "7 ", "5"]
+    n = 60_000
+    s = [words[i] for i in rng.integers(0, len(words), n)]
+    sc = frontend.StageCompiler([T_STR], ["s"])
+    sc.add_with_column("v", lambda x: int(x['s']), 100001)                    # ValueError rows (prefilter launch)
+    sc.add_filter(lambda x: x['v'] % 3 != 0, 100002)
+    sc.add_with_column("w", lambda x: ('%03d' % (100 // (x['v'] - 7))) + x['s'].replace('7', 'seven'), 100003)  # ZeroDivisionError
+    sc.add_with_column("u", lambda x: x['w'].upper() + '!' + x['s'], 100004)
+    prog = sc.finish_memory()
+    assert prog.prefilter is not None and prog.hidden_out_cols == 1
+    cols = [Column.from_values(s, T_STR)]
+    st, res, ora = run_both(prog, cols, n, first_row_no=5)
+    codes = set(ora.exceptions["code"].tolist())
+    assert codes == {135, 136}
+    assert_result_equals_oracle(res, ora, "prefilter exceptions")
+    assert res.exception_partition() == pyoracle.exception_partition(cols, ora.exceptions)
+    # same stage without the prefilter hint gives the same answer
+    sc2 = frontend.StageCompiler([T_STR], ["s"])
+    for name, a in sc.oplog:
+        getattr(sc2, name)(*a)
+    p2 = sc2.finish_memory(prefilter=False)
+    assert p2.prefilter is None
+    st2, res2, ora2 = run_both(p2, cols, n, first_row_no=5)
+    assert_result_equals_oracle(res2, ora, "no prefilter")

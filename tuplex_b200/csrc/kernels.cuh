@@ -42,7 +42,7 @@ struct AccP {
 struct KParams {
     uint64_t n_rows;
     int64_t first_row_no;
-    uint32_t n_instr, split_pc, n_slots, n_in, n_out, n_str_out, n_accs, R, n_tiles, scratch_per_thread;
+    uint32_t n_instr, pad_split, n_slots, n_in, n_out, n_str_out, n_accs, R, n_tiles, scratch_per_thread;
     uint32_t K;            // scan vector width = 2 + n_str_out
     uint32_t smem_regs_off, smem_stage_off, smem_misc_off, smem_cols_off;
     uint64_t cap_rows, cap_exc;
@@ -56,6 +56,8 @@ struct KParams {
     uint8_t *scratch;
     uint64_t *tile_partials;  // aggregate: n_tiles * n_accs
     uint64_t *agg_out;        // aggregate: n_accs
+    const uint64_t *rowlist;  // optional: evaluate these input rows only (output of a prefilter stage), ascending
+    uint64_t n_work;          // rows to evaluate: n_rows, or the length of rowlist
     ColIn in[TPLX_MAX_COLS];
     OutCol out[TPLX_MAX_COLS];
     AccP accs[TPLX_MAX_ACCS];
@@ -122,7 +124,7 @@ __device__ __forceinline__ bool bit_test(const uint32_t *bits, uint32_t lr) {
 // K1: rows in -> rows out
 // =============================================================================================
 // Shared memory map (byte offsets from KParams): prog | cols | regs | staging | misc
-// misc: keep_bits[W] exc_bits[W] keep_pre[W+1] exc_pre[W+1] exc_stage[T] surv[T] (u16) scan scratch
+// misc: keep_bits[W] exc_bits[W] keep_pre[W+1] exc_pre[W+1] exc_stage[T] scan scratch
 __global__ void __launch_bounds__(NT) stage_rows_kernel(const KParams *__restrict__ Pg) {
     extern __shared__ __align__(16) uint8_t smem[];
     const KParams &P = *Pg;
@@ -138,11 +140,10 @@ __global__ void __launch_bounds__(NT) stage_rows_kernel(const KParams *__restric
     uint32_t *keep_pre = exc_bits + W;
     uint32_t *exc_pre = keep_pre + W + 1;
     uint32_t *exc_stage = exc_pre + W + 1;
-    uint16_t *surv = reinterpret_cast<uint16_t *>(exc_stage + T);
-    uint64_t *s_vals = reinterpret_cast<uint64_t *>(surv + T + ((T & 3) ? 4 - (T & 3) : 0));  // K tile values
+    uint64_t *s_vals = reinterpret_cast<uint64_t *>(exc_stage + T);  // K tile values
     uint64_t *s_excl = s_vals + MAX_SCAN;                                                    // K exclusive prefixes
     uint64_t *s_warp = s_excl + MAX_SCAN;                                                    // NT/32 scan scratch
-    uint32_t *s_ctl = reinterpret_cast<uint32_t *>(s_warp + NT / 32 + 1);                     // [0] tile, [1] n_surv
+    uint32_t *s_ctl = reinterpret_cast<uint32_t *>(s_warp + NT / 32 + 1);                     // [0] tile
 
     // one-time: program + column table into shared memory
     for (uint32_t i = tid; i < P.n_instr * (sizeof(tplx_instr) / 16); i += NT)
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(NT) stage_rows_kernel(const KParams *__restric
         __syncthreads();
         const uint32_t tile = s_ctl[0];
         if (tile >= P.n_tiles) break;
-        const uint64_t base = (uint64_t)tile * T;
+        const uint64_t base = (uint64_t)tile * T;  // position in the work list (== input row without a rowlist)
         t.scr_used = 0;
 
         // ---- evaluate -----------------------------------------------------------------------
@@ -183,59 +184,22 @@ __global__ void __launch_bounds__(NT) stage_rows_kernel(const KParams *__restric
             }
         };
 
-        if (P.split_pc == 0) {
-            for (uint32_t s = 0; s < R; ++s) {
-                const uint32_t lr = s * NT + tid;
-                const uint64_t row = base + lr;
-                t.alive = row < P.n_rows;
-                t.exc_code = 0;
-                VM<NT>::run(s_prog, 0, P.n_instr, s_regs, s_cols, row, P.cpool, t);
-                const bool exc = t.exc_code != 0;
-                const uint32_t kb = __ballot_sync(0xFFFFFFFFu, t.alive);
-                const uint32_t eb = __ballot_sync(0xFFFFFFFFu, exc);
-                if (lane == 0) { keep_bits[lr >> 5] = kb; exc_bits[lr >> 5] = eb; }
-                if (t.alive) stage_row(lr);
-                if (exc) exc_stage[lr] = t.exc_code | (t.exc_op << 16);
-            }
-        } else {
-            // phase 1: selective prefix on every row, collect survivors
-            for (uint32_t s = 0; s < R; ++s) {
-                const uint32_t lr = s * NT + tid;
-                const uint64_t row = base + lr;
-                t.alive = row < P.n_rows;
-                t.exc_code = 0;
-                VM<NT>::run(s_prog, 0, P.split_pc, s_regs, s_cols, row, P.cpool, t);
-                const bool exc = t.exc_code != 0;
-                const uint32_t sb = __ballot_sync(0xFFFFFFFFu, t.alive);
-                const uint32_t eb = __ballot_sync(0xFFFFFFFFu, exc);
-                uint32_t wbase = 0;
-                if (lane == 0) {
-                    exc_bits[lr >> 5] = eb;
-                    if (sb) wbase = atomicAdd(&s_ctl[1], (uint32_t)__popc(sb));
-                }
-                wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
-                if (t.alive) surv[wbase + __popc(sb & ((1u << lane) - 1u))] = (uint16_t)lr;
-                if (exc) exc_stage[lr] = t.exc_code | (t.exc_op << 16);
-            }
-            __syncthreads();
-            // phase 2: whole program, densely, on survivors
-            const uint32_t n_surv = s_ctl[1];
-            t.scr_used = 0;
-            for (uint32_t i0 = 0; i0 < n_surv; i0 += NT) {
-                const uint32_t i = i0 + tid;
-                const bool valid = i < n_surv;
-                const uint32_t lr = valid ? surv[i] : 0;
-                t.alive = valid;
-                t.exc_code = 0;
-                VM<NT>::run(s_prog, 0, P.n_instr, s_regs, s_cols, base + lr, P.cpool, t);
-                if (t.alive) {
-                    atomicOr(&keep_bits[lr >> 5], 1u << (lr & 31));
-                    stage_row(lr);
-                }
-                if (t.exc_code != 0) {
-                    atomicOr(&exc_bits[lr >> 5], 1u << (lr & 31));
-                    exc_stage[lr] = t.exc_code | (t.exc_op << 16);
-                }
+        for (uint32_t s = 0; s < R; ++s) {
+            const uint32_t lr = s * NT + tid;
+            const uint64_t w = base + lr;
+            const bool valid = w < P.n_work;
+            const uint64_t row = P.rowlist ? (valid ? P.rowlist[w] : 0) : w;
+            t.alive = valid;
+            t.exc_code = 0;
+            VM<NT>::run(s_prog, 0, P.n_instr, s_regs, s_cols, row, P.cpool, t);
+            const bool exc = t.exc_code != 0;
+            const uint32_t kb = __ballot_sync(0xFFFFFFFFu, t.alive);
+            const uint32_t eb = __ballot_sync(0xFFFFFFFFu, exc);
+            if (lane == 0) { keep_bits[lr >> 5] = kb; exc_bits[lr >> 5] = eb; }
+            if (t.alive) stage_row(lr);
+            if (exc) {
+                exc_stage[lr] = t.exc_code | (t.exc_op << 16);
+
             }
         }
         __syncthreads();
@@ -263,9 +227,12 @@ __global__ void __launch_bounds__(NT) stage_rows_kernel(const KParams *__restric
                 s_vals[1] = ce;
             }
         }
+        __syncthreads();
+        const bool any_keep = s_vals[0] != 0;
+        if (!any_keep && tid < MAX_SCAN - 2) s_vals[2 + tid] = 0;
         // string bytes per output column: thread owns local rows [tid*R, tid*R+R)
         // (consecutive rows per thread so that one block scan yields in-order byte offsets)
-        for (uint32_t c = 0; c < P.n_out; ++c) {
+        for (uint32_t c = 0; any_keep && c < P.n_out; ++c) {
             const OutCol &oc = P.out[c];
             if (oc.strk < 0) continue;
             const uint64_t *st = reinterpret_cast<const uint64_t *>(s_stage + oc.stage_off);
@@ -390,7 +357,7 @@ __global__ void __launch_bounds__(NT) stage_rows_kernel(const KParams *__restric
                     const uint32_t ke = bit_rank(exc_bits, exc_pre, lr);
                     const uint32_t kk = bit_rank(keep_bits, keep_pre, lr);
                     tplx_exception_rec rec;
-                    rec.row = (int64_t)(base + lr);
+                    rec.row = (int64_t)(P.rowlist ? P.rowlist[base + lr] : base + lr);
                     // _outputRowCounter semantics: rows written + exceptions so far (TransformTask.cc:764,885)
                     rec.row_no = P.first_row_no + (int64_t)(pre_keep + pre_exc + kk + ke);
                     const uint32_t es = exc_stage[lr];

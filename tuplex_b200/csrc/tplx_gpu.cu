@@ -152,6 +152,9 @@ struct tplx_stage {
     // adaptive output capacities learnt from earlier blocks (bytes per input row per str out col)
     std::vector<double> est_bytes_per_row;
     double est_exc_per_row = 0.0;
+    tplx_stage *prefilter = nullptr;  // nested selective stage (row index output), may be null
+    bool prefilter_enabled = true;    // switched off at run time when it turns out not to be selective
+    uint32_t hidden = 0;              // trailing executor-internal output columns
     std::mutex mu;
 };
 
@@ -165,6 +168,7 @@ extern "C" int32_t tplx_gpu_stage_create(const void *desc, uint64_t desc_bytes, 
     if (h.magic != TPLX_IR_MAGIC) return fail(TPLX_E_BADDESC, "stage descriptor: bad magic");
     if (h.version != TPLX_IR_VERSION) return fail(TPLX_E_BADDESC, "stage descriptor: version mismatch");
     if (h.total_bytes != desc_bytes) return fail(TPLX_E_BADDESC, "stage descriptor: size mismatch");
+    if (desc_bytes < sizeof(h) + h.prefilter_bytes) return fail(TPLX_E_BADDESC, "stage descriptor: prefilter size");
     if (h.n_in_cols > TPLX_MAX_COLS || h.n_out_cols > TPLX_MAX_COLS || h.n_accs > TPLX_MAX_ACCS || h.n_keys > TPLX_MAX_KEYS)
         return fail(TPLX_E_BADDESC, "stage descriptor: too many columns/accumulators");
     size_t off = sizeof(h);
@@ -229,7 +233,18 @@ extern "C" int32_t tplx_gpu_stage_create(const void *desc, uint64_t desc_bytes, 
         if (in.op >= TPLX_OP_SLEN && in.op <= TPLX_OP_SSTRIP) s->has_str = true;
         if (in.op == TPLX_OP_LDS) s->has_str = true;
     }
-    if (h.split_pc > h.n_instr) return bad("program: split_pc out of range");
+    if (h.hidden_out_cols > h.n_out_cols) return bad("stage descriptor: hidden_out_cols out of range");
+    s->hidden = h.hidden_out_cols;
+    if (h.prefilter_bytes) {
+        if (!need(h.prefilter_bytes) || h.endpoint != TPLX_EP_MEMORY) return bad("stage descriptor: bad prefilter section");
+        int32_t prc = tplx_gpu_stage_create(p + off, h.prefilter_bytes, &s->prefilter);
+        if (prc) { delete s; return prc; }
+        tplx_stage *q = s->prefilter;
+        if (q->prefilter || q->hdr.endpoint != TPLX_EP_MEMORY || q->out_cols.size() != 1 || q->out_cols[0].type != TPLX_T_I64 ||
+            q->in_types != s->in_types || !s->hidden)
+            return bad("stage descriptor: prefilter must be a row-index MEMORY stage over the same input schema");
+        off += h.prefilter_bytes;
+    }
     for (auto t : s->in_types) {
         if (t > TPLX_T_STR) return bad("stage descriptor: unknown input type");
         if (t == TPLX_T_STR) s->has_str = true;
@@ -280,6 +295,7 @@ extern "C" int32_t tplx_gpu_stage_destroy(tplx_stage *s) {
         cudaFree(sd.opids);
         if (sd.ht) hash_table_destroy(sd.ht);
     }
+    if (s->prefilter) tplx_gpu_stage_destroy(s->prefilter);
     delete s;
     return TPLX_OK;
 }
@@ -377,7 +393,8 @@ struct tplx_result {
     uint32_t n_accs = 0;
     std::vector<void *> owned;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
-    double kernel_ms = 0, total_ms = 0;
+    double kernel_ms = 0, total_ms = 0, kernel_ms_extra = 0;
+    uint32_t hidden = 0;  // trailing internal output columns
     uint32_t launches = 0;
     bool owns_block = false;
     tplx_block *owned_block = nullptr;
@@ -419,7 +436,7 @@ static Layout make_layout(const tplx_stage *s, uint32_t R, bool rows_ep) {
         }
         off = align_up(off + so, 16);
         L.misc_off = (uint32_t)off;
-        off += (size_t)(4 * W + 2 + T) * 4 + (size_t)T * 2 + (size_t)(2 * MAX_SCAN + NT / 32 + 1) * 8 + 16;
+        off += (size_t)(4 * W + 2 + T) * 4 + (size_t)(2 * MAX_SCAN + NT / 32 + 1) * 8 + 16;
     } else {
         L.misc_off = (uint32_t)off;
         off += (size_t)(NT / 32) * std::max<size_t>(s->accs.size(), 1) * 8;
@@ -439,7 +456,9 @@ static int32_t ensure_scratch(Device *d, size_t bytes) {
     return TPLX_OK;
 }
 
-static int32_t run_rows(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_t first_row_no, tplx_result *r);
+static int32_t run_rows(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_t first_row_no, tplx_result *r,
+                        const uint64_t *rowlist, uint64_t n_list);
+static int32_t run_rows_prefiltered(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_t first_row_no, tplx_result *r);
 static int32_t run_agg(tplx_stage *s, StageDev *sd, const tplx_block *b, tplx_result *r);
 static int32_t run_hash(tplx_stage *s, StageDev *sd, const tplx_block *b, tplx_result *r);
 
@@ -465,7 +484,10 @@ extern "C" int32_t tplx_gpu_stage_run(tplx_stage *s, const tplx_block *b, int64_
     CU(cudaEventCreate(&r->evk1));
     CU(cudaEventRecord(r->ev0, d->stream));
     switch (s->hdr.endpoint) {
-        case TPLX_EP_MEMORY: rc = run_rows(s, sd, b, first_row_no, r); break;
+        case TPLX_EP_MEMORY:
+            rc = (s->prefilter && s->prefilter_enabled) ? run_rows_prefiltered(s, sd, b, first_row_no, r)
+                                                         : run_rows(s, sd, b, first_row_no, r, nullptr, 0);
+            break;
         case TPLX_EP_AGGREGATE: rc = run_agg(s, sd, b, r); break;
         default: rc = run_hash(s, sd, b, r); break;
     }
@@ -505,13 +527,14 @@ static int32_t fill_common(KParams &P, tplx_stage *s, StageDev *sd, const tplx_b
     memset(&P, 0, sizeof(P));
     P.n_rows = b->n_rows;
     P.n_instr = (uint32_t)s->instrs.size();
-    P.split_pc = s->hdr.split_pc;
     P.n_slots = s->hdr.n_slots;
     P.n_in = (uint32_t)s->in_types.size();
     P.n_out = (uint32_t)s->out_cols.size();
     P.n_str_out = s->n_str_out;
     P.n_accs = (uint32_t)s->accs.size();
     P.R = R;
+    P.n_work = b->n_rows;
+    P.rowlist = nullptr;
     P.n_tiles = (uint32_t)((b->n_rows + (uint64_t)R * NT - 1) / ((uint64_t)R * NT));
     P.K = 2 + s->n_str_out;
     P.smem_cols_off = L.cols_off;
@@ -539,14 +562,18 @@ static int32_t dalloc(tplx_result *r, T **p, size_t count) {
     return TPLX_OK;
 }
 
-static int32_t run_rows(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_t first_row_no, tplx_result *r) {
+static int32_t run_rows(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_t first_row_no, tplx_result *r,
+                        const uint64_t *rowlist, uint64_t n_list) {
     Device *d = sd->dev;
-    const uint64_t n = b->n_rows;
+    const uint64_t n = rowlist ? n_list : b->n_rows;  // rows to evaluate
+    r->hidden = s->hidden;
     r->out_types.clear();
     for (auto &oc : s->out_cols) r->out_types.push_back(oc.type);
     r->str_bytes.assign(s->out_cols.size(), 0);
     r->out.assign(s->out_cols.size(), OutCol{});
     if (n == 0) {
+        CU(cudaEventRecord(r->evk0, d->stream));
+        CU(cudaEventRecord(r->evk1, d->stream));
         for (size_t c = 0; c < s->out_cols.size(); ++c)
             if (s->out_cols[c].type == TPLX_T_STR) {
                 int32_t rc = dalloc(r, &r->out[c].offsets, 1);
@@ -569,6 +596,9 @@ static int32_t run_rows(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_
     if (occ < 1) return fail(TPLX_E_UNSUPPORTED, "stage kernel cannot be resident");
     KParams P;
     fill_common(P, s, sd, b, L, R);
+    P.rowlist = rowlist;
+    P.n_work = n;
+    P.n_tiles = (uint32_t)((n + (uint64_t)R * NT - 1) / ((uint64_t)R * NT));
     const uint32_t grid = std::min<uint32_t>(P.n_tiles, (uint32_t)(occ * d->prop.multiProcessorCount));
     P.first_row_no = first_row_no;
     P.scratch_per_thread = s->materialises ? std::max<uint32_t>(s->hdr.scratch_bytes, 64) * R : 0;
@@ -669,6 +699,63 @@ static int32_t run_rows(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_
     return TPLX_OK;
 }
 
+// Selective pipelines: (1) prefilter stage over every row -> ascending list of surviving row indices,
+// (2) this stage densely over that list. Exception rows of both launches are merged and numbered like one
+// TransformTask would have numbered them (rows written + exceptions so far, TransformTask.cc:764,885).
+static int32_t run_rows_prefiltered(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_t first_row_no, tplx_result *r) {
+    Device *d = sd->dev;
+    tplx_stage *ps = s->prefilter;
+    StageDev *psd = nullptr;
+    int32_t rc = stage_dev(ps, d, &psd);
+    if (rc) return rc;
+    tplx_result ra;
+    ra.dev = d;
+    ra.stage = ps;
+    CU(cudaEventCreate(&ra.evk0));
+    CU(cudaEventCreate(&ra.evk1));
+    auto drop_ra = [&]() {
+        for (void *p : ra.owned) cudaFreeAsync(p, d->stream);
+        ra.owned.clear();
+        cudaEventDestroy(ra.evk0);
+        cudaEventDestroy(ra.evk1);
+    };
+    rc = run_rows(ps, psd, b, 0, &ra, nullptr, 0);
+    if (rc) { drop_ra(); return rc; }
+    float msa = 0;
+    CU(cudaEventElapsedTime(&msa, ra.evk0, ra.evk1));  // run_rows synchronised the stream already
+    const uint64_t n_surv = ra.n_out;
+    if (b->n_rows >= (1u << 16) && n_surv * 2 > b->n_rows) s->prefilter_enabled = false;  // not selective: stop using it
+    rc = run_rows(s, sd, b, first_row_no, r, ra.out[0].data, n_surv);
+    if (rc) { drop_ra(); return rc; }
+    r->kernel_ms_extra = msa;
+    r->launches += ra.launches;
+    const uint64_t na = ra.n_exc, nb = r->n_exc;
+    if (na) {
+        std::vector<tplx_exception_rec> ea(na), eb(nb), merged;
+        CU(cudaMemcpy(ea.data(), ra.exc, na * sizeof(tplx_exception_rec), cudaMemcpyDeviceToHost));
+        if (nb) CU(cudaMemcpy(eb.data(), r->exc, nb * sizeof(tplx_exception_rec), cudaMemcpyDeviceToHost));
+        // input row index of every output row (hidden last column), ascending
+        std::vector<int64_t> out_rows(r->n_out);
+        if (r->n_out) CU(cudaMemcpy(out_rows.data(), r->out.back().data, r->n_out * 8, cudaMemcpyDeviceToHost));
+        // B numbered its exceptions within its own stream: rows written before + index among B's exceptions
+        for (uint64_t i = 0; i < nb; ++i) eb[i].row_no = eb[i].row_no - first_row_no - (int64_t)i;  // = rows written before
+        for (uint64_t i = 0; i < na; ++i)
+            ea[i].row_no = (int64_t)(std::lower_bound(out_rows.begin(), out_rows.end(), ea[i].row) - out_rows.begin());
+        merged.resize(na + nb);
+        std::merge(ea.begin(), ea.end(), eb.begin(), eb.end(), merged.begin(),
+                   [](const tplx_exception_rec &x, const tplx_exception_rec &y) { return x.row < y.row; });
+        for (uint64_t i = 0; i < merged.size(); ++i) merged[i].row_no += first_row_no + (int64_t)i;
+        tplx_exception_rec *dm = nullptr;
+        rc = dalloc(r, &dm, merged.size());
+        if (rc) { drop_ra(); return rc; }
+        CU(cudaMemcpy(dm, merged.data(), merged.size() * sizeof(tplx_exception_rec), cudaMemcpyHostToDevice));
+        r->exc = dm;
+        r->n_exc = merged.size();
+    }
+    drop_ra();
+    return TPLX_OK;
+}
+
 static int32_t run_agg(tplx_stage *s, StageDev *sd, const tplx_block *b, tplx_result *r) {
     Device *d = sd->dev;
     const uint64_t n = b->n_rows;
@@ -744,7 +831,7 @@ extern "C" int32_t tplx_gpu_result_info(tplx_result *r, tplx_result_info *info) 
     CU(cudaEventSynchronize(r->ev1));
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, r->evk0, r->evk1));
-    r->kernel_ms = ms;
+    r->kernel_ms = ms + r->kernel_ms_extra;
     CU(cudaEventElapsedTime(&ms, r->ev0, r->ev1));
     r->total_ms = ms;
     memset(info, 0, sizeof(*info));
@@ -759,7 +846,7 @@ extern "C" int32_t tplx_gpu_result_info(tplx_result *r, tplx_result_info *info) 
 }
 
 extern "C" int32_t tplx_gpu_result_fetch_column(tplx_result *r, uint32_t col, void *data, uint32_t *offsets) {
-    if (!r || col >= r->out.size()) return fail(TPLX_E_BADARG, "result_fetch_column: bad arguments");
+    if (!r || col + r->hidden >= r->out.size()) return fail(TPLX_E_BADARG, "result_fetch_column: bad arguments");
     CU(cudaSetDevice(r->dev->id));
     const OutCol &oc = r->out[col];
     if (r->out_types[col] == TPLX_T_STR) {
@@ -773,7 +860,7 @@ extern "C" int32_t tplx_gpu_result_fetch_column(tplx_result *r, uint32_t col, vo
 }
 
 extern "C" int32_t tplx_gpu_result_device_column(tplx_result *r, uint32_t col, const void **data, const uint32_t **offsets) {
-    if (!r || col >= r->out.size()) return fail(TPLX_E_BADARG, "result_device_column: bad arguments");
+    if (!r || col + r->hidden >= r->out.size()) return fail(TPLX_E_BADARG, "result_device_column: bad arguments");
     const OutCol &oc = r->out[col];
     if (r->out_types[col] == TPLX_T_STR) {
         if (data) *data = oc.bytes;

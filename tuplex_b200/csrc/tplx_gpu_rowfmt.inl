@@ -135,7 +135,7 @@ extern "C" int32_t tplx_gpu_block_from_partitions(int32_t device, const uint8_t 
 
 static void result_rowfmt(const tplx_result *r, RowFmtCols &C) {
     memset(&C, 0, sizeof(C));
-    C.n_cols = (uint32_t)r->out.size();
+    C.n_cols = (uint32_t)(r->out.size() - r->hidden);
     for (uint32_t c = 0; c < C.n_cols; ++c) {
         C.types[c] = r->out_types[c];
         if (C.types[c] == TPLX_T_STR) {

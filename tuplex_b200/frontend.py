@@ -167,7 +167,8 @@ class StageCompiler:
         self._col_cache: Dict[int, Val] = {}
         self.cur_op = 0
         self.guard: Optional[int] = None  # vreg of current guard
-        self.filters: List[int] = []      # pcs of FILTER instructions
+        self.filters: List[Tuple[int, int]] = []  # (pc after the FILTER instruction, number of logged operators incl. it)
+        self.oplog: List[Tuple[str, tuple]] = []  # operators in order, so that a prefix can be replayed (prefilter stage)
         for c, t in enumerate(in_types):
             self.row.append(Val(t, None, ("col", c)))  # lazily loaded column reference
 
@@ -326,6 +327,7 @@ class StageCompiler:
         return fc.run(argnames, args_vals, body)
 
     def add_map(self, func, op_id: int):
+        self.oplog.append(("add_map", (func, op_id)))
         self.begin_op(op_id)
         res = self._call_udf(func, [self.row_value()])
         if isinstance(res, TupleVal):
@@ -340,11 +342,12 @@ class StageCompiler:
             self.row, self.names = [res], [None]
 
     def add_filter(self, func, op_id: int):
+        self.oplog.append(("add_filter", (func, op_id)))
         self.begin_op(op_id)
         res = self.truth(self._call_udf(func, [self.row_value()]))
         self.guard = None
         self.emit(C["TPLX_OP_FILTER"], a=self.reg(res))
-        self.filters.append(len(self.prog.instrs))
+        self.filters.append((len(self.prog.instrs), len(self.oplog)))
 
     def col_index(self, key) -> int:
         if isinstance(key, int):
@@ -356,6 +359,7 @@ class StageCompiler:
         return self.names.index(key)
 
     def add_with_column(self, name: str, func, op_id: int):
+        self.oplog.append(("add_with_column", (name, func, op_id)))
         self.begin_op(op_id)
         res = self._call_udf(func, [self.row_value()])
         if isinstance(res, TupleVal):
@@ -367,6 +371,7 @@ class StageCompiler:
             self.names.append(name)
 
     def add_map_column(self, name, func, op_id: int):
+        self.oplog.append(("add_map_column", (name, func, op_id)))
         self.begin_op(op_id)
         i = self.col_index(name)
         res = self._call_udf(func, [self.row[i]])
@@ -375,12 +380,14 @@ class StageCompiler:
         self.row[i] = res
 
     def add_select(self, cols: Sequence[Union[int, str]], op_id: int):
+        self.oplog.append(("add_select", (cols, op_id)))
         self.begin_op(op_id)
         idx = [self.col_index(c) for c in cols]
         self.row = [self.row[i] for i in idx]
         self.names = [self.names[i] for i in idx]
 
     def add_rename(self, old, new: str, op_id: int):
+        self.oplog.append(("add_rename", (old, new, op_id)))
         self.begin_op(op_id)
         self.names[self.col_index(old)] = new
 
@@ -391,30 +398,47 @@ class StageCompiler:
         slots = self._regalloc(regs)
         return slots
 
-    def finish_memory(self, selective_hint: Optional[float] = None) -> Program:
+    def finish_memory(self, prefilter: bool = True) -> Program:
         self.prog.endpoint = C["TPLX_EP_MEMORY"]
+        n_user = len(self.row)
+        k = self._choose_split() if prefilter else 0
+        if k:
+            # selective pipeline: a prefilter stage finds the surviving rows, this stage then runs densely over
+            # them. The hidden trailing column (input row index of each output row) lets the executor number
+            # exception rows across the two launches.
+            pre = StageCompiler(self.prog.in_types, self.prog.in_names)
+            for name, a in self.oplog[:k]:
+                getattr(pre, name)(*a)
+            pre.begin_op(self.oplog[k - 1][1][-1])
+            d = pre.new_vreg(T_I64)
+            pre.emit(C["TPLX_OP_LDROW"], d)
+            pre.row, pre.names = [Val(T_I64, d)], ["__row"]
+            self.prog.prefilter = pre.finish_memory(prefilter=False)
+            self.begin_op(self.oplog[-1][1][-1] if self.oplog else 0)
+            d = self.new_vreg(T_I64)
+            self.emit(C["TPLX_OP_LDROW"], d)
+            self.row.append(Val(T_I64, d))
+            self.names.append("__row")
+            self.prog.hidden_out_cols = 1
         slots = self._finish(self.row)
         self.prog.out_cols = [(s, v.type) for s, v in zip(slots, self.row)]
-        self.prog.out_names = list(self.names)
-        self._choose_split()
+        self.prog.out_names = list(self.names[:n_user])
+        if k:
+            self.row.pop()
+            self.names.pop()
         return self.prog
 
-    def _choose_split(self):
-        """Split after the last filter when later work is heavy: rows are evaluated up to the split,
-        survivors are compacted inside the tile, and only they run the rest densely."""
-        if not self.filters:
-            return
-        pc = self.filters[-1]
+    def _choose_split(self) -> int:
+        """Number of leading operators to put into a prefilter stage (0 = none): the last filter that still has
+        heavy work behind it. Late materialisation: everything behind it only touches surviving rows."""
         heavy = {C[k] for k in ("TPLX_OP_SREPLACE", "TPLX_OP_SCONCAT", "TPLX_OP_SFMTD", "TPLX_OP_SFIND", "TPLX_OP_SRFIND",
                                 "TPLX_OP_S2I", "TPLX_OP_SIN", "TPLX_OP_I2S")}
-        # candidate split points: after each filter; pick the last one that still has heavy work behind it
         best = 0
-        for f in self.filters:
-            rest = self.prog.instrs[f:]
-            if sum(1 for i in rest if i.op in heavy) >= 2 or len(rest) >= 24:
-                best = f
-        if best and best < len(self.prog.instrs):
-            self.prog.split_pc = best
+        for pc, nops in self.filters:
+            rest = self.prog.instrs[pc:]
+            if rest and (sum(1 for i in rest if i.op in heavy) >= 2 or len(rest) >= 24):
+                best = nops
+        return best
 
     def finish_aggregate(self, agg_func, combine_func, init, op_id: int) -> Program:
         """aggregate(combine, agg, init) -> AGG_GENERAL endpoint (AggregateFunctions.cc:16-243)."""

@@ -35,8 +35,8 @@ OP_NAMES = {v: k[len("TPLX_OP_"):] for k, v in C.items() if k.startswith("TPLX_O
 
 INSTR_FMT = "<BBHHHHHHHqq"  # 32 bytes
 assert struct.calcsize(INSTR_FMT) == 32
-HEADER_FMT = "<IIIHHHHHHIIBBHI"
-assert struct.calcsize(HEADER_FMT) == 40
+HEADER_FMT = "<IIIHHHHHHIIBBHIII"
+assert struct.calcsize(HEADER_FMT) == 48
 
 
 @dataclass
@@ -85,7 +85,8 @@ class Program:
     opids: List[int] = field(default_factory=list)
     n_slots: int = 0
     endpoint: int = 0
-    split_pc: int = 0
+    hidden_out_cols: int = 0
+    prefilter: Optional["Program"] = None  # selective leading part, output = surviving row indices
     scratch_bytes: int = 256
     _cpool_index: Dict[bytes, int] = field(default_factory=dict)
 
@@ -111,14 +112,17 @@ class Program:
         body += b"".join(struct.pack("<q", o) for o in self.opids)
         body += b"".join(i.pack() for i in self.instrs)
         body += pad8(bytes(self.cpool))
+        pre = self.prefilter.serialize() if self.prefilter is not None else b""
+        body += pre
         total = struct.calcsize(HEADER_FMT) + len(body)
         hdr = struct.pack(HEADER_FMT, C["TPLX_IR_MAGIC"], C["TPLX_IR_VERSION"], total, len(self.in_types),
                           len(self.out_cols), len(self.accs), self.n_keys, len(self.opids), self.n_slots,
-                          len(self.instrs), len(self.cpool), self.endpoint, 0, self.split_pc, self.scratch_bytes)
+                          len(self.instrs), len(self.cpool), self.endpoint, 0, self.hidden_out_cols, self.scratch_bytes,
+                          len(pre), 0)
         return hdr + body
 
     def dump(self) -> str:
-        lines = [f"in: {[TYPE_NAMES[t] for t in self.in_types]} slots={self.n_slots} split_pc={self.split_pc}"]
+        lines = [f"in: {[TYPE_NAMES[t] for t in self.in_types]} slots={self.n_slots} prefilter={self.prefilter is not None}"]
         for i, ins in enumerate(self.instrs):
             lines.append(f"{i:4d}: {ins!r}")
         lines.append(f"out: {[(s, TYPE_NAMES[t]) for s, t in self.out_cols]} accs={self.accs} keys={self.n_keys}")
