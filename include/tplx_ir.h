@@ -24,7 +24,7 @@ extern "C" {
 #endif
 
 #define TPLX_IR_MAGIC 0x58504C54u /* "TPLX" */
-#define TPLX_IR_VERSION 4u
+#define TPLX_IR_VERSION 5u
 #define TPLX_NOSLOT 0xFFFFu
 #define TPLX_MAX_COLS 64
 #define TPLX_MAX_ACCS 16
@@ -72,6 +72,15 @@ enum tplx_strflag {
     TPLX_SF_UPPER = 2,
 };
 
+/* operand-is-constant bits of tplx_instr.flags (upper three bits; the low bits stay op specific).
+ * A constant operand is not read from a slot: scalars are the immediate itself, strings are
+ * constant-pool views encoded as offset | length << 32.  a <- imm2, b <- imm, c <- imm2. */
+enum tplx_constflag {
+    TPLX_F_C_CONST = 32,
+    TPLX_F_A_CONST = 64,
+    TPLX_F_B_CONST = 128,
+};
+
 /* slice flags (BlockGeneratorVisitor.cc:4469-4690; stride is always 1 on this path) */
 enum tplx_sliceflag {
     TPLX_SL_HAS_START = 1,
@@ -91,7 +100,7 @@ enum tplx_exception_code {
 };
 
 /*
- * Opcodes. A value lives in 8-byte slots: scalars (i64 / f64 bits / bool 0-1) take one slot,
+ * Opcodes (dense numbering: the VM dispatches through a jump table). A value lives in 8-byte slots: scalars (i64 / f64 bits / bool 0-1) take one slot,
  * strings take two consecutive slots: [s] = byte address (generic pointer), [s+1] = len | flags<<32.
  * Every instruction is predicated: it executes for a row iff the row is alive and
  * (guard == TPLX_NOSLOT or slot[guard] != 0). Python if/elif/else and early returns are
@@ -107,60 +116,60 @@ enum tplx_op {
     TPLX_OP_SEL = 5,    /* dst <- c ? a : b ; flags = slot count (1|2) */
     TPLX_OP_LDROW = 6,  /* dst <- index of this row inside the block (used to merge CPython-resolved rows in order) */
     /* i64 arithmetic: wrapping, no overflow detection (BlockGeneratorVisitor.cc:152-313,372-495) */
-    TPLX_OP_IADD = 10,
-    TPLX_OP_ISUB = 11,
-    TPLX_OP_IMUL = 12,
-    TPLX_OP_IFLOORDIV = 13, /* ZeroDivisionError; floor fix-up (LLVMEnvironment.cc:1377-1399) */
-    TPLX_OP_IMOD = 14,      /* ZeroDivisionError; floor fix-up (LLVMEnvironment.cc:1402-1430) */
-    TPLX_OP_INEG = 15,
-    TPLX_OP_IAND = 16,
-    TPLX_OP_IOR = 17,
-    TPLX_OP_IXOR = 18,
-    TPLX_OP_ISHL = 19, /* BlockGeneratorVisitor.cc:612-670 */
-    TPLX_OP_ISHR = 20,
-    TPLX_OP_IABS = 21,
+    TPLX_OP_IADD = 7,
+    TPLX_OP_ISUB = 8,
+    TPLX_OP_IMUL = 9,
+    TPLX_OP_IFLOORDIV = 10, /* ZeroDivisionError; floor fix-up (LLVMEnvironment.cc:1377-1399) */
+    TPLX_OP_IMOD = 11,      /* ZeroDivisionError; floor fix-up (LLVMEnvironment.cc:1402-1430) */
+    TPLX_OP_INEG = 12,
+    TPLX_OP_IAND = 13,
+    TPLX_OP_IOR = 14,
+    TPLX_OP_IXOR = 15,
+    TPLX_OP_ISHL = 16, /* BlockGeneratorVisitor.cc:612-670 */
+    TPLX_OP_ISHR = 17,
+    TPLX_OP_IABS = 18,
     /* f64 arithmetic: single IEEE-754 ops, no contraction (BlockGeneratorVisitor.cc:152-584) */
-    TPLX_OP_FADD = 30,
-    TPLX_OP_FSUB = 31,
-    TPLX_OP_FMUL = 32,
-    TPLX_OP_FDIV = 33,      /* ZeroDivisionError when divisor == 0.0 (divisionInst :497-530) */
-    TPLX_OP_FMOD = 34,      /* frem + sign fix (LLVMEnvironment.cc:1415-1422); ZeroDivisionError */
-    TPLX_OP_FNEG = 35,
-    TPLX_OP_FFLOORDIV = 36, /* both sides fptosi, floor-div, sitofp (integerDivisionInst :360-365) */
-    TPLX_OP_FABS = 37,
+    TPLX_OP_FADD = 19,
+    TPLX_OP_FSUB = 20,
+    TPLX_OP_FMUL = 21,
+    TPLX_OP_FDIV = 22,      /* ZeroDivisionError when divisor == 0.0 (divisionInst :497-530) */
+    TPLX_OP_FMOD = 23,      /* frem + sign fix (LLVMEnvironment.cc:1415-1422); ZeroDivisionError */
+    TPLX_OP_FNEG = 24,
+    TPLX_OP_FFLOORDIV = 25, /* both sides fptosi, floor-div, sitofp (integerDivisionInst :360-365) */
+    TPLX_OP_FABS = 26,
     /* conversions (FunctionRegistry.cc:83-148, upCast) */
-    TPLX_OP_I2F = 40, /* sitofp */
-    TPLX_OP_F2I = 41, /* fptosi (trunc) — int(f64) */
+    TPLX_OP_I2F = 27, /* sitofp */
+    TPLX_OP_F2I = 28, /* fptosi (trunc) — int(f64) */
     /* comparisons -> bool; flags = tplx_cmp */
-    TPLX_OP_ICMP = 50,
-    TPLX_OP_FCMP = 51,
+    TPLX_OP_ICMP = 29,
+    TPLX_OP_FCMP = 30,
     /* logical on 0/1 values */
-    TPLX_OP_BAND = 55,
-    TPLX_OP_BOR = 56,
-    TPLX_OP_BNOT = 57,
+    TPLX_OP_BAND = 31,
+    TPLX_OP_BOR = 32,
+    TPLX_OP_BNOT = 33,
     /* strings (ASCII bytes; FunctionRegistry.cc / runtime/src/Runtime.cc / StringFunctions.cc) */
-    TPLX_OP_SLEN = 60,     /* len(s) */
-    TPLX_OP_SFIND = 61,    /* s.find(b): strstr (FunctionRegistry.cc:2165-2188); -1 if absent */
-    TPLX_OP_SRFIND = 62,   /* s.rfind(b): std::string::rfind (Runtime.cc:387-397) */
-    TPLX_OP_SIN = 63,      /* a in b -> strstr(b, a) != NULL (BlockGeneratorVisitor.cc:838-880) */
-    TPLX_OP_SEQ = 64,      /* strcmp == 0 ; flags bit0 = negate (!=) */
-    TPLX_OP_SSLICE = 65,   /* a[b:c], flags = tplx_sliceflag (processSliceIndex :4618-4690) */
-    TPLX_OP_SINDEX = 66,   /* a[b] one-char string; IndexError (BlockGeneratorVisitor.cc:3869-3903) */
-    TPLX_OP_SLOWER = 67,   /* lazy flag (StringFunctions.cc:71-89) */
-    TPLX_OP_SUPPER = 68,   /* lazy flag (StringFunctions.cc:91-108) */
-    TPLX_OP_SREPLACE = 69, /* a.replace(b, c), materialises (Runtime.cc:401-540) */
-    TPLX_OP_SCONCAT = 70,  /* a + b, materialises (BlockGeneratorVisitor.cc:381-436) */
-    TPLX_OP_SFMTD = 71,    /* '%[0][w]d' % a : snprintf %d of (int)a, imm=width, flags bit0=zero pad,
+    TPLX_OP_SLEN = 34,     /* len(s) */
+    TPLX_OP_SFIND = 35,    /* s.find(b): strstr (FunctionRegistry.cc:2165-2188); -1 if absent */
+    TPLX_OP_SRFIND = 36,   /* s.rfind(b): std::string::rfind (Runtime.cc:387-397) */
+    TPLX_OP_SIN = 37,      /* a in b -> strstr(b, a) != NULL (BlockGeneratorVisitor.cc:838-880) */
+    TPLX_OP_SEQ = 38,      /* strcmp == 0 ; flags bit0 = negate (!=) */
+    TPLX_OP_SSLICE = 39,   /* a[b:c], flags = tplx_sliceflag (processSliceIndex :4618-4690) */
+    TPLX_OP_SINDEX = 40,   /* a[b] one-char string; IndexError (BlockGeneratorVisitor.cc:3869-3903) */
+    TPLX_OP_SLOWER = 41,   /* lazy flag (StringFunctions.cc:71-89) */
+    TPLX_OP_SUPPER = 42,   /* lazy flag (StringFunctions.cc:91-108) */
+    TPLX_OP_SREPLACE = 43, /* a.replace(b, c), materialises (Runtime.cc:401-540) */
+    TPLX_OP_SCONCAT = 44,  /* a + b, materialises (BlockGeneratorVisitor.cc:381-436) */
+    TPLX_OP_SFMTD = 45,    /* '%[0][w]d' % a : snprintf %d of (int)a, imm=width, flags bit0=zero pad,
                               constant prefix/suffix via b/c string slots (BlockGeneratorVisitor.cc:675-775) */
-    TPLX_OP_S2I = 72,      /* int(s): fast_atoi64 (Runtime.cc:319-341, StringUtils.cc:22-63); ValueError */
-    TPLX_OP_STRUTH = 73,   /* bool(s): len > 0 */
-    TPLX_OP_SSTARTS = 74,  /* a.startswith(b) */
-    TPLX_OP_SENDS = 75,    /* a.endswith(b) */
-    TPLX_OP_I2S = 76,      /* str(i64), materialises */
-    TPLX_OP_SSTRIP = 77,   /* a.strip() whitespace view; flags bit0 = left, bit1 = right */
+    TPLX_OP_S2I = 46,      /* int(s): fast_atoi64 (Runtime.cc:319-341, StringUtils.cc:22-63); ValueError */
+    TPLX_OP_STRUTH = 47,   /* bool(s): len > 0 */
+    TPLX_OP_SSTARTS = 48,  /* a.startswith(b) */
+    TPLX_OP_SENDS = 49,    /* a.endswith(b) */
+    TPLX_OP_I2S = 50,      /* str(i64), materialises */
+    TPLX_OP_SSTRIP = 51,   /* a.strip() whitespace view; flags bit0 = left, bit1 = right */
     /* row control */
-    TPLX_OP_FILTER = 90, /* alive &= slot[a] != 0 (PipelineBuilder.cc:615-700) */
-    TPLX_OP_RAISE = 91,  /* unconditional (guarded) exception imm = code */
+    TPLX_OP_FILTER = 52, /* alive &= slot[a] != 0 (PipelineBuilder.cc:615-700) */
+    TPLX_OP_RAISE = 53,  /* unconditional (guarded) exception imm = code */
 };
 
 /* 32-byte instruction */

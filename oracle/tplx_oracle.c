@@ -284,6 +284,24 @@ static int eval_row(const ostage *S, const tplx_ocol *cols, uint64_t row, oval *
         const oval *a = in->a != TPLX_NOSLOT ? &regs[in->a] : NULL;
         const oval *b = in->b != TPLX_NOSLOT ? &regs[in->b] : NULL;
         const oval *c = in->c != TPLX_NOSLOT ? &regs[in->c] : NULL;
+        /* constant operands (TPLX_F_*_CONST): scalars are the immediate, strings are constant-pool views
+         * (offset | length << 32) that the reference would hold as NUL-terminated global strings */
+        oval ka, kb, kc;
+        if (in->flags & (TPLX_F_A_CONST | TPLX_F_B_CONST | TPLX_F_C_CONST)) {
+            const int op = in->op;
+            const int strsel = (op == TPLX_OP_SEL || op == TPLX_OP_MOV) && (in->flags & 3) == 2;
+            const int a_str = strsel || (op >= TPLX_OP_SLEN && op <= TPLX_OP_SSTRIP && op != TPLX_OP_SFMTD && op != TPLX_OP_I2S);
+            const int b_str = strsel || op == TPLX_OP_SFIND || op == TPLX_OP_SRFIND || op == TPLX_OP_SIN || op == TPLX_OP_SEQ ||
+                              op == TPLX_OP_SSTARTS || op == TPLX_OP_SENDS || op == TPLX_OP_SCONCAT || op == TPLX_OP_SREPLACE;
+            const int c_str = op == TPLX_OP_SREPLACE;
+#define KONST(dst, enc, is_str) do { if (is_str) { (dst).len = (int64_t)((uint64_t)(enc) >> 32); \
+                (dst).s = dup_n(A, (const char *)S->cpool + ((uint64_t)(enc) & 0xFFFFFFFFull), (size_t)(dst).len); (dst).i = 0; } \
+            else { (dst).i = (enc); (dst).s = NULL; (dst).len = 0; } } while (0)
+            if (in->flags & TPLX_F_A_CONST) { KONST(ka, in->imm2, a_str); a = &ka; }
+            if (in->flags & TPLX_F_B_CONST) { KONST(kb, in->imm, b_str); b = &kb; }
+            if (in->flags & TPLX_F_C_CONST) { KONST(kc, in->imm2, c_str); c = &kc; }
+#undef KONST
+        }
 #define RAISE(code) do { *ec = (code); *opidx = in->opidx; return 2; } while (0)
         switch (in->op) {
             case TPLX_OP_NOP: break;
@@ -299,7 +317,7 @@ static int eval_row(const ostage *S, const tplx_ocol *cols, uint64_t row, oval *
             }
             case TPLX_OP_LDI: d->i = in->imm; break;
             case TPLX_OP_LDROW: d->i = (int64_t)row; break;
-            case TPLX_OP_LDS: d->s = dup_n(A, (const char *)S->cpool + in->imm, (size_t)in->imm2); d->len = in->imm2; break;
+            case TPLX_OP_LDS: d->len = (int64_t)((uint64_t)in->imm >> 32); d->s = dup_n(A, (const char *)S->cpool + ((uint64_t)in->imm & 0xFFFFFFFFull), (size_t)d->len); break;
             case TPLX_OP_MOV: *d = *a; break;
             case TPLX_OP_SEL: { oval v = c->i ? *a : *b; *d = v; break; }
             case TPLX_OP_IADD: d->i = (int64_t)((uint64_t)a->i + (uint64_t)b->i); break;
@@ -333,7 +351,7 @@ static int eval_row(const ostage *S, const tplx_ocol *cols, uint64_t row, oval *
             case TPLX_OP_ICMP: {
                 int64_t x = a->i, y = b->i;
                 int r = 0;
-                switch (in->flags) {
+                switch (in->flags & 7) {
                     case TPLX_CMP_EQ: r = x == y; break;
                     case TPLX_CMP_NE: r = x != y; break;
                     case TPLX_CMP_LT: r = x < y; break;
@@ -347,7 +365,7 @@ static int eval_row(const ostage *S, const tplx_ocol *cols, uint64_t row, oval *
             case TPLX_OP_FCMP: {
                 double x = as_f(a->i), y = as_f(b->i);
                 int r = 0;
-                switch (in->flags) {
+                switch (in->flags & 7) {
                     case TPLX_CMP_EQ: r = x == y; break;
                     case TPLX_CMP_NE: r = islessgreater(x, y); break; /* FCMP_ONE */
                     case TPLX_CMP_LT: r = x < y; break;

@@ -50,18 +50,18 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
 }
 
 template <int NTT>
-__device__ __forceinline__ uint64_t hash_key(const HashParams &H, uint64_t *regs, uint32_t *blob_size) {
+__device__ __forceinline__ uint64_t hash_key(const HashParams &H, uint8_t *regs, uint32_t *blob_size) {
     uint64_t h = 0x9E3779B97F4A7C15ull;
     uint32_t sz = 0;
     for (uint32_t k = 0; k < H.n_keys; ++k) {
         if (H.key_type[k] == TPLX_T_STR) {
-            StrV s = VM<NTT>::RS(regs, H.key_slot[k]);
+            StrV s = VM<NTT>::RS(regs, H.key_slot[k] * VM<NTT>::SLOT_BYTES);
             uint64_t f = 0xcbf29ce484222325ull;
             for (uint32_t i = 0; i < s.len; ++i) f = (f ^ sch(s, i)) * 0x100000001b3ull;
             h = mix64(h ^ f ^ ((uint64_t)s.len << 48));
             sz += 4 + s.len;
         } else {
-            h = mix64(h ^ VM<NTT>::R(regs, H.key_slot[k]));
+            h = mix64(h ^ VM<NTT>::R(regs, H.key_slot[k] * VM<NTT>::SLOT_BYTES));
             sz += 8;
         }
     }
@@ -70,10 +70,10 @@ __device__ __forceinline__ uint64_t hash_key(const HashParams &H, uint64_t *regs
 }
 
 template <int NTT>
-__device__ __forceinline__ bool key_equal(const HashParams &H, uint64_t *regs, const uint8_t *blob) {
+__device__ __forceinline__ bool key_equal(const HashParams &H, uint8_t *regs, const uint8_t *blob) {
     for (uint32_t k = 0; k < H.n_keys; ++k) {
         if (H.key_type[k] == TPLX_T_STR) {
-            StrV s = VM<NTT>::RS(regs, H.key_slot[k]);
+            StrV s = VM<NTT>::RS(regs, H.key_slot[k] * VM<NTT>::SLOT_BYTES);
             uint32_t len = blob[0] | (blob[1] << 8) | (blob[2] << 16) | ((uint32_t)blob[3] << 24);
             if (len != s.len) return false;
             blob += 4;
@@ -83,7 +83,7 @@ __device__ __forceinline__ bool key_equal(const HashParams &H, uint64_t *regs, c
         } else {
             uint64_t v = 0;
             for (int b = 0; b < 8; ++b) v |= (uint64_t)blob[b] << (8 * b);
-            if (v != VM<NTT>::R(regs, H.key_slot[k])) return false;
+            if (v != VM<NTT>::R(regs, H.key_slot[k] * VM<NTT>::SLOT_BYTES)) return false;
             blob += 8;
         }
     }
@@ -91,16 +91,16 @@ __device__ __forceinline__ bool key_equal(const HashParams &H, uint64_t *regs, c
 }
 
 template <int NTT>
-__device__ __forceinline__ void key_write(const HashParams &H, uint64_t *regs, uint8_t *blob) {
+__device__ __forceinline__ void key_write(const HashParams &H, uint8_t *regs, uint8_t *blob) {
     for (uint32_t k = 0; k < H.n_keys; ++k) {
         if (H.key_type[k] == TPLX_T_STR) {
-            StrV s = VM<NTT>::RS(regs, H.key_slot[k]);
+            StrV s = VM<NTT>::RS(regs, H.key_slot[k] * VM<NTT>::SLOT_BYTES);
             blob[0] = (uint8_t)s.len; blob[1] = (uint8_t)(s.len >> 8); blob[2] = (uint8_t)(s.len >> 16); blob[3] = (uint8_t)(s.len >> 24);
             blob += 4;
             for (uint32_t i = 0; i < s.len; ++i) blob[i] = sch(s, i);
             blob += s.len;
         } else {
-            uint64_t v = VM<NTT>::R(regs, H.key_slot[k]);
+            uint64_t v = VM<NTT>::R(regs, H.key_slot[k] * VM<NTT>::SLOT_BYTES);
             for (int b = 0; b < 8; ++b) blob[b] = (uint8_t)(v >> (8 * b));
             blob += 8;
         }
@@ -118,7 +118,7 @@ __device__ __forceinline__ void st_release_u64(uint64_t *p, uint64_t v) {
 
 // returns table slot of the key, inserting it if absent; HT_NOT_FOUND when the table or heap is full
 template <int NTT>
-__device__ uint32_t find_or_insert(const HashParams &H, uint64_t *regs, uint64_t h, uint32_t blob_size) {
+__device__ uint32_t find_or_insert(const HashParams &H, uint8_t *regs, uint64_t h, uint32_t blob_size) {
     const HashTableDev &T = H.ht;
     const uint64_t fp = h | 2ull;
     uint64_t idx = (h >> 17) & T.mask;
@@ -197,15 +197,15 @@ __global__ void __launch_bounds__(NT) stage_hash_kernel(const KParams *__restric
     const uint32_t tid = threadIdx.x;
     const uint32_t R = P.R, T = R * NT;
 
-    tplx_instr *s_prog = reinterpret_cast<tplx_instr *>(smem);
+    DInstr *s_prog = reinterpret_cast<DInstr *>(smem);
     ColIn *s_cols = reinterpret_cast<ColIn *>(smem + P.smem_cols_off);
-    uint64_t *s_regs = reinterpret_cast<uint64_t *>(smem + P.smem_regs_off) + tid;
+    uint8_t *s_regs = smem + P.smem_regs_off + tid * 8;  // this thread's register column
     // pre-aggregation buckets: gidx[SM_BUCKETS] (u32) then acc[n_accs][SM_BUCKETS] (u64)
     uint64_t *s_bacc = reinterpret_cast<uint64_t *>(smem + P.smem_misc_off);
     uint32_t *s_bkey = reinterpret_cast<uint32_t *>(s_bacc + (size_t)P.n_accs * SM_BUCKETS);
     uint32_t *s_stat = s_bkey + SM_BUCKETS;  // [0] bucket hits, [1] bucket misses, [2] disabled
 
-    for (uint32_t i = tid; i < P.n_instr * (sizeof(tplx_instr) / 16); i += NT)
+    for (uint32_t i = tid; i < P.n_instr * (sizeof(DInstr) / 16); i += NT)
         reinterpret_cast<uint4 *>(s_prog)[i] = reinterpret_cast<const uint4 *>(P.prog)[i];
     for (uint32_t i = tid; i < P.n_in * (sizeof(ColIn) / 8); i += NT)
         reinterpret_cast<uint64_t *>(s_cols)[i] = reinterpret_cast<const uint64_t *>(P.in)[i];
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(NT) stage_hash_kernel(const KParams *__restric
                             uint32_t prev = atomicCAS(&s_bkey[b], HT_NOT_FOUND, g);
                             if (prev == HT_NOT_FOUND || prev == g) {
                                 for (uint32_t k = 0; k < na; ++k) {
-                                    uint64_t v = s_regs[P.accs[k].slot * NT];
+                                    uint64_t v = VM<NT>::R(s_regs, P.accs[k].slot * VM<NT>::SLOT_BYTES);
                                     uint64_t *p = &s_bacc[(size_t)k * SM_BUCKETS + b];
                                     switch (P.accs[k].kind) {
                                         case TPLX_ACC_SUM_I64: atomicAdd((unsigned long long *)p, (unsigned long long)v); break;
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(NT) stage_hash_kernel(const KParams *__restric
                     }
                     if (!done)
                         for (uint32_t k = 0; k < na; ++k)
-                            atomic_acc_global(P.accs[k].kind, &H.ht.accs[(size_t)k * H.ht.cap + g], s_regs[P.accs[k].slot * NT]);
+                            atomic_acc_global(P.accs[k].kind, &H.ht.accs[(size_t)k * H.ht.cap + g], VM<NT>::R(s_regs, P.accs[k].slot * VM<NT>::SLOT_BYTES));
                 }
             }
             if (t.exc_code) {

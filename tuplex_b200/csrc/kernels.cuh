@@ -46,7 +46,7 @@ struct KParams {
     uint32_t K;            // scan vector width = 2 + n_str_out
     uint32_t smem_regs_off, smem_stage_off, smem_misc_off, smem_cols_off;
     uint64_t cap_rows, cap_exc;
-    const tplx_instr *prog;
+    const DInstr *prog;    // pre-decoded program (device format)
     const uint8_t *cpool;
     const int64_t *opids;
     uint64_t *tile_state;   // n_tiles * (1 + 2K)
@@ -131,9 +131,9 @@ __global__ void __launch_bounds__(NT) stage_rows_kernel(const KParams *__restric
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t R = P.R, T = R * NT, W = T / 32, K = P.K;
 
-    tplx_instr *s_prog = reinterpret_cast<tplx_instr *>(smem);
+    DInstr *s_prog = reinterpret_cast<DInstr *>(smem);
     ColIn *s_cols = reinterpret_cast<ColIn *>(smem + P.smem_cols_off);
-    uint64_t *s_regs = reinterpret_cast<uint64_t *>(smem + P.smem_regs_off) + tid;
+    uint8_t *s_regs = smem + P.smem_regs_off + tid * 8;  // this thread's register column
     uint8_t *s_stage = smem + P.smem_stage_off;
     uint32_t *keep_bits = reinterpret_cast<uint32_t *>(smem + P.smem_misc_off);
     uint32_t *exc_bits = keep_bits + W;
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(NT) stage_rows_kernel(const KParams *__restric
     uint32_t *s_ctl = reinterpret_cast<uint32_t *>(s_warp + NT / 32 + 1);                     // [0] tile
 
     // one-time: program + column table into shared memory
-    for (uint32_t i = tid; i < P.n_instr * (sizeof(tplx_instr) / 16); i += NT)
+    for (uint32_t i = tid; i < P.n_instr * (sizeof(DInstr) / 16); i += NT)
         reinterpret_cast<uint4 *>(s_prog)[i] = reinterpret_cast<const uint4 *>(P.prog)[i];
     for (uint32_t i = tid; i < P.n_in * (sizeof(ColIn) / 8); i += NT)
         reinterpret_cast<uint64_t *>(s_cols)[i] = reinterpret_cast<const uint64_t *>(P.in)[i];
@@ -176,10 +176,10 @@ __global__ void __launch_bounds__(NT) stage_rows_kernel(const KParams *__restric
                 const OutCol &oc = P.out[c];
                 if (oc.strk >= 0) {
                     uint64_t *st = reinterpret_cast<uint64_t *>(s_stage + oc.stage_off) + 2 * (size_t)lr;
-                    st[0] = s_regs[oc.slot * NT];
-                    st[1] = s_regs[(oc.slot + 1) * NT];
+                    st[0] = VM<NT>::R(s_regs, oc.slot * VM<NT>::SLOT_BYTES);
+                    st[1] = VM<NT>::R(s_regs, (oc.slot + 1) * VM<NT>::SLOT_BYTES);
                 } else {
-                    reinterpret_cast<uint64_t *>(s_stage + oc.stage_off)[lr] = s_regs[oc.slot * NT];
+                    reinterpret_cast<uint64_t *>(s_stage + oc.stage_off)[lr] = VM<NT>::R(s_regs, oc.slot * VM<NT>::SLOT_BYTES);
                 }
             }
         };
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(NT) stage_rows_kernel(const KParams *__restric
             }
             // stash this thread's exclusive byte offset in the (now free) register file slot area:
             // regs are dead after evaluation, reuse slot 0..n_str_out-1 of this thread
-            s_regs[(uint32_t)oc.strk * NT] = (uint64_t)(wofs + inc - mine);
+            VM<NT>::R(s_regs, (uint32_t)oc.strk * VM<NT>::SLOT_BYTES) = (uint64_t)(wofs + inc - mine);
             if (tid == 0) s_vals[2 + oc.strk] = tot;
         }
         __syncthreads();
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(NT) stage_rows_kernel(const KParams *__restric
                         if (tid == 0) atomicOr(&P.counters[1], 2u);
                         continue;
                     }
-                    uint64_t off = pre_b + s_regs[(uint32_t)oc.strk * NT];
+                    uint64_t off = pre_b + VM<NT>::R(s_regs, (uint32_t)oc.strk * VM<NT>::SLOT_BYTES);
                     for (uint32_t j = 0; j < R; ++j) {
                         const uint32_t lr = tid * R + j;
                         if (!bit_test(keep_bits, lr)) continue;
@@ -381,12 +381,12 @@ __global__ void __launch_bounds__(NT) stage_agg_kernel(const KParams *__restrict
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t R = P.R, T = R * NT;
 
-    tplx_instr *s_prog = reinterpret_cast<tplx_instr *>(smem);
+    DInstr *s_prog = reinterpret_cast<DInstr *>(smem);
     ColIn *s_cols = reinterpret_cast<ColIn *>(smem + P.smem_cols_off);
-    uint64_t *s_regs = reinterpret_cast<uint64_t *>(smem + P.smem_regs_off) + tid;
+    uint8_t *s_regs = smem + P.smem_regs_off + tid * 8;  // this thread's register column
     uint64_t *s_wacc = reinterpret_cast<uint64_t *>(smem + P.smem_misc_off);  // [NT/32][n_accs]
 
-    for (uint32_t i = tid; i < P.n_instr * (sizeof(tplx_instr) / 16); i += NT)
+    for (uint32_t i = tid; i < P.n_instr * (sizeof(DInstr) / 16); i += NT)
         reinterpret_cast<uint4 *>(s_prog)[i] = reinterpret_cast<const uint4 *>(P.prog)[i];
     for (uint32_t i = tid; i < P.n_in * (sizeof(ColIn) / 8); i += NT)
         reinterpret_cast<uint64_t *>(s_cols)[i] = reinterpret_cast<const uint64_t *>(P.in)[i];
@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(NT) stage_agg_kernel(const KParams *__restrict
             if (t.alive) {
 #pragma unroll
                 for (uint32_t k = 0; k < TPLX_MAX_ACCS; ++k)
-                    if (k < na) acc[k] = acc_combine(P.accs[k].kind, acc[k], s_regs[P.accs[k].slot * NT]);
+                    if (k < na) acc[k] = acc_combine(P.accs[k].kind, acc[k], VM<NT>::R(s_regs, P.accs[k].slot * VM<NT>::SLOT_BYTES));
             }
             if (t.exc_code) {
                 uint32_t pos = atomicAdd(&P.counters[2], 1u);

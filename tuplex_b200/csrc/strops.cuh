@@ -1,0 +1,223 @@
+// strops.cuh — string primitives of the VM, written word-at-a-time (SWAR over aligned 32-bit loads).
+//
+// Semantics restated from the reference (paths relative to /root/reference/tuplex/):
+//   find    = strstr                       codegen/src/FunctionRegistry.cc:2165-2188
+//   rfind   = std::string::rfind           runtime/src/Runtime.cc:387-397
+//   ==      = strcmp == 0                  codegen/src/BlockGeneratorVisitor.cc:838-856
+//   lower / upper: ASCII only, C locale    runtime/src/StringFunctions.cc:71-110
+// A string value is a view (pointer, length, lazy case flag); see include/tplx_ir.h.
+//
+// Memory contract: a view's bytes live in a buffer whose allocation is a multiple of 4 bytes and 4-byte
+// aligned at its base (all buffers this library allocates are), so every ALIGNED 32-bit word that contains
+// at least one byte of the string may be loaded. Words that contain no string byte are never touched.
+//
+// The header compiles for the host too (TPLX_HD) so that tests/test_strops_host.py can fuzz these exact
+// functions on the CPU against CPython's str methods.
+#pragma once
+#include <stdint.h>
+#include "../../include/tplx_ir.h"
+
+#ifdef __CUDACC__
+#define TPLX_HD __host__ __device__ __forceinline__
+#define TPLX_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define TPLX_HD inline
+#define TPLX_HD_NOINLINE inline
+#endif
+
+namespace tplx {
+
+struct StrV {
+    const uint8_t *p;
+    uint32_t len;
+    uint32_t flags;
+};
+
+TPLX_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {
+#ifdef __CUDA_ARCH__
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+#endif
+}
+
+// packed ASCII case mapping of 4 bytes; bytes >= 0x80 are left alone (tolower/toupper in the C locale)
+TPLX_HD uint32_t lower4(uint32_t w) {
+    uint32_t w7 = w & 0x7f7f7f7fu;
+    uint32_t m = (w7 + 0x3f3f3f3fu) & ~(w7 + 0x25252525u) & ~w & 0x80808080u;  // 'A'..'Z'
+    return w | (m >> 2);
+}
+TPLX_HD uint32_t upper4(uint32_t w) {
+    uint32_t w7 = w & 0x7f7f7f7fu;
+    uint32_t m = (w7 + 0x1f1f1f1fu) & ~(w7 + 0x05050505u) & ~w & 0x80808080u;  // 'a'..'z'
+    return w & ~(m >> 2);
+}
+TPLX_HD uint32_t case4(uint32_t w, uint32_t flags) {
+    return flags == TPLX_SF_LOWER ? lower4(w) : (flags == TPLX_SF_UPPER ? upper4(w) : w);
+}
+TPLX_HD uint8_t case1(uint8_t c, uint32_t flags) {
+    if (flags == TPLX_SF_LOWER) {
+        if ((uint8_t)(c - 'A') < 26u) c += 32;
+    } else if (flags == TPLX_SF_UPPER) {
+        if ((uint8_t)(c - 'a') < 26u) c -= 32;
+    }
+    return c;
+}
+// 0x80 in every byte lane of w that equals c (exact, no false positives)
+TPLX_HD uint32_t eq_mask4(uint32_t w, uint32_t c) {
+    uint32_t x = w ^ (c * 0x01010101u);
+    uint32_t t = ((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x;
+    return ~t & 0x80808080u;
+}
+
+TPLX_HD uint8_t sch(const StrV &s, uint32_t i) { return case1(s.p[i], s.flags); }
+
+// Sequential reader of a string as little-endian 32-bit words of 4 characters (word k = chars 4k..4k+3),
+// built from aligned loads + funnel shift. Characters past the end read as garbage: callers mask.
+struct WordReader {
+    const uint32_t *w;  // aligned base
+    uint32_t sh;        // bit offset of the string start inside *w
+    uint32_t nwords;    // aligned words that contain string bytes
+    uint32_t flags;
+    TPLX_HD void init(const StrV &s) {
+        uintptr_t a = (uintptr_t)s.p;
+        w = (const uint32_t *)(a & ~(uintptr_t)3);
+        sh = (uint32_t)(a & 3) * 8;
+        nwords = (uint32_t)(((a & 3) + s.len + 3) >> 2);
+        flags = s.flags;
+    }
+    TPLX_HD uint32_t aligned(uint32_t j) const { return j < nwords ? w[j] : 0u; }
+    // characters 4k..4k+3 (case-mapped)
+    TPLX_HD uint32_t get(uint32_t k) const {
+        uint32_t lo = aligned(k);
+        uint32_t hi = sh ? aligned(k + 1) : 0u;
+        return case4(funnel_r(lo, hi, sh), flags);
+    }
+};
+
+TPLX_HD uint32_t low_mask(uint32_t nbytes) {  // mask of the low nbytes (0..4) bytes
+    return nbytes >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nbytes)) - 1u);
+}
+
+// a == b (both possibly case-flagged)
+TPLX_HD_NOINLINE bool str_eq(const StrV &a, const StrV &b) {
+    if (a.len != b.len) return false;
+    WordReader ra, rb;
+    ra.init(a);
+    rb.init(b);
+    const uint32_t n = a.len;
+    for (uint32_t k = 0; 4 * k < n; ++k) {
+        uint32_t x = ra.get(k) ^ rb.get(k);
+        uint32_t rem = n - 4 * k;
+        if (x & low_mask(rem)) return false;
+    }
+    return true;
+}
+
+// does hay[pos..pos+n.len) equal n ? (byte path, used to verify SWAR candidates)
+TPLX_HD bool match_at(const StrV &h, uint32_t pos, const StrV &n, uint32_t from) {
+    for (uint32_t j = from; j < n.len; ++j)
+        if (sch(h, pos + j) != sch(n, j)) return false;
+    return true;
+}
+
+// strstr semantics: first occurrence or -1; empty needle -> 0.
+// SWAR filter on the first (and, when present, second) needle character, 4 haystack positions per step.
+TPLX_HD_NOINLINE int64_t str_find(const StrV &h, const StrV &n) {
+    if (n.len == 0) return 0;
+    if (n.len > h.len) return -1;
+    const uint32_t last = h.len - n.len;  // last admissible start
+    const uint32_t c0 = sch(n, 0);
+    const bool two = n.len >= 2;
+    const uint32_t c1 = two ? sch(n, 1) : 0;
+    WordReader r;
+    r.init(h);
+    uint32_t cur = r.get(0);
+    for (uint32_t k = 0; 4 * k <= last; ++k) {
+        // next word is needed for the second-character test of position 4k+3 (only if it holds string bytes)
+        uint32_t nxt = (4 * (k + 1) < h.len) ? r.get(k + 1) : 0u;
+        uint32_t m = eq_mask4(cur, c0);
+        if (two) m &= eq_mask4((cur >> 8) | (nxt << 24), c1);
+        // drop positions beyond `last`
+        uint32_t valid = last - 4 * k;  // positions 0..valid of this word are admissible
+        if (valid < 3) m &= low_mask(valid + 1);
+        while (m) {
+#ifdef __CUDA_ARCH__
+            uint32_t bit = __ffs(m) - 1;
+#else
+            uint32_t bit = (uint32_t)__builtin_ctz(m);
+#endif
+            uint32_t pos = 4 * k + (bit >> 3);
+            if (match_at(h, pos, n, two ? 2 : 1)) return (int64_t)pos;
+            m &= m - 1;
+        }
+        cur = nxt;
+    }
+    return -1;
+}
+
+// std::string::rfind: last occurrence or -1; empty needle -> len
+TPLX_HD_NOINLINE int64_t str_rfind(const StrV &h, const StrV &n) {
+    if (n.len > h.len) return -1;
+    if (n.len == 0) return (int64_t)h.len;
+    const uint8_t n0 = sch(n, 0);
+    for (int64_t i = (int64_t)(h.len - n.len); i >= 0; --i) {
+        if (sch(h, (uint32_t)i) != n0) continue;
+        if (match_at(h, (uint32_t)i, n, 1)) return i;
+    }
+    return -1;
+}
+
+TPLX_HD bool is_pyspace(uint8_t c) {
+    // string.whitespace = ' \t\n\r\x0b\x0c' (runtime/src/Runtime.cc:322-333)
+    return c == ' ' || (c >= 9 && c <= 13);
+}
+
+// Python slice index normalisation for stride +1 (BlockGeneratorVisitor.cc:4618-4690)
+TPLX_HD int64_t slice_index(int64_t idx, int64_t len) {
+    if (idx < -len) return 0;
+    if (idx <= -1) return idx + len;
+    if (idx < len) return idx;
+    return len;
+}
+
+// fast_atoi64 (runtime/src/Runtime.cc:319-341 + utils/src/StringUtils.cc:22-63); false = ValueError
+TPLX_HD bool str_to_i64(const StrV &s, int64_t *out) {
+    uint32_t i = 0, e = s.len;
+    while (i < e && is_pyspace(s.p[i])) ++i;
+    if (e > i) {
+        uint32_t e2 = e - 1;
+        while (e2 > i && is_pyspace(s.p[e2])) --e2;
+        e = e2 + 1;
+    }
+    if (i == e) return false;
+    bool neg = false;
+    if (s.p[i] == '-') {
+        neg = true;
+        ++i;
+    }
+    uint64_t x = 0;
+    while (i < s.len) {
+        uint8_t d = (uint8_t)(s.p[i] - '0');
+        if (d > 9) break;
+        x = x * 10 + d;
+        ++i;
+    }
+    if (i != e) return false;
+    *out = (int64_t)(neg ? (uint64_t)0 - x : x);
+    return true;
+}
+
+// floor division / modulo with sign fix-up (codegen/src/LLVMEnvironment.cc:1377-1430)
+TPLX_HD int64_t floordiv_i64(int64_t x, int64_t y) {
+    int64_t q = x / y, r = x % y;
+    if (r != 0 && ((r < 0) != (y < 0))) --q;
+    return q;
+}
+TPLX_HD int64_t floormod_i64(int64_t x, int64_t y) {
+    int64_t r = x % y;
+    if (r != 0 && ((r < 0) != (y < 0))) r += y;
+    return r;
+}
+
+}  // namespace tplx

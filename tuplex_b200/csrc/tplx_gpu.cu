@@ -131,7 +131,7 @@ extern "C" int32_t tplx_gpu_device_info(int32_t device, char *name_buf, int32_t 
 // ---------------------------------------------------------------------------------------------
 struct StageDev {
     Device *dev = nullptr;
-    tplx_instr *prog = nullptr;
+    DInstr *prog = nullptr;  // pre-decoded program
     uint8_t *cpool = nullptr;
     int64_t *opids = nullptr;
     HashTable *ht = nullptr;  // HASH endpoint
@@ -222,7 +222,7 @@ extern "C" int32_t tplx_gpu_stage_create(const void *desc, uint64_t desc_bytes, 
                 if (in.flags != s->in_types[in.imm]) return bad("program: LDCOL type mismatch");
                 break;
             case TPLX_OP_LDS:
-                if (in.imm < 0 || in.imm2 < 0 || (uint64_t)in.imm + (uint64_t)in.imm2 > h.const_bytes)
+                if (((uint64_t)in.imm & 0xFFFFFFFFull) + ((uint64_t)in.imm >> 32) > h.const_bytes)
                     return bad("program: LDS constant out of range");
                 break;
             case TPLX_OP_SREPLACE: case TPLX_OP_SCONCAT: case TPLX_OP_SFMTD: case TPLX_OP_I2S:
@@ -230,7 +230,22 @@ extern "C" int32_t tplx_gpu_stage_create(const void *desc, uint64_t desc_bytes, 
                 break;
             default: break;
         }
-        if (in.op >= TPLX_OP_SLEN && in.op <= TPLX_OP_SSTRIP) s->has_str = true;
+        if (in.op >= TPLX_OP_SLEN && in.op <= TPLX_OP_SSTRIP) {
+            s->has_str = true;
+            // constant string operands are constant-pool views (offset | length << 32)
+            auto cs_ok = [&](int64_t enc) { return ((uint64_t)enc & 0xFFFFFFFFull) + ((uint64_t)enc >> 32) <= h.const_bytes; };
+            const bool str_b = in.op == TPLX_OP_SFIND || in.op == TPLX_OP_SRFIND || in.op == TPLX_OP_SIN || in.op == TPLX_OP_SEQ ||
+                               in.op == TPLX_OP_SSTARTS || in.op == TPLX_OP_SENDS || in.op == TPLX_OP_SCONCAT || in.op == TPLX_OP_SREPLACE;
+            if (in.op != TPLX_OP_SFMTD && in.op != TPLX_OP_I2S && (in.flags & TPLX_F_A_CONST) && !cs_ok(in.imm2)) return bad("program: constant operand a out of range");
+            if (str_b && (in.flags & TPLX_F_B_CONST) && !cs_ok(in.imm)) return bad("program: constant operand b out of range");
+            if (in.op == TPLX_OP_SREPLACE && (in.flags & TPLX_F_C_CONST) && !cs_ok(in.imm2)) return bad("program: constant operand c out of range");
+        }
+        if ((in.op == TPLX_OP_SEL || in.op == TPLX_OP_MOV) && (in.flags & 3) == 2) {
+            auto cs_ok = [&](int64_t enc) { return ((uint64_t)enc & 0xFFFFFFFFull) + ((uint64_t)enc >> 32) <= h.const_bytes; };
+            if ((in.flags & TPLX_F_A_CONST) && !cs_ok(in.imm2)) return bad("program: constant operand a out of range");
+            if ((in.flags & TPLX_F_B_CONST) && !cs_ok(in.imm)) return bad("program: constant operand b out of range");
+            s->has_str = true;
+        }
         if (in.op == TPLX_OP_LDS) s->has_str = true;
     }
     if (h.hidden_out_cols > h.n_out_cols) return bad("stage descriptor: hidden_out_cols out of range");
@@ -265,6 +280,26 @@ extern "C" int32_t tplx_gpu_stage_create(const void *desc, uint64_t desc_bytes, 
     return TPLX_OK;
 }
 
+// tplx_instr -> device format: slot numbers become byte offsets into a thread's register column
+static std::vector<DInstr> predecode(const std::vector<tplx_instr> &ins) {
+    std::vector<DInstr> out(ins.size());
+    auto off = [](uint16_t slot) { return slot == TPLX_NOSLOT ? NOOFF : (uint32_t)slot * (uint32_t)(NT * 8); };
+    for (size_t i = 0; i < ins.size(); ++i) {
+        const tplx_instr &in = ins[i];
+        DInstr d{};
+        d.op_flags = (uint32_t)in.op | ((uint32_t)in.flags << 8) | ((uint32_t)in.opidx << 16);
+        d.dst = off(in.dst);
+        d.a = off(in.a);
+        d.b = off(in.b);
+        d.c = off(in.c);
+        d.guard = off(in.guard);
+        d.imm = in.imm;
+        d.imm2 = in.imm2;
+        out[i] = d;
+    }
+    return out;
+}
+
 static int32_t stage_dev(tplx_stage *s, Device *d, StageDev **out) {
     std::lock_guard<std::mutex> lk(s->mu);
     for (auto &sd : s->devs)
@@ -273,10 +308,11 @@ static int32_t stage_dev(tplx_stage *s, Device *d, StageDev **out) {
     StageDev sd;
     sd.dev = d;
     CU(cudaSetDevice(d->id));
-    size_t nb = std::max<size_t>(s->instrs.size() * sizeof(tplx_instr), 16);
+    std::vector<DInstr> dec = predecode(s->instrs);
+    size_t nb = std::max<size_t>(dec.size() * sizeof(DInstr), 16);
     CU(cudaMalloc(&sd.prog, nb));
-    CU(cudaMemcpy(sd.prog, s->instrs.data(), s->instrs.size() * sizeof(tplx_instr), cudaMemcpyHostToDevice));
-    CU(cudaMalloc(&sd.cpool, std::max<size_t>(s->cpool.size(), 16)));
+    CU(cudaMemcpy(sd.prog, dec.data(), dec.size() * sizeof(DInstr), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&sd.cpool, align_up(s->cpool.size(), 16) + 16));  // word-wise readers may touch the padding
     CU(cudaMemcpy(sd.cpool, s->cpool.data(), s->cpool.size(), cudaMemcpyHostToDevice));
     CU(cudaMalloc(&sd.opids, std::max<size_t>(s->opids.size() * 8, 16)));
     CU(cudaMemcpy(sd.opids, s->opids.data(), s->opids.size() * 8, cudaMemcpyHostToDevice));
@@ -325,7 +361,7 @@ extern "C" int32_t tplx_gpu_block_upload(int32_t device, const tplx_column *cols
         ci.type = cols[c].type;
         uint64_t nb = cols[c].type == TPLX_T_STR ? cols[c].data_bytes : n_rows * 8;
         void *dd = nullptr;
-        CU(cudaMallocAsync(&dd, std::max<uint64_t>(nb, 16), d->stream));
+        CU(cudaMallocAsync(&dd, align_up(nb, 16) + 16, d->stream));  // 4-byte-multiple buffers: strops.cuh memory contract
         b->owned.push_back(dd);
         if (nb) CU(cudaMemcpyAsync(dd, cols[c].data, nb, cudaMemcpyHostToDevice, d->stream));
         ci.data = dd;
@@ -421,7 +457,7 @@ struct Layout {
 static Layout make_layout(const tplx_stage *s, uint32_t R, bool rows_ep) {
     Layout L;
     const uint32_t T = R * NT, W = T / 32;
-    size_t off = align_up(std::max<size_t>(s->instrs.size(), 1) * sizeof(tplx_instr), 16);
+    size_t off = align_up(std::max<size_t>(s->instrs.size(), 1) * sizeof(DInstr), 16);
     L.cols_off = (uint32_t)off;
     off = align_up(off + std::max<size_t>(s->in_types.size(), 1) * sizeof(ColIn), 16);
     L.regs_off = (uint32_t)off;

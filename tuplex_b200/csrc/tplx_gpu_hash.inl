@@ -213,9 +213,11 @@ extern "C" int32_t tplx_gpu_stage_hash_merge(tplx_stage *s, const tplx_block *pa
     tmp.hdr.n_slots = (uint16_t)slot;
     tmp.hdr.n_instr = nk + na;
     for (uint32_t k = 0; k < na; ++k) tmp.accs[k].slot = (uint16_t)col_slot[nk + k];
-    tplx_instr *dprog = nullptr;
-    CU(cudaMallocAsync(&dprog, tmp.instrs.size() * sizeof(tplx_instr), d->stream));
-    CU(cudaMemcpyAsync(dprog, tmp.instrs.data(), tmp.instrs.size() * sizeof(tplx_instr), cudaMemcpyHostToDevice, d->stream));
+    DInstr *dprog = nullptr;
+    std::vector<DInstr> dec = predecode(tmp.instrs);
+    CU(cudaMallocAsync(&dprog, dec.size() * sizeof(DInstr), d->stream));
+    CU(cudaMemcpyAsync(dprog, dec.data(), dec.size() * sizeof(DInstr), cudaMemcpyHostToDevice, d->stream));
+    CU(cudaStreamSynchronize(d->stream));
     StageDev tsd = *sd;
     tsd.prog = dprog;
     const uint32_t R = 4;

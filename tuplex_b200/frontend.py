@@ -203,8 +203,7 @@ class StageCompiler:
         d = self.new_vreg(v.type)
         g, self.guard = self.guard, None  # constants are unconditional
         if v.type == T_STR:
-            off, ln = self.prog.const_bytes(v.const.encode("utf-8"))
-            self.emit(C["TPLX_OP_LDS"], d, imm=off, imm2=ln)
+            self.emit(C["TPLX_OP_LDS"], d, imm=self._enc_const(v))
         elif v.type == T_F64:
             self.emit(C["TPLX_OP_LDI"], d, imm=ir.f64_bits(float(v.const)))
         else:
@@ -218,14 +217,55 @@ class StageCompiler:
     def is_const(self, v) -> bool:
         return isinstance(v, Val) and v.vreg is None and not self._is_colref(v)
 
+    def _enc_const(self, v: Val) -> int:
+        """Immediate encoding of a compile-time constant operand (include/tplx_ir.h tplx_constflag)."""
+        if v.type == T_STR:
+            off, ln = self.prog.const_bytes(v.const.encode("utf-8"))
+            return off | (ln << 32)
+        if v.type == T_F64:
+            return ir.f64_bits(float(v.const))
+        return int(v.const) & ((1 << 64) - 1)
+
+    _NO_CONST_OPS = None
+
+    def emit_vals(self, op, dst, a: Optional[Val] = None, b: Optional[Val] = None, c: Optional[Val] = None, flags=0, imm=0):
+        """Emit an instruction whose operands are Vals; compile-time constants ride in the immediates
+        (a <- imm2, b <- imm, c <- imm2) instead of being loaded into slots for every row."""
+        if StageCompiler._NO_CONST_OPS is None:
+            StageCompiler._NO_CONST_OPS = {C[k] for k in ("TPLX_OP_FILTER", "TPLX_OP_SFMTD", "TPLX_OP_I2S", "TPLX_OP_LDCOL", "TPLX_OP_LDI",
+                                                             "TPLX_OP_LDS", "TPLX_OP_LDROW", "TPLX_OP_RAISE")}
+        imm2 = 0
+        ra = rb_ = rc = None
+        ok = op not in StageCompiler._NO_CONST_OPS
+        if b is not None:
+            if ok and self.is_const(b):
+                flags |= C["TPLX_F_B_CONST"]
+                imm = self._enc_const(b)
+            else:
+                rb_ = self.reg(b)
+        c_const = c is not None and ok and self.is_const(c) and op != C["TPLX_OP_SEL"]
+        if c is not None:
+            if c_const:
+                flags |= C["TPLX_F_C_CONST"]
+                imm2 = self._enc_const(c)
+            else:
+                rc = self.reg(c)
+        if a is not None:
+            if ok and self.is_const(a) and not c_const:
+                flags |= C["TPLX_F_A_CONST"]
+                imm2 = self._enc_const(a)
+            else:
+                ra = self.reg(a)
+        self.emit(op, dst, ra, rb_, rc, flags=flags, imm=imm, imm2=imm2)
+
     def op2(self, op, t, a: Val, b: Val, flags=0) -> Val:
         d = self.new_vreg(t)
-        self.emit(op, d, self.reg(a), self.reg(b), flags=flags)
+        self.emit_vals(op, d, a, b, flags=flags)
         return Val(t, d)
 
     def op1(self, op, t, a: Val, flags=0, imm=0) -> Val:
         d = self.new_vreg(t)
-        self.emit(op, d, self.reg(a), flags=flags, imm=imm)
+        self.emit_vals(op, d, a, flags=flags, imm=imm)
         return Val(t, d)
 
     # ---- type coercions (BlockGeneratorVisitor upCast) -----------------------------------------
@@ -293,7 +333,7 @@ class StageCompiler:
         a, b = self.unify(a, b)
         d = self.new_vreg(a.type)
         # SEL itself must run wherever either side may be needed later: emit under the current guard
-        self.emit(C["TPLX_OP_SEL"], d, self.reg(a), self.reg(b), self.reg(cond), flags=2 if a.type == T_STR else 1)
+        self.emit_vals(C["TPLX_OP_SEL"], d, a, b, cond, flags=2 if a.type == T_STR else 1)
         return Val(a.type, d)
 
     def unify(self, a: Val, b: Val) -> Tuple[Val, Val]:
@@ -1004,8 +1044,8 @@ class _FuncCompiler:
                 return const_val(base.const[(lo.const if lo else None):(hi.const if hi else None)])
             flags = (C["TPLX_SL_HAS_START"] if lo is not None else 0) | (C["TPLX_SL_HAS_END"] if hi is not None else 0)
             d = sc.new_vreg(T_STR)
-            sc.emit(C["TPLX_OP_SSLICE"], d, sc.reg(base), sc.reg(sc.to_i64(lo)) if lo is not None else None,
-                    sc.reg(sc.to_i64(hi)) if hi is not None else None, flags=flags)
+            sc.emit_vals(C["TPLX_OP_SSLICE"], d, base, sc.to_i64(lo) if lo is not None else None,
+                         sc.to_i64(hi) if hi is not None else None, flags=flags)
             return Val(T_STR, d)
         idx = self.expr(e.slice)
         if isinstance(idx, TupleVal) or idx.type not in (T_I64, T_BOOL):
@@ -1078,7 +1118,7 @@ class _FuncCompiler:
             if m == "replace":
                 want_str(2)
                 d = sc.new_vreg(T_STR)
-                sc.emit(C["TPLX_OP_SREPLACE"], d, sc.reg(obj), sc.reg(args[0]), sc.reg(args[1]))
+                sc.emit_vals(C["TPLX_OP_SREPLACE"], d, obj, args[0], args[1])
                 return Val(T_STR, d)
             if m in ("startswith", "endswith"):
                 want_str(1)
