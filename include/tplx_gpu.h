@@ -71,7 +71,8 @@ typedef struct tplx_result_info {
     double kernel_ms;    /* CUDA-event time of the stage kernel(s) on the device stream */
     double total_ms;     /* CUDA-event time submit→results ready (incl. H2D when input was on host) */
     uint32_t kernel_launches;
-    uint32_t pad;
+    uint32_t zero_copy_cols; /* run_host: input columns read in place from page-locked host memory (late materialisation) */
+    uint64_t h2d_bytes;      /* run_host: bytes of input explicitly copied host->device */
 } tplx_result_info;
 
 /* ---- process / devices ------------------------------------------------------------------ */

@@ -1,0 +1,113 @@
+"""No-GPU checks: the C-ABI library builds for sm_100a, loads, and exports every symbol include/tplx_gpu.h
+declares; compute entry points fail loudly without a device (no CPU fallback); host-side logic."""
+import ctypes as ct
+import os
+import re
+
+import numpy as np
+import pytest
+
+from tuplex_b200 import backend, frontend, ir, pyexec, workloads
+from tuplex_b200.context import Context
+from tuplex_b200.dataset import _merge_by_rowno
+from tuplex_b200.ir import T_F64, T_I64, T_STR
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(built):
+    hdr = open(os.path.join(ROOT, "include", "tplx_gpu.h")).read()
+    declared = sorted(set(re.findall(r"\b(tplx_gpu_[a-z_0-9]+)\s*\(", hdr)))
+    assert len(declared) >= 25
+    L = ct.CDLL(os.path.join(ROOT, "tuplex_b200", "lib", "libtplx_gpu.so"))
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in tplx_gpu.h but not exported"
+    assert sorted(backend.lib()._declared) == declared  # the Python binding covers the whole ABI
+
+
+def test_sass_is_sm100a(built):
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", os.path.join(ROOT, "tuplex_b200", "lib", "libtplx_gpu.so")], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_no_cpu_fallback(built):
+    if backend.device_count() > 0:
+        pytest.skip("a GPU is visible")
+    with pytest.raises(backend.GpuBackendError):
+        backend.init([0])
+    st = backend.Stage(workloads.c1_program())  # descriptor validation works without a device
+    with pytest.raises(backend.GpuBackendError):
+        st.run_host(0, [backend.Column(T_I64, np.arange(4))], 4)
+
+
+def test_descriptor_validation(built):
+    blob = bytearray(workloads.zillow_program().serialize())
+    bad = bytes(blob[:-8])
+    h = ct.c_void_p()
+    buf = ct.create_string_buffer(bad, len(bad))
+    assert backend.lib().tplx_gpu_stage_create(buf, len(bad), ct.byref(h)) == ir.C.get("TPLX_E_BADDESC", -3)
+    blob[0] ^= 0xFF
+    buf = ct.create_string_buffer(bytes(blob), len(blob))
+    assert backend.lib().tplx_gpu_stage_create(buf, len(blob), ct.byref(h)) != 0
+    assert b"magic" in backend.lib().tplx_gpu_last_error()
+
+
+def test_frontend_lowering_shapes():
+    p = workloads.zillow_program()
+    assert p.prefilter is not None and p.hidden_out_cols == 1 and len(p.out_cols) == 12
+    assert [t for _, t in p.out_cols][:11].count(T_STR) == 7
+    assert len(p.opids) >= 12 and p.opids[0] == 100001
+    q = workloads.q6_program()
+    assert q.endpoint == ir.C["TPLX_EP_AGGREGATE"] and len(q.accs) == 1 and q.accs[0].kind == ir.C["TPLX_ACC_SUM_F64"]
+    # unsupported constructs fall back instead of miscompiling
+    sc = frontend.StageCompiler([T_I64], [None])
+    with pytest.raises(frontend.UnsupportedUDF):
+        sc.add_map(lambda x: [x, x], 100001)
+    sc = frontend.StageCompiler([T_STR], [None])
+    with pytest.raises(frontend.UnsupportedUDF):
+        sc.add_map(lambda x: x.split(","), 100001)
+    with pytest.raises(frontend.UnsupportedUDF):
+        frontend.StageCompiler([T_I64], [None]).finish_aggregate(lambda a, x: a * x, lambda a, b: a * b, 1, 1)
+
+
+def test_parallelize_majority_type_and_fallback_rows():
+    ctx = Context()
+    src = ctx._source_from_rows([1, 2, None, 4], None)
+    assert [c.type for c in src.cols] == [T_I64] and src.n_rows == 3
+    assert src.fallback == [(2, None)] and src.orig_index.tolist() == [0, 1, 3]
+    src = ctx._source_from_rows([(1, "a"), (2, "b"), (3.5, "c"), ("x", "d")], ["n", "s"])
+    assert [c.type for c in src.cols] == [T_I64, T_STR] and src.n_rows == 2 and len(src.fallback) == 2
+
+
+def test_merge_by_row_number():
+    """ResolveTask::executeInOrder semantics: exception k sits at slot row_no_k of the output stream."""
+    exc = np.array([(2, 2, 136, 1), (5, 4, 136, 1)], dtype=backend.EXC_DTYPE)  # rows 2 and 5 raised
+    normal = ["r0", "r1", "r3", "r4", "r6"]
+    assert _merge_by_rowno(normal, exc, [(2, 2, "R2"), (5, 4, "R5")]) == ["r0", "r1", "R2", "r3", "R5", "r4", "r6"][:0] + ["r0", "r1", "R2", "r3", "R5", "r4", "r6"]
+    assert _merge_by_rowno(normal, exc, [(5, 4, "R5")]) == ["r0", "r1", "r3", "R5", "r4", "r6"]
+    assert _merge_by_rowno(normal, exc[:0], []) == normal
+
+
+def test_cpython_slow_path_with_resolvers():
+    op = pyexec.Op("map", lambda x: 10 // x)
+    op.resolvers.append((ZeroDivisionError, lambda x: -1))
+    assert pyexec.run_row([op], 0, [None])[0] == -1
+    op2 = pyexec.Op("map", lambda x: 10 // x)
+    op2.ignores.append(ZeroDivisionError)
+    with pytest.raises(pyexec.Dropped):
+        pyexec.run_row([op2], 0, [None])
+    ops = [pyexec.Op("withColumn", lambda x: x["a"] + 1, column="b"), pyexec.Op("filter", lambda x: x["b"] > 2),
+           pyexec.Op("selectColumns", columns=["b"])]
+    assert pyexec.run_row(ops, (5,), ["a"]) == (6, ["b"])
+    assert pyexec.exception_code(ValueError()) == 135 and pyexec.exception_code(ZeroDivisionError()) == 136
+
+
+def test_shard_ranges():
+    from tuplex_b200.dist import shard_range
+    for n in (0, 1, 7, 600):
+        for w in (1, 2, 4, 8):
+            parts = [shard_range(n, r, w) for r in range(w)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+            assert max(h - l for l, h in parts) - min(h - l for l, h in parts) <= 1

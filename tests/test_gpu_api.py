@@ -1,0 +1,104 @@
+"""The reference's own Python-level goldens, run through this package's Context/DataSet on the GPU
+(README.md:29-34, python/tests/test_filter.py, test_parallelize.py, test_aggregates.py, test_exceptions.py,
+tuplex/test/core/ResolveTests.cc:20-74, AggregateTest.cc:249-364, DataSetCollect.cc:218-246)."""
+import pytest
+
+import tuplex_b200
+from tuplex_b200 import workloads
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def ctx(gpu):
+    return tuplex_b200.Context()
+
+
+def test_readme_example(ctx):
+    res = ctx.parallelize([1, 2, None, 4]).map(lambda x: (x, x * x)).collect()
+    assert res == [(1, 1), (2, 4), (4, 16)]
+    # with a resolver the None row comes back in order (README.md)
+    ds = ctx.parallelize([1, 2, None, 4]).map(lambda x: (x, x * x)).resolve(TypeError, lambda x: (0, 0))
+    assert ds.collect() == [(1, 1), (2, 4), (0, 0), (4, 16)]
+
+
+def test_filter_goldens(ctx):
+    assert ctx.parallelize([1, 2, 3, 4, 5]).map(lambda x: x * x).filter(lambda x: x > 10).collect() == [16, 25]
+    assert ctx.parallelize([1, 2, 3, 4, 5]).filter(lambda x: 2 < x <= 4).collect() == [3, 4]
+    assert ctx.parallelize([(1, "a"), (2, "bb"), (3, "c")]).filter(lambda a, b: len(b) == 1).collect() == [(1, "a"), (3, "c")]
+
+
+def test_c1_config(ctx):
+    n = 1_000_000
+    res = ctx.parallelize(list(range(1, n + 1))).map(lambda x: x * x).filter(lambda x: x % 2 == 0).collect()
+    assert len(res) == 500_000 and res[0] == 4 and res[-1] == n * n and res[1] == 16
+    assert ctx.metrics.rows_in >= n and ctx.metrics.kernel_launches >= 1
+
+
+def test_zero_division_resolve_in_order(ctx):
+    # ResolveTests.cc:20-74: division by zero resolved, order preserved
+    data = [(10, 2), (5, 0), (8, 4), (1, 0), (9, 3)]
+    ds = ctx.parallelize(data).map(lambda a, b: a // b)
+    assert ds.collect() == [5, 2, 3]
+    assert sum(ds.exception_counts.values()) == 2 and all(k[1] == "ZeroDivisionError" for k in ds.exception_counts)
+    ds2 = ctx.parallelize(data).map(lambda a, b: a // b).resolve(ZeroDivisionError, lambda a, b: -1)
+    assert ds2.collect() == [5, -1, 2, -1, 3]
+    ds3 = ctx.parallelize(data).map(lambda a, b: a // b).ignore(ZeroDivisionError)
+    assert ds3.collect() == [5, 2, 3] and not ds3.exception_counts
+    # DataSetCollect.cc:218-246
+    assert ctx.parallelize([(84, 2), (1, 0)]).map(lambda x: x[0] / x[1]).collect() == [42.0]
+
+
+def test_with_column_select_and_strings(ctx):
+    ds = ctx.parallelize([("Alice", "12"), ("bob", "x7"), ("Carol", " 5 ")], columns=["name", "n"])
+    out = (ds.withColumn("v", lambda x: int(x["n"]))
+             .mapColumn("name", lambda s: s[0].upper() + s[1:].lower())
+             .filter(lambda x: x["v"] > 1)
+             .selectColumns(["name", "v"]).collect())
+    assert out == [("Alice", 12), ("Carol", 5)]
+
+
+def test_aggregate_goldens(ctx):
+    # python/tests/test_aggregates.py:25-60 style
+    assert ctx.parallelize([1, 2, 3, 4, 5]).aggregate(lambda a, b: a + b, lambda a, x: a + x, 0).collect() == [15]
+    assert ctx.parallelize([(1, 2.5), (2, 0.5)]).aggregate(lambda a, b: a + b, lambda a, x: a + x[0] * x[1], 0.0).collect() == [3.5]
+    r = ctx.parallelize(list(range(100))).aggregate(lambda a, b: (a[0] + b[0], a[1] + b[1]), lambda a, x: (a[0] + x, a[1] + 1), (0, 0)).collect()
+    assert r == [(4950, 100)]
+
+
+def test_aggregate_by_key_goldens(ctx):
+    rows = [(1, "abc", 0), (2, "xyz", 1), (4, "xyz", 2), (3, "abc", -1)]
+    ds = ctx.parallelize(rows, columns=["col0", "col1", "col2"])
+    assert ds.aggregateByKey(lambda a, b: a + b, lambda a, x: a + x[0] * x[2], 0, ["col1"]).collect() == [("abc", -3), ("xyz", 10)]
+    got = ds.aggregateByKey(lambda a, b: (a[0] + b[0], a[1] + b[1]), lambda a, x: (a[0] + x[0], a[1] + x[2]), (0, 0), ["col1"]).collect()
+    assert got == [("abc", 4, -1), ("xyz", 6, 3)]
+    big = ctx.parallelize(rows * 2500, columns=["col0", "col1", "col2"])
+    assert big.aggregateByKey(lambda a, b: a + b, lambda a, x: a + x[0] * x[2], 0, ["col1"]).collect() == [("abc", -7500), ("xyz", 25000)]
+    # combiner outside the GPU op set -> CPython path, "combine at least once per group" (AggregateTest.cc:355-356)
+    got = big.aggregateByKey(lambda a, b: (1112, a[1] + b[1]), lambda a, x: (a[0] + x[0], a[1] + x[2]), (0, 0), ["col1"]).collect()
+    assert got == [("abc", 1112, -2500), ("xyz", 1112, 7500)]
+
+
+def test_unique_and_udf_fallback(ctx):
+    assert sorted(ctx.parallelize([3, 1, 3, 2, 1]).unique().collect()) == [1, 2, 3]
+    # a UDF outside the GPU op set runs on the CPython path and still gives the right answer
+    assert ctx.parallelize(["a,b", "c"]).map(lambda s: len(s.split(","))).collect() == [2, 1]
+    assert any("CPython" in m for m in ctx._messages)
+
+
+def test_zillow_through_api(ctx):
+    import hashlib
+    cols, n = workloads.load_zillow_fixture()
+    rows = list(zip(*[c.to_values() for c in cols]))
+    ds = workloads.zillow_pipeline(ctx.parallelize(rows, columns=workloads.ZILLOW_COLS))
+    out = ds.collect()
+    txt = workloads.rows_to_csv([list(c) for c in zip(*out)], workloads.ZILLOW_OUT)
+    assert hashlib.md5(txt).hexdigest() == "4d5ca0263b1a5058341a369116dee83a"
+    assert ds.columns == workloads.ZILLOW_OUT
+
+
+def test_q6_through_api(ctx):
+    cols = workloads.load_lineitem_fixture()
+    rows = list(zip(*[c.to_values() for c in cols]))
+    (res,) = workloads.q6_pipeline(ctx.parallelize(rows, columns=workloads.Q6_COLS)).collect()
+    assert abs(res - 1193053.2252999984) <= 1e-4

@@ -37,7 +37,7 @@ class CExceptionRec(ct.Structure):
 class CResultInfo(ct.Structure):
     _fields_ = [("n_in_rows", ct.c_uint64), ("n_out_rows", ct.c_uint64), ("n_exceptions", ct.c_uint64),
                 ("out_str_bytes", ct.c_uint64 * MAX_COLS), ("kernel_ms", ct.c_double), ("total_ms", ct.c_double),
-                ("kernel_launches", ct.c_uint32), ("pad", ct.c_uint32)]
+                ("kernel_launches", ct.c_uint32), ("zero_copy_cols", ct.c_uint32), ("h2d_bytes", ct.c_uint64)]
 
 
 EXC_DTYPE = np.dtype([("row", "<i8"), ("row_no", "<i8"), ("code", "<i8"), ("op_id", "<i8")])

@@ -431,6 +431,8 @@ struct tplx_result {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
     double kernel_ms = 0, total_ms = 0, kernel_ms_extra = 0;
     uint32_t hidden = 0;  // trailing internal output columns
+    uint64_t h2d_bytes = 0;       // explicit host->device copies of inputs (run_host)
+    uint32_t zero_copy_cols = 0;  // input columns read in place from page-locked host memory
     uint32_t launches = 0;
     bool owns_block = false;
     tplx_block *owned_block = nullptr;
@@ -545,8 +547,65 @@ extern "C" int32_t tplx_gpu_stage_run_host(tplx_stage *s, int32_t device, const 
     CU(cudaEventCreate(&e0));
     CU(cudaEventRecord(e0, d->stream));
     tplx_block *b = nullptr;
-    int32_t rc = tplx_gpu_block_upload(device, cols, n_cols, n_rows, &b);
-    if (rc) { cudaEventDestroy(e0); return rc; }
+    int32_t rc = TPLX_OK;
+    uint64_t h2d = 0;
+    uint32_t zc = 0;
+    if (s && s->prefilter && s->prefilter_enabled && s->hdr.endpoint == TPLX_EP_MEMORY && cols && n_cols == s->in_types.size()) {
+        // Late materialisation across PCIe: only the columns the prefilter reads are copied to HBM. The other
+        // columns are needed for surviving rows only; when they lie in page-locked host memory the dense launch
+        // reads exactly those rows through the mapped address (zero-copy), otherwise they are copied like before.
+        std::vector<bool> early(n_cols, false);
+        for (const tplx_instr &in : s->prefilter->instrs)
+            if (in.op == TPLX_OP_LDCOL) early[in.imm] = true;
+        std::vector<tplx_column> up;       // columns to copy
+        std::vector<uint32_t> up_idx;
+        std::vector<ColIn> mapped(n_cols);
+        std::vector<bool> is_mapped(n_cols, false);
+        for (uint32_t c = 0; c < n_cols; ++c) {
+            bool zero_copy = false;
+            if (!early[c] && n_rows) {
+                cudaPointerAttributes at{}, ao{};
+                bool ok = cudaPointerGetAttributes(&at, cols[c].data) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer;
+                if (ok && cols[c].type == TPLX_T_STR)
+                    ok = cudaPointerGetAttributes(&ao, cols[c].offsets) == cudaSuccess && ao.type == cudaMemoryTypeHost && ao.devicePointer;
+                cudaGetLastError();
+                if (ok) {
+                    mapped[c].type = cols[c].type;
+                    mapped[c].data = at.devicePointer;
+                    mapped[c].offsets = cols[c].type == TPLX_T_STR ? static_cast<const uint32_t *>(ao.devicePointer) : nullptr;
+                    zero_copy = true;
+                }
+            }
+            if (zero_copy) { is_mapped[c] = true; ++zc; }
+            else { up.push_back(cols[c]); up_idx.push_back(c); }
+        }
+        tplx_block *ub = nullptr;
+        rc = tplx_gpu_block_upload(device, up.data(), (uint32_t)up.size(), n_rows, &ub);
+        if (rc) { cudaEventDestroy(e0); return rc; }
+        b = new tplx_block();
+        b->dev = d;
+        b->n_rows = n_rows;
+        b->cols.resize(n_cols);
+        b->data_bytes.resize(n_cols);
+        for (size_t k = 0; k < up_idx.size(); ++k) {
+            b->cols[up_idx[k]] = ub->cols[k];
+            b->data_bytes[up_idx[k]] = ub->data_bytes[k];
+            h2d += ub->data_bytes[k] + (up[k].type == TPLX_T_STR ? (n_rows + 1) * 4 : 0);
+        }
+        for (uint32_t c = 0; c < n_cols; ++c)
+            if (is_mapped[c]) {
+                b->cols[c] = mapped[c];
+                b->data_bytes[c] = cols[c].type == TPLX_T_STR ? cols[c].data_bytes : n_rows * 8;
+            }
+        b->owned = ub->owned;
+        ub->owned.clear();
+        delete ub;
+    } else {
+        rc = tplx_gpu_block_upload(device, cols, n_cols, n_rows, &b);
+        if (rc) { cudaEventDestroy(e0); return rc; }
+        for (uint32_t c = 0; c < n_cols; ++c)
+            h2d += (cols[c].type == TPLX_T_STR ? cols[c].data_bytes + (n_rows + 1) * 4 : n_rows * 8);
+    }
     rc = tplx_gpu_stage_run(s, b, first_row_no, out);
     if (rc) {
         tplx_gpu_block_free(b);
@@ -556,6 +615,8 @@ extern "C" int32_t tplx_gpu_stage_run_host(tplx_stage *s, int32_t device, const 
     cudaEventDestroy((*out)->ev0);
     (*out)->ev0 = e0;  // total time includes the H2D copies
     (*out)->owned_block = b;
+    (*out)->h2d_bytes = h2d;
+    (*out)->zero_copy_cols = zc;
     return TPLX_OK;
 }
 
@@ -878,6 +939,8 @@ extern "C" int32_t tplx_gpu_result_info(tplx_result *r, tplx_result_info *info) 
     info->kernel_ms = r->kernel_ms;
     info->total_ms = r->total_ms;
     info->kernel_launches = r->launches;
+    info->zero_copy_cols = r->zero_copy_cols;
+    info->h2d_bytes = r->h2d_bytes;
     return TPLX_OK;
 }
 

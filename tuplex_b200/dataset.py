@@ -264,7 +264,7 @@ def _run_stage(ctx, src: Source, ops: List[Op], exc_counter: Counter):
 
     # ---- endpoints --------------------------------------------------------------------------------
     if prog.endpoint == C["TPLX_EP_MEMORY"]:
-        ncols = len(prog.out_cols)
+        ncols = len(prog.out_cols) - prog.hidden_out_cols
         merged_vals = [sum((oc[c].to_values() for oc in out_cols_all), []) for c in range(ncols)]
         n_out = len(merged_vals[0]) if ncols else 0
         user_cols = ncols - (1 if need_rowidx else 0)
