@@ -24,7 +24,7 @@ extern "C" {
 #endif
 
 #define TPLX_IR_MAGIC 0x58504C54u /* "TPLX" */
-#define TPLX_IR_VERSION 5u
+#define TPLX_IR_VERSION 6u
 #define TPLX_NOSLOT 0xFFFFu
 #define TPLX_MAX_COLS 64
 #define TPLX_MAX_ACCS 16
@@ -212,6 +212,7 @@ typedef struct tplx_acc {
  *   tplx_instr instrs[n_instr]
  *   uint8_t  const_pool[const_bytes]  (padded to 8)
  *   uint8_t  prefilter[prefilter_bytes]  -- optional nested stage descriptor (same layout), see below
+ *   uint8_t  fused[fused_bytes]          -- optional tplx_fused_header + predicates + terms, see below
  *
  * Prefilter (selective pipelines): a MEMORY stage whose single output column is the row index
  * (TPLX_OP_LDROW) of the rows that survive the leading, selective part of the pipeline. The executor runs
@@ -219,6 +220,48 @@ typedef struct tplx_acc {
  * columns that only survivors need are never read for the other rows). It is an execution hint: running
  * this stage over all rows gives the same result, which is what the oracle does.
  */
+/*
+ * Fused scan-aggregate hint (AGGREGATE endpoint): when every operator of the stage is a filter made of range
+ * comparisons between one fixed-width column and constants, and every accumulator is a sum of a constant, a column
+ * or a product of two columns (the TPC-H Q6 class, benchmarks/tpch/Q06/runtuplex.py:96-99), the planner ALSO
+ * states the stage in this closed form. The executor may then run a dedicated streaming kernel instead of the VM.
+ * Like the prefilter it is an execution hint: same rows, same per-row IEEE operations, same reduction tree — the
+ * oracle ignores it and the parity tests compare the two.
+ */
+#define TPLX_FUSED_MAGIC 0x31415346u /* "FSA1" */
+enum tplx_fused_predflag {
+    TPLX_FP_F64 = 1,      /* compare as f64 (ordered), else signed i64 */
+    TPLX_FP_HAS_LO = 2,
+    TPLX_FP_LO_INCL = 4,
+    TPLX_FP_HAS_HI = 8,
+    TPLX_FP_HI_INCL = 16,
+    TPLX_FP_CAST = 32,    /* column is i64, converted with sitofp before an f64 compare */
+};
+enum tplx_fused_termop {
+    TPLX_FT_CONST = 0,    /* g(x) = imm */
+    TPLX_FT_COL = 1,      /* g(x) = col_a */
+    TPLX_FT_MUL = 2,      /* g(x) = col_a * col_b (single IEEE multiply, or wrapping i64 multiply) */
+};
+typedef struct tplx_fused_pred {
+    uint32_t col;
+    uint32_t flags; /* tplx_fused_predflag */
+    int64_t lo, hi; /* i64 values or f64 bits */
+} tplx_fused_pred;
+typedef struct tplx_fused_term {
+    uint32_t kind;   /* tplx_acc_kind, same order as the stage's accumulators */
+    uint32_t op;     /* tplx_fused_termop */
+    uint32_t col_a, col_b;
+    uint32_t cast_a, cast_b; /* 1: i64 column converted with sitofp first */
+    int64_t imm;
+} tplx_fused_term;
+typedef struct tplx_fused_header {
+    uint32_t magic;
+    uint32_t n_preds;
+    uint32_t n_terms;
+    uint32_t pad;
+} tplx_fused_header;
+#define TPLX_MAX_FUSED_PREDS 8
+
 typedef struct tplx_stage_header {
     uint32_t magic;
     uint32_t version;
@@ -237,7 +280,7 @@ typedef struct tplx_stage_header {
                                  row, used to number exception rows when a prefilter ran); never handed out */
     uint32_t scratch_bytes;   /* per-row scratch for materialised strings */
     uint32_t prefilter_bytes; /* size of the nested prefilter stage descriptor, 0 = none */
-    uint32_t pad1;
+    uint32_t fused_bytes;     /* size of the optional fused-scan section (tplx_fused_header ...), 0 = none */
 } tplx_stage_header;
 
 #ifdef __cplusplus

@@ -252,7 +252,7 @@ static int parse_stage(const void *desc, uint64_t bytes, ostage *s) {
     off += (size_t)s->h.n_instr * sizeof(tplx_instr);
     s->cpool = p + off;
     /* a nested prefilter stage is an execution hint only: the oracle runs the full stage over every row */
-    return off + pad8(s->h.const_bytes) + s->h.prefilter_bytes == bytes ? 0 : -1;
+    return off + pad8(s->h.const_bytes) + s->h.prefilter_bytes + s->h.fused_bytes == bytes ? 0 : -1;
 }
 
 static double as_f(int64_t bits) {

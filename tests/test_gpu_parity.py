@@ -243,3 +243,35 @@ def test_prefilter_exception_numbering(gpu):
     assert p2.prefilter is None
     st2, res2, ora2 = run_both(p2, cols, n, first_row_no=5)
     assert_result_equals_oracle(res2, ora, "no prefilter")
+
+
+def test_fused_scan_aggregate_matches_vm_and_oracle(gpu):
+    """K3f (closed-form streaming kernel) vs the VM path (TPLX_NO_FUSED=1) vs the oracle: identical bits."""
+    import os
+    n = 1_000_003
+    cols = workloads.gen_lineitem(n, seed=7)
+    progs = []
+    progs.append(workloads.q6_program())
+    sc = frontend.StageCompiler(workloads.Q6_TYPES, workloads.Q6_COLS)
+    sc.add_filter(lambda x: 0.06 - 0.01 <= x['l_discount'] <= 0.06 + 0.01 and x['l_quantity'] < 24, 100001)
+    sc.add_filter(lambda x: x['l_shipdate'] >= 19940101, 100002)
+    progs.append(sc.finish_aggregate(lambda a, x: (a[0] + 1, a[1] + x[0], a[2] + x[1]), lambda a, b: (a[0] + b[0], a[1] + b[1], a[2] + b[2]),
+                                     (0, 0, 0.0), 100003))
+    sc = frontend.StageCompiler(workloads.Q6_TYPES, workloads.Q6_COLS)
+    sc.add_filter(lambda x: x['l_quantity'] == 7, 100001)
+    sc.add_filter(lambda x: x['l_quantity'] < 20.5, 100002)   # i64 column against a float constant -> f64 compare
+    progs.append(sc.finish_aggregate(lambda a, x: a + x[0] * x[3], lambda a, b: a + b, 0, 100003))
+    sc = frontend.StageCompiler(workloads.Q6_TYPES, workloads.Q6_COLS)
+    progs.append(sc.finish_aggregate(lambda a, x: a + x[0] * x[2], lambda a, b: a + b, 0.0, 100001))  # no filter, i64 * f64
+    for i, prog in enumerate(progs):
+        assert prog.fused is not None, f"program {i} should match the closed form"
+        st = backend.Stage(prog)
+        ora = pyoracle.run_program(prog, cols, n)
+        os.environ.pop("TPLX_NO_FUSED", None)
+        fused_bits = st.run_host(0, cols, n).aggregate_bits()
+        os.environ["TPLX_NO_FUSED"] = "1"
+        try:
+            vm_bits = st.run_host(0, cols, n).aggregate_bits()
+        finally:
+            os.environ.pop("TPLX_NO_FUSED", None)
+        assert fused_bits == vm_bits == ora.acc_tree, f"program {i}"

@@ -21,6 +21,7 @@
 #include "kernels.cuh"
 #include "rowfmt.cuh"
 #include "hashagg.cuh"
+#include "fused.cuh"
 
 using namespace tplx;
 
@@ -155,6 +156,8 @@ struct tplx_stage {
     tplx_stage *prefilter = nullptr;  // nested selective stage (row index output), may be null
     bool prefilter_enabled = true;    // switched off at run time when it turns out not to be selective
     uint32_t hidden = 0;              // trailing executor-internal output columns
+    bool has_fused = false;           // closed-form scan-aggregate hint present and valid
+    FusedParams fused{};
     std::mutex mu;
 };
 
@@ -259,6 +262,34 @@ extern "C" int32_t tplx_gpu_stage_create(const void *desc, uint64_t desc_bytes, 
             q->in_types != s->in_types || !s->hidden)
             return bad("stage descriptor: prefilter must be a row-index MEMORY stage over the same input schema");
         off += h.prefilter_bytes;
+    }
+    if (h.fused_bytes) {
+        // closed-form scan-aggregate hint (execution hint; validated, and ignored when it does not fit)
+        if (!need(h.fused_bytes) || h.fused_bytes < sizeof(tplx_fused_header) || h.endpoint != TPLX_EP_AGGREGATE)
+            return bad("stage descriptor: bad fused section");
+        tplx_fused_header fh;
+        memcpy(&fh, p + off, sizeof(fh));
+        if (fh.magic != TPLX_FUSED_MAGIC || fh.n_preds > TPLX_MAX_FUSED_PREDS || fh.n_terms != h.n_accs ||
+            h.fused_bytes != sizeof(fh) + fh.n_preds * sizeof(tplx_fused_pred) + fh.n_terms * sizeof(tplx_fused_term))
+            return bad("stage descriptor: malformed fused section");
+        FusedParams &F = s->fused;
+        memset(&F, 0, sizeof(F));
+        F.n_preds = fh.n_preds;
+        F.n_terms = fh.n_terms;
+        memcpy(F.preds, p + off + sizeof(fh), fh.n_preds * sizeof(tplx_fused_pred));
+        memcpy(F.terms, p + off + sizeof(fh) + fh.n_preds * sizeof(tplx_fused_pred), fh.n_terms * sizeof(tplx_fused_term));
+        bool ok = true;
+        auto fixed_col = [&](uint32_t c) { return c < h.n_in_cols && s->in_types[c] != TPLX_T_STR; };
+        for (uint32_t i = 0; i < F.n_preds; ++i) ok = ok && fixed_col(F.preds[i].col);
+        for (uint32_t i = 0; i < F.n_terms; ++i) {
+            const tplx_fused_term &t = F.terms[i];
+            ok = ok && t.kind == s->accs[i].kind && t.op <= TPLX_FT_MUL && (t.kind == TPLX_ACC_SUM_I64 || t.kind == TPLX_ACC_SUM_F64);
+            if (t.op != TPLX_FT_CONST) ok = ok && fixed_col(t.col_a);
+            if (t.op == TPLX_FT_MUL) ok = ok && fixed_col(t.col_b);
+        }
+        if (!ok) return bad("stage descriptor: fused section references bad columns or accumulators");
+        s->has_fused = true;
+        off += h.fused_bytes;
     }
     for (auto t : s->in_types) {
         if (t > TPLX_T_STR) return bad("stage descriptor: unknown input type");
@@ -853,6 +884,44 @@ static int32_t run_rows_prefiltered(tplx_stage *s, StageDev *sd, const tplx_bloc
     return TPLX_OK;
 }
 
+// K3f dispatch: smallest instantiation that holds the predicates / terms; padding entries are neutral
+template <int NP>
+static int32_t launch_fused_np(uint32_t ntm, uint32_t grid, cudaStream_t st, const KParams *dP, const FusedParams *dF) {
+    switch (ntm) {
+        case 1: fused_scan_agg_kernel<NP, 1><<<grid, NT, 0, st>>>(dP, dF); break;
+        case 2: fused_scan_agg_kernel<NP, 2><<<grid, NT, 0, st>>>(dP, dF); break;
+        case 4: fused_scan_agg_kernel<NP, 4><<<grid, NT, 0, st>>>(dP, dF); break;
+        default: fused_scan_agg_kernel<NP, 8><<<grid, NT, 0, st>>>(dP, dF); break;
+    }
+    return TPLX_OK;
+}
+static int32_t launch_fused(tplx_stage *s, Device *d, const KParams *dP, const KParams &P, tplx_result *r) {
+    FusedParams F = s->fused;
+    uint32_t np = F.n_preds <= 1 ? 1 : F.n_preds <= 2 ? 2 : F.n_preds <= 3 ? 3 : F.n_preds <= 4 ? 4 : 8;
+    uint32_t ntm = F.n_terms <= 1 ? 1 : F.n_terms <= 2 ? 2 : F.n_terms <= 4 ? 4 : 8;
+    if (F.n_terms > 8) return fail(TPLX_E_UNSUPPORTED, "fused scan: too many accumulators");
+    const uint32_t some_col = F.n_preds ? F.preds[0].col : (F.terms[0].op != TPLX_FT_CONST ? F.terms[0].col_a : 0);
+    for (uint32_t i = F.n_preds; i < np; ++i) { F.preds[i].col = some_col; F.preds[i].flags = 0; }
+    for (uint32_t i = F.n_terms; i < ntm; ++i) { F.terms[i] = tplx_fused_term{}; F.terms[i].kind = TPLX_ACC_SUM_I64; F.terms[i].op = TPLX_FT_CONST; }
+    if (P.n_in == 0) return fail(TPLX_E_UNSUPPORTED, "fused scan without input columns");
+    FusedParams *dF = nullptr;
+    int32_t rc = dalloc(r, &dF, 1);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(dF, &F, sizeof(F), cudaMemcpyHostToDevice, d->stream));
+    // memory-bound streaming kernel: fill every SM with resident CTAs (multiple of the SM count)
+    const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(P.n_tiles, (uint32_t)d->prop.multiProcessorCount * 8));
+    switch (np) {
+        case 1: launch_fused_np<1>(ntm, grid, d->stream, dP, dF); break;
+        case 2: launch_fused_np<2>(ntm, grid, d->stream, dP, dF); break;
+        case 3: launch_fused_np<3>(ntm, grid, d->stream, dP, dF); break;
+        case 4: launch_fused_np<4>(ntm, grid, d->stream, dP, dF); break;
+        default: launch_fused_np<8>(ntm, grid, d->stream, dP, dF); break;
+    }
+    CU(cudaGetLastError());
+    r->launches += 1;
+    return TPLX_OK;
+}
+
 static int32_t run_agg(tplx_stage *s, StageDev *sd, const tplx_block *b, tplx_result *r) {
     Device *d = sd->dev;
     const uint64_t n = b->n_rows;
@@ -889,7 +958,10 @@ static int32_t run_agg(tplx_stage *s, StageDev *sd, const tplx_block *b, tplx_re
         CU(cudaMemsetAsync(counters, 0, 16, d->stream));
         CU(cudaMemcpyAsync(dP, &P, sizeof(P), cudaMemcpyHostToDevice, d->stream));
         CU(cudaEventRecord(r->evk0, d->stream));
-        if (P.n_tiles) {
+        if (P.n_tiles && s->has_fused && !getenv("TPLX_NO_FUSED")) {
+            int32_t frc = launch_fused(s, d, dP, P, r);
+            if (frc) return frc;
+        } else if (P.n_tiles) {
             stage_agg_kernel<<<grid, NT, L.total, d->stream>>>(dP);
             CU(cudaGetLastError());
             r->launches += 1;

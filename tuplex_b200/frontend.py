@@ -482,6 +482,10 @@ class StageCompiler:
 
     def finish_aggregate(self, agg_func, combine_func, init, op_id: int) -> Program:
         """aggregate(combine, agg, init) -> AGG_GENERAL endpoint (AggregateFunctions.cc:16-243)."""
+        try:
+            self.prog.fused = _match_fused_scan_aggregate(self, agg_func, combine_func, init)
+        except UnsupportedUDF:
+            self.prog.fused = None
         self.begin_op(op_id)
         accs = self._lower_aggregate(agg_func, combine_func, init)
         self.prog.endpoint = C["TPLX_EP_AGGREGATE"]
@@ -635,6 +639,155 @@ class StageCompiler:
         if self.prog.n_slots >= NOSLOT:
             raise UnsupportedUDF("program too large")
         return [assign[r] for r in live_out]
+
+
+def _match_fused_scan_aggregate(sc: "StageCompiler", agg_func, combine_func, init) -> Optional[bytes]:
+    """Recognise the closed form `filters of (column <op> constant) ranges -> sum of const | col | col*col`
+    (include/tplx_ir.h tplx_fused_header). Returns the serialized hint or None. Works on a scratch compiler so the
+    real program is untouched; constants go through the same folding (incl. the reference's 6-digit quirk)."""
+    import struct
+    if any(name != "add_filter" for name, _ in sc.oplog):
+        return None
+    tmp = StageCompiler(sc.prog.in_types, sc.prog.in_names)
+    fixed = (T_I64, T_F64, T_BOOL)
+
+    def col_of(v):
+        if isinstance(v, Val) and tmp._is_colref(v) and v.type in fixed:
+            return v.const[1]
+        return None
+
+    preds = {}  # col -> [flags, lo, hi] merged per column and compare domain
+
+    def add_bound(col, as_f64, cast, is_lo, value, incl):
+        key = (col, as_f64)
+        e = preds.setdefault(key, {"lo": None, "hi": None, "cast": cast})
+        cur = e["lo" if is_lo else "hi"]
+        cand = (value, incl)
+        if cur is None:
+            e["lo" if is_lo else "hi"] = cand
+        else:  # keep the tighter bound
+            if is_lo:
+                tighter = cand[0] > cur[0] or (cand[0] == cur[0] and not cand[1])
+            else:
+                tighter = cand[0] < cur[0] or (cand[0] == cur[0] and not cand[1])
+            if tighter:
+                e["lo" if is_lo else "hi"] = cand
+
+    def one_compare(op, l, r):
+        cl, cr = col_of(l), col_of(r)
+        if (cl is None) == (cr is None):
+            raise UnsupportedUDF("fused: need exactly one column per comparison")
+        col = cl if cl is not None else cr
+        k = r if cl is not None else l
+        if not tmp.is_const(k) or isinstance(k.const, str):
+            raise UnsupportedUDF("fused: non-constant bound")
+        ctype = tmp.row[col].type
+        as_f64 = ctype == T_F64 or isinstance(k.const, float)
+        cast = as_f64 and ctype != T_F64
+        val = float(k.const) if as_f64 else int(k.const)
+        t = type(op)
+        if cl is None:  # const OP col  ->  col OP' const
+            t = {ast.Lt: ast.Gt, ast.LtE: ast.GtE, ast.Gt: ast.Lt, ast.GtE: ast.LtE, ast.Eq: ast.Eq}.get(t)
+        if t is ast.Lt:
+            add_bound(col, as_f64, cast, False, val, False)
+        elif t is ast.LtE:
+            add_bound(col, as_f64, cast, False, val, True)
+        elif t is ast.Gt:
+            add_bound(col, as_f64, cast, True, val, False)
+        elif t is ast.GtE:
+            add_bound(col, as_f64, cast, True, val, True)
+        elif t is ast.Eq:
+            add_bound(col, as_f64, cast, True, val, True)
+            add_bound(col, as_f64, cast, False, val, True)
+        else:
+            raise UnsupportedUDF("fused: comparison operator")
+
+    def walk(fc, node):
+        if isinstance(node, ast.BoolOp) and isinstance(node.op, ast.And):
+            for v in node.values:
+                walk(fc, v)
+            return
+        if not isinstance(node, ast.Compare):
+            raise UnsupportedUDF("fused: filter is not a comparison")
+        left = fc.expr(node.left)
+        for op, rn in zip(node.ops, node.comparators):
+            right = fc.expr(rn)
+            one_compare(op, left, right)
+            left = right
+
+    for _, (func, _opid) in sc.oplog:
+        argn, body, env = get_udf_ast(func)
+        body = _single_return(body)
+        if len(argn) != 1:
+            raise UnsupportedUDF("fused: filter arity")
+        fc = _FuncCompiler(tmp, env)
+        fc.env[argn[0]] = tmp.row_value()
+        walk(fc, body)
+    if len(tmp.prog.instrs):
+        raise UnsupportedUDF("fused: filter needed run-time evaluation")
+
+    # aggregate terms
+    inits = list(init) if isinstance(init, (tuple, list)) else [init]
+    an, abody, aenv = get_udf_ast(agg_func)
+    abody = _single_return(abody)
+    parts = abody.elts if isinstance(abody, ast.Tuple) else [abody]
+    if len(an) != 2 or len(parts) != len(inits):
+        raise UnsupportedUDF("fused: aggregate shape")
+    terms = []
+    fc = _FuncCompiler(tmp, aenv)
+    fc.env[an[1]] = tmp.row_value()
+    for i, (ap, iv) in enumerate(zip(parts, inits)):
+        if not (isinstance(ap, ast.BinOp) and isinstance(ap.op, ast.Add)):
+            raise UnsupportedUDF("fused: term")
+
+        def is_acc(n_):
+            if len(inits) == 1 and isinstance(n_, ast.Name) and n_.id == an[0]:
+                return True
+            return (isinstance(n_, ast.Subscript) and isinstance(n_.value, ast.Name) and n_.value.id == an[0]
+                    and isinstance(n_.slice, ast.Constant) and n_.slice.value == i)
+        g = ap.right if is_acc(ap.left) else ap.left if is_acc(ap.right) else None
+        if g is None or _mentions(g, an[0]):
+            raise UnsupportedUDF("fused: term")
+        is_f = isinstance(iv, float)
+        if isinstance(g, ast.BinOp) and isinstance(g.op, ast.Mult):
+            a_, b_ = fc.expr(g.left), fc.expr(g.right)
+            ca, cb = col_of(a_), col_of(b_)
+            if ca is None or cb is None:
+                raise UnsupportedUDF("fused: product of non-columns")
+            ta, tb = tmp.row[ca].type, tmp.row[cb].type
+            f = is_f or ta == T_F64 or tb == T_F64
+            terms.append((C["TPLX_ACC_SUM_F64"] if f else C["TPLX_ACC_SUM_I64"], C["TPLX_FT_MUL"], ca, cb,
+                          int(f and ta != T_F64), int(f and tb != T_F64), 0))
+        else:
+            v = fc.expr(g)
+            cv = col_of(v)
+            if cv is not None:
+                f = is_f or tmp.row[cv].type == T_F64
+                terms.append((C["TPLX_ACC_SUM_F64"] if f else C["TPLX_ACC_SUM_I64"], C["TPLX_FT_COL"], cv, 0,
+                              int(f and tmp.row[cv].type != T_F64), 0, 0))
+            elif tmp.is_const(v) and not isinstance(v.const, str):
+                f = is_f or isinstance(v.const, float)
+                imm = ir.f64_bits(float(v.const)) if f else int(v.const) & ((1 << 64) - 1)
+                terms.append((C["TPLX_ACC_SUM_F64"] if f else C["TPLX_ACC_SUM_I64"], C["TPLX_FT_CONST"], 0, 0, 0, 0, imm))
+            else:
+                raise UnsupportedUDF("fused: term")
+    if len(tmp.prog.instrs) or len(preds) > C["TPLX_MAX_FUSED_PREDS"] or not terms:
+        raise UnsupportedUDF("fused: not closed form")
+    # the combiner must be the matching sum (checked by _lower_aggregate on the real program)
+    out = struct.pack("<IIII", C["TPLX_FUSED_MAGIC"], len(preds), len(terms), 0)
+    for (col, as_f64), e in preds.items():
+        fl = (C["TPLX_FP_F64"] if as_f64 else 0) | (C["TPLX_FP_CAST"] if e["cast"] else 0)
+        lo = hi = 0
+        if e["lo"] is not None:
+            fl |= C["TPLX_FP_HAS_LO"] | (C["TPLX_FP_LO_INCL"] if e["lo"][1] else 0)
+            lo = ir.f64_bits(e["lo"][0]) if as_f64 else e["lo"][0] & ((1 << 64) - 1)
+        if e["hi"] is not None:
+            fl |= C["TPLX_FP_HAS_HI"] | (C["TPLX_FP_HI_INCL"] if e["hi"][1] else 0)
+            hi = ir.f64_bits(e["hi"][0]) if as_f64 else e["hi"][0] & ((1 << 64) - 1)
+        out += struct.pack("<IIQQ", col, fl, lo, hi)
+    for t in terms:
+        out += struct.pack("<IIIIIIQ", *t)
+    return out
 
 
 def _single_return(body):

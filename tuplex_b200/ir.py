@@ -87,6 +87,7 @@ class Program:
     endpoint: int = 0
     hidden_out_cols: int = 0
     prefilter: Optional["Program"] = None  # selective leading part, output = surviving row indices
+    fused: Optional[bytes] = None  # serialized tplx_fused_header section (closed-form scan-aggregate hint)
     scratch_bytes: int = 256
     _cpool_index: Dict[bytes, int] = field(default_factory=dict)
 
@@ -114,11 +115,13 @@ class Program:
         body += pad8(bytes(self.cpool))
         pre = self.prefilter.serialize() if self.prefilter is not None else b""
         body += pre
+        fused = self.fused or b""
+        body += fused
         total = struct.calcsize(HEADER_FMT) + len(body)
         hdr = struct.pack(HEADER_FMT, C["TPLX_IR_MAGIC"], C["TPLX_IR_VERSION"], total, len(self.in_types),
                           len(self.out_cols), len(self.accs), self.n_keys, len(self.opids), self.n_slots,
                           len(self.instrs), len(self.cpool), self.endpoint, 0, self.hidden_out_cols, self.scratch_bytes,
-                          len(pre), 0)
+                          len(pre), len(fused))
         return hdr + body
 
     def dump(self) -> str:
