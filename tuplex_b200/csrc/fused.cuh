@@ -25,19 +25,22 @@ __device__ __forceinline__ uint64_t ld_stream_u64(const uint64_t *p) {
     return v;
 }
 
+// Predicates are normalised on the host (launch_fused) to an inclusive range test on an ordered 64-bit key:
+//   i64 column : key = value
+//   f64 column : key = order-preserving transform of the IEEE bits (-0.0 canonicalised to +0.0; NaN keys fall
+//                outside [key(-inf), key(+inf)], so ordered comparisons with NaN are false like FCMP_O*)
+//   cast       : i64 column converted with sitofp, then as f64
+// strict bounds become inclusive by stepping one key, missing bounds become the extreme keys.
+__host__ __device__ __forceinline__ int64_t f64_key(uint64_t bits) {
+    if (bits == 0x8000000000000000ull) bits = 0;  // -0.0 == +0.0
+    return (int64_t)(bits ^ ((uint64_t)((int64_t)bits >> 63) & 0x7FFFFFFFFFFFFFFFull));
+}
 __device__ __forceinline__ bool pred_pass(const tplx_fused_pred &p, uint64_t raw) {
-    bool ok = true;
-    if (p.flags & TPLX_FP_F64) {
-        const double x = (p.flags & TPLX_FP_CAST) ? (double)(int64_t)raw : __longlong_as_double((long long)raw);
-        const double lo = __longlong_as_double((long long)p.lo), hi = __longlong_as_double((long long)p.hi);
-        if (p.flags & TPLX_FP_HAS_LO) ok = ok && ((p.flags & TPLX_FP_LO_INCL) ? (x >= lo) : (x > lo));
-        if (p.flags & TPLX_FP_HAS_HI) ok = ok && ((p.flags & TPLX_FP_HI_INCL) ? (x <= hi) : (x < hi));
-    } else {
-        const int64_t x = (int64_t)raw;
-        if (p.flags & TPLX_FP_HAS_LO) ok = ok && ((p.flags & TPLX_FP_LO_INCL) ? (x >= p.lo) : (x > p.lo));
-        if (p.flags & TPLX_FP_HAS_HI) ok = ok && ((p.flags & TPLX_FP_HI_INCL) ? (x <= p.hi) : (x < p.hi));
-    }
-    return ok;
+    // p.flags here: 0 = i64 key, 1 = f64 key, 2 = cast then f64 key; p.lo / p.hi = inclusive key bounds
+    int64_t k = (int64_t)raw;
+    if (p.flags == 2) k = f64_key((uint64_t)__double_as_longlong((double)(int64_t)raw));
+    else if (p.flags == 1) k = f64_key(raw);
+    return (k >= p.lo) & (k <= p.hi);
 }
 
 template <int NP, int NTM>

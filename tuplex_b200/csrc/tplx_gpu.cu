@@ -901,7 +901,35 @@ static int32_t launch_fused(tplx_stage *s, Device *d, const KParams *dP, const K
     uint32_t ntm = F.n_terms <= 1 ? 1 : F.n_terms <= 2 ? 2 : F.n_terms <= 4 ? 4 : 8;
     if (F.n_terms > 8) return fail(TPLX_E_UNSUPPORTED, "fused scan: too many accumulators");
     const uint32_t some_col = F.n_preds ? F.preds[0].col : (F.terms[0].op != TPLX_FT_CONST ? F.terms[0].col_a : 0);
-    for (uint32_t i = F.n_preds; i < np; ++i) { F.preds[i].col = some_col; F.preds[i].flags = 0; }
+    // normalise predicates to inclusive ranges over ordered keys (see fused.cuh pred_pass)
+    for (uint32_t i = 0; i < F.n_preds; ++i) {
+        tplx_fused_pred &p = F.preds[i];
+        const uint32_t fl = p.flags;
+        int64_t lo = INT64_MIN, hi = INT64_MAX;
+        if (fl & TPLX_FP_F64) {
+            const int64_t kinf = f64_key(0x7FF0000000000000ull), kninf = f64_key(0xFFF0000000000000ull);
+            lo = kninf;
+            hi = kinf;  // NaN keys lie outside [-inf, +inf]: ordered compares with NaN are false
+            if (fl & TPLX_FP_HAS_LO) {
+                double v; memcpy(&v, &p.lo, 8);
+                if (v != v) { lo = 1; hi = 0; }  // comparison against NaN is never true
+                else { lo = f64_key((uint64_t)p.lo); if (!(fl & TPLX_FP_LO_INCL)) lo = lo == INT64_MAX ? lo : lo + 1; if (lo < kninf) lo = kninf; }
+            }
+            if ((fl & TPLX_FP_HAS_HI) && lo <= hi) {
+                double v; memcpy(&v, &p.hi, 8);
+                if (v != v) { lo = 1; hi = 0; }
+                else { hi = f64_key((uint64_t)p.hi); if (!(fl & TPLX_FP_HI_INCL)) hi = hi == INT64_MIN ? hi : hi - 1; if (hi > kinf) hi = kinf; }
+            }
+            p.flags = (fl & TPLX_FP_CAST) ? 2 : 1;
+        } else {
+            if (fl & TPLX_FP_HAS_LO) { lo = p.lo; if (!(fl & TPLX_FP_LO_INCL)) { if (lo == INT64_MAX) { lo = 1; hi = 0; } else lo += 1; } }
+            if ((fl & TPLX_FP_HAS_HI) && lo <= hi) { hi = p.hi; if (!(fl & TPLX_FP_HI_INCL)) { if (hi == INT64_MIN) { lo = 1; hi = 0; } else hi -= 1; } }
+            p.flags = 0;
+        }
+        p.lo = lo;
+        p.hi = hi;
+    }
+    for (uint32_t i = F.n_preds; i < np; ++i) { F.preds[i].col = some_col; F.preds[i].flags = 0; F.preds[i].lo = INT64_MIN; F.preds[i].hi = INT64_MAX; }
     for (uint32_t i = F.n_terms; i < ntm; ++i) { F.terms[i] = tplx_fused_term{}; F.terms[i].kind = TPLX_ACC_SUM_I64; F.terms[i].op = TPLX_FT_CONST; }
     if (P.n_in == 0) return fail(TPLX_E_UNSUPPORTED, "fused scan without input columns");
     FusedParams *dF = nullptr;

@@ -120,6 +120,7 @@ class Val:
     type: int
     vreg: Optional[int] = None
     const: Any = None
+    sel: Any = None  # (cond, a, b) when this value is cond ? a : b
 
     @property
     def is_const(self):
@@ -331,10 +332,20 @@ class StageCompiler:
         if self.is_const(cond):
             return a if cond.const else b
         a, b = self.unify(a, b)
+        if a.type == T_BOOL:
+            # boolean selects with constant arms are plain logic
+            if self.is_const(a) and self.is_const(b):
+                return a if bool(a.const) == bool(b.const) else (cond if a.const else self.b_not(cond))
+            if self.is_const(a):
+                return self.b_or(cond, b) if a.const else self.b_and(self.b_not(cond), b)
+            if self.is_const(b):
+                return self.b_or(self.b_not(cond), a) if b.const else self.b_and(cond, a)
         d = self.new_vreg(a.type)
         # SEL itself must run wherever either side may be needed later: emit under the current guard
         self.emit_vals(C["TPLX_OP_SEL"], d, a, b, cond, flags=2 if a.type == T_STR else 1)
-        return Val(a.type, d)
+        out = Val(a.type, d)
+        out.sel = (cond, a, b)  # provenance: lets comparisons against constants fold through the select
+        return out
 
     def unify(self, a: Val, b: Val) -> Tuple[Val, Val]:
         if a.type == b.type:
@@ -435,8 +446,26 @@ class StageCompiler:
     def _finish(self, used_vals: List[Val]) -> List[int]:
         self.guard = None
         regs = [self.reg(v) for v in used_vals]
+        self._dce(regs)
         slots = self._regalloc(regs)
         return slots
+
+    def _dce(self, live_out: List[int]):
+        """Drop pure instructions whose result is never used. Instructions that can raise or that steer rows
+        (FILTER) always stay, so exception behaviour is unchanged (the reference's LLVM -O2 removes the same dead
+        code, tuplex/core/src/physical/LLVMOptimizer.cc:119-191)."""
+        side = {C[k] for k in ("TPLX_OP_FILTER", "TPLX_OP_RAISE", "TPLX_OP_IFLOORDIV", "TPLX_OP_IMOD", "TPLX_OP_FDIV", "TPLX_OP_FMOD",
+                               "TPLX_OP_FFLOORDIV", "TPLX_OP_SINDEX", "TPLX_OP_S2I")}
+        live = set(live_out)
+        keep = []
+        for ins in reversed(self.prog.instrs):
+            if ins.op in side or (ins.dst != NOSLOT and ins.dst in live):
+                keep.append(ins)
+                for r in (ins.a, ins.b, ins.c, ins.guard):
+                    if r != NOSLOT:
+                        live.add(r)
+        keep.reverse()
+        self.prog.instrs[:] = keep
 
     def finish_memory(self, prefilter: bool = True) -> Program:
         self.prog.endpoint = C["TPLX_EP_MEMORY"]
@@ -1150,6 +1179,11 @@ class _FuncCompiler:
                 raise UnsupportedUDF("ordering comparison of strings")
             if sc.is_const(l) and sc.is_const(r):
                 return const_val((l.const == r.const) == isinstance(op, ast.Eq))
+            if sc.is_const(l) or sc.is_const(r):
+                k, v = (l, r) if sc.is_const(l) else (r, l)
+                folded = self._fold_eq_through_select(v, k.const)
+                if folded is not None:
+                    return folded if isinstance(op, ast.Eq) else sc.b_not(folded)
             return sc.op2(C["TPLX_OP_SEQ"], T_BOOL, l, r, flags=0 if isinstance(op, ast.Eq) else 1)
         pred = C["TPLX_CMP_" + _CMP[type(op)]]
         if sc.is_const(l) and sc.is_const(r):
@@ -1158,6 +1192,19 @@ class _FuncCompiler:
         if l.type == T_F64 or r.type == T_F64:
             return sc.op2(C["TPLX_OP_FCMP"], T_BOOL, sc.to_f64(l), sc.to_f64(r), flags=pred)
         return sc.op2(C["TPLX_OP_ICMP"], T_BOOL, sc.to_i64(l), sc.to_i64(r), flags=pred)
+
+    def _fold_eq_through_select(self, v, k: str):
+        """(cond ? 'a' : 'b') == 'k'  ->  logic over cond when every leaf is a constant (else None)."""
+        sc = self.sc
+        if sc.is_const(v):
+            return const_val(v.const == k)
+        if getattr(v, "sel", None) is None:
+            return None
+        cond, a, b = v.sel
+        ea, eb = self._fold_eq_through_select(a, k), self._fold_eq_through_select(b, k)
+        if ea is None or eb is None:
+            return None
+        return sc.select(cond, ea, eb)
 
     # ---- subscripts -------------------------------------------------------------------------------------
     def subscript(self, e: ast.Subscript):
