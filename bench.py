@@ -303,6 +303,8 @@ def main():
             dist.barrier()
 
     stats = {}
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(max_workers=2)
 
     def step_resident():
         first = 0
@@ -351,20 +353,27 @@ def main():
         if ep == ir.C["TPLX_EP_HASH"]:
             st.hash_reset(local)
             st.hash_reserve(local, wl.get("nkeys", 1 << 20))
-        for cols, n in wl["blocks"]:
-            r = st.run_host(local, cols, n, first)
+        # two blocks in flight: the H2D copy of block i+1 (copy stream) overlaps the kernels of block i.
+        # Every block is its own task (row numbers start at 0 per task, like one TransformTask per partition group).
+        def one(block):
+            cols, n = block
+            r = st.run_host(local, cols, n, 0)
             inf = r.info
-            h2d += int(inf.h2d_bytes)
-            zc = max(zc, int(inf.zero_copy_cols))
-            first += int(inf.n_out_rows) + int(inf.n_exceptions)
+            nb = 0
             if ep == ir.C["TPLX_EP_MEMORY"]:
                 for c in r.columns():
-                    d2h += c.nbytes()
-                d2h += r.exceptions().nbytes
+                    nb += c.nbytes()
+                nb += r.exceptions().nbytes
             elif ep == ir.C["TPLX_EP_AGGREGATE"]:
                 r.aggregate_bits()
-                d2h += 8 * len(prog.accs)
+                nb += 8 * len(prog.accs)
+            out = (int(inf.h2d_bytes), int(inf.zero_copy_cols), nb)
             r.free()
+            return out
+        for hb, z, nb in pool.map(one, wl["blocks"]):
+            h2d += hb
+            zc = max(zc, z)
+            d2h += nb
         if ep == ir.C["TPLX_EP_HASH"]:
             fin = st.hash_finish(local)
             for c in fin.columns():

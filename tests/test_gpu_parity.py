@@ -268,10 +268,17 @@ def test_fused_scan_aggregate_matches_vm_and_oracle(gpu):
         st = backend.Stage(prog)
         ora = pyoracle.run_program(prog, cols, n)
         os.environ.pop("TPLX_NO_FUSED", None)
-        fused_bits = st.run_host(0, cols, n).aggregate_bits()
+        os.environ.pop("TPLX_NO_TMA", None)
+        fused_bits = st.run_host(0, cols, n).aggregate_bits()          # K3f, TMA-staged ring
+        os.environ["TPLX_NO_TMA"] = "1"
+        try:
+            ldg_bits = st.run_host(0, cols, n).aggregate_bits()        # K3f, plain loads
+        finally:
+            os.environ.pop("TPLX_NO_TMA", None)
         os.environ["TPLX_NO_FUSED"] = "1"
         try:
-            vm_bits = st.run_host(0, cols, n).aggregate_bits()
+            vm_bits = st.run_host(0, cols, n).aggregate_bits()         # K3 through the VM
         finally:
             os.environ.pop("TPLX_NO_FUSED", None)
+        assert ldg_bits == fused_bits, f"program {i}: TMA vs LDG"
         assert fused_bits == vm_bits == ora.acc_tree, f"program {i}"

@@ -48,7 +48,8 @@ extern "C" const char *tplx_gpu_last_error(void) { return g_last_error.c_str(); 
 // ---------------------------------------------------------------------------------------------
 struct Device {
     int id = -1;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // compute stream
+    cudaStream_t copy_stream = nullptr;  // H2D uploads, so that the next block's copy overlaps this block's kernels
     cudaDeviceProp prop{};
     int smem_optin = 0;
     uint8_t *scratch = nullptr;
@@ -88,6 +89,7 @@ extern "C" int32_t tplx_gpu_init(const int32_t *devices, int32_t n) {
         CU(cudaSetDevice(id));
         CU(cudaGetDeviceProperties(&d->prop, id));
         CU(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
         CU(cudaDeviceGetAttribute(&d->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, id));
         cudaMemPool_t pool;
         CU(cudaDeviceGetDefaultMemPool(&pool, id));
@@ -108,6 +110,7 @@ extern "C" int32_t tplx_gpu_shutdown(void) {
         cudaStreamSynchronize(d->stream);
         if (d->scratch) cudaFree(d->scratch);
         cudaStreamDestroy(d->stream);
+        cudaStreamDestroy(d->copy_stream);
         delete d;
     }
     g_devices.clear();
@@ -376,6 +379,7 @@ struct tplx_block {
     std::vector<ColIn> cols;           // device pointers
     std::vector<uint64_t> data_bytes;  // per column
     std::vector<void *> owned;         // allocations to free
+    cudaEvent_t ready = nullptr;       // recorded on the copy stream when the upload has been enqueued
 };
 
 extern "C" int32_t tplx_gpu_block_upload(int32_t device, const tplx_column *cols, uint32_t n_cols, uint64_t n_rows,
@@ -392,20 +396,22 @@ extern "C" int32_t tplx_gpu_block_upload(int32_t device, const tplx_column *cols
         ci.type = cols[c].type;
         uint64_t nb = cols[c].type == TPLX_T_STR ? cols[c].data_bytes : n_rows * 8;
         void *dd = nullptr;
-        CU(cudaMallocAsync(&dd, align_up(nb, 16) + 16, d->stream));  // 4-byte-multiple buffers: strops.cuh memory contract
+        CU(cudaMallocAsync(&dd, align_up(nb, 16) + 16, d->copy_stream));  // 4-byte-multiple buffers: strops.cuh memory contract
         b->owned.push_back(dd);
-        if (nb) CU(cudaMemcpyAsync(dd, cols[c].data, nb, cudaMemcpyHostToDevice, d->stream));
+        if (nb) CU(cudaMemcpyAsync(dd, cols[c].data, nb, cudaMemcpyHostToDevice, d->copy_stream));
         ci.data = dd;
         if (cols[c].type == TPLX_T_STR) {
             void *od = nullptr;
-            CU(cudaMallocAsync(&od, (n_rows + 1) * 4, d->stream));
+            CU(cudaMallocAsync(&od, (n_rows + 1) * 4, d->copy_stream));
             b->owned.push_back(od);
-            CU(cudaMemcpyAsync(od, cols[c].offsets, (n_rows + 1) * 4, cudaMemcpyHostToDevice, d->stream));
+            CU(cudaMemcpyAsync(od, cols[c].offsets, (n_rows + 1) * 4, cudaMemcpyHostToDevice, d->copy_stream));
             ci.offsets = static_cast<const uint32_t *>(od);
         }
         b->cols.push_back(ci);
         b->data_bytes.push_back(nb);
     }
+    CU(cudaEventCreateWithFlags(&b->ready, cudaEventDisableTiming));
+    CU(cudaEventRecord(b->ready, d->copy_stream));
     *out = b;
     return TPLX_OK;
 }
@@ -440,6 +446,7 @@ extern "C" int32_t tplx_gpu_block_free(tplx_block *b) {
     if (!b) return TPLX_OK;
     cudaSetDevice(b->dev->id);
     for (void *p : b->owned) cudaFreeAsync(p, b->dev->stream);
+    if (b->ready) cudaEventDestroy(b->ready);
     delete b;
     return TPLX_OK;
 }
@@ -551,6 +558,7 @@ extern "C" int32_t tplx_gpu_stage_run(tplx_stage *s, const tplx_block *b, int64_
     CU(cudaEventCreate(&r->ev1));
     CU(cudaEventCreate(&r->evk0));
     CU(cudaEventCreate(&r->evk1));
+    if (b->ready) CU(cudaStreamWaitEvent(d->stream, b->ready, 0));
     CU(cudaEventRecord(r->ev0, d->stream));
     switch (s->hdr.endpoint) {
         case TPLX_EP_MEMORY:
@@ -576,7 +584,7 @@ extern "C" int32_t tplx_gpu_stage_run_host(tplx_stage *s, int32_t device, const 
     CU(cudaSetDevice(d->id));
     cudaEvent_t e0;
     CU(cudaEventCreate(&e0));
-    CU(cudaEventRecord(e0, d->stream));
+    CU(cudaEventRecord(e0, d->copy_stream));  // the upload runs on the copy stream
     tplx_block *b = nullptr;
     int32_t rc = TPLX_OK;
     uint64_t h2d = 0;
@@ -629,6 +637,7 @@ extern "C" int32_t tplx_gpu_stage_run_host(tplx_stage *s, int32_t device, const 
                 b->data_bytes[c] = cols[c].type == TPLX_T_STR ? cols[c].data_bytes : n_rows * 8;
             }
         b->owned = ub->owned;
+        b->ready = ub->ready;
         ub->owned.clear();
         delete ub;
     } else {
@@ -885,6 +894,24 @@ static int32_t run_rows_prefiltered(tplx_stage *s, StageDev *sd, const tplx_bloc
 }
 
 // K3f dispatch: smallest instantiation that holds the predicates / terms; padding entries are neutral
+template <int NP, int NTM>
+static int32_t launch_fused_tma_one(uint32_t sms, uint32_t n_tiles, uint32_t smem, cudaStream_t st, const KParams *dP, const FusedTmaParams *dF) {
+    CU(cudaFuncSetAttribute(fused_scan_agg_tma_kernel<NP, NTM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fused_scan_agg_tma_kernel<NP, NTM>, NT, smem));
+    if (occ < 1) return fail(TPLX_E_UNSUPPORTED, "fused TMA kernel cannot be resident");
+    const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(n_tiles, sms * (uint32_t)std::min(occ, 2)));
+    fused_scan_agg_tma_kernel<NP, NTM><<<grid, NT, smem, st>>>(dP, dF);
+    return TPLX_OK;
+}
+template <int NP>
+static int32_t launch_fused_tma_np(uint32_t ntm, uint32_t sms, uint32_t n_tiles, uint32_t smem, cudaStream_t st, const KParams *dP, const FusedTmaParams *dF) {
+    switch (ntm) {
+        case 1: return launch_fused_tma_one<NP, 1>(sms, n_tiles, smem, st, dP, dF);
+        case 2: return launch_fused_tma_one<NP, 2>(sms, n_tiles, smem, st, dP, dF);
+        default: return launch_fused_tma_one<NP, 4>(sms, n_tiles, smem, st, dP, dF);
+    }
+}
 template <int NP>
 static int32_t launch_fused_np(uint32_t ntm, uint32_t grid, cudaStream_t st, const KParams *dP, const FusedParams *dF) {
     switch (ntm) {
@@ -932,6 +959,44 @@ static int32_t launch_fused(tplx_stage *s, Device *d, const KParams *dP, const K
     for (uint32_t i = F.n_preds; i < np; ++i) { F.preds[i].col = some_col; F.preds[i].flags = 0; F.preds[i].lo = INT64_MIN; F.preds[i].hi = INT64_MAX; }
     for (uint32_t i = F.n_terms; i < ntm; ++i) { F.terms[i] = tplx_fused_term{}; F.terms[i].kind = TPLX_ACC_SUM_I64; F.terms[i].op = TPLX_FT_CONST; }
     if (P.n_in == 0) return fail(TPLX_E_UNSUPPORTED, "fused scan without input columns");
+    // TMA-staged variant when the distinct columns fit the ring and every column base is 16-byte aligned
+    if (!getenv("TPLX_NO_TMA") && ntm <= 4 && np <= 4) {
+        FusedTmaParams FT;
+        memset(&FT, 0, sizeof(FT));
+        FT.f = F;
+        bool ok = true;
+        auto ucol_of = [&](uint32_t col) -> uint32_t {
+            for (uint32_t i = 0; i < FT.n_ucols; ++i)
+                if (FT.ucol[i] == col) return i;
+            if (FT.n_ucols == TMA_MAX_UCOLS) { ok = false; return 0; }
+            FT.ucol[FT.n_ucols] = col;
+            return FT.n_ucols++;
+        };
+        for (uint32_t i = 0; i < np; ++i) FT.f.preds[i].col = ucol_of(F.preds[i].col);
+        for (uint32_t i = 0; i < ntm; ++i) {
+            if (F.terms[i].op != TPLX_FT_CONST) FT.f.terms[i].col_a = ucol_of(F.terms[i].col_a);
+            if (F.terms[i].op == TPLX_FT_MUL) FT.f.terms[i].col_b = ucol_of(F.terms[i].col_b);
+        }
+        for (uint32_t i = 0; ok && i < FT.n_ucols; ++i) ok = ((uintptr_t)P.in[FT.ucol[i]].data & 15) == 0;
+        const uint32_t smem = TMA_STAGES * FT.n_ucols * TMA_CHUNK * 8;
+        if (ok && FT.n_ucols && smem <= (uint32_t)d->smem_optin - 4096) {
+            FusedTmaParams *dFT = nullptr;
+            int32_t rc2 = dalloc(r, &dFT, 1);
+            if (rc2) return rc2;
+            CU(cudaMemcpyAsync(dFT, &FT, sizeof(FT), cudaMemcpyHostToDevice, d->stream));
+            const uint32_t sms = (uint32_t)d->prop.multiProcessorCount;
+            switch (np) {
+                case 1: rc2 = launch_fused_tma_np<1>(ntm, sms, P.n_tiles, smem, d->stream, dP, dFT); break;
+                case 2: rc2 = launch_fused_tma_np<2>(ntm, sms, P.n_tiles, smem, d->stream, dP, dFT); break;
+                case 3: rc2 = launch_fused_tma_np<3>(ntm, sms, P.n_tiles, smem, d->stream, dP, dFT); break;
+                default: rc2 = launch_fused_tma_np<4>(ntm, sms, P.n_tiles, smem, d->stream, dP, dFT); break;
+            }
+            if (rc2) return rc2;
+            CU(cudaGetLastError());
+            r->launches += 1;
+            return TPLX_OK;
+        }
+    }
     FusedParams *dF = nullptr;
     int32_t rc = dalloc(r, &dF, 1);
     if (rc) return rc;

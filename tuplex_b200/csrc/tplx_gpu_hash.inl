@@ -189,6 +189,7 @@ extern "C" int32_t tplx_gpu_stage_hash_merge(tplx_stage *s, const tplx_block *pa
     Device *d = packed->dev;
     std::lock_guard<std::mutex> lk(d->mu);
     CU(cudaSetDevice(d->id));
+    if (packed->ready) CU(cudaStreamWaitEvent(d->stream, packed->ready, 0));
     StageDev *sd = nullptr;
     int32_t rc = stage_dev(s, d, &sd);
     if (rc) return rc;
