@@ -197,7 +197,7 @@ def cpu_zillow_reference(sample_rows: int, procs: int):
     subprocess.call(["rm", "-rf", td])
     if len(ns) != procs:
         return None
-    return dict(value=procs * rows / (max(ns) * 1e-9), unit="rows/s", cores=procs, kind="reference",
+    return dict(value=procs * rows / (max(ns) * 1e-9), unit="rows/s", cores=procs, kind="reference", rows_total=procs * rows,
                 sample=f"{procs} processes x {rows} rows (cyclic replication of the fixture, CSV preloaded), compute stage of "
                        f"oracle/_ref/zillow_ref = reference benchmarks/zillow/Z1/baseline/zillow.cpp; slowest process {max(ns) * 1e-6:.1f} ms")
 
@@ -270,7 +270,8 @@ def main():
         names = {"zillow": "zillow_z1", "q6": "tpch_q6", "c1": "c1_map_filter", "aggbykey": "aggbykey_str"}
         line = {"metric": "rows/sec on Zillow pipeline + TPC-H Q6" if args.workload in ("zillow", "q6") else "rows/sec",
                 "impl": "reference", "value": v, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i64/f64",
+                "ms_per_step": (last["rows_total"] / v * 1e3) if last.get("rows_total") else None, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u8/i64/f64",
                 "data": "synthetic", "config": {"workload": names[args.workload]},
                 "cpu_baseline": dict(last, value=v),
                 "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

@@ -17,7 +17,7 @@ import numpy as np
 from . import ir
 from .ir import T_BOOL, T_F64, T_I64, T_STR
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libtplx_gpu.so")
+_LIB_PATH = os.environ.get("TPLX_GPU_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libtplx_gpu.so")
 MAX_COLS = ir.C["TPLX_MAX_COLS"]
 
 

@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(NT) stage_hash_kernel(const KParams *__restric
             t.alive = valid;
             t.exc_code = 0;
             t.scr_used = 0;
-            VM<NT>::run(s_prog, 0, P.n_instr, s_regs, s_cols, row, P.cpool, t);
+            VM<NT>::run(s_prog, 0, P.n_instr, s_regs, s_cols, row, row, P.cpool, t);
             if (t.alive) {
                 uint32_t blob = 0;
                 const uint64_t h = hash_key<NT>(H, s_regs, &blob);

@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(NT) stage_rows_kernel(const KParams *__restric
             const uint64_t row = P.rowlist ? (valid ? P.rowlist[w] : 0) : w;
             t.alive = valid;
             t.exc_code = 0;
-            VM<NT>::run(s_prog, 0, P.n_instr, s_regs, s_cols, row, P.cpool, t);
+            VM<NT>::run(s_prog, 0, P.n_instr, s_regs, s_cols, row, w, P.cpool, t);
             const bool exc = t.exc_code != 0;
             const uint32_t kb = __ballot_sync(0xFFFFFFFFu, t.alive);
             const uint32_t eb = __ballot_sync(0xFFFFFFFFu, exc);
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(NT) stage_agg_kernel(const KParams *__restrict
             t.alive = row < P.n_rows;
             t.exc_code = 0;
             t.scr_used = 0;
-            VM<NT>::run(s_prog, 0, P.n_instr, s_regs, s_cols, row, P.cpool, t);
+            VM<NT>::run(s_prog, 0, P.n_instr, s_regs, s_cols, row, row, P.cpool, t);
             if (t.alive) {
 #pragma unroll
                 for (uint32_t k = 0; k < TPLX_MAX_ACCS; ++k)

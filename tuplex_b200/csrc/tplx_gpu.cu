@@ -22,6 +22,7 @@
 #include "rowfmt.cuh"
 #include "hashagg.cuh"
 #include "fused.cuh"
+#include "gather.cuh"
 
 using namespace tplx;
 
@@ -380,6 +381,7 @@ struct tplx_block {
     std::vector<uint64_t> data_bytes;  // per column
     std::vector<void *> owned;         // allocations to free
     cudaEvent_t ready = nullptr;       // recorded on the copy stream when the upload has been enqueued
+    std::vector<uint8_t> mapped;       // per column: 1 = read in place from page-locked host memory (run_host)
 };
 
 extern "C" int32_t tplx_gpu_block_upload(int32_t device, const tplx_column *cols, uint32_t n_cols, uint64_t n_rows,
@@ -533,7 +535,8 @@ static int32_t ensure_scratch(Device *d, size_t bytes) {
 }
 
 static int32_t run_rows(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_t first_row_no, tplx_result *r,
-                        const uint64_t *rowlist, uint64_t n_list);
+                        const uint64_t *rowlist, uint64_t n_list, const std::vector<ColIn> *cols_override = nullptr);
+static int32_t device_scan(Device *d, const uint64_t *in, uint64_t *out, uint64_t n, bool write_total);
 static int32_t run_rows_prefiltered(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_t first_row_no, tplx_result *r);
 static int32_t run_agg(tplx_stage *s, StageDev *sd, const tplx_block *b, tplx_result *r);
 static int32_t run_hash(tplx_stage *s, StageDev *sd, const tplx_block *b, tplx_result *r);
@@ -631,8 +634,10 @@ extern "C" int32_t tplx_gpu_stage_run_host(tplx_stage *s, int32_t device, const 
             b->data_bytes[up_idx[k]] = ub->data_bytes[k];
             h2d += ub->data_bytes[k] + (up[k].type == TPLX_T_STR ? (n_rows + 1) * 4 : 0);
         }
+        b->mapped.assign(n_cols, 0);
         for (uint32_t c = 0; c < n_cols; ++c)
             if (is_mapped[c]) {
+                b->mapped[c] = 1;
                 b->cols[c] = mapped[c];
                 b->data_bytes[c] = cols[c].type == TPLX_T_STR ? cols[c].data_bytes : n_rows * 8;
             }
@@ -700,7 +705,7 @@ static int32_t dalloc(tplx_result *r, T **p, size_t count) {
 }
 
 static int32_t run_rows(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_t first_row_no, tplx_result *r,
-                        const uint64_t *rowlist, uint64_t n_list) {
+                        const uint64_t *rowlist, uint64_t n_list, const std::vector<ColIn> *cols_override) {
     Device *d = sd->dev;
     const uint64_t n = rowlist ? n_list : b->n_rows;  // rows to evaluate
     r->hidden = s->hidden;
@@ -733,6 +738,8 @@ static int32_t run_rows(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_
     if (occ < 1) return fail(TPLX_E_UNSUPPORTED, "stage kernel cannot be resident");
     KParams P;
     fill_common(P, s, sd, b, L, R);
+    if (cols_override)
+        for (size_t c = 0; c < cols_override->size(); ++c) P.in[c] = (*cols_override)[c];
     P.rowlist = rowlist;
     P.n_work = n;
     P.n_tiles = (uint32_t)((n + (uint64_t)R * NT - 1) / ((uint64_t)R * NT));
@@ -862,9 +869,79 @@ static int32_t run_rows_prefiltered(tplx_stage *s, StageDev *sd, const tplx_bloc
     CU(cudaEventElapsedTime(&msa, ra.evk0, ra.evk1));  // run_rows synchronised the stream already
     const uint64_t n_surv = ra.n_out;
     if (b->n_rows >= (1u << 16) && n_surv * 2 > b->n_rows) s->prefilter_enabled = false;  // not selective: stop using it
-    rc = run_rows(s, sd, b, first_row_no, r, ra.out[0].data, n_surv);
+    // late columns that still live in host memory: bring over the surviving rows only (gather.cuh)
+    std::vector<ColIn> dense_cols;
+    float msg = 0;
+    bool any_mapped = false;
+    for (uint8_t m : b->mapped) any_mapped = any_mapped || m;
+    if (any_mapped && n_surv) {
+        cudaEvent_t g0, g1;
+        CU(cudaEventCreate(&g0));
+        CU(cudaEventCreate(&g1));
+        CU(cudaEventRecord(g0, d->stream));
+        GatherCols G;
+        memset(&G, 0, sizeof(G));
+        std::vector<uint32_t> gcol;
+        dense_cols.assign(b->cols.begin(), b->cols.end());
+        for (uint32_t c = 0; c < b->cols.size(); ++c) {
+            if (!b->mapped[c]) continue;
+            const uint32_t k = G.n_cols++;
+            gcol.push_back(c);
+            G.type[k] = (uint8_t)b->cols[c].type;
+            G.src_data[k] = b->cols[c].data;
+            G.src_off[k] = b->cols[c].offsets;
+            if (G.type[k] == TPLX_T_STR) {
+                rc = dalloc(r, &G.lens[k], n_surv + 1);
+                if (rc) { drop_ra(); return rc; }
+                CU(cudaMemsetAsync(G.lens[k] + n_surv, 0, 8, d->stream));
+                rc = dalloc(r, &G.srcpos[k], n_surv);
+                if (rc) { drop_ra(); return rc; }
+                rc = dalloc(r, &G.dst_off[k], n_surv + 1);
+                if (rc) { drop_ra(); return rc; }
+            } else {
+                rc = dalloc(r, &G.dst_data[k], n_surv);
+                if (rc) { drop_ra(); return rc; }
+            }
+        }
+        GatherCols *dG = nullptr;
+        rc = dalloc(r, &dG, 1);
+        if (rc) { drop_ra(); return rc; }
+        CU(cudaMemcpyAsync(dG, &G, sizeof(G), cudaMemcpyHostToDevice, d->stream));
+        gather_pass1<<<(uint32_t)((n_surv + 255) / 256), 256, 0, d->stream>>>(ra.out[0].data, n_surv, dG);
+        std::vector<uint64_t> totals(G.n_cols, 0);
+        for (uint32_t k = 0; k < G.n_cols; ++k) {
+            if (G.type[k] != TPLX_T_STR) continue;
+            rc = device_scan(d, G.lens[k], G.lens[k], n_surv, true);
+            if (rc) { drop_ra(); return rc; }
+            CU(cudaMemcpyAsync(&totals[k], G.lens[k] + n_surv, 8, cudaMemcpyDeviceToHost, d->stream));
+        }
+        CU(cudaStreamSynchronize(d->stream));
+        for (uint32_t k = 0; k < G.n_cols; ++k) {
+            if (G.type[k] != TPLX_T_STR) continue;
+            if (totals[k] > 0xFFFFFFFFull) { drop_ra(); return fail(TPLX_E_OVERFLOW, "gathered string column exceeds 4 GiB"); }
+            rc = dalloc(r, &G.dst_bytes[k], align_up(totals[k], 16) + 16);
+            if (rc) { drop_ra(); return rc; }
+        }
+        CU(cudaMemcpyAsync(dG, &G, sizeof(G), cudaMemcpyHostToDevice, d->stream));
+        gather_pass2<<<(uint32_t)(((n_surv + 1) * 32 + 255) / 256), 256, 0, d->stream>>>(n_surv, dG);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(g1, d->stream));
+        for (uint32_t k = 0; k < G.n_cols; ++k) {
+            ColIn ci{};
+            ci.type = (uint64_t)G.type[k] | COL_COMPACT;
+            if (G.type[k] == TPLX_T_STR) { ci.data = G.dst_bytes[k]; ci.offsets = G.dst_off[k]; }
+            else ci.data = G.dst_data[k];
+            dense_cols[gcol[k]] = ci;
+        }
+        CU(cudaEventSynchronize(g1));
+        CU(cudaEventElapsedTime(&msg, g0, g1));
+        cudaEventDestroy(g0);
+        cudaEventDestroy(g1);
+        r->launches += 2 + 3 * G.n_cols;
+    }
+    rc = run_rows(s, sd, b, first_row_no, r, ra.out[0].data, n_surv, dense_cols.empty() ? nullptr : &dense_cols);
     if (rc) { drop_ra(); return rc; }
-    r->kernel_ms_extra = msa;
+    r->kernel_ms_extra = msa + msg;
     r->launches += ra.launches;
     const uint64_t na = ra.n_exc, nb = r->n_exc;
     if (na) {

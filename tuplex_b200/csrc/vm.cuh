@@ -91,8 +91,10 @@ struct VM {
     }
 
     // Run instructions [pc0, pc1) for this thread's row.
+    // row = input row index (LDROW, exceptions); w = position in the work list (== row unless a row list is used):
+    // columns flagged compact (gather.cuh) are indexed by w.
     static __device__ void run(const DInstr *__restrict__ prog, uint32_t pc0, uint32_t pc1, uint8_t *__restrict__ rb,
-                               const ColIn *__restrict__ cols, uint64_t row, const uint8_t *__restrict__ cpool, VMThread &t) {
+                               const ColIn *__restrict__ cols, uint64_t row, uint64_t w, const uint8_t *__restrict__ cpool, VMThread &t) {
         for (uint32_t pc = pc0; pc < pc1; ++pc) {
             // uniform fetch (broadcast from shared memory)
             const uint4 w0 = *reinterpret_cast<const uint4 *>(&prog[pc]);
@@ -119,11 +121,12 @@ struct VM {
             switch (op) {
                 case TPLX_OP_LDCOL: {
                     const ColIn &ci = cols[imm];
+                    const uint64_t idx = (ci.type & 0x100) ? w : row;  // COL_COMPACT
                     if (flags == TPLX_T_STR) {
-                        uint32_t o0 = ci.offsets[row], o1 = ci.offsets[row + 1];
+                        uint32_t o0 = ci.offsets[idx], o1 = ci.offsets[idx + 1];
                         WS(rb, dst, (const uint8_t *)ci.data + o0, o1 - o0, 0);
                     } else {
-                        R(rb, dst) = ((const uint64_t *)ci.data)[row];
+                        R(rb, dst) = ((const uint64_t *)ci.data)[idx];
                     }
                     break;
                 }
