@@ -53,11 +53,8 @@ class Instr:
     imm2: int = 0
 
     def pack(self) -> bytes:
-        imm = self.imm
-        if imm >= 1 << 63:
-            imm -= 1 << 64
         return struct.pack(INSTR_FMT, self.op, self.flags, self.dst, self.a, self.b, self.c, self.guard,
-                           self.opidx, 0, imm, self.imm2)
+                           self.opidx, 0, _as_i64(self.imm), _as_i64(self.imm2))
 
     def __repr__(self):
         return (f"{OP_NAMES.get(self.op, self.op)} dst={self.dst} a={self.a} b={self.b} c={self.c} "
