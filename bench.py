@@ -305,7 +305,7 @@ def main():
 
     stats = {}
     from concurrent.futures import ThreadPoolExecutor
-    pool = ThreadPoolExecutor(max_workers=2)
+    pool = ThreadPoolExecutor(max_workers=3)
 
     def step_resident():
         first = 0
@@ -354,7 +354,8 @@ def main():
         if ep == ir.C["TPLX_EP_HASH"]:
             st.hash_reset(local)
             st.hash_reserve(local, wl.get("nkeys", 1 << 20))
-        # two blocks in flight: the H2D copy of block i+1 (copy stream) overlaps the kernels of block i.
+        # three blocks in flight: the H2D copy of the next blocks (copy stream) overlaps the kernels and the result
+        # fetch (D2H stream) of earlier ones.
         # Every block is its own task (row numbers start at 0 per task, like one TransformTask per partition group).
         def one(block):
             cols, n = block

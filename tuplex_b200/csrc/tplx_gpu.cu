@@ -51,6 +51,7 @@ struct Device {
     int id = -1;
     cudaStream_t stream = nullptr;       // compute stream
     cudaStream_t copy_stream = nullptr;  // H2D uploads, so that the next block's copy overlaps this block's kernels
+    cudaStream_t d2h_stream = nullptr;   // result fetches: must not queue behind another block's kernels
     cudaDeviceProp prop{};
     int smem_optin = 0;
     uint8_t *scratch = nullptr;
@@ -91,6 +92,7 @@ extern "C" int32_t tplx_gpu_init(const int32_t *devices, int32_t n) {
         CU(cudaGetDeviceProperties(&d->prop, id));
         CU(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&d->d2h_stream, cudaStreamNonBlocking));
         CU(cudaDeviceGetAttribute(&d->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, id));
         cudaMemPool_t pool;
         CU(cudaDeviceGetDefaultMemPool(&pool, id));
@@ -112,6 +114,7 @@ extern "C" int32_t tplx_gpu_shutdown(void) {
         if (d->scratch) cudaFree(d->scratch);
         cudaStreamDestroy(d->stream);
         cudaStreamDestroy(d->copy_stream);
+        cudaStreamDestroy(d->d2h_stream);
         delete d;
     }
     g_devices.clear();
@@ -1191,12 +1194,12 @@ extern "C" int32_t tplx_gpu_result_fetch_column(tplx_result *r, uint32_t col, vo
     CU(cudaSetDevice(r->dev->id));
     const OutCol &oc = r->out[col];
     if (r->out_types[col] == TPLX_T_STR) {
-        if (offsets) CU(cudaMemcpyAsync(offsets, oc.offsets, (r->n_out + 1) * 4, cudaMemcpyDeviceToHost, r->dev->stream));
-        if (data && r->str_bytes[col]) CU(cudaMemcpyAsync(data, oc.bytes, r->str_bytes[col], cudaMemcpyDeviceToHost, r->dev->stream));
+        if (offsets) CU(cudaMemcpyAsync(offsets, oc.offsets, (r->n_out + 1) * 4, cudaMemcpyDeviceToHost, r->dev->d2h_stream));
+        if (data && r->str_bytes[col]) CU(cudaMemcpyAsync(data, oc.bytes, r->str_bytes[col], cudaMemcpyDeviceToHost, r->dev->d2h_stream));
     } else if (data && r->n_out) {
-        CU(cudaMemcpyAsync(data, oc.data, r->n_out * 8, cudaMemcpyDeviceToHost, r->dev->stream));
+        CU(cudaMemcpyAsync(data, oc.data, r->n_out * 8, cudaMemcpyDeviceToHost, r->dev->d2h_stream));
     }
-    CU(cudaStreamSynchronize(r->dev->stream));
+    CU(cudaStreamSynchronize(r->dev->d2h_stream));
     return TPLX_OK;
 }
 
@@ -1217,16 +1220,16 @@ extern "C" int32_t tplx_gpu_result_fetch_exceptions(tplx_result *r, tplx_excepti
     if (!r || (!recs && r->n_exc)) return fail(TPLX_E_BADARG, "result_fetch_exceptions: bad arguments");
     if (!r->n_exc) return TPLX_OK;
     CU(cudaSetDevice(r->dev->id));
-    CU(cudaMemcpyAsync(recs, r->exc, r->n_exc * sizeof(tplx_exception_rec), cudaMemcpyDeviceToHost, r->dev->stream));
-    CU(cudaStreamSynchronize(r->dev->stream));
+    CU(cudaMemcpyAsync(recs, r->exc, r->n_exc * sizeof(tplx_exception_rec), cudaMemcpyDeviceToHost, r->dev->d2h_stream));
+    CU(cudaStreamSynchronize(r->dev->d2h_stream));
     return TPLX_OK;
 }
 
 extern "C" int32_t tplx_gpu_result_fetch_aggregate(tplx_result *r, int64_t *acc_bits) {
     if (!r || !acc_bits || !r->agg_out) return fail(TPLX_E_BADARG, "result_fetch_aggregate: not an aggregate result");
     CU(cudaSetDevice(r->dev->id));
-    CU(cudaMemcpyAsync(acc_bits, r->agg_out, r->n_accs * 8, cudaMemcpyDeviceToHost, r->dev->stream));
-    CU(cudaStreamSynchronize(r->dev->stream));
+    CU(cudaMemcpyAsync(acc_bits, r->agg_out, r->n_accs * 8, cudaMemcpyDeviceToHost, r->dev->d2h_stream));
+    CU(cudaStreamSynchronize(r->dev->d2h_stream));
     return TPLX_OK;
 }
 
