@@ -50,7 +50,7 @@ class Clocks:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -399,7 +399,6 @@ def main():
         launches += stats["launches"]
     sync_all()
     dt = time.perf_counter() - t0
-    clk = clocks.stop()
 
     # end-to-end through the C ABI with host buffers (H2D of inputs + D2H of results inside the timed region)
     e2e_steps = max(1, min(args.steps, 3))
@@ -410,6 +409,7 @@ def main():
         step_e2e()
     sync_all()
     dt_e2e = time.perf_counter() - t1
+    clk = clocks.stop()  # sampled over both timed regions (device-resident steps and end-to-end steps)
 
     times = torch.tensor([dt, dt_e2e], dtype=torch.float64, device="cuda")
     if dist is not None:

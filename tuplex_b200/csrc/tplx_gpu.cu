@@ -727,13 +727,27 @@ static int32_t run_rows(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_
             }
         return TPLX_OK;
     }
-    // tile shape: strings are compute heavy -> small tiles; fixed width -> as large as shared memory allows
-    const uint32_t smem_budget = (uint32_t)std::min<int>(d->smem_optin, 113 * 1024);
-    uint32_t R = s->has_str ? 4 : 16;
+    // tile shape: the largest tile (fewest barrier / look-back episodes, best load balance inside the CTA) that does
+    // not cost occupancy: the register-limited number of resident CTAs divides the SM's shared memory into budgets
+    int occ_regs = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_regs, stage_rows_kernel, NT, 0));
+    occ_regs = std::max(occ_regs, 1);
+    const uint32_t env_R = getenv("TPLX_TILE_R") ? (uint32_t)atoi(getenv("TPLX_TILE_R")) : 0;
+    uint32_t smem_budget = (uint32_t)(d->prop.sharedMemPerMultiprocessor / occ_regs) - 1024;
+    uint32_t R = env_R ? env_R : 16;
     Layout L = make_layout(s, R, true);
     while (R > 1 && L.total > smem_budget) {
         R /= 2;
         L = make_layout(s, R, true);
+    }
+    if (L.total > smem_budget) {  // even one row per thread does not fit the budget: give up occupancy instead
+        smem_budget = (uint32_t)std::min<int>(d->smem_optin, 113 * 1024);
+        R = env_R ? env_R : 4;
+        L = make_layout(s, R, true);
+        while (R > 1 && L.total > smem_budget) {
+            R /= 2;
+            L = make_layout(s, R, true);
+        }
     }
     if (L.total > (uint32_t)d->smem_optin) return fail(TPLX_E_UNSUPPORTED, "stage needs more shared memory than one SM has");
     int occ = 0;
