@@ -123,37 +123,55 @@ TPLX_HD bool match_at(const StrV &h, uint32_t pos, const StrV &n, uint32_t from)
 
 // strstr semantics: first occurrence or -1; empty needle -> 0.
 // SWAR filter on the first (and, when present, second) needle character, 4 haystack positions per step.
-TPLX_HD_NOINLINE int64_t str_find(const StrV &h, const StrV &n) {
-    if (n.len == 0) return 0;
-    if (n.len > h.len) return -1;
+// The haystack is streamed through three rolling aligned words (one new aligned load per step); the case flag is
+// a template parameter so the loop body carries no per-word flag tests.
+template <uint32_t HFLAGS>
+TPLX_HD int64_t str_find_impl(const StrV &h, const StrV &n) {
     const uint32_t last = h.len - n.len;  // last admissible start
     const uint32_t c0 = sch(n, 0);
     const bool two = n.len >= 2;
     const uint32_t c1 = two ? sch(n, 1) : 0;
-    WordReader r;
-    r.init(h);
-    uint32_t cur = r.get(0);
+    const uintptr_t addr = (uintptr_t)h.p;
+    const uint32_t *aw = (const uint32_t *)(addr & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(addr & 3) * 8;
+    const uint32_t nwords = (uint32_t)(((addr & 3) + h.len + 3) >> 2);  // aligned words holding string bytes (>= 1)
+    uint32_t a0 = aw[0];
+    uint32_t a1 = nwords > 1 ? aw[1] : 0u;
+    uint32_t cur = funnel_r(a0, a1, sh);
+    if (HFLAGS == TPLX_SF_LOWER) cur = lower4(cur);
+    if (HFLAGS == TPLX_SF_UPPER) cur = upper4(cur);
     for (uint32_t k = 0; 4 * k <= last; ++k) {
-        // next word is needed for the second-character test of position 4k+3 (only if it holds string bytes)
-        uint32_t nxt = (4 * (k + 1) < h.len) ? r.get(k + 1) : 0u;
+        // string word k+1 (only its first character is ever needed, for the 2-character test of position 4k+3)
+        const uint32_t a2 = (k + 2 < nwords) ? aw[k + 2] : 0u;
+        uint32_t nxt = funnel_r(a1, a2, sh);
+        if (HFLAGS == TPLX_SF_LOWER) nxt = lower4(nxt);
+        if (HFLAGS == TPLX_SF_UPPER) nxt = upper4(nxt);
         uint32_t m = eq_mask4(cur, c0);
         if (two) m &= eq_mask4((cur >> 8) | (nxt << 24), c1);
-        // drop positions beyond `last`
-        uint32_t valid = last - 4 * k;  // positions 0..valid of this word are admissible
+        const uint32_t valid = last - 4 * k;  // positions 0..valid of this word are admissible
         if (valid < 3) m &= low_mask(valid + 1);
         while (m) {
 #ifdef __CUDA_ARCH__
-            uint32_t bit = __ffs(m) - 1;
+            const uint32_t bit = __ffs(m) - 1;
 #else
-            uint32_t bit = (uint32_t)__builtin_ctz(m);
+            const uint32_t bit = (uint32_t)__builtin_ctz(m);
 #endif
-            uint32_t pos = 4 * k + (bit >> 3);
+            const uint32_t pos = 4 * k + (bit >> 3);
             if (match_at(h, pos, n, two ? 2 : 1)) return (int64_t)pos;
             m &= m - 1;
         }
         cur = nxt;
+        a1 = a2;
     }
     return -1;
+}
+
+TPLX_HD_NOINLINE int64_t str_find(const StrV &h, const StrV &n) {
+    if (n.len == 0) return 0;
+    if (n.len > h.len) return -1;
+    if (h.flags == TPLX_SF_LOWER) return str_find_impl<TPLX_SF_LOWER>(h, n);
+    if (h.flags == TPLX_SF_UPPER) return str_find_impl<TPLX_SF_UPPER>(h, n);
+    return str_find_impl<TPLX_SF_NONE>(h, n);
 }
 
 // std::string::rfind: last occurrence or -1; empty needle -> len
