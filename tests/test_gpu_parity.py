@@ -282,3 +282,33 @@ def test_fused_scan_aggregate_matches_vm_and_oracle(gpu):
             os.environ.pop("TPLX_NO_FUSED", None)
         assert ldg_bits == fused_bits, f"program {i}: TMA vs LDG"
         assert fused_bits == vm_bits == ora.acc_tree, f"program {i}"
+
+
+def test_full_block_sizes_properties(gpu):
+    """At the block sizes bench.py uses: every 32,661-row cycle of the replicated Zillow input must reproduce the
+    golden 577 rows (periodicity of the output), and Q6 over 50M rows must equal the oracle's tree bit for bit."""
+    cols, n0 = workloads.load_zillow_fixture()
+    cycles = 500
+    n = cycles * n0
+    big = workloads.replicate(cols, n0, n)
+    prog = workloads.zillow_program()
+    st = backend.Stage(prog)
+    res = st.run_host(0, big, n)
+    assert int(res.info.n_out_rows) == 577 * cycles and int(res.info.n_exceptions) == 0
+    ora = pyoracle.run_program(prog, cols, n0)  # one cycle
+    for c, (t, odata, ooffs) in enumerate(ora.columns):
+        col = res.column(c)
+        if t == T_STR:
+            lens = np.diff(ooffs.astype(np.int64))
+            assert np.array_equal(np.diff(col.offsets.astype(np.int64)), np.tile(lens, cycles)), f"col {c} lengths"
+            assert col.data.tobytes() == odata.tobytes() * cycles, f"col {c} bytes"
+        else:
+            assert np.array_equal(col.data.view(np.int64), np.tile(odata.view(np.int64), cycles)), f"col {c}"
+    res.free()
+    m = 50_000_000
+    lcols = workloads.gen_lineitem(m, seed=123)
+    q = workloads.q6_program()
+    r = backend.Stage(q).run_host(0, lcols, m)
+    o = pyoracle.run_program(q, lcols, m)
+    assert r.aggregate_bits() == o.acc_tree
+    assert abs(ir.bits_f64(o.acc_tree[0]) - ir.bits_f64(o.acc_seq[0])) <= 1e-9 * abs(ir.bits_f64(o.acc_seq[0]))
