@@ -33,6 +33,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--keys", type=int, default=0, help="distinct keys of the aggbykey workload (default rows/100)")
     return ap.parse_args()
 
 
@@ -78,6 +79,16 @@ class Clocks:
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
                 "samples": len(self.samples)}
+
+
+def ncu_traffic(wl, n_launch):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
+    (profiles/r01_*.md), scaled to this run's rows per launch; None when no capture exists for the workload."""
+    per_row = {"zillow_z1": (963.67e6 + 6.98e6 + 262.70e6 + 50.03e6) / 16330500,   # prefilter + dense launch, 16.33M-row block
+               "tpch_q6": 3.200e9 / 100_000_000}.get(wl["name"])                     # K3f: reads exactly 32 B/row
+    if per_row is None:
+        return None
+    return per_row * wl["rows"] / n_launch
 
 
 def peaks():
@@ -158,7 +169,7 @@ def build_workload(args):
         return dict(name="c1_map_filter", prog=W.c1_program(), blocks=blocks, rows=total, in_bytes=total * 8, keep=keep,
                     desc=f"parallelize([1..{total}]).map(x*x).filter(x%2==0)")
     total = args.rows or 100_000_000
-    nkeys = max(1000, total // 100)
+    nkeys = args.keys or max(1000, total // 100)
     blocks = [(pin_cols(W.gen_keyed(total, nkeys, seed=42)), total)]
     return dict(name="aggbykey_str", prog=W.keyed_program(), blocks=blocks, rows=total, in_bytes=total * 20, keep=keep, nkeys=nkeys,
                 desc=f"aggregateByKey string key, {total} rows, {nkeys} distinct keys")
@@ -443,8 +454,9 @@ def main():
                     "note": "h2d = explicit copies of the columns the prefilter reads; zero_copy_cols input columns stay in "
                             "page-locked host memory and are read over PCIe for surviving rows only (late materialisation)"},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": {0: "stage_rows_kernel", 1: "stage_agg_kernel", 2: "stage_hash_kernel"}[ep],
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "kernel": {0: "stage_rows_kernel (prefilter + dense launch)", 1: "fused_scan_agg_tma_kernel", 2: "stage_hash_kernel"}[ep]
+                         if wl["name"] in ("zillow_z1", "tpch_q6", "aggbykey_str") else {0: "stage_rows_kernel", 1: "stage_agg_kernel", 2: "stage_hash_kernel"}[ep],
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(wl, n_launch),
                          "peak_source": peak_src, "algorithmic_bytes_per_row": alg_bytes / wl["rows"],
                          "kernel_ms_per_launch": k_ms_per_launch, "kernel_share_of_step": (kms / args.steps) / ms_step},
         }

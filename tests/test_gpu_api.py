@@ -147,3 +147,53 @@ def test_five_percent_exception_rows_resolve_in_order(ctx):
     assert got == exp
     assert sum(ds.exception_counts.values()) == n_exc
     assert 0.03 * n < n_exc < 0.08 * n  # ~5 % exception rows
+
+
+def test_multi_block_execution_matches_single_block(gpu):
+    """tuplex.gpu.blockRows plays the role of the reference's tiny partitions in its tests (128 KB partitions,
+    python/tests/helper.py:12-20): many blocks per stage must give the same rows, order and exception handling."""
+    small = tuplex_b200.Context({"tuplex.gpu.blockRows": 1000})
+    big = tuplex_b200.Context()
+    data = [(i, i % 7, "s%d" % (i % 13)) for i in range(10_500)]
+
+    def pipe(c):
+        return (c.parallelize(data, columns=["a", "b", "s"])
+                .withColumn("q", lambda x: x["a"] // x["b"])           # ZeroDivisionError on every 7th row
+                .resolve(ZeroDivisionError, lambda x: -1)
+                .filter(lambda x: x["q"] % 5 != 0)
+                .mapColumn("s", lambda s: s.upper() + "!")
+                .selectColumns(["a", "q", "s"]))
+    a, b = pipe(small).collect(), pipe(big).collect()
+    assert a == b and len(a) > 5000
+    exp = []
+    for i, m, s in data:
+        q = i // m if m else -1
+        if q % 5 != 0:
+            exp.append((i, q, s.upper() + "!"))
+    assert a == exp
+    assert small.metrics.kernel_launches > big.metrics.kernel_launches
+    # aggregates and group-bys across blocks
+    agg = lambda c: c.parallelize(data, columns=["a", "b", "s"]).aggregate(lambda x, y: x + y, lambda acc, r: acc + r["a"] * r["b"], 0).collect()
+    assert agg(small) == agg(big) == [sum(i * (i % 7) for i in range(10_500))]
+    grp = lambda c: c.parallelize(data, columns=["a", "b", "s"]).aggregateByKey(lambda x, y: x + y, lambda acc, r: acc + r["a"], 0, ["s"]).collect()
+    want = {}
+    for i, m, s in data:
+        want[s] = want.get(s, 0) + i
+    assert dict(grp(small)) == dict(grp(big)) == want
+
+
+def test_csv_source_to_csv_sink_zillow(ctx, tmp_path):
+    """The benchmark script's own flow (benchmarks/zillow/Z1/runtuplex.py:186-205): ctx.csv(...) -> pipeline -> tocsv,
+    on the reference's fixture; the produced file must be byte-identical to the reference baselines' output."""
+    import gzip
+    import hashlib
+    import os
+    src = tmp_path / "zillow.csv"
+    with gzip.open(os.path.join(workloads.GOLDEN, "zillow_noexc_cols.csv.gz"), "rb") as fp:
+        src.write_bytes(fp.read())
+    ds = ctx.csv(str(src))
+    assert ds.columns == workloads.ZILLOW_COLS
+    out_dir = tmp_path / "out"
+    workloads.zillow_pipeline(ds).tocsv(str(out_dir))
+    produced = (out_dir / "part0.csv").read_bytes()
+    assert hashlib.md5(produced).hexdigest() == "4d5ca0263b1a5058341a369116dee83a"
