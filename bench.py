@@ -327,16 +327,23 @@ def main():
         if ep == ir.C["TPLX_EP_HASH"]:
             st.hash_reset(local)
             st.hash_reserve(local, wl.get("nkeys", 1 << 20))
-        for b in dev_blocks:
-            r = st.run(b, first)
+        def one_resident(b):
+            r = st.run(b, 0)   # every block is its own task (row numbers per task), so blocks need not run in sequence
             inf = r.info
-            kms += inf.kernel_ms
-            launches += inf.kernel_launches
-            n_out += int(inf.n_out_rows)
-            first += int(inf.n_out_rows) + int(inf.n_exceptions)
-            if ep == ir.C["TPLX_EP_AGGREGATE"]:
-                partials.append(ir.bits_f64(r.aggregate_bits()[0]))
+            out = (inf.kernel_ms, inf.kernel_launches, int(inf.n_out_rows),
+                   ir.bits_f64(r.aggregate_bits()[0]) if ep == ir.C["TPLX_EP_AGGREGATE"] else None)
             r.free()
+            return out
+        # row stages: two blocks in flight on the GPU's two execution lanes (the latency-bound dense launch of one block
+        # overlaps the prefilter of the next). Aggregate scans are DRAM-bound (nothing to overlap) and hash stages share
+        # one table per device: those run one block at a time.
+        runner = pool.map if ep == ir.C["TPLX_EP_MEMORY"] else map
+        for km, kl, no, part in runner(one_resident, dev_blocks):
+            kms += km
+            launches += kl
+            n_out += no
+            if part is not None:
+                partials.append(part)
         if ep == ir.C["TPLX_EP_AGGREGATE"]:
             tot = 0.0
             for p in partials:
@@ -438,7 +445,10 @@ def main():
         alg_bytes = wl["in_bytes"] + out_bytes
         n_launch = max(1, len(dev_blocks))
         k_ms_per_launch = kms / args.steps / n_launch
-        achieved = (alg_bytes / n_launch) / (k_ms_per_launch * 1e-3) / 1e9 if k_ms_per_launch > 0 else 0.0
+        # launches of different blocks overlap on the GPU's two execution lanes, so the per-launch event times can add up
+        # to more than the step: the device time the kernels really occupied is at most the step itself
+        k_ms_step = min(kms / args.steps, ms_step)
+        achieved = alg_bytes / (k_ms_step * 1e-3) / 1e9 if k_ms_step > 0 else 0.0
         line = {
             "metric": "rows/sec on Zillow pipeline + TPC-H Q6" if args.workload in ("zillow", "q6") else "rows/sec",
             "value": rows_all / (dt / args.steps), "unit": "rows/s", "n_gpus": world, "steps": args.steps,
@@ -458,7 +468,8 @@ def main():
                          if wl["name"] in ("zillow_z1", "tpch_q6", "aggbykey_str") else {0: "stage_rows_kernel", 1: "stage_agg_kernel", 2: "stage_hash_kernel"}[ep],
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(wl, n_launch),
                          "peak_source": peak_src, "algorithmic_bytes_per_row": alg_bytes / wl["rows"],
-                         "kernel_ms_per_launch": k_ms_per_launch, "kernel_share_of_step": (kms / args.steps) / ms_step},
+                         "kernel_ms_per_launch": k_ms_per_launch, "kernel_share_of_step": k_ms_step / ms_step,
+                         "launches_overlap": (kms / args.steps) > ms_step},
         }
         if "result" in stats:
             line["config"]["result"] = repr(stats["result"])

@@ -57,6 +57,8 @@ struct Device {
     uint8_t *scratch = nullptr;
     size_t scratch_bytes = 0;
     std::mutex mu;
+    Device *alt = nullptr;  // second execution lane on the same GPU (own streams + scratch): lets the kernels of two
+                            // blocks overlap (e.g. the latency-bound dense launch of one with the prefilter of the next)
 };
 static std::vector<Device *> g_devices;
 static std::mutex g_mu;
@@ -101,6 +103,14 @@ extern "C" int32_t tplx_gpu_init(const int32_t *devices, int32_t n) {
         CU(cudaFuncSetAttribute(stage_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d->smem_optin));
         CU(cudaFuncSetAttribute(stage_agg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d->smem_optin));
         CU(cudaFuncSetAttribute(stage_hash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d->smem_optin));
+        Device *a = new Device();
+        a->id = id;
+        a->prop = d->prop;
+        a->smem_optin = d->smem_optin;
+        CU(cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&a->copy_stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&a->d2h_stream, cudaStreamNonBlocking));
+        d->alt = a;
         g_devices.push_back(d);
     }
     return TPLX_OK;
@@ -110,6 +120,14 @@ extern "C" int32_t tplx_gpu_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_mu);
     for (auto *d : g_devices) {
         cudaSetDevice(d->id);
+        if (d->alt) {
+            cudaStreamSynchronize(d->alt->stream);
+            if (d->alt->scratch) cudaFree(d->alt->scratch);
+            cudaStreamDestroy(d->alt->stream);
+            cudaStreamDestroy(d->alt->copy_stream);
+            cudaStreamDestroy(d->alt->d2h_stream);
+            delete d->alt;
+        }
         cudaStreamSynchronize(d->stream);
         if (d->scratch) cudaFree(d->scratch);
         cudaStreamDestroy(d->stream);
@@ -341,7 +359,7 @@ static std::vector<DInstr> predecode(const std::vector<tplx_instr> &ins) {
 static int32_t stage_dev(tplx_stage *s, Device *d, StageDev **out) {
     std::lock_guard<std::mutex> lk(s->mu);
     for (auto &sd : s->devs)
-        if (sd.dev == d) { *out = &sd; return TPLX_OK; }
+        if (sd.dev->id == d->id) { *out = &sd; return TPLX_OK; }  // lanes of one GPU share the device copies
     s->devs.reserve(16);
     StageDev sd;
     sd.dev = d;
@@ -550,10 +568,20 @@ extern "C" int32_t tplx_gpu_stage_run(tplx_stage *s, const tplx_block *b, int64_
     for (size_t c = 0; c < b->cols.size(); ++c)
         if ((uint8_t)b->cols[c].type != s->in_types[c]) return fail(TPLX_E_BADARG, "stage_run: block column type != stage input schema");
     Device *d = b->dev;
-    std::lock_guard<std::mutex> lk(d->mu);
+    // two execution lanes per GPU: a second caller does not wait for the first one's kernels (hash stages keep to
+    // the primary lane: one table per device)
+    std::unique_lock<std::mutex> lk(d->mu, std::try_to_lock);
+    if (!lk.owns_lock()) {
+        if (s->hdr.endpoint != TPLX_EP_HASH && d->alt) {
+            d = d->alt;
+            lk = std::unique_lock<std::mutex>(d->mu);
+        } else {
+            lk = std::unique_lock<std::mutex>(d->mu);
+        }
+    }
     CU(cudaSetDevice(d->id));
     StageDev *sd = nullptr;
-    int32_t rc = stage_dev(s, d, &sd);
+    int32_t rc = stage_dev(s, b->dev, &sd);
     if (rc) return rc;
     tplx_result *r = new tplx_result();
     r->dev = d;
@@ -709,7 +737,7 @@ static int32_t dalloc(tplx_result *r, T **p, size_t count) {
 
 static int32_t run_rows(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_t first_row_no, tplx_result *r,
                         const uint64_t *rowlist, uint64_t n_list, const std::vector<ColIn> *cols_override) {
-    Device *d = sd->dev;
+    Device *d = r->dev;  // execution lane chosen by tplx_gpu_stage_run
     const uint64_t n = rowlist ? n_list : b->n_rows;  // rows to evaluate
     r->hidden = s->hidden;
     r->out_types.clear();
@@ -864,7 +892,7 @@ static int32_t run_rows(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_
 // (2) this stage densely over that list. Exception rows of both launches are merged and numbered like one
 // TransformTask would have numbered them (rows written + exceptions so far, TransformTask.cc:764,885).
 static int32_t run_rows_prefiltered(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_t first_row_no, tplx_result *r) {
-    Device *d = sd->dev;
+    Device *d = r->dev;
     tplx_stage *ps = s->prefilter;
     StageDev *psd = nullptr;
     int32_t rc = stage_dev(ps, d, &psd);
@@ -1110,7 +1138,7 @@ static int32_t launch_fused(tplx_stage *s, Device *d, const KParams *dP, const K
 }
 
 static int32_t run_agg(tplx_stage *s, StageDev *sd, const tplx_block *b, tplx_result *r) {
-    Device *d = sd->dev;
+    Device *d = r->dev;
     const uint64_t n = b->n_rows;
     const uint32_t R = 16;
     Layout L = make_layout(s, R, false);
