@@ -441,10 +441,18 @@ static int eval_row(const ostage *S, const tplx_ocol *cols, uint64_t row, oval *
             case TPLX_OP_SFMTD: {
                 /* snprintf with a C %d conversion, which consumes an int (formatStr, BlockGeneratorVisitor.cc:675-775) */
                 char fmt[32], out[64];
-                if (in->flags & 1) snprintf(fmt, sizeof fmt, "%%0%dd", (int)in->imm);
-                else if (in->imm) snprintf(fmt, sizeof fmt, "%%%dd", (int)in->imm);
-                else snprintf(fmt, sizeof fmt, "%%d");
-                int nlen = snprintf(out, sizeof out, fmt, (int)a->i);
+                int nlen;
+                if (in->flags & 2) { /* str.format / f-string: fmt keeps the whole 64-bit value (Runtime.cc:544-607) */
+                    if (in->flags & 1) snprintf(fmt, sizeof fmt, "%%0%dlld", (int)in->imm);
+                    else if (in->imm) snprintf(fmt, sizeof fmt, "%%%dlld", (int)in->imm);
+                    else snprintf(fmt, sizeof fmt, "%%lld");
+                    nlen = snprintf(out, sizeof out, fmt, (long long)a->i);
+                } else {
+                    if (in->flags & 1) snprintf(fmt, sizeof fmt, "%%0%dd", (int)in->imm);
+                    else if (in->imm) snprintf(fmt, sizeof fmt, "%%%dd", (int)in->imm);
+                    else snprintf(fmt, sizeof fmt, "%%d");
+                    nlen = snprintf(out, sizeof out, fmt, (int)a->i);
+                }
                 d->s = dup_n(A, out, (size_t)nlen);
                 d->len = nlen;
                 break;

@@ -50,8 +50,10 @@ class Gen:
             return f"{self.str_(d - 1)}.rfind({r.choice(NEEDLES)!r})"
         if k < 0.88:
             return f"int({self.str_(d - 1)})"
-        if k < 0.94:
+        if k < 0.92:
             return f"({self.int_(d - 1)} if {self.bool_(d - 1)} else {self.int_(d - 1)})"
+        if k < 0.96:
+            return f"{r.choice(['min', 'max'])}({self.int_(d - 1)}, {self.int_(d - 1)})"
         return f"int({self.float_(d - 1)})"
 
     def float_(self, d):
@@ -85,8 +87,11 @@ class Gen:
             return f"({self.str_(d - 1)} + {self.str_(d - 1)})"
         if k < 0.78:
             return f"{self.str_(d - 1)}.replace({r.choice(NEEDLES)!r}, {r.choice(['', '_', 'xy'])!r})"
-        if k < 0.86:
+        if k < 0.82:
             return f"({r.choice(['%d', '%05d', 'n=%d!', '%3d'])!r} % {self.int_(d - 1)})"
+        if k < 0.86:
+            return r.choice([f"{r.choice(['{:03}|{}', 'v={}', '{1}-{0:4d}'])!r}.format({self.int_(d - 1)}, {self.str_(0)})",
+                             "f\"{x['a']:04}:{x['s']}\""])
         if k < 0.93:
             return f"({self.str_(d - 1)} if {self.bool_(d - 1)} else {self.str_(d - 1)})"
         return f"str({self.int_(d - 1)})"
@@ -103,8 +108,10 @@ class Gen:
             return f"({r.choice(NEEDLES)!r} in {self.str_(d - 1)})"
         if k < 0.65:
             return f"({self.str_(d - 1)} {r.choice(['==', '!='])} {self.str_(d - 1)})"
-        if k < 0.72:
+        if k < 0.69:
             return f"{self.str_(d - 1)}.{r.choice(['startswith', 'endswith'])}({r.choice(NEEDLES)!r})"
+        if k < 0.72:
+            return r.choice([f"({self.int_(0)} {r.choice(['in', 'not in'])} (1, -2, 7))", f"({self.str_(0)} in ['a', 'house', ''])"])
         if k < 0.86:
             return f"({self.bool_(d - 1)} {r.choice(['and', 'or'])} {self.bool_(d - 1)})"
         if k < 0.93:

@@ -111,3 +111,32 @@ def test_shard_ranges():
             assert parts[0][0] == 0 and parts[-1][1] == n
             assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
             assert max(h - l for l, h in parts) - min(h - l for l, h in parts) <= 1
+
+
+def test_frontend_breadth_vs_cpython(built):
+    """Constructs beyond the benchmark UDFs: membership in literal containers, min/max, str.format / f-strings with
+    integer specs, dict-valued map; each lowered program run by the oracle must equal CPython."""
+    from oracle import pyoracle
+    rows = [(i - 5, "w%d" % (i % 3), float(i) / 4) for i in range(40)]
+    cols = [backend.Column.from_values([r[0] for r in rows], T_I64), backend.Column.from_values([r[1] for r in rows], T_STR),
+            backend.Column.from_values([r[2] for r in rows], T_F64)]
+    udfs = [
+        lambda x: (x['a'] in (1, -2, 7), x['s'] not in ['w0', 'zz'], min(x['a'], 3), max(x['f'], 1.5), min(x['a'], x['f'])),
+        lambda x: ('{:03}|{}'.format(x['a'], x['s']), f"{x['a']:04}:{x['s']}!", '{1}-{0:4d}'.format(x['a'], x['s']), f"{x['s']}{x['a']}"),
+        lambda x: {'k': x['s'].upper(), 'v': x['a'] * 2},
+    ]
+    for f in udfs:
+        sc = frontend.StageCompiler([T_I64, T_STR, T_F64], ["a", "s", "f"])
+        sc.add_map(f, 100001)
+        prog = sc.finish_memory()
+        res = pyoracle.run_program(prog, cols, len(rows))
+        got = list(zip(*[res.values(c) for c in range(len(res.columns))]))
+        exp = []
+        for r in rows:
+            v = f(pyexec.Row(r, ["a", "s", "f"]))
+            exp.append(tuple(v.values()) if isinstance(v, dict) else v)
+        assert got == exp
+    sc = frontend.StageCompiler([T_I64, T_STR, T_F64], ["a", "s", "f"])
+    sc.add_map(udfs[2], 100001)
+    sc.finish_memory()
+    assert sc.names == ["k", "v"]

@@ -350,12 +350,13 @@ struct VM {
                     break;
                 }
                 case TPLX_OP_SFMTD: {
-                    // snprintf("%[0]<w>d", (int)v): C %d consumes an int (BlockGeneratorVisitor.cc:675-775)
-                    int32_t v = (int32_t)(int64_t)R(rb, a);
+                    // '%[0]<w>d' % v: snprintf with C's %d, which consumes an int (BlockGeneratorVisitor.cc:675-775);
+                    // flags bit1: '{:0<w>}'.format(v) / f-strings go through fmt and keep all 64 bits (Runtime.cc:544-607)
+                    const int64_t v = (flags & 2) ? (int64_t)R(rb, a) : (int64_t)(int32_t)(int64_t)R(rb, a);
                     uint32_t width = (uint32_t)imm;
-                    uint32_t mag = v < 0 ? (uint32_t)0 - (uint32_t)v : (uint32_t)v;
+                    uint64_t mag = v < 0 ? (uint64_t)0 - (uint64_t)v : (uint64_t)v;
                     uint32_t nd = 1;
-                    for (uint32_t q = mag; q >= 10; q /= 10) ++nd;
+                    for (uint64_t q = mag; q >= 10; q /= 10) ++nd;
                     uint32_t body = nd + (v < 0 ? 1 : 0);
                     uint32_t total = body > width ? body : width;
                     uint8_t *o = scratch_alloc(t, total, opidx);

@@ -131,6 +131,7 @@ class Val:
 class TupleVal:
     elems: List[Any]  # Val | TupleVal
     names: Optional[List[Optional[str]]] = None
+    is_list: bool = False
 
 
 def _py_type_of(v) -> int:
@@ -381,6 +382,8 @@ class StageCompiler:
         self.oplog.append(("add_map", (func, op_id)))
         self.begin_op(op_id)
         res = self._call_udf(func, [self.row_value()])
+        if isinstance(res, TupleVal) and res.is_list:
+            raise UnsupportedUDF("list-valued map output")
         if isinstance(res, TupleVal):
             flat, names = [], []
             for i, e in enumerate(res.elems):
@@ -980,6 +983,18 @@ class _FuncCompiler:
             raise UnsupportedUDF(f"name {e.id!r} is not a parameter, local or constant global")
         if isinstance(e, ast.Tuple):
             return TupleVal([self.expr(x) for x in e.elts])
+        if isinstance(e, ast.List):
+            tv = TupleVal([self.expr(x) for x in e.elts])
+            tv.is_list = True  # only usable as the container of an `in` test; a list-valued column is not normal-case
+            return tv
+        if isinstance(e, ast.Dict):
+            # {'a': e1, 'b': e2}: a row with named columns (python/tuplex/dataset.py map() with dict output)
+            if not all(isinstance(k, ast.Constant) and isinstance(k.value, str) for k in e.keys):
+                raise UnsupportedUDF("dict keys must be string literals")
+            return TupleVal([self.expr(v) for v in e.values], [k.value for k in e.keys])
+        if isinstance(e, ast.JoinedStr):
+            return self.format_pieces([("lit", p.value) if isinstance(p, ast.Constant) else
+                                       ("val", self.expr(p.value), self._spec_of(p)) for p in e.values])
         if isinstance(e, ast.BinOp):
             return self.binop(e.op, self.expr(e.left), self.expr(e.right))
         if isinstance(e, ast.UnaryOp):
@@ -1139,6 +1154,68 @@ class _FuncCompiler:
             out = self.binop(ast.Add(), out, p)
         return out
 
+    # ---- '{}'.format(...) and f-strings (FunctionRegistry::createFormatCall -> strFormat, Runtime.cc:544-607) ------
+    _BRACE = re.compile(r"\{\{|\}\}|\{(\d*)(?::([^{}]*))?\}")
+
+    def _spec_of(self, fv: ast.FormattedValue) -> str:
+        if fv.conversion not in (-1, 115):
+            raise UnsupportedUDF("f-string conversion")
+        if fv.format_spec is None:
+            return ""
+        if len(fv.format_spec.values) == 1 and isinstance(fv.format_spec.values[0], ast.Constant):
+            return str(fv.format_spec.values[0].value)
+        raise UnsupportedUDF("dynamic format spec")
+
+    def format_braces(self, fmt: str, args):
+        pieces = []
+        pos = 0
+        auto = 0
+        for m in self._BRACE.finditer(fmt):
+            if m.start() > pos:
+                pieces.append(("lit", fmt[pos:m.start()]))
+            pos = m.end()
+            if m.group(0) in ("{{", "}}"):
+                pieces.append(("lit", m.group(0)[0]))
+                continue
+            idx = int(m.group(1)) if m.group(1) else auto
+            auto += 1
+            if idx >= len(args):
+                raise UnsupportedUDF("format() argument index")
+            pieces.append(("val", args[idx], m.group(2) or ""))
+        if pos < len(fmt):
+            pieces.append(("lit", fmt[pos:]))
+        return self.format_pieces(pieces)
+
+    def format_pieces(self, pieces):
+        sc = self.sc
+        out = None
+        for p in pieces:
+            if p[0] == "lit":
+                v = const_val(p[1])
+            else:
+                a, spec = p[1], p[2]
+                if isinstance(a, TupleVal):
+                    raise UnsupportedUDF("format of a tuple")
+                if a.type == T_STR:
+                    if spec not in ("", "s"):
+                        raise UnsupportedUDF("string format spec")
+                    v = a
+                elif a.type in (T_I64,):
+                    ms = re.fullmatch(r"(0?)(\d*)d?", spec)
+                    if not ms:
+                        raise UnsupportedUDF("integer format spec")
+                    width = int(ms.group(2) or 0)
+                    if sc.is_const(a):
+                        v = const_val(format(a.const, spec))
+                    elif width == 0:
+                        v = sc.op1(C["TPLX_OP_I2S"], T_STR, a)
+                    else:  # flags: bit0 zero pad, bit1 full 64-bit value (fmt / str.format, unlike C's %d)
+                        v = sc.op1(C["TPLX_OP_SFMTD"], T_STR, a, flags=(1 if ms.group(1) else 0) | 2, imm=width)
+                else:
+                    raise UnsupportedUDF("format of float/bool")
+            out = v if out is None else self.binop(ast.Add(), out, v)
+        return out if out is not None else const_val("")
+
     # ---- comparisons (BlockGeneratorVisitor.cc:776-880) -------------------------------------------------
     def compare(self, e: ast.Compare):
         sc = self.sc
@@ -1159,6 +1236,15 @@ class _FuncCompiler:
 
     def compare1(self, op, l, r):
         sc = self.sc
+        if isinstance(op, (ast.In, ast.NotIn)) and isinstance(r, TupleVal):
+            # x in (c1, c2, ...): membership in a literal tuple/list = a chain of equality tests
+            if isinstance(l, TupleVal) or not r.elems:
+                raise UnsupportedUDF("`in` over this container")
+            acc = None
+            for e_ in r.elems:
+                c = self.compare1(ast.Eq(), l, e_)
+                acc = c if acc is None else sc.b_or(acc, c)
+            return sc.b_not(acc) if isinstance(op, ast.NotIn) else acc
         if isinstance(l, TupleVal) or isinstance(r, TupleVal):
             raise UnsupportedUDF("tuple comparison")
         if isinstance(op, (ast.In, ast.NotIn)):
@@ -1292,6 +1378,15 @@ class _FuncCompiler:
             if name == "abs" and len(args) == 1 and args[0].type != T_STR:
                 a = args[0]
                 return sc.op1(C["TPLX_OP_FABS"], T_F64, a) if a.type == T_F64 else sc.op1(C["TPLX_OP_IABS"], T_I64, sc.to_i64(a))
+            if name in ("min", "max") and len(args) == 2 and all(a.type != T_STR for a in args):
+                x, y = args
+                if x.type == T_F64 or y.type == T_F64:
+                    x, y = sc.to_f64(x), sc.to_f64(y)
+                    c = sc.op2(C["TPLX_OP_FCMP"], T_BOOL, y, x, flags=C["TPLX_CMP_LT" if name == "min" else "TPLX_CMP_GT"])
+                else:
+                    x, y = sc.to_i64(x), sc.to_i64(y)
+                    c = sc.op2(C["TPLX_OP_ICMP"], T_BOOL, y, x, flags=C["TPLX_CMP_LT" if name == "min" else "TPLX_CMP_GT"])
+                return sc.select(c, y, x)  # Python: min(x, y) returns y only if y < x
             raise UnsupportedUDF(f"call to {name}()")
         if isinstance(e.func, ast.Attribute):
             obj = self.expr(e.func.value)
@@ -1305,6 +1400,10 @@ class _FuncCompiler:
             def want_str(n):
                 if len(args) != n or any(a.type != T_STR for a in args):
                     raise UnsupportedUDF(f"str.{m} expects {n} string argument(s)")
+            if m == "format":
+                if not sc.is_const(obj):
+                    raise UnsupportedUDF("format string must be a literal")
+                return self.format_braces(obj.const, args)
             if m in ("find", "rfind", "index"):
                 want_str(1)
                 if m == "index":
