@@ -160,6 +160,51 @@ int32_t tplx_gpu_stage_hash_export_raw(tplx_stage *stage, int32_t device, tplx_r
 /* Drop the device's table (start a new job on the same stage). */
 int32_t tplx_gpu_stage_hash_reset(tplx_stage *stage, int32_t device);
 
+/* ---- CSV source (K6) ----------------------------------------------------------------------- */
+/* Replaces the reference's host CSV source in front of a TransformStage: CSVReader::read +
+ * csvmonkey row/cell splitting (core/src/physical/CSVReader.cc:388-634, core/include/physical/csvmonkey.h:523-672)
+ * and the cell decoding at the head of the stage function (decodeCells, codegen/src/FlattenedTuple.cc:1215-1330;
+ * fast_atoi64 / fast_atod / fast_atob, utils/src/StringUtils.cc:22-255 behind runtime/src/Runtime.cc:319-385).
+ * Output: a column block of the rows that fit the normal case (tplx_gpu_stage_run input) and a list of the rows
+ * that do not (cell-count mismatch, null value in a non-Option column, conversion error): those go to the
+ * interpreter path as BADPARSE_STRING_INPUT / NULLERROR rows do in the reference (CSVReader.cc:470-520,583-600). */
+#define TPLX_CSV_SKIP 0xFF /* col_types entry: column is not read (projection pushdown, willBeSerialized = false) */
+typedef struct tplx_csv_buffer tplx_csv_buffer; /* CSV bytes resident on a device */
+typedef struct tplx_csv_result tplx_csv_result;
+typedef struct tplx_csv_desc {
+    uint8_t delimiter;      /* ',' */
+    uint8_t quotechar;      /* '"' */
+    uint8_t skip_header;    /* 1: the first row is a header and is dropped (CSVReader.cc:419-449) */
+    uint8_t n_null_values;  /* <= 8, together <= 64 bytes */
+    uint32_t n_file_cols;   /* cells every row must have */
+    const uint8_t *col_types;       /* [n_file_cols] tplx_type or TPLX_CSV_SKIP; at most TPLX_MAX_COLS are read */
+    const char *const *null_values; /* compared with the dequoted cell (compareToNullValues) */
+} tplx_csv_desc;
+typedef struct tplx_csv_bad_row {
+    uint32_t row;        /* index among the data rows (header excluded) */
+    uint32_t code;       /* TPLX_EC_BADPARSE_STRING_INPUT or TPLX_EC_NULLERROR */
+    uint32_t line_start; /* byte range of the row inside the buffer, newline excluded */
+    uint32_t line_end;
+} tplx_csv_bad_row;
+typedef struct tplx_csv_info {
+    uint64_t n_rows;   /* data rows found (header excluded) */
+    uint64_t n_normal; /* rows in the block */
+    uint64_t n_bad;    /* rows for the interpreter path */
+    uint32_t sequential_rows; /* 1: irregular quoting, rows were found by the exact sequential kernel */
+    uint32_t kernel_launches;
+    double parse_ms;   /* CUDA-event time of the parse on the device stream */
+} tplx_csv_info;
+/* Copy n_bytes (< 4 GiB - 64 KiB) of CSV text to the device (pinned or pageable host memory). */
+int32_t tplx_gpu_csv_upload(int32_t device, const void *bytes, uint64_t n_bytes, tplx_csv_buffer **out);
+int32_t tplx_gpu_csv_buffer_free(tplx_csv_buffer *buf);
+/* Parse a resident buffer into a column block holding the non-skipped columns in file order. */
+int32_t tplx_gpu_csv_parse(tplx_csv_buffer *buf, const tplx_csv_desc *desc, tplx_block **out_block,
+                           tplx_csv_result **out_res);
+int32_t tplx_gpu_csv_result_info(tplx_csv_result *res, tplx_csv_info *info);
+int32_t tplx_gpu_csv_result_fetch_bad_rows(tplx_csv_result *res, tplx_csv_bad_row *rows /* n_bad, ascending row */);
+int32_t tplx_gpu_csv_result_fetch_rowmap(tplx_csv_result *res, uint32_t *rowmap /* n_normal: block row -> data row */);
+int32_t tplx_gpu_csv_result_free(tplx_csv_result *res);
+
 #ifdef __cplusplus
 }
 #endif

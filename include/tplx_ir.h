@@ -92,6 +92,7 @@ enum tplx_exception_code {
     TPLX_EC_SUCCESS = 0,
     TPLX_EC_NORMALCASEVIOLATION = 7,
     TPLX_EC_NULLERROR = 50,
+    TPLX_EC_BADPARSE_STRING_INPUT = 70, /* CSV row that does not fit the normal case (ExceptionCodes.h:118) */
     TPLX_EC_PYTHON_PARALLELIZE = 80,
     TPLX_EC_INDEXERROR = 111,
     TPLX_EC_TYPEERROR = 129,

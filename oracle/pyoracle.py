@@ -212,3 +212,88 @@ def cpython_pipeline(rows: Sequence, ops: Sequence[Tuple[str, object]]):
         except Exception as e:  # noqa: BLE001
             bad.append((i, type(e).__name__))
     return out, bad
+
+
+# ---------------------------------------------------------------------------------------------
+# CSV source oracle (csv_oracle.c)
+# ---------------------------------------------------------------------------------------------
+T_SKIP = 0xFF
+
+
+class _CsvBad(ct.Structure):
+    _fields_ = [("row", ct.c_uint32), ("code", ct.c_uint32), ("line_start", ct.c_uint32), ("line_end", ct.c_uint32)]
+
+
+class _CsvResult(ct.Structure):
+    _fields_ = [("n_out_cols", ct.c_uint32), ("out_types", ct.c_uint8 * 256),
+                ("n_rows", ct.c_uint64), ("n_normal", ct.c_uint64), ("n_bad", ct.c_uint64),
+                ("fixed", ct.c_void_p * 256), ("offsets", ct.c_void_p * 256), ("bytes", ct.c_void_p * 256),
+                ("bytes_len", ct.c_uint64 * 256), ("bytes_cap", ct.c_uint64 * 256),
+                ("rowmap", ct.c_void_p), ("bad", ct.c_void_p), ("cap_rows", ct.c_uint64), ("cap_bad", ct.c_uint64),
+                ("dump", ct.c_void_p), ("dump_len", ct.c_uint64), ("dump_cap", ct.c_uint64)]
+
+
+class CsvOracleResult:
+    """columns: list of np.int64/float64/bool arrays or (bytes, offsets) pairs for the parsed (non-skipped) columns."""
+
+    def __init__(self, n_rows, columns, types, rowmap, bad, dump):
+        self.n_rows, self.columns, self.types, self.rowmap, self.bad, self.dump = n_rows, columns, types, rowmap, bad, dump
+        self.n_normal = len(rowmap)
+
+
+def csv_parse(data: bytes, col_types: Sequence[int], delimiter=",", quotechar='"', header=False,
+              null_values: Sequence[str] = ("",), dump_cells=False) -> CsvOracleResult:
+    L = lib()
+    L.csv_oracle_parse.restype = ct.POINTER(_CsvResult)
+    L.csv_oracle_parse.argtypes = [ct.c_char_p, ct.c_uint64, ct.c_char, ct.c_char, ct.c_int, ct.c_uint32, ct.c_char_p,
+                                   ct.c_uint32, ct.POINTER(ct.c_char_p), ct.c_int]
+    L.csv_oracle_free.argtypes = [ct.POINTER(_CsvResult)]
+    nulls = (ct.c_char_p * max(1, len(null_values)))(*[s.encode() for s in null_values])
+    rp = L.csv_oracle_parse(data, len(data), delimiter.encode(), quotechar.encode(), int(header), len(col_types),
+                            bytes(col_types), len(null_values), nulls, int(dump_cells))
+    r = rp.contents
+    n = int(r.n_normal)
+    cols, types = [], []
+    for c in range(r.n_out_cols):
+        t = r.out_types[c]
+        types.append(t)
+        if t == T_STR:
+            offs = np.ctypeslib.as_array(ct.cast(r.offsets[c], ct.POINTER(ct.c_uint32)), (n + 1,)).copy()
+            nb = int(r.bytes_len[c])
+            by = ct.string_at(r.bytes[c], nb) if nb else b""
+            cols.append((by, offs))
+        else:
+            a = np.ctypeslib.as_array(ct.cast(r.fixed[c], ct.POINTER(ct.c_int64)), (n,)).copy() if n else np.zeros(0, np.int64)
+            cols.append(a.view(np.float64) if t == T_F64 else a)
+    rowmap = np.ctypeslib.as_array(ct.cast(r.rowmap, ct.POINTER(ct.c_uint32)), (n,)).copy() if n else np.zeros(0, np.uint32)
+    bad = [(b.row, b.code, b.line_start, b.line_end) for b in
+           (ct.cast(r.bad, ct.POINTER(_CsvBad))[i] for i in range(int(r.n_bad)))]
+    dump = ct.string_at(r.dump, int(r.dump_len)) if r.dump_len else b""
+    out = CsvOracleResult(int(r.n_rows), cols, types, rowmap, bad, dump)
+    L.csv_oracle_free(rp)
+    return out
+
+
+def csv_ref_cells(data: bytes, delimiter=",", quotechar='"') -> Optional[bytes]:
+    """Cell dump of the reference's own csvmonkey reader (oracle/_ref/csv_ref); None when the binary is absent."""
+    exe = os.path.join(_HERE, "_ref", "csv_ref")
+    if not os.path.exists(exe):
+        return None
+    import tempfile
+    with tempfile.NamedTemporaryFile(suffix=".csv") as f:
+        f.write(data)
+        f.flush()
+        return subprocess.run([exe, f.name, delimiter, quotechar], check=True, capture_output=True).stdout
+
+
+def csv_scalar(kind: str, s: str):
+    """fast_atoi64 / fast_atod / fast_atob behind the runtime's trimming wrapper; None = ValueError."""
+    L = lib()
+    if kind == "i64":
+        v = ct.c_int64()
+        return None if L.csv_oracle_atoi64(s.encode("latin1"), ct.byref(v)) else v.value
+    if kind == "f64":
+        d = ct.c_double()
+        return None if L.csv_oracle_atod(s.encode("latin1"), ct.byref(d)) else d.value
+    b = ct.c_int()
+    return None if L.csv_oracle_atob(s.encode("latin1"), ct.byref(b)) else bool(b.value)

@@ -1,0 +1,131 @@
+"""GPU parity for the CSV source (K6), through the C ABI: tplx_gpu_csv_upload / tplx_gpu_csv_parse.
+
+The parsed block is read back through an identity stage (tplx_gpu_stage_run) and compared bit for bit with the CPU
+oracle (oracle/csv_oracle.c, pinned in tests/test_csv_oracle.py): values, string bytes and offsets, the block-row ->
+data-row map, and the list of rows handed to the interpreter path (row, code, byte range).
+"""
+import gzip
+import hashlib
+import os
+import random
+
+import numpy as np
+import pytest
+
+from tuplex_b200 import backend, frontend, ir, workloads
+from tuplex_b200.ir import T_BOOL, T_F64, T_I64, T_STR
+from oracle import pyoracle as po
+from csv_helpers import T_SKIP, Parsed, assert_same_parse, gen_csv
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+I, F, B, S, X = T_I64, T_F64, T_BOOL, T_STR, T_SKIP
+
+
+def gpu_parse(data: bytes, types, **kw) -> Parsed:
+    buf = backend.CsvBuffer(0, data)
+    p = buf.parse(types, **kw)
+    info = p.info
+    out_types = [t for t in types if t != X]
+    cols = []
+    if out_types:
+        sc = frontend.StageCompiler(out_types, [None] * len(out_types))
+        sc.add_map(lambda x: x, 100001)
+        st = backend.Stage(sc.finish_memory())
+        res = st.run(p.block)
+        assert int(res.info.n_out_rows) == int(info.n_normal) and int(res.info.n_exceptions) == 0
+        for c, t in enumerate(out_types):
+            col = res.column(c)
+            cols.append((col.data.tobytes(), col.offsets) if t == T_STR else (col.data.view(np.float64) if t == T_F64 else col.data))
+        res.free()
+        st.close()
+    bad = [(int(b["row"]), int(b["code"]), int(b["line_start"]), int(b["line_end"])) for b in p.bad_rows()]
+    out = Parsed(int(info.n_rows), cols, out_types, p.rowmap(), bad, int(info.sequential_rows))
+    assert int(info.n_normal) + int(info.n_bad) == int(info.n_rows)
+    p.free()
+    buf.free()
+    return out
+
+
+def test_reference_vectors_on_gpu(gpu):
+    from test_csv_oracle import VECTORS, _values
+    for text, types, ok, expect in VECTORS:
+        r = gpu_parse(text.encode(), types, null_values=[])
+        assert r.n_rows == 1
+        if ok:
+            assert not r.bad and _values(r) == expect, text
+        else:
+            assert len(r.bad) == 1 and r.bad[0][1] == 70, text
+
+
+def test_fuzz_equals_oracle(gpu):
+    rng = random.Random(23)
+    seq = 0
+    for it in range(120):
+        ncols = rng.randint(1, 7)
+        types = [rng.choice([I, F, B, S, S, X]) for _ in range(ncols)]
+        data = gen_csv(rng, rng.choice([0, 1, 7, 300, 3000]), types, dirty=rng.choice([0.0, 0.05, 0.3]),
+                       weird_quotes=rng.choice([0.0, 0.0, 0.01]))
+        kw = dict(header=rng.random() < 0.5, null_values=rng.choice([[], [""], ["", "NULL"]]))
+        a = gpu_parse(data, types, **kw)
+        assert_same_parse(a, po.csv_parse(data, types, **kw), what=(it, data[:120]))
+        seq += a.sequential
+    assert seq > 0  # irregular quoting went through csv_rows_sequential on the device
+
+
+def test_edge_inputs(gpu):
+    for data in (b"", b"\n", b"\r\n\r\n", b"a", b"a,b", b'"', b'""', b'"a\nb"', b",", b",\n,", b"x" * 70000, b'"' + b"y" * 40000 + b'"\n1',
+                 (b"1,2\n" * 5000) + b'3,"4', b"a\r\nb\rc\nd"):
+        for types in ([S], [S, S], [I, S]):
+            for header in (False, True):
+                a = gpu_parse(data, types, header=header)
+                assert_same_parse(a, po.csv_parse(data, types, header=header), what=(data[:40], types, header))
+
+
+def test_tile_boundaries(gpu):
+    """quotes, newlines and \\r\\n pairs placed across 64-byte span and 16 KB tile boundaries"""
+    rng = random.Random(5)
+    for it in range(30):
+        pad = rng.choice([60, 62, 63, 64, 16380, 16383, 16384, 32767])
+        body = rng.choice([b'"q,\n"', b"\r\n", b'""', b'a,"b\r\nc"\r\n', b"\n\n\n"])
+        data = b"x" * pad + body + b"tail,1\n" + b"u,v\n" * rng.randint(0, 5000) + b'"last ""one""",2'
+        a = gpu_parse(data, [S, S])
+        assert_same_parse(a, po.csv_parse(data, [S, S]), what=(pad, body))
+
+
+def _zillow_csv():
+    return gzip.open(os.path.join(HERE, "golden", "zillow_noexc.csv.gz"), "rb").read()
+
+
+ZILLOW_FILE_TYPES = [S, S, S, S, F, S, S, X, S, X]  # title..url with projection pushdown; postal_code inferred f64
+
+
+def test_zillow_csv_to_golden_md5(gpu):
+    """reference fixture CSV -> device parse -> Z1 stage -> the md5 of the reference's own C++ / Python baselines"""
+    data = _zillow_csv()
+    buf = backend.CsvBuffer(0, data)
+    p = buf.parse(ZILLOW_FILE_TYPES, header=True)
+    assert int(p.info.n_rows) == 32661 and int(p.info.n_bad) == 0 and int(p.info.sequential_rows) == 0
+    st = backend.Stage(workloads.zillow_program())
+    res = st.run(p.block)
+    vals = [c.to_values() for c in res.columns()]
+    txt = workloads.rows_to_csv(vals, workloads.ZILLOW_OUT)
+    assert hashlib.md5(txt).hexdigest() == "4d5ca0263b1a5058341a369116dee83a"
+
+
+def test_zillow_csv_replicated(gpu):
+    """full-size property: k copies of the fixture body parse to k * 32,661 rows and k * 577 output rows"""
+    data = _zillow_csv()
+    head, body = data.split(b"\n", 1)
+    k = 40  # ~270 MB of CSV
+    big = head + b"\n" + body * k
+    buf = backend.CsvBuffer(0, big)
+    p = buf.parse(ZILLOW_FILE_TYPES, header=True)
+    assert int(p.info.n_rows) == 32661 * k and int(p.info.n_bad) == 0
+    st = backend.Stage(workloads.zillow_program())
+    res = st.run(p.block)
+    assert int(res.info.n_out_rows) == 577 * k and int(res.info.n_exceptions) == 0
+    vals = [c.to_values() for c in res.columns()]
+    golden = workloads.zillow_golden_csv().decode().split("\n")[1:-1]
+    for j in (0, 17, k - 1):
+        assert workloads.rows_to_csv([v[j * 577:(j + 1) * 577] for v in vals], None).decode().split("\n")[:-1] == golden

@@ -40,6 +40,18 @@ class CResultInfo(ct.Structure):
                 ("kernel_launches", ct.c_uint32), ("zero_copy_cols", ct.c_uint32), ("h2d_bytes", ct.c_uint64)]
 
 
+class CCsvDesc(ct.Structure):
+    _fields_ = [("delimiter", ct.c_uint8), ("quotechar", ct.c_uint8), ("skip_header", ct.c_uint8), ("n_null_values", ct.c_uint8),
+                ("n_file_cols", ct.c_uint32), ("col_types", ct.c_char_p), ("null_values", ct.POINTER(ct.c_char_p))]
+
+
+class CCsvInfo(ct.Structure):
+    _fields_ = [("n_rows", ct.c_uint64), ("n_normal", ct.c_uint64), ("n_bad", ct.c_uint64), ("sequential_rows", ct.c_uint32),
+                ("kernel_launches", ct.c_uint32), ("parse_ms", ct.c_double)]
+
+
+CSV_SKIP = 0xFF
+CSV_BAD_DTYPE = np.dtype([("row", "<u4"), ("code", "<u4"), ("line_start", "<u4"), ("line_end", "<u4")])
 EXC_DTYPE = np.dtype([("row", "<i8"), ("row_no", "<i8"), ("code", "<i8"), ("op_id", "<i8")])
 
 _lib = None
@@ -84,6 +96,13 @@ def lib():
         "tplx_gpu_stage_hash_export_raw": ([vp, i32, P(vp)], i32),
         "tplx_gpu_stage_hash_merge": ([vp, vp], i32),
         "tplx_gpu_stage_hash_reset": ([vp, i32], i32),
+        "tplx_gpu_csv_upload": ([i32, vp, u64, P(vp)], i32),
+        "tplx_gpu_csv_buffer_free": ([vp], i32),
+        "tplx_gpu_csv_parse": ([vp, P(CCsvDesc), P(vp), P(vp)], i32),
+        "tplx_gpu_csv_result_info": ([vp, P(CCsvInfo)], i32),
+        "tplx_gpu_csv_result_fetch_bad_rows": ([vp, vp], i32),
+        "tplx_gpu_csv_result_fetch_rowmap": ([vp, vp], i32),
+        "tplx_gpu_csv_result_free": ([vp], i32),
     }
     for name, (argtypes, restype) in sig.items():
         fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
@@ -382,6 +401,86 @@ class Result:
         if self._h:
             lib().tplx_gpu_result_free(self._h)
             self._h = ct.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------------------------
+# CSV source (K6): bytes -> column block on the device
+# ------------------------------------------------------------------------------------------------
+class CsvBuffer:
+    """CSV text resident on a device (tplx_gpu_csv_upload)."""
+
+    def __init__(self, device: int, data):
+        init([device])
+        self.device = device
+        self._arr = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+        self.n_bytes = int(self._arr.size)
+        self._h = ct.c_void_p()
+        _check(lib().tplx_gpu_csv_upload(device, self._arr.ctypes.data if self.n_bytes else None, self.n_bytes, ct.byref(self._h)),
+               "tplx_gpu_csv_upload")
+
+    def parse(self, col_types: Sequence[int], delimiter=",", quotechar='"', header=False, null_values: Sequence[str] = ("",)) -> "CsvParse":
+        d = CCsvDesc()
+        d.delimiter, d.quotechar, d.skip_header = ord(delimiter), ord(quotechar), int(bool(header))
+        d.n_null_values = len(null_values)
+        d.n_file_cols = len(col_types)
+        types = bytes(col_types)
+        d.col_types = types
+        nv = (ct.c_char_p * max(1, len(null_values)))(*[s.encode() for s in null_values])
+        d.null_values = nv
+        hb, hr = ct.c_void_p(), ct.c_void_p()
+        _check(lib().tplx_gpu_csv_parse(self._h, ct.byref(d), ct.byref(hb), ct.byref(hr)), "tplx_gpu_csv_parse")
+        nr = ct.c_uint64()
+        _check(lib().tplx_gpu_block_rows(hb, ct.byref(nr)), "tplx_gpu_block_rows")
+        return CsvParse(Block(hb, nr.value, self.device), hr, [t for t in col_types if t != CSV_SKIP])
+
+    def free(self):
+        if self._h:
+            lib().tplx_gpu_csv_buffer_free(self._h)
+            self._h = ct.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class CsvParse:
+    """Result of CsvBuffer.parse: `.block` feeds Stage.run; bad rows go to the interpreter path."""
+
+    def __init__(self, block: Block, h, types: List[int]):
+        self.block, self._h, self.types = block, h, types
+        self._info = None
+
+    @property
+    def info(self) -> CCsvInfo:
+        if self._info is None:
+            i = CCsvInfo()
+            _check(lib().tplx_gpu_csv_result_info(self._h, ct.byref(i)), "tplx_gpu_csv_result_info")
+            self._info = i
+        return self._info
+
+    def bad_rows(self) -> np.ndarray:
+        out = np.zeros(int(self.info.n_bad), dtype=CSV_BAD_DTYPE)
+        _check(lib().tplx_gpu_csv_result_fetch_bad_rows(self._h, out.ctypes.data if len(out) else None), "tplx_gpu_csv_result_fetch_bad_rows")
+        return out
+
+    def rowmap(self) -> np.ndarray:
+        out = np.zeros(int(self.info.n_normal), dtype=np.uint32)
+        _check(lib().tplx_gpu_csv_result_fetch_rowmap(self._h, out.ctypes.data if len(out) else None), "tplx_gpu_csv_result_fetch_rowmap")
+        return out
+
+    def free(self):
+        if self._h:
+            lib().tplx_gpu_csv_result_free(self._h)
+            self._h = ct.c_void_p()
+        self.block.free()
 
     def __del__(self):
         try:

@@ -1,0 +1,451 @@
+// csvops.cuh — CSV row machine and cell decoders (K6), host + device.
+//
+// Restated from the reference's default CSV source (paths relative to /root/reference/tuplex/):
+//   row / cell splitting   csvmonkey::CsvReader::try_parse      core/include/physical/csvmonkey.h:523-672
+//   cell dequoting         csvmonkey::CsvCell::as_str            core/include/physical/csvmonkey.h:320-335
+//   newline at EOF         VFCSVStreamCursor (appends '\n')      core/src/physical/CSVReader.cc:66-100,167-177
+//   cells -> typed row     decodeCells                           codegen/src/FlattenedTuple.cc:1215-1330
+//   int / float / bool     fast_atoi64, fast_atod, fast_atob     runtime/src/Runtime.cc:319-385, utils/src/StringUtils.cc:22-260
+// The generated parser (core/src/physical/CSVParseRowGenerator.cc:436-760) splits rows the same way on the inputs its
+// tests hold (test/core/CSVRowParseGeneratorTests.cc); those tests are this file's known-answer vectors.
+//
+// Buffer contract: positions are uint32; the caller guarantees buf[n] == '\n' (the newline the reference's cursor
+// appends), so every scan below terminates at or before position n.
+//
+// Compiles for the host as well (tests/test_csv_host.py fuzzes these exact functions against the oracle).
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+#include "strops.cuh"
+
+namespace tplx {
+
+constexpr uint32_t CSV_UNDERRUN = 0xFFFFFFFFu;  // input ended inside a quoted cell: csvmonkey yields no row
+constexpr uint32_t CSV_DEQ_CAP = 64;            // local buffer for escaped numeric cells
+
+#ifdef __CUDA_ARCH__
+#define TPLX_DMUL(a, b) __dmul_rn((a), (b))
+#define TPLX_DADD(a, b) __dadd_rn((a), (b))
+#define TPLX_DDIV(a, b) __ddiv_rn((a), (b))
+#else  // host build uses -ffp-contract=off
+#define TPLX_DMUL(a, b) ((a) * (b))
+#define TPLX_DADD(a, b) ((a) + (b))
+#define TPLX_DDIV(a, b) ((a) / (b))
+#endif
+
+TPLX_HD bool csv_is_nl(uint8_t c) { return c == '\n' || c == '\r'; }
+
+// Runs the row machine from p (first byte of the row, never a newline). f(cell_index, begin, end, escaped) is
+// called for every cell ([begin,end) = raw content, quotes of a quoted cell excluded). Returns the position of
+// the row's terminating newline and the number of cells, or CSV_UNDERRUN.
+template <class F>
+TPLX_HD uint32_t csv_row_machine(const uint8_t *buf, uint32_t p, uint32_t n, uint8_t delim, uint8_t quote, uint32_t *ncells,
+                                 F &&f) {
+    uint32_t cell = 0;
+    for (;;) {
+        uint8_t c = buf[p];
+        if (csv_is_nl(c)) {  // newline right after a delimiter: empty final cell (csvmonkey.h:567-577)
+            f(cell, p, p, false);
+            *ncells = cell + 1;
+            return p;
+        }
+        if (c == quote) {
+            const uint32_t b = ++p;
+            bool esc = false;
+            for (;;) {
+                while (p <= n && buf[p] != quote) ++p;
+                if (p >= n) return CSV_UNDERRUN;  // buf[n] is the appended newline, never a quote
+                const uint32_t q = p++;           // p = byte after the quote (<= n)
+                c = buf[p];
+                if (c == delim) {
+                    f(cell, b, q, esc);
+                    ++cell;
+                    ++p;
+                    break;
+                }
+                if (csv_is_nl(c)) {
+                    f(cell, b, q, esc);
+                    *ncells = cell + 1;
+                    return p;
+                }
+                esc = true;  // doubled quote or stray quote: the following byte is skipped (csvmonkey.h:619-623)
+                ++p;
+            }
+        } else {
+            const uint32_t b = p;
+            while (buf[p] != delim && !csv_is_nl(buf[p])) ++p;
+            f(cell, b, p, false);
+            if (buf[p] == delim) {
+                ++cell;
+                ++p;
+            } else {
+                *ncells = cell + 1;
+                return p;
+            }
+        }
+    }
+}
+
+// as_str(): every quote character is dropped and the byte after it copied verbatim
+TPLX_HD uint32_t csv_dequoted_len(const uint8_t *buf, uint32_t b, uint32_t e, uint8_t quote) {
+    uint32_t o = 0;
+    for (uint32_t i = b; i < e; ++i) {
+        if (buf[i] == quote) {
+            ++i;
+            if (i >= e) break;
+        }
+        ++o;
+    }
+    return o;
+}
+TPLX_HD uint32_t csv_dequote(const uint8_t *buf, uint32_t b, uint32_t e, uint8_t quote, uint8_t *out, uint32_t cap) {
+    uint32_t o = 0;
+    for (uint32_t i = b; i < e; ++i) {
+        if (buf[i] == quote) {
+            ++i;
+            if (i >= e) break;
+        }
+        if (o < cap) out[o] = buf[i];
+        ++o;
+    }
+    return o;
+}
+
+// dequoted cell == s ?
+TPLX_HD bool csv_cell_equals(const uint8_t *buf, uint32_t b, uint32_t e, bool escaped, uint8_t quote, const uint8_t *s,
+                             uint32_t slen) {
+    if (!escaped) {
+        if (e - b != slen) return false;
+        for (uint32_t i = 0; i < slen; ++i)
+            if (buf[b + i] != s[i]) return false;
+        return true;
+    }
+    uint32_t o = 0;
+    for (uint32_t i = b; i < e; ++i) {
+        if (buf[i] == quote) {
+            ++i;
+            if (i >= e) break;
+        }
+        if (o >= slen || buf[i] != s[o]) return false;
+        ++o;
+    }
+    return o == slen;
+}
+
+// whitespace trimming shared by the runtime wrappers (Runtime.cc:319-341,343-365): [i, e) of p[0..len)
+TPLX_HD void csv_trim(const uint8_t *p, uint32_t len, uint32_t *pi, uint32_t *pe) {
+    uint32_t i = 0, e = len;
+    while (i < e && is_pyspace(p[i])) ++i;
+    if (e > i) {
+        uint32_t e2 = e - 1;
+        while (e2 > i && is_pyspace(p[e2])) --e2;
+        e = e2 + 1;
+    }
+    *pi = i;
+    *pe = e;
+}
+
+// fast_atod (StringUtils.cc:71-163) behind the runtime wrapper's trim; false = ValueError.
+// The accumulation is the reference's own (not correctly rounded): value = 10*value + d; value += d / pow10.
+TPLX_HD bool csv_atod(const uint8_t *s, uint32_t len, double *out) {
+    uint32_t i0, e;
+    csv_trim(s, len, &i0, &e);
+    if (i0 == e) return false;
+    // bytes at or past e never match a digit, sign, '.', 'e' or a letter of nan/infinity in the reference either
+    // (there it is whitespace or the terminator), so they read as 0 here
+#define CH(k) ((k) < e ? s[(k)] : (uint8_t)0)
+    uint32_t p = i0;
+    double sign = 1.0;
+    if (CH(p) == '-') {
+        sign = -1.0;
+        ++p;
+    } else if (CH(p) == '+')
+        ++p;
+    double value = 0.0;
+    for (; (uint8_t)(CH(p) - '0') <= 9; ++p) value = TPLX_DADD(TPLX_DMUL(10.0, value), (double)(CH(p) - '0'));
+    if (CH(p) == '.') {
+        double pow10 = 10.0;
+        ++p;
+        while ((uint8_t)(CH(p) - '0') <= 9) {
+            value = TPLX_DADD(value, TPLX_DDIV((double)(CH(p) - '0'), pow10));
+            pow10 = TPLX_DMUL(pow10, 10.0);
+            ++p;
+        }
+    }
+    int frac = 0;
+    double scale = 1.0;
+    if (CH(p) == 'e' || CH(p) == 'E') {
+        uint32_t exponent = 0;
+        ++p;
+        if (CH(p) == '-') {
+            frac = 1;
+            ++p;
+        } else if (CH(p) == '+')
+            ++p;
+        for (; (uint8_t)(CH(p) - '0') <= 9; ++p) exponent = exponent * 10u + (uint32_t)(CH(p) - '0');
+        if (exponent > 308) exponent = 308;
+        while (exponent >= 50) {
+            scale = TPLX_DMUL(scale, 1E50);
+            exponent -= 50;
+        }
+        while (exponent >= 8) {
+            scale = TPLX_DMUL(scale, 1E8);
+            exponent -= 8;
+        }
+        while (exponent > 0) {
+            scale = TPLX_DMUL(scale, 10.0);
+            exponent -= 1;
+        }
+    }
+    int nanmatch = 0, infmatch = 0;
+    if (p == i0) {
+        const char *nanstr = "nan";
+        while (nanmatch < 3 && (CH(p) == (uint8_t)nanstr[nanmatch] || CH(p) == (uint8_t)(nanstr[nanmatch] - 32))) {
+            ++p;
+            ++nanmatch;
+        }
+    }
+    if (p == i0) {
+        const char *infstr = "infinity";
+        while (infmatch < 8 && (CH(p) == (uint8_t)infstr[infmatch] || CH(p) == (uint8_t)(infstr[infmatch] - 32))) {
+            ++p;
+            ++infmatch;
+        }
+    }
+#undef CH
+    if (p != e) return false;
+    if (nanmatch == 3) {
+        uint64_t bits = 0x7FF8000000000000ull;  // NAN
+        *out = *reinterpret_cast<double *>(&bits);
+    } else if (infmatch == 3 || infmatch == 8) {
+        uint64_t bits = 0x7FF0000000000000ull;  // +INFINITY (the sign is not applied, StringUtils.cc:155)
+        *out = *reinterpret_cast<double *>(&bits);
+    } else {
+        *out = TPLX_DMUL(sign, frac ? TPLX_DDIV(value, scale) : TPLX_DMUL(value, scale));
+    }
+    return true;
+}
+
+// fast_atob (StringUtils.cc:180-255): no trimming; t/y/f/n, no, yes, true, false — case-insensitive
+TPLX_HD bool csv_atob(const uint8_t *s, uint32_t len, int64_t *out) {
+    uint8_t b[5];
+    if (len == 0 || len > 5) return false;
+    for (uint32_t i = 0; i < len; ++i) b[i] = case1(s[i], TPLX_SF_LOWER);
+    switch (len) {
+        case 1:
+            if (b[0] == 'y' || b[0] == 't') {
+                *out = 1;
+                return true;
+            }
+            if (b[0] == 'n' || b[0] == 'f') {
+                *out = 0;
+                return true;
+            }
+            return false;
+        case 2:
+            if (b[0] == 'n' && b[1] == 'o') {
+                *out = 0;
+                return true;
+            }
+            return false;
+        case 3:
+            if (b[0] == 'y' && b[1] == 'e' && b[2] == 's') {
+                *out = 1;
+                return true;
+            }
+            return false;
+        case 4:
+            if (b[0] == 't' && b[1] == 'r' && b[2] == 'u' && b[3] == 'e') {
+                *out = 1;
+                return true;
+            }
+            return false;
+        default:
+            if (b[0] == 'f' && b[1] == 'a' && b[2] == 'l' && b[3] == 's' && b[4] == 'e') {
+                *out = 0;
+                return true;
+            }
+            return false;
+    }
+}
+
+// what a selected column needs from one cell
+struct CsvNulls {
+    uint8_t n;
+    uint8_t off[9];     // value k = bytes[off[k], off[k+1])
+    uint8_t bytes[64];
+};
+
+TPLX_HD bool csv_cell_is_null(const uint8_t *buf, uint32_t b, uint32_t e, bool escaped, uint8_t quote, const CsvNulls &nv) {
+    for (uint32_t k = 0; k < nv.n; ++k)
+        if (csv_cell_equals(buf, b, e, escaped, quote, nv.bytes + nv.off[k], (uint32_t)(nv.off[k + 1] - nv.off[k]))) return true;
+    return false;
+}
+
+// typed decode of one numeric / bool cell -> 64-bit slot value; false = conversion error
+TPLX_HD bool csv_decode_scalar(const uint8_t *buf, uint32_t b, uint32_t e, bool escaped, uint8_t quote, uint8_t type,
+                               uint64_t *bits) {
+    uint8_t tmp[CSV_DEQ_CAP];
+    const uint8_t *p = buf + b;
+    uint32_t len = e - b;
+    if (escaped) {
+        len = csv_dequote(buf, b, e, quote, tmp, CSV_DEQ_CAP);
+        if (len > CSV_DEQ_CAP) return false;  // left to the interpreter path
+        p = tmp;
+    }
+    if (type == TPLX_T_I64) {
+        StrV s{p, len, 0};
+        int64_t v;
+        if (!str_to_i64(s, &v)) return false;
+        *bits = (uint64_t)v;
+        return true;
+    }
+    if (type == TPLX_T_F64) {
+        double d;
+        if (!csv_atod(p, len, &d)) return false;
+        *bits = *reinterpret_cast<uint64_t *>(&d);
+        return true;
+    }
+    int64_t bv;
+    if (!csv_atob(p, len, &bv)) return false;
+    *bits = (uint64_t)bv;
+    return true;
+}
+
+// ---- row finding by quote parity ------------------------------------------------------------------
+constexpr uint32_t CSV_SPAN = 64;  // bytes walked by one thread
+constexpr uint32_t CSV_SKIP = 0xFF;
+
+struct CsvState {
+    uint32_t par;  // quotes in the span, mod 2
+    uint32_t c0;   // row ends in the span if it starts outside quotes
+    uint32_t c1;   // ... if it starts inside quotes
+};
+TPLX_HD CsvState csv_compose(const CsvState &a, const CsvState &b) {
+    CsvState r;
+    r.par = a.par ^ b.par;
+    r.c0 = a.c0 + (a.par ? b.c1 : b.c0);
+    r.c1 = a.c1 + (a.par ? b.c0 : b.c1);
+    return r;
+}
+
+// A newline ends a row iff it lies outside quotes and the byte before it is not a newline (blank lines and the '\n'
+// of "\r\n" are skipped at row start, csvmonkey.h:551-561). The buffer is zero padded to a span multiple, so spans
+// need no bounds checks (NUL is neither quote nor newline). emit(pos) is called for every row end when the span's
+// start parity is par0 (pass a value > 1 to only count).
+template <class Emit>
+TPLX_HD CsvState csv_walk_span(const uint8_t *buf, uint64_t start, uint8_t quote, uint32_t par0, Emit &&emit) {
+    CsvState s{0, 0, 0};
+    bool prev_nl = start == 0 ? true : csv_is_nl(buf[start - 1]);
+    for (uint32_t k = 0; k < CSV_SPAN / 16; ++k) {
+        uint32_t w[4];
+#ifdef __CUDA_ARCH__
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(buf + start) + k);
+        w[0] = v.x, w[1] = v.y, w[2] = v.z, w[3] = v.w;
+#else
+        for (int j = 0; j < 4; ++j) {
+            const uint8_t *q = buf + start + k * 16 + j * 4;
+            w[j] = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
+        }
+#endif
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+        for (uint32_t i = 0; i < 16; ++i) {
+            const uint8_t c = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
+            if (c == quote) {
+                s.par ^= 1;
+                prev_nl = false;
+            } else if (csv_is_nl(c)) {
+                if (!prev_nl) {
+                    if (s.par)
+                        ++s.c1;
+                    else
+                        ++s.c0;
+                    if ((s.par ^ par0) == 0) emit(start + k * 16 + i);
+                }
+                prev_nl = true;
+            } else
+                prev_nl = false;
+        }
+    }
+    return s;
+}
+
+// ---- one row: machine + decode + verification of the predicted row end --------------------------------
+struct CsvParseParams {
+    const uint8_t *buf;
+    uint32_t n;  // data bytes; buf[n] == '\n'
+    const uint32_t *row_end;
+    uint32_t r0;  // first data row (1 when a header row is skipped)
+    uint32_t nd;  // data rows
+    uint8_t delim, quote;
+    uint32_t n_file_cols;
+    const uint8_t *col_kind;  // [n_file_cols] tplx_type or CSV_SKIP
+    const uint8_t *col_slot;  // [n_file_cols] output column
+    CsvNulls nulls;
+    uint32_t n_out, n_str;
+    uint8_t out_types[TPLX_MAX_COLS];
+    int8_t strk[TPLX_MAX_COLS];
+    uint64_t *tmp[TPLX_MAX_COLS];  // [nd] numeric: value bits; string: start | raw_len << 32 | escaped << 63
+    uint64_t *lens;                // [n_str][nd + 1] dequoted lengths (scanned in place)
+    uint64_t *good;                // [nd + 1] 1 = normal-case row (scanned in place)
+    uint32_t *code;                // [nd] exception code, 0 = good
+    uint32_t *flags;               // [0] != 0: a row did not end where quote parity predicted
+};
+
+TPLX_HD uint32_t csv_row_start(const uint8_t *buf, const uint32_t *row_end, uint32_t r) {
+    uint32_t p = r == 0 ? 0u : row_end[r - 1] + 1;
+    while (csv_is_nl(buf[p])) ++p;  // stops: row r has at least one non-newline byte before row_end[r]
+    return p;
+}
+
+TPLX_HD void csv_parse_one_row(const CsvParseParams &P, uint32_t i) {
+    const uint32_t r = P.r0 + i;
+    const uint32_t start = csv_row_start(P.buf, P.row_end, r), end = P.row_end[r];
+    uint32_t code = 0, ncells = 0;
+    const uint32_t got = csv_row_machine(P.buf, start, P.n, P.delim, P.quote, &ncells, [&](uint32_t c, uint32_t b, uint32_t e, bool esc) {
+        if (c >= P.n_file_cols || code) return;
+        const uint32_t kind = P.col_kind[c];
+        if (kind == CSV_SKIP) return;
+        const uint32_t slot = P.col_slot[c];
+        if (csv_cell_is_null(P.buf, b, e, esc, P.quote, P.nulls)) {
+            code = TPLX_EC_NULLERROR;  // null in a non-Option column (FlattenedTuple.cc:1266-1279)
+            return;
+        }
+        if (kind == TPLX_T_STR) {
+            P.tmp[slot][i] = (uint64_t)b | ((uint64_t)(e - b) << 32) | ((uint64_t)esc << 63);
+            P.lens[(size_t)P.strk[slot] * (P.nd + 1) + i] = esc ? csv_dequoted_len(P.buf, b, e, P.quote) : (e - b);
+        } else {
+            uint64_t bits = 0;
+            if (!csv_decode_scalar(P.buf, b, e, esc, P.quote, (uint8_t)kind, &bits)) code = TPLX_EC_BADPARSE_STRING_INPUT;
+            P.tmp[slot][i] = bits;
+        }
+    });
+    if (got != end) {
+        P.flags[0] = 1;  // speculation failed: the host switches to the sequential row finder
+        code = TPLX_EC_BADPARSE_STRING_INPUT;
+    }
+    if (ncells != P.n_file_cols) code = TPLX_EC_BADPARSE_STRING_INPUT;  // checked before any cell is decoded (CSVReader.cc:470-479)
+    if (code)
+        for (uint32_t k = 0; k < P.n_str; ++k) P.lens[(size_t)k * (P.nd + 1) + i] = 0;
+    P.code[i] = code;
+    P.good[i] = code ? 0 : 1;
+}
+
+// exact, sequential row finding (repair path for irregular quoting); returns the number of rows
+TPLX_HD uint32_t csv_find_rows_sequential(const uint8_t *buf, uint32_t n, uint8_t delim, uint8_t quote, uint32_t *row_end) {
+    uint32_t p = 0, rows = 0;
+    for (;;) {
+        while (p <= n && csv_is_nl(buf[p])) ++p;
+        if (p > n) break;
+        uint32_t nc;
+        const uint32_t e = csv_row_machine(buf, p, n, delim, quote, &nc, [](uint32_t, uint32_t, uint32_t, bool) {});
+        if (e == CSV_UNDERRUN) break;
+        row_end[rows++] = e;
+        p = e + 1;
+    }
+    return rows;
+}
+
+}  // namespace tplx

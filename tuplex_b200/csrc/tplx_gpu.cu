@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -23,6 +24,7 @@
 #include "hashagg.cuh"
 #include "fused.cuh"
 #include "gather.cuh"
+#include "csv.cuh"
 
 using namespace tplx;
 
@@ -1277,3 +1279,4 @@ extern "C" int32_t tplx_gpu_result_fetch_aggregate(tplx_result *r, int64_t *acc_
 
 #include "tplx_gpu_rowfmt.inl"
 #include "tplx_gpu_hash.inl"
+#include "tplx_gpu_csv.inl"

@@ -140,3 +140,55 @@ def f64_bits(x: float) -> int:
 
 def bits_f64(b: int) -> float:
     return struct.unpack("<d", struct.pack("<Q", b & ((1 << 64) - 1)))[0]
+
+
+def referenced_inputs(prog: Program) -> List[int]:
+    """Input columns a stage actually loads (projection pushdown: the reference keeps only these when it reads a
+    file, LogicalOptimizer projection pushdown / `columnsToSerialize`, StageBuilder.cc:1045-1070)."""
+    used = set()
+    p = prog
+    while p is not None:
+        used.update(int(i.imm) for i in p.instrs if i.op == C["TPLX_OP_LDCOL"])
+        p = p.prefilter
+    if prog.fused:
+        _, n_preds, n_terms, _ = struct.unpack_from("<IIII", prog.fused, 0)
+        off = 16
+        for _ in range(n_preds):
+            used.add(struct.unpack_from("<I", prog.fused, off)[0])
+            off += 24
+        for _ in range(n_terms):
+            _, op, ca, cb = struct.unpack_from("<IIII", prog.fused, off)
+            if op in (C["TPLX_FT_COL"], C["TPLX_FT_MUL"]):
+                used.add(ca)
+            if op == C["TPLX_FT_MUL"]:
+                used.add(cb)
+            off += 32
+    return sorted(used)
+
+
+def project_inputs(prog: Program, used: List[int]) -> None:
+    """Renumber the input columns of `prog` (in place) so that it reads a block holding only `used`."""
+    remap = {c: k for k, c in enumerate(used)}
+    p = prog
+    while p is not None:
+        for i in p.instrs:
+            if i.op == C["TPLX_OP_LDCOL"]:
+                i.imm = remap[int(i.imm)]
+        p.in_types = [p.in_types[c] for c in used]
+        p.in_names = [p.in_names[c] for c in used] if p.in_names else p.in_names
+        p = p.prefilter
+    if prog.fused:
+        b = bytearray(prog.fused)
+        _, n_preds, n_terms, _ = struct.unpack_from("<IIII", b, 0)
+        off = 16
+        for _ in range(n_preds):
+            struct.pack_into("<I", b, off, remap[struct.unpack_from("<I", b, off)[0]])
+            off += 24
+        for _ in range(n_terms):
+            _, op, ca, cb = struct.unpack_from("<IIII", b, off)
+            if op in (C["TPLX_FT_COL"], C["TPLX_FT_MUL"]):
+                struct.pack_into("<I", b, off + 8, remap[ca])
+            if op == C["TPLX_FT_MUL"]:
+                struct.pack_into("<I", b, off + 12, remap[cb])
+            off += 32
+        prog.fused = bytes(b)
