@@ -105,6 +105,8 @@ int32_t tplx_gpu_block_from_partitions(int32_t device, const uint8_t *const *par
                                        const uint64_t *partition_bytes, uint32_t n_partitions,
                                        const uint8_t *col_types, uint32_t n_cols, tplx_block **out);
 int32_t tplx_gpu_block_rows(const tplx_block *block, uint64_t *n_rows);
+/* Device bytes of every column (values, or string payload + offsets): what a kernel reading the block moves. */
+int32_t tplx_gpu_block_column_bytes(const tplx_block *block, uint64_t *bytes, uint32_t max_cols, uint32_t *n_cols);
 int32_t tplx_gpu_block_free(tplx_block *block);
 
 /* ---- execution -------------------------------------------------------------------------- */
@@ -203,6 +205,10 @@ int32_t tplx_gpu_csv_parse(tplx_csv_buffer *buf, const tplx_csv_desc *desc, tplx
 int32_t tplx_gpu_csv_result_info(tplx_csv_result *res, tplx_csv_info *info);
 int32_t tplx_gpu_csv_result_fetch_bad_rows(tplx_csv_result *res, tplx_csv_bad_row *rows /* n_bad, ascending row */);
 int32_t tplx_gpu_csv_result_fetch_rowmap(tplx_csv_result *res, uint32_t *rowmap /* n_normal: block row -> data row */);
+/* ends[0 .. n_rows]: ends[i + 1] = byte position of the newline that ends data row i; ends[i] + 1 = first byte that can
+ * belong to data row i (leading newlines are skipped); ends[0] = 0xFFFFFFFF when no row precedes data row 0. Lets the host
+ * cut the text of any row (interpreter path for rows whose UDF raised). */
+int32_t tplx_gpu_csv_result_fetch_row_ends(tplx_csv_result *res, uint32_t *ends /* n_rows + 1 */);
 int32_t tplx_gpu_csv_result_free(tplx_csv_result *res);
 
 #ifdef __cplusplus

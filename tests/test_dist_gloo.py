@@ -41,12 +41,15 @@ print("rank", rank, "ok")
 def test_gloo_world_size_2(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
-    with socket.socket() as s:
-        s.bind(("127.0.0.1", 0))
-        port = s.getsockname()[1]
     env = dict(os.environ, TPLX_ROOT=ROOT, CUDA_VISIBLE_DEVICES="")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", str(port), str(script)]
-    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    for attempt in range(2):  # the free port found below can be taken by another process before torchrun binds it
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0))
+            port = s.getsockname()[1]
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+               "--master-port", str(port), str(script)]
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+        if r.returncode == 0 or "address already in use" not in (r.stdout + r.stderr).lower():
+            break
     assert r.returncode == 0, r.stdout + r.stderr
     assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout

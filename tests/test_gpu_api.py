@@ -197,3 +197,62 @@ def test_csv_source_to_csv_sink_zillow(ctx, tmp_path):
     workloads.zillow_pipeline(ds).tocsv(str(out_dir))
     produced = (out_dir / "part0.csv").read_bytes()
     assert hashlib.md5(produced).hexdigest() == "4d5ca0263b1a5058341a369116dee83a"
+
+
+def test_csv_full_fixture_projection_pushdown(ctx, tmp_path):
+    """The reference's own fixture file (10 columns, quoted cells with commas, header): parsed on the device with
+    projection pushdown of the 8 referenced columns, Z1 pipeline, byte-identical output."""
+    import gzip
+    import hashlib
+    import os
+    src = tmp_path / "zillow_full.csv"
+    with gzip.open(os.path.join(workloads.GOLDEN, "zillow_noexc.csv.gz"), "rb") as fp:
+        src.write_bytes(fp.read())
+    ds = ctx.csv(str(src))
+    assert ds.columns[:7] == workloads.ZILLOW_COLS[:7] and len(ds.columns) == 10
+    before = ctx.metrics.csv_rows
+    out_dir = tmp_path / "out"
+    workloads.zillow_pipeline(ds).tocsv(str(out_dir))
+    assert hashlib.md5((out_dir / "part0.csv").read_bytes()).hexdigest() == "4d5ca0263b1a5058341a369116dee83a"
+    assert ctx.metrics.csv_rows - before == 32661 and ctx.metrics.csv_bad_rows == 0  # parsed by the GPU source
+
+
+def test_csv_dirty_rows_take_the_interpreter_path_in_order(ctx, tmp_path):
+    src = tmp_path / "dirty.csv"
+    lines = ["a,b"]
+    expect = []
+    for i in range(3000):
+        if i % 97 == 5:
+            lines.append(f"7.0,\"v,{i}\"")           # not an integer -> interpreter path, parse() gives 7.0
+            expect.append((1000 // 7.0 * 2, f"v,{i}"))
+        elif i % 101 == 7:
+            lines.append(f",w{i}")                     # null in a non-Option column -> None: the UDF raises TypeError -> dropped
+        elif i % 113 == 9:
+            lines.append(f"n/a,w{i}")                  # str on the interpreter path: 1000 // 'n/a' raises -> dropped
+        elif i % 50 == 0:
+            lines.append(f"0,z{i}")                    # ZeroDivisionError on the device -> resolved by resolve()
+            expect.append((-1, f"z{i}"))
+        else:
+            lines.append(f"{i},\"s{i}\"")
+            expect.append((1000 // i * 2, f"s{i}"))
+    src.write_text("\n".join(lines) + "\n")
+    ds = ctx.csv(str(src))
+    bad0 = ctx.metrics.csv_bad_rows
+    got = ds.map(lambda x: (1000 // x['a'] * 2, x['b'])).resolve(ZeroDivisionError, lambda x: (-1, x['b'])).collect()
+    assert got == expect
+    assert ctx.metrics.csv_bad_rows - bad0 == sum(1 for i in range(3000) if i % 97 == 5 or i % 101 == 7 or i % 113 == 9)
+    assert ds.map(lambda x: (1000 // x['a'] * 2, x['b'])).exception_counts is not None
+
+
+def test_csv_aggregate_q6_from_text(ctx, tmp_path):
+    """Q6 over a CSV rendering of the lineitem fixture: device parse (fast_atod semantics) + fused scan-aggregate."""
+    cols = workloads.load_lineitem_fixture()
+    n = len(cols[0].data)
+    src = tmp_path / "lineitem.csv"
+    with open(src, "w") as fp:
+        fp.write(",".join(workloads.Q6_COLS) + ",l_comment\n")
+        for i in range(n):
+            fp.write(f"{int(cols[0].data[i])},{cols[1].data[i]:.2f},{cols[2].data[i]:.2f},{int(cols[3].data[i])},\"c, {i}\"\n")
+    ds = ctx.csv(str(src))
+    got = workloads.q6_pipeline(ds).collect()[0]
+    assert abs(got - 1193053.2252999984) <= 1e-4  # tuplex/test/core/TPCH.cc:85-97

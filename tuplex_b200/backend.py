@@ -80,6 +80,7 @@ def lib():
         "tplx_gpu_block_wrap_device": ([i32, P(CColumn), u32, u64, P(vp)], i32),
         "tplx_gpu_block_from_partitions": ([i32, P(vp), P(u64), u32, P(ct.c_uint8), u32, P(vp)], i32),
         "tplx_gpu_block_rows": ([vp, P(u64)], i32),
+        "tplx_gpu_block_column_bytes": ([vp, P(u64), u32, P(u32)], i32),
         "tplx_gpu_block_free": ([vp], i32),
         "tplx_gpu_stage_run": ([vp, vp, i64, P(vp)], i32),
         "tplx_gpu_stage_run_host": ([vp, i32, P(CColumn), u32, u64, i64, P(vp)], i32),
@@ -102,6 +103,7 @@ def lib():
         "tplx_gpu_csv_result_info": ([vp, P(CCsvInfo)], i32),
         "tplx_gpu_csv_result_fetch_bad_rows": ([vp, vp], i32),
         "tplx_gpu_csv_result_fetch_rowmap": ([vp, vp], i32),
+        "tplx_gpu_csv_result_fetch_row_ends": ([vp, vp], i32),
         "tplx_gpu_csv_result_free": ([vp], i32),
     }
     for name, (argtypes, restype) in sig.items():
@@ -474,6 +476,19 @@ class CsvParse:
     def rowmap(self) -> np.ndarray:
         out = np.zeros(int(self.info.n_normal), dtype=np.uint32)
         _check(lib().tplx_gpu_csv_result_fetch_rowmap(self._h, out.ctypes.data if len(out) else None), "tplx_gpu_csv_result_fetch_rowmap")
+        return out
+
+    def block_bytes(self) -> List[int]:
+        """bytes of every column of the parsed block (values, or string payload + offsets)"""
+        arr = (ct.c_uint64 * 64)()
+        n = ct.c_uint32()
+        _check(lib().tplx_gpu_block_column_bytes(self.block._h, arr, 64, ct.byref(n)), "tplx_gpu_block_column_bytes")
+        return [int(arr[i]) for i in range(n.value)]
+
+    def row_ends(self) -> np.ndarray:
+        """ends[i] + 1 .. ends[i + 1]: byte window of data row i (leading newlines to be skipped); ends[0] wraps to -1."""
+        out = np.zeros(int(self.info.n_rows) + 1, dtype=np.uint32)
+        _check(lib().tplx_gpu_csv_result_fetch_row_ends(self._h, out.ctypes.data), "tplx_gpu_csv_result_fetch_row_ends")
         return out
 
     def free(self):

@@ -51,6 +51,8 @@ class Metrics:
         self.rows_in = self.rows_out = self.exceptions = 0
         self.kernel_ms = self.total_ms = 0.0
         self.kernel_launches = 0
+        self.csv_rows = self.csv_bad_rows = 0  # rows the device CSV source found / handed to the interpreter path
+        self.csv_parse_ms = 0.0
 
     def _add(self, info):
         self.rows_in += int(info.n_in_rows)
@@ -144,60 +146,33 @@ class Context:
         return Source(cols, names, len(orig), oi, fallback, n)
 
     def csv(self, pattern, columns=None, header=None, delimiter=None, quotechar='"', null_values=[''], type_hints={}) -> DataSet:
+        """tuplex.Context.csv (python/tuplex/context.py:203-290). Planning (delimiter, header, normal-case types) looks at
+        a sample of the first file on the host, like the reference's CSVStatistic; the rows themselves are parsed on
+        the GPU when the first stage runs (csvsource.CsvSource -> tplx_gpu_csv_parse)."""
+        from . import csvsource as cs
         files = sorted(f for p in pattern.split(",") for f in (glob.glob(p) or [p]))
-        rows: List[List[str]] = []
-        names = None
-        for fn in files:
-            with open(fn, newline="") as fp:
-                sample = fp.read(65536)
-                fp.seek(0)
-                delim = delimiter or (_csv.Sniffer().sniff(sample, delimiters=",;|\t").delimiter if sample else ",")
-                rd = _csv.reader(fp, delimiter=delim, quotechar=quotechar)
-                data = list(rd)
-            if not data:
-                continue
-            if delim == "|" and data and data[0] and data[0][-1] == "":
-                data = [r[:-1] if r and r[-1] == "" else r for r in data]  # dbgen trailing delimiter
-            has_header = header if header is not None else (columns is None and not _looks_numeric(data[0]))
-            if has_header:
-                if names is None:
-                    names = data[0]
-                data = data[1:]
-            rows.extend(data)
+        arrays = [np.fromfile(fn, dtype=np.uint8) for fn in files]
+        arrays = [a for a in arrays if a.size] or [np.zeros(0, np.uint8)]
+        sample = arrays[0][: cs.SAMPLE_BYTES].tobytes()
+        if len(sample) == cs.SAMPLE_BYTES:  # keep whole lines only
+            sample = sample[: max(sample.rfind(b"\n"), 0)]
+        text = sample.decode("utf-8", "replace")
+        delim = delimiter or (_csv.Sniffer().sniff(text[:65536], delimiters=",;|\t").delimiter if text.strip() else ",")
+        rows = [[c.decode("utf-8", "replace") for c in cells] for cells, _, _ in cs.iter_rows(sample, ord(delim), ord(quotechar))]
+        has_header = header if header is not None else (columns is None and bool(rows) and not _looks_numeric(rows[0]))
+        names = rows[0] if (has_header and rows) else None
+        data_rows = rows[1:] if has_header else rows
         if columns is not None:
             names = list(columns)
-        ncols = len(names) if names is not None else (len(rows[0]) if rows else 0)
+        ncols = len(names) if names is not None else (len(data_rows[0]) if data_rows else 0)
         names = names if names is not None else [None] * ncols
-        nulls = set(null_values or [])
-        # per-column normal-case type: majority over cells (CSVStatistic), hints win
-        types = []
+        nulls = list(null_values or [])
+        types = cs.infer_types(data_rows[:10000], ncols, set(nulls), float(self._options.get("tuplex.normalcaseThreshold", 0.9)))
         for c in range(ncols):
-            if c in type_hints or (names[c] in type_hints):
-                h = type_hints.get(c, type_hints.get(names[c]))
-                types.append({int: T_I64, float: T_F64, str: T_STR, bool: T_BOOL}[h])
-                continue
-            cnt = Counter(_cell_kind(r[c]) for r in rows[:10000] if len(r) == ncols and r[c] not in nulls)
-            if not cnt:
-                types.append(T_STR)
-            elif cnt.get(T_STR, 0) > 0.1 * sum(cnt.values()):
-                types.append(T_STR)
-            elif cnt.get(T_F64, 0):
-                types.append(T_F64)
-            else:
-                types.append(T_I64)
-        normal: List[list] = [[] for _ in range(ncols)]
-        orig, fallback = [], []
-        for i, r in enumerate(rows):
-            vals = _parse_row(r, types, nulls) if len(r) == ncols else None
-            if vals is None:
-                fallback.append((i, tuple(_parse_cell_general(x, nulls) for x in r) if len(r) != 1 else _parse_cell_general(r[0], nulls)))
-            else:
-                for c, v in enumerate(vals):
-                    normal[c].append(v)
-                orig.append(i)
-        cols = [Column.from_values(normal[c], types[c]) for c in range(ncols)]
-        oi = None if not fallback else np.asarray(orig, dtype=np.int64)
-        return DataSet(self, Source(cols, list(names), len(orig), oi, fallback, len(rows)))
+            h = type_hints.get(c, type_hints.get(names[c])) if (c in type_hints or names[c] in type_hints) else None
+            if h is not None:
+                types[c] = {int: T_I64, float: T_F64, str: T_STR, bool: T_BOOL}[h]
+        return DataSet(self, cs.CsvSource(arrays, list(names), types, delim, quotechar, bool(has_header), nulls))
 
 
 def _looks_numeric(cells) -> bool:

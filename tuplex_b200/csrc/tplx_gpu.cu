@@ -467,6 +467,14 @@ extern "C" int32_t tplx_gpu_block_rows(const tplx_block *b, uint64_t *n_rows) {
     return TPLX_OK;
 }
 
+extern "C" int32_t tplx_gpu_block_column_bytes(const tplx_block *b, uint64_t *bytes, uint32_t max_cols, uint32_t *n_cols) {
+    if (!b || !n_cols || (!bytes && max_cols)) return fail(TPLX_E_BADARG, "block_column_bytes: bad arguments");
+    *n_cols = (uint32_t)b->cols.size();
+    for (uint32_t c = 0; c < b->cols.size() && c < max_cols; ++c)
+        bytes[c] = b->data_bytes[c] + (b->cols[c].type == TPLX_T_STR ? (b->n_rows + 1) * 4 : 0);
+    return TPLX_OK;
+}
+
 extern "C" int32_t tplx_gpu_block_free(tplx_block *b) {
     if (!b) return TPLX_OK;
     cudaSetDevice(b->dev->id);

@@ -13,6 +13,8 @@ struct tplx_csv_result {
     tplx_csv_info info{};
     tplx_csv_bad_row *bad = nullptr;  // device
     uint32_t *rowmap = nullptr;       // device
+    uint32_t *row_end = nullptr;      // device: newline position of every row found (header included)
+    uint32_t n_rows_total = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
@@ -142,13 +144,16 @@ extern "C" int32_t tplx_gpu_csv_parse(tplx_csv_buffer *cb, const tplx_csv_desc *
     for (int attempt = 0; attempt < 2; ++attempt) {
         if (!sequential) {
             n_rows_total = h_tot[1];
-            CU(T.alloc(&row_end, (size_t)n_rows_total + 1));
+            CU(cudaMallocAsync((void **)&row_end, ((size_t)n_rows_total + 1) * 4, st));
+            res->row_end = row_end;
             if (n_rows_total) {
                 csv_row_ends<<<n_tiles, CSV_NT, 0, st>>>(cb->d, desc->quotechar, tile_start, row_end);
                 ++launches;
             }
         } else {
-            CU(T.alloc(&row_end, (size_t)(cb->n / 2) + 2));  // a row has at least one byte and a newline
+            if (res->row_end) CU(cudaFreeAsync(res->row_end, st));
+            CU(cudaMallocAsync((void **)&row_end, ((size_t)(cb->n / 2) + 2) * 4, st));  // a row has at least one byte and a newline
+            res->row_end = row_end;
             csv_rows_sequential<<<1, 32, 0, st>>>(cb->d, (uint32_t)cb->n, desc->delimiter, desc->quotechar, row_end, totals);
             ++launches;
             CU(cudaMemcpyAsync(h_tot, totals, 8, cudaMemcpyDeviceToHost, st));
@@ -260,6 +265,7 @@ extern "C" int32_t tplx_gpu_csv_parse(tplx_csv_buffer *cb, const tplx_csv_desc *
     CU(cudaEventRecord(res->ev1, st));
     CU(cudaEventCreateWithFlags(&b->ready, cudaEventDisableTiming));
     CU(cudaEventRecord(b->ready, st));
+    res->n_rows_total = n_rows_total;
     res->info.n_rows = nd;
     res->info.n_normal = n_good;
     res->info.n_bad = n_bad;
@@ -301,9 +307,26 @@ extern "C" int32_t tplx_gpu_csv_result_fetch_rowmap(tplx_csv_result *r, uint32_t
     return TPLX_OK;
 }
 
+extern "C" int32_t tplx_gpu_csv_result_fetch_row_ends(tplx_csv_result *r, uint32_t *ends) {
+    if (!r || (!ends && r->info.n_rows)) return fail(TPLX_E_BADARG, "csv_result_fetch_row_ends: bad arguments");
+    if (!r->info.n_rows) return TPLX_OK;
+    CU(cudaSetDevice(r->dev->id));
+    CU(cudaEventSynchronize(r->ev1));
+    const uint32_t r0 = r->n_rows_total - (uint32_t)r->info.n_rows;  // 1 when a header row was skipped
+    if (r0) {  // ends[0] = end of the header row, so that ends[i] / ends[i + 1] bracket data row i
+        CU(cudaMemcpyAsync(ends, r->row_end, ((size_t)r->info.n_rows + 1) * 4, cudaMemcpyDeviceToHost, r->dev->d2h_stream));
+    } else {
+        ends[0] = 0xFFFFFFFFu;  // no row before data row 0: it starts at byte 0
+        CU(cudaMemcpyAsync(ends + 1, r->row_end, (size_t)r->info.n_rows * 4, cudaMemcpyDeviceToHost, r->dev->d2h_stream));
+    }
+    CU(cudaStreamSynchronize(r->dev->d2h_stream));
+    return TPLX_OK;
+}
+
 extern "C" int32_t tplx_gpu_csv_result_free(tplx_csv_result *r) {
     if (!r) return TPLX_OK;
     cudaSetDevice(r->dev->id);
+    if (r->row_end) cudaFreeAsync(r->row_end, r->dev->stream);
     if (r->bad) cudaFreeAsync(r->bad, r->dev->stream);
     if (r->rowmap) cudaFreeAsync(r->rowmap, r->dev->stream);
     if (r->ev0) cudaEventDestroy(r->ev0);

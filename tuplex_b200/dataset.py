@@ -182,6 +182,7 @@ def _run_stage(ctx, src: Source, ops: List[Op], exc_counter: Counter):
     end = ops[-1] if ops and ops[-1].kind in ("aggregate", "aggregateByKey", "unique") else None
     row_ops = ops[:-1] if end else ops
     in_types = [c.type for c in src.cols]
+    is_csv = hasattr(src, "chunks")  # csvsource.CsvSource: the device parses the file right in front of the stage
     prog = None
     try:
         sc = StageCompiler(in_types, src.names)
@@ -201,7 +202,7 @@ def _run_stage(ctx, src: Source, ops: List[Op], exc_counter: Counter):
             elif op.kind == "renameColumn":
                 sc.add_rename(op.column, op.extra, op.id)
         out_names = list(sc.names)
-        need_rowidx = end is None and bool(src.fallback)
+        need_rowidx = end is None and (bool(src.fallback) or is_csv)
         if end is None:
             if need_rowidx:
                 sc.begin_op(row_ops[-1].id if row_ops else 0)
@@ -219,19 +220,29 @@ def _run_stage(ctx, src: Source, ops: List[Op], exc_counter: Counter):
             prog = sc.finish_hash(list(range(len(sc.row))), None, None, None, end.id)
     except UnsupportedUDF as e:
         ctx._log(f"stage falls back to the CPython path: {e}")
-        return _run_stage_python(ctx, src, ops, exc_counter)
+        return _run_stage_python(ctx, src.to_host_source() if is_csv else src, ops, exc_counter)
 
+    used_cols = list(range(len(in_types)))
+    if is_csv:  # projection pushdown: the device decodes only the columns the stage loads
+        used_cols = ir.referenced_inputs(prog)
+        ir.project_inputs(prog, used_cols)
     dev = ctx._device
     backend.init([dev])
     stage = backend.Stage(prog)
     block_rows = ctx._block_rows
     in_values: Optional[List[list]] = None  # python values of input columns, built lazily for resolve
 
+    csv_rows: Dict[int, Any] = {}  # CSV input: python value of the rows the interpreter path needs
+
     def input_row(i: int):
         nonlocal in_values
+        if is_csv:
+            return csv_rows[i]
         if in_values is None:
             in_values = [c.to_values() for c in src.cols]
         return _row_of(src.cols, in_values, i)
+
+    fallback = list(src.fallback)
 
     out_cols_all: List[List[Column]] = []
     exc_all: List[np.ndarray] = []
@@ -240,20 +251,61 @@ def _run_stage(ctx, src: Source, ops: List[Op], exc_counter: Counter):
     base = 0
     n = src.n_rows
     starts = list(range(0, n, block_rows)) or [0]
-    for lo in starts:
-        hi = min(n, lo + block_rows)
-        cols = [c.slice(lo, hi) for c in src.cols] if (lo, hi) != (0, n) else src.cols
-        res = stage.run_host(dev, cols, hi - lo, first_row_no)
+
+    def host_blocks():
+        for lo in starts:
+            hi = min(n, lo + block_rows)
+            cols = [c.slice(lo, hi) for c in src.cols] if (lo, hi) != (0, n) else src.cols
+            yield (lambda cols=cols, lo=lo, hi=hi: stage.run_host(dev, cols, hi - lo, first_row_no)), lo, None, None
+
+    def csv_blocks():
+        base = 0
+        col_types = [t if c in used_cols else backend.CSV_SKIP for c, t in enumerate(in_types)]
+        for data, skip_header in src.chunks():
+            buf = backend.CsvBuffer(dev, data)
+            parse = buf.parse(col_types, src.delimiter, src.quotechar, skip_header, src.null_values)
+            yield (lambda parse=parse: stage.run(parse.block, first_row_no)), base, parse, data
+            base += int(parse.info.n_rows)
+            parse.free()
+            buf.free()
+        src.total_rows = base
+
+    for run, lo, parse, data in (csv_blocks() if is_csv else host_blocks()):
+        res = run()
         info = res.info
         ctx.metrics._add(info)
         exc = res.exceptions()
+        rowmap = None
+        if parse is not None:
+            pinfo = parse.info
+            ctx.metrics.csv_rows += int(pinfo.n_rows)
+            ctx.metrics.csv_bad_rows += int(pinfo.n_bad)
+            ctx.metrics.csv_parse_ms += float(pinfo.parse_ms)
+            if pinfo.n_bad:  # block row -> data row
+                rowmap = parse.rowmap().astype(np.int64)
+                raw = data.tobytes()
+                for b in parse.bad_rows():
+                    fallback.append((lo + int(b["row"]), src.line_object(raw[int(b["line_start"]):int(b["line_end"])], False)))
         if len(exc):
             exc = exc.copy()
+            if rowmap is not None:
+                exc["row"] = rowmap[exc["row"]]
+            if parse is not None:  # text of the rows whose UDF raised, decoded as the device decoded them
+                ends = parse.row_ends().astype(np.int64)
+                ends[0] = -1 if ends[0] == 0xFFFFFFFF else ends[0]
+                raw = data.tobytes()
+                for r in exc["row"]:
+                    a = int(ends[r]) + 1
+                    while raw[a] in (10, 13):
+                        a += 1
+                    csv_rows[lo + int(r)] = src.line_object(raw[a:int(ends[r + 1])], True)
             exc["row"] += lo
             exc_all.append(exc)
         if prog.endpoint == C["TPLX_EP_MEMORY"]:
             oc = res.columns()
             if need_rowidx:
+                if rowmap is not None:
+                    oc[-1].data = rowmap[oc[-1].data]
                 oc[-1].data += lo
             out_cols_all.append(oc)
             first_row_no += int(info.n_out_rows) + int(info.n_exceptions)
@@ -280,7 +332,7 @@ def _run_stage(ctx, src: Source, ops: List[Op], exc_counter: Counter):
                 pass
             except Exception as ex:  # noqa: BLE001 — stays an exception, counted like the reference's exception_counts
                 exc_counter[(getattr(ex, "tplx_op", int(e["op_id"])), type(ex).__name__)] += 1
-        if not src.fallback:
+        if not need_rowidx:
             rows = _merge_by_rowno(normal_rows, excs, resolved)
         else:
             # rows outside the normal-case schema run entirely on the CPython path; merge by original position
@@ -288,7 +340,7 @@ def _run_stage(ctx, src: Source, ops: List[Op], exc_counter: Counter):
             orig = src.orig_index
             keyed = [(int(orig[j]) if orig is not None else int(j), r) for j, r in zip(idx_normal, normal_rows)]
             keyed += [(int(orig[i]) if orig is not None else i, v) for i, _, v in resolved]
-            for pos, obj in src.fallback:
+            for pos, obj in fallback:
                 try:
                     val, _ = pyexec.run_row(row_ops, obj, src.names)
                     keyed.append((pos, val))
@@ -314,7 +366,7 @@ def _run_stage(ctx, src: Source, ops: List[Op], exc_counter: Counter):
         # exception rows + fallback rows: fold on the CPython path with the user's own aggregate UDF
         for i in [int(e["row"]) for e in excs]:
             value = _py_fold(row_ops, end, value, input_row(i), src.names, exc_counter)
-        for _, obj in src.fallback:
+        for _, obj in fallback:
             value = _py_fold(row_ops, end, value, obj, src.names, exc_counter)
         stage.close()
         return [value], [None] * (len(value) if isinstance(value, tuple) else 1)
@@ -332,9 +384,9 @@ def _run_stage(ctx, src: Source, ops: List[Op], exc_counter: Counter):
         key = tuple(vals[c][i] for c in range(nk))
         table[key] = [vals[nk + k][i] for k in range(len(prog.accs))]
         order.append(key)
-    if end.kind == "aggregateByKey" and (len(excs) or src.fallback):
+    if end.kind == "aggregateByKey" and (len(excs) or fallback):
         combine, init = end.extra
-        pending = [input_row(int(e["row"])) for e in excs] + [obj for _, obj in src.fallback]
+        pending = [input_row(int(e["row"])) for e in excs] + [obj for _, obj in fallback]
         for obj in pending:
             try:
                 val, names2 = pyexec.run_row(row_ops, obj, src.names)
