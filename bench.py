@@ -553,7 +553,7 @@ def main_csv(args, rank, world, local):
     st = backend.Stage(W.zillow_program())
     bufs = [backend.CsvBuffer(local, host) for _ in range(n_blocks)]  # distinct HBM buffers, each >> L2
     torch.cuda.synchronize()
-    pool = ThreadPoolExecutor(max_workers=2)
+    pool = ThreadPoolExecutor(max_workers=3)
     stats = {}
 
     def sync_all():

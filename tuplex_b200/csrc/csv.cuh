@@ -178,23 +178,44 @@ __global__ void __launch_bounds__(CSV_NT) csv_compact(const CsvCompactParams P) 
             if (P.out_types[c] == TPLX_T_STR) P.offsets[c][pos + 1] = (uint32_t)P.lens[(size_t)P.strk[c] * (P.nd + 1) + P.nd];
 }
 
-// one warp per row: packs the row's string cells; cells with doubled quotes are dequoted by lane 0
+// One warp per 32 consecutive rows. For a string column the packed bytes of those rows are one contiguous destination
+// range; lanes walk it byte by byte (coalesced stores), find the owning row with a shuffle binary search over the rows'
+// output offsets (lane i holds row i's), and read the byte from that row's cell. Cells with doubled quotes (rare) are
+// dequoted by the lane that owns the row.
 __global__ void __launch_bounds__(CSV_NT) csv_copy_strings(const CsvCompactParams P) {
-    const uint32_t i = (blockIdx.x * CSV_NT + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (i >= P.nd || P.code[i]) return;
+    const uint32_t g = (blockIdx.x * CSV_NT + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const uint32_t r_first = g * 32;
+    if (r_first >= P.nd) return;
+    const uint32_t i = min(r_first + lane, P.nd - 1);  // tail lanes shadow the last row and copy nothing
+    const bool mine = r_first + lane < P.nd && P.code[i] == 0;
     for (uint32_t c = 0; c < P.n_out; ++c) {
         if (P.out_types[c] != TPLX_T_STR) continue;
-        const uint64_t info = P.tmp[c][i];
-        const uint32_t b = (uint32_t)info, raw = (uint32_t)(info >> 32) & 0x7FFFFFFFu;
-        uint8_t *dst = P.bytes[c] + P.lens[(size_t)P.strk[c] * (P.nd + 1) + i];
-        const uint8_t *src = P.buf + b;
-        if (!(info >> 63)) {
-            for (uint32_t k = lane; k < raw; k += 32) dst[k] = src[k];
-        } else if (lane == 0) {
-            const uint8_t q = P.quote;
-            uint32_t o = 0;
+        const uint64_t *lens = P.lens + (size_t)P.strk[c] * (P.nd + 1);
+        const uint64_t o_first = lens[r_first];
+        const uint32_t total = (uint32_t)(lens[min(r_first + 32, P.nd)] - o_first);
+        const uint32_t rel = r_first + lane < P.nd ? (uint32_t)(lens[i] - o_first) : total;  // start of this lane's row
+        const uint64_t info = mine ? P.tmp[c][i] : 0;
+        const uint32_t b = (uint32_t)info;
+        const bool esc = (info >> 63) != 0;
+        uint8_t *dst = P.bytes[c] + o_first;
+        const uint32_t esc_mask = __ballot_sync(0xFFFFFFFFu, esc);
+        for (uint32_t j0 = 0; j0 < total; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            uint32_t row = 0;
+#pragma unroll
+            for (uint32_t step = 16; step; step >>= 1) {
+                const uint32_t v = __shfl_sync(0xFFFFFFFFu, rel, row + step);
+                if (v <= j) row += step;
+            }
+            const uint32_t rb = __shfl_sync(0xFFFFFFFFu, b, row), rrel = __shfl_sync(0xFFFFFFFFu, rel, row);
+            if (j < total && !((esc_mask >> row) & 1)) dst[j] = P.buf[rb + (j - rrel)];
+        }
+        if (esc) {
+            const uint32_t raw = (uint32_t)(info >> 32) & 0x7FFFFFFFu;
+            const uint8_t *src = P.buf + b;
+            uint32_t o = rel;
             for (uint32_t k = 0; k < raw; ++k) {
-                if (src[k] == q) {
+                if (src[k] == P.quote) {
                     ++k;
                     if (k >= raw) break;
                 }

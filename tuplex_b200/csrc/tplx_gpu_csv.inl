@@ -257,7 +257,7 @@ extern "C" int32_t tplx_gpu_csv_parse(tplx_csv_buffer *cb, const tplx_csv_desc *
         csv_compact<<<(nd + CSV_NT - 1) / CSV_NT, CSV_NT, 0, st>>>(C);
         ++launches;
         if (P.n_str) {
-            csv_copy_strings<<<(uint32_t)(((uint64_t)nd * 32 + CSV_NT - 1) / CSV_NT), CSV_NT, 0, st>>>(C);
+            csv_copy_strings<<<(nd + CSV_NT - 1) / CSV_NT, CSV_NT, 0, st>>>(C);  // one warp per 32 rows
             ++launches;
         }
         CU(cudaGetLastError());
