@@ -50,3 +50,16 @@ for qq, pp, dd, ss in zip(q, p, d, s):
         acc = acc + pp * dd
 assert repr(acc) == "1193053.2252999984", repr(acc)
 print("golden fixtures written; q6 =", repr(acc), "rows", len(q))
+
+
+def zillow_full_fixture():
+    """tests/golden/zillow_noexc.csv.gz = the reference's fixture file as is (10 columns, header, quoted cells),
+    gzip'ed with mtime 0: input of the CSV-source (K6) parity tests."""
+    import gzip
+    import shutil
+    src = "/root/reference/tuplex/test/resources/pipelines/zillow/zillow_noexc.csv"
+    with open(src, "rb") as f, gzip.GzipFile(os.path.join(os.path.dirname(os.path.abspath(__file__)), "zillow_noexc.csv.gz"), "wb", mtime=0) as g:
+        shutil.copyfileobj(f, g)
+
+
+zillow_full_fixture()
