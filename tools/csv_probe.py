@@ -27,3 +27,17 @@ for it in range(2):
           "out", int(r.info.n_out_rows), "wall_ms", round((time.perf_counter() - t0) * 1e3, 2))
     r.free()
     p.free()
+
+# host -> device bandwidth of the text itself (page-locked source), for the e2e discussion in profiles/
+import torch  # noqa: E402
+t = torch.empty(text.size, dtype=torch.uint8, pin_memory=True)
+t.numpy()[...] = text
+torch.cuda.synchronize()
+for rep in range(2):
+    t0 = time.perf_counter()
+    bs = [backend.CsvBuffer(0, t.numpy()) for _ in range(3)]
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    print("upload x3: %.1f ms, %.1f GB/s" % (dt * 1e3, 3 * text.size / dt / 1e9))
+    for b in bs:
+        b.free()

@@ -63,9 +63,12 @@ __device__ __forceinline__ CsvState csv_block_scan(const CsvState &mine, CsvStat
     return csv_compose(pre, ex);
 }
 
-__global__ void __launch_bounds__(CSV_NT) csv_tile_states(const uint8_t *__restrict__ buf, uint8_t quote, CsvState *__restrict__ tiles) {
+// span state packed for step 3: parity | c0 << 8 | c1 << 16 (counts <= 64)
+__global__ void __launch_bounds__(CSV_NT) csv_tile_states(const uint8_t *__restrict__ buf, uint8_t quote, CsvState *__restrict__ tiles,
+                                                          uint32_t *__restrict__ span_state) {
     const uint64_t start = (uint64_t)blockIdx.x * CSV_TILE + (uint64_t)threadIdx.x * CSV_SPAN;
     CsvState s = csv_walk_span(buf, start, quote, 1u << 31, [](uint64_t) {});
+    span_state[(size_t)blockIdx.x * CSV_NT + threadIdx.x] = s.par | (s.c0 << 8) | (s.c1 << 16);
     CsvState tot;
     csv_block_scan(s, &tot);
     if (threadIdx.x == 0) tiles[blockIdx.x] = tot;
@@ -107,9 +110,10 @@ __global__ void __launch_bounds__(1024) csv_scan_tiles(const CsvState *__restric
 }
 
 __global__ void __launch_bounds__(CSV_NT) csv_row_ends(const uint8_t *__restrict__ buf, uint8_t quote, const uint2 *__restrict__ tile_start,
-                                                       uint32_t *__restrict__ row_end) {
+                                                       const uint32_t *__restrict__ span_state, uint32_t *__restrict__ row_end) {
     const uint64_t start = (uint64_t)blockIdx.x * CSV_TILE + (uint64_t)threadIdx.x * CSV_SPAN;
-    CsvState s = csv_walk_span(buf, start, quote, 1u << 31, [](uint64_t) {});
+    const uint32_t packed = span_state[(size_t)blockIdx.x * CSV_NT + threadIdx.x];  // step 1's walk, not repeated
+    CsvState s{packed & 1u, (packed >> 8) & 0xFFu, (packed >> 16) & 0xFFu};
     const CsvState pre = csv_block_scan(s, nullptr);
     const uint2 ts = tile_start[blockIdx.x];
     const uint32_t par0 = ts.x ^ pre.par;
@@ -178,48 +182,41 @@ __global__ void __launch_bounds__(CSV_NT) csv_compact(const CsvCompactParams P) 
             if (P.out_types[c] == TPLX_T_STR) P.offsets[c][pos + 1] = (uint32_t)P.lens[(size_t)P.strk[c] * (P.nd + 1) + P.nd];
 }
 
-// One warp per 32 consecutive rows. For a string column the packed bytes of those rows are one contiguous destination
-// range; lanes walk it byte by byte (coalesced stores), find the owning row with a shuffle binary search over the rows'
-// output offsets (lane i holds row i's), and read the byte from that row's cell. Cells with doubled quotes (rare) are
-// dequoted by the lane that owns the row.
+// One warp per 32 consecutive rows; lane i first loads row i's cell info and output offset (coalesced), then the warp
+// copies four cells at a time: 8 lanes per cell, consecutive lanes on consecutive bytes (rows are consecutive in the
+// destination, so the four groups write one contiguous region). Cells with doubled quotes (rare) are dequoted by the
+// first lane of their group.
 __global__ void __launch_bounds__(CSV_NT) csv_copy_strings(const CsvCompactParams P) {
     const uint32_t g = (blockIdx.x * CSV_NT + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const uint32_t r_first = g * 32;
     if (r_first >= P.nd) return;
-    const uint32_t i = min(r_first + lane, P.nd - 1);  // tail lanes shadow the last row and copy nothing
-    const bool mine = r_first + lane < P.nd && P.code[i] == 0;
+    const uint32_t i = r_first + lane;
+    const bool mine = i < P.nd && P.code[i] == 0;
+    const uint32_t sub = lane >> 3, k0 = lane & 7;
     for (uint32_t c = 0; c < P.n_out; ++c) {
         if (P.out_types[c] != TPLX_T_STR) continue;
-        const uint64_t *lens = P.lens + (size_t)P.strk[c] * (P.nd + 1);
-        const uint64_t o_first = lens[r_first];
-        const uint32_t total = (uint32_t)(lens[min(r_first + 32, P.nd)] - o_first);
-        const uint32_t rel = r_first + lane < P.nd ? (uint32_t)(lens[i] - o_first) : total;  // start of this lane's row
-        const uint64_t info = mine ? P.tmp[c][i] : 0;
-        const uint32_t b = (uint32_t)info;
-        const bool esc = (info >> 63) != 0;
-        uint8_t *dst = P.bytes[c] + o_first;
-        const uint32_t esc_mask = __ballot_sync(0xFFFFFFFFu, esc);
-        for (uint32_t j0 = 0; j0 < total; j0 += 32) {
-            const uint32_t j = j0 + lane;
-            uint32_t row = 0;
-#pragma unroll
-            for (uint32_t step = 16; step; step >>= 1) {
-                const uint32_t v = __shfl_sync(0xFFFFFFFFu, rel, row + step);
-                if (v <= j) row += step;
-            }
-            const uint32_t rb = __shfl_sync(0xFFFFFFFFu, b, row), rrel = __shfl_sync(0xFFFFFFFFu, rel, row);
-            if (j < total && !((esc_mask >> row) & 1)) dst[j] = P.buf[rb + (j - rrel)];
-        }
-        if (esc) {
-            const uint32_t raw = (uint32_t)(info >> 32) & 0x7FFFFFFFu;
-            const uint8_t *src = P.buf + b;
-            uint32_t o = rel;
-            for (uint32_t k = 0; k < raw; ++k) {
-                if (src[k] == P.quote) {
-                    ++k;
-                    if (k >= raw) break;
+        const uint64_t info = mine ? P.tmp[c][i] : 0;  // raw length 0 for rows that are not copied
+        const uint64_t off = mine ? P.lens[(size_t)P.strk[c] * (P.nd + 1) + i] : 0;
+        uint8_t *const base = P.bytes[c];
+#pragma unroll 1
+        for (uint32_t step = 0; step < 8; ++step) {
+            const uint32_t src_lane = step * 4 + sub;
+            const uint64_t ci = __shfl_sync(0xFFFFFFFFu, info, src_lane);
+            const uint64_t co = __shfl_sync(0xFFFFFFFFu, off, src_lane);
+            const uint32_t raw = (uint32_t)(ci >> 32) & 0x7FFFFFFFu;
+            const uint8_t *src = P.buf + (uint32_t)ci;
+            uint8_t *dst = base + co;
+            if (!(ci >> 63)) {
+                for (uint32_t k = k0; k < raw; k += 8) dst[k] = src[k];
+            } else if (k0 == 0) {
+                uint32_t o = 0;
+                for (uint32_t k = 0; k < raw; ++k) {
+                    if (src[k] == P.quote) {
+                        ++k;
+                        if (k >= raw) break;
+                    }
+                    dst[o++] = src[k];
                 }
-                dst[o++] = src[k];
             }
         }
     }

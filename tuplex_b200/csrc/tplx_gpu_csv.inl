@@ -116,7 +116,8 @@ extern "C" int32_t tplx_gpu_csv_parse(tplx_csv_buffer *cb, const tplx_csv_desc *
     const uint32_t n_tiles = (uint32_t)(cb->padded / CSV_TILE);
     CsvState *tiles = nullptr;
     uint2 *tile_start = nullptr;
-    uint32_t *totals = nullptr, *row_end = nullptr, *flags = nullptr;
+    uint32_t *totals = nullptr, *row_end = nullptr, *flags = nullptr, *span_state = nullptr;
+    CU(T.alloc(&span_state, (size_t)n_tiles * CSV_NT));
     CU(T.alloc(&tiles, n_tiles));
     CU(T.alloc(&tile_start, n_tiles));
     CU(T.alloc(&totals, 2));
@@ -124,7 +125,7 @@ extern "C" int32_t tplx_gpu_csv_parse(tplx_csv_buffer *cb, const tplx_csv_desc *
     CU(cudaMemsetAsync(flags, 0, 16, st));
 
     // ---- rows by quote parity ---------------------------------------------------------------------
-    csv_tile_states<<<n_tiles, CSV_NT, 0, st>>>(cb->d, desc->quotechar, tiles);
+    csv_tile_states<<<n_tiles, CSV_NT, 0, st>>>(cb->d, desc->quotechar, tiles, span_state);
     csv_scan_tiles<<<1, 1024, 0, st>>>(tiles, n_tiles, tile_start, totals);
     launches += 2;
     CU(cudaGetLastError());
@@ -147,7 +148,7 @@ extern "C" int32_t tplx_gpu_csv_parse(tplx_csv_buffer *cb, const tplx_csv_desc *
             CU(cudaMallocAsync((void **)&row_end, ((size_t)n_rows_total + 1) * 4, st));
             res->row_end = row_end;
             if (n_rows_total) {
-                csv_row_ends<<<n_tiles, CSV_NT, 0, st>>>(cb->d, desc->quotechar, tile_start, row_end);
+                csv_row_ends<<<n_tiles, CSV_NT, 0, st>>>(cb->d, desc->quotechar, tile_start, span_state, row_end);
                 ++launches;
             }
         } else {
