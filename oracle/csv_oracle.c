@@ -416,3 +416,59 @@ void csv_oracle_free(csv_result *r) {
     free(r->dump);
     free(r);
 }
+
+/* ---- CSV sink oracle: fast_csvwriter (core/src/physical/PipelineBuilder.cc:1550-1722) + quoteForCSV
+ * (runtime/src/Runtime.cc:682-738), one row at a time with snprintf. Known answers: test/runtime/RuntimeTest.cc:207-213. */
+#include <stdio.h>
+typedef struct {
+    uint8_t type;
+    uint8_t pad[7];
+    const void *data;
+    const uint32_t *offsets;
+    uint64_t data_bytes;
+} sink_col;
+
+/* returns bytes written; out may be NULL to size */
+uint64_t csv_oracle_write(const sink_col *cols, uint32_t n_cols, uint64_t n_rows, char delim, char quote, uint8_t *out) {
+    uint64_t pos = 0;
+    char tmp[32];
+    for (uint64_t r = 0; r < n_rows; ++r) {
+        for (uint32_t c = 0; c < n_cols; ++c) {
+            if (cols[c].type == T_STR) {
+                const char *s = (const char *)cols[c].data + cols[c].offsets[r];
+                uint32_t len = cols[c].offsets[r + 1] - cols[c].offsets[r];
+                size_t num_quotes = 0;
+                int need_to_quote = 0;
+                for (uint32_t i = 0; i < len; ++i) {
+                    if (s[i] == quote) num_quotes++;
+                    if (s[i] == delim || s[i] == '\n' || s[i] == '\r') need_to_quote = 1;
+                }
+                if (num_quotes > 0 || need_to_quote) {
+                    if (out) out[pos] = (uint8_t)quote;
+                    pos++;
+                    for (uint32_t i = 0; i < len; ++i) {
+                        if (s[i] == quote) {
+                            if (out) out[pos] = (uint8_t)quote;
+                            pos++;
+                        }
+                        if (out) out[pos] = (uint8_t)s[i];
+                        pos++;
+                    }
+                    if (out) out[pos] = (uint8_t)quote;
+                    pos++;
+                } else {
+                    if (out) memcpy(out + pos, s, len);
+                    pos += len;
+                }
+            } else {
+                int64_t v = ((const int64_t *)cols[c].data)[r];
+                int k = cols[c].type == T_BOOL ? snprintf(tmp, sizeof tmp, "%s", v ? "true" : "false") : snprintf(tmp, sizeof tmp, "%lld", (long long)v);
+                if (out) memcpy(out + pos, tmp, (size_t)k);
+                pos += (uint64_t)k;
+            }
+            if (out) out[pos] = (uint8_t)(c + 1 == n_cols ? '\n' : delim);
+            pos++;
+        }
+    }
+    return pos;
+}

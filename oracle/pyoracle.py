@@ -297,3 +297,15 @@ def csv_scalar(kind: str, s: str):
         return None if L.csv_oracle_atod(s.encode("latin1"), ct.byref(d)) else d.value
     b = ct.c_int()
     return None if L.csv_oracle_atob(s.encode("latin1"), ct.byref(b)) else bool(b.value)
+
+
+def csv_write(cols, n_rows: int, delimiter=",", quotechar='"') -> bytes:
+    """CSV sink oracle (fast_csvwriter + quoteForCSV): cols = backend.Column-like objects of type i64 / bool / str."""
+    L = lib()
+    arr, keep = _ocols(cols)
+    L.csv_oracle_write.restype = ct.c_uint64
+    L.csv_oracle_write.argtypes = [ct.c_void_p, ct.c_uint32, ct.c_uint64, ct.c_char, ct.c_char, ct.c_void_p]
+    need = L.csv_oracle_write(arr, len(cols), n_rows, delimiter.encode(), quotechar.encode(), None)
+    buf = np.empty(need, dtype=np.uint8)
+    L.csv_oracle_write(arr, len(cols), n_rows, delimiter.encode(), quotechar.encode(), buf.ctypes.data if need else None)
+    return buf.tobytes()

@@ -79,6 +79,9 @@ def host_shim(tmpdir=None):
             getattr(L, f).argtypes = [ct.c_void_p] + ([ct.c_uint32] if f in ("hcsv_type", "hcsv_fixed", "hcsv_offsets") else []) + \
                                      ([ct.POINTER(ct.c_uint32)] if f == "hcsv_counts" else [])
         L.hcsv_bytes.argtypes = [ct.c_void_p, ct.c_uint32, ct.POINTER(ct.c_uint64)]
+        L.hcsv_write.restype = ct.c_ulonglong
+        L.hcsv_write.argtypes = [ct.c_uint, ct.c_char_p, ct.POINTER(ct.c_void_p), ct.POINTER(ct.c_void_p), ct.POINTER(ct.c_void_p),
+                                 ct.c_ulonglong, ct.c_uint8, ct.c_uint8, ct.c_void_p]
         L.hcsv_atod.argtypes = [ct.c_char_p, ct.c_uint32, ct.POINTER(ct.c_double)]
         L.hcsv_atob.argtypes = [ct.c_char_p, ct.c_uint32, ct.POINTER(ct.c_longlong)]
         _SO = L
@@ -129,3 +132,28 @@ def assert_same_parse(a, b, what=""):
             assert np.array_equal(x[1], y[1]), (what, "offsets of column", c)
         else:
             assert np.array_equal(np.asarray(x).view(np.int64), np.asarray(y).view(np.int64)), (what, "values of column", c)
+
+
+def host_csv_write(cols, n_rows: int, delimiter=",", quotechar='"') -> bytes:
+    """The device row writer (csvops.cuh csv_sink_*) run on the host over Column-like objects."""
+    L = host_shim()
+    n = len(cols)
+    keep = []
+    data = (ct.c_void_p * n)()
+    offs = (ct.c_void_p * n)()
+    byts = (ct.c_void_p * n)()
+    for i, c in enumerate(cols):
+        d = np.ascontiguousarray(c.data)
+        keep.append(d)
+        if c.type == T_STR:
+            o = np.ascontiguousarray(c.offsets, dtype=np.uint32)
+            keep.append(o)
+            offs[i] = o.ctypes.data
+            byts[i] = d.ctypes.data
+        else:
+            data[i] = d.ctypes.data
+    types = bytes(c.type for c in cols)
+    need = L.hcsv_write(n, types, data, offs, byts, n_rows, ord(delimiter), ord(quotechar), None)
+    buf = np.empty(need + 1, dtype=np.uint8)
+    L.hcsv_write(n, types, data, offs, byts, n_rows, ord(delimiter), ord(quotechar), buf.ctypes.data)
+    return buf[:need].tobytes()

@@ -141,6 +141,27 @@ const uint8_t *hcsv_bytes(HostCsv *H, uint32_t c, uint64_t *n) { *n = H->bytes[c
 const uint32_t *hcsv_rowmap(HostCsv *H) { return H->rowmap.data(); }
 const uint32_t *hcsv_bad(HostCsv *H) { return H->bad.data(); }
 void hcsv_free(HostCsv *H) { delete H; }
+// CSV sink (K7): the device row writer over host column arrays
+unsigned long long hcsv_write(unsigned n_cols, const uint8_t *types, const uint64_t *const *data, const uint32_t *const *offsets,
+                              const uint8_t *const *bytes, unsigned long long n_rows, uint8_t delim, uint8_t quote, uint8_t *out) {
+    CsvSinkCols C{};
+    C.n_cols = n_cols;
+    C.delim = delim;
+    C.quote = quote;
+    for (unsigned c = 0; c < n_cols; ++c) {
+        C.types[c] = types[c];
+        C.data[c] = data[c];
+        C.offsets[c] = offsets[c];
+        C.bytes[c] = bytes[c];
+    }
+    unsigned long long pos = 0;
+    for (unsigned long long r = 0; r < n_rows; ++r) {
+        const uint64_t l = csv_sink_row_len(C, r);
+        if (out) csv_sink_row_write(C, r, out + pos);
+        pos += l;
+    }
+    return pos;
+}
 int hcsv_atod(const uint8_t *s, uint32_t len, double *out) { return csv_atod(s, len, out); }
 int hcsv_atob(const uint8_t *s, uint32_t len, long long *out) { int64_t v = 0; bool ok = csv_atob(s, len, &v); *out = v; return ok; }
 }

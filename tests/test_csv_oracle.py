@@ -206,3 +206,54 @@ def test_zillow_fixture_parses_to_the_pipeline_columns():
                     assert by[offs[i]:offs[i + 1]].decode() == rows[i][src]
             else:
                 assert r.columns[c][0] == 1801.0 and r.columns[c][32660] == float(rows[32660][src])
+
+
+# ---- CSV sink (K7) -----------------------------------------------------------------------------------------------------
+def _cols_from(values_by_col, types):
+    from tuplex_b200.backend import Column
+    return [Column.from_values(v, t) for v, t in zip(values_by_col, types)]
+
+
+def test_quote_for_csv_known_answers():
+    """tuplex/test/runtime/RuntimeTest.cc:207-213 (quoteForCSV) through the oracle and through the device code on the host"""
+    from csv_helpers import host_csv_write
+    cases = [("", ""), ("hello", "hello"), (",,,,", '",,,,"'), ("\n\r", '"\n\r"'), ('"', '""""'), ('""', '""""""'), (',"a"\n', '",""a""\n"')]
+    for raw, want in cases:
+        cols = _cols_from([[raw]], [T_STR])
+        assert po.csv_write(cols, 1) == (want + "\n").encode(), raw
+        assert host_csv_write(cols, 1) == (want + "\n").encode(), raw
+
+
+def test_sink_device_code_on_host_equals_oracle_fuzz():
+    from csv_helpers import host_csv_write
+    rng = random.Random(99)
+    words = ["", "a", "x,y", 'q"q', "l\nb", "r\rb", "plain text", "é", '""', ";", "tab\t"]
+    for it in range(300):
+        ncols = rng.randint(1, 6)
+        types = [rng.choice([T_I64, T_BOOL, T_STR, T_STR]) for _ in range(ncols)]
+        n = rng.randint(0, 40)
+        vals = []
+        for t in types:
+            if t == T_I64:
+                vals.append([rng.choice([0, -1, 9, 10, -10, 2**63 - 1, -2**63, rng.randint(-10**18, 10**18)]) for _ in range(n)])
+            elif t == T_BOOL:
+                vals.append([rng.random() < 0.5 for _ in range(n)])
+            else:
+                vals.append([rng.choice(words) for _ in range(n)])
+        cols = _cols_from(vals, types)
+        d = rng.choice([",", ";", "|"])
+        assert host_csv_write(cols, n, delimiter=d) == po.csv_write(cols, n, delimiter=d), (it, types)
+
+
+def test_sink_zillow_output_is_the_golden_file():
+    """the Z1 output columns (oracle run of the stage) through the sink oracle = the reference baselines' output file"""
+    from tuplex_b200 import workloads
+    from tuplex_b200.backend import Column
+    from csv_helpers import host_csv_write
+    cols, n = workloads.load_zillow_fixture()
+    ora = po.run_program(workloads.zillow_program(), cols, n)
+    out_cols = [Column(t, d, o) for t, d, o in ora.columns]
+    golden = workloads.zillow_golden_csv()
+    body = golden.split(b"\n", 1)[1]
+    assert po.csv_write(out_cols, ora.n_out) == body
+    assert host_csv_write(out_cols, ora.n_out) == body

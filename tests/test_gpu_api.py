@@ -256,3 +256,41 @@ def test_csv_aggregate_q6_from_text(ctx, tmp_path):
     ds = ctx.csv(str(src))
     got = workloads.q6_pipeline(ds).collect()[0]
     assert abs(got - 1193053.2252999984) <= 1e-4  # tuplex/test/core/TPCH.cc:85-97
+
+
+def test_reference_test_csv_goldens(ctx, tmp_path):
+    """tuplex/python/tests/test_csv.py:19-78 — map over csv / tsv / header files (multi-parameter lambdas)"""
+    def gen(path, delimiter, has_header=False):
+        with open(path, "w") as f:
+            if has_header:
+                f.write(delimiter.join(["a", "b", "c", "d"]) + "\n")
+            for i in range(3):
+                f.write(delimiter.join([str(3 * i + j + 1) for j in range(3)] + ["FAST ETL!"]) + "\n")
+    gen(tmp_path / "test.csv", ",")
+    gen(tmp_path / "test.tsv", "\t")
+    gen(tmp_path / "test_header.csv", ",", True)
+    assert ctx.csv(str(tmp_path / "test.csv")).map(lambda a, b, c, d: a).collect() == [1, 4, 7]
+    assert ctx.csv(str(tmp_path / "test.csv")).map(lambda a, b, c, d: d).collect() == ["FAST ETL!"] * 3
+    assert ctx.csv(str(tmp_path / "test.tsv"), delimiter="\t").map(lambda a, b, c, d: a).collect() == [1, 4, 7]
+    assert ctx.csv(str(tmp_path / "test.tsv"), delimiter="\t").map(lambda a, b, c, d: d).collect() == ["FAST ETL!"] * 3
+    assert ctx.csv(str(tmp_path / "test_header.csv"), header=True).map(lambda a, b, c, d: a).collect() == [1, 4, 7]
+
+
+def test_tocsv_written_on_the_device(ctx, tmp_path):
+    """csv -> pipeline -> tocsv with no interpreter-path rows: the file body comes from tplx_gpu_result_csv (K7)"""
+    import gzip
+    import hashlib
+    import os
+    src = tmp_path / "zillow_full.csv"
+    with gzip.open(os.path.join(workloads.GOLDEN, "zillow_noexc.csv.gz"), "rb") as fp:
+        src.write_bytes(fp.read())
+    ds = workloads.zillow_pipeline(ctx.csv(str(src)))
+    ds.tocsv(str(tmp_path / "out"))
+    assert hashlib.md5((tmp_path / "out" / "part0.csv").read_bytes()).hexdigest() == "4d5ca0263b1a5058341a369116dee83a"
+    # quoting + bool formatting + a row that takes the interpreter path (host formatter must agree with the device's)
+    rows = [("a,b", True, 1), ('say "hi"', False, 0), ("plain", True, 3)]
+    ctx.parallelize(rows, columns=["s", "b", "i"]).map(lambda x: (x["s"], x["b"], 10 // x["i"])) \
+       .resolve(ZeroDivisionError, lambda x: (x["s"], x["b"], -1)).tocsv(str(tmp_path / "mixed.csv"))
+    assert (tmp_path / "mixed.csv").read_text() == '"a,b",true,10\n"say ""hi""",false,-1\nplain,true,3\n'
+    ctx.parallelize(rows, columns=["s", "b", "i"]).map(lambda x: (x["s"], x["b"], x["i"] + 1)).tocsv(str(tmp_path / "dev.csv"))
+    assert (tmp_path / "dev.csv").read_text() == '"a,b",true,2\n"say ""hi""",false,1\nplain,true,4\n'

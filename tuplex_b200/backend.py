@@ -91,6 +91,7 @@ def lib():
         "tplx_gpu_result_fetch_aggregate": ([vp, P(i64)], i32),
         "tplx_gpu_result_partitions": ([vp, u64, vp, u64, P(u64), P(u64), u32, P(u32)], i32),
         "tplx_gpu_result_exception_partition": ([vp, vp, u64, P(u64)], i32),
+        "tplx_gpu_result_csv": ([vp, u32, ct.c_uint8, ct.c_uint8, vp, u64, P(u64)], i32),
         "tplx_gpu_result_free": ([vp], i32),
         "tplx_gpu_stage_hash_reserve": ([vp, i32, u64], i32),
         "tplx_gpu_stage_hash_finish": ([vp, i32, P(vp)], i32),
@@ -390,6 +391,19 @@ class Result:
                                                 nparts.value, ct.byref(nparts)), "result_partitions")
         raw = buf.tobytes()
         return [raw[offs[p]:offs[p + 1]] for p in range(nparts.value)]
+
+    def csv_bytes(self, delimiter=",", quotechar='"', n_cols: int = 0) -> Optional[bytes]:
+        """First n_cols (0 = all) output columns as CSV text written on the device (K7); None when one of them is f64."""
+        need = ct.c_uint64()
+        rc = lib().tplx_gpu_result_csv(self._h, n_cols, ord(delimiter), ord(quotechar), None, 0, ct.byref(need))
+        if rc == -6:  # TPLX_E_UNSUPPORTED
+            return None
+        _check(rc, "tplx_gpu_result_csv")
+        buf = np.empty(need.value, dtype=np.uint8)
+        if need.value:
+            _check(lib().tplx_gpu_result_csv(self._h, n_cols, ord(delimiter), ord(quotechar), buf.ctypes.data, need.value, ct.byref(need)),
+                   "tplx_gpu_result_csv")
+        return buf.tobytes()
 
     def exception_partition(self) -> bytes:
         need = ct.c_uint64()

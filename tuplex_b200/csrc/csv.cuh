@@ -222,4 +222,15 @@ __global__ void __launch_bounds__(CSV_NT) csv_copy_strings(const CsvCompactParam
     }
 }
 
+// ---- K7: result columns -> CSV text (fast_csvwriter, PipelineBuilder.cc:1550-1722) ------------------------------
+__global__ void __launch_bounds__(CSV_NT) csv_sink_sizes(const CsvSinkCols C, uint64_t n, uint64_t *__restrict__ sizes) {
+    const uint64_t r = (uint64_t)blockIdx.x * CSV_NT + threadIdx.x;
+    if (r < n) sizes[r] = csv_sink_row_len(C, r);
+}
+__global__ void __launch_bounds__(CSV_NT) csv_sink_write(const CsvSinkCols C, uint64_t n, const uint64_t *__restrict__ row_off,
+                                                         uint8_t *__restrict__ out) {
+    const uint64_t r = (uint64_t)blockIdx.x * CSV_NT + threadIdx.x;
+    if (r < n) csv_sink_row_write(C, r, out + row_off[r]);
+}
+
 }  // namespace tplx

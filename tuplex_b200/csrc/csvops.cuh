@@ -448,4 +448,87 @@ TPLX_HD uint32_t csv_find_rows_sequential(const uint8_t *buf, uint32_t n, uint8_
     return rows;
 }
 
+// ---- CSV sink (K7): one output row as text --------------------------------------------------------------
+// fast_csvwriter (core/src/physical/PipelineBuilder.cc:1550-1722): bool -> true / false, i64 -> decimal (i64toa),
+// str -> quoteForCSV (runtime/src/Runtime.cc:682-738: quoted iff the cell holds a quote, the separator, '\n' or '\r';
+// quotes doubled), cells joined by the delimiter, '\n' after the row. f64 (ryu d2fixed, 8 digits) is not written on
+// the device yet: such results take the host formatter.
+TPLX_HD uint32_t csv_i64_len(int64_t v) {
+    uint64_t m = v < 0 ? (uint64_t)0 - (uint64_t)v : (uint64_t)v;
+    uint32_t n = v < 0 ? 2u : 1u;
+    while (m >= 10) {
+        m /= 10;
+        ++n;
+    }
+    return n;
+}
+TPLX_HD uint32_t csv_i64_write(uint8_t *p, int64_t v) {
+    const uint32_t n = csv_i64_len(v);
+    uint64_t m = v < 0 ? (uint64_t)0 - (uint64_t)v : (uint64_t)v;
+    if (v < 0) p[0] = '-';
+    uint32_t k = n;
+    do {
+        p[--k] = (uint8_t)('0' + m % 10);
+        m /= 10;
+    } while (m);
+    return n;
+}
+TPLX_HD uint32_t csv_quoted_len(const uint8_t *s, uint32_t len, uint8_t delim, uint8_t quote) {
+    uint32_t nq = 0;
+    bool need = false;
+    for (uint32_t i = 0; i < len; ++i) {
+        nq += s[i] == quote;
+        need |= s[i] == delim || s[i] == '\n' || s[i] == '\r';
+    }
+    return (nq || need) ? len + 2 + nq : len;
+}
+TPLX_HD uint32_t csv_quoted_write(uint8_t *p, const uint8_t *s, uint32_t len, uint8_t delim, uint8_t quote) {
+    const uint32_t out = csv_quoted_len(s, len, delim, quote);
+    if (out == len) {
+        for (uint32_t i = 0; i < len; ++i) p[i] = s[i];
+        return len;
+    }
+    uint32_t o = 0;
+    p[o++] = quote;
+    for (uint32_t i = 0; i < len; ++i) {
+        if (s[i] == quote) p[o++] = quote;
+        p[o++] = s[i];
+    }
+    p[o++] = quote;
+    return o;
+}
+
+struct CsvSinkCols {
+    uint32_t n_cols;
+    uint8_t delim, quote;
+    uint8_t types[TPLX_MAX_COLS];
+    const uint64_t *data[TPLX_MAX_COLS];
+    const uint32_t *offsets[TPLX_MAX_COLS];
+    const uint8_t *bytes[TPLX_MAX_COLS];
+};
+TPLX_HD uint64_t csv_sink_row_len(const CsvSinkCols &C, uint64_t r) {
+    uint64_t n = C.n_cols;  // delimiters + newline
+    for (uint32_t c = 0; c < C.n_cols; ++c) {
+        if (C.types[c] == TPLX_T_STR)
+            n += csv_quoted_len(C.bytes[c] + C.offsets[c][r], C.offsets[c][r + 1] - C.offsets[c][r], C.delim, C.quote);
+        else if (C.types[c] == TPLX_T_BOOL)
+            n += C.data[c][r] ? 4 : 5;
+        else
+            n += csv_i64_len((int64_t)C.data[c][r]);
+    }
+    return n;
+}
+TPLX_HD void csv_sink_row_write(const CsvSinkCols &C, uint64_t r, uint8_t *p) {
+    for (uint32_t c = 0; c < C.n_cols; ++c) {
+        if (C.types[c] == TPLX_T_STR)
+            p += csv_quoted_write(p, C.bytes[c] + C.offsets[c][r], C.offsets[c][r + 1] - C.offsets[c][r], C.delim, C.quote);
+        else if (C.types[c] == TPLX_T_BOOL) {
+            const char *t = C.data[c][r] ? "true" : "false";
+            while (*t) *p++ = (uint8_t)*t++;
+        } else
+            p += csv_i64_write(p, (int64_t)C.data[c][r]);
+        *p++ = c + 1 == C.n_cols ? (uint8_t)'\n' : C.delim;
+    }
+}
+
 }  // namespace tplx

@@ -335,3 +335,54 @@ extern "C" int32_t tplx_gpu_csv_result_free(tplx_csv_result *r) {
     delete r;
     return TPLX_OK;
 }
+
+// ---- K7: CSV sink ----------------------------------------------------------------------------------------------------
+extern "C" int32_t tplx_gpu_result_csv(tplx_result *r, uint32_t n_cols, uint8_t delimiter, uint8_t quotechar, uint8_t *buf,
+                                       uint64_t buf_bytes, uint64_t *bytes_needed) {
+    if (!r || !bytes_needed || r->agg_out) return fail(TPLX_E_BADARG, "result_csv: needs a row result");
+    Device *d = r->dev;
+    CsvSinkCols C{};
+    C.n_cols = (uint32_t)(r->out.size() - r->hidden);
+    if (n_cols && n_cols < C.n_cols) C.n_cols = n_cols;
+    C.delim = delimiter;
+    C.quote = quotechar;
+    for (uint32_t c = 0; c < C.n_cols; ++c) {
+        C.types[c] = r->out_types[c];
+        if (C.types[c] == TPLX_T_F64)
+            return fail(TPLX_E_UNSUPPORTED, "result_csv: f64 columns (ryu d2fixed) are formatted on the host");
+        C.data[c] = r->out[c].data;
+        C.offsets[c] = r->out[c].offsets;
+        C.bytes[c] = r->out[c].bytes;
+    }
+    tplx_result_info info;
+    int32_t rc = tplx_gpu_result_info(r, &info);  // synchronises the stage
+    if (rc) return rc;
+    const uint64_t n = r->n_out;
+    if (n == 0 || C.n_cols == 0) {
+        *bytes_needed = 0;
+        return TPLX_OK;
+    }
+    std::lock_guard<std::mutex> lk(d->mu);
+    CU(cudaSetDevice(d->id));
+    CsvTemps T{d->stream, {}};
+    uint64_t *sizes = nullptr;
+    CU(T.alloc(&sizes, n + 1));
+    const uint32_t nb = (uint32_t)((n + CSV_NT - 1) / CSV_NT);
+    csv_sink_sizes<<<nb, CSV_NT, 0, d->stream>>>(C, n, sizes);
+    rc = device_scan(d, sizes, sizes, n, true);
+    if (rc) return rc;
+    uint64_t total = 0;
+    CU(cudaMemcpyAsync(&total, sizes + n, 8, cudaMemcpyDeviceToHost, d->stream));
+    CU(cudaStreamSynchronize(d->stream));
+    *bytes_needed = total;
+    if (!buf) return TPLX_OK;
+    if (buf_bytes < total) return fail(TPLX_E_BADARG, "result_csv: buffer too small");
+    uint8_t *out = nullptr;
+    CU(T.alloc(&out, total));
+    csv_sink_write<<<nb, CSV_NT, 0, d->stream>>>(C, n, sizes, out);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(buf, out, total, cudaMemcpyDeviceToHost, d->stream));
+    CU(cudaStreamSynchronize(d->stream));
+    r->launches += 5;
+    return TPLX_OK;
+}

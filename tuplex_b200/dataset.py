@@ -116,16 +116,28 @@ class DataSet:
             print(r)
 
     def tocsv(self, path, part_size=0, num_rows=None, num_parts=0, part_name_generator=None, null_value=None, header=True):
+        """CSV sink (python/tuplex/dataset.py:502-560). Rows are formatted like the reference's row writer
+        (fast_csvwriter, PipelineBuilder.cc:1550-1722): on the device (K7, tplx_gpu_result_csv) when the last stage ran
+        there without rows from the interpreter path, else by the host twin `_csv_cell`."""
         import os
-        rows, names = self._execute()
+        self._csv_sink = []
+        try:
+            rows, names = self._execute(sink="csv")
+            chunks = self._csv_sink
+        finally:
+            self._csv_sink = None
         os.makedirs(path, exist_ok=True) if not path.endswith(".csv") else None
         fn = path if path.endswith(".csv") else os.path.join(path, "part0.csv")
-        with open(fn, "w", newline="") as fp:
+        with open(fn, "wb") as fp:
             if header and any(names):
-                fp.write(",".join(str(n) for n in names) + "\n")
-            for r in rows:
-                vals = r if isinstance(r, tuple) else (r,)
-                fp.write(",".join(_csv_cell(v) for v in vals) + "\n")
+                fp.write((",".join(_csv_cell(str(n)) for n in names) + "\n").encode())
+            if rows is None:
+                for ch in chunks:
+                    fp.write(ch)
+            else:
+                for r in rows:
+                    vals = r if isinstance(r, tuple) else (r,)
+                    fp.write((",".join(_csv_cell(v, null_value) for v in vals) + "\n").encode())
 
     @property
     def columns(self):
@@ -140,7 +152,7 @@ class DataSet:
     def _plan_names(self):
         return None, self._execute(dry=True)[1]
 
-    def _execute(self, dry: bool = False):
+    def _execute(self, dry: bool = False, sink: Optional[str] = None):
         """Split the operator chain into stages and run them. Returns (python rows, column names)."""
         src = self._source
         if self._parent is not None:
@@ -158,18 +170,29 @@ class DataSet:
         for si, ops in enumerate(stages):
             if si > 0:
                 src = self._ctx._source_from_rows(rows, names)
-            rows, names = _run_stage(self._ctx, src, ops, self._last_exceptions)
+            last = si == len(stages) - 1
+            rows, names = _run_stage(self._ctx, src, ops, self._last_exceptions,
+                                     csv_sink=self._csv_sink if (sink == "csv" and last) else None)
         return rows, names
 
 
-def _csv_cell(v) -> str:
+def _csv_cell(v, null_value=None) -> str:
+    """Host twin of the row writer (fast_csvwriter + quoteForCSV + ryu d2fixed(8) for floats)."""
     if isinstance(v, str):
-        if any(ch in v for ch in ',"\n'):
+        if any(ch in v for ch in ',"\n\r'):
             return '"' + v.replace('"', '""') + '"'
         return v
+    if v is None:
+        return _csv_cell(null_value or "")
     if isinstance(v, bool):
-        return "True" if v else "False"
-    return repr(v) if isinstance(v, float) else str(v)
+        return "true" if v else "false"
+    if isinstance(v, float):
+        if v != v:
+            return "NaN"
+        if v in (float("inf"), float("-inf")):
+            return "Infinity" if v > 0 else "-Infinity"
+        return "%.8f" % v
+    return str(v)
 
 
 def _row_of(cols: List[Column], values_cache: List[list], i: int):
@@ -177,7 +200,7 @@ def _row_of(cols: List[Column], values_cache: List[list], i: int):
     return vals if len(vals) != 1 else vals[0]
 
 
-def _run_stage(ctx, src: Source, ops: List[Op], exc_counter: Counter):
+def _run_stage(ctx, src: Source, ops: List[Op], exc_counter: Counter, csv_sink: Optional[list] = None):
     """One TransformStage on the GPU + CPython resolve of its exception rows."""
     end = ops[-1] if ops and ops[-1].kind in ("aggregate", "aggregateByKey", "unique") else None
     row_ops = ops[:-1] if end else ops
@@ -270,6 +293,16 @@ def _run_stage(ctx, src: Source, ops: List[Op], exc_counter: Counter):
             buf.free()
         src.total_rows = base
 
+    held: List[tuple] = []
+
+    def fetch_cols(res, lo, rowmap):
+        oc = res.columns()
+        if need_rowidx:
+            if rowmap is not None:
+                oc[-1].data = rowmap[oc[-1].data]
+            oc[-1].data += lo
+        return oc
+
     for run, lo, parse, data in (csv_blocks() if is_csv else host_blocks()):
         res = run()
         info = res.info
@@ -302,13 +335,11 @@ def _run_stage(ctx, src: Source, ops: List[Op], exc_counter: Counter):
             exc["row"] += lo
             exc_all.append(exc)
         if prog.endpoint == C["TPLX_EP_MEMORY"]:
-            oc = res.columns()
-            if need_rowidx:
-                if rowmap is not None:
-                    oc[-1].data = rowmap[oc[-1].data]
-                oc[-1].data += lo
-            out_cols_all.append(oc)
             first_row_no += int(info.n_out_rows) + int(info.n_exceptions)
+            if csv_sink is not None:
+                held.append((res, lo, rowmap))  # decide at the end: device CSV writer or column fetch + merge
+                continue
+            out_cols_all.append(fetch_cols(res, lo, rowmap))
         elif prog.endpoint == C["TPLX_EP_AGGREGATE"]:
             agg_partials.append(res.aggregate_bits())
         res.free()
@@ -317,6 +348,25 @@ def _run_stage(ctx, src: Source, ops: List[Op], exc_counter: Counter):
     # ---- endpoints --------------------------------------------------------------------------------
     if prog.endpoint == C["TPLX_EP_MEMORY"]:
         ncols = len(prog.out_cols) - prog.hidden_out_cols
+        if csv_sink is not None:
+            # CSV sink: when no row took the interpreter path the rows are formatted on the device (K7) in block order
+            ok = not len(excs) and not fallback
+            if ok:
+                for res, _, _ in held:
+                    txt = res.csv_bytes(n_cols=ncols - (1 if need_rowidx else 0))
+                    if txt is None:  # f64 output column: host formatter
+                        ok = False
+                        break
+                    csv_sink.append(txt)
+            if ok:
+                for res, _, _ in held:
+                    res.free()
+                stage.close()
+                return None, out_names
+            del csv_sink[:]
+            for res, lo_, rowmap_ in held:
+                out_cols_all.append(fetch_cols(res, lo_, rowmap_))
+                res.free()
         merged_vals = [sum((oc[c].to_values() for oc in out_cols_all), []) for c in range(ncols)]
         n_out = len(merged_vals[0]) if ncols else 0
         user_cols = ncols - (1 if need_rowidx else 0)
