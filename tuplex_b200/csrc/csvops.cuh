@@ -35,6 +35,56 @@ constexpr uint32_t CSV_DEQ_CAP = 64;            // local buffer for escaped nume
 
 TPLX_HD bool csv_is_nl(uint8_t c) { return c == '\n' || c == '\r'; }
 
+// ---- 8 bytes at a time (little endian). Buffers are padded past [n], so the aligned word holding any position <= n
+// may be read whole.
+TPLX_HD uint64_t csv_load8(const uint8_t *p) {  // p is 8-byte aligned on the device
+#ifdef __CUDA_ARCH__
+    return *reinterpret_cast<const uint64_t *>(p);
+#else
+    uint64_t w = 0;
+    for (int k = 7; k >= 0; --k) w = (w << 8) | p[k];
+    return w;
+#endif
+}
+// 0x80 in every byte lane of w that equals c (exact)
+TPLX_HD uint64_t csv_eq8(uint64_t w, uint8_t c) {
+    const uint64_t x = w ^ (0x0101010101010101ull * c);
+    const uint64_t t = ((x & 0x7f7f7f7f7f7f7f7full) + 0x7f7f7f7f7f7f7f7full) | x;
+    return ~t & 0x8080808080808080ull;
+}
+// lane mask (0x80 per byte) -> 8 bits, bit i = byte i
+TPLX_HD uint32_t csv_pack8(uint64_t m) { return (uint32_t)(((m >> 7) * 0x0102040810204080ull) >> 56); }
+TPLX_HD uint32_t csv_ctz64(uint64_t m) {
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__ffsll((long long)m) - 1;
+#else
+    return (uint32_t)__builtin_ctzll(m);
+#endif
+}
+// first position >= p whose byte is a, b or c; the caller guarantees one exists at or before [n] (the appended newline)
+TPLX_HD uint32_t csv_find3(const uint8_t *buf, uint32_t p, uint8_t a, uint8_t b, uint8_t c) {
+    uint32_t base = p & ~7u;
+    uint64_t w = csv_load8(buf + base);
+    uint64_t m = (csv_eq8(w, a) | csv_eq8(w, b) | csv_eq8(w, c)) & (~0ull << (8 * (p & 7)));
+    while (!m) {
+        base += 8;
+        w = csv_load8(buf + base);
+        m = csv_eq8(w, a) | csv_eq8(w, b) | csv_eq8(w, c);
+    }
+    return base + (csv_ctz64(m) >> 3);
+}
+// first position in [p, n] whose byte is q, or a value > n
+TPLX_HD uint32_t csv_find1(const uint8_t *buf, uint32_t p, uint32_t n, uint8_t q) {
+    uint32_t base = p & ~7u;
+    uint64_t m = csv_eq8(csv_load8(buf + base), q) & (~0ull << (8 * (p & 7)));
+    while (!m) {
+        base += 8;
+        if (base > n) return n + 1;
+        m = csv_eq8(csv_load8(buf + base), q);
+    }
+    return base + (csv_ctz64(m) >> 3);
+}
+
 // Runs the row machine from p (first byte of the row, never a newline). f(cell_index, begin, end, escaped) is
 // called for every cell ([begin,end) = raw content, quotes of a quoted cell excluded). Returns the position of
 // the row's terminating newline and the number of cells, or CSV_UNDERRUN.
@@ -53,7 +103,7 @@ TPLX_HD uint32_t csv_row_machine(const uint8_t *buf, uint32_t p, uint32_t n, uin
             const uint32_t b = ++p;
             bool esc = false;
             for (;;) {
-                while (p <= n && buf[p] != quote) ++p;
+                p = csv_find1(buf, p, n, quote);
                 if (p >= n) return CSV_UNDERRUN;  // buf[n] is the appended newline, never a quote
                 const uint32_t q = p++;           // p = byte after the quote (<= n)
                 c = buf[p];
@@ -73,7 +123,7 @@ TPLX_HD uint32_t csv_row_machine(const uint8_t *buf, uint32_t p, uint32_t n, uin
             }
         } else {
             const uint32_t b = p;
-            while (buf[p] != delim && !csv_is_nl(buf[p])) ++p;
+            p = csv_find3(buf, p, delim, '\n', '\r');
             f(cell, b, p, false);
             if (buf[p] == delim) {
                 ++cell;
@@ -336,39 +386,38 @@ TPLX_HD CsvState csv_compose(const CsvState &a, const CsvState &b) {
 template <class Emit>
 TPLX_HD CsvState csv_walk_span(const uint8_t *buf, uint64_t start, uint8_t quote, uint32_t par0, Emit &&emit) {
     CsvState s{0, 0, 0};
-    bool prev_nl = start == 0 ? true : csv_is_nl(buf[start - 1]);
-    for (uint32_t k = 0; k < CSV_SPAN / 16; ++k) {
-        uint32_t w[4];
+    uint32_t par = 0;                                                              // quotes so far in the span, mod 2
+    uint32_t prev_nl = start == 0 ? 1u : (csv_is_nl(buf[start - 1]) ? 1u : 0u);  // is the previous byte a newline
+    const uint32_t flip0 = par0 == 1 ? 0xFFu : 0u;
+    for (uint32_t k = 0; k < CSV_SPAN / 8; ++k) {
+        const uint64_t w = csv_load8(buf + start + 8 * k);
+        const uint32_t q = csv_pack8(csv_eq8(w, quote));
+        const uint32_t nl = csv_pack8(csv_eq8(w, '\n') | csv_eq8(w, '\r'));
+        uint32_t x = q;  // inclusive prefix parity of the quote bits
+        x ^= x << 1;
+        x ^= x << 2;
+        x ^= x << 4;
+        const uint32_t inside = (x ^ (par ? 0xFFu : 0u)) & 0xFFu;  // relative to a span that starts outside quotes
+        const uint32_t cand = nl & ~((nl << 1) | prev_nl) & 0xFFu;  // newline whose previous byte is not one
 #ifdef __CUDA_ARCH__
-        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(buf + start) + k);
-        w[0] = v.x, w[1] = v.y, w[2] = v.z, w[3] = v.w;
+        s.c1 += __popc(cand & inside);
+        s.c0 += __popc(cand & ~inside);
 #else
-        for (int j = 0; j < 4; ++j) {
-            const uint8_t *q = buf + start + k * 16 + j * 4;
-            w[j] = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
-        }
+        s.c1 += (uint32_t)__builtin_popcount(cand & inside);
+        s.c0 += (uint32_t)__builtin_popcount(cand & ~inside & 0xFFu);
 #endif
-#ifdef __CUDA_ARCH__
-#pragma unroll
-#endif
-        for (uint32_t i = 0; i < 16; ++i) {
-            const uint8_t c = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
-            if (c == quote) {
-                s.par ^= 1;
-                prev_nl = false;
-            } else if (csv_is_nl(c)) {
-                if (!prev_nl) {
-                    if (s.par)
-                        ++s.c1;
-                    else
-                        ++s.c0;
-                    if ((s.par ^ par0) == 0) emit(start + k * 16 + i);
-                }
-                prev_nl = true;
-            } else
-                prev_nl = false;
+        if (par0 <= 1) {
+            uint32_t e = cand & ~(inside ^ flip0) & 0xFFu;  // outside quotes given the real start parity
+            while (e) {
+                const uint32_t i = csv_ctz64(e);
+                emit(start + 8 * k + i);
+                e &= e - 1;
+            }
         }
+        par = (inside >> 7) & 1u;
+        prev_nl = (nl >> 7) & 1u;
     }
+    s.par = par;
     return s;
 }
 
