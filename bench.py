@@ -645,7 +645,10 @@ def main_csv(args, rank, world, local):
                         "note": "host CSV bytes (page-locked) -> tplx_gpu_csv_upload -> tplx_gpu_csv_parse -> tplx_gpu_stage_run -> result columns fetched"},
                 "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "kernel": "csv_tile_states + csv_row_ends + csv_parse_rows + scans + csv_compact + csv_copy_strings (K6)",
-                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             # dram__bytes_read + dram__bytes_write of the six K6 kernels per parse, ncu --set full (profiles/r01_csv_k6.md:
+                             # 5.47 GB for 804.1 MB of text), scaled to this buffer size
+                             "traffic": 5.47e9 / 804.1e6 * int(text.size), "peak_source": peak_src,
                              "algorithmic_bytes_per_row": alg / total, "kernel_ms_per_launch": parse_ms_step / n_blocks,
                              "kernel_share_of_step": parse_ms_step / ms_step, "stage_ms_per_step": sms / args.steps,
                              "csv_gb_per_s": csv_bytes / (parse_ms_step * 1e-3) / 1e9}}

@@ -140,3 +140,34 @@ def test_frontend_breadth_vs_cpython(built):
     sc.add_map(udfs[2], 100001)
     sc.finish_memory()
     assert sc.names == ["k", "v"]
+
+
+def test_csv_source_planning_and_chunking(tmp_path, monkeypatch):
+    """host side of Context.csv: sniffing / header / type inference from a sample, and chunking of large inputs at row
+    boundaries (quote parity) — chunks re-joined must give the same rows as one pass."""
+    import numpy as np
+    from tuplex_b200 import csvsource as cs
+    from tuplex_b200.ir import T_F64, T_I64, T_STR
+    from csv_helpers import gen_csv
+    import random
+    rng = random.Random(4)
+    body = gen_csv(rng, 400, [T_I64, T_STR, T_F64, T_STR], dirty=0.0)
+    p = tmp_path / "t.csv"
+    p.write_bytes(b"id,name,score,note\n" + body)
+    import tuplex_b200
+    ds = tuplex_b200.Context().csv(str(p))
+    src = ds._source
+    assert src.names == ["id", "name", "score", "note"] and src.header and src.delimiter == ","
+    assert src.types == [T_I64, T_STR, T_F64, T_STR]
+    whole = [cells for cells, _, _ in cs.iter_rows(src.files[0].tobytes(), 44, 34)]
+    monkeypatch.setattr(cs, "MAX_CHUNK", 997)
+    parts = list(src.chunks())
+    assert len(parts) > 10 and parts[0][1] is True and not any(h for _, h in parts[1:])
+    assert b"".join(d.tobytes() for d, _ in parts) == src.files[0].tobytes()
+    joined = [cells for d, _ in parts for cells, _, _ in cs.iter_rows(d.tobytes(), 44, 34)]
+    assert joined == whole
+    # interpreter-path decoders: typed (as the device decodes) vs general (`parse` of the reference's fallback code)
+    assert src.line_object(b'7,"a,b",1.50,x', True) == (7, "a,b", 1.5, "x")
+    assert src.line_object(b"n/a,t,,x", False) == ("n/a", True, None, "x")
+    hs = src.to_host_source()
+    assert hs.n_rows + len(hs.fallback) == 400

@@ -294,3 +294,28 @@ def test_tocsv_written_on_the_device(ctx, tmp_path):
     assert (tmp_path / "mixed.csv").read_text() == '"a,b",true,10\n"say ""hi""",false,-1\nplain,true,3\n'
     ctx.parallelize(rows, columns=["s", "b", "i"]).map(lambda x: (x["s"], x["b"], x["i"] + 1)).tocsv(str(tmp_path / "dev.csv"))
     assert (tmp_path / "dev.csv").read_text() == '"a,b",true,2\n"say ""hi""",false,1\nplain,true,4\n'
+
+
+def test_csv_many_chunks_equal_one(ctx, tmp_path, monkeypatch):
+    """inputs larger than one device buffer are cut at row boundaries; row numbering, bad-row merge and exception
+    resolution must not depend on the cut points"""
+    import random
+    from tuplex_b200 import csvsource as cs
+    rng = random.Random(8)
+    lines = ["k,v,s"]
+    for i in range(20000):
+        r = rng.random()
+        if r < 0.01:
+            lines.append(f"x{i},1,\"bad, int\"")
+        elif r < 0.02:
+            lines.append(f"{i},0,zero")
+        else:
+            lines.append(f"{i},{rng.randint(1, 9)},\"s,{i}\"" if i % 7 == 0 else f"{i},{rng.randint(1, 9)},s{i}")
+    p = tmp_path / "big.csv"
+    p.write_text("\n".join(lines) + "\n")
+    pipeline = lambda ds: ds.map(lambda x: (x['k'], 100 // x['v'], x['s'])).resolve(ZeroDivisionError, lambda x: (x['k'], -1, x['s'])) \
+                            .filter(lambda x: x[1] != 50).collect()
+    one = pipeline(ctx.csv(str(p)))
+    monkeypatch.setattr(cs, "MAX_CHUNK", 40_000)
+    many = pipeline(ctx.csv(str(p)))
+    assert len(one) > 15000 and many == one
