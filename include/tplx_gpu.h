@@ -147,8 +147,8 @@ int32_t tplx_gpu_result_exception_partition(tplx_result *res, uint8_t *buf, uint
 /* K7, CSV sink: the output rows as CSV text, byte for byte what the reference's CSV row writer emits per row
  * (fast_csvwriter, core/src/physical/PipelineBuilder.cc:1550-1722; quoteForCSV, runtime/src/Runtime.cc:682-738):
  * bool -> true / false, i64 -> decimal, str quoted iff it holds the quote char, the delimiter, '\n' or '\r'. No header
- * (LocalBackend::writeOutput adds it per file). f64 columns -> TPLX_E_UNSUPPORTED (host formatter). Call with buf == NULL
- * for the size. */
+ * (LocalBackend::writeOutput adds it per file). f64 -> 8 fixed decimals, correctly rounded (ryu d2fixed(8) digits); a value of
+ * magnitude >= 2^63 makes the call return TPLX_E_UNSUPPORTED (host formatter). Call with buf == NULL for the size. */
 int32_t tplx_gpu_result_csv(tplx_result *res, uint32_t n_cols /* first n_cols output columns, 0 = all */, uint8_t delimiter,
                             uint8_t quotechar, uint8_t *buf, uint64_t buf_bytes, uint64_t *bytes_needed);
 int32_t tplx_gpu_result_free(tplx_result *res);

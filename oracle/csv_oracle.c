@@ -460,6 +460,14 @@ uint64_t csv_oracle_write(const sink_col *cols, uint32_t n_cols, uint64_t n_rows
                     if (out) memcpy(out + pos, s, len);
                     pos += len;
                 }
+            } else if (cols[c].type == T_F64) {
+                /* ryu d2fixed_buffered_n(d, 8, buf): printf("%.8f") digits (glibc is exact), specials "nan" / "[-]Infinity" */
+                double d = ((const double *)cols[c].data)[r];
+                char fb[400];
+                int k = isnan(d) ? snprintf(fb, sizeof fb, "nan") : isinf(d) ? snprintf(fb, sizeof fb, d < 0 ? "-Infinity" : "Infinity")
+                                                                           : snprintf(fb, sizeof fb, "%.8f", d);
+                if (out) memcpy(out + pos, fb, (size_t)k);
+                pos += (uint64_t)k;
             } else {
                 int64_t v = ((const int64_t *)cols[c].data)[r];
                 int k = cols[c].type == T_BOOL ? snprintf(tmp, sizeof tmp, "%s", v ? "true" : "false") : snprintf(tmp, sizeof tmp, "%lld", (long long)v);

@@ -257,3 +257,26 @@ def test_sink_zillow_output_is_the_golden_file():
     body = golden.split(b"\n", 1)[1]
     assert po.csv_write(out_cols, ora.n_out) == body
     assert host_csv_write(out_cols, ora.n_out) == body
+
+
+def test_sink_f64_fixed8_exact():
+    """device f64 formatter (exact 128-bit integer arithmetic) vs the oracle's printf("%.8f") on ties, boundaries, specials"""
+    import struct as st
+    from csv_helpers import host_csv_write
+    rng = random.Random(123)
+    vals = [0.0, -0.0, 1.5, -2.25, 2**-9, 3 * 2**-9, 0.000000005, 0.000000015, 0.999999995, 0.9999999949999999, 1e-9, -1e-10, 123456789.123456789,
+            9.007199254740992e15, 2**62 * 1.0, -(2**63 - 1024) * 1.0, 5e-324, 2.2250738585072014e-308, 1 / 3, 2 / 3, 1801.0, 0.07, 99999999.999999994,
+            float("inf"), float("-inf"), float("nan")]
+    for _ in range(20000):
+        r = rng.random()
+        if r < 0.3:
+            vals.append(st.unpack("<d", st.pack("<Q", rng.getrandbits(64)))[0])
+        elif r < 0.6:
+            vals.append(rng.uniform(-1e6, 1e6))
+        elif r < 0.8:
+            vals.append(rng.randint(-10**9, 10**9) / 10 ** rng.randint(0, 12))
+        else:
+            vals.append(rng.randint(0, 2**20) * 2.0 ** -rng.randint(1, 40))  # many exact ties at the 8th decimal
+    small = [v for v in vals if v != v or abs(v) == float("inf") or abs(v) < 2.0**63]
+    cols = _cols_from([small], [T_F64])
+    assert host_csv_write(cols, len(small)) == po.csv_write(cols, len(small))

@@ -170,11 +170,18 @@ def test_sink_fuzz_equals_oracle(gpu):
         st.close()
 
 
-def test_sink_rejects_f64(gpu):
+def test_sink_f64_columns(gpu):
+    """f64 cells: 8 fixed decimals, correctly rounded (ryu d2fixed(8) digits) — exact on the device below 2^63"""
     from tuplex_b200.backend import Column
-    st = backend.Stage(workloads.c1_program())
-    sc = frontend.StageCompiler([T_F64], [None])
-    sc.add_map(lambda x: x * 2.0, 100001)
+    rng = random.Random(3)
+    vals = [0.0, -0.0, 1.5, 2**-9, 0.999999995, 1 / 3, 1801.0, 123456789.123456789, -2.5e-9, float("inf"), float("-inf"), float("nan"), 2.0**62]
+    vals += [rng.uniform(-1e7, 1e7) for _ in range(5000)] + [rng.randint(0, 2**20) * 2.0 ** -rng.randint(1, 40) for _ in range(5000)]
+    cols = [Column.from_values(vals, T_F64), Column.from_values(list(range(len(vals))), T_I64)]
+    sc = frontend.StageCompiler([T_F64, T_I64], [None, None])
+    sc.add_map(lambda x: x, 100001)
     st = backend.Stage(sc.finish_memory())
-    res = st.run_host(0, [Column.from_values([1.5, 2.5], T_F64)], 2)
-    assert res.csv_bytes() is None  # ryu d2fixed output stays on the host formatter
+    res = st.run_host(0, cols, len(vals))
+    assert res.csv_bytes() == po.csv_write(cols, len(vals))
+    res.free()
+    res = st.run_host(0, [Column.from_values([1.0, 1e30], T_F64), Column.from_values([1, 2], T_I64)], 2)
+    assert res.csv_bytes() is None  # magnitude >= 2^63: the call reports TPLX_E_UNSUPPORTED, tocsv formats on the host

@@ -393,7 +393,8 @@ class Result:
         return [raw[offs[p]:offs[p + 1]] for p in range(nparts.value)]
 
     def csv_bytes(self, delimiter=",", quotechar='"', n_cols: int = 0) -> Optional[bytes]:
-        """First n_cols (0 = all) output columns as CSV text written on the device (K7); None when one of them is f64."""
+        """First n_cols (0 = all) output columns as CSV text written on the device (K7); None when an f64 cell has a magnitude
+        >= 2^63 (TPLX_E_UNSUPPORTED: the caller formats on the host)."""
         need = ct.c_uint64()
         rc = lib().tplx_gpu_result_csv(self._h, n_cols, ord(delimiter), ord(quotechar), None, 0, ct.byref(need))
         if rc == -6:  # TPLX_E_UNSUPPORTED

@@ -223,9 +223,13 @@ __global__ void __launch_bounds__(CSV_NT) csv_copy_strings(const CsvCompactParam
 }
 
 // ---- K7: result columns -> CSV text (fast_csvwriter, PipelineBuilder.cc:1550-1722) ------------------------------
-__global__ void __launch_bounds__(CSV_NT) csv_sink_sizes(const CsvSinkCols C, uint64_t n, uint64_t *__restrict__ sizes) {
+__global__ void __launch_bounds__(CSV_NT) csv_sink_sizes(const CsvSinkCols C, uint64_t n, uint64_t *__restrict__ sizes,
+                                                         uint32_t *__restrict__ unsupported) {
     const uint64_t r = (uint64_t)blockIdx.x * CSV_NT + threadIdx.x;
-    if (r < n) sizes[r] = csv_sink_row_len(C, r);
+    if (r >= n) return;
+    const uint64_t l = csv_sink_row_len(C, r);
+    if (!l) *unsupported = 1;  // an f64 cell beyond the exact-arithmetic range
+    sizes[r] = l;
 }
 __global__ void __launch_bounds__(CSV_NT) csv_sink_write(const CsvSinkCols C, uint64_t n, const uint64_t *__restrict__ row_off,
                                                          uint8_t *__restrict__ out) {

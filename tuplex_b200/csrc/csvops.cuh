@@ -501,7 +501,8 @@ TPLX_HD uint32_t csv_find_rows_sequential(const uint8_t *buf, uint32_t n, uint8_
 // fast_csvwriter (core/src/physical/PipelineBuilder.cc:1550-1722): bool -> true / false, i64 -> decimal (i64toa),
 // str -> quoteForCSV (runtime/src/Runtime.cc:682-738: quoted iff the cell holds a quote, the separator, '\n' or '\r';
 // quotes doubled), cells joined by the delimiter, '\n' after the row. f64 (ryu d2fixed, 8 digits) is not written on
-// the device yet: such results take the host formatter.
+// device for |v| < 2^63 (exact integer arithmetic below); larger magnitudes make the call report TPLX_E_UNSUPPORTED and the
+// caller formats on the host.
 TPLX_HD uint32_t csv_i64_len(int64_t v) {
     uint64_t m = v < 0 ? (uint64_t)0 - (uint64_t)v : (uint64_t)v;
     uint32_t n = v < 0 ? 2u : 1u;
@@ -547,6 +548,70 @@ TPLX_HD uint32_t csv_quoted_write(uint8_t *p, const uint8_t *s, uint32_t len, ui
     return o;
 }
 
+// f64 -> fixed notation with 8 decimals, correctly rounded (ties to even on the exact binary value): what the reference's
+// row writer gets from ryu's d2fixed_buffered_n(d, 8, buf) (third-party ryu, not vendored in the reference tree; restated
+// from its published contract = printf("%.8f") digits; special values per ryu d2fixed.c copy_special_str_printf: "nan",
+// "Infinity", "-Infinity"). Exact integer arithmetic: value = m * 2^e2; the fraction m_frac * 10^8 fits in 80 bits.
+// Returns the length, or 0 when |v| >= 2^63 (needs a bignum: the caller falls back to the host formatter).
+TPLX_HD uint32_t csv_f64_fixed8(double v, uint8_t *out /* may be null: length only */) {
+    uint64_t bits;
+    bits = *reinterpret_cast<const uint64_t *>(&v);
+    const bool neg = (bits >> 63) != 0;
+    const uint32_t ex = (uint32_t)((bits >> 52) & 0x7FF);
+    const uint64_t mant = bits & 0xFFFFFFFFFFFFFull;
+    uint32_t o = 0;
+    if (ex == 0x7FF) {
+        const char *t = mant ? "nan" : (neg ? "-Infinity" : "Infinity");
+        while (t[o]) {
+            if (out) out[o] = (uint8_t)t[o];
+            ++o;
+        }
+        return o;
+    }
+    const uint64_t m = ex ? (mant | (1ull << 52)) : mant;
+    const int32_t e2 = (int32_t)(ex ? ex : 1) - 1075;
+    uint64_t ip = 0, frac8 = 0;  // integer part, 8 fraction digits
+    if (e2 >= 0) {
+        if (e2 > 10) return 0;
+        ip = m << e2;
+    } else {
+        const uint32_t k = (uint32_t)(-e2);
+        if (k <= 100) {
+            ip = k < 64 ? (m >> k) : 0;
+            const uint64_t fr = k < 64 ? (m & ((1ull << k) - 1)) : m;
+            const unsigned __int128 F = (unsigned __int128)fr * 100000000ull;
+            const unsigned __int128 one = (unsigned __int128)1 << k;
+            frac8 = (uint64_t)(F >> k);
+            const unsigned __int128 rem = F & (one - 1), half = one >> 1;
+            if (rem > half || (rem == half && (frac8 & 1))) ++frac8;
+            if (frac8 == 100000000ull) {
+                frac8 = 0;
+                ++ip;
+            }
+        }  // smaller values round to zero
+    }
+    if (neg) {
+        if (out) out[o] = '-';
+        ++o;
+    }
+    uint32_t nd = 1;
+    for (uint64_t t = ip; t >= 10; t /= 10) ++nd;
+    if (out) {
+        uint64_t t = ip;
+        for (uint32_t i = nd; i-- > 0;) {
+            out[o + i] = (uint8_t)('0' + t % 10);
+            t /= 10;
+        }
+        out[o + nd] = '.';
+        uint64_t f = frac8;
+        for (uint32_t i = 8; i-- > 0;) {
+            out[o + nd + 1 + i] = (uint8_t)('0' + f % 10);
+            f /= 10;
+        }
+    }
+    return o + nd + 9;
+}
+
 struct CsvSinkCols {
     uint32_t n_cols;
     uint8_t delim, quote;
@@ -555,10 +620,15 @@ struct CsvSinkCols {
     const uint32_t *offsets[TPLX_MAX_COLS];
     const uint8_t *bytes[TPLX_MAX_COLS];
 };
+// returns 0 when a cell cannot be formatted here (f64 of magnitude >= 2^63)
 TPLX_HD uint64_t csv_sink_row_len(const CsvSinkCols &C, uint64_t r) {
     uint64_t n = C.n_cols;  // delimiters + newline
     for (uint32_t c = 0; c < C.n_cols; ++c) {
-        if (C.types[c] == TPLX_T_STR)
+        if (C.types[c] == TPLX_T_F64) {
+            const uint32_t l = csv_f64_fixed8(*reinterpret_cast<const double *>(&C.data[c][r]), nullptr);
+            if (!l) return 0;
+            n += l;
+        } else if (C.types[c] == TPLX_T_STR)
             n += csv_quoted_len(C.bytes[c] + C.offsets[c][r], C.offsets[c][r + 1] - C.offsets[c][r], C.delim, C.quote);
         else if (C.types[c] == TPLX_T_BOOL)
             n += C.data[c][r] ? 4 : 5;
@@ -571,6 +641,8 @@ TPLX_HD void csv_sink_row_write(const CsvSinkCols &C, uint64_t r, uint8_t *p) {
     for (uint32_t c = 0; c < C.n_cols; ++c) {
         if (C.types[c] == TPLX_T_STR)
             p += csv_quoted_write(p, C.bytes[c] + C.offsets[c][r], C.offsets[c][r + 1] - C.offsets[c][r], C.delim, C.quote);
+        else if (C.types[c] == TPLX_T_F64)
+            p += csv_f64_fixed8(*reinterpret_cast<const double *>(&C.data[c][r]), p);
         else if (C.types[c] == TPLX_T_BOOL) {
             const char *t = C.data[c][r] ? "true" : "false";
             while (*t) *p++ = (uint8_t)*t++;

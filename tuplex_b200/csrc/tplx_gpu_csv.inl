@@ -348,8 +348,6 @@ extern "C" int32_t tplx_gpu_result_csv(tplx_result *r, uint32_t n_cols, uint8_t 
     C.quote = quotechar;
     for (uint32_t c = 0; c < C.n_cols; ++c) {
         C.types[c] = r->out_types[c];
-        if (C.types[c] == TPLX_T_F64)
-            return fail(TPLX_E_UNSUPPORTED, "result_csv: f64 columns (ryu d2fixed) are formatted on the host");
         C.data[c] = r->out[c].data;
         C.offsets[c] = r->out[c].offsets;
         C.bytes[c] = r->out[c].bytes;
@@ -368,12 +366,17 @@ extern "C" int32_t tplx_gpu_result_csv(tplx_result *r, uint32_t n_cols, uint8_t 
     uint64_t *sizes = nullptr;
     CU(T.alloc(&sizes, n + 1));
     const uint32_t nb = (uint32_t)((n + CSV_NT - 1) / CSV_NT);
-    csv_sink_sizes<<<nb, CSV_NT, 0, d->stream>>>(C, n, sizes);
+    uint32_t *d_unsup = nullptr, h_unsup = 0;
+    CU(T.alloc(&d_unsup, 4));
+    CU(cudaMemsetAsync(d_unsup, 0, 16, d->stream));
+    csv_sink_sizes<<<nb, CSV_NT, 0, d->stream>>>(C, n, sizes, d_unsup);
     rc = device_scan(d, sizes, sizes, n, true);
     if (rc) return rc;
     uint64_t total = 0;
     CU(cudaMemcpyAsync(&total, sizes + n, 8, cudaMemcpyDeviceToHost, d->stream));
+    CU(cudaMemcpyAsync(&h_unsup, d_unsup, 4, cudaMemcpyDeviceToHost, d->stream));
     CU(cudaStreamSynchronize(d->stream));
+    if (h_unsup) return fail(TPLX_E_UNSUPPORTED, "result_csv: an f64 value of magnitude >= 2^63 needs the host formatter");
     *bytes_needed = total;
     if (!buf) return TPLX_OK;
     if (buf_bytes < total) return fail(TPLX_E_BADARG, "result_csv: buffer too small");

@@ -188,7 +188,7 @@ def _csv_cell(v, null_value=None) -> str:
         return "true" if v else "false"
     if isinstance(v, float):
         if v != v:
-            return "NaN"
+            return "nan"
         if v in (float("inf"), float("-inf")):
             return "Infinity" if v > 0 else "-Infinity"
         return "%.8f" % v
