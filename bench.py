@@ -28,7 +28,7 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="zillow", choices=["zillow", "q6", "c1", "aggbykey", "zillow_csv"])
+    ap.add_argument("--workload", default="zillow", choices=["zillow", "q6", "c1", "aggbykey", "zillow_csv", "q6_csv"])
     ap.add_argument("--rows", type=int, default=0, help="rows per GPU (default: 100M zillow / 600M q6 / 1e6*100 c1)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
@@ -250,6 +250,38 @@ def cpu_zillow_csv_reference(sample_rows: int, procs: int):
                        f"benchmarks/zillow/Z1/baseline/zillow.cpp; slowest process {max(ns) * 1e-6:.1f} ms")
 
 
+def _q6_csv_worker(path):
+    import time as _t
+    from oracle import pyoracle
+    from tuplex_b200 import ir
+    data = open(path, "rb").read()
+    t0 = _t.perf_counter()
+    r = pyoracle.csv_parse(data, [ir.T_I64, ir.T_F64, ir.T_F64, ir.T_I64], delimiter="|", header=False)
+    v = pyoracle.q6(*r.columns)
+    return _t.perf_counter() - t0, r.n_rows, v
+
+
+def cpu_q6_csv_port(sample_rows: int, procs: int):
+    """CPU arm of q6_csv (kind 'port'): oracle/csv_oracle.c (csvmonkey restatement + fast_atoi64 / fast_atod) followed by
+    oracle/workloads.c's Q6 loop, one process per host core over the same text (the reference's own LLVM path cannot be
+    built here; its C++ Q6 baseline needs weld.h)."""
+    import multiprocessing as mp
+    from tuplex_b200 import workloads as W
+    n = max(100_000, min(sample_rows, 2_000_000))
+    q, p_, d_, s_ = (c.data for c in W.gen_lineitem(n, seed=42))
+    td = tempfile.mkdtemp(prefix="tplx_cpu_")
+    path = os.path.join(td, "lineitem.tbl")
+    with open(path, "wb") as fp:
+        fp.write(b"\n".join(b"%d|%.2f|%.2f|%d" % (int(a), float(b), float(c), int(e)) for a, b, c, e in zip(q, p_, d_, s_)) + b"\n")
+    with mp.get_context("fork").Pool(procs) as pool:
+        res = pool.map(_q6_csv_worker, [path] * procs)
+    subprocess.call(["rm", "-rf", td])
+    slow = max(r[0] for r in res)
+    return dict(value=procs * n / slow, unit="rows/s", cores=procs, kind="port", rows_total=procs * n,
+                sample=f"{procs} processes x {n} rows of '|'-separated text: oracle/csv_oracle.c parse + oracle/workloads.c Q6 loop; "
+                       f"slowest process {slow * 1e3:.1f} ms")
+
+
 def cpu_port(wl, sample_rows: int, threads: int):
     """oracle port (kind 'port') on a bounded sample."""
     from oracle import pyoracle
@@ -301,7 +333,7 @@ def main():
         wl_args = types.SimpleNamespace(**vars(args))
         wl_args.rows = min(args.rows or 10**9, 2_000_000) if args.workload != "q6" else min(args.rows or 10**9, 100_000_000)
         wl = None
-        if args.workload not in ("zillow", "zillow_csv"):
+        if args.workload not in ("zillow", "zillow_csv", "q6_csv"):
             os.environ.setdefault("CUDA_VISIBLE_DEVICES", "")
             wl = build_workload_nopin(wl_args)
         vals = []
@@ -309,6 +341,7 @@ def main():
         for i in range(args.warmup + args.steps):
             last = cpu_zillow_reference(args.cpu_sample_rows, os.cpu_count() or 1) if args.workload == "zillow" else \
                 cpu_zillow_csv_reference(args.cpu_sample_rows, os.cpu_count() or 1) if args.workload == "zillow_csv" else \
+                cpu_q6_csv_port(args.cpu_sample_rows, os.cpu_count() or 1) if args.workload == "q6_csv" else \
                 cpu_port(wl, args.cpu_sample_rows, os.cpu_count() or 1)
             if last is None:
                 print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/zillow_ref missing and no port for this workload"}))
@@ -316,7 +349,7 @@ def main():
             if i >= args.warmup:
                 vals.append(last["value"])
         v = float(np.mean(vals))
-        names = {"zillow": "zillow_z1", "q6": "tpch_q6", "c1": "c1_map_filter", "aggbykey": "aggbykey_str", "zillow_csv": "zillow_z1_from_csv"}
+        names = {"zillow": "zillow_z1", "q6": "tpch_q6", "c1": "c1_map_filter", "aggbykey": "aggbykey_str", "zillow_csv": "zillow_z1_from_csv", "q6_csv": "tpch_q6_from_csv"}
         line = {"metric": "rows/sec on Zillow pipeline + TPC-H Q6" if args.workload in ("zillow", "q6") else "rows/sec",
                 "impl": "reference", "value": v, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": (last["rows_total"] / v * 1e3) if last.get("rows_total") else None, "higher_is_better": True,
@@ -327,7 +360,7 @@ def main():
         print(json.dumps(line))
         return 0
 
-    if args.workload == "zillow_csv":
+    if args.workload in ("zillow_csv", "q6_csv"):
         return main_csv(args, rank, world, local)
     import torch
     torch.cuda.set_device(local)
@@ -537,20 +570,53 @@ def main_csv(args, rank, world, local):
     from tuplex_b200 import backend, ir, workloads as W
     from concurrent.futures import ThreadPoolExecutor
     backend.init([local])
-    with gzip.open(os.path.join(ROOT, "tests", "golden", "zillow_noexc.csv.gz"), "rb") as fp:
-        raw = fp.read()
-    header, body = raw.split(b"\n", 1)
-    n0 = body.count(b"\n")
-    total = args.rows or 32_661_000
-    cycles = 250
-    bn = cycles * n0
-    n_blocks = max(1, total // bn)
-    total = n_blocks * bn
-    text = np.frombuffer(header + b"\n" + body * cycles, dtype=np.uint8)
+    S, F, I, X = ir.T_STR, ir.T_F64, ir.T_I64, backend.CSV_SKIP
+    if args.workload == "zillow_csv":
+        with gzip.open(os.path.join(ROOT, "tests", "golden", "zillow_noexc.csv.gz"), "rb") as fp:
+            raw = fp.read()
+        header, body = raw.split(b"\n", 1)
+        n0 = body.count(b"\n")
+        total = args.rows or 32_661_000
+        cycles = 125
+        bn = cycles * n0
+        n_blocks = max(1, total // bn)
+        total = n_blocks * bn
+        text = np.frombuffer(header + b"\n" + body * cycles, dtype=np.uint8)
+        types, has_header, delim = [S, S, S, S, F, S, S, X, S, X], True, ","
+        prog = W.zillow_program()
+        expect_out = 577 * cycles * n_blocks
+        name = "zillow_z1_from_csv"
+        desc = (f"Zillow Z1 from raw CSV text: {total} rows = {n_blocks} buffers of {cycles} cycles of the reference's 10-column "
+                f"zillow_noexc.csv (header + quoted cells), parsed on the device (8 of 10 columns, projection pushdown) and fed to the Z1 stage")
+        expect_agg = None
+    else:
+        # TPC-H Q6 in the reference benchmark's own end-to-end form (benchmarks/tpch/Q06/runtuplex.py:96-99, --preprocessed):
+        # '|'-separated text of l_quantity|l_extendedprice|l_discount|l_shipdate, no header, parse + 3 filters + sum
+        n0 = 2_000_000
+        cols = W.gen_lineitem(n0, seed=42)
+        q, p_, d_, s_ = (c.data for c in cols)
+        lines = [b"%d|%.2f|%.2f|%d" % (int(a), float(b), float(c), int(e)) for a, b, c, e in zip(q, p_, d_, s_)]
+        body = b"\n".join(lines) + b"\n"
+        total = args.rows or 600_000_000
+        cycles = max(1, (1 << 30) // len(body))  # ~1 GiB per buffer
+        bn = cycles * n0
+        n_blocks = max(1, total // bn)
+        total = n_blocks * bn
+        text = np.frombuffer(body * cycles, dtype=np.uint8)
+        types, has_header, delim = [I, F, F, I], False, "|"
+        prog = W.q6_program()
+        expect_out = None
+        name = "tpch_q6_from_csv"
+        desc = (f"TPC-H Q6 from '|'-separated text (the reference benchmark's --preprocessed end-to-end form): {total} rows = {n_blocks} "
+                f"buffers of {cycles} cycles of 2,000,000 generated lineitem rows (4 columns, 2-decimal prices and discounts), parsed on the "
+                f"device (fast_atoi64 / fast_atod) and reduced by the fused scan-aggregate; published reference, end-to-end from the full "
+                f"16-column .tbl at SF10 on 16 threads of an r5d.8xlarge: 37 M rows/s (BASELINE.md)")
+        # expected aggregate: the stage over the generator's own binary columns, summed per cycle like the blocks below
+        from oracle import pyoracle
+        expect_agg = pyoracle.q6(q, p_, d_, s_)
     host, keep = pinned(text)
-    S, F, X = ir.T_STR, ir.T_F64, backend.CSV_SKIP
-    types = [S, S, S, S, F, S, S, X, S, X]
-    st = backend.Stage(W.zillow_program())
+    st = backend.Stage(prog)
+    is_agg = prog.endpoint == ir.C["TPLX_EP_AGGREGATE"]
     bufs = [backend.CsvBuffer(local, host) for _ in range(n_blocks)]  # distinct HBM buffers, each >> L2
     torch.cuda.synchronize()
     pool = ThreadPoolExecutor(max_workers=3)
@@ -562,11 +628,14 @@ def main_csv(args, rank, world, local):
             dist.barrier()
 
     def run_block(buf, fetch):
-        p = buf.parse(types, header=True)
+        p = buf.parse(types, delimiter=delim, header=has_header)
         r = st.run(p.block, 0)
         inf, pinf = r.info, p.info
         nb = 0
-        if fetch:
+        if is_agg:
+            stats["agg"] = ir.bits_f64(r.aggregate_bits()[0])
+            nb = 8
+        elif fetch:
             for c in r.columns():
                 nb += c.nbytes()
         out = (float(pinf.parse_ms), float(inf.kernel_ms), int(pinf.kernel_launches) + int(inf.kernel_launches), int(inf.n_out_rows),
@@ -595,7 +664,9 @@ def main_csv(args, rank, world, local):
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
-    assert stats["rows"] == total and stats["bad"] == 0 and stats["n_out"] == 577 * cycles * n_blocks, stats
+    assert stats["rows"] == total and stats["bad"] == 0 and (expect_out is None or stats["n_out"] == expect_out), stats
+    if expect_agg is not None:  # one buffer = `cycles` copies of the generated rows
+        assert abs(stats["agg"] - cycles * expect_agg) <= 1e-9 * abs(cycles * expect_agg), (stats["agg"], cycles * expect_agg)
     clocks = Clocks(local)
     sync_all()
     clocks.start()
@@ -634,10 +705,8 @@ def main_csv(args, rank, world, local):
         line = {"metric": "rows/sec on Zillow pipeline + TPC-H Q6", "value": rows_all / (dt / args.steps), "unit": "rows/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8/i64/f64", "data": "synthetic",
-                "config": {"workload": "zillow_z1_from_csv", "rows_per_gpu": total, "blocks": n_blocks, "csv_bytes_per_gpu": csv_bytes,
-                           "description": f"Zillow Z1 from raw CSV text: {total} rows = {n_blocks} buffers of {cycles} cycles of the reference's "
-                                          f"10-column zillow_noexc.csv (header + quoted cells), parsed on the device (8 of 10 columns, "
-                                          f"projection pushdown) and fed to the Z1 stage",
+                "config": {"workload": name, "rows_per_gpu": total, "blocks": n_blocks, "csv_bytes_per_gpu": csv_bytes,
+                           "description": desc,
                            "l2": "inputs larger than L2 (every buffer >> 126 MB, distinct HBM buffers)", "out_rows_per_gpu": stats["n_out"]},
                 "clocks": clk,
                 "e2e": {"value": rows_all / (dt_e2e / e2e_steps), "unit": "rows/s", "h2d_bytes_per_step": csv_bytes,
@@ -648,12 +717,13 @@ def main_csv(args, rank, world, local):
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              # dram__bytes_read + dram__bytes_write of the six K6 kernels per parse, ncu --set full (profiles/r01_csv_k6.md:
                              # 5.47 GB for 804.1 MB of text), scaled to this buffer size
-                             "traffic": 5.47e9 / 804.1e6 * int(text.size), "peak_source": peak_src,
+                             "traffic": (5.47e9 / 804.1e6 * int(text.size)) if args.workload == "zillow_csv" else None, "peak_source": peak_src,
                              "algorithmic_bytes_per_row": alg / total, "kernel_ms_per_launch": parse_ms_step / n_blocks,
                              "kernel_share_of_step": parse_ms_step / ms_step, "stage_ms_per_step": sms / args.steps,
                              "csv_gb_per_s": csv_bytes / (parse_ms_step * 1e-3) / 1e9}}
         if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_zillow_csv_reference(args.cpu_sample_rows, os.cpu_count() or 1)
+            line["cpu_baseline"] = cpu_zillow_csv_reference(args.cpu_sample_rows, os.cpu_count() or 1) if args.workload == "zillow_csv" \
+                else cpu_q6_csv_port(args.cpu_sample_rows, os.cpu_count() or 1)
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
