@@ -195,6 +195,37 @@ TPLX_HD void csv_trim(const uint8_t *p, uint32_t len, uint32_t *pi, uint32_t *pe
     *pe = e;
 }
 
+// (double)d / 10^k for d = 0..9, k = 1..22, computed exactly as fast_atod does at run time (pow10 = 10.0; pow10 *= 10.0 per
+// digit — exact up to 10^22 — and one IEEE division): the quotients are fixed doubles, so the device reads them instead of
+// dividing (an f64 division costs tens of instructions). Generated by a 6-line Python loop (float.hex of d / pow10).
+#define CSV_FRAC_KMAX 22
+#ifdef __CUDA_ARCH__
+__device__
+#endif
+static const double csv_frac_tab[CSV_FRAC_KMAX * 10] = {
+    0x0p+0, 0x1.999999999999ap-4, 0x1.999999999999ap-3, 0x1.3333333333333p-2, 0x1.999999999999ap-2, 0x1.0000000000000p-1, 0x1.3333333333333p-1, 0x1.6666666666666p-1, 0x1.999999999999ap-1, 0x1.ccccccccccccdp-1,
+    0x0p+0, 0x1.47ae147ae147bp-7, 0x1.47ae147ae147bp-6, 0x1.eb851eb851eb8p-6, 0x1.47ae147ae147bp-5, 0x1.999999999999ap-5, 0x1.eb851eb851eb8p-5, 0x1.1eb851eb851ecp-4, 0x1.47ae147ae147bp-4, 0x1.70a3d70a3d70ap-4,
+    0x0p+0, 0x1.0624dd2f1a9fcp-10, 0x1.0624dd2f1a9fcp-9, 0x1.89374bc6a7efap-9, 0x1.0624dd2f1a9fcp-8, 0x1.47ae147ae147bp-8, 0x1.89374bc6a7efap-8, 0x1.cac083126e979p-8, 0x1.0624dd2f1a9fcp-7, 0x1.26e978d4fdf3bp-7,
+    0x0p+0, 0x1.a36e2eb1c432dp-14, 0x1.a36e2eb1c432dp-13, 0x1.3a92a30553261p-12, 0x1.a36e2eb1c432dp-12, 0x1.0624dd2f1a9fcp-11, 0x1.3a92a30553261p-11, 0x1.6f0068db8bac7p-11, 0x1.a36e2eb1c432dp-11, 0x1.d7dbf487fcb92p-11,
+    0x0p+0, 0x1.4f8b588e368f1p-17, 0x1.4f8b588e368f1p-16, 0x1.f75104d551d69p-16, 0x1.4f8b588e368f1p-15, 0x1.a36e2eb1c432dp-15, 0x1.f75104d551d69p-15, 0x1.2599ed7c6fbd2p-14, 0x1.4f8b588e368f1p-14, 0x1.797cc39ffd60fp-14,
+    0x0p+0, 0x1.0c6f7a0b5ed8dp-20, 0x1.0c6f7a0b5ed8dp-19, 0x1.92a737110e454p-19, 0x1.0c6f7a0b5ed8dp-18, 0x1.4f8b588e368f1p-18, 0x1.92a737110e454p-18, 0x1.d5c31593e5fb7p-18, 0x1.0c6f7a0b5ed8dp-17, 0x1.2dfd694ccab3fp-17,
+    0x0p+0, 0x1.ad7f29abcaf48p-24, 0x1.ad7f29abcaf48p-23, 0x1.421f5f40d8376p-22, 0x1.ad7f29abcaf48p-22, 0x1.0c6f7a0b5ed8dp-21, 0x1.421f5f40d8376p-21, 0x1.77cf44765195fp-21, 0x1.ad7f29abcaf48p-21, 0x1.e32f0ee144531p-21,
+    0x0p+0, 0x1.5798ee2308c3ap-27, 0x1.5798ee2308c3ap-26, 0x1.01b2b29a4692bp-25, 0x1.5798ee2308c3ap-25, 0x1.ad7f29abcaf48p-25, 0x1.01b2b29a4692bp-24, 0x1.2ca5d05ea7ab3p-24, 0x1.5798ee2308c3ap-24, 0x1.828c0be769dc1p-24,
+    0x0p+0, 0x1.12e0be826d695p-30, 0x1.12e0be826d695p-29, 0x1.9c511dc3a41dfp-29, 0x1.12e0be826d695p-28, 0x1.5798ee2308c3ap-28, 0x1.9c511dc3a41dfp-28, 0x1.e1094d643f784p-28, 0x1.12e0be826d695p-27, 0x1.353cd652bb167p-27,
+    0x0p+0, 0x1.b7cdfd9d7bdbbp-34, 0x1.b7cdfd9d7bdbbp-33, 0x1.49da7e361ce4cp-32, 0x1.b7cdfd9d7bdbbp-32, 0x1.12e0be826d695p-31, 0x1.49da7e361ce4cp-31, 0x1.80d43de9cc603p-31, 0x1.b7cdfd9d7bdbbp-31, 0x1.eec7bd512b572p-31,
+    0x0p+0, 0x1.5fd7fe1796495p-37, 0x1.5fd7fe1796495p-36, 0x1.07e1fe91b0b70p-35, 0x1.5fd7fe1796495p-35, 0x1.b7cdfd9d7bdbbp-35, 0x1.07e1fe91b0b70p-34, 0x1.33dcfe54a3803p-34, 0x1.5fd7fe1796495p-34, 0x1.8bd2fdda89128p-34,
+    0x0p+0, 0x1.19799812dea11p-40, 0x1.19799812dea11p-39, 0x1.a636641c4df1ap-39, 0x1.19799812dea11p-38, 0x1.5fd7fe1796495p-38, 0x1.a636641c4df1ap-38, 0x1.ec94ca210599ep-38, 0x1.19799812dea11p-37, 0x1.3ca8cb153a753p-37,
+    0x0p+0, 0x1.c25c268497682p-44, 0x1.c25c268497682p-43, 0x1.51c51ce3718e1p-42, 0x1.c25c268497682p-42, 0x1.19799812dea11p-41, 0x1.51c51ce3718e1p-41, 0x1.8a10a1b4047b2p-41, 0x1.c25c268497682p-41, 0x1.faa7ab552a552p-41,
+    0x0p+0, 0x1.6849b86a12b9bp-47, 0x1.6849b86a12b9bp-46, 0x1.0e374a4f8e0b4p-45, 0x1.6849b86a12b9bp-45, 0x1.c25c268497682p-45, 0x1.0e374a4f8e0b4p-44, 0x1.3b40815cd0628p-44, 0x1.6849b86a12b9bp-44, 0x1.9552ef775510ep-44,
+    0x0p+0, 0x1.203af9ee75616p-50, 0x1.203af9ee75616p-49, 0x1.b05876e5b0120p-49, 0x1.203af9ee75616p-48, 0x1.6849b86a12b9bp-48, 0x1.b05876e5b0120p-48, 0x1.f86735614d6a6p-48, 0x1.203af9ee75616p-47, 0x1.4442592c440d8p-47,
+    0x0p+0, 0x1.cd2b297d889bcp-54, 0x1.cd2b297d889bcp-53, 0x1.59e05f1e2674dp-52, 0x1.cd2b297d889bcp-52, 0x1.203af9ee75616p-51, 0x1.59e05f1e2674dp-51, 0x1.9385c44dd7885p-51, 0x1.cd2b297d889bcp-51, 0x1.036847569cd7ap-50,
+    0x0p+0, 0x1.70ef54646d497p-57, 0x1.70ef54646d497p-56, 0x1.14b37f4b51f71p-55, 0x1.70ef54646d497p-55, 0x1.cd2b297d889bcp-55, 0x1.14b37f4b51f71p-54, 0x1.42d169d7dfa04p-54, 0x1.70ef54646d497p-54, 0x1.9f0d3ef0faf29p-54,
+    0x0p+0, 0x1.2725dd1d243acp-60, 0x1.2725dd1d243acp-59, 0x1.bab8cbabb6581p-59, 0x1.2725dd1d243acp-58, 0x1.70ef54646d497p-58, 0x1.bab8cbabb6581p-58, 0x1.024121797fb36p-57, 0x1.2725dd1d243acp-57, 0x1.4c0a98c0c8c21p-57,
+    0x0p+0, 0x1.d83c94fb6d2acp-64, 0x1.d83c94fb6d2acp-63, 0x1.622d6fbc91e01p-62, 0x1.d83c94fb6d2acp-62, 0x1.2725dd1d243acp-61, 0x1.622d6fbc91e01p-61, 0x1.9d35025bff857p-61, 0x1.d83c94fb6d2acp-61, 0x1.09a213cd6d681p-60,
+    0x0p+0, 0x1.79ca10c924223p-67, 0x1.79ca10c924223p-66, 0x1.1b578c96db19bp-65, 0x1.79ca10c924223p-65, 0x1.d83c94fb6d2acp-65, 0x1.1b578c96db19bp-64, 0x1.4a90ceafff9dfp-64, 0x1.79ca10c924223p-64, 0x1.a90352e248a68p-64,
+    0x0p+0, 0x1.2e3b40a0e9b4fp-70, 0x1.2e3b40a0e9b4fp-69, 0x1.c558e0f15e8f7p-69, 0x1.2e3b40a0e9b4fp-68, 0x1.79ca10c924223p-68, 0x1.c558e0f15e8f7p-68, 0x1.0873d88ccc7e6p-67, 0x1.2e3b40a0e9b4fp-67, 0x1.5402a8b506eb9p-67,
+    0x0p+0, 0x1.e392010175ee6p-74, 0x1.e392010175ee6p-73, 0x1.6aad80c11872cp-72, 0x1.e392010175ee6p-72, 0x1.2e3b40a0e9b4fp-71, 0x1.6aad80c11872cp-71, 0x1.a71fc0e147309p-71, 0x1.e392010175ee6p-71, 0x1.10022090d2561p-70};
+
 // fast_atod (StringUtils.cc:71-163) behind the runtime wrapper's trim; false = ValueError.
 // The accumulation is the reference's own (not correctly rounded): value = 10*value + d; value += d / pow10.
 TPLX_HD bool csv_atod(const uint8_t *s, uint32_t len, double *out) {
@@ -215,10 +246,16 @@ TPLX_HD bool csv_atod(const uint8_t *s, uint32_t len, double *out) {
     for (; (uint8_t)(CH(p) - '0') <= 9; ++p) value = TPLX_DADD(TPLX_DMUL(10.0, value), (double)(CH(p) - '0'));
     if (CH(p) == '.') {
         double pow10 = 10.0;
+        uint32_t k = 0;  // fraction digits seen
         ++p;
         while ((uint8_t)(CH(p) - '0') <= 9) {
-            value = TPLX_DADD(value, TPLX_DDIV((double)(CH(p) - '0'), pow10));
+            const uint32_t d = (uint32_t)(CH(p) - '0');
+            if (k < CSV_FRAC_KMAX)
+                value = TPLX_DADD(value, csv_frac_tab[k * 10 + d]);
+            else
+                value = TPLX_DADD(value, TPLX_DDIV((double)d, pow10));
             pow10 = TPLX_DMUL(pow10, 10.0);
+            ++k;
             ++p;
         }
     }
