@@ -23,7 +23,7 @@ HostCsv *hcsv_parse(const uint8_t *data, uint32_t n, uint8_t delim, uint8_t quot
                     const uint8_t *col_types, uint32_t n_nulls, const char *const *nulls) {
     HostCsv *H = new HostCsv();
     const uint64_t padded = ((uint64_t)n + 1 + CSV_SPAN - 1) / CSV_SPAN * CSV_SPAN;
-    std::vector<uint8_t> buf(padded + 16, 0);
+    std::vector<uint8_t> buf(padded + 64, 0);
     memcpy(buf.data(), data, n);
     buf[n] = '\n';
     const uint32_t n_spans = (uint32_t)(padded / CSV_SPAN);

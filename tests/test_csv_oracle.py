@@ -280,3 +280,32 @@ def test_sink_f64_fixed8_exact():
     small = [v for v in vals if v != v or abs(v) == float("inf") or abs(v) < 2.0**63]
     cols = _cols_from([small], [T_F64])
     assert host_csv_write(cols, len(small)) == po.csv_write(cols, len(small))
+
+
+def test_numeric_cells_decode_fuzz():
+    """numeric / bool cells through the register-resident cell path (<= 32 bytes), the memory path (longer cells) and the
+    dequoting path (escaped cells), all against the oracle"""
+    rng = random.Random(77)
+
+    def cell():
+        r = rng.random()
+        if r < 0.3:
+            return str(rng.randint(-10**18, 10**18))
+        if r < 0.5:
+            return f"{rng.uniform(-1e9, 1e9):.{rng.randint(0, 17)}f}"
+        if r < 0.6:
+            return " " * rng.randint(0, 20) + str(rng.randint(0, 99999)) + "\t" * rng.randint(0, 20)
+        if r < 0.7:
+            return "0" * rng.randint(25, 60) + str(rng.randint(0, 9))
+        if r < 0.8:
+            return '"' + str(rng.randint(0, 999)) + '"'
+        if r < 0.85:
+            return '"1""2"'
+        if r < 0.9:
+            return rng.choice(["true", "F", "yes", "No", "nan", "inf", "1e5", "-", "+3", ""])
+        return rng.choice(["abc", "1.2.3", "--1", "9" * 40])
+    for it in range(400):
+        types = [rng.choice([I, F, B]) for _ in range(rng.randint(1, 5))]
+        rows = [",".join(cell() for _ in types) for _ in range(rng.randint(1, 40))]
+        data = ("\n".join(rows) + "\n").encode()
+        assert_same_parse(host_parse(data, types), po.csv_parse(data, types), what=data[:100])

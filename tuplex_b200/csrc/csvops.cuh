@@ -183,17 +183,43 @@ TPLX_HD bool csv_cell_equals(const uint8_t *buf, uint32_t b, uint32_t e, bool es
 }
 
 // whitespace trimming shared by the runtime wrappers (Runtime.cc:319-341,343-365): [i, e) of p[0..len)
-TPLX_HD void csv_trim(const uint8_t *p, uint32_t len, uint32_t *pi, uint32_t *pe) {
+// The decoders read the cell through an accessor get(k) -> byte k, so that the same code runs over memory (host tests,
+// escaped cells) and over a cell held in registers (CsvCell32 below).
+template <class G>
+TPLX_HD void csv_trim_g(G &&get, uint32_t len, uint32_t *pi, uint32_t *pe) {
     uint32_t i = 0, e = len;
-    while (i < e && is_pyspace(p[i])) ++i;
+    while (i < e && is_pyspace(get(i))) ++i;
     if (e > i) {
         uint32_t e2 = e - 1;
-        while (e2 > i && is_pyspace(p[e2])) --e2;
+        while (e2 > i && is_pyspace(get(e2))) --e2;
         e = e2 + 1;
     }
     *pi = i;
     *pe = e;
 }
+
+// A cell of at most 32 bytes in four registers: five independent aligned loads instead of one dependent byte load per
+// character (csv_parse_rows was latency-bound on those, profiles/r01_csv_k6.md).
+struct CsvCell32 {
+    uint64_t w0, w1, w2, w3;
+    TPLX_HD void load(const uint8_t *buf, uint32_t b) {
+        const uint32_t base = b & ~7u, sh = (b & 7u) * 8;
+        const uint64_t a0 = csv_load8(buf + base), a1 = csv_load8(buf + base + 8), a2 = csv_load8(buf + base + 16),
+                       a3 = csv_load8(buf + base + 24), a4 = csv_load8(buf + base + 32);
+        if (sh) {
+            w0 = (a0 >> sh) | (a1 << (64 - sh));
+            w1 = (a1 >> sh) | (a2 << (64 - sh));
+            w2 = (a2 >> sh) | (a3 << (64 - sh));
+            w3 = (a3 >> sh) | (a4 << (64 - sh));
+        } else {
+            w0 = a0, w1 = a1, w2 = a2, w3 = a3;
+        }
+    }
+    TPLX_HD uint8_t get(uint32_t k) const {  // k < 32
+        const uint64_t w = k < 16 ? (k < 8 ? w0 : w1) : (k < 24 ? w2 : w3);
+        return (uint8_t)(w >> (8 * (k & 7)));
+    }
+};
 
 // (double)d / 10^k for d = 0..9, k = 1..22, computed exactly as fast_atod does at run time (pow10 = 10.0; pow10 *= 10.0 per
 // digit — exact up to 10^22 — and one IEEE division): the quotients are fixed doubles, so the device reads them instead of
@@ -228,13 +254,14 @@ static const double csv_frac_tab[CSV_FRAC_KMAX * 10] = {
 
 // fast_atod (StringUtils.cc:71-163) behind the runtime wrapper's trim; false = ValueError.
 // The accumulation is the reference's own (not correctly rounded): value = 10*value + d; value += d / pow10.
-TPLX_HD bool csv_atod(const uint8_t *s, uint32_t len, double *out) {
+template <class G>
+TPLX_HD bool csv_atod_g(G &&get, uint32_t len, double *out) {
     uint32_t i0, e;
-    csv_trim(s, len, &i0, &e);
+    csv_trim_g(get, len, &i0, &e);
     if (i0 == e) return false;
     // bytes at or past e never match a digit, sign, '.', 'e' or a letter of nan/infinity in the reference either
     // (there it is whitespace or the terminator), so they read as 0 here
-#define CH(k) ((k) < e ? s[(k)] : (uint8_t)0)
+#define CH(k) ((k) < e ? get(k) : (uint8_t)0)
     uint32_t p = i0;
     double sign = 1.0;
     if (CH(p) == '-') {
@@ -313,11 +340,39 @@ TPLX_HD bool csv_atod(const uint8_t *s, uint32_t len, double *out) {
     return true;
 }
 
+TPLX_HD bool csv_atod(const uint8_t *s, uint32_t len, double *out) {
+    return csv_atod_g([s](uint32_t k) { return s[k]; }, len, out);
+}
+
+// fast_atoi64 (StringUtils.cc:22-63) behind the runtime wrapper's trim (Runtime.cc:319-341); accessor twin of str_to_i64
+template <class G>
+TPLX_HD bool csv_atoi64_g(G &&get, uint32_t len, int64_t *out) {
+    uint32_t i, e;
+    csv_trim_g(get, len, &i, &e);
+    if (i == e) return false;
+    bool neg = false;
+    if (get(i) == '-') {
+        neg = true;
+        ++i;
+    }
+    uint64_t x = 0;
+    while (i < len) {  // like str_to_i64: digits may run up to the end of the cell, then the position must equal e
+        const uint8_t d = (uint8_t)(get(i) - '0');
+        if (d > 9) break;
+        x = x * 10 + d;
+        ++i;
+    }
+    if (i != e) return false;
+    *out = (int64_t)(neg ? (uint64_t)0 - x : x);
+    return true;
+}
+
 // fast_atob (StringUtils.cc:180-255): no trimming; t/y/f/n, no, yes, true, false — case-insensitive
-TPLX_HD bool csv_atob(const uint8_t *s, uint32_t len, int64_t *out) {
+template <class G>
+TPLX_HD bool csv_atob_g(G &&get, uint32_t len, int64_t *out) {
     uint8_t b[5];
     if (len == 0 || len > 5) return false;
-    for (uint32_t i = 0; i < len; ++i) b[i] = case1(s[i], TPLX_SF_LOWER);
+    for (uint32_t i = 0; i < len; ++i) b[i] = case1(get(i), TPLX_SF_LOWER);
     switch (len) {
         case 1:
             if (b[0] == 'y' || b[0] == 't') {
@@ -356,6 +411,10 @@ TPLX_HD bool csv_atob(const uint8_t *s, uint32_t len, int64_t *out) {
     }
 }
 
+TPLX_HD bool csv_atob(const uint8_t *s, uint32_t len, int64_t *out) {
+    return csv_atob_g([s](uint32_t k) { return s[k]; }, len, out);
+}
+
 // what a selected column needs from one cell
 struct CsvNulls {
     uint8_t n;
@@ -380,21 +439,42 @@ TPLX_HD bool csv_decode_scalar(const uint8_t *buf, uint32_t b, uint32_t e, bool 
         if (len > CSV_DEQ_CAP) return false;  // left to the interpreter path
         p = tmp;
     }
+    if (!escaped && len <= 32) {  // the common case: decode from registers
+        CsvCell32 cell;
+        cell.load(buf, b);
+        auto get = [&cell](uint32_t k) { return cell.get(k); };
+        if (type == TPLX_T_I64) {
+            int64_t v;
+            if (!csv_atoi64_g(get, len, &v)) return false;
+            *bits = (uint64_t)v;
+            return true;
+        }
+        if (type == TPLX_T_F64) {
+            double d;
+            if (!csv_atod_g(get, len, &d)) return false;
+            *bits = *reinterpret_cast<uint64_t *>(&d);
+            return true;
+        }
+        int64_t bv;
+        if (!csv_atob_g(get, len, &bv)) return false;
+        *bits = (uint64_t)bv;
+        return true;
+    }
+    auto getm = [p](uint32_t k) { return p[k]; };
     if (type == TPLX_T_I64) {
-        StrV s{p, len, 0};
         int64_t v;
-        if (!str_to_i64(s, &v)) return false;
+        if (!csv_atoi64_g(getm, len, &v)) return false;
         *bits = (uint64_t)v;
         return true;
     }
     if (type == TPLX_T_F64) {
         double d;
-        if (!csv_atod(p, len, &d)) return false;
+        if (!csv_atod_g(getm, len, &d)) return false;
         *bits = *reinterpret_cast<uint64_t *>(&d);
         return true;
     }
     int64_t bv;
-    if (!csv_atob(p, len, &bv)) return false;
+    if (!csv_atob_g(getm, len, &bv)) return false;
     *bits = (uint64_t)bv;
     return true;
 }

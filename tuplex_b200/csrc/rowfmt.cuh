@@ -31,7 +31,11 @@ __device__ __forceinline__ void st64u(uint8_t *p, uint64_t v) {
 
 // ---- generic exclusive scan over uint64 (three small kernels; boundary path, not the hot path) ---
 constexpr int SCAN_ITEMS = 2048;  // per block
-__global__ void scan_block_sums(const uint64_t *in, uint64_t *block_sums, uint64_t n) {
+// The three kernels also run batched: blockIdx.y selects one of several arrays laid out `stride` elements apart (its
+// block sums `sums_stride` apart), so K scans cost 3 launches instead of 3 K (used by the CSV source).
+__global__ void scan_block_sums(const uint64_t *in, uint64_t *block_sums, uint64_t n, uint64_t stride = 0, uint64_t sums_stride = 0) {
+    in += blockIdx.y * stride;
+    block_sums += blockIdx.y * sums_stride;
     __shared__ uint64_t s[RF_NT / 32];
     uint64_t base = (uint64_t)blockIdx.x * SCAN_ITEMS;
     uint64_t v = 0;
@@ -47,7 +51,8 @@ __global__ void scan_block_sums(const uint64_t *in, uint64_t *block_sums, uint64
     }
 }
 // single block: exclusive scan of block sums in place; total -> block_sums[n_blocks]
-__global__ void scan_of_sums(uint64_t *block_sums, uint32_t n_blocks) {
+__global__ void scan_of_sums(uint64_t *block_sums, uint32_t n_blocks, uint64_t sums_stride = 0) {
+    block_sums += blockIdx.y * sums_stride;
     __shared__ uint64_t s[1024 / 32];
     __shared__ uint64_t carry;
     if (threadIdx.x == 0) carry = 0;
@@ -72,7 +77,11 @@ __global__ void scan_of_sums(uint64_t *block_sums, uint32_t n_blocks) {
     if (threadIdx.x == 0) block_sums[n_blocks] = carry;
 }
 // out[i] = exclusive prefix (may alias in); out[n] = total when write_total
-__global__ void scan_downsweep(const uint64_t *in, uint64_t *out, const uint64_t *block_sums, uint64_t n, int write_total) {
+__global__ void scan_downsweep(const uint64_t *in, uint64_t *out, const uint64_t *block_sums, uint64_t n, int write_total,
+                               uint64_t stride = 0, uint64_t sums_stride = 0) {
+    in += blockIdx.y * stride;
+    out += blockIdx.y * stride;
+    block_sums += blockIdx.y * sums_stride;
     __shared__ uint64_t s[RF_NT / 32];
     const uint32_t per = SCAN_ITEMS / RF_NT;
     uint64_t base = (uint64_t)blockIdx.x * SCAN_ITEMS + (uint64_t)threadIdx.x * per;

@@ -28,9 +28,9 @@ extern "C" int32_t tplx_gpu_csv_upload(int32_t device, const void *bytes, uint64
     b->dev = d;
     b->n = n_bytes;
     b->padded = align_up(n_bytes + 1, CSV_TILE);
-    CU(cudaMallocAsync((void **)&b->d, b->padded + 16, d->copy_stream));
+    CU(cudaMallocAsync((void **)&b->d, b->padded + 64, d->copy_stream));  // slack: cells are read as whole 8-byte words
     if (n_bytes) CU(cudaMemcpyAsync(b->d, bytes, n_bytes, cudaMemcpyHostToDevice, d->copy_stream));
-    CU(cudaMemsetAsync(b->d + n_bytes, 0, b->padded + 16 - n_bytes, d->copy_stream));
+    CU(cudaMemsetAsync(b->d + n_bytes, 0, b->padded + 64 - n_bytes, d->copy_stream));
     CU(cudaMemsetAsync(b->d + n_bytes, '\n', 1, d->copy_stream));  // the newline VFCSVStreamCursor appends (CSVReader.cc:94-100)
     CU(cudaEventCreateWithFlags(&b->ready, cudaEventDisableTiming));
     CU(cudaEventRecord(b->ready, d->copy_stream));
@@ -175,8 +175,8 @@ extern "C" int32_t tplx_gpu_csv_parse(tplx_csv_buffer *cb, const tplx_csv_desc *
         P.col_slot = d_slot;
         P.flags = flags;
         for (uint32_t c = 0; c < P.n_out; ++c) CU(T.alloc(&P.tmp[c], nd));
-        CU(T.alloc(&P.lens, (size_t)std::max<uint32_t>(P.n_str, 1) * ((size_t)nd + 1)));
-        CU(T.alloc(&P.good, (size_t)nd + 1));
+        CU(T.alloc(&P.lens, ((size_t)P.n_str + 1) * ((size_t)nd + 1)));  // string lengths, then the good flags: one batched scan
+        P.good = P.lens + (size_t)P.n_str * ((size_t)nd + 1);
         CU(T.alloc(&P.code, nd));
         if (nd) {
             csv_parse_rows<<<(nd + CSV_NT - 1) / CSV_NT, CSV_NT, 0, st>>>(P);
@@ -184,13 +184,9 @@ extern "C" int32_t tplx_gpu_csv_parse(tplx_csv_buffer *cb, const tplx_csv_desc *
             CU(cudaGetLastError());
         }
         // output positions of the good rows and of their string bytes
-        int32_t rc = device_scan(d, P.good, P.good, nd, true);
+        int32_t rc = device_scan_batched(d, P.lens, (uint64_t)nd + 1, P.n_str + 1, nd);
         if (rc) return rc;
-        for (uint32_t k = 0; k < P.n_str; ++k) {
-            rc = device_scan(d, P.lens + (size_t)k * (nd + 1), P.lens + (size_t)k * (nd + 1), nd, true);
-            if (rc) return rc;
-        }
-        launches += 3 * (1 + P.n_str);
+        launches += 3;
         uint32_t h_flag = 0;
         CU(cudaMemcpyAsync(&h_flag, flags, 4, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(&n_good, P.good + nd, 8, cudaMemcpyDeviceToHost, st));

@@ -13,6 +13,21 @@ static int32_t device_scan(Device *d, const uint64_t *in, uint64_t *out, uint64_
     return TPLX_OK;
 }
 
+// K in-place exclusive scans (totals written at [n]) of arrays that lie `stride` elements apart: 3 launches in all
+static int32_t device_scan_batched(Device *d, uint64_t *arrays, uint64_t stride, uint32_t K, uint64_t n) {
+    if (K == 0) return TPLX_OK;
+    const uint32_t nb = (uint32_t)std::max<uint64_t>(1, (n + SCAN_ITEMS - 1) / SCAN_ITEMS);
+    uint64_t *sums = nullptr;
+    const uint64_t ss = nb + 1;
+    CU(cudaMallocAsync(&sums, ss * K * 8, d->stream));
+    scan_block_sums<<<dim3(nb, K), RF_NT, 0, d->stream>>>(arrays, sums, n, stride, ss);
+    scan_of_sums<<<dim3(1, K), 1024, 0, d->stream>>>(sums, nb, ss);
+    scan_downsweep<<<dim3(nb, K), RF_NT, 0, d->stream>>>(arrays, arrays, sums, n, 1, stride, ss);
+    CU(cudaGetLastError());
+    CU(cudaFreeAsync(sums, d->stream));
+    return TPLX_OK;
+}
+
 // Walk the rows of one partition on the host to find row starts. Row length is only known from the row
 // itself (fixed slots + optional var-len total), so this is inherently sequential per partition
 // (Deserializer::inferLength, Serializer.cc:1227-1284); it touches 8-16 bytes per row.
