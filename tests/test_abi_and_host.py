@@ -171,3 +171,13 @@ def test_csv_source_planning_and_chunking(tmp_path, monkeypatch):
     assert src.line_object(b"n/a,t,,x", False) == ("n/a", True, None, "x")
     hs = src.to_host_source()
     assert hs.n_rows + len(hs.fallback) == 400
+
+
+def test_csv_missing_file_gives_empty_dataset():
+    """tuplex/python/tests/test_csv.py:66-69 (test_non_existent_file): no exception, nothing to show"""
+    import tuplex_b200
+    ctx = tuplex_b200.Context()
+    ds = ctx.csv("/tmp/tplx_definitely_missing_file.ccc")
+    assert ds.collect() == []
+    ds.show()
+    assert any("no such file" in m for m in ctx._messages)

@@ -151,7 +151,11 @@ class Context:
         the GPU when the first stage runs (csvsource.CsvSource -> tplx_gpu_csv_parse)."""
         from . import csvsource as cs
         files = sorted(f for p in pattern.split(",") for f in (glob.glob(p) or [p]))
-        arrays = [np.fromfile(fn, dtype=np.uint8) for fn in files]
+        import os
+        missing = [fn for fn in files if not os.path.isfile(fn)]
+        for fn in missing:  # the reference logs the missing file and yields an empty dataset (python/tests/test_csv.py:66-69)
+            self._log(f"csv: no such file {fn!r}")
+        arrays = [np.fromfile(fn, dtype=np.uint8) for fn in files if fn not in missing]
         arrays = [a for a in arrays if a.size] or [np.zeros(0, np.uint8)]
         sample = arrays[0][: cs.SAMPLE_BYTES].tobytes()
         if len(sample) == cs.SAMPLE_BYTES:  # keep whole lines only
