@@ -171,6 +171,7 @@ enum tplx_op {
     /* row control */
     TPLX_OP_FILTER = 52, /* alive &= slot[a] != 0 (PipelineBuilder.cc:615-700) */
     TPLX_OP_RAISE = 53,  /* unconditional (guarded) exception imm = code */
+    TPLX_OP_S2F = 54,    /* float(s): fast_atod behind the runtime's trim (Runtime.cc:343-365, StringUtils.cc:71-163); ValueError */
 };
 
 /* 32-byte instruction */

@@ -470,6 +470,13 @@ static int eval_row(const ostage *S, const tplx_ocol *cols, uint64_t row, oval *
                 d->i = v;
                 break;
             }
+            case TPLX_OP_S2F: { /* float(str): the runtime's fast_atod wrapper (csv_oracle.c restates it) */
+                extern int csv_oracle_atod(const char *s, double *out);
+                double dv = 0;
+                if (csv_oracle_atod(a->s, &dv)) RAISE(TPLX_EC_VALUEERROR);
+                d->i = as_i(dv);
+                break;
+            }
             case TPLX_OP_FILTER: if (a->i == 0) return 1; break;
             case TPLX_OP_RAISE: RAISE(in->imm);
             default: *ec = -1; *opidx = in->opidx; return 2;

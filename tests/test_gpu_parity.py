@@ -312,3 +312,16 @@ def test_full_block_sizes_properties(gpu):
     o = pyoracle.run_program(q, lcols, m)
     assert r.aggregate_bits() == o.acc_tree
     assert abs(ir.bits_f64(o.acc_tree[0]) - ir.bits_f64(o.acc_seq[0])) <= 1e-9 * abs(ir.bits_f64(o.acc_seq[0]))
+
+
+def test_float_of_str_s2f(gpu):
+    """float(str) on the device (fast_atod semantics, lazy case flags on the view) vs the oracle, incl. ValueError rows"""
+    from test_float_cast import float_cases
+    vals = float_cases() + ["INF", "Nan", "1E5", " 7 "]
+    sc = frontend.StageCompiler([T_STR], ["s"])
+    sc.add_map(lambda x: (float(x["s"]) * 2.0, float(x["s"].lower()), float(x["s"].upper()) + 1.0), 100001)
+    prog = sc.finish_memory()
+    col = Column.from_values(vals, T_STR)
+    st, res, ora = run_both(prog, [col], len(vals))
+    assert len(ora.exceptions) > 5
+    assert_result_equals_oracle(res, ora, "float(str)")

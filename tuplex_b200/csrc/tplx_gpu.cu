@@ -260,7 +260,7 @@ extern "C" int32_t tplx_gpu_stage_create(const void *desc, uint64_t desc_bytes, 
                 break;
             default: break;
         }
-        if (in.op >= TPLX_OP_SLEN && in.op <= TPLX_OP_SSTRIP) {
+        if ((in.op >= TPLX_OP_SLEN && in.op <= TPLX_OP_SSTRIP) || in.op == TPLX_OP_S2F) {
             s->has_str = true;
             // constant string operands are constant-pool views (offset | length << 32)
             auto cs_ok = [&](int64_t enc) { return ((uint64_t)enc & 0xFFFFFFFFull) + ((uint64_t)enc >> 32) <= h.const_bytes; };

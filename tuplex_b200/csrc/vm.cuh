@@ -17,6 +17,7 @@
 #include <stdint.h>
 #include "../../include/tplx_ir.h"
 #include "strops.cuh"
+#include "csvops.cuh"
 
 namespace tplx {
 
@@ -390,6 +391,13 @@ struct VM {
                     int64_t v;
                     if (!str_to_i64(SA(), &v)) { raise_exc(t, TPLX_EC_VALUEERROR, opidx); break; }
                     R(rb, dst) = (uint64_t)v;
+                    break;
+                }
+                case TPLX_OP_S2F: {
+                    const StrV s = SA();
+                    double d;
+                    if (!csv_atod_g([&s](uint32_t k) { return sch(s, k); }, s.len, &d)) { raise_exc(t, TPLX_EC_VALUEERROR, opidx); break; }
+                    WF(d);
                     break;
                 }
                 case TPLX_OP_FILTER:

@@ -458,7 +458,7 @@ class StageCompiler:
         (FILTER) always stay, so exception behaviour is unchanged (the reference's LLVM -O2 removes the same dead
         code, tuplex/core/src/physical/LLVMOptimizer.cc:119-191)."""
         side = {C[k] for k in ("TPLX_OP_FILTER", "TPLX_OP_RAISE", "TPLX_OP_IFLOORDIV", "TPLX_OP_IMOD", "TPLX_OP_FDIV", "TPLX_OP_FMOD",
-                               "TPLX_OP_FFLOORDIV", "TPLX_OP_SINDEX", "TPLX_OP_S2I")}
+                               "TPLX_OP_FFLOORDIV", "TPLX_OP_SINDEX", "TPLX_OP_S2I", "TPLX_OP_S2F")}
         live = set(live_out)
         keep = []
         for ins in reversed(self.prog.instrs):
@@ -1364,6 +1364,8 @@ class _FuncCompiler:
                 return sc.op1(C["TPLX_OP_S2I"], T_I64, a)
             if name == "float" and len(args) == 1 and args[0].type != T_STR:
                 return sc.to_f64(args[0])
+            if name == "float" and len(args) == 1 and not sc.is_const(args[0]):
+                return sc.op1(C["TPLX_OP_S2F"], T_F64, args[0])  # fast_atod semantics (FunctionRegistry.cc createFloatCast)
             if name == "bool" and len(args) == 1:
                 return sc.truth(args[0])
             if name == "len" and len(args) == 1 and args[0].type == T_STR:
