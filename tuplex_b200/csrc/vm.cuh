@@ -46,6 +46,11 @@ struct ColIn {
     uint64_t type;
 };
 
+// float(str): out of line so that the VM's register allocation is not shaped by a rarely used op
+TPLX_HD_NOINLINE bool str_to_f64(const StrV &s, double *out) {
+    return csv_atod_g([&s](uint32_t k) { return sch(s, k); }, s.len, out);
+}
+
 __device__ __forceinline__ uint8_t *scratch_alloc(VMThread &t, uint32_t n, uint32_t opidx) {
     if (t.scr_used + n > t.scr_cap) {
         // internal limit, not a Python error: hand the row to the resolve path
@@ -396,7 +401,7 @@ struct VM {
                 case TPLX_OP_S2F: {
                     const StrV s = SA();
                     double d;
-                    if (!csv_atod_g([&s](uint32_t k) { return sch(s, k); }, s.len, &d)) { raise_exc(t, TPLX_EC_VALUEERROR, opidx); break; }
+                    if (!str_to_f64(s, &d)) { raise_exc(t, TPLX_EC_VALUEERROR, opidx); break; }
                     WF(d);
                     break;
                 }
