@@ -104,6 +104,9 @@ class Context:
 
     def _source_from_rows(self, rows: Sequence, names: Optional[List[Optional[str]]], infer: bool = True) -> Source:
         n = len(rows)
+        fast = self._homogeneous_source(rows, names)
+        if fast is not None:
+            return fast
         # row shape: majority of (is tuple, arity)
         shapes = Counter((len(r) if isinstance(r, tuple) else -1) for r in rows)
         arity = shapes.most_common(1)[0][0] if shapes else -1
@@ -144,6 +147,42 @@ class Context:
         cols = [Column.from_values(normal_vals[c], col_types[c]) for c in range(ncols)]
         oi = None if not fallback else np.asarray(orig, dtype=np.int64)
         return Source(cols, names, len(orig), oi, fallback, n)
+
+    def _homogeneous_source(self, rows: Sequence, names) -> Optional[Source]:
+        """Fast path of parallelize for the common case — every row has the same shape and every column one primitive type
+        (the reference's fastI64Parallelize / fastMixedSimpleTypeTupleTransfer, python/src/PythonContext.cc:126-209,388-520):
+        type checks by set(map(type, …)) and column building by numpy instead of per-value Python code."""
+        n = len(rows)
+        if n == 0:
+            return None
+        prim = {int: T_I64, float: T_F64, str: T_STR, bool: T_BOOL}
+        row_types = set(map(type, rows))
+        if len(row_types) != 1:
+            return None
+        (rt,) = row_types
+        if rt in prim:
+            cols_vals = [rows]
+        elif rt is tuple:
+            if len(set(map(len, rows))) != 1 or len(rows[0]) == 0:
+                return None
+            cols_vals = list(zip(*rows))
+        else:
+            return None
+        types = []
+        for cv in cols_vals:
+            ts = set(map(type, cv))
+            if len(ts) != 1 or next(iter(ts)) not in prim:
+                return None
+            types.append(prim[next(iter(ts))])
+        ncols = len(cols_vals)
+        if names is not None and len(names) != ncols:
+            return None  # let the general path report / pad
+        names = list(names) if names is not None else [None] * ncols
+        try:
+            cols = [Column.from_values(cv, t) for cv, t in zip(cols_vals, types)]
+        except OverflowError:
+            return None  # ints beyond 64 bits take the general path (fallback rows)
+        return Source(cols, names, n, None, [], n)
 
     def csv(self, pattern, columns=None, header=None, delimiter=None, quotechar='"', null_values=[''], type_hints={}) -> DataSet:
         """tuplex.Context.csv (python/tuplex/context.py:203-290). Planning (delimiter, header, normal-case types) looks at
