@@ -250,6 +250,9 @@ def _run_stage(ctx, src: Source, ops: List[Op], exc_counter: Counter, csv_sink: 
     used_cols = list(range(len(in_types)))
     if is_csv:  # projection pushdown: the device decodes only the columns the stage loads
         used_cols = ir.referenced_inputs(prog)
+        if len(used_cols) > C["TPLX_MAX_COLS"]:
+            ctx._log(f"stage reads {len(used_cols)} columns (> TPLX_MAX_COLS): CPython path")
+            return _run_stage_python(ctx, src.to_host_source(), ops, exc_counter)
         ir.project_inputs(prog, used_cols)
     dev = ctx._device
     backend.init([dev])
