@@ -319,3 +319,32 @@ def test_csv_many_chunks_equal_one(ctx, tmp_path, monkeypatch):
     monkeypatch.setattr(cs, "MAX_CHUNK", 40_000)
     many = pipeline(ctx.csv(str(p)))
     assert len(one) > 15000 and many == one
+
+
+def test_csv_aggregate_by_key_and_unique(ctx, tmp_path):
+    """hash endpoints fed by the device CSV source (several chunks, a few rows through the interpreter path)"""
+    import random
+    from tuplex_b200 import csvsource as cs
+    rng = random.Random(12)
+    lines = ["city,price,tag"]
+    want = {}
+    for i in range(30000):
+        city = rng.choice(["Boston", "New York", "Woburn, MA", "LA"])
+        price = rng.randint(1, 1000)
+        if i % 500 == 3:
+            lines.append(f"\"{city}\",n/a,x")   # conversion error: the UDF raises on the interpreter path too -> dropped
+            continue
+        lines.append(f"\"{city}\",{price},t{i % 3}")
+        want[city] = want.get(city, 0) + price
+    p = tmp_path / "sales.csv"
+    p.write_text("\n".join(lines) + "\n")
+    for chunk in (None, 100_000):
+        if chunk:
+            cs.MAX_CHUNK = chunk
+        try:
+            got = ctx.csv(str(p)).aggregateByKey(lambda a, b: a + b, lambda a, x: a + x["price"], 0, ["city"]).collect()
+            assert dict(got) == want
+            tags = ctx.csv(str(p)).selectColumns(["tag"]).unique().collect()
+            assert sorted(tags) == ["t0", "t1", "t2", "x"]
+        finally:
+            cs.MAX_CHUNK = 0xFFFFFFFF - (1 << 20)
