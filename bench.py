@@ -546,7 +546,7 @@ def main():
         }
         if "result" in stats:
             line["config"]["result"] = repr(stats["result"])
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # the CPU arm is reported at N = 1 only
             line["cpu_baseline"] = cpu_baseline(args, wl)
         print(json.dumps(line))
     if dist is not None:
@@ -721,7 +721,7 @@ def main_csv(args, rank, world, local):
                              "algorithmic_bytes_per_row": alg / total, "kernel_ms_per_launch": parse_ms_step / n_blocks,
                              "kernel_share_of_step": parse_ms_step / ms_step, "stage_ms_per_step": sms / args.steps,
                              "csv_gb_per_s": csv_bytes / (parse_ms_step * 1e-3) / 1e9}}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_zillow_csv_reference(args.cpu_sample_rows, os.cpu_count() or 1) if args.workload == "zillow_csv" \
                 else cpu_q6_csv_port(args.cpu_sample_rows, os.cpu_count() or 1)
         print(json.dumps(line))
