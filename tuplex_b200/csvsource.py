@@ -14,9 +14,8 @@ such rows in CPython too) or to planning; the normal-case parse happens on the d
 from __future__ import annotations
 
 import json
-import struct
 from collections import Counter
-from typing import Any, Dict, List, Optional, Sequence, Tuple
+from typing import Any, List, Optional, Sequence
 
 import numpy as np
 
