@@ -233,27 +233,3 @@ def _cell_kind(s: str) -> int:
         return T_F64
     except ValueError:
         return T_STR
-
-
-def _parse_row(r, types, nulls):
-    out = []
-    for s, t in zip(r, types):
-        if t == T_STR:
-            if s in nulls and s != "":
-                return None
-            out.append(s)
-            continue
-        if s in nulls:
-            return None
-        try:
-            out.append(int(s) if t == T_I64 else float(s) if t == T_F64 else {"true": True, "false": False}[s.lower()])
-        except (ValueError, KeyError):
-            return None
-    return out
-
-
-def _parse_cell_general(s, nulls):
-    if s in nulls:
-        return None
-    k = _cell_kind(s)
-    return int(s) if k == T_I64 else float(s) if k == T_F64 else s
