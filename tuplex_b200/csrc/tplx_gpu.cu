@@ -105,14 +105,23 @@ extern "C" int32_t tplx_gpu_init(const int32_t *devices, int32_t n) {
         CU(cudaFuncSetAttribute(stage_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d->smem_optin));
         CU(cudaFuncSetAttribute(stage_agg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d->smem_optin));
         CU(cudaFuncSetAttribute(stage_hash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d->smem_optin));
-        Device *a = new Device();
-        a->id = id;
-        a->prop = d->prop;
-        a->smem_optin = d->smem_optin;
-        CU(cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking));
-        CU(cudaStreamCreateWithFlags(&a->copy_stream, cudaStreamNonBlocking));
-        CU(cudaStreamCreateWithFlags(&a->d2h_stream, cudaStreamNonBlocking));
-        d->alt = a;
+        // extra execution lanes on the same GPU (chain d -> alt -> alt ...): TPLX_LANES lanes in all. Measured on the
+        // Zillow bench: 2 lanes 6.18 G rows/s resident / 653 M rows/s end to end; 3 lanes 6.28 G / 625 M; 4 lanes as 3.
+        // The end-to-end number is the headline, so the default stays 2.
+        int lanes = 2;
+        if (const char *e = getenv("TPLX_LANES")) lanes = std::max(1, std::min(8, atoi(e)));
+        Device *tail = d;
+        for (int l = 1; l < lanes; ++l) {
+            Device *a = new Device();
+            a->id = id;
+            a->prop = d->prop;
+            a->smem_optin = d->smem_optin;
+            CU(cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking));
+            CU(cudaStreamCreateWithFlags(&a->copy_stream, cudaStreamNonBlocking));
+            CU(cudaStreamCreateWithFlags(&a->d2h_stream, cudaStreamNonBlocking));
+            tail->alt = a;
+            tail = a;
+        }
         g_devices.push_back(d);
     }
     return TPLX_OK;
@@ -122,13 +131,15 @@ extern "C" int32_t tplx_gpu_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_mu);
     for (auto *d : g_devices) {
         cudaSetDevice(d->id);
-        if (d->alt) {
-            cudaStreamSynchronize(d->alt->stream);
-            if (d->alt->scratch) cudaFree(d->alt->scratch);
-            cudaStreamDestroy(d->alt->stream);
-            cudaStreamDestroy(d->alt->copy_stream);
-            cudaStreamDestroy(d->alt->d2h_stream);
-            delete d->alt;
+        for (Device *a = d->alt; a;) {
+            Device *next = a->alt;
+            cudaStreamSynchronize(a->stream);
+            if (a->scratch) cudaFree(a->scratch);
+            cudaStreamDestroy(a->stream);
+            cudaStreamDestroy(a->copy_stream);
+            cudaStreamDestroy(a->d2h_stream);
+            delete a;
+            a = next;
         }
         cudaStreamSynchronize(d->stream);
         if (d->scratch) cudaFree(d->scratch);
@@ -579,13 +590,13 @@ extern "C" int32_t tplx_gpu_stage_run(tplx_stage *s, const tplx_block *b, int64_
     for (size_t c = 0; c < b->cols.size(); ++c)
         if ((uint8_t)b->cols[c].type != s->in_types[c]) return fail(TPLX_E_BADARG, "stage_run: block column type != stage input schema");
     Device *d = b->dev;
-    // two execution lanes per GPU: a second caller does not wait for the first one's kernels (hash stages keep to
-    // the primary lane: one table per device)
+    // several execution lanes per GPU: a concurrent caller does not wait for the first one's kernels, it takes the next
+    // free lane (hash stages keep to the primary lane: one table per device)
     std::unique_lock<std::mutex> lk(d->mu, std::try_to_lock);
-    if (!lk.owns_lock()) {
+    while (!lk.owns_lock()) {
         if (s->hdr.endpoint != TPLX_EP_HASH && d->alt) {
             d = d->alt;
-            lk = std::unique_lock<std::mutex>(d->mu);
+            lk = d->alt ? std::unique_lock<std::mutex>(d->mu, std::try_to_lock) : std::unique_lock<std::mutex>(d->mu);
         } else {
             lk = std::unique_lock<std::mutex>(d->mu);
         }
