@@ -617,6 +617,9 @@ def main_csv(args, rank, world, local):
     host, keep = pinned(text)
     st = backend.Stage(prog)
     is_agg = prog.endpoint == ir.C["TPLX_EP_AGGREGATE"]
+    # late materialisation: string columns the prefilter does not read stay as cell references in the CSV buffer
+    from tuplex_b200.dataset import csv_lazy_columns
+    lazy = csv_lazy_columns(prog, [c for c, t in enumerate(types) if t != X], types)
     bufs = [backend.CsvBuffer(local, host) for _ in range(n_blocks)]  # distinct HBM buffers, each >> L2
     torch.cuda.synchronize()
     pool = ThreadPoolExecutor(max_workers=3)
@@ -628,7 +631,7 @@ def main_csv(args, rank, world, local):
             dist.barrier()
 
     def run_block(buf, fetch):
-        p = buf.parse(types, delimiter=delim, header=has_header)
+        p = buf.parse(types, delimiter=delim, header=has_header, lazy=lazy)
         r = st.run(p.block, 0)
         inf, pinf = r.info, p.info
         nb = 0

@@ -188,6 +188,9 @@ typedef struct tplx_csv_desc {
     uint32_t n_file_cols;   /* cells every row must have */
     const uint8_t *col_types;       /* [n_file_cols] tplx_type or TPLX_CSV_SKIP; at most TPLX_MAX_COLS are read */
     const char *const *null_values; /* compared with the dequoted cell (compareToNullValues) */
+    const uint8_t *col_lazy;        /* optional [n_file_cols]: 1 = string column whose bytes stay in the CSV buffer; the block
+                                     * carries cell references and tplx_gpu_stage_run materialises the column only for the rows a
+                                     * prefilter stage lets through (late materialisation). The buffer must outlive the block. */
 } tplx_csv_desc;
 typedef struct tplx_csv_bad_row {
     uint32_t row;        /* index among the data rows (header excluded) */

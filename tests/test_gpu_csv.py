@@ -185,3 +185,58 @@ def test_sink_f64_columns(gpu):
     res.free()
     res = st.run_host(0, [Column.from_values([1.0, 1e30], T_F64), Column.from_values([1, 2], T_I64)], 2)
     assert res.csv_bytes() is None  # magnitude >= 2^63: the call reports TPLX_E_UNSUPPORTED, tocsv formats on the host
+
+
+# ---- lazy (late materialised) string columns -------------------------------------------------------------------------------
+def test_lazy_columns_zillow_md5(gpu):
+    """string columns the Z1 prefilter does not read stay as cell references in the CSV buffer and are gathered for the
+    surviving rows only; the result must not change"""
+    from tuplex_b200.dataset import csv_lazy_columns
+    data = _zillow_csv()
+    prog = workloads.zillow_program()
+    lazy = csv_lazy_columns(prog, [c for c, t in enumerate(ZILLOW_FILE_TYPES) if t != X], ZILLOW_FILE_TYPES)
+    assert lazy and 0 not in lazy and 6 not in lazy  # title and "facts and features" feed the prefilter
+    buf = backend.CsvBuffer(0, data)
+    p = buf.parse(ZILLOW_FILE_TYPES, header=True, lazy=lazy)
+    st = backend.Stage(prog)
+    res = st.run(p.block)
+    txt = workloads.rows_to_csv([c.to_values() for c in res.columns()], workloads.ZILLOW_OUT)
+    assert hashlib.md5(txt).hexdigest() == "4d5ca0263b1a5058341a369116dee83a"
+    # a stage without a prefilter cannot read such a block: loud error, no silent garbage
+    sc = frontend.StageCompiler([t for t in ZILLOW_FILE_TYPES if t != X], [None] * 8)
+    sc.add_map(lambda x: x, 100001)
+    with pytest.raises(backend.GpuBackendError):
+        backend.Stage(sc.finish_memory()).run(p.block)
+
+
+def test_lazy_columns_with_escaped_cells_equal_oracle(gpu):
+    from tuplex_b200.backend import Column
+    from tuplex_b200.dataset import csv_lazy_columns
+    from helpers import assert_result_equals_oracle
+    rng = random.Random(41)
+    words = ["plain", "x,y", 'say "hi"', "", "line\nbreak", 'q""q', "tail\"", "é é"]
+    lines = []
+    for i in range(20000):
+        s1 = rng.choice(["keep me", "drop", "kkk", "nothing"])
+        s2 = rng.choice(words)
+        s3 = rng.choice(words)
+        q = lambda v: '"' + v.replace('"', '""') + '"' if any(ch in v for ch in ',"\n') or rng.random() < 0.2 else v
+        lines.append(f"{i},{q(s1)},{q(s2)},{q(s3)}")
+    data = ("\n".join(lines) + "\n").encode()
+    types = [I, S, S, S]
+    sc = frontend.StageCompiler(types, ["i", "s1", "s2", "s3"])
+    sc.add_filter(lambda x: 'k' in x['s1'] and x['s1'].find('e') >= 0, 100001)
+    sc.add_with_column("t", lambda x: x['s2'].replace('a', 'b') + '|' + x['s3'].upper() + '|' + x['s2'].lower(), 100002)
+    sc.add_with_column("u", lambda x: x['s3'].replace('"', "'") + x['s2'][1:], 100003)
+    prog = sc.finish_memory()
+    assert prog.prefilter is not None
+    lazy = csv_lazy_columns(prog, [0, 1, 2, 3], types)
+    assert lazy == [2, 3]
+    buf = backend.CsvBuffer(0, data)
+    p = buf.parse(types, lazy=lazy)
+    res = backend.Stage(prog).run(p.block)
+    o = po.csv_parse(data, types)
+    cols = [Column(T_I64, o.columns[0])] + [Column(T_STR, np.frombuffer(b, np.uint8), off) for b, off in o.columns[1:]]
+    ora = po.run_program(prog, cols, o.n_normal)
+    assert ora.n_out > 1000
+    assert_result_equals_oracle(res, ora, "lazy csv columns")

@@ -42,7 +42,8 @@ class CResultInfo(ct.Structure):
 
 class CCsvDesc(ct.Structure):
     _fields_ = [("delimiter", ct.c_uint8), ("quotechar", ct.c_uint8), ("skip_header", ct.c_uint8), ("n_null_values", ct.c_uint8),
-                ("n_file_cols", ct.c_uint32), ("col_types", ct.c_char_p), ("null_values", ct.POINTER(ct.c_char_p))]
+                ("n_file_cols", ct.c_uint32), ("col_types", ct.c_char_p), ("null_values", ct.POINTER(ct.c_char_p)),
+                ("col_lazy", ct.c_char_p)]
 
 
 class CCsvInfo(ct.Structure):
@@ -441,7 +442,10 @@ class CsvBuffer:
         _check(lib().tplx_gpu_csv_upload(device, self._arr.ctypes.data if self.n_bytes else None, self.n_bytes, ct.byref(self._h)),
                "tplx_gpu_csv_upload")
 
-    def parse(self, col_types: Sequence[int], delimiter=",", quotechar='"', header=False, null_values: Sequence[str] = ("",)) -> "CsvParse":
+    def parse(self, col_types: Sequence[int], delimiter=",", quotechar='"', header=False, null_values: Sequence[str] = ("",),
+              lazy: Optional[Sequence[int]] = None) -> "CsvParse":
+        """lazy: file-column indices of string columns that stay as cell references (materialised by Stage.run only for the
+        rows its prefilter lets through); the buffer must stay alive as long as the block."""
         d = CCsvDesc()
         d.delimiter, d.quotechar, d.skip_header = ord(delimiter), ord(quotechar), int(bool(header))
         d.n_null_values = len(null_values)
@@ -450,6 +454,8 @@ class CsvBuffer:
         d.col_types = types
         nv = (ct.c_char_p * max(1, len(null_values)))(*[s.encode() for s in null_values])
         d.null_values = nv
+        lz = bytes(1 if (lazy and c in lazy) else 0 for c in range(len(col_types)))
+        d.col_lazy = lz if lazy else None
         hb, hr = ct.c_void_p(), ct.c_void_p()
         _check(lib().tplx_gpu_csv_parse(self._h, ct.byref(d), ct.byref(hb), ct.byref(hr)), "tplx_gpu_csv_parse")
         nr = ct.c_uint64()

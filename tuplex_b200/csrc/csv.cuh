@@ -149,6 +149,7 @@ struct CsvCompactParams {
     uint64_t *data[TPLX_MAX_COLS];
     uint32_t *offsets[TPLX_MAX_COLS];
     uint8_t *bytes[TPLX_MAX_COLS];
+    uint64_t *refs[TPLX_MAX_COLS];  // lazy string columns (strk < 0): the cell reference of every good row
     uint32_t *rowmap;
     tplx_csv_bad_row *bad;
 };
@@ -172,14 +173,16 @@ __global__ void __launch_bounds__(CSV_NT) csv_compact(const CsvCompactParams P) 
     }
     P.rowmap[pos] = i;
     for (uint32_t c = 0; c < P.n_out; ++c) {
-        if (P.out_types[c] == TPLX_T_STR)
+        if (P.out_types[c] == TPLX_T_STR && P.strk[c] < 0)
+            P.refs[c][pos] = P.tmp[c][i];
+        else if (P.out_types[c] == TPLX_T_STR)
             P.offsets[c][pos] = (uint32_t)P.lens[(size_t)P.strk[c] * (P.nd + 1) + i];
         else
             P.data[c][pos] = P.tmp[c][i];
     }
     if (pos + 1 == P.good[P.nd])  // last good row also writes the closing offsets
         for (uint32_t c = 0; c < P.n_out; ++c)
-            if (P.out_types[c] == TPLX_T_STR) P.offsets[c][pos + 1] = (uint32_t)P.lens[(size_t)P.strk[c] * (P.nd + 1) + P.nd];
+            if (P.out_types[c] == TPLX_T_STR && P.strk[c] >= 0) P.offsets[c][pos + 1] = (uint32_t)P.lens[(size_t)P.strk[c] * (P.nd + 1) + P.nd];
 }
 
 // One warp per 32 consecutive rows; lane i first loads row i's cell info and output offset (coalesced), then the warp
@@ -194,7 +197,7 @@ __global__ void __launch_bounds__(CSV_NT) csv_copy_strings(const CsvCompactParam
     const bool mine = i < P.nd && P.code[i] == 0;
     const uint32_t sub = lane >> 3, k0 = lane & 7;
     for (uint32_t c = 0; c < P.n_out; ++c) {
-        if (P.out_types[c] != TPLX_T_STR) continue;
+        if (P.out_types[c] != TPLX_T_STR || P.strk[c] < 0) continue;
         const uint64_t info = mine ? P.tmp[c][i] : 0;  // raw length 0 for rows that are not copied
         const uint64_t off = mine ? P.lens[(size_t)P.strk[c] * (P.nd + 1) + i] : 0;
         uint8_t *const base = P.bytes[c];

@@ -581,7 +581,8 @@ TPLX_HD void csv_parse_one_row(const CsvParseParams &P, uint32_t i) {
         }
         if (kind == TPLX_T_STR) {
             P.tmp[slot][i] = (uint64_t)b | ((uint64_t)(e - b) << 32) | ((uint64_t)esc << 63);
-            P.lens[(size_t)P.strk[slot] * (P.nd + 1) + i] = esc ? csv_dequoted_len(P.buf, b, e, P.quote) : (e - b);
+            if (P.strk[slot] >= 0)  // lazy columns (strk < 0) keep the reference only
+                P.lens[(size_t)P.strk[slot] * (P.nd + 1) + i] = esc ? csv_dequoted_len(P.buf, b, e, P.quote) : (e - b);
         } else {
             uint64_t bits = 0;
             if (!csv_decode_scalar(P.buf, b, e, esc, P.quote, (uint8_t)kind, &bits)) code = TPLX_EC_BADPARSE_STRING_INPUT;

@@ -415,7 +415,9 @@ struct tplx_block {
     std::vector<uint64_t> data_bytes;  // per column
     std::vector<void *> owned;         // allocations to free
     cudaEvent_t ready = nullptr;       // recorded on the copy stream when the upload has been enqueued
-    std::vector<uint8_t> mapped;       // per column: 1 = read in place from page-locked host memory (run_host)
+    std::vector<uint8_t> mapped;       // per column: 1 = read in place from page-locked host memory (run_host);
+                                       // 2 = lazy CSV column: data = CSV text, offsets = (uint64) cell references (K6)
+    uint8_t csv_quote = '"';
 };
 
 extern "C" int32_t tplx_gpu_block_upload(int32_t device, const tplx_column *cols, uint32_t n_cols, uint64_t n_rows,
@@ -617,12 +619,26 @@ extern "C" int32_t tplx_gpu_stage_run(tplx_stage *s, const tplx_block *b, int64_
     if (b->ready) CU(cudaStreamWaitEvent(d->stream, b->ready, 0));
     CU(cudaEventRecord(r->ev0, d->stream));
     switch (s->hdr.endpoint) {
-        case TPLX_EP_MEMORY:
-            rc = (s->prefilter && s->prefilter_enabled) ? run_rows_prefiltered(s, sd, b, first_row_no, r)
-                                                         : run_rows(s, sd, b, first_row_no, r, nullptr, 0);
+        case TPLX_EP_MEMORY: {
+            bool lazy = false;
+            for (uint8_t m : b->mapped) lazy = lazy || m == 2;
+            // lazy columns are materialised between the two launches, so such blocks always take the two-launch path
+            // (also after the prefilter was switched off for not being selective)
+            if (lazy && !s->prefilter)
+                rc = fail(TPLX_E_UNSUPPORTED, "stage_run: block has lazy CSV columns but the stage has no prefilter; parse without col_lazy");
+            else
+                rc = (s->prefilter && (s->prefilter_enabled || lazy)) ? run_rows_prefiltered(s, sd, b, first_row_no, r)
+                                                                        : run_rows(s, sd, b, first_row_no, r, nullptr, 0);
             break;
-        case TPLX_EP_AGGREGATE: rc = run_agg(s, sd, b, r); break;
-        default: rc = run_hash(s, sd, b, r); break;
+        }
+        case TPLX_EP_AGGREGATE:
+        default: {
+            bool lazy = false;
+            for (uint8_t m : b->mapped) lazy = lazy || m == 2;
+            if (lazy) rc = fail(TPLX_E_UNSUPPORTED, "stage_run: lazy CSV columns need a row stage with a prefilter");
+            else rc = s->hdr.endpoint == TPLX_EP_AGGREGATE ? run_agg(s, sd, b, r) : run_hash(s, sd, b, r);
+            break;
+        }
     }
     if (rc) {
         tplx_gpu_result_free(r);
@@ -957,6 +973,11 @@ static int32_t run_rows_prefiltered(tplx_stage *s, StageDev *sd, const tplx_bloc
             G.type[k] = (uint8_t)b->cols[c].type;
             G.src_data[k] = b->cols[c].data;
             G.src_off[k] = b->cols[c].offsets;
+            if (b->mapped[c] == 2) {
+                G.src_ref[k] = reinterpret_cast<const uint64_t *>(b->cols[c].offsets);
+                G.src_off[k] = nullptr;
+                G.quote = b->csv_quote;
+            }
             if (G.type[k] == TPLX_T_STR) {
                 rc = dalloc(r, &G.lens[k], n_surv + 1);
                 if (rc) { drop_ra(); return rc; }
@@ -990,7 +1011,7 @@ static int32_t run_rows_prefiltered(tplx_stage *s, StageDev *sd, const tplx_bloc
             if (rc) { drop_ra(); return rc; }
         }
         CU(cudaMemcpyAsync(dG, &G, sizeof(G), cudaMemcpyHostToDevice, d->stream));
-        gather_pass2<<<(uint32_t)(((n_surv + 1) * 32 + 255) / 256), 256, 0, d->stream>>>(n_surv, dG);
+        gather_pass2<<<(uint32_t)(((n_surv + 1) * 32 + 255) / 256), 256, 0, d->stream>>>(n_surv, dG, ra.out[0].data);
         CU(cudaGetLastError());
         CU(cudaEventRecord(g1, d->stream));
         for (uint32_t k = 0; k < G.n_cols; ++k) {

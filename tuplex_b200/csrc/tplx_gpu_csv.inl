@@ -89,7 +89,8 @@ extern "C" int32_t tplx_gpu_csv_parse(tplx_csv_buffer *cb, const tplx_csv_desc *
         if (P.n_out == TPLX_MAX_COLS) return fail(TPLX_E_UNSUPPORTED, "csv_parse: more than TPLX_MAX_COLS columns selected");
         slot[c] = (uint8_t)P.n_out;
         P.out_types[P.n_out] = t;
-        P.strk[P.n_out] = t == TPLX_T_STR ? (int8_t)P.n_str++ : (int8_t)-1;
+        const bool lazy = t == TPLX_T_STR && desc->col_lazy && desc->col_lazy[c];
+        P.strk[P.n_out] = (t == TPLX_T_STR && !lazy) ? (int8_t)P.n_str++ : (int8_t)-1;
         ++P.n_out;
     }
     if (desc->n_null_values > 8) return fail(TPLX_E_UNSUPPORTED, "csv_parse: at most 8 null values");
@@ -223,7 +224,17 @@ extern "C" int32_t tplx_gpu_csv_parse(tplx_csv_buffer *cb, const tplx_csv_desc *
         ColIn ci{};
         ci.type = P.out_types[c];
         void *p = nullptr;
-        if (P.out_types[c] == TPLX_T_STR) {
+        if (P.out_types[c] == TPLX_T_STR && P.strk[c] < 0) {  // lazy: cell references into the CSV buffer
+            CU(cudaMallocAsync(&p, std::max<uint64_t>(n_good * 8, 16), st));
+            b->owned.push_back(p);
+            C.refs[c] = static_cast<uint64_t *>(p);
+            ci.data = cb->d;
+            ci.offsets = reinterpret_cast<const uint32_t *>(p);
+            b->data_bytes.push_back(n_good * 8);
+            b->mapped.resize(P.n_out, 0);
+            b->mapped[c] = 2;
+            b->csv_quote = desc->quotechar;
+        } else if (P.out_types[c] == TPLX_T_STR) {
             const uint64_t tot = str_total[P.strk[c]];
             if (tot > 0xFFFFFFFFull) return fail(TPLX_E_OVERFLOW, "csv_parse: string column exceeds 4 GiB");
             CU(cudaMallocAsync(&p, align_up(tot, 16) + 16, st));

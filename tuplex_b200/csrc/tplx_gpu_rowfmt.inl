@@ -239,6 +239,8 @@ extern "C" int32_t tplx_gpu_result_partitions(tplx_result *r, uint64_t partition
 extern "C" int32_t tplx_gpu_result_exception_partition(tplx_result *r, uint8_t *buf, uint64_t buf_bytes, uint64_t *bytes_needed) {
     if (!r || !bytes_needed) return fail(TPLX_E_BADARG, "result_exception_partition: bad arguments");
     if (!r->block) return fail(TPLX_E_BADARG, "result_exception_partition: input block no longer available");
+    for (uint8_t m : r->block->mapped)
+        if (m == 2) return fail(TPLX_E_UNSUPPORTED, "result_exception_partition: block has lazy CSV columns (use the row text, tplx_gpu_csv_result_fetch_row_ends)");
     Device *d = r->dev;
     std::lock_guard<std::mutex> lk(d->mu);
     CU(cudaSetDevice(d->id));

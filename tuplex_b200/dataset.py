@@ -176,6 +176,16 @@ class DataSet:
         return rows, names
 
 
+def csv_lazy_columns(prog, used_cols, in_types):
+    """File columns the device CSV source may leave as cell references: string columns of a row stage that its prefilter
+    does not read (the stage materialises them for surviving rows only). `prog` reads the projected block `used_cols`."""
+    if prog.prefilter is None or prog.endpoint != C["TPLX_EP_MEMORY"]:
+        return None
+    early = {int(i.imm) for i in prog.prefilter.instrs if i.op == C["TPLX_OP_LDCOL"]}
+    lazy = [c for k, c in enumerate(used_cols) if k not in early and in_types[c] == T_STR]
+    return lazy or None
+
+
 def _csv_cell(v, null_value=None) -> str:
     """Host twin of the row writer (fast_csvwriter + quoteForCSV + ryu d2fixed(8) for floats)."""
     if isinstance(v, str):
@@ -289,9 +299,10 @@ def _run_stage(ctx, src: Source, ops: List[Op], exc_counter: Counter, csv_sink: 
     def csv_blocks():
         base = 0
         col_types = [t if c in used_cols else backend.CSV_SKIP for c, t in enumerate(in_types)]
+        lazy = csv_lazy_columns(prog, used_cols, in_types)
         for data, skip_header in src.chunks():
             buf = backend.CsvBuffer(dev, data)
-            parse = buf.parse(col_types, src.delimiter, src.quotechar, skip_header, src.null_values)
+            parse = buf.parse(col_types, src.delimiter, src.quotechar, skip_header, src.null_values, lazy=lazy)
             yield (lambda parse=parse: stage.run(parse.block, first_row_no)), base, parse, data
             base += int(parse.info.n_rows)
             parse.free()
