@@ -24,7 +24,7 @@ extern "C" {
 #endif
 
 #define TPLX_IR_MAGIC 0x58504C54u /* "TPLX" */
-#define TPLX_IR_VERSION 6u
+#define TPLX_IR_VERSION 7u
 #define TPLX_NOSLOT 0xFFFFu
 #define TPLX_MAX_COLS 64
 #define TPLX_MAX_ACCS 16
@@ -172,6 +172,10 @@ enum tplx_op {
     TPLX_OP_FILTER = 52, /* alive &= slot[a] != 0 (PipelineBuilder.cc:615-700) */
     TPLX_OP_RAISE = 53,  /* unconditional (guarded) exception imm = code */
     TPLX_OP_S2F = 54,    /* float(s): fast_atod behind the runtime's trim (Runtime.cc:343-365, StringUtils.cc:71-163); ValueError */
+    /* fused forms of two idioms the planner recognises (what inlining + select folding give the reference's LLVM -O2,
+     * LLVMOptimizer.cc:119-191); each is defined as the primitive sequence it replaces */
+    TPLX_OP_SFINDE = 55,  /* i = a.find(b); dst <- i < 0 ? len(a) : i          ("split at marker, else whole string") */
+    TPLX_OP_SRFINDK = 56, /* i = a.rfind(b); dst <- i < 0 ? 0 : i + imm2       ("start after the last separator"); a is never constant */
 };
 
 /* 32-byte instruction */

@@ -290,8 +290,8 @@ static int eval_row(const ostage *S, const tplx_ocol *cols, uint64_t row, oval *
         if (in->flags & (TPLX_F_A_CONST | TPLX_F_B_CONST | TPLX_F_C_CONST)) {
             const int op = in->op;
             const int strsel = (op == TPLX_OP_SEL || op == TPLX_OP_MOV) && (in->flags & 3) == 2;
-            const int a_str = strsel || (op >= TPLX_OP_SLEN && op <= TPLX_OP_SSTRIP && op != TPLX_OP_SFMTD && op != TPLX_OP_I2S);
-            const int b_str = strsel || op == TPLX_OP_SFIND || op == TPLX_OP_SRFIND || op == TPLX_OP_SIN || op == TPLX_OP_SEQ ||
+            const int a_str = strsel || (op >= TPLX_OP_SLEN && op <= TPLX_OP_SSTRIP && op != TPLX_OP_SFMTD && op != TPLX_OP_I2S) || op == TPLX_OP_SFINDE;
+            const int b_str = strsel || op == TPLX_OP_SFIND || op == TPLX_OP_SRFIND || op == TPLX_OP_SIN || op == TPLX_OP_SEQ || op == TPLX_OP_SFINDE || op == TPLX_OP_SRFINDK ||
                               op == TPLX_OP_SSTARTS || op == TPLX_OP_SENDS || op == TPLX_OP_SCONCAT || op == TPLX_OP_SREPLACE;
             const int c_str = op == TPLX_OP_SREPLACE;
 #define KONST(dst, enc, is_str) do { if (is_str) { (dst).len = (int64_t)((uint64_t)(enc) >> 32); \
@@ -382,6 +382,9 @@ static int eval_row(const ostage *S, const tplx_ocol *cols, uint64_t row, oval *
             case TPLX_OP_SLEN: d->i = a->len; break;
             case TPLX_OP_SFIND: { const char *r = strstr(a->s, b->s); d->i = r ? (int64_t)(r - a->s) : -1; break; }
             case TPLX_OP_SRFIND: d->i = tplx_o_rfind(a->s, b->s); break;
+            /* fused idioms, evaluated as the primitive sequences they stand for (include/tplx_ir.h) */
+            case TPLX_OP_SFINDE: { const char *r = strstr(a->s, b->s); d->i = r ? (int64_t)(r - a->s) : a->len; break; }
+            case TPLX_OP_SRFINDK: { int64_t r = tplx_o_rfind(a->s, b->s); d->i = r < 0 ? 0 : (int64_t)((uint64_t)r + (uint64_t)in->imm2); break; }
             case TPLX_OP_SIN: d->i = strstr(b->s, a->s) != NULL; break;
             case TPLX_OP_SEQ: d->i = (strcmp(a->s, b->s) == 0) != (in->flags & 1); break;
             case TPLX_OP_STRUTH: d->i = a->len > 0; break;

@@ -271,11 +271,12 @@ extern "C" int32_t tplx_gpu_stage_create(const void *desc, uint64_t desc_bytes, 
                 break;
             default: break;
         }
-        if ((in.op >= TPLX_OP_SLEN && in.op <= TPLX_OP_SSTRIP) || in.op == TPLX_OP_S2F) {
+        if (in.op == TPLX_OP_SRFINDK && ((in.flags & TPLX_F_A_CONST) || in.a == TPLX_NOSLOT)) return bad("program: SRFINDK needs a slot operand a");
+        if ((in.op >= TPLX_OP_SLEN && in.op <= TPLX_OP_SSTRIP) || in.op == TPLX_OP_S2F || in.op == TPLX_OP_SFINDE || in.op == TPLX_OP_SRFINDK) {
             s->has_str = true;
             // constant string operands are constant-pool views (offset | length << 32)
             auto cs_ok = [&](int64_t enc) { return ((uint64_t)enc & 0xFFFFFFFFull) + ((uint64_t)enc >> 32) <= h.const_bytes; };
-            const bool str_b = in.op == TPLX_OP_SFIND || in.op == TPLX_OP_SRFIND || in.op == TPLX_OP_SIN || in.op == TPLX_OP_SEQ ||
+            const bool str_b = in.op == TPLX_OP_SFIND || in.op == TPLX_OP_SRFIND || in.op == TPLX_OP_SIN || in.op == TPLX_OP_SEQ || in.op == TPLX_OP_SFINDE || in.op == TPLX_OP_SRFINDK ||
                                in.op == TPLX_OP_SSTARTS || in.op == TPLX_OP_SENDS || in.op == TPLX_OP_SCONCAT || in.op == TPLX_OP_SREPLACE;
             if (in.op != TPLX_OP_SFMTD && in.op != TPLX_OP_I2S && (in.flags & TPLX_F_A_CONST) && !cs_ok(in.imm2)) return bad("program: constant operand a out of range");
             if (str_b && (in.flags & TPLX_F_B_CONST) && !cs_ok(in.imm)) return bad("program: constant operand b out of range");

@@ -247,6 +247,17 @@ struct VM {
                 case TPLX_OP_SLEN: R(rb, dst) = (uint64_t)SA().len; break;
                 case TPLX_OP_SFIND: R(rb, dst) = (uint64_t)str_find(SA(), SB()); break;
                 case TPLX_OP_SRFIND: R(rb, dst) = (uint64_t)str_rfind(SA(), SB()); break;
+                case TPLX_OP_SFINDE: {  // find, or len(a) when absent
+                    const StrV s = SA();
+                    const int64_t r = str_find(s, SB());
+                    R(rb, dst) = r < 0 ? (uint64_t)s.len : (uint64_t)r;
+                    break;
+                }
+                case TPLX_OP_SRFINDK: {  // rfind + K, or 0 when absent
+                    const int64_t r = str_rfind(RS(rb, a), SB());
+                    R(rb, dst) = r < 0 ? 0ull : (uint64_t)r + (uint64_t)prog[pc].imm2;
+                    break;
+                }
                 case TPLX_OP_SIN: R(rb, dst) = str_find(SB(), SA()) >= 0; break;
                 case TPLX_OP_SEQ: R(rb, dst) = (uint64_t)(str_eq(SA(), SB()) != (bool)(flags & 1)); break;
                 case TPLX_OP_STRUTH: R(rb, dst) = SA().len != 0; break;

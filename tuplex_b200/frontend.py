@@ -450,8 +450,78 @@ class StageCompiler:
         self.guard = None
         regs = [self.reg(v) for v in used_vals]
         self._dce(regs)
+        self._fuse(regs)
         slots = self._regalloc(regs)
         return slots
+
+    def _fuse(self, live_out: List[int]):
+        """Peephole fusion on the (single-assignment) vreg program: two idioms that every 'split at a marker' UDF
+        produces become one instruction each (include/tplx_ir.h TPLX_OP_SFINDE / TPLX_OP_SRFINDK). Each fused op is
+        defined as the primitive sequence it replaces, which is what the oracle evaluates; the reference gets the same
+        effect from LLVM's inlining + select folding (tuplex/core/src/physical/LLVMOptimizer.cc:119-191).
+          i = s.find(m);  stop = len(s) if i < 0 else i          -> SFINDE
+          i = s.rfind(m); start = 0 if i < 0 else i + K          -> SRFINDK"""
+        ins = self.prog.instrs
+        ndef: Dict[int, int] = {}
+        nuse: Dict[int, int] = {}
+        where: Dict[int, int] = {}
+        for pc, i in enumerate(ins):
+            if i.dst != NOSLOT:
+                ndef[i.dst] = ndef.get(i.dst, 0) + 1
+                where[i.dst] = pc
+            for r in (i.a, i.b, i.c, i.guard):
+                if r != NOSLOT:
+                    nuse[r] = nuse.get(r, 0) + 1
+        for r in live_out:
+            nuse[r] = nuse.get(r, 0) + 1
+        OP = lambda k: C["TPLX_OP_" + k]
+        AC, BC = C["TPLX_F_A_CONST"], C["TPLX_F_B_CONST"]
+
+        def single(v):
+            return v != NOSLOT and ndef.get(v, 0) == 1
+
+        def d(v):
+            return ins[where[v]] if single(v) else None
+
+        def stable(v):  # operand may be read later than where it was read originally
+            return v == NOSLOT or ndef.get(v, 0) == 1
+
+        def is_lt0(ci, xv):
+            return (ci is not None and ci.op == OP("ICMP") and ci.a == xv and (ci.flags & BC) and not (ci.flags & AC)
+                    and (ci.flags & 7) == C["TPLX_CMP_LT"] and ci.imm == 0 and ci.guard == NOSLOT)
+
+        dead = set()
+        for y in ins:
+            if y.op != OP("SEL") or (y.flags & 3) != 1 or y.guard != NOSLOT or not single(y.dst) or y.c == NOSLOT:
+                continue
+            cv = y.c
+            ci = d(cv)
+            if ci is None:
+                continue
+            if not (y.flags & (AC | BC)) and y.a != NOSLOT and y.b != NOSLOT:
+                # SEL(c ? len(s) : x),  x = find(s, m), c = x < 0, len(s) guarded by c
+                xi, li = d(y.b), d(y.a)
+                if (xi is not None and li is not None and xi.op == OP("SFIND") and li.op == OP("SLEN") and is_lt0(ci, y.b)
+                        and xi.guard == NOSLOT and li.guard == cv and li.a == xi.a and xi.a != NOSLOT and not (xi.flags & AC)
+                        and stable(xi.a) and stable(xi.b) and nuse.get(y.b, 0) == 2 and nuse.get(cv, 0) == 2 and nuse.get(y.a, 0) == 1):
+                    y.op, y.a, y.b, y.c = OP("SFINDE"), xi.a, xi.b, NOSLOT
+                    y.flags, y.imm, y.imm2 = xi.flags & BC, xi.imm, 0
+                    dead.update(id(k) for k in (xi, ci, li))
+            elif (y.flags & AC) and not (y.flags & BC) and y.imm2 == 0 and y.b != NOSLOT:
+                # SEL(c ? 0 : z),  z = x + K under !c,  x = rfind(s, m), c = x < 0
+                zi = d(y.b)
+                if zi is None or zi.op != OP("IADD") or not (zi.flags & BC) or (zi.flags & AC) or zi.guard == NOSLOT:
+                    continue
+                nci, xi = d(zi.guard), d(zi.a)
+                if (nci is not None and xi is not None and nci.op == OP("BNOT") and nci.a == cv and nci.guard == NOSLOT
+                        and xi.op == OP("SRFIND") and xi.guard == NOSLOT and xi.a != NOSLOT and not (xi.flags & AC) and is_lt0(ci, zi.a)
+                        and stable(xi.a) and stable(xi.b) and nuse.get(zi.a, 0) == 2 and nuse.get(cv, 0) == 2
+                        and nuse.get(zi.guard, 0) == 1 and nuse.get(y.b, 0) == 1):
+                    y.op, y.a, y.b, y.c = OP("SRFINDK"), xi.a, xi.b, NOSLOT
+                    y.flags, y.imm, y.imm2 = xi.flags & BC, xi.imm, zi.imm
+                    dead.update(id(k) for k in (xi, ci, nci, zi))
+        if dead:
+            self.prog.instrs[:] = [i for i in ins if id(i) not in dead]
 
     def _dce(self, live_out: List[int]):
         """Drop pure instructions whose result is never used. Instructions that can raise or that steer rows
