@@ -28,12 +28,17 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="zillow", choices=["zillow", "q6", "c1", "aggbykey", "zillow_csv", "q6_csv"])
+    ap.add_argument("--workload", default="both", choices=["both", "zillow", "q6", "c1", "aggbykey", "zillow_csv", "q6_csv"],
+                    help="both (default) = BASELINE.json's metric: Zillow Z1 (top level of the line) + TPC-H Q6 (nested under \"q6\")")
     ap.add_argument("--rows", type=int, default=0, help="rows per GPU (default: 100M zillow / 600M q6 / 1e6*100 c1)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--keys", type=int, default=0, help="distinct keys of the aggbykey workload (default rows/100)")
+    ap.add_argument("--min-region-s", type=float, default=2.0,
+                    help="the K-step timed region is repeated (each repeat bracketed by barrier + synchronize) until this much time has "
+                         "been measured; the reported time is the median repeat")
+    ap.add_argument("--no-pageable", action="store_true", help="skip the pageable-host-memory end-to-end variant")
     return ap.parse_args()
 
 
@@ -81,14 +86,78 @@ class Clocks:
                 "samples": len(self.samples)}
 
 
+def kernel_source_hash():
+    """sha256 over the CUDA sources: the key that ties profiles/traffic.json (DRAM bytes from an `ncu --set full` capture) to the
+    code it was captured from."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "tuplex_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        h.update(f.encode())
+        h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def ncu_traffic(wl, n_launch):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
-    (profiles/r01_*.md), scaled to this run's rows per launch; None when no capture exists for the workload."""
-    per_row = {"zillow_z1": (963.67e6 + 6.98e6 + 262.70e6 + 50.03e6) / 16330500,   # prefilter + dense launch, 16.33M-row block
-               "tpch_q6": 3.200e9 / 100_000_000}.get(wl["name"])                     # K3f: reads exactly 32 B/row
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu capture summarised in
+    profiles/traffic.json, scaled to this run's rows per launch. The file records the hash of the kernel sources it was
+    captured from: when the sources have changed since, the number is stale and None is reported instead."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    t = json.load(open(p))
+    if t.get("kernel_source_hash") != kernel_source_hash():
+        return None
+    per_row = t.get("dram_bytes_per_row", {}).get(wl["name"])
     if per_row is None:
         return None
     return per_row * wl["rows"] / n_launch
+
+
+def host_cores(calibrate=True):
+    """CPU cores this process may really use: scheduler affinity, capped by the cgroup CPU quota (a quota-limited container
+    still sees every core in os.cpu_count(); oversubscribing it made round 1's CPU arm 7x too slow on the 1-GPU lease)."""
+    visible = os.cpu_count() or 1
+    try:
+        aff = len(os.sched_getaffinity(0))
+    except Exception:
+        aff = visible
+    quota = None
+    try:
+        txt = open("/sys/fs/cgroup/cpu.max").read().split()
+        if txt and txt[0] != "max":
+            quota = float(txt[0]) / float(txt[1])
+    except Exception:
+        try:
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    used = aff if quota is None else max(1, min(aff, int(quota + 0.5)))
+    out = {"cores_visible": visible, "cores_affinity": aff, "cores_quota": quota, "cores_used": used}
+    if calibrate:
+        # what the box really delivers (catches limits the cgroup files do not show): use no more processes than that
+        par = effective_parallelism(used)
+        out["parallelism_measured"] = round(par, 1)
+        if par < 0.7 * used:  # suspicious: the CPU arm is then ALSO run with this many processes and the faster run is reported
+            out["cores_alt"] = max(1, int(par + 0.5))
+    return out
+
+
+def effective_parallelism(procs: int) -> float:
+    """Measured: aggregate throughput of `procs` spinning processes / one spinning process (what the box really gives us,
+    whatever the cgroup files say)."""
+    code = ("import sys,time\nT0=float(sys.argv[1])\nwhile time.time()<T0: pass\nn=0\nwhile time.time()<T0+0.8:\n"
+            "    for _ in range(20000): n+=1\nprint(n)")
+
+    def run(k):  # k processes spin over the SAME 0.8 s window (interpreter start-up is kept out of it)
+        t0 = time.time() + 0.5 + 0.01 * k
+        ps = [subprocess.Popen([sys.executable, "-S", "-E", "-c", code, repr(t0)], stdout=subprocess.PIPE, text=True) for _ in range(k)]
+        return sum(int(p.communicate()[0].strip() or 0) for p in ps)
+    one = max(1, sorted(run(1) for _ in range(3))[1])
+    return max(run(procs) for _ in range(2)) / one
 
 
 def peaks():
@@ -109,6 +178,21 @@ def pinned(arr: np.ndarray):
     out[...] = arr
     out_flags_keep = t  # keep the tensor alive through the numpy view's base
     return out, out_flags_keep
+
+
+def unpin(blocks):
+    """The same blocks in ordinary pageable memory (plain numpy copies; blocks that share arrays keep sharing the copy)."""
+    from tuplex_b200.backend import Column
+    memo = {}
+
+    def cp(a):
+        if a is None:
+            return None
+        k = a.ctypes.data
+        if k not in memo:
+            memo[k] = np.array(a, copy=True)
+        return memo[k]
+    return [([Column(c.type, cp(c.data), cp(c.offsets)) for c in cols], n) for cols, n in blocks]
 
 
 def build_workload(args):
@@ -146,7 +230,7 @@ def build_workload(args):
             done += m
         prog = W.zillow_program()
         in_bytes = sum(sum(c.nbytes() for c in cols) for cols, _ in blocks)
-        return dict(name="zillow_z1", prog=prog, blocks=blocks, rows=total, in_bytes=in_bytes, keep=keep,
+        return dict(name="zillow_z1", prog=prog, blocks=blocks, rows=total, in_bytes=in_bytes, keep=keep, pageable_blocks=lambda: unpin(blocks),
                     desc=f"Zillow Z1 map/withColumn/filter pipeline, {total} synthetic rows (cyclic replication of the 32,661-row "
                          f"zillow_noexc fixture), 8 column-blocked inputs, {len(blocks)} blocks of <= {bn} rows")
     if args.workload == "q6":
@@ -160,7 +244,7 @@ def build_workload(args):
             blocks.append((base if m == len(base[0].data) else [c.slice(0, m) for c in base], m))
             done += m
         prog = W.q6_program()
-        return dict(name="tpch_q6", prog=prog, blocks=blocks, rows=total, in_bytes=total * 32, keep=keep,
+        return dict(name="tpch_q6", prog=prog, blocks=blocks, rows=total, in_bytes=total * 32, keep=keep, pageable_blocks=lambda: unpin(blocks),
                     desc=f"TPC-H Q6 filter+aggregate, {total} synthetic lineitem rows (SF100 ~ 600M), 4 columns i64,f64,f64,i64")
     if args.workload == "c1":
         total = args.rows or 100_000_000
@@ -310,68 +394,100 @@ def cpu_port(wl, sample_rows: int, threads: int):
     return dict(value=m / dt, unit="rows/s", cores=1, kind="port", sample=f"{m} rows through oracle/tplx_oracle.c (scalar interpreter)")
 
 
-def cpu_baseline(args, wl):
-    cores = os.cpu_count() or 1
-    if wl["name"] == "zillow_z1":
+def cpu_arm(args, wl_key, wl, hc):
+    """One bounded CPU sample of workload `wl_key` on hc['cores_used'] host cores -> cpu_baseline dict."""
+    if hc.get("cores_alt") and not hc.get("_in_alt"):
+        a = cpu_arm(args, wl_key, wl, dict(hc, cores_alt=None))
+        b = cpu_arm(args, wl_key, wl, dict(hc, cores_used=hc["cores_alt"], cores_alt=None))
+        best = a if a["value"] >= b["value"] else b
+        best["also_tried"] = {"cores": (b if best is a else a)["cores_used"], "value": (b if best is a else a)["value"]}
+        return best
+    cores = hc["cores_used"]
+    if wl_key == "zillow":
         r = cpu_zillow_reference(args.cpu_sample_rows, cores)
-        if r:
-            return r
-    return cpu_port(wl, args.cpu_sample_rows, cores)
+    elif wl_key == "zillow_csv":
+        r = cpu_zillow_csv_reference(args.cpu_sample_rows, cores)
+    elif wl_key == "q6_csv":
+        r = cpu_q6_csv_port(args.cpu_sample_rows, cores)
+    else:
+        r = None
+    if r is None:
+        r = cpu_port(wl, args.cpu_sample_rows, cores)
+    r.update(cores_visible=hc["cores_visible"], cores_affinity=hc["cores_affinity"], cores_quota=hc["cores_quota"], cores_used=cores)
+    return r
+
+
+WL_NAMES = {"zillow": "zillow_z1", "q6": "tpch_q6", "c1": "c1_map_filter", "aggbykey": "aggbykey_str", "zillow_csv": "zillow_z1_from_csv",
+            "q6_csv": "tpch_q6_from_csv"}
+DEFAULT_ROWS = {"zillow": 100_000_000, "q6": 600_000_000, "c1": 100_000_000, "aggbykey": 100_000_000}
+
+
+def static_config(args, wl_key):
+    """The workload description both arms print (`config`): nothing measured in here, so the driver can compare the two lines."""
+    rows = args.rows or DEFAULT_ROWS.get(wl_key, 0)
+    desc = {"zillow": "Zillow Z1 map/withColumn/filter pipeline (benchmarks/zillow/Z1), synthetic rows = cyclic replication of the 32,661-row "
+                      "zillow_noexc fixture (the reference's own generator), 8 column-blocked inputs, blocks of <= 16,330,500 rows",
+            "q6": "TPC-H Q6 filter+aggregate (benchmarks/tpch/Q06, pre-processed columns), synthetic lineitem rows (SF100 ~ 600M), "
+                  "4 columns i64,f64,f64,i64, blocks of 100M rows",
+            "c1": "parallelize([1..n]).map(x*x).filter(x%2==0)", "aggbykey": "aggregateByKey string key"}[wl_key]
+    return {"workload": WL_NAMES[wl_key], "rows_per_gpu": rows, "description": desc,
+            "l2": "inputs larger than L2 (every block >> 126 MB, distinct HBM buffers per block)"}
+
+
+def reference_line(args):
+    """`--impl reference`: the reference's own CPU implementation of the path (oracle/_ref/zillow_ref = the reference's zillow.cpp
+    compiled unmodified; the C port of oracle/workloads.c for Q6/C1) on the host cores this process may use. Every step is a
+    bounded sample of the workload named in `config`."""
+    import types
+    hc = host_cores()
+    keys = ["zillow", "q6"] if args.workload == "both" else [args.workload]
+    out = {}
+    for wl_key in keys:
+        wl_args = types.SimpleNamespace(**vars(args))
+        wl_args.workload = wl_key
+        wl_args.rows = min(args.rows or 10**9, 2_000_000) if wl_key != "q6" else min(args.rows or 10**9, 100_000_000)
+        wl = None
+        if wl_key not in ("zillow", "zillow_csv", "q6_csv"):
+            os.environ.setdefault("CUDA_VISIBLE_DEVICES", "")
+            wl = build_workload_nopin(wl_args)
+        vals, last = [], None
+        # the secondary workload of the default pair gets fewer repeats so that the whole arm stays within a few minutes
+        steps, warm = (args.steps, args.warmup) if wl_key == keys[0] else (max(3, args.steps // 4), 1)
+        for i in range(warm + steps):
+            last = cpu_arm(args, wl_key, wl, hc)
+            if i >= warm:
+                vals.append(last["value"])
+        v = float(np.mean(vals))
+        out[wl_key] = (v, last, steps, warm)
+    k0 = keys[0]
+    v, last, _, _ = out[k0]
+    cfg = static_config(args, k0)
+    if args.workload == "both":
+        cfg["q6"] = static_config(args, "q6")
+    line = {"metric": "rows/sec on Zillow pipeline + TPC-H Q6" if args.workload in ("both", "zillow", "q6") else "rows/sec",
+            "impl": "reference", "value": v, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": (last["rows_total"] / v * 1e3) if last.get("rows_total") else None, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8/i64/f64", "data": "synthetic", "config": cfg,
+            "cpu_baseline": dict(last, value=v),
+            "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "host": hc}
+    if args.workload == "both":
+        v6, last6, st6, w6 = out["q6"]
+        line["q6"] = {"value": v6, "unit": "rows/s", "steps": st6, "warmup": w6, "cpu_baseline": dict(last6, value=v6),
+                      "e2e": {"value": v6, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
 
 
 # ------------------------------------------------------------------------------------------------------
-def main():
-    args = parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-
-    if args.impl == "reference":
-        if rank != 0:
-            return 0
-        import types
-        wl_args = types.SimpleNamespace(**vars(args))
-        wl_args.rows = min(args.rows or 10**9, 2_000_000) if args.workload != "q6" else min(args.rows or 10**9, 100_000_000)
-        wl = None
-        if args.workload not in ("zillow", "zillow_csv", "q6_csv"):
-            os.environ.setdefault("CUDA_VISIBLE_DEVICES", "")
-            wl = build_workload_nopin(wl_args)
-        vals = []
-        last = None
-        for i in range(args.warmup + args.steps):
-            last = cpu_zillow_reference(args.cpu_sample_rows, os.cpu_count() or 1) if args.workload == "zillow" else \
-                cpu_zillow_csv_reference(args.cpu_sample_rows, os.cpu_count() or 1) if args.workload == "zillow_csv" else \
-                cpu_q6_csv_port(args.cpu_sample_rows, os.cpu_count() or 1) if args.workload == "q6_csv" else \
-                cpu_port(wl, args.cpu_sample_rows, os.cpu_count() or 1)
-            if last is None:
-                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/zillow_ref missing and no port for this workload"}))
-                return 0
-            if i >= args.warmup:
-                vals.append(last["value"])
-        v = float(np.mean(vals))
-        names = {"zillow": "zillow_z1", "q6": "tpch_q6", "c1": "c1_map_filter", "aggbykey": "aggbykey_str", "zillow_csv": "zillow_z1_from_csv", "q6_csv": "tpch_q6_from_csv"}
-        line = {"metric": "rows/sec on Zillow pipeline + TPC-H Q6" if args.workload in ("zillow", "q6") else "rows/sec",
-                "impl": "reference", "value": v, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": (last["rows_total"] / v * 1e3) if last.get("rows_total") else None, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "u8/i64/f64",
-                "data": "synthetic", "config": {"workload": names[args.workload]},
-                "cpu_baseline": dict(last, value=v),
-                "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
-        return 0
-
-    if args.workload in ("zillow_csv", "q6_csv"):
-        return main_csv(args, rank, world, local)
+def measure(args, wl_key, rank, world, local, dist, hc):
+    """Device-resident `value`, `roofline`, end-to-end `e2e` (page-locked and pageable host inputs) and the CPU arm of one workload.
+    Returns the fields of its JSON object (rank 0) or None."""
     import torch
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_
-        dist = dist_
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from tuplex_b200 import backend, ir
-    backend.init([local])
-    wl = build_workload(args)
+    wargs = argparse.Namespace(**vars(args))
+    wargs.workload = wl_key
+    wl = build_workload(wargs)
     prog = wl["prog"]
     st = backend.Stage(prog)
     ep = prog.endpoint
@@ -391,8 +507,20 @@ def main():
     from concurrent.futures import ThreadPoolExecutor
     pool = ThreadPoolExecutor(max_workers=3)
 
+    def combine_partials(partials):
+        tot = 0.0
+        for p in partials:
+            tot = tot + p
+        if dist is not None:  # the one collective of the path: combine per-GPU partials, fixed rank order
+            t = torch.tensor([tot], dtype=torch.float64, device="cuda")
+            g = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(g, t)
+            tot = 0.0
+            for x in g:
+                tot = tot + float(x.item())
+        return tot
+
     def step_resident():
-        first = 0
         kms = 0.0
         launches = 0
         n_out = 0
@@ -400,6 +528,7 @@ def main():
         if ep == ir.C["TPLX_EP_HASH"]:
             st.hash_reset(local)
             st.hash_reserve(local, wl.get("nkeys", 1 << 20))
+
         def one_resident(b):
             r = st.run(b, 0)   # every block is its own task (row numbers per task), so blocks need not run in sequence
             inf = r.info
@@ -407,9 +536,9 @@ def main():
                    ir.bits_f64(r.aggregate_bits()[0]) if ep == ir.C["TPLX_EP_AGGREGATE"] else None)
             r.free()
             return out
-        # row stages: two blocks in flight on the GPU's two execution lanes (the latency-bound dense launch of one block
-        # overlaps the prefilter of the next). Aggregate scans are DRAM-bound (nothing to overlap) and hash stages share
-        # one table per device: those run one block at a time.
+        # row stages: blocks in flight on the GPU's execution lanes (the latency-bound dense launch of one block overlaps the
+        # prefilter of the next). Aggregate scans are DRAM-bound (nothing to overlap) and hash stages share one table per
+        # device: those run one block at a time.
         runner = pool.map if ep == ir.C["TPLX_EP_MEMORY"] else map
         for km, kl, no, part in runner(one_resident, dev_blocks):
             kms += km
@@ -418,17 +547,7 @@ def main():
             if part is not None:
                 partials.append(part)
         if ep == ir.C["TPLX_EP_AGGREGATE"]:
-            tot = 0.0
-            for p in partials:
-                tot = tot + p
-            if dist is not None:  # the one collective of the path: combine per-GPU partials, fixed rank order
-                t = torch.tensor([tot], dtype=torch.float64, device="cuda")
-                g = [torch.empty_like(t) for _ in range(world)]
-                dist.all_gather(g, t)
-                tot = 0.0
-                for x in g:
-                    tot = tot + float(x.item())
-            stats["result"] = tot
+            stats["result"] = combine_partials(partials)
         if ep == ir.C["TPLX_EP_HASH"]:
             fin = st.hash_finish(local)
             n_out = int(fin.info.n_out_rows)
@@ -437,8 +556,7 @@ def main():
             fin.free()
         stats.update(kernel_ms=kms, launches=launches, n_out=n_out)
 
-    def step_e2e():
-        first = 0
+    def step_e2e(blocks):
         d2h = 0
         h2d = 0
         zc = 0
@@ -448,25 +566,32 @@ def main():
         # three blocks in flight: the H2D copy of the next blocks (copy stream) overlaps the kernels and the result
         # fetch (D2H stream) of earlier ones.
         # Every block is its own task (row numbers start at 0 per task, like one TransformTask per partition group).
+        partials = []
+
         def one(block):
             cols, n = block
             r = st.run_host(local, cols, n, 0)
             inf = r.info
             nb = 0
+            part = None
             if ep == ir.C["TPLX_EP_MEMORY"]:
                 for c in r.columns():
                     nb += c.nbytes()
                 nb += r.exceptions().nbytes
             elif ep == ir.C["TPLX_EP_AGGREGATE"]:
-                r.aggregate_bits()
+                part = ir.bits_f64(r.aggregate_bits()[0])
                 nb += 8 * len(prog.accs)
-            out = (int(inf.h2d_bytes), int(inf.zero_copy_cols), nb)
+            out = (int(inf.h2d_bytes), int(inf.zero_copy_cols), nb, part)
             r.free()
             return out
-        for hb, z, nb in pool.map(one, wl["blocks"]):
+        for hb, z, nb, part in pool.map(one, blocks):
             h2d += hb
             zc = max(zc, z)
             d2h += nb
+            if part is not None:
+                partials.append(part)
+        if ep == ir.C["TPLX_EP_AGGREGATE"]:
+            stats["result_e2e"] = combine_partials(partials)
         if ep == ir.C["TPLX_EP_HASH"]:
             fin = st.hash_finish(local)
             for c in fin.columns():
@@ -476,78 +601,159 @@ def main():
         stats["h2d"] = h2d
         stats["zero_copy_cols"] = zc
 
-    for _ in range(max(args.warmup, 3)):
+    def timed(fn, k):
+        """K steps bracketed by barrier + synchronize on both sides; wall time of this rank."""
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(k):
+            fn()
+        sync_all()
+        return time.perf_counter() - t0
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    W = max(args.warmup, 3)
+    for _ in range(W):
         step_resident()
     clocks = Clocks(local)
-    sync_all()
     clocks.start()
-    t0 = time.perf_counter()
+    # the K-step region is repeated until min_region_s of it has been measured (a 20-step region of this stage is well under
+    # a second); every repeat is K steps between barrier + synchronize, the reported one is the median repeat (max over ranks)
+    reps = []
     kms = 0.0
     launches = 0
-    for _ in range(args.steps):
-        step_resident()
-        kms += stats["kernel_ms"]
-        launches += stats["launches"]
-    sync_all()
-    dt = time.perf_counter() - t0
+    spent = 0.0
+    while True:
+        kacc = lacc = 0
 
-    # end-to-end through the C ABI with host buffers (H2D of inputs + D2H of results inside the timed region)
-    e2e_steps = max(1, min(args.steps, 3))
-    step_e2e()
-    sync_all()
-    t1 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_e2e()
-    sync_all()
-    dt_e2e = time.perf_counter() - t1
-    clk = clocks.stop()  # sampled over both timed regions (device-resident steps and end-to-end steps)
+        def one_step():
+            nonlocal kacc, lacc
+            step_resident()
+            kacc += stats["kernel_ms"]
+            lacc += stats["launches"]
+        dt_r = max_over_ranks(timed(one_step, args.steps))
+        reps.append((dt_r, kacc, lacc))
+        spent += dt_r
+        if spent >= args.min_region_s or len(reps) >= 25:
+            break
+    reps.sort()
+    dt, kms, launches = reps[len(reps) // 2]
 
-    times = torch.tensor([dt, dt_e2e], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dt, dt_e2e = float(times[0]), float(times[1])
+    # end-to-end through the C ABI with host buffers (H2D of inputs + D2H of results inside the timed region), K steps
+    step_e2e(wl["blocks"])
+    dt_e2e = max_over_ranks(timed(lambda: step_e2e(wl["blocks"]), args.steps))
+    e2e_stats = dict(stats)
+    # the same with ordinary (pageable) host memory: what a caller pays who hands over plain malloc'ed partitions
+    dt_pg = None
+    pg_steps = max(1, min(args.steps, 3))
+    if world == 1 and not args.no_pageable and wl.get("pageable_blocks") is not None:
+        try:
+            pb = wl["pageable_blocks"]()
+            step_e2e(pb)
+            dt_pg = timed(lambda: step_e2e(pb), pg_steps)
+            pg_stats = dict(stats)
+            del pb
+        except MemoryError:
+            dt_pg = None
+    clk = clocks.stop()  # sampled over all timed regions (device-resident repeats and end-to-end steps)
 
+    line = None
     if rank == 0:
         rows_all = wl["rows"] * world
         ms_step = dt / args.steps * 1e3
         peak, peak_src = peaks()
         # algorithmic bytes: every input byte read once + output bytes written once
-        out_bytes = 0
-        if ep == ir.C["TPLX_EP_MEMORY"]:
-            out_bytes = stats.get("d2h", 0)
+        out_bytes = e2e_stats.get("d2h", 0) if ep == ir.C["TPLX_EP_MEMORY"] else 0
         alg_bytes = wl["in_bytes"] + out_bytes
         n_launch = max(1, len(dev_blocks))
         k_ms_per_launch = kms / args.steps / n_launch
-        # launches of different blocks overlap on the GPU's two execution lanes, so the per-launch event times can add up
+        # launches of different blocks overlap on the GPU's execution lanes, so the per-launch event times can add up
         # to more than the step: the device time the kernels really occupied is at most the step itself
         k_ms_step = min(kms / args.steps, ms_step)
         achieved = alg_bytes / (k_ms_step * 1e-3) / 1e9 if k_ms_step > 0 else 0.0
+        kname = {"zillow_z1": "stage_mask_kernel (prefilter, TMA-staged strings) + stage_rows_kernel (dense launch)",
+                 "tpch_q6": "fused_scan_agg_tma_kernel", "aggbykey_str": "stage_hash_kernel"}.get(
+            wl["name"], {0: "stage_rows_kernel", 1: "stage_agg_kernel", 2: "stage_hash_kernel"}[ep])
         line = {
-            "metric": "rows/sec on Zillow pipeline + TPC-H Q6" if args.workload in ("zillow", "q6") else "rows/sec",
-            "value": rows_all / (dt / args.steps), "unit": "rows/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8/i64/f64", "data": "synthetic",
-            "config": {"workload": wl["name"], "rows_per_gpu": wl["rows"], "blocks": len(dev_blocks), "description": wl["desc"],
-                       "l2": "inputs larger than L2 (every block >> 126 MB, distinct HBM buffers per block)",
-                       "out_rows_per_gpu": stats.get("n_out")},
+            "value": rows_all / (dt / args.steps), "unit": "rows/s", "ms_per_step": ms_step,
+            "timed_region": {"repeats": len(reps), "seconds_measured": spent, "reported": "median repeat of K steps, max over ranks",
+                             "min_ms_per_step": reps[0][0] / args.steps * 1e3, "max_ms_per_step": reps[-1][0] / args.steps * 1e3},
+            "checks": {"out_rows_per_gpu": stats.get("n_out"), "blocks": len(dev_blocks)},
             "clocks": clk,
-            "e2e": {"value": rows_all / (dt_e2e / e2e_steps), "unit": "rows/s", "h2d_bytes_per_step": stats.get("h2d", wl["in_bytes"]),
-                    "d2h_bytes_per_step": stats.get("d2h", 0), "steps": e2e_steps,
-                    "host_input_bytes_per_step": wl["in_bytes"], "zero_copy_cols": stats.get("zero_copy_cols", 0),
-                    "note": "h2d = explicit copies of the columns the prefilter reads; zero_copy_cols input columns stay in "
-                            "page-locked host memory and are read over PCIe for surviving rows only (late materialisation)"},
+            "e2e": {"value": rows_all / (dt_e2e / args.steps), "unit": "rows/s", "h2d_bytes_per_step": e2e_stats.get("h2d", wl["in_bytes"]),
+                    "d2h_bytes_per_step": e2e_stats.get("d2h", 0), "steps": args.steps, "inputs_prepinned": True,
+                    "host_input_bytes_per_step": wl["in_bytes"], "zero_copy_cols": e2e_stats.get("zero_copy_cols", 0),
+                    "note": "inputs lie in page-locked host memory before the timed region (inputs_prepinned); h2d = explicit copies of the "
+                            "columns the prefilter reads; zero_copy_cols input columns stay in host memory and are read over PCIe for "
+                            "surviving rows only (late materialisation); every output column and the exception records are fetched"},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": {0: "stage_rows_kernel (prefilter + dense launch)", 1: "fused_scan_agg_tma_kernel", 2: "stage_hash_kernel"}[ep]
-                         if wl["name"] in ("zillow_z1", "tpch_q6", "aggbykey_str") else {0: "stage_rows_kernel", 1: "stage_agg_kernel", 2: "stage_hash_kernel"}[ep],
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(wl, n_launch),
-                         "peak_source": peak_src, "algorithmic_bytes_per_row": alg_bytes / wl["rows"],
+            "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic(wl, n_launch), "peak_source": peak_src, "algorithmic_bytes_per_row": alg_bytes / wl["rows"],
                          "kernel_ms_per_launch": k_ms_per_launch, "kernel_share_of_step": k_ms_step / ms_step,
                          "launches_overlap": (kms / args.steps) > ms_step},
         }
+        if dt_pg is not None:
+            line["e2e"]["pageable"] = {"value": wl["rows"] / (dt_pg / pg_steps), "unit": "rows/s", "steps": pg_steps,
+                                       "h2d_bytes_per_step": pg_stats.get("h2d"), "zero_copy_cols": pg_stats.get("zero_copy_cols", 0),
+                                       "note": "same call with ordinary pageable numpy buffers (every column is copied; the driver stages the copies)"}
         if "result" in stats:
-            line["config"]["result"] = repr(stats["result"])
+            line["checks"]["result"] = repr(stats["result"])
+            line["checks"]["collective"] = "all_gather of the per-GPU partial (NCCL), combined in rank order" if world > 1 else None
         if not args.no_cpu_baseline and world == 1:  # the CPU arm is reported at N = 1 only
-            line["cpu_baseline"] = cpu_baseline(args, wl)
+            line["cpu_baseline"] = cpu_arm(args, wl_key, wl, hc)
+    # free this workload's device and pinned memory before the next one is built
+    for b in dev_blocks:
+        b.free()
+    st.close()
+    del dev_blocks, wl
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    return line
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        return reference_line(args)
+
+    if args.workload in ("zillow_csv", "q6_csv"):
+        return main_csv(args, rank, world, local)
+    import torch
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from tuplex_b200 import backend
+    backend.init([local])
+    hc = host_cores()
+    keys = ["zillow", "q6"] if args.workload == "both" else [args.workload]
+    parts = {k: measure(args, k, rank, world, local, dist, hc) for k in keys}
+    if rank == 0:
+        k0 = keys[0]
+        cfg = static_config(args, k0)
+        if args.workload == "both":
+            cfg["q6"] = static_config(args, "q6")
+        line = {"metric": "rows/sec on Zillow pipeline + TPC-H Q6" if args.workload in ("both", "zillow", "q6") else "rows/sec",
+                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8/i64/f64", "data": "synthetic", "config": cfg}
+        line.update(parts[k0])
+        if args.workload == "both":
+            line["q6"] = parts["q6"]
+            line["gpu_launches"] += parts["q6"]["gpu_launches"]
+        line["host"] = hc
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
@@ -725,8 +931,7 @@ def main_csv(args, rank, world, local):
                              "kernel_share_of_step": parse_ms_step / ms_step, "stage_ms_per_step": sms / args.steps,
                              "csv_gb_per_s": csv_bytes / (parse_ms_step * 1e-3) / 1e9}}
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_zillow_csv_reference(args.cpu_sample_rows, os.cpu_count() or 1) if args.workload == "zillow_csv" \
-                else cpu_q6_csv_port(args.cpu_sample_rows, os.cpu_count() or 1)
+            line["cpu_baseline"] = cpu_arm(args, args.workload, None, host_cores())
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()

@@ -12,6 +12,7 @@ long long h_rfind(const uint8_t *hb, unsigned ho, unsigned hl, unsigned hf, cons
 int h_eq(const uint8_t *hb, unsigned ho, unsigned hl, unsigned hf, const uint8_t *nb, unsigned no, unsigned nl, unsigned nf) {
     return str_eq(mk(hb, ho, hl, hf), mk(nb, no, nl, nf)); }
 int h_atoi(const uint8_t *b, unsigned o, unsigned l, long long *out) { int64_t v = 0; bool ok = str_to_i64(mk(b, o, l, 0), &v); *out = v; return ok; }
+void h_copy(uint8_t *dst, unsigned dofs, const uint8_t *sb, unsigned so, unsigned sl, unsigned sf) { str_copy(dst + dofs, mk(sb, so, sl, sf)); }
 unsigned h_lower4(unsigned w) { return lower4(w); }
 unsigned h_upper4(unsigned w) { return upper4(w); }
 long long h_slice_index(long long i, long long n) { return slice_index(i, n); }

@@ -325,3 +325,63 @@ def test_float_of_str_s2f(gpu):
     st, res, ora = run_both(prog, [col], len(vals))
     assert len(ora.exceptions) > 5
     assert_result_equals_oracle(res, ora, "float(str)")
+
+
+def _idiom_prog(fn, with_filter=True):
+    sc = frontend.StageCompiler([T_STR, T_I64], ["s", "k"])
+    sc.add_with_column("r", fn, 100001)
+    if with_filter:  # selective filter with heavy work behind it -> prefilter (mask kernel) + dense launch
+        sc.add_filter(lambda x: x['k'] == 2, 100002)
+        sc.add_with_column("t", lambda x: x['s'].replace(',', ';') + '|' + x['s'].upper() + ('%04d' % x['k']), 100003)
+        sc.add_with_column("u", lambda x: x['t'].find('BD') + int(x['s'][0:1].replace('-', '1').replace(' ', '2').replace(',', '3')
+                                                                   .replace('S', '4').replace('n', '5').replace('b', '6').replace('e', '7').replace('a', '8').replace('x', '9')), 100004)
+    return sc.finish_memory()
+
+
+@pytest.mark.parametrize("case", ["head_len", "number_before_marker", "after_last_sep", "both_as_expr", "miss_default_one", "miss_reuse", "miss_dynamic_k"])
+def test_fused_idioms_gpu_vs_oracle(gpu, case):
+    """TPLX_OP_SFINDE / TPLX_OP_SRFINDK on the device (and the unfused near misses) against the oracle, with and without
+    the prefilter split."""
+    import idiom_udfs as U
+    fn = getattr(U, case)
+    n = 40_000
+    cols, _ = U.make_columns(n, 3)
+    for with_filter in (False, True):
+        prog = _idiom_prog(fn, with_filter)
+        if with_filter:
+            assert prog.prefilter is not None
+        st, res, ora = run_both(prog, cols, n, first_row_no=3)
+        assert_result_equals_oracle(res, ora, f"{case} filter={with_filter}")
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 63, 64, 65, 255, 257, 8191, 8192, 8193, 100_003])
+def test_mask_stage_ragged_sizes_and_modes(gpu, n, monkeypatch):
+    """K1m (mask.cuh): bitmaps + survivor list for every tail shape; staged (TMA ring) == unstaged (global loads) == old
+    look-back prefilter (TPLX_NO_MASK=1) == oracle; MR = 1 and 2 rows per lane."""
+    import idiom_udfs as U
+    cols, _ = U.make_columns(n, n)
+    prog = _idiom_prog(U.number_before_marker, True)
+    ora = pyoracle.run_program(prog, cols, n, 11)
+    for env in ({}, {"TPLX_MASK_STAGE": "0"}, {"TPLX_MASK_MR": "2"}, {"TPLX_NO_MASK": "1"}):
+        for k in ("TPLX_MASK_STAGE", "TPLX_MASK_MR", "TPLX_NO_MASK"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        res = backend.Stage(prog).run_host(0, cols, n, 11)
+        assert_result_equals_oracle(res, ora, f"n={n} env={env}")
+
+
+def test_mask_stage_oversized_rows_fall_back_to_global(gpu):
+    """Tiles whose string bytes exceed the ring slot keep their global pointers: rare very long strings between short ones."""
+    rng = np.random.default_rng(5)
+    n = 30_000
+    base = ["3 bds , 2 ba", "1 bd", "x", "", "12 bds , 1 ba , 700 sqft"]
+    s = [base[i] for i in rng.integers(0, len(base), n)]
+    for i in rng.integers(0, n, 40):
+        s[i] = ("pad," * int(rng.integers(50, 3000))) + " 7 bds , 2 ba"
+    k = rng.integers(0, 4, n).astype(np.int64)
+    cols = [Column.from_values(s, T_STR), Column(T_I64, k)]
+    import idiom_udfs as U
+    prog = _idiom_prog(U.number_before_marker, True)
+    st, res, ora = run_both(prog, cols, n)
+    assert_result_equals_oracle(res, ora, "oversized rows")

@@ -67,6 +67,24 @@ def test_find_rfind_eq_fuzz(H):
         assert bool(H.h_eq(*args)) == (hh == nn), (h, n, hf, nf)
 
 
+def test_str_copy_fuzz(H):
+    """str_copy (word-wise, case-mapped) == byte-wise copy for every source / destination alignment and never touches a byte
+    outside [dst, dst + len)."""
+    rnd = random.Random(99)
+    alphabet = "abYZ09 ,./"
+    for it in range(20000):
+        n = rnd.randint(0, 45)
+        h = "".join(rnd.choice(alphabet) for _ in range(n))
+        flag = rnd.choice([0, 0, 1, 2])
+        sb = _buf(h.encode(), rnd.randint(0, 7))
+        so = int(np.where(sb == 0xAA)[0].size)
+        dofs = rnd.randint(0, 7)
+        dst = np.full(dofs + n + 9, 0xEE, dtype=np.uint8)
+        H.h_copy(dst.ctypes.data_as(ct.c_void_p), dofs, sb.ctypes.data_as(ct.c_void_p), so, n, flag)
+        assert dst[dofs:dofs + n].tobytes() == _case(h, flag).encode(), (h, flag, so, dofs)
+        assert (dst[:dofs] == 0xEE).all() and (dst[dofs + n:] == 0xEE).all(), (h, so, dofs)
+
+
 def test_case_words(H):
     rnd = random.Random(7)
     for _ in range(20000):

@@ -11,5 +11,6 @@ st = backend.Stage(W.zillow_program())
 blk = backend.Block.upload(0, cols, n)
 ms = []
 for it in range(6):
+    if it == 5: os.environ["TPLX_TRACE"] = "1"
     r = st.run(blk); inf = r.info; ms.append(inf.kernel_ms); r.free()
 print(os.environ.get("TPLX_GPU_LIB", "default").split("/")[-1], "rows", n, "kernel ms", ["%.3f" % m for m in ms[2:]], "-> %.2f G rows/s" % (n / (min(ms[2:]) * 1e-3) / 1e9))

@@ -97,7 +97,7 @@ __device__ __forceinline__ void key_write(const HashParams &H, uint8_t *regs, ui
             StrV s = VM<NTT>::RS(regs, H.key_slot[k] * VM<NTT>::SLOT_BYTES);
             blob[0] = (uint8_t)s.len; blob[1] = (uint8_t)(s.len >> 8); blob[2] = (uint8_t)(s.len >> 16); blob[3] = (uint8_t)(s.len >> 24);
             blob += 4;
-            for (uint32_t i = 0; i < s.len; ++i) blob[i] = sch(s, i);
+            str_copy(blob, s);
             blob += s.len;
         } else {
             uint64_t v = VM<NTT>::R(regs, H.key_slot[k] * VM<NTT>::SLOT_BYTES);

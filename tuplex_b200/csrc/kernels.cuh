@@ -339,8 +339,7 @@ __global__ void __launch_bounds__(NT) stage_rows_kernel(const KParams *__restric
                         sv.len = (uint32_t)m;
                         sv.flags = (uint32_t)(m >> 32);
                         oc.offsets[pre_keep + bit_rank(keep_bits, keep_pre, lr)] = (uint32_t)off;
-                        uint8_t *o = oc.bytes + off;
-                        for (uint32_t i = 0; i < sv.len; ++i) o[i] = sch(sv, i);
+                        str_copy(oc.bytes + off, sv);
                         off += sv.len;
                     }
                     if (tile == P.n_tiles - 1 && tid == 0) oc.offsets[pre_keep + n_keep] = (uint32_t)(pre_b + tile_b);

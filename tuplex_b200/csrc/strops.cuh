@@ -99,6 +99,35 @@ TPLX_HD uint32_t low_mask(uint32_t nbytes) {  // mask of the low nbytes (0..4) b
     return nbytes >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nbytes)) - 1u);
 }
 
+// Copy the (case-mapped) characters of s to dst, four at a time: dst is written with aligned 32-bit stores between an unaligned head
+// and tail (bytes that share a word with a neighbouring string are only ever written as bytes), src is read with aligned loads and a
+// funnel shift (memory contract above). Replaces `for i: dst[i] = sch(s, i)`: ~8 instructions per 4 characters instead of ~12 per character.
+TPLX_HD void str_copy(uint8_t *dst, const StrV &s) {
+    const uint32_t n = s.len;
+    uint32_t i = 0;
+    while (i < n && ((uintptr_t)(dst + i) & 3)) {
+        dst[i] = sch(s, i);
+        ++i;
+    }
+    if (i + 4 <= n) {
+        const uintptr_t a = (uintptr_t)(s.p + i);
+        const uint32_t *aw = (const uint32_t *)(a & ~(uintptr_t)3);
+        const uint32_t sh = (uint32_t)(a & 3) * 8;
+        uint32_t *dw = (uint32_t *)(dst + i);
+        if (sh == 0) {
+            for (; i + 4 <= n; i += 4) *dw++ = case4(*aw++, s.flags);
+        } else {
+            uint32_t cur = *aw++;
+            for (; i + 4 <= n; i += 4) {  // characters i..i+3 straddle two aligned words, both hold string bytes
+                const uint32_t nxt = *aw++;
+                *dw++ = case4(funnel_r(cur, nxt, sh), s.flags);
+                cur = nxt;
+            }
+        }
+    }
+    for (; i < n; ++i) dst[i] = sch(s, i);
+}
+
 // a == b (both possibly case-flagged)
 TPLX_HD_NOINLINE bool str_eq(const StrV &a, const StrV &b) {
     if (a.len != b.len) return false;
@@ -174,16 +203,55 @@ TPLX_HD_NOINLINE int64_t str_find(const StrV &h, const StrV &n) {
     return str_find_impl<TPLX_SF_NONE>(h, n);
 }
 
-// std::string::rfind: last occurrence or -1; empty needle -> len
+// std::string::rfind: last occurrence or -1; empty needle -> len.
+// Same SWAR filter as str_find, walking the haystack backwards four positions per step (one new aligned load per step).
+template <uint32_t HFLAGS>
+TPLX_HD int64_t str_rfind_impl(const StrV &h, const StrV &n) {
+    const uint32_t last = h.len - n.len;  // last admissible start
+    const uint32_t c0 = sch(n, 0);
+    const bool two = n.len >= 2;
+    const uint32_t c1 = two ? sch(n, 1) : 0;
+    const uintptr_t addr = (uintptr_t)h.p;
+    const uint32_t *aw = (const uint32_t *)(addr & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(addr & 3) * 8;
+    const uint32_t nwords = (uint32_t)(((addr & 3) + h.len + 3) >> 2);  // aligned words holding string bytes (>= 1)
+    int32_t k = (int32_t)(last >> 2);                                    // string word (characters 4k..4k+3) that holds position `last`
+    uint32_t hi1 = ((uint32_t)k + 1 < nwords) ? aw[k + 1] : 0u;
+    const uint32_t hi2 = ((uint32_t)k + 2 < nwords) ? aw[k + 2] : 0u;
+    uint32_t nxt = funnel_r(hi1, hi2, sh);  // string word k+1: only its first character is needed (2-character test of position 4k+3)
+    if (HFLAGS == TPLX_SF_LOWER) nxt = lower4(nxt);
+    if (HFLAGS == TPLX_SF_UPPER) nxt = upper4(nxt);
+    for (; k >= 0; --k) {
+        const uint32_t lo = aw[k];
+        uint32_t cur = funnel_r(lo, hi1, sh);
+        if (HFLAGS == TPLX_SF_LOWER) cur = lower4(cur);
+        if (HFLAGS == TPLX_SF_UPPER) cur = upper4(cur);
+        uint32_t m = eq_mask4(cur, c0);
+        if (two) m &= eq_mask4((cur >> 8) | (nxt << 24), c1);
+        const uint32_t valid = last - 4 * (uint32_t)k;  // positions 0..valid of this word are admissible
+        if (valid < 3) m &= low_mask(valid + 1);
+        while (m) {
+#ifdef __CUDA_ARCH__
+            const uint32_t bit = 31u - (uint32_t)__clz((int)m);
+#else
+            const uint32_t bit = 31u - (uint32_t)__builtin_clz(m);
+#endif
+            const uint32_t pos = 4 * (uint32_t)k + (bit >> 3);
+            if (match_at(h, pos, n, two ? 2 : 1)) return (int64_t)pos;
+            m ^= 1u << bit;
+        }
+        nxt = cur;
+        hi1 = lo;
+    }
+    return -1;
+}
+
 TPLX_HD_NOINLINE int64_t str_rfind(const StrV &h, const StrV &n) {
     if (n.len > h.len) return -1;
     if (n.len == 0) return (int64_t)h.len;
-    const uint8_t n0 = sch(n, 0);
-    for (int64_t i = (int64_t)(h.len - n.len); i >= 0; --i) {
-        if (sch(h, (uint32_t)i) != n0) continue;
-        if (match_at(h, (uint32_t)i, n, 1)) return i;
-    }
-    return -1;
+    if (h.flags == TPLX_SF_LOWER) return str_rfind_impl<TPLX_SF_LOWER>(h, n);
+    if (h.flags == TPLX_SF_UPPER) return str_rfind_impl<TPLX_SF_UPPER>(h, n);
+    return str_rfind_impl<TPLX_SF_NONE>(h, n);
 }
 
 TPLX_HD bool is_pyspace(uint8_t c) {

@@ -24,6 +24,7 @@
 #include "hashagg.cuh"
 #include "fused.cuh"
 #include "gather.cuh"
+#include "mask.cuh"
 #include "csv.cuh"
 
 using namespace tplx;
@@ -105,6 +106,7 @@ extern "C" int32_t tplx_gpu_init(const int32_t *devices, int32_t n) {
         CU(cudaFuncSetAttribute(stage_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d->smem_optin));
         CU(cudaFuncSetAttribute(stage_agg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d->smem_optin));
         CU(cudaFuncSetAttribute(stage_hash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d->smem_optin));
+        CU(cudaFuncSetAttribute(stage_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d->smem_optin));
         // extra execution lanes on the same GPU (chain d -> alt -> alt ...): TPLX_LANES lanes in all. Measured on the
         // Zillow bench: 2 lanes 6.18 G rows/s resident / 653 M rows/s end to end; 3 lanes 6.28 G / 625 M; 4 lanes as 3.
         // The end-to-end number is the headline, so the default stays 2.
@@ -515,6 +517,7 @@ struct tplx_result {
     std::vector<void *> owned;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
     double kernel_ms = 0, total_ms = 0, kernel_ms_extra = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> extra_ev;  // further kernel intervals on the lane's stream (timed lazily in result_info)
     uint32_t hidden = 0;  // trailing internal output columns
     uint64_t h2d_bytes = 0;       // explicit host->device copies of inputs (run_host)
     uint32_t zero_copy_cols = 0;  // input columns read in place from page-locked host memory
@@ -531,6 +534,7 @@ extern "C" int32_t tplx_gpu_result_free(tplx_result *r) {
     if (r->ev1) cudaEventDestroy(r->ev1);
     if (r->evk0) cudaEventDestroy(r->evk0);
     if (r->evk1) cudaEventDestroy(r->evk1);
+    for (auto &e : r->extra_ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (r->owned_block) tplx_gpu_block_free(r->owned_block);
     delete r;
     return TPLX_OK;
@@ -584,6 +588,7 @@ static int32_t run_rows(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_
 static int32_t device_scan(Device *d, const uint64_t *in, uint64_t *out, uint64_t n, bool write_total);
 static int32_t device_scan_batched(Device *d, uint64_t *arrays, uint64_t stride, uint32_t K, uint64_t n);
 static int32_t run_rows_prefiltered(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_t first_row_no, tplx_result *r);
+static int32_t run_mask(tplx_stage *ps, StageDev *psd, const tplx_block *b, tplx_result *ra);
 static int32_t run_agg(tplx_stage *s, StageDev *sd, const tplx_block *b, tplx_result *r);
 static int32_t run_hash(tplx_stage *s, StageDev *sd, const tplx_block *b, tplx_result *r);
 
@@ -927,6 +932,128 @@ static int32_t run_rows(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_
     return TPLX_OK;
 }
 
+// K1m (mask.cuh): the prefilter stage as a pure map -> bitmaps -> ascending survivor list + exception records.
+// Fills ra like run_rows would for a row-index stage: ra->out[0].data = survivor list, ra->n_out, ra->exc, ra->n_exc.
+static int32_t run_mask(tplx_stage *ps, StageDev *psd, const tplx_block *b, tplx_result *ra) {
+    Device *d = ra->dev;
+    const uint64_t n = b->n_rows;
+    ra->out.assign(1, OutCol{});
+    ra->out_types.assign(1, TPLX_T_I64);
+    ra->str_bytes.assign(1, 0);
+    CU(cudaEventRecord(ra->evk0, d->stream));
+    if (n == 0) {
+        CU(cudaEventRecord(ra->evk1, d->stream));
+        return TPLX_OK;
+    }
+    if (n > 0xFFFFFFFFull * 16) return fail(TPLX_E_UNSUPPORTED, "block too large for the mask stage");
+    MaskParams P;
+    memset(&P, 0, sizeof(P));
+    P.n_rows = n;
+    P.n_instr = (uint32_t)ps->instrs.size();
+    // the stage's only output is the row index (LDROW): the bitmaps carry it, so the trailing load is not evaluated
+    if (P.n_instr && ps->instrs.back().op == TPLX_OP_LDROW && ps->instrs.back().guard == TPLX_NOSLOT) P.n_instr -= 1;
+    P.n_in = (uint32_t)ps->in_types.size();
+    P.n_slots = std::max<uint32_t>(ps->hdr.n_slots, 1);
+    P.MR = getenv("TPLX_MASK_MR") ? (uint32_t)std::max(1, std::min(4, atoi(getenv("TPLX_MASK_MR")))) : 1;
+    const uint32_t TR = 32 * P.MR;
+    P.n_tiles = (uint32_t)((n + TR - 1) / TR);
+    P.off_bytes = (uint32_t)align_up((TR + 1) * 4, 16);
+    P.prog = psd->prog;
+    P.cpool = psd->cpool;
+    for (size_t c = 0; c < b->cols.size(); ++c) P.in[c] = b->cols[c];
+    // string columns the program loads are staged through the warps' shared-memory rings (TPLX_MASK_STAGE=0: plain loads)
+    const bool want_stage = !(getenv("TPLX_MASK_STAGE") && atoi(getenv("TPLX_MASK_STAGE")) == 0);
+    std::vector<uint32_t> cand;
+    for (uint32_t i = 0; i < P.n_instr && want_stage; ++i) {
+        const tplx_instr &in = ps->instrs[i];
+        if (in.op != TPLX_OP_LDCOL || in.flags != TPLX_T_STR) continue;
+        const uint32_t c = (uint32_t)in.imm;
+        if ((c < b->mapped.size() && b->mapped[c]) || (b->cols[c].type & COL_COMPACT)) continue;
+        if (std::find(cand.begin(), cand.end(), c) == cand.end()) cand.push_back(c);
+    }
+    const double slack = getenv("TPLX_MASK_SLACK") ? atof(getenv("TPLX_MASK_SLACK")) : 1.5;
+    auto cap_of = [&](uint32_t c) {
+        const double avg = (double)b->data_bytes[c] / (double)n;
+        return (uint32_t)std::min<uint64_t>(align_up((uint64_t)(avg * TR * slack) + 48, 16), 32768);
+    };
+    std::sort(cand.begin(), cand.end(), [&](uint32_t x, uint32_t y) { return cap_of(x) < cap_of(y); });
+    if (cand.size() > MASK_MAX_STAGED) cand.resize(MASK_MAX_STAGED);
+    uint32_t smem_total = 0;
+    const uint32_t smem_limit = getenv("TPLX_MASK_SMEM") ? (uint32_t)atoi(getenv("TPLX_MASK_SMEM")) : 72 * 1024;
+    for (;;) {  // drop the largest staged column until the CTA's shared memory fits the budget
+        P.n_staged = (uint32_t)cand.size();
+        uint32_t so = 0;
+        for (uint32_t k = 0; k < P.n_staged; ++k) {
+            P.st_col[k] = cand[k];
+            P.st_cap[k] = cap_of(cand[k]);
+            P.st_boff[k] = so;
+            so += P.st_cap[k];
+            P.st_ooff[k] = so;
+            so += P.off_bytes;
+        }
+        P.slot_bytes = (uint32_t)align_up(so, 128);
+        size_t off = align_up(std::max<size_t>(P.n_instr, 1) * sizeof(DInstr), 16);
+        P.smem_regs_off = (uint32_t)off;
+        off = align_up(off + (size_t)P.n_slots * NT * 8, 16);
+        P.smem_wcols_off = (uint32_t)off;
+        off = align_up(off + (size_t)MASK_WARPS * std::max<uint32_t>(P.n_in, 1) * sizeof(ColIn), 16);
+        P.smem_bar_off = (uint32_t)off;
+        off += MASK_WARPS * MASK_RING * 8;
+        P.smem_info_off = (uint32_t)off;
+        off = align_up(off + MASK_WARPS * MASK_RING * 2 * MASK_MAX_STAGED * 4, 128);
+        P.smem_ring_off = (uint32_t)off;
+        off += (size_t)MASK_WARPS * MASK_RING * P.slot_bytes;
+        smem_total = (uint32_t)off;
+        if (smem_total <= smem_limit || cand.empty()) break;
+        cand.pop_back();
+    }
+    if (smem_total > (uint32_t)d->smem_optin) return fail(TPLX_E_UNSUPPORTED, "mask stage needs more shared memory than one SM has");
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stage_mask_kernel, NT, smem_total));
+    if (occ < 1) return fail(TPLX_E_UNSUPPORTED, "mask kernel cannot be resident");
+    const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>((P.n_tiles + MASK_WARPS - 1) / MASK_WARPS, (uint32_t)(occ * d->prop.multiProcessorCount)));
+    P.scratch_per_thread = ps->materialises ? std::max<uint32_t>(ps->hdr.scratch_bytes, 64) : 0;
+    int32_t rc = ensure_scratch(d, (size_t)grid * NT * P.scratch_per_thread);
+    if (rc) return rc;
+    P.scratch = d->scratch;
+    const uint32_t n_words = P.n_tiles * P.MR;
+    const uint32_t nb = (n_words + CMP_NT - 1) / CMP_NT;
+    uint64_t *part = nullptr, *totals = nullptr;
+    MaskParams *dP = nullptr;
+    rc = dalloc(ra, &P.keep_words, n_words);
+    if (rc) return rc;
+    rc = dalloc(ra, &P.exc_words, n_words);
+    if (rc) return rc;
+    rc = dalloc(ra, &P.exc_codes, n);
+    if (rc) return rc;
+    rc = dalloc(ra, &part, (size_t)nb * 2);
+    if (rc) return rc;
+    rc = dalloc(ra, &totals, 2);
+    if (rc) return rc;
+    rc = dalloc(ra, &dP, 1);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(dP, &P, sizeof(P), cudaMemcpyHostToDevice, d->stream));
+    stage_mask_kernel<<<grid, NT, smem_total, d->stream>>>(dP);
+    CU(cudaGetLastError());
+    mask_count_kernel<<<nb, CMP_NT, 0, d->stream>>>(P.keep_words, P.exc_words, n_words, part);
+    mask_scan_kernel<<<1, CMP_NT, 0, d->stream>>>(part, nb, totals);
+    CU(cudaGetLastError());
+    uint64_t h_tot[2] = {0, 0};
+    CU(cudaMemcpyAsync(h_tot, totals, 16, cudaMemcpyDeviceToHost, d->stream));
+    CU(cudaStreamSynchronize(d->stream));
+    ra->n_out = h_tot[0];
+    ra->n_exc = h_tot[1];
+    rc = dalloc(ra, &ra->out[0].data, ra->n_out);
+    if (rc) return rc;
+    rc = dalloc(ra, &ra->exc, ra->n_exc);
+    if (rc) return rc;
+    mask_expand_kernel<<<nb, CMP_NT, 0, d->stream>>>(P.keep_words, P.exc_words, n_words, part, ra->out[0].data, P.exc_codes, psd->opids, ra->exc);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ra->evk1, d->stream));
+    ra->launches += 4;
+    return TPLX_OK;
+}
+
 // Selective pipelines: (1) prefilter stage over every row -> ascending list of surviving row indices,
 // (2) this stage densely over that list. Exception rows of both launches are merged and numbered like one
 // TransformTask would have numbered them (rows written + exceptions so far, TransformTask.cc:764,885).
@@ -944,13 +1071,17 @@ static int32_t run_rows_prefiltered(tplx_stage *s, StageDev *sd, const tplx_bloc
     auto drop_ra = [&]() {
         for (void *p : ra.owned) cudaFreeAsync(p, d->stream);
         ra.owned.clear();
-        cudaEventDestroy(ra.evk0);
-        cudaEventDestroy(ra.evk1);
+        if (ra.evk0) cudaEventDestroy(ra.evk0);
+        if (ra.evk1) cudaEventDestroy(ra.evk1);
+        ra.evk0 = ra.evk1 = nullptr;
     };
-    rc = run_rows(ps, psd, b, 0, &ra, nullptr, 0);
+    const bool use_mask = !(getenv("TPLX_NO_MASK") && atoi(getenv("TPLX_NO_MASK")));
+    rc = use_mask ? run_mask(ps, psd, b, &ra) : run_rows(ps, psd, b, 0, &ra, nullptr, 0);
     if (rc) { drop_ra(); return rc; }
+    // the prefilter's kernel interval is timed lazily (result_info): no host synchronisation for it here
+    r->extra_ev.emplace_back(ra.evk0, ra.evk1);
+    ra.evk0 = ra.evk1 = nullptr;
     float msa = 0;
-    CU(cudaEventElapsedTime(&msa, ra.evk0, ra.evk1));  // run_rows synchronised the stream already
     const uint64_t n_surv = ra.n_out;
     if (b->n_rows >= (1u << 16) && n_surv * 2 > b->n_rows) s->prefilter_enabled = false;  // not selective: stop using it
     // late columns that still live in host memory: bring over the surviving rows only (gather.cuh)
@@ -1260,6 +1391,14 @@ extern "C" int32_t tplx_gpu_result_info(tplx_result *r, tplx_result_info *info) 
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, r->evk0, r->evk1));
     r->kernel_ms = ms + r->kernel_ms_extra;
+    const bool trace = getenv("TPLX_TRACE") != nullptr;
+    if (trace) fprintf(stderr, "[tplx] stage kernels %.3f ms, gather %.3f ms", ms, r->kernel_ms_extra);
+    for (auto &e : r->extra_ev) {
+        CU(cudaEventElapsedTime(&ms, e.first, e.second));
+        r->kernel_ms += ms;
+        if (trace) fprintf(stderr, ", prefilter %.3f ms", ms);
+    }
+    if (trace) fprintf(stderr, "\n");
     CU(cudaEventElapsedTime(&ms, r->ev0, r->ev1));
     r->total_ms = ms;
     memset(info, 0, sizeof(*info));

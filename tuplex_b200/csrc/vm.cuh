@@ -317,8 +317,8 @@ struct VM {
                     if (y.len == 0) { WS(rb, dst, x.p, x.len, x.flags); break; }
                     uint8_t *o = scratch_alloc(t, x.len + y.len, opidx);
                     if (!o) break;
-                    for (uint32_t i = 0; i < x.len; ++i) o[i] = sch(x, i);
-                    for (uint32_t i = 0; i < y.len; ++i) o[x.len + i] = sch(y, i);
+                    str_copy(o, x);
+                    str_copy(o + x.len, y);
                     WS(rb, dst, o, x.len + y.len, 0);
                     break;
                 }
