@@ -511,13 +511,8 @@ def measure(args, wl_key, rank, world, local, dist, hc):
         tot = 0.0
         for p in partials:
             tot = tot + p
-        if dist is not None:  # the one collective of the path: combine per-GPU partials, fixed rank order
-            t = torch.tensor([tot], dtype=torch.float64, device="cuda")
-            g = [torch.empty_like(t) for _ in range(world)]
-            dist.all_gather(g, t)
-            tot = 0.0
-            for x in g:
-                tot = tot + float(x.item())
+        if dist is not None:  # the one collective of the path, inside the C ABI: ncclAllGather + fold in rank order
+            tot = ir.bits_f64(st.agg_finish(local, [ir.f64_bits(tot)])[0])
         return tot
 
     def step_resident():
@@ -549,6 +544,8 @@ def measure(args, wl_key, rank, world, local, dist, hc):
         if ep == ir.C["TPLX_EP_AGGREGATE"]:
             stats["result"] = combine_partials(partials)
         if ep == ir.C["TPLX_EP_HASH"]:
+            if dist is not None:  # hash-partitioned all-to-all between the GPUs' tables (tplx_gpu_stage_hash_exchange)
+                st.hash_exchange(local)
             fin = st.hash_finish(local)
             n_out = int(fin.info.n_out_rows)
             kms += fin.info.kernel_ms
@@ -593,6 +590,8 @@ def measure(args, wl_key, rank, world, local, dist, hc):
         if ep == ir.C["TPLX_EP_AGGREGATE"]:
             stats["result_e2e"] = combine_partials(partials)
         if ep == ir.C["TPLX_EP_HASH"]:
+            if dist is not None:
+                st.hash_exchange(local)
             fin = st.hash_finish(local)
             for c in fin.columns():
                 d2h += c.nbytes()
@@ -702,7 +701,8 @@ def measure(args, wl_key, rank, world, local, dist, hc):
                                        "note": "same call with ordinary pageable numpy buffers (every column is copied; the driver stages the copies)"}
         if "result" in stats:
             line["checks"]["result"] = repr(stats["result"])
-            line["checks"]["collective"] = "all_gather of the per-GPU partial (NCCL), combined in rank order" if world > 1 else None
+            line["checks"]["collective"] = ("tplx_gpu_agg_finish: ncclAllGather of the per-GPU partial + fold in rank order on the device"
+                                            if world > 1 else None)
         if not args.no_cpu_baseline and world == 1:  # the CPU arm is reported at N = 1 only
             line["cpu_baseline"] = cpu_arm(args, wl_key, wl, hc)
     # free this workload's device and pinned memory before the next one is built
@@ -738,6 +738,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from tuplex_b200 import backend
     backend.init([local])
+    if dist is not None:
+        from tuplex_b200 import dist as tdist
+        tdist.init_comm(local)  # this rank's NCCL communicator inside libtplx_gpu.so (id broadcast over the launcher's group)
     hc = host_cores()
     keys = ["zillow", "q6"] if args.workload == "both" else [args.workload]
     parts = {k: measure(args, k, rank, world, local, dist, hc) for k in keys}

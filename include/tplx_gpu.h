@@ -169,6 +169,31 @@ int32_t tplx_gpu_stage_hash_export_raw(tplx_stage *stage, int32_t device, tplx_r
 /* Drop the device's table (start a new job on the same stage). */
 int32_t tplx_gpu_stage_hash_reset(tplx_stage *stage, int32_t device);
 
+/* ---- multi-GPU: the one exchange step of the path ------------------------------------------- */
+/* One rank per (process, device) over NCCL (NVLink 5 / NVSwitch). Map / filter stages shard over ranks without any
+ * communication (one task per partition group, LocalBackend.cc:679-735); only aggregate endpoints exchange data:
+ * the combine of per-task partial aggregates (TransformTask.cc:218-299, LocalBackend.cc:917-960) and the merge of the
+ * per-task hash tables (LocalBackend::createFinalHashmap, LocalBackend.cc:2219-2376). NCCL is resolved at run time
+ * (dlopen): without it these calls return TPLX_E_UNSUPPORTED and nothing else in the library is affected. */
+#define TPLX_COMM_ID_BYTES 128
+/* rank 0 creates the id (ncclGetUniqueId); the host side hands it to every rank by its own means */
+int32_t tplx_gpu_comm_unique_id(uint8_t *id /* TPLX_COMM_ID_BYTES */);
+/* join: collective over all ranks (ncclCommInitRank); one communicator per device */
+int32_t tplx_gpu_comm_init(int32_t device, int32_t rank, int32_t world, const uint8_t *id);
+/* one process driving n devices (ncclCommInitAll): rank = position in `devices` */
+int32_t tplx_gpu_comm_init_local(const int32_t *devices, int32_t n);
+int32_t tplx_gpu_comm_info(int32_t device, int32_t *rank, int32_t *world);
+int32_t tplx_gpu_comm_destroy(int32_t device);
+/* AGGREGATE endpoint, collective: every rank passes its partial (n_accs raw 8-byte values, e.g. its blocks' results folded in
+ * block order); ncclAllGather + a fold in RANK ORDER on the device; every rank receives the same bits (fixed association:
+ * f64 sums are reproducible). Without a communicator (or world == 1) the partial is returned unchanged. */
+int32_t tplx_gpu_agg_finish(tplx_stage *stage, int32_t device, const int64_t *local_bits, int64_t *out_bits);
+/* HASH endpoint, collective: every key gets an owner rank = hash(key) mod world; each rank splits its table by owner on the
+ * device, sizes travel in one ncclAllGather, the packed (key, partial) records in grouped ncclSend / ncclRecv between device
+ * buffers (all-to-all), and every rank merges what it owns into a fresh table. Afterwards tplx_gpu_stage_hash_finish on
+ * rank r yields exactly the groups rank r owns; the union over ranks is the result. No-op for a single rank. */
+int32_t tplx_gpu_stage_hash_exchange(tplx_stage *stage, int32_t device);
+
 /* ---- CSV source (K6) ----------------------------------------------------------------------- */
 /* Replaces the reference's host CSV source in front of a TransformStage: CSVReader::read +
  * csvmonkey row/cell splitting (core/src/physical/CSVReader.cc:388-634, core/include/physical/csvmonkey.h:523-672)

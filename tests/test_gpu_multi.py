@@ -28,8 +28,12 @@ lo, hi = tdist.shard_range(n, rank, world)
 mine = [c.slice(lo, hi) for c in cols]
 prog = W.q6_program()
 st = backend.Stage(prog)
-part = ir.bits_f64(st.run_host(local, mine, hi - lo).aggregate_bits()[0])
-(total,) = tdist.combine_aggregate([part], [a.kind for a in prog.accs])
+tdist.init_comm(local)
+assert backend.comm_info(local) == (rank, world)
+part_bits = st.run_host(local, mine, hi - lo).aggregate_bits()
+total = ir.bits_f64(st.agg_finish(local, part_bits)[0])      # NCCL all-gather + rank-order fold inside the C ABI
+(total_t,) = tdist.combine_aggregate([ir.bits_f64(part_bits[0])], [a.kind for a in prog.accs])
+assert total == total_t, (total, total_t)                     # == the torch.distributed restatement of the same fold
 # expected: per-shard oracle trees combined in rank order
 exp = None
 for r in range(world):
@@ -46,12 +50,33 @@ lo, hi = tdist.shard_range(m, rank, world)
 hp = W.keyed_program()
 hs = backend.Stage(hp)
 hs.run_host(local, [c.slice(lo, hi) for c in kcols], hi - lo).info
-tdist.exchange_hash_tables(hs, local)
+tdist.exchange_hash_tables(hs, local)                          # owner-partitioned all-to-all on the device
 fin = hs.hash_finish(local)
-got = dict(zip(fin.column(0).to_values(), fin.column(1).to_values()))
+mine_k, mine_v = fin.column(0).to_values(), fin.column(1).to_values()
+assert len(set(mine_k)) == len(mine_k)
+# every rank holds the groups it owns: gather the shares (test plumbing) and compare the union with the oracle
+import pickle
+blob = pickle.dumps((mine_k, mine_v))
+shares = [None] * world
+dist.all_gather_object(shares, blob)
+got = {}
+n_total = 0
+for b in shares:
+    k, v = pickle.loads(b)
+    n_total += len(k)
+    got.update(zip(k, v))
 ora = pyoracle.run_program(hp, kcols, m)
-assert got == dict(zip(ora.values(0), ora.values(1))), "rank %d table differs" % rank
+assert n_total == len(got), "a key is owned by two ranks"
+assert got == dict(zip(ora.values(0), ora.values(1))), "rank %d: union of the owned groups differs from the oracle" % rank
+assert 0 < len(mine_k) < len(got)
+# a second exchange round on a fresh table: uniform keys, f64 partials are not used here (i64 sums are exact)
+hs.hash_reset(local)
+hs.run_host(local, [c.slice(lo, hi) for c in kcols], hi - lo).info
+tdist.exchange_hash_tables(hs, local)
+fin2 = hs.hash_finish(local)
+assert dict(zip(fin2.column(0).to_values(), fin2.column(1).to_values())) == dict(zip(mine_k, mine_v))
 dist.barrier()
+backend.comm_destroy(local)
 dist.destroy_process_group()
 print("rank", rank, "ok", total)
 '''
@@ -72,3 +97,58 @@ def test_two_gpus_nccl(gpu, tmp_path):
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
     assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
+
+
+def test_two_gpus_one_process_local_comm(gpu):
+    """One process driving two devices (tplx_gpu_comm_init_local = ncclCommInitAll), one host thread per device: the
+    collectives of the C ABI (agg_finish, hash_exchange) against the oracle."""
+    from concurrent.futures import ThreadPoolExecutor
+    import numpy as np
+    from tuplex_b200 import backend, dist as tdist, ir, workloads as W
+    from oracle import pyoracle
+    if backend.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    devs = [0, 1]
+    backend.init(devs)
+    backend.comm_init_local(devs)
+    try:
+        n = 2_000_000
+        cols = W.gen_lineitem(n, seed=9)
+        prog = W.q6_program()
+        st = backend.Stage(prog)
+
+        def q6(r):
+            lo, hi = tdist.shard_range(n, r, 2)
+            bits = st.run_host(devs[r], [c.slice(lo, hi) for c in cols], hi - lo).aggregate_bits()
+            return st.agg_finish(devs[r], bits)[0]
+        with ThreadPoolExecutor(2) as ex:
+            a, b = list(ex.map(q6, range(2)))
+        assert a == b
+        exp = None
+        for r in range(2):
+            lo, hi = tdist.shard_range(n, r, 2)
+            v = ir.bits_f64(pyoracle.run_program(prog, [c.slice(lo, hi) for c in cols], hi - lo).acc_tree[0])
+            exp = v if exp is None else exp + v
+        assert ir.bits_f64(a) == exp
+        m = 300_000
+        kcols = W.gen_keyed(m, 5000, seed=3)
+        hp = W.keyed_program()
+        hs = backend.Stage(hp)
+
+        def byk(r):
+            lo, hi = tdist.shard_range(m, r, 2)
+            hs.run_host(devs[r], [c.slice(lo, hi) for c in kcols], hi - lo).info
+            hs.hash_exchange(devs[r])
+            fin = hs.hash_finish(devs[r])
+            return fin.column(0).to_values(), fin.column(1).to_values()
+        with ThreadPoolExecutor(2) as ex:
+            shares = list(ex.map(byk, range(2)))
+        got = {}
+        for k, v in shares:
+            got.update(zip(k, v))
+        ora = pyoracle.run_program(hp, kcols, m)
+        assert sum(len(k) for k, _ in shares) == len(got)
+        assert got == dict(zip(ora.values(0), ora.values(1)))
+    finally:
+        for dv in devs:
+            backend.comm_destroy(dv)

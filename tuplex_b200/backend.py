@@ -99,6 +99,13 @@ def lib():
         "tplx_gpu_stage_hash_export_raw": ([vp, i32, P(vp)], i32),
         "tplx_gpu_stage_hash_merge": ([vp, vp], i32),
         "tplx_gpu_stage_hash_reset": ([vp, i32], i32),
+        "tplx_gpu_comm_unique_id": ([vp], i32),
+        "tplx_gpu_comm_init": ([i32, i32, i32, vp], i32),
+        "tplx_gpu_comm_init_local": ([P(i32), i32], i32),
+        "tplx_gpu_comm_info": ([i32, P(i32), P(i32)], i32),
+        "tplx_gpu_comm_destroy": ([i32], i32),
+        "tplx_gpu_agg_finish": ([vp, i32, P(i64), P(i64)], i32),
+        "tplx_gpu_stage_hash_exchange": ([vp, i32], i32),
         "tplx_gpu_csv_upload": ([i32, vp, u64, P(vp)], i32),
         "tplx_gpu_csv_buffer_free": ([vp], i32),
         "tplx_gpu_csv_parse": ([vp, P(CCsvDesc), P(vp), P(vp)], i32),
@@ -138,6 +145,40 @@ def init(devices: Optional[Sequence[int]] = None):
 
 def device_count() -> int:
     return lib().tplx_gpu_device_count()
+
+
+# ---- communicator (the one exchange step of the path; include/tplx_gpu.h "multi-GPU") -------------------------------
+COMM_ID_BYTES = ir.C["TPLX_COMM_ID_BYTES"]
+
+
+def comm_unique_id() -> bytes:
+    buf = ct.create_string_buffer(COMM_ID_BYTES)
+    _check(lib().tplx_gpu_comm_unique_id(buf), "tplx_gpu_comm_unique_id")
+    return buf.raw
+
+
+def comm_init(device: int, rank: int, world: int, uid: bytes):
+    """Collective over all ranks (one rank per process and device)."""
+    init([device])
+    buf = ct.create_string_buffer(bytes(uid), COMM_ID_BYTES)
+    _check(lib().tplx_gpu_comm_init(device, rank, world, buf), "tplx_gpu_comm_init")
+
+
+def comm_init_local(devices: Sequence[int]):
+    """One process driving several devices: rank = position in `devices`."""
+    init(devices)
+    arr = (ct.c_int32 * len(devices))(*devices)
+    _check(lib().tplx_gpu_comm_init_local(arr, len(devices)), "tplx_gpu_comm_init_local")
+
+
+def comm_info(device: int):
+    r, w = ct.c_int32(), ct.c_int32()
+    rc = lib().tplx_gpu_comm_info(device, ct.byref(r), ct.byref(w))
+    return (r.value, w.value) if rc == 0 else None
+
+
+def comm_destroy(device: int):
+    lib().tplx_gpu_comm_destroy(device)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -251,6 +292,19 @@ class Stage:
         r = Result(h, self, None)
         r._keep = keep
         return r
+
+    def agg_finish(self, device: int, local_bits: Sequence[int]) -> List[int]:
+        """Collective: combine this rank's partial aggregate with every other rank's, in rank order (tplx_gpu_agg_finish)."""
+        n = len(self.program.accs)
+        src = (ct.c_int64 * n)(*[ir._as_i64(b) for b in local_bits])
+        dst = (ct.c_int64 * n)()
+        _check(lib().tplx_gpu_agg_finish(self._h, device, src, dst), "tplx_gpu_agg_finish")
+        return [v & ((1 << 64) - 1) for v in dst]
+
+    def hash_exchange(self, device: int):
+        """Collective: hash-partitioned all-to-all of the per-rank tables; afterwards hash_finish yields the groups this
+        rank owns (tplx_gpu_stage_hash_exchange)."""
+        _check(lib().tplx_gpu_stage_hash_exchange(self._h, device), "tplx_gpu_stage_hash_exchange")
 
     def hash_reserve(self, device: int, expected_keys: int):
         _check(lib().tplx_gpu_stage_hash_reserve(self._h, device, expected_keys), "tplx_gpu_stage_hash_reserve")

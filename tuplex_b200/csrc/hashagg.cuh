@@ -323,16 +323,25 @@ __global__ void hash_rehash(HashTableDev old, HashTableDev neu, uint32_t n_accs,
     for (uint32_t k = 0; k < n_accs; ++k) neu.accs[(size_t)k * neu.cap + idx] = old.accs[(size_t)k * old.cap + i];
 }
 
-// finish: flag occupied slots (uint64 0/1 for the scan) ...
-__global__ void hash_flag_slots(HashTableDev T, uint64_t *flags) {
+// Owner rank of a key in the multi-GPU exchange: a function of the key's hash only (state = hash | 2), so every rank
+// computes the same owner for equal keys. The high bits are independent of the bits that pick the table slot.
+struct HashSel {
+    int32_t owner;   // -1: every occupied slot, else only slots whose key is owned by this rank
+    uint32_t world;
+};
+__device__ __forceinline__ bool slot_selected(uint64_t st, HashSel sel) {
+    return st >= 2 && (sel.owner < 0 || (uint32_t)((st >> 40) % sel.world) == (uint32_t)sel.owner);
+}
+// finish: flag selected slots (uint64 0/1 for the scan) ...
+__global__ void hash_flag_slots(HashTableDev T, uint64_t *flags, HashSel sel) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < T.cap) flags[i] = T.state[i] >= 2 ? 1 : 0;
+    if (i < T.cap) flags[i] = slot_selected(T.state[i], sel) ? 1 : 0;
 }
 // ... per-key string lengths of key column kc at compacted position (for the per-column offset scan)
 __global__ void hash_key_lens(HashTableDev T, const uint64_t *pos, uint32_t n_keys, const uint32_t *key_types, uint32_t kc,
-                              uint64_t *lens) {
+                              uint64_t *lens, HashSel sel) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= T.cap || T.state[i] < 2) return;
+    if (i >= T.cap || !slot_selected(T.state[i], sel)) return;
     const uint8_t *blob = T.heap + (T.keyoff[i] & ((1ull << 40) - 1));
     for (uint32_t k = 0; k < kc; ++k) {
         if (key_types[k] == TPLX_T_STR) {
@@ -355,12 +364,12 @@ struct HashEmit {
     uint64_t *acc_data[TPLX_MAX_ACCS];
 };
 // ... and emit key + accumulator columns at the compacted position
-__global__ void hash_emit(HashTableDev T, const uint64_t *pos, uint64_t n_out, HashEmit E) {
+__global__ void hash_emit(HashTableDev T, const uint64_t *pos, uint64_t n_out, HashEmit E, HashSel sel) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0)
         for (uint32_t k = 0; k < E.n_keys; ++k)
             if (E.key_types[k] == TPLX_T_STR) E.key_offsets[k][n_out] = (uint32_t)E.key_lens_scan[k][n_out];
-    if (i >= T.cap || T.state[i] < 2) return;
+    if (i >= T.cap || !slot_selected(T.state[i], sel)) return;
     const uint64_t o = pos[i];
     const uint8_t *blob = T.heap + (T.keyoff[i] & ((1ull << 40) - 1));
     for (uint32_t k = 0; k < E.n_keys; ++k) {

@@ -1461,3 +1461,4 @@ extern "C" int32_t tplx_gpu_result_fetch_aggregate(tplx_result *r, int64_t *acc_
 #include "tplx_gpu_rowfmt.inl"
 #include "tplx_gpu_hash.inl"
 #include "tplx_gpu_csv.inl"
+#include "tplx_gpu_comm.inl"

@@ -182,12 +182,17 @@ static int32_t run_hash(tplx_stage *s, StageDev *sd, const tplx_block *b, tplx_r
 }
 
 // packed block = key columns followed by one 8-byte column per accumulator (raw partials, no init)
+static int32_t hash_merge_locked(tplx_stage *s, const tplx_block *packed);
 extern "C" int32_t tplx_gpu_stage_hash_merge(tplx_stage *s, const tplx_block *packed) {
     if (!s || !packed || s->hdr.endpoint != TPLX_EP_HASH) return fail(TPLX_E_BADARG, "hash_merge: bad arguments");
+    std::lock_guard<std::mutex> lk(packed->dev->mu);
+    return hash_merge_locked(s, packed);
+}
+static int32_t hash_merge_locked(tplx_stage *s, const tplx_block *packed) {
     const uint32_t nk = s->hdr.n_keys, na = (uint32_t)s->accs.size();
     if (packed->cols.size() != nk + na) return fail(TPLX_E_BADARG, "hash_merge: packed block must hold key + accumulator columns");
+    if (packed->n_rows == 0) return TPLX_OK;
     Device *d = packed->dev;
-    std::lock_guard<std::mutex> lk(d->mu);
     CU(cudaSetDevice(d->id));
     if (packed->ready) CU(cudaStreamWaitEvent(d->stream, packed->ready, 0));
     StageDev *sd = nullptr;
@@ -247,12 +252,17 @@ extern "C" int32_t tplx_gpu_stage_hash_merge(tplx_stage *s, const tplx_block *pa
     return rc;
 }
 
-// flags bit0: raw accumulators (no init) — used for the multi-GPU exchange before the owner finishes
+// raw: accumulators without the initial value — the form exchanged between GPUs before the owner finishes.
+// sel: which slots to emit (all, or the keys one rank owns).
+static int32_t hash_export_locked(tplx_stage *s, Device *d, bool raw, HashSel sel, tplx_result **out);
 static int32_t hash_finish_impl(tplx_stage *s, int32_t device, bool raw, tplx_result **out) {
     Device *d = get_device(device);
     if (!d) return fail(TPLX_E_NODEVICE, "hash_finish: device not initialised (no CPU fallback)");
     if (!s || !out || s->hdr.endpoint != TPLX_EP_HASH) return fail(TPLX_E_BADARG, "hash_finish: not a hash stage");
     std::lock_guard<std::mutex> lk(d->mu);
+    return hash_export_locked(s, d, raw, HashSel{-1, 1}, out);
+}
+static int32_t hash_export_locked(tplx_stage *s, Device *d, bool raw, HashSel sel, tplx_result **out) {
     CU(cudaSetDevice(d->id));
     StageDev *sd = nullptr;
     int32_t rc = stage_dev(s, d, &sd);
@@ -276,7 +286,7 @@ static int32_t hash_finish_impl(tplx_stage *s, int32_t device, bool raw, tplx_re
     rc = dalloc(r, &pos, T.cap + 1);
     if (rc) return rc;
     const uint32_t nb = (uint32_t)((T.cap + 255) / 256);
-    hash_flag_slots<<<nb, 256, 0, d->stream>>>(T, pos);
+    hash_flag_slots<<<nb, 256, 0, d->stream>>>(T, pos, sel);
     rc = device_scan(d, pos, pos, T.cap, true);
     if (rc) return rc;
     uint64_t n_out = 0;
@@ -302,7 +312,7 @@ static int32_t hash_finish_impl(tplx_stage *s, int32_t device, bool raw, tplx_re
             rc = dalloc(r, &lens, n_out + 1);
             if (rc) return rc;
             CU(cudaMemsetAsync(lens, 0, (n_out + 1) * 8, d->stream));
-            hash_key_lens<<<nb, 256, 0, d->stream>>>(T, pos, nk, d_types, k, lens);
+            hash_key_lens<<<nb, 256, 0, d->stream>>>(T, pos, nk, d_types, k, lens, sel);
             rc = device_scan(d, lens, lens, n_out, true);
             if (rc) return rc;
             uint64_t tot = 0;
@@ -344,7 +354,7 @@ static int32_t hash_finish_impl(tplx_stage *s, int32_t device, bool raw, tplx_re
                 default: E.acc_init[k] = (int64_t)0xFFF0000000000000ull; break;
             }
         }
-    hash_emit<<<nb, 256, 0, d->stream>>>(T, pos, n_out, E);
+    hash_emit<<<nb, 256, 0, d->stream>>>(T, pos, n_out, E, sel);
     CU(cudaGetLastError());
     CU(cudaEventRecord(r->evk1, d->stream));
     CU(cudaEventRecord(r->ev1, d->stream));

@@ -6,9 +6,12 @@ sequential combine of partial aggregates on the driver (TransformTask.cc:278-299
 pairwise, LocalBackend.cc:2288-2375). Here: blocks are sharded contiguously over ranks (so that concatenating
 per-rank outputs in rank order preserves input order, LocalBackend.cc:1104-1152), the map/filter phase needs
 no communication, and only aggregate endpoints exchange data:
-  aggregate       -> all_gather of the per-rank partial, combined in rank order (fixed association)
-  aggregateByKey  -> all_gather of every rank's raw (key, partial) table, merged into each rank's table
-The backend is NCCL on GPUs (NVLink/NVSwitch) and gloo in the CPU tests.
+  aggregate       -> ncclAllGather of the per-rank partial + fold in rank order on the device (tplx_gpu_agg_finish)
+  aggregateByKey  -> owner = hash(key) mod world, grouped ncclSend/ncclRecv all-to-all of packed (key, partial) records
+                     between device buffers, local merge (tplx_gpu_stage_hash_exchange); nothing passes through the host
+Both live inside the C ABI (csrc/tplx_gpu_comm.inl); this module only bootstraps the communicator (the 128-byte NCCL id travels
+over the process group the launcher already set up) and shards work. combine_aggregate / allgather_arrays are the
+torch.distributed restatement of the same rank-order fold, kept for the gloo (CPU) tests of the host-side logic.
 """
 from __future__ import annotations
 
@@ -24,6 +27,22 @@ def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
     base, rem = divmod(n_items, world)
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+def init_comm(device: int, group=None):
+    """Create this rank's NCCL communicator inside libtplx_gpu.so. Collective over the torch.distributed group: rank 0
+    draws the id, every rank joins with its own device."""
+    import torch
+    import torch.distributed as dist
+    from . import backend
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if backend.comm_info(device) is not None:
+        return rank, world
+    uid = backend.comm_unique_id() if rank == 0 else bytes(backend.COMM_ID_BYTES)
+    t = torch.tensor(list(uid), dtype=torch.uint8, device=_device_for(dist))
+    dist.broadcast(t, src=0, group=group)
+    backend.comm_init(device, rank, world, bytes(t.cpu().tolist()))
+    return rank, world
 
 
 def _combine(kind: int, a, b):
@@ -87,34 +106,7 @@ def allgather_arrays(arrays: Sequence[np.ndarray], group=None) -> List[List[np.n
 
 
 def exchange_hash_tables(stage, device: int, group=None):
-    """aggregateByKey across ranks: every rank exports its raw table (keys + partials without the initial
-    value), all tables are all-gathered, and each rank merges the others' rows into its own table with the
-    accumulators' combine operation. Afterwards every rank's table holds the global result."""
-    import torch.distributed as dist
-    from . import backend
-    from .ir import T_STR
-    rank = dist.get_rank(group)
-    raw = stage.hash_finish(device, raw=True)
-    cols = raw.columns()
-    raw.free()
-    flat: List[np.ndarray] = []
-    for c in cols:
-        flat.append(c.data)
-        if c.type == T_STR:
-            flat.append(c.offsets)
-    gathered = allgather_arrays(flat, group)
-    for r, arrs in enumerate(gathered):
-        if r == rank:
-            continue
-        it = iter(arrs)
-        rcols = []
-        for c in cols:
-            data = next(it)
-            offs = next(it) if c.type == T_STR else None
-            rcols.append(backend.Column(c.type, data, offs))
-        n = len(rcols[0])
-        if n == 0:
-            continue
-        blk = backend.Block.upload(device, rcols, n)
-        stage.hash_merge(blk)
-        blk.free()
+    """aggregateByKey across ranks, on the device (tplx_gpu_stage_hash_exchange): afterwards every rank's table holds exactly
+    the groups it owns (owner = hash(key) mod world); the union over ranks is the global result."""
+    init_comm(device, group)
+    stage.hash_exchange(device)
