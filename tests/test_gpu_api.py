@@ -348,3 +348,40 @@ def test_csv_aggregate_by_key_and_unique(ctx, tmp_path):
             assert sorted(tags) == ["t0", "t1", "t2", "x"]
         finally:
             cs.MAX_CHUNK = 0xFFFFFFFF - (1 << 20)
+
+
+def test_unique_keeps_rows_from_the_interpreter_path(ctx, tmp_path):
+    """unique(): rows outside the normal case (other type in parallelize, CSV rows with a null / unparsable cell, rows whose UDF
+    raised on the device) are resolved by the interpreter and join the result set (ResolveTask feeds the same hash sink)."""
+    assert sorted(ctx.parallelize([1, 2, "a", 1]).unique().collect(), key=str) == [1, 2, "a"]
+    got = ctx.parallelize([(1, "x"), (2, "y"), (1, "x"), (None, "z"), (2, "y"), (None, "z")]).unique().collect()
+    assert sorted(got, key=repr) == sorted([(1, "x"), (2, "y"), (None, "z")], key=repr)
+    # a UDF that raises on the device for some rows and is resolved: the resolved values take part in unique()
+    ds = ctx.parallelize([(6, 3), (5, 0), (8, 4), (7, 0), (4, 2)]).map(lambda a, b: a // b).resolve(ZeroDivisionError, lambda a, b: -1)
+    assert sorted(ds.unique().collect()) == [-1, 2]
+    p = tmp_path / "u.csv"
+    p.write_text("a,b\n1,x\n2,y\n,z\n1,x\nn/a,w\n2,y\n")
+    rows = ctx.csv(str(p)).unique().collect()
+    assert sorted(rows, key=repr) == sorted([(1, "x"), (2, "y"), (None, "z"), ("n/a", "w")], key=repr)
+
+
+def test_lazy_csv_column_read_by_the_prefilter_is_rejected(gpu):
+    """C-ABI contract check: a column parsed with col_lazy carries cell references; a stage whose prefilter loads it must be
+    refused (TPLX_E_BADARG) instead of reading the references as offsets."""
+    from tuplex_b200 import backend, frontend, ir
+    raw = b"s,k\n" + b"".join(b"%d bds ,%d\n" % (i % 7, i % 3) for i in range(5000))
+    sc = frontend.StageCompiler([ir.T_STR, ir.T_I64], ["s", "k"])
+    sc.add_with_column("n", lambda x: int(x["s"][0:1]), 100001)
+    sc.add_filter(lambda x: x["n"] == 2, 100002)
+    sc.add_with_column("t", lambda x: x["s"].replace("bds", "beds") + "!" + x["s"].upper(), 100003)
+    sc.add_with_column("u", lambda x: x["t"].find("BDS") + int(x["s"][0:1]), 100004)
+    prog = sc.finish_memory()
+    assert prog.prefilter is not None
+    buf = backend.CsvBuffer(0, raw)
+    good = buf.parse([ir.T_STR, ir.T_I64], header=True)            # eager: fine
+    res = backend.Stage(prog).run(good.block)
+    assert int(res.info.n_out_rows) == sum(1 for i in range(5000) if i % 7 == 2)
+    bad = buf.parse([ir.T_STR, ir.T_I64], header=True, lazy=[0])    # column 0 is what the prefilter reads
+    with pytest.raises(backend.GpuBackendError) as e:
+        backend.Stage(prog).run(bad.block)
+    assert "col_lazy" in str(e.value)

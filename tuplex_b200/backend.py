@@ -214,7 +214,9 @@ class Column:
         if self.type == T_STR:
             raw = self.data.tobytes()
             o = self.offsets
-            return [raw[o[i]:o[i + 1]].decode("utf-8") for i in range(len(o) - 1)]
+            # device string ops are byte based (ASCII case mapping, byte slices): a slice may cut a multi-byte sequence. Decode like
+            # csvsource._text does, so that such a cell becomes a row value instead of failing the whole collect()
+            return [raw[o[i]:o[i + 1]].decode("utf-8", "replace") for i in range(len(o) - 1)]
         if self.type == T_BOOL:
             return [bool(v) for v in self.data.tolist()]
         return self.data.tolist()

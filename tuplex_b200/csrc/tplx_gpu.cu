@@ -630,8 +630,14 @@ extern "C" int32_t tplx_gpu_stage_run(tplx_stage *s, const tplx_block *b, int64_
             for (uint8_t m : b->mapped) lazy = lazy || m == 2;
             // lazy columns are materialised between the two launches, so such blocks always take the two-launch path
             // (also after the prefilter was switched off for not being selective)
+            bool lazy_read_early = false;  // a lazy column holds cell references, not offsets: the prefilter must not load it
+            if (lazy && s->prefilter)
+                for (const tplx_instr &in : s->prefilter->instrs)
+                    if (in.op == TPLX_OP_LDCOL && (size_t)in.imm < b->mapped.size() && b->mapped[in.imm] == 2) lazy_read_early = true;
             if (lazy && !s->prefilter)
                 rc = fail(TPLX_E_UNSUPPORTED, "stage_run: block has lazy CSV columns but the stage has no prefilter; parse without col_lazy");
+            else if (lazy_read_early)
+                rc = fail(TPLX_E_BADARG, "stage_run: a column parsed with col_lazy is read by the stage's prefilter; parse it eagerly");
             else
                 rc = (s->prefilter && (s->prefilter_enabled || lazy)) ? run_rows_prefiltered(s, sd, b, first_row_no, r)
                                                                         : run_rows(s, sd, b, first_row_no, r, nullptr, 0);
@@ -1075,6 +1081,10 @@ static int32_t run_rows_prefiltered(tplx_stage *s, StageDev *sd, const tplx_bloc
         if (ra.evk1) cudaEventDestroy(ra.evk1);
         ra.evk0 = ra.evk1 = nullptr;
     };
+    struct OnExit {  // CU(...) early returns release the prefilter's temporaries too (drop_ra is idempotent)
+        decltype(drop_ra) &f;
+        ~OnExit() { f(); }
+    } ra_guard{drop_ra};
     const bool use_mask = !(getenv("TPLX_NO_MASK") && atoi(getenv("TPLX_NO_MASK")));
     rc = use_mask ? run_mask(ps, psd, b, &ra) : run_rows(ps, psd, b, 0, &ra, nullptr, 0);
     if (rc) { drop_ra(); return rc; }
@@ -1090,9 +1100,13 @@ static int32_t run_rows_prefiltered(tplx_stage *s, StageDev *sd, const tplx_bloc
     bool any_mapped = false;
     for (uint8_t m : b->mapped) any_mapped = any_mapped || m;
     if (any_mapped && n_surv) {
-        cudaEvent_t g0, g1;
-        CU(cudaEventCreate(&g0));
-        CU(cudaEventCreate(&g1));
+        struct EvPair {  // released on every exit path
+            cudaEvent_t a = nullptr, b = nullptr;
+            ~EvPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+        } gev;
+        CU(cudaEventCreate(&gev.a));
+        CU(cudaEventCreate(&gev.b));
+        cudaEvent_t g0 = gev.a, g1 = gev.b;
         CU(cudaEventRecord(g0, d->stream));
         GatherCols G;
         memset(&G, 0, sizeof(G));
@@ -1155,8 +1169,6 @@ static int32_t run_rows_prefiltered(tplx_stage *s, StageDev *sd, const tplx_bloc
         }
         CU(cudaEventSynchronize(g1));
         CU(cudaEventElapsedTime(&msg, g0, g1));
-        cudaEventDestroy(g0);
-        cudaEventDestroy(g1);
         r->launches += 2 + 3 * G.n_cols;
     }
     rc = run_rows(s, sd, b, first_row_no, r, ra.out[0].data, n_surv, dense_cols.empty() ? nullptr : &dense_cols);

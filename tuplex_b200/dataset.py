@@ -24,6 +24,16 @@ from .ir import C, T_BOOL, T_F64, T_I64, T_STR
 from .pyexec import Dropped, Op
 
 
+def _clone_op(op: Op) -> Op:
+    """Same operator (same id: exception counts are keyed by it) with its own resolver / ignore lists. The reference adds a
+    separate ResolveOperator / IgnoreOperator node and leaves the parent plan untouched (python/tuplex/dataset.py:344-389)."""
+    import copy
+    c = copy.copy(op)
+    c.resolvers = list(op.resolvers)
+    c.ignores = list(op.ignores)
+    return c
+
+
 class Source:
     """Input of a plan: normal-case column block + rows that did not fit the normal-case schema
     (PythonContext::parallelize fallback rows, tuplex/python/src/PythonContext.cc:178-204)."""
@@ -74,6 +84,7 @@ class DataSet:
         if not self._ops:
             raise ValueError("resolve() needs a preceding operator")
         ds = DataSet(self._ctx, self._source, self._ops, self._parent)
+        ds._ops[-1] = _clone_op(ds._ops[-1])  # the parent DataSet (and its other branches) keep the operator without this resolver
         ds._ops[-1].resolvers.append((eclass, ftor))
         return ds
 
@@ -81,6 +92,7 @@ class DataSet:
         if not self._ops:
             raise ValueError("ignore() needs a preceding operator")
         ds = DataSet(self._ctx, self._source, self._ops, self._parent)
+        ds._ops[-1] = _clone_op(ds._ops[-1])
         ds._ops[-1].ignores.append(eclass)
         return ds
 
@@ -150,7 +162,58 @@ class DataSet:
 
     # ---- planning + execution -------------------------------------------------------------------------
     def _plan_names(self):
-        return None, self._execute(dry=True)[1]
+        """Column names from the logical plan alone (the reference derives them without executing,
+        python/tuplex/dataset.py:720-735): operators are replayed over names only."""
+        if self._parent is not None:
+            _, names = self._parent._plan_names()
+            names = list(names)
+        else:
+            names = list(self._source.names) if self._source is not None else []
+        for op in self._ops:
+            if op.kind == "withColumn":
+                if op.column not in names:
+                    names = names + [op.column]
+            elif op.kind == "selectColumns":
+                names = [c if isinstance(c, str) else names[c] for c in op.columns]
+            elif op.kind == "renameColumn":
+                names = [op.extra if (n == op.column or (isinstance(op.column, int) and i == op.column % max(len(names), 1))) else n
+                         for i, n in enumerate(names)]
+            elif op.kind == "map":
+                names = self._names_after_map(op, names)
+            elif op.kind == "aggregate":
+                init = op.extra[1]
+                names = [None] * (len(init) if isinstance(init, (tuple, list)) else 1)
+            elif op.kind == "aggregateByKey":
+                init = op.extra[1]
+                names = [c if isinstance(c, str) else names[c] for c in op.columns] + [None] * (len(init) if isinstance(init, (tuple, list)) else 1)
+        return None, names
+
+    def _names_after_map(self, op, names):
+        """Compile (never run) the operator chain up to `op` to learn the shape its map() returns; UDFs outside the GPU op set
+        fall back to reading the UDF's return expression."""
+        if self._parent is None and self._source is not None and len(self._source.cols) == len(names):
+            try:
+                sc = StageCompiler([c.type for c in self._source.cols], self._source.names)
+                for o in self._ops:
+                    if o.kind == "map":
+                        sc.add_map(o.udf, o.id)
+                    elif o.kind == "filter":
+                        sc.add_filter(o.udf, o.id)
+                    elif o.kind == "withColumn":
+                        sc.add_with_column(o.column, o.udf, o.id)
+                    elif o.kind == "mapColumn":
+                        sc.add_map_column(o.column, o.udf, o.id)
+                    elif o.kind == "selectColumns":
+                        sc.add_select(o.columns, o.id)
+                    elif o.kind == "renameColumn":
+                        sc.add_rename(o.column, o.extra, o.id)
+                    else:
+                        break
+                    if o is op:
+                        return list(sc.names)
+            except Exception:  # noqa: BLE001 — UnsupportedUDF or a UDF the front end cannot read
+                pass
+        return _map_output_names(op.udf, names)
 
     def _execute(self, dry: bool = False, sink: Optional[str] = None):
         """Split the operator chain into stages and run them. Returns (python rows, column names)."""
@@ -174,6 +237,24 @@ class DataSet:
             rows, names = _run_stage(self._ctx, src, ops, self._last_exceptions,
                                      csv_sink=self._csv_sink if (sink == "csv" and last) else None)
         return rows, names
+
+
+def _map_output_names(udf, names):
+    """Names after a map(): a dict literal names its columns, anything else yields unnamed columns (one per tuple element)."""
+    import ast as _ast
+    from .frontend import get_udf_ast, _single_return
+    try:
+        _, body, _ = get_udf_ast(udf)
+        node = body if isinstance(body, _ast.expr) else _single_return(body)
+    except Exception:  # noqa: BLE001
+        return [None]
+    if isinstance(node, _ast.Dict) and all(isinstance(k, _ast.Constant) and isinstance(k.value, str) for k in node.keys):
+        return [k.value for k in node.keys]
+    if isinstance(node, _ast.Tuple):
+        return [None] * len(node.elts)
+    if isinstance(node, _ast.Name) and len(names) > 1:
+        return list(names)  # identity-style map of the whole row
+    return [None]
 
 
 def csv_lazy_columns(prog, used_cols, in_types):
@@ -473,6 +554,23 @@ def _run_stage(ctx, src: Source, ops: List[Op], exc_counter: Counter, csv_sink: 
             if cur is None:
                 order.append(key)
             table[key] = list(nv) if isinstance(nv, tuple) else [nv]
+    elif end.kind == "unique" and (len(excs) or fallback):
+        # rows outside the normal case (other types, CSV rows with nulls / unparsable cells, rows whose UDF raised on the device)
+        # are resolved by the interpreter and join the set like any other row (ResolveTask feeds the same hash sink,
+        # core/src/physical/ResolveTask.cc:618-700)
+        pending = [input_row(int(e["row"])) for e in excs] + [obj for _, obj in fallback]
+        for obj in pending:
+            try:
+                val, _ = pyexec.run_row(row_ops, obj, src.names)
+            except Dropped:
+                continue
+            except Exception as ex:  # noqa: BLE001
+                exc_counter[(getattr(ex, "tplx_op", 0), type(ex).__name__)] += 1
+                continue
+            key = val if isinstance(val, tuple) else (val,)
+            if key not in table:
+                table[key] = []
+                order.append(key)
     order.sort(key=lambda k: tuple((0, x) if not isinstance(x, str) else (1, x) for x in k))
     rows = [tuple(list(k) + table[k]) if (len(k) + len(table[k])) != 1 else k[0] for k in order]
     names = list(prog.out_names) + [None] * len(prog.accs)
