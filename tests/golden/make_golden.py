@@ -63,3 +63,20 @@ def zillow_full_fixture():
 
 
 zillow_full_fixture()
+
+
+def zillow_reference_udfs():
+    """tests/golden/zillow_z1_udfs_ref.py = the UDF definitions of the reference's Z1 benchmark script, LITERALLY
+    (benchmarks/zillow/Z1/runtuplex.py: extractBd ... filterBd). A fixture (the workload's user code), so that a parity test can
+    lower the reference's own statements (intermediate variables and all) instead of this repo's re-worded workloads.py."""
+    src = open("/root/reference/benchmarks/zillow/Z1/runtuplex.py").read()
+    a = src.index("def extractBd(x):")
+    b = src.index("if __name__ == \"__main__\":") if "if __name__ == \"__main__\":" in src else src.index("if __name__ == '__main__':")
+    body = src[a:b].rstrip() + "\n"
+    hdr = ('"""LITERAL copy of the UDFs of /root/reference/benchmarks/zillow/Z1/runtuplex.py (test fixture: the workload\'s user code),\n'
+           'written by tests/golden/make_golden.py:zillow_reference_udfs. Do not edit."""\n\n')
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "zillow_z1_udfs_ref.py"), "w") as fp:
+        fp.write(hdr + body)
+
+
+zillow_reference_udfs()

@@ -385,3 +385,17 @@ def test_mask_stage_oversized_rows_fall_back_to_global(gpu):
     prog = _idiom_prog(U.number_before_marker, True)
     st, res, ora = run_both(prog, cols, n)
     assert_result_equals_oracle(res, ora, "oversized rows")
+
+
+def test_power_operator_gpu_vs_oracle(gpu):
+    """`**` with literal exponents (multiply chains, ZeroDivisionError for 0 ** -k, guarded RAISE) on the device == oracle."""
+    import power_udfs as U
+    n = 30_000
+    cols, _ = U.make_columns(n, 4)
+    for src, _k in U.INT_CASES + U.NEG_CASES + U.FLOAT_CASES + [(m, 0) for m in U.MIXED]:
+        sc = frontend.StageCompiler([T_I64, T_F64], ["a", "f"])
+        sc.add_with_column("r", src, 100001)
+        sc.add_filter("lambda x: x['a'] != 5", 100002)
+        prog = sc.finish_memory()
+        st, res, ora = run_both(prog, cols, n, first_row_no=2)
+        assert_result_equals_oracle(res, ora, src)

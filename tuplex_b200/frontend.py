@@ -1134,6 +1134,8 @@ class _FuncCompiler:
             if isinstance(op, ast.Mod) and l.type == T_STR:
                 return self.format_percent(l, r)
             raise UnsupportedUDF("string operator not supported")
+        if isinstance(op, ast.Pow):
+            return self.power(self._force(l) if sc.is_const(l) else l, r)
         if sc.is_const(l) and sc.is_const(r):
             return self.fold(op, l.const, r.const)
         is_f = l.type == T_F64 or r.type == T_F64
@@ -1151,6 +1153,58 @@ class _FuncCompiler:
         if type(op) in (ast.BitAnd, ast.BitOr, ast.BitXor) and l.type == T_BOOL and r.type == T_BOOL:
             return sc.op2(C["TPLX_OP_" + table[type(op)]], T_BOOL, l, r)
         return sc.op2(C["TPLX_OP_" + table[type(op)]], T_I64, sc.to_i64(l), sc.to_i64(r))
+
+    def power(self, l: Val, r: Val) -> Val:
+        """base ** k for a literal integer exponent |k| <= 6: the reference's constant-exponent code
+        (BlockGeneratorVisitor::powerInst :1313-1522 -> generateConstantIntegerPower :5837-5957): addition chains of single
+        multiplies (wrapping i64 / IEEE f64, same association), base == 0 short-cuts to 0, a negative exponent gives
+        1.0 / power as f64 and ZeroDivisionError for base == 0. Other exponents (its general path speculates on the sign of
+        the exponent and calls libm pow; its chain for |k| >= 7 is not a power) stay on the CPython path."""
+        sc = self.sc
+        if not (sc.is_const(r) and r.type in (T_I64, T_BOOL)) or l.type == T_STR:
+            raise UnsupportedUDF("** needs a literal integer exponent")
+        k = int(r.const)
+        if abs(k) > 6:
+            raise UnsupportedUDF("** with |exponent| > 6")
+        base = sc.to_f64(l) if l.type == T_F64 else sc.to_i64(l)
+        is_f = base.type == T_F64
+        if k == 0:
+            return const_val(1.0 if is_f else 1)
+        zero = const_val(0.0 if is_f else 0)
+        is_zero = sc.op2(C["TPLX_OP_FCMP" if is_f else "TPLX_OP_ICMP"], T_BOOL, base, zero, flags=C["TPLX_CMP_EQ"])
+        if k < 0:
+            self.raise_if(is_zero, C["TPLX_EC_ZERODIVISIONERROR"])
+        mul = lambda a, b: sc.op2(C["TPLX_OP_FMUL" if is_f else "TPLX_OP_IMUL"], base.type, a, b)
+        n = abs(k)
+        if n == 1:
+            p = base
+        else:
+            b2 = mul(base, base)
+            if n == 2:
+                p = b2
+            elif n == 3:
+                p = mul(b2, base)
+            else:
+                b4 = mul(b2, b2)
+                p = b4 if n == 4 else (mul(base, b4) if n == 5 else mul(b2, b4))
+        if k < 0:
+            return sc.op2(C["TPLX_OP_FDIV"], T_F64, const_val(1.0), p if is_f else sc.to_f64(p))
+        # base == 0 -> the constant 0 / 0.0 (for -0.0 too: FCmpOEQ(-0.0, 0.0) holds)
+        return sc.select(is_zero, zero, p) if is_f else p
+
+    def raise_if(self, cond: Val, code: int):
+        """Raise `code` for the rows where cond holds (on the executed path only)."""
+        sc = self.sc
+        if sc.is_const(cond) and not cond.const:
+            return
+        g = sc.guard
+        if sc.is_const(cond):
+            sc.emit(C["TPLX_OP_RAISE"], imm=code)
+            return
+        both = cond if g is None else self._with_unguarded(lambda: sc.b_and(Val(T_BOOL, g), cond))
+        sc.guard = sc.reg(both)
+        sc.emit(C["TPLX_OP_RAISE"], imm=code)
+        sc.guard = g
 
     def fold(self, op, a, b):
         """Literal folding with the reference's quirk: folded floats are re-parsed from their
