@@ -399,3 +399,42 @@ def test_power_operator_gpu_vs_oracle(gpu):
         prog = sc.finish_memory()
         st, res, ora = run_both(prog, cols, n, first_row_no=2)
         assert_result_equals_oracle(res, ora, src)
+
+
+def _vec_udf(x):
+    # if-converted branches (guarded ops + phi), division that can raise inside a branch, power-of-two // and %
+    a = x['a']
+    if a % 4 == 1:
+        r = a // (x['b'] - 2)        # ZeroDivisionError only on this branch
+    elif a % 4 == 2:
+        r = (a * a) // 8 - a % 16
+    else:
+        r = -a
+    return r
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 511, 512, 513, 2047, 2048, 2049, 300_001])
+def test_vector_kernel_equals_scalar_kernel_and_oracle(gpu, n, monkeypatch):
+    """K1v (vecvm.cuh, fixed-width stages, 128-bit loads, 8 rows per dispatch) == K1 through the scalar VM (TPLX_NO_VEC=1) == oracle:
+    guarded ops, exceptions on one branch only, strength-reduced // and %, several outputs, f64 ops, ragged tails."""
+    rng = np.random.default_rng(n + 1)
+    a = rng.integers(-1000, 1000, n, dtype=np.int64)
+    b = rng.integers(0, 5, n, dtype=np.int64)
+    f = rng.normal(0, 50, n)
+    sc = frontend.StageCompiler([T_I64, T_I64, T_F64], ["a", "b", "f"])
+    sc.add_with_column("r", _vec_udf, 100001)
+    sc.add_with_column("g", lambda x: x['f'] * 0.5 + x['a'] / 4 if x['f'] > 0.0 else abs(x['f']) % 3.0, 100002)
+    sc.add_filter(lambda x: x['r'] % 3 != 0 and x['g'] < 60.0, 100003)
+    sc.add_with_column("h", lambda x: (x['a'] << 2) ^ (x['b'] | 1), 100004)
+    sc.add_select(["r", "g", "h", "a"], 100005)
+    prog = sc.finish_memory(prefilter=False)
+    cols = [Column(T_I64, a), Column(T_I64, b), Column(T_F64, f)]
+    ora = pyoracle.run_program(prog, cols, n, 9)
+    for env in ({}, {"TPLX_NO_VEC": "1"}):
+        monkeypatch.delenv("TPLX_NO_VEC", raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        res = backend.Stage(prog).run_host(0, cols, n, 9)
+        assert_result_equals_oracle(res, ora, f"n={n} env={env}")
+    if n > 1000:
+        assert len(ora.exceptions) > 0 and 0 < ora.n_out < n

@@ -120,6 +120,184 @@ __device__ __forceinline__ bool bit_test(const uint32_t *bits, uint32_t lr) {
     return (bits[lr >> 5] >> (lr & 31)) & 1u;
 }
 
+// Tail of a tile, shared by the scalar (VM) and the vector (VecVM) row kernels: per-tile counts, decoupled look-back over the
+// K-vector, stable compacted write of the staged outputs, exception records. On entry keep_bits / exc_bits / exc_stage and the
+// staged output values (s_stage + out[c].stage_off, indexed by local row) are complete and a __syncthreads() has been passed.
+struct TileSmem {
+    uint8_t *s_stage, *s_regs;
+    uint32_t *keep_bits, *exc_bits, *keep_pre, *exc_pre, *exc_stage;
+    uint64_t *s_vals, *s_excl, *s_warp;
+};
+__device__ __forceinline__ void rows_tile_finish(const KParams &P, const TileSmem &S, uint32_t tile, uint64_t base, uint32_t R, uint32_t T,
+                                                 uint32_t W, uint32_t K, uint32_t state_stride) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint8_t *s_stage = S.s_stage, *s_regs = S.s_regs;
+    uint32_t *keep_bits = S.keep_bits, *exc_bits = S.exc_bits, *keep_pre = S.keep_pre, *exc_pre = S.exc_pre, *exc_stage = S.exc_stage;
+    uint64_t *s_vals = S.s_vals, *s_excl = S.s_excl, *s_warp = S.s_warp;
+    // ---- per-tile counts: word prefixes (warp 0), string byte totals ----------------------
+    if (warp == 0) {
+        uint32_t ck = 0, ce = 0;
+        for (uint32_t w0 = 0; w0 < W; w0 += 32) {
+            uint32_t w = w0 + lane;
+            uint32_t pk = w < W ? __popc(keep_bits[w]) : 0, pe = w < W ? __popc(exc_bits[w]) : 0;
+            uint32_t ik = pk, ie = pe;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t a = __shfl_up_sync(0xFFFFFFFFu, ik, o), b = __shfl_up_sync(0xFFFFFFFFu, ie, o);
+                if (lane >= (uint32_t)o) { ik += a; ie += b; }
+            }
+            if (w < W) { keep_pre[w] = ck + ik - pk; exc_pre[w] = ce + ie - pe; }
+            ck += __shfl_sync(0xFFFFFFFFu, ik, 31);
+            ce += __shfl_sync(0xFFFFFFFFu, ie, 31);
+        }
+        if (lane == 0) {
+            keep_pre[W] = ck;
+            exc_pre[W] = ce;
+            s_vals[0] = ck;
+            s_vals[1] = ce;
+        }
+    }
+    __syncthreads();
+    const bool any_keep = s_vals[0] != 0;
+    if (!any_keep && tid < MAX_SCAN - 2) s_vals[2 + tid] = 0;
+    // string bytes per output column: thread owns local rows [tid*R, tid*R+R)
+    // (consecutive rows per thread so that one block scan yields in-order byte offsets)
+    for (uint32_t c = 0; any_keep && c < P.n_out; ++c) {
+        const OutCol &oc = P.out[c];
+        if (oc.strk < 0) continue;
+        const uint64_t *st = reinterpret_cast<const uint64_t *>(s_stage + oc.stage_off);
+        uint32_t mine = 0;
+        for (uint32_t j = 0; j < R; ++j) {
+            uint32_t lr = tid * R + j;
+            if (bit_test(keep_bits, lr)) mine += (uint32_t)st[2 * (size_t)lr + 1];
+        }
+        uint32_t inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t a = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+            if (lane >= (uint32_t)o) inc += a;
+        }
+        __syncthreads();  // s_warp reuse
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        uint32_t wofs = 0, tot = 0;
+        for (uint32_t w = 0; w < NT / 32; ++w) {
+            uint32_t v = (uint32_t)s_warp[w];
+            if (w < warp) wofs += v;
+            tot += v;
+        }
+        // stash this thread's exclusive byte offset in the (now free) register file slot area:
+        // regs are dead after evaluation, reuse slot 0..n_str_out-1 of this thread
+        VM<NT>::R(s_regs, (uint32_t)oc.strk * VM<NT>::SLOT_BYTES) = (uint64_t)(wofs + inc - mine);
+        if (tid == 0) s_vals[2 + oc.strk] = tot;
+    }
+    __syncthreads();
+
+    // ---- decoupled look-back over the K-vector (warp 0) -----------------------------------
+    if (warp == 0) {
+        uint64_t *my = P.tile_state + (size_t)tile * state_stride;
+        uint64_t myval = lane < K ? s_vals[lane] : 0;
+        if (lane < K) {
+            st_cg_u64(my + 1 + lane, myval);
+            if (tile == 0) st_cg_u64(my + 1 + K + lane, myval);
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) st_release_u32(reinterpret_cast<uint32_t *>(my), tile == 0 ? 2u : 1u);
+        uint64_t excl = 0;
+        if (tile > 0) {
+            int64_t p = (int64_t)tile - 1;
+            while (true) {
+                const int64_t q = p - lane;
+                uint32_t st = 2;
+                const uint64_t *qs = nullptr;
+                if (q >= 0) {
+                    qs = P.tile_state + (size_t)q * state_stride;
+                    do { st = ld_acquire_u32(reinterpret_cast<const uint32_t *>(qs)); } while (st == 0);
+                }
+                const uint32_t pm = __ballot_sync(0xFFFFFFFFu, st == 2);
+                const uint32_t first = pm ? (uint32_t)(__ffs(pm) - 1) : 31u;
+                const bool use = (lane <= first) && q >= 0;
+                for (uint32_t k = 0; k < K; ++k) {
+                    uint64_t v = use ? ld_cg_u64(qs + 1 + (st == 2 ? K : 0) + k) : 0;
+                    v = warp_sum_u64(v);
+                    if (lane == k) excl += v;
+                }
+                if (pm) break;
+                p -= 32;
+            }
+            if (lane < K) st_cg_u64(my + 1 + K + lane, excl + myval);
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) st_release_u32(reinterpret_cast<uint32_t *>(my), 2u);
+        }
+        if (lane < K) {
+            s_excl[lane] = excl;
+            if (tile == P.n_tiles - 1) P.totals[lane] = excl + myval;
+        }
+    }
+    __syncthreads();
+
+    // ---- write ----------------------------------------------------------------------------
+    const uint64_t pre_keep = s_excl[0], pre_exc = s_excl[1];
+    const uint32_t n_keep = (uint32_t)s_vals[0], n_exc = (uint32_t)s_vals[1];
+    const bool rows_fit = pre_keep + n_keep <= P.cap_rows;
+    if (!rows_fit && tid == 0) atomicOr(&P.counters[1], 1u);
+    if (n_keep && rows_fit) {
+        for (uint32_t c = 0; c < P.n_out; ++c) {
+            const OutCol &oc = P.out[c];
+            if (oc.strk < 0) {
+                const uint64_t *st = reinterpret_cast<const uint64_t *>(s_stage + oc.stage_off);
+                for (uint32_t lr = tid; lr < T; lr += NT)
+                    if (bit_test(keep_bits, lr)) oc.data[pre_keep + bit_rank(keep_bits, keep_pre, lr)] = st[lr];
+            } else {
+                const uint64_t *st = reinterpret_cast<const uint64_t *>(s_stage + oc.stage_off);
+                const uint64_t pre_b = s_excl[2 + oc.strk];
+                const uint64_t tile_b = s_vals[2 + oc.strk];
+                const bool fit = pre_b + tile_b <= oc.cap_bytes && pre_b + tile_b <= 0xFFFFFFFFull;
+                if (!fit) {
+                    if (tid == 0) atomicOr(&P.counters[1], 2u);
+                    continue;
+                }
+                uint64_t off = pre_b + VM<NT>::R(s_regs, (uint32_t)oc.strk * VM<NT>::SLOT_BYTES);
+                for (uint32_t j = 0; j < R; ++j) {
+                    const uint32_t lr = tid * R + j;
+                    if (!bit_test(keep_bits, lr)) continue;
+                    StrV sv;
+                    sv.p = reinterpret_cast<const uint8_t *>(st[2 * (size_t)lr]);
+                    const uint64_t m = st[2 * (size_t)lr + 1];
+                    sv.len = (uint32_t)m;
+                    sv.flags = (uint32_t)(m >> 32);
+                    oc.offsets[pre_keep + bit_rank(keep_bits, keep_pre, lr)] = (uint32_t)off;
+                    str_copy(oc.bytes + off, sv);
+                    off += sv.len;
+                }
+                if (tile == P.n_tiles - 1 && tid == 0) oc.offsets[pre_keep + n_keep] = (uint32_t)(pre_b + tile_b);
+            }
+        }
+    } else if (tile == P.n_tiles - 1 && rows_fit && tid == 0) {
+        for (uint32_t c = 0; c < P.n_out; ++c)
+            if (P.out[c].strk >= 0) P.out[c].offsets[pre_keep] = (uint32_t)s_excl[2 + P.out[c].strk];
+    }
+    if (n_exc) {
+        if (pre_exc + n_exc <= P.cap_exc) {
+            for (uint32_t lr = tid; lr < T; lr += NT) {
+                if (!bit_test(exc_bits, lr)) continue;
+                const uint32_t ke = bit_rank(exc_bits, exc_pre, lr);
+                const uint32_t kk = bit_rank(keep_bits, keep_pre, lr);
+                tplx_exception_rec rec;
+                rec.row = (int64_t)(P.rowlist ? P.rowlist[base + lr] : base + lr);
+                // _outputRowCounter semantics: rows written + exceptions so far (TransformTask.cc:764,885)
+                rec.row_no = P.first_row_no + (int64_t)(pre_keep + pre_exc + kk + ke);
+                const uint32_t es = exc_stage[lr];
+                rec.code = es & 0xFFFF;
+                rec.op_id = P.opids[es >> 16];
+                P.exc[pre_exc + ke] = rec;
+            }
+        } else if (tid == 0) atomicOr(&P.counters[1], 4u);
+    }
+}
+
 // =============================================================================================
 // K1: rows in -> rows out
 // =============================================================================================
@@ -204,168 +382,8 @@ __global__ void __launch_bounds__(NT) stage_rows_kernel(const KParams *__restric
         }
         __syncthreads();
 
-        // ---- per-tile counts: word prefixes (warp 0), string byte totals ----------------------
-        if (warp == 0) {
-            uint32_t ck = 0, ce = 0;
-            for (uint32_t w0 = 0; w0 < W; w0 += 32) {
-                uint32_t w = w0 + lane;
-                uint32_t pk = w < W ? __popc(keep_bits[w]) : 0, pe = w < W ? __popc(exc_bits[w]) : 0;
-                uint32_t ik = pk, ie = pe;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    uint32_t a = __shfl_up_sync(0xFFFFFFFFu, ik, o), b = __shfl_up_sync(0xFFFFFFFFu, ie, o);
-                    if (lane >= (uint32_t)o) { ik += a; ie += b; }
-                }
-                if (w < W) { keep_pre[w] = ck + ik - pk; exc_pre[w] = ce + ie - pe; }
-                ck += __shfl_sync(0xFFFFFFFFu, ik, 31);
-                ce += __shfl_sync(0xFFFFFFFFu, ie, 31);
-            }
-            if (lane == 0) {
-                keep_pre[W] = ck;
-                exc_pre[W] = ce;
-                s_vals[0] = ck;
-                s_vals[1] = ce;
-            }
-        }
-        __syncthreads();
-        const bool any_keep = s_vals[0] != 0;
-        if (!any_keep && tid < MAX_SCAN - 2) s_vals[2 + tid] = 0;
-        // string bytes per output column: thread owns local rows [tid*R, tid*R+R)
-        // (consecutive rows per thread so that one block scan yields in-order byte offsets)
-        for (uint32_t c = 0; any_keep && c < P.n_out; ++c) {
-            const OutCol &oc = P.out[c];
-            if (oc.strk < 0) continue;
-            const uint64_t *st = reinterpret_cast<const uint64_t *>(s_stage + oc.stage_off);
-            uint32_t mine = 0;
-            for (uint32_t j = 0; j < R; ++j) {
-                uint32_t lr = tid * R + j;
-                if (bit_test(keep_bits, lr)) mine += (uint32_t)st[2 * (size_t)lr + 1];
-            }
-            uint32_t inc = mine;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t a = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-                if (lane >= (uint32_t)o) inc += a;
-            }
-            __syncthreads();  // s_warp reuse
-            if (lane == 31) s_warp[warp] = inc;
-            __syncthreads();
-            uint32_t wofs = 0, tot = 0;
-            for (uint32_t w = 0; w < NT / 32; ++w) {
-                uint32_t v = (uint32_t)s_warp[w];
-                if (w < warp) wofs += v;
-                tot += v;
-            }
-            // stash this thread's exclusive byte offset in the (now free) register file slot area:
-            // regs are dead after evaluation, reuse slot 0..n_str_out-1 of this thread
-            VM<NT>::R(s_regs, (uint32_t)oc.strk * VM<NT>::SLOT_BYTES) = (uint64_t)(wofs + inc - mine);
-            if (tid == 0) s_vals[2 + oc.strk] = tot;
-        }
-        __syncthreads();
-
-        // ---- decoupled look-back over the K-vector (warp 0) -----------------------------------
-        if (warp == 0) {
-            uint64_t *my = P.tile_state + (size_t)tile * state_stride;
-            uint64_t myval = lane < K ? s_vals[lane] : 0;
-            if (lane < K) {
-                st_cg_u64(my + 1 + lane, myval);
-                if (tile == 0) st_cg_u64(my + 1 + K + lane, myval);
-            }
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) st_release_u32(reinterpret_cast<uint32_t *>(my), tile == 0 ? 2u : 1u);
-            uint64_t excl = 0;
-            if (tile > 0) {
-                int64_t p = (int64_t)tile - 1;
-                while (true) {
-                    const int64_t q = p - lane;
-                    uint32_t st = 2;
-                    const uint64_t *qs = nullptr;
-                    if (q >= 0) {
-                        qs = P.tile_state + (size_t)q * state_stride;
-                        do { st = ld_acquire_u32(reinterpret_cast<const uint32_t *>(qs)); } while (st == 0);
-                    }
-                    const uint32_t pm = __ballot_sync(0xFFFFFFFFu, st == 2);
-                    const uint32_t first = pm ? (uint32_t)(__ffs(pm) - 1) : 31u;
-                    const bool use = (lane <= first) && q >= 0;
-                    for (uint32_t k = 0; k < K; ++k) {
-                        uint64_t v = use ? ld_cg_u64(qs + 1 + (st == 2 ? K : 0) + k) : 0;
-                        v = warp_sum_u64(v);
-                        if (lane == k) excl += v;
-                    }
-                    if (pm) break;
-                    p -= 32;
-                }
-                if (lane < K) st_cg_u64(my + 1 + K + lane, excl + myval);
-                __threadfence();
-                __syncwarp();
-                if (lane == 0) st_release_u32(reinterpret_cast<uint32_t *>(my), 2u);
-            }
-            if (lane < K) {
-                s_excl[lane] = excl;
-                if (tile == P.n_tiles - 1) P.totals[lane] = excl + myval;
-            }
-        }
-        __syncthreads();
-
-        // ---- write ----------------------------------------------------------------------------
-        const uint64_t pre_keep = s_excl[0], pre_exc = s_excl[1];
-        const uint32_t n_keep = (uint32_t)s_vals[0], n_exc = (uint32_t)s_vals[1];
-        const bool rows_fit = pre_keep + n_keep <= P.cap_rows;
-        if (!rows_fit && tid == 0) atomicOr(&P.counters[1], 1u);
-        if (n_keep && rows_fit) {
-            for (uint32_t c = 0; c < P.n_out; ++c) {
-                const OutCol &oc = P.out[c];
-                if (oc.strk < 0) {
-                    const uint64_t *st = reinterpret_cast<const uint64_t *>(s_stage + oc.stage_off);
-                    for (uint32_t lr = tid; lr < T; lr += NT)
-                        if (bit_test(keep_bits, lr)) oc.data[pre_keep + bit_rank(keep_bits, keep_pre, lr)] = st[lr];
-                } else {
-                    const uint64_t *st = reinterpret_cast<const uint64_t *>(s_stage + oc.stage_off);
-                    const uint64_t pre_b = s_excl[2 + oc.strk];
-                    const uint64_t tile_b = s_vals[2 + oc.strk];
-                    const bool fit = pre_b + tile_b <= oc.cap_bytes && pre_b + tile_b <= 0xFFFFFFFFull;
-                    if (!fit) {
-                        if (tid == 0) atomicOr(&P.counters[1], 2u);
-                        continue;
-                    }
-                    uint64_t off = pre_b + VM<NT>::R(s_regs, (uint32_t)oc.strk * VM<NT>::SLOT_BYTES);
-                    for (uint32_t j = 0; j < R; ++j) {
-                        const uint32_t lr = tid * R + j;
-                        if (!bit_test(keep_bits, lr)) continue;
-                        StrV sv;
-                        sv.p = reinterpret_cast<const uint8_t *>(st[2 * (size_t)lr]);
-                        const uint64_t m = st[2 * (size_t)lr + 1];
-                        sv.len = (uint32_t)m;
-                        sv.flags = (uint32_t)(m >> 32);
-                        oc.offsets[pre_keep + bit_rank(keep_bits, keep_pre, lr)] = (uint32_t)off;
-                        str_copy(oc.bytes + off, sv);
-                        off += sv.len;
-                    }
-                    if (tile == P.n_tiles - 1 && tid == 0) oc.offsets[pre_keep + n_keep] = (uint32_t)(pre_b + tile_b);
-                }
-            }
-        } else if (tile == P.n_tiles - 1 && rows_fit && tid == 0) {
-            for (uint32_t c = 0; c < P.n_out; ++c)
-                if (P.out[c].strk >= 0) P.out[c].offsets[pre_keep] = (uint32_t)s_excl[2 + P.out[c].strk];
-        }
-        if (n_exc) {
-            if (pre_exc + n_exc <= P.cap_exc) {
-                for (uint32_t lr = tid; lr < T; lr += NT) {
-                    if (!bit_test(exc_bits, lr)) continue;
-                    const uint32_t ke = bit_rank(exc_bits, exc_pre, lr);
-                    const uint32_t kk = bit_rank(keep_bits, keep_pre, lr);
-                    tplx_exception_rec rec;
-                    rec.row = (int64_t)(P.rowlist ? P.rowlist[base + lr] : base + lr);
-                    // _outputRowCounter semantics: rows written + exceptions so far (TransformTask.cc:764,885)
-                    rec.row_no = P.first_row_no + (int64_t)(pre_keep + pre_exc + kk + ke);
-                    const uint32_t es = exc_stage[lr];
-                    rec.code = es & 0xFFFF;
-                    rec.op_id = P.opids[es >> 16];
-                    P.exc[pre_exc + ke] = rec;
-                }
-            } else if (tid == 0) atomicOr(&P.counters[1], 4u);
-        }
+        rows_tile_finish(P, TileSmem{s_stage, s_regs, keep_bits, exc_bits, keep_pre, exc_pre, exc_stage, s_vals, s_excl, s_warp}, tile, base, R, T,
+                         W, K, state_stride);
     }
 }
 

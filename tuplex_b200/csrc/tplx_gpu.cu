@@ -25,6 +25,7 @@
 #include "fused.cuh"
 #include "gather.cuh"
 #include "mask.cuh"
+#include "vecvm.cuh"
 #include "csv.cuh"
 
 using namespace tplx;
@@ -173,6 +174,7 @@ extern "C" int32_t tplx_gpu_device_info(int32_t device, char *name_buf, int32_t 
 struct StageDev {
     Device *dev = nullptr;
     DInstr *prog = nullptr;  // pre-decoded program
+    DInstr *prog_vec[2] = {nullptr, nullptr};  // the same for the vector kernel (slot stride of T = 1024 / 2048 rows), built on demand
     uint8_t *cpool = nullptr;
     int64_t *opids = nullptr;
     HashTable *ht = nullptr;  // HASH endpoint
@@ -196,6 +198,7 @@ struct tplx_stage {
     tplx_stage *prefilter = nullptr;  // nested selective stage (row index output), may be null
     bool prefilter_enabled = true;    // switched off at run time when it turns out not to be selective
     uint32_t hidden = 0;              // trailing executor-internal output columns
+    bool vec_ok = false;              // fixed-width values and vector-VM ops only: eligible for K1v (vecvm.cuh)
     bool has_fused = false;           // closed-form scan-aggregate hint present and valid
     FusedParams fused{};
     std::mutex mu;
@@ -348,14 +351,29 @@ extern "C" int32_t tplx_gpu_stage_create(const void *desc, uint64_t desc_bytes, 
     if (h.endpoint == TPLX_EP_AGGREGATE && h.n_accs == 0) return bad("aggregate endpoint without accumulators");
     if (h.endpoint == TPLX_EP_HASH && (h.n_keys == 0 || h.n_keys > h.n_out_cols)) return bad("hash endpoint without key columns");
     s->est_bytes_per_row.assign(h.n_out_cols, -1.0);
+    // K1v eligibility: no string value anywhere and only operations the vector VM implements
+    s->vec_ok = !s->has_str && h.endpoint == TPLX_EP_MEMORY && h.n_instr > 0;
+    for (const tplx_instr &in : s->instrs) {
+        switch (in.op) {
+            case TPLX_OP_LDCOL: case TPLX_OP_LDI: case TPLX_OP_LDROW: case TPLX_OP_MOV: case TPLX_OP_SEL: case TPLX_OP_IADD: case TPLX_OP_ISUB:
+            case TPLX_OP_IMUL: case TPLX_OP_IFLOORDIV: case TPLX_OP_IMOD: case TPLX_OP_INEG: case TPLX_OP_IAND: case TPLX_OP_IOR: case TPLX_OP_IXOR:
+            case TPLX_OP_ISHL: case TPLX_OP_ISHR: case TPLX_OP_IABS: case TPLX_OP_FADD: case TPLX_OP_FSUB: case TPLX_OP_FMUL: case TPLX_OP_FDIV:
+            case TPLX_OP_FMOD: case TPLX_OP_FNEG: case TPLX_OP_FFLOORDIV: case TPLX_OP_FABS: case TPLX_OP_I2F: case TPLX_OP_F2I: case TPLX_OP_ICMP:
+            case TPLX_OP_FCMP: case TPLX_OP_BAND: case TPLX_OP_BOR: case TPLX_OP_BNOT: case TPLX_OP_FILTER: case TPLX_OP_RAISE: case TPLX_OP_NOP:
+                break;
+            default: s->vec_ok = false;
+        }
+        if ((in.op == TPLX_OP_SEL || in.op == TPLX_OP_MOV) && (in.flags & 3) != 1) s->vec_ok = false;
+    }
     *out = s;
     return TPLX_OK;
 }
 
 // tplx_instr -> device format: slot numbers become byte offsets into a thread's register column
-static std::vector<DInstr> predecode(const std::vector<tplx_instr> &ins) {
+// (slot_bytes = NT * 8 for the scalar VM; T * 8 for the vector VM, which also gets strength-reduced micro-ops)
+static std::vector<DInstr> predecode(const std::vector<tplx_instr> &ins, uint32_t slot_bytes = NT * 8, bool vec = false) {
     std::vector<DInstr> out(ins.size());
-    auto off = [](uint16_t slot) { return slot == TPLX_NOSLOT ? NOOFF : (uint32_t)slot * (uint32_t)(NT * 8); };
+    auto off = [slot_bytes](uint16_t slot) { return slot == TPLX_NOSLOT ? NOOFF : (uint32_t)slot * slot_bytes; };
     for (size_t i = 0; i < ins.size(); ++i) {
         const tplx_instr &in = ins[i];
         DInstr d{};
@@ -367,6 +385,14 @@ static std::vector<DInstr> predecode(const std::vector<tplx_instr> &ins) {
         d.guard = off(in.guard);
         d.imm = in.imm;
         d.imm2 = in.imm2;
+        if (vec && (in.op == TPLX_OP_IMOD || in.op == TPLX_OP_IFLOORDIV) && (in.flags & TPLX_F_B_CONST) && in.imm > 0 && (in.imm & (in.imm - 1)) == 0) {
+            // constant power-of-two divisor: x % 2^k == x & (2^k - 1), x // 2^k == x >> k under floored semantics; cannot raise
+            int k = 0;
+            while ((1ll << k) != in.imm) ++k;
+            const uint32_t uop = in.op == TPLX_OP_IMOD ? UOP_IAND_MOD : UOP_ISHR_FLOORDIV;
+            d.op_flags = uop | ((uint32_t)in.flags << 8) | ((uint32_t)in.opidx << 16);
+            d.imm = in.op == TPLX_OP_IMOD ? in.imm - 1 : k;
+        }
         out[i] = d;
     }
     return out;
@@ -399,6 +425,8 @@ extern "C" int32_t tplx_gpu_stage_destroy(tplx_stage *s) {
         cudaSetDevice(sd.dev->id);
         cudaStreamSynchronize(sd.dev->stream);
         cudaFree(sd.prog);
+        cudaFree(sd.prog_vec[0]);
+        cudaFree(sd.prog_vec[1]);
         cudaFree(sd.cpool);
         cudaFree(sd.opids);
         if (sd.ht) hash_table_destroy(sd.ht);
@@ -785,6 +813,133 @@ static int32_t dalloc(tplx_result *r, T **p, size_t count) {
     return TPLX_OK;
 }
 
+// K1v (vecvm.cuh): fixed-width stages, vector-at-a-time. Outputs are fixed width, so capacities are exact (n rows) and the only
+// retry is for exception records.
+template <int J>
+static int32_t launch_rows_vec(uint32_t grid, uint32_t smem, cudaStream_t st, const KParams *dP) {
+    CU(cudaFuncSetAttribute(stage_rows_vec_kernel<J>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    stage_rows_vec_kernel<J><<<grid, NT, smem, st>>>(dP);
+    return TPLX_OK;
+}
+static int32_t run_rows_vec(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_t first_row_no, tplx_result *r) {
+    Device *d = r->dev;
+    const uint64_t n = b->n_rows;
+    const uint32_t ns = std::max<uint32_t>(s->hdr.n_slots, 1);
+    // J = 4 (2048-row tiles, 8 rows per thread per dispatch) when the register file leaves room for >= 3 CTAs per SM, else J = 2
+    int Jsel = 0;
+    uint32_t smem = 0, T = 0, cols_off = 0, regs_off = 0, misc_off = 0;
+    for (int J : {4, 2}) {
+        T = 2u * J * NT;
+        const uint32_t W = T / 32;
+        size_t off = align_up(std::max<size_t>(s->instrs.size(), 1) * sizeof(DInstr), 16);
+        cols_off = (uint32_t)off;
+        off = align_up(off + std::max<size_t>(s->in_types.size(), 1) * sizeof(ColIn), 16);
+        regs_off = (uint32_t)off;
+        off = align_up(off + (size_t)ns * T * 8, 16);
+        misc_off = (uint32_t)off;
+        off += (size_t)(4 * W + 2 + T) * 4 + (size_t)(2 * MAX_SCAN + NT / 32 + 1) * 8 + 16;
+        smem = (uint32_t)align_up(off, 16);
+        if (smem <= 72 * 1024 || (J == 2 && smem <= (uint32_t)d->smem_optin)) { Jsel = J; break; }
+    }
+    if (!Jsel) return TPLX_E_UNSUPPORTED;
+    const int ji = Jsel == 4 ? 1 : 0;
+    if (!sd->prog_vec[ji]) {
+        std::lock_guard<std::mutex> lk(s->mu);
+        if (!sd->prog_vec[ji]) {
+            std::vector<DInstr> dec = predecode(s->instrs, T * 8, true);
+            DInstr *p = nullptr;
+            CU(cudaMalloc(&p, std::max<size_t>(dec.size() * sizeof(DInstr), 16)));
+            CU(cudaMemcpy(p, dec.data(), dec.size() * sizeof(DInstr), cudaMemcpyHostToDevice));
+            sd->prog_vec[ji] = p;
+        }
+    }
+    Layout L;
+    L.cols_off = cols_off;
+    L.regs_off = regs_off;
+    L.stage_off = regs_off;  // output columns are staged in place: a slot is indexed by the local row
+    L.misc_off = misc_off;
+    L.total = smem;
+    KParams P;
+    fill_common(P, s, sd, b, L, 2 * Jsel);
+    P.prog = sd->prog_vec[ji];
+    P.n_tiles = (uint32_t)((n + T - 1) / T);
+    P.first_row_no = first_row_no;
+    int occ = 0;
+    if (Jsel == 4) {
+        CU(cudaFuncSetAttribute(stage_rows_vec_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stage_rows_vec_kernel<4>, NT, smem));
+    } else {
+        CU(cudaFuncSetAttribute(stage_rows_vec_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stage_rows_vec_kernel<2>, NT, smem));
+    }
+    if (occ < 1) return TPLX_E_UNSUPPORTED;
+    const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(P.n_tiles, (uint32_t)(occ * d->prop.multiProcessorCount)));
+    r->hidden = s->hidden;
+    r->out_types.clear();
+    for (auto &oc : s->out_cols) r->out_types.push_back(oc.type);
+    r->str_bytes.assign(s->out_cols.size(), 0);
+    r->out.assign(s->out_cols.size(), OutCol{});
+    CU(cudaEventRecord(r->evk0, d->stream));
+    if (n == 0) {
+        CU(cudaEventRecord(r->evk1, d->stream));
+        return TPLX_OK;
+    }
+    uint64_t *tile_state = nullptr, *totals = nullptr;
+    uint32_t *counters = nullptr;
+    KParams *dP = nullptr;
+    const size_t state_words = (size_t)P.n_tiles * (1 + 2 * P.K);
+    int32_t rc = dalloc(r, &tile_state, state_words);
+    if (rc) return rc;
+    rc = dalloc(r, &totals, MAX_SCAN);
+    if (rc) return rc;
+    rc = dalloc(r, &counters, 4);
+    if (rc) return rc;
+    rc = dalloc(r, &dP, 1);
+    if (rc) return rc;
+    P.tile_state = tile_state;
+    P.totals = totals;
+    P.counters = counters;
+    for (size_t c = 0; c < s->out_cols.size(); ++c) {
+        OutCol &oc = P.out[c];
+        oc.slot = s->out_cols[c].slot;
+        oc.type = s->out_cols[c].type;
+        oc.strk = -1;
+        oc.stage_off = (uint32_t)s->out_cols[c].slot * T * 8;
+        rc = dalloc(r, &oc.data, n);
+        if (rc) return rc;
+    }
+    P.cap_rows = n;
+    uint64_t cap_exc = std::max<uint64_t>(4096, (uint64_t)(s->est_exc_per_row * 1.5 * (double)n) + n / 64);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        P.cap_exc = cap_exc;
+        rc = dalloc(r, &P.exc, cap_exc);
+        if (rc) return rc;
+        CU(cudaMemsetAsync(tile_state, 0, state_words * 8, d->stream));
+        CU(cudaMemsetAsync(counters, 0, 16, d->stream));
+        CU(cudaMemsetAsync(totals, 0, MAX_SCAN * 8, d->stream));
+        CU(cudaMemcpyAsync(dP, &P, sizeof(P), cudaMemcpyHostToDevice, d->stream));
+        rc = Jsel == 4 ? launch_rows_vec<4>(grid, smem, d->stream, dP) : launch_rows_vec<2>(grid, smem, d->stream, dP);
+        if (rc) return rc;
+        CU(cudaGetLastError());
+        r->launches += 1;
+        uint64_t h_tot[MAX_SCAN];
+        uint32_t h_cnt[4];
+        CU(cudaMemcpyAsync(h_tot, totals, MAX_SCAN * 8, cudaMemcpyDeviceToHost, d->stream));
+        CU(cudaMemcpyAsync(h_cnt, counters, 16, cudaMemcpyDeviceToHost, d->stream));
+        CU(cudaStreamSynchronize(d->stream));
+        r->n_out = h_tot[0];
+        r->n_exc = h_tot[1];
+        s->est_exc_per_row = (double)r->n_exc / (double)n;
+        if (h_cnt[1] == 0) break;
+        if (attempt == 1) return fail(TPLX_E_OVERFLOW, "exception capacity retry failed");
+        cap_exc = r->n_exc + 16;
+    }
+    CU(cudaEventRecord(r->evk1, d->stream));
+    for (size_t c = 0; c < s->out_cols.size(); ++c) r->out[c] = P.out[c];
+    r->exc = P.exc;
+    return TPLX_OK;
+}
+
 static int32_t run_rows(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_t first_row_no, tplx_result *r,
                         const uint64_t *rowlist, uint64_t n_list, const std::vector<ColIn> *cols_override) {
     Device *d = r->dev;  // execution lane chosen by tplx_gpu_stage_run
@@ -804,6 +959,15 @@ static int32_t run_rows(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_
                 CU(cudaMemsetAsync(r->out[c].offsets, 0, 4, d->stream));
             }
         return TPLX_OK;
+    }
+    if (s->vec_ok && !rowlist && !cols_override && !getenv("TPLX_NO_VEC")) {
+        bool ok = true;
+        for (size_t c = 0; c < b->cols.size(); ++c)
+            ok = ok && !(b->cols[c].type & COL_COMPACT) && (c >= b->mapped.size() || !b->mapped[c]) && (((uintptr_t)b->cols[c].data & 15) == 0);
+        if (ok) {
+            int32_t vrc = run_rows_vec(s, sd, b, first_row_no, r);
+            if (vrc != TPLX_E_UNSUPPORTED) return vrc;  // does not fit the vector kernel's shared memory: scalar kernel below
+        }
     }
     // tile shape: the largest tile (fewest barrier / look-back episodes, best load balance inside the CTA) that does
     // not cost occupancy: the register-limited number of resident CTAs divides the SM's shared memory into budgets

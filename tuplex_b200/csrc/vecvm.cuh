@@ -1,0 +1,310 @@
+// vecvm.cuh — K1v: the row kernel for stages made of fixed-width columns only (BASELINE config 0 / C1 and every numeric
+// map / filter / project pipeline): the closed-form fast path the reference gets from specialising its block loop per stage
+// (tuplex/core/src/physical/TuplexSourceTaskBuilder.cc:104-215 + PipelineBuilder.cc:565-700 for fixed-width rows).
+//
+// Same op program, same per-row semantics as vm.cuh (every op is the same single integer / IEEE operation), evaluated
+// VECTOR-AT-A-TIME: a thread owns V = 2J rows of a tile; one instruction dispatch (uniform fetch + decode) is followed by 2J
+// row operations, so the interpretive overhead per row shrinks by 2J. B200 mapping:
+//   * inputs: coalesced 128-bit global loads (LDG.E.128: thread t reads rows 2t, 2t+1 of every 512-row slab of the tile);
+//   * register file in shared memory as regs[slot][local row] — one conflict-free LDS.128 / STS.128 moves two rows;
+//     because a slot is indexed by the local row it IS the staging array of an output column (no copy before the write);
+//   * filter mask -> warp ballots -> bitmaps -> rows_tile_finish (decoupled look-back scan + dense coalesced write), shared
+//     with the scalar kernel.
+// Strings never enter this kernel (the host selects it only for programs without string values).
+#pragma once
+#include <stdint.h>
+#include "kernels.cuh"
+
+namespace tplx {
+
+// internal micro-ops produced by the pre-decoder (never part of the IR): strength-reduced forms with a constant power-of-two
+// divisor; floored semantics make both exact for every dividend:  x // 2^k == x >> k (arithmetic),  x % 2^k == x & (2^k - 1)
+constexpr uint32_t UOP_ISHR_FLOORDIV = 200;  // imm = k
+constexpr uint32_t UOP_IAND_MOD = 201;       // imm = 2^k - 1
+
+__device__ __forceinline__ uint32_t spread16(uint32_t x) {  // bit i -> bit 2i
+    x &= 0xFFFFu;
+    x = (x | (x << 8)) & 0x00FF00FFu;
+    x = (x | (x << 4)) & 0x0F0F0F0Fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return x;
+}
+
+template <int J>
+struct VecVM {
+    static constexpr uint32_t V = 2 * J;                 // rows per thread
+    static constexpr uint32_t T = V * NT;                // rows per tile
+    static constexpr uint32_t SLAB = NT * 16;            // bytes between the two-row groups j and j+1 of one slot
+    static constexpr uint32_t SLOT_BYTES = T * 8;        // one slot = T values indexed by local row
+
+    struct State {
+        uint32_t alive;  // bit v: row v of this thread is still in the pipeline
+        uint32_t exc;    // bit v: row v raised
+    };
+    // local row of (j, b) for this thread: lr = j * 2 NT + 2 tid + b
+    static __device__ __forceinline__ uint32_t lrow(uint32_t j, uint32_t b) { return j * 2 * NT + 2 * threadIdx.x + b; }
+
+    static __device__ __forceinline__ ulonglong2 ld2(const uint8_t *rb, uint32_t off, uint32_t j) {
+        return *reinterpret_cast<const ulonglong2 *>(rb + off + j * SLAB);
+    }
+    static __device__ __forceinline__ void st2(uint8_t *rb, uint32_t off, uint32_t j, ulonglong2 v) {
+        *reinterpret_cast<ulonglong2 *>(rb + off + j * SLAB) = v;
+    }
+    static __device__ __forceinline__ void raise_row(State &st, uint32_t v, uint32_t code, uint32_t opidx, uint32_t *exc_stage, uint32_t lr) {
+        st.alive &= ~(1u << v);
+        st.exc |= 1u << v;
+        exc_stage[lr] = code | (opidx << 16);
+    }
+
+    // rb = regs base + tid * 16. tile_row0 = first input row of the tile. Rows >= n_rows are inactive from the start.
+    static __device__ void run(const DInstr *__restrict__ prog, uint32_t n_instr, uint8_t *__restrict__ rb, const ColIn *__restrict__ cols,
+                               uint64_t tile_row0, uint64_t n_rows, State &st, uint32_t *__restrict__ exc_stage) {
+        for (uint32_t pc = 0; pc < n_instr; ++pc) {
+            const uint4 w0 = *reinterpret_cast<const uint4 *>(&prog[pc]);
+            const uint2 w1 = *reinterpret_cast<const uint2 *>(&prog[pc].c);
+            const uint32_t op = w0.x & 0xFF, flags = (w0.x >> 8) & 0xFF, opidx = w0.x >> 16;
+            const uint32_t dst = w0.y, a = w0.z, b = w0.w, c = w1.x, guard = w1.y;
+            const uint64_t imm = (uint64_t)prog[pc].imm, imm2 = (uint64_t)prog[pc].imm2;
+            uint32_t act = st.alive;  // rows this instruction executes for
+            if (guard != NOOFF) {
+#pragma unroll
+                for (uint32_t j = 0; j < J; ++j) {
+                    const ulonglong2 g = ld2(rb, guard, j);
+                    if (g.x == 0) act &= ~(1u << (2 * j));
+                    if (g.y == 0) act &= ~(2u << (2 * j));
+                }
+            }
+            if (!__any_sync(0xFFFFFFFFu, act != 0)) continue;
+            const bool guarded = guard != NOOFF;
+            // operands: constants ride in the immediates (a <- imm2, b <- imm, c <- imm2)
+#define LDA(j) ((flags & TPLX_F_A_CONST) ? make_ulonglong2(imm2, imm2) : ld2(rb, a, j))
+#define LDB(j) ((flags & TPLX_F_B_CONST) ? make_ulonglong2(imm, imm) : ld2(rb, b, j))
+            // store: unguarded ops write both rows unconditionally (a row that is not alive never reaches an output);
+            // guarded ops must leave the destination of rows outside the guard untouched (phi of an if-converted branch)
+#define STD(j, R0, R1)                                                                     \
+    do {                                                                                   \
+        ulonglong2 _r = make_ulonglong2((R0), (R1));                                       \
+        if (guarded) {                                                                     \
+            const ulonglong2 _o = ld2(rb, dst, j);                                         \
+            if (!((act >> (2 * (j))) & 1u)) _r.x = _o.x;                                   \
+            if (!((act >> (2 * (j) + 1)) & 1u)) _r.y = _o.y;                               \
+        }                                                                                  \
+        st2(rb, dst, j, _r);                                                               \
+    } while (0)
+#define BIN(EXPR)                                                                          \
+    _Pragma("unroll") for (uint32_t j = 0; j < J; ++j) {                                   \
+        const ulonglong2 A = LDA(j), B = LDB(j);                                           \
+        uint64_t r0, r1;                                                                   \
+        { const uint64_t x = A.x, y = B.x; r0 = (EXPR); }                                  \
+        { const uint64_t x = A.y, y = B.y; r1 = (EXPR); }                                  \
+        STD(j, r0, r1);                                                                    \
+    }                                                                                      \
+    break
+#define UNA(EXPR)                                                                          \
+    _Pragma("unroll") for (uint32_t j = 0; j < J; ++j) {                                   \
+        const ulonglong2 A = LDA(j);                                                       \
+        uint64_t r0, r1;                                                                   \
+        { const uint64_t x = A.x; r0 = (EXPR); }                                           \
+        { const uint64_t x = A.y; r1 = (EXPR); }                                           \
+        STD(j, r0, r1);                                                                    \
+    }                                                                                      \
+    break
+#define F(x) __longlong_as_double((long long)(x))
+#define U(d) ((uint64_t)__double_as_longlong(d))
+            // ops that can raise: evaluated row by row for the active rows only
+#define RAISING(...)                                                                       \
+    _Pragma("unroll") for (uint32_t v = 0; v < V; ++v) {                                   \
+        if (!((act >> v) & 1u)) continue;                                                  \
+        const uint32_t off8 = (v >> 1) * SLAB + (v & 1) * 8;                               \
+        const uint64_t x = (flags & TPLX_F_A_CONST) ? imm2 : *reinterpret_cast<const uint64_t *>(rb + a + off8); \
+        const uint64_t y = (flags & TPLX_F_B_CONST) ? imm : *reinterpret_cast<const uint64_t *>(rb + b + off8);  \
+        uint64_t r;                                                                        \
+        bool bad = false;                                                                  \
+        __VA_ARGS__;                                                                       \
+        if (bad) raise_row(st, v, TPLX_EC_ZERODIVISIONERROR, opidx, exc_stage, lrow(v >> 1, v & 1)); \
+        else *reinterpret_cast<uint64_t *>(rb + dst + off8) = r;                           \
+    }                                                                                      \
+    break
+            switch (op) {
+                case TPLX_OP_LDCOL: {
+                    const ColIn &ci = cols[imm];
+                    const uint64_t *src = reinterpret_cast<const uint64_t *>(ci.data);
+#pragma unroll
+                    for (uint32_t j = 0; j < J; ++j) {
+                        const uint64_t row = tile_row0 + lrow(j, 0);
+                        ulonglong2 v = make_ulonglong2(0, 0);
+                        if (row + 1 < n_rows) v = *reinterpret_cast<const ulonglong2 *>(src + row);  // 16-byte aligned: row is even, base is
+                        else if (row < n_rows) v.x = src[row];
+                        STD(j, v.x, v.y);
+                    }
+                    break;
+                }
+                case TPLX_OP_LDI:
+#pragma unroll
+                    for (uint32_t j = 0; j < J; ++j) STD(j, imm, imm);
+                    break;
+                case TPLX_OP_LDROW:
+#pragma unroll
+                    for (uint32_t j = 0; j < J; ++j) {
+                        const uint64_t row = tile_row0 + lrow(j, 0);
+                        STD(j, row, row + 1);
+                    }
+                    break;
+                case TPLX_OP_MOV: UNA(x);
+                case TPLX_OP_SEL:
+#pragma unroll
+                    for (uint32_t j = 0; j < J; ++j) {
+                        const ulonglong2 A = LDA(j), B = LDB(j), Cn = ld2(rb, c, j);
+                        STD(j, Cn.x ? A.x : B.x, Cn.y ? A.y : B.y);
+                    }
+                    break;
+                case TPLX_OP_IADD: BIN(x + y);
+                case TPLX_OP_ISUB: BIN(x - y);
+                case TPLX_OP_IMUL: BIN(x * y);
+                case TPLX_OP_INEG: UNA((uint64_t)0 - x);
+                case TPLX_OP_IAND: BIN(x & y);
+                case TPLX_OP_IOR: BIN(x | y);
+                case TPLX_OP_IXOR: BIN(x ^ y);
+                case TPLX_OP_ISHL: BIN(x << (y & 63));
+                case TPLX_OP_ISHR: BIN((uint64_t)((int64_t)x >> (y & 63)));
+                case UOP_ISHR_FLOORDIV: UNA((uint64_t)((int64_t)x >> (imm & 63)));
+                case UOP_IAND_MOD: UNA(x & imm);
+                case TPLX_OP_IABS: UNA((int64_t)x < 0 ? (uint64_t)0 - x : x);
+                case TPLX_OP_FADD: BIN(U(__dadd_rn(F(x), F(y))));
+                case TPLX_OP_FSUB: BIN(U(__dsub_rn(F(x), F(y))));
+                case TPLX_OP_FMUL: BIN(U(__dmul_rn(F(x), F(y))));
+                case TPLX_OP_FNEG: UNA(x ^ 0x8000000000000000ull);
+                case TPLX_OP_FABS: UNA(x & 0x7FFFFFFFFFFFFFFFull);
+                case TPLX_OP_I2F: UNA(U((double)(int64_t)x));
+                case TPLX_OP_F2I: UNA((uint64_t)(int64_t)F(x));
+                case TPLX_OP_BAND: BIN((uint64_t)((x != 0) & (y != 0)));
+                case TPLX_OP_BOR: BIN((uint64_t)((x != 0) | (y != 0)));
+                case TPLX_OP_BNOT: UNA((uint64_t)(x == 0));
+                case TPLX_OP_ICMP:
+                    switch (flags & 7) {
+                        case TPLX_CMP_EQ: BIN((uint64_t)(x == y));
+                        case TPLX_CMP_NE: BIN((uint64_t)(x != y));
+                        case TPLX_CMP_LT: BIN((uint64_t)((int64_t)x < (int64_t)y));
+                        case TPLX_CMP_LE: BIN((uint64_t)((int64_t)x <= (int64_t)y));
+                        case TPLX_CMP_GT: BIN((uint64_t)((int64_t)x > (int64_t)y));
+                        default: BIN((uint64_t)((int64_t)x >= (int64_t)y));
+                    }
+                    break;
+                case TPLX_OP_FCMP:
+                    switch (flags & 7) {  // ordered predicates: false when either side is NaN
+                        case TPLX_CMP_EQ: BIN((uint64_t)(F(x) == F(y)));
+                        case TPLX_CMP_NE: BIN((uint64_t)((F(x) < F(y)) || (F(x) > F(y))));
+                        case TPLX_CMP_LT: BIN((uint64_t)(F(x) < F(y)));
+                        case TPLX_CMP_LE: BIN((uint64_t)(F(x) <= F(y)));
+                        case TPLX_CMP_GT: BIN((uint64_t)(F(x) > F(y)));
+                        default: BIN((uint64_t)(F(x) >= F(y)));
+                    }
+                    break;
+                case TPLX_OP_IFLOORDIV: RAISING({ if ((int64_t)y == 0) bad = true; else r = (uint64_t)floordiv_i64((int64_t)x, (int64_t)y); });
+                case TPLX_OP_IMOD: RAISING({ if ((int64_t)y == 0) bad = true; else r = (uint64_t)floormod_i64((int64_t)x, (int64_t)y); });
+                case TPLX_OP_FDIV: RAISING({ if (F(y) == 0.0) bad = true; else r = U(__ddiv_rn(F(x), F(y))); });
+                case TPLX_OP_FMOD: RAISING({
+                    if (F(y) == 0.0) bad = true;
+                    else {
+                        double m = fmod(F(x), F(y));  // == LLVM frem, exact
+                        if (m != 0.0 && ((m < 0.0) != (F(y) < 0.0))) m = __dadd_rn(m, F(y));
+                        r = U(m);
+                    }
+                });
+                case TPLX_OP_FFLOORDIV: RAISING({
+                    const int64_t xi = (int64_t)F(x), yi = (int64_t)F(y);
+                    if (F(y) == 0.0 || yi == 0) bad = true;
+                    else r = U((double)floordiv_i64(xi, yi));
+                });
+                case TPLX_OP_FILTER:
+#pragma unroll
+                    for (uint32_t j = 0; j < J; ++j) {
+                        const ulonglong2 A = ld2(rb, a, j);
+                        if (A.x == 0) st.alive &= ~(act & (1u << (2 * j)));
+                        if (A.y == 0) st.alive &= ~(act & (2u << (2 * j)));
+                    }
+                    break;
+                case TPLX_OP_RAISE:
+#pragma unroll
+                    for (uint32_t v = 0; v < V; ++v)
+                        if ((act >> v) & 1u) raise_row(st, v, (uint32_t)imm, opidx, exc_stage, lrow(v >> 1, v & 1));
+                    break;
+                default: break;
+            }
+#undef LDA
+#undef LDB
+#undef STD
+#undef BIN
+#undef UNA
+#undef F
+#undef U
+#undef RAISING
+        }
+    }
+};
+
+// K1v kernel: persistent CTAs, ticketed tiles of T = 2J * 256 rows, VecVM evaluation, shared tail (rows_tile_finish).
+// Shared memory: prog | cols | regs (n_slots x T x 8 B; output columns are staged in place) | misc (bitmaps, scan scratch).
+template <int J>
+__global__ void __launch_bounds__(NT) stage_rows_vec_kernel(const KParams *__restrict__ Pg) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const KParams &P = *Pg;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr uint32_t T = VecVM<J>::T, W = T / 32;
+    const uint32_t K = P.K;
+
+    DInstr *s_prog = reinterpret_cast<DInstr *>(smem);
+    ColIn *s_cols = reinterpret_cast<ColIn *>(smem + P.smem_cols_off);
+    uint8_t *s_regs = smem + P.smem_regs_off;
+    uint32_t *keep_bits = reinterpret_cast<uint32_t *>(smem + P.smem_misc_off);
+    uint32_t *exc_bits = keep_bits + W;
+    uint32_t *keep_pre = exc_bits + W;
+    uint32_t *exc_pre = keep_pre + W + 1;
+    uint32_t *exc_stage = exc_pre + W + 1;
+    uint64_t *s_vals = reinterpret_cast<uint64_t *>(exc_stage + T);
+    uint64_t *s_excl = s_vals + MAX_SCAN;
+    uint64_t *s_warp = s_excl + MAX_SCAN;
+    uint32_t *s_ctl = reinterpret_cast<uint32_t *>(s_warp + NT / 32 + 1);
+
+    for (uint32_t i = tid; i < P.n_instr * (sizeof(DInstr) / 16); i += NT)
+        reinterpret_cast<uint4 *>(s_prog)[i] = reinterpret_cast<const uint4 *>(P.prog)[i];
+    for (uint32_t i = tid; i < P.n_in * (sizeof(ColIn) / 8); i += NT)
+        reinterpret_cast<uint64_t *>(s_cols)[i] = reinterpret_cast<const uint64_t *>(P.in)[i];
+    const uint32_t state_stride = 1 + 2 * K;
+
+    while (true) {
+        __syncthreads();
+        if (tid == 0) s_ctl[0] = atomicAdd(&P.counters[0], 1u);
+        __syncthreads();
+        const uint32_t tile = s_ctl[0];
+        if (tile >= P.n_tiles) break;
+        const uint64_t base = (uint64_t)tile * T;
+
+        typename VecVM<J>::State st;
+        st.alive = 0;
+        st.exc = 0;
+#pragma unroll
+        for (uint32_t v = 0; v < 2 * J; ++v)
+            if (base + VecVM<J>::lrow(v >> 1, v & 1) < P.n_rows) st.alive |= 1u << v;
+        VecVM<J>::run(s_prog, P.n_instr, s_regs + tid * 16, s_cols, base, P.n_rows, st, exc_stage);
+        // bitmaps indexed by local row: rows (2 tid, 2 tid + 1) of slab j -> word j * 16 + tid / 16, bits 2 (tid % 16) + {0, 1}
+#pragma unroll
+        for (uint32_t j = 0; j < J; ++j) {
+            const uint32_t ke = __ballot_sync(0xFFFFFFFFu, (st.alive >> (2 * j)) & 1u), ko = __ballot_sync(0xFFFFFFFFu, (st.alive >> (2 * j + 1)) & 1u);
+            const uint32_t ee = __ballot_sync(0xFFFFFFFFu, (st.exc >> (2 * j)) & 1u), eo = __ballot_sync(0xFFFFFFFFu, (st.exc >> (2 * j + 1)) & 1u);
+            if (lane == 0) {
+                const uint32_t w = j * (2 * NT / 32) + 2 * warp;
+                keep_bits[w] = spread16(ke) | (spread16(ko) << 1);
+                keep_bits[w + 1] = spread16(ke >> 16) | (spread16(ko >> 16) << 1);
+                exc_bits[w] = spread16(ee) | (spread16(eo) << 1);
+                exc_bits[w + 1] = spread16(ee >> 16) | (spread16(eo >> 16) << 1);
+            }
+        }
+        __syncthreads();
+        rows_tile_finish(P, TileSmem{s_regs, nullptr, keep_bits, exc_bits, keep_pre, exc_pre, exc_stage, s_vals, s_excl, s_warp}, tile, base, 2 * J, T, W,
+                         K, state_stride);
+    }
+}
+
+}  // namespace tplx
