@@ -385,3 +385,36 @@ def test_lazy_csv_column_read_by_the_prefilter_is_rejected(gpu):
     with pytest.raises(backend.GpuBackendError) as e:
         backend.Stage(prog).run(bad.block)
     assert "col_lazy" in str(e.value)
+
+
+def test_sharded_execution_over_two_tasks_matches_one(gpu):
+    """tuplex.gpu.devices lists the devices a stage's blocks are sharded over (one task per device, contiguous block ranges, shards
+    concatenated in order). With the same device listed twice the sharding / row numbering / merge logic runs on a single GPU:
+    results, exception counts and resolved-row order must equal the unsharded run (LocalBackend.cc:679-735,1104-1152)."""
+    import random
+    rng = random.Random(4)
+    data = [(rng.randint(-50, 50), rng.randint(0, 6), "w%d" % rng.randint(0, 9)) for _ in range(40_000)]
+    one = tuplex_b200.Context({"tuplex.gpu.blockRows": 5000})
+    two = tuplex_b200.Context({"tuplex.gpu.blockRows": 5000, "tuplex.gpu.devices": "0,0"})
+    three = tuplex_b200.Context({"tuplex.gpu.blockRows": 3000, "tuplex.gpu.devices": "0,0,0"})
+
+    def pipe(c):
+        return (c.parallelize(data, columns=["a", "b", "s"])
+                 .withColumn("q", lambda x: x["a"] // x["b"])                  # ZeroDivisionError rows
+                 .resolve(ZeroDivisionError, lambda x: -999)
+                 .filter(lambda x: x["q"] % 5 != 1)
+                 .withColumn("t", lambda x: x["s"].upper() + str(x["q"])))
+    want = pipe(one).collect()
+    assert pipe(two).collect() == want
+    assert pipe(three).collect() == want
+    # unresolved exceptions: dropped rows and counts agree
+    def pipe2(c):
+        return c.parallelize(data, columns=["a", "b", "s"]).map(lambda x: (x["a"] % x["b"], x["s"]))
+    d1, d2 = pipe2(one), pipe2(two)
+    assert d1.collect() == d2.collect() and d1.exception_counts == d2.exception_counts and sum(d1.exception_counts.values()) > 1000
+    # aggregate (i64: exact whatever the association) and aggregateByKey / unique over the shards
+    agg = lambda c: c.parallelize(data, columns=["a", "b", "s"]).aggregate(lambda x, y: x + y, lambda acc, r: acc + r["a"] * r["b"], 0).collect()
+    assert agg(one) == agg(two) == agg(three) == [sum(a * b for a, b, _ in data)]
+    byk = lambda c: c.parallelize(data, columns=["a", "b", "s"]).aggregateByKey(lambda x, y: x + y, lambda acc, r: acc + r["a"], 0, ["s"]).collect()
+    assert sorted(byk(one)) == sorted(byk(two)) == sorted(byk(three))
+    assert len(byk(one)) == 10

@@ -152,3 +152,28 @@ def test_two_gpus_one_process_local_comm(gpu):
     finally:
         for dv in devs:
             backend.comm_destroy(dv)
+
+
+def test_context_over_two_devices(gpu):
+    """Context(tuplex.gpu.devices='0,1'): blocks sharded over both GPUs inside one process, outputs concatenated in order, the
+    aggregate combined by tplx_gpu_agg_finish and aggregateByKey by tplx_gpu_stage_hash_exchange over the context's communicator."""
+    import random
+    import tuplex_b200
+    from tuplex_b200 import backend
+    if backend.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    rng = random.Random(8)
+    data = [(rng.randint(-50, 50), rng.randint(0, 6), "w%d" % rng.randint(0, 99)) for _ in range(60_000)]
+    one = tuplex_b200.Context({"tuplex.gpu.blockRows": 7000})
+    two = tuplex_b200.Context({"tuplex.gpu.blockRows": 7000, "tuplex.gpu.devices": "0,1"})
+    pipe = lambda c: (c.parallelize(data, columns=["a", "b", "s"]).withColumn("q", lambda x: x["a"] // x["b"])
+                       .resolve(ZeroDivisionError, lambda x: -999).filter(lambda x: x["q"] % 5 != 1)
+                       .withColumn("t", lambda x: x["s"].upper() + str(x["q"])))
+    assert pipe(two).collect() == pipe(one).collect()
+    agg = lambda c: c.parallelize(data, columns=["a", "b", "s"]).aggregate(lambda x, y: x + y, lambda acc, r: acc + r["a"] * r["b"], 0).collect()
+    assert agg(two) == agg(one) == [sum(a * b for a, b, _ in data)]
+    fagg = lambda c: c.parallelize(data, columns=["a", "b", "s"]).aggregate(lambda x, y: x + y, lambda acc, r: acc + r["a"] * 0.1, 0.0).collect()
+    assert abs(fagg(two)[0] - fagg(one)[0]) <= 1e-9 * abs(fagg(one)[0])
+    byk = lambda c: c.parallelize(data, columns=["a", "b", "s"]).aggregateByKey(lambda x, y: x + y, lambda acc, r: acc + r["a"], 0, ["s"]).collect()
+    assert sorted(byk(two)) == sorted(byk(one)) and len(byk(one)) == 100
+    assert sorted(two.parallelize([r[2] for r in data]).unique().collect()) == sorted({r[2] for r in data})

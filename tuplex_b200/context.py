@@ -80,10 +80,18 @@ class Context:
         if self._options["tuplex.backend"] not in ("gpu",):
             raise ValueError("this build provides the gpu backend only")
         devs = [int(d) for d in str(self._options["tuplex.gpu.devices"]).replace(";", ",").split(",") if d != ""]
-        self._device = devs[0] if devs else 0
+        self._devices = devs or [0]        # blocks of a stage are sharded contiguously over these (one task per device)
+        self._device = self._devices[0]
         self._block_rows = int(self._options["tuplex.gpu.blockRows"])
         self.metrics = Metrics()
         self._messages: List[str] = []
+
+    def _ensure_local_comm(self, devs):
+        """One NCCL communicator over this context's devices, created once (tplx_gpu_comm_init_local): the aggregate endpoints'
+        combine / exchange run through it inside the C ABI."""
+        backend.init(devs)
+        if backend.comm_info(devs[0]) is None:
+            backend.comm_init_local(devs)
 
     def _log(self, msg: str):
         self._messages.append(msg)

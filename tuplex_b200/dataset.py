@@ -346,7 +346,7 @@ def _run_stage(ctx, src: Source, ops: List[Op], exc_counter: Counter, csv_sink: 
             return _run_stage_python(ctx, src.to_host_source(), ops, exc_counter)
         ir.project_inputs(prog, used_cols)
     dev = ctx._device
-    backend.init([dev])
+    backend.init(sorted(set(getattr(ctx, "_devices", [dev]))))
     stage = backend.Stage(prog)
     block_rows = ctx._block_rows
     in_values: Optional[List[list]] = None  # python values of input columns, built lazily for resolve
@@ -363,34 +363,22 @@ def _run_stage(ctx, src: Source, ops: List[Op], exc_counter: Counter, csv_sink: 
 
     fallback = list(src.fallback)
 
-    out_cols_all: List[List[Column]] = []
-    exc_all: List[np.ndarray] = []
-    agg_partials: List[List[int]] = []
-    first_row_no = 0
-    base = 0
     n = src.n_rows
     starts = list(range(0, n, block_rows)) or [0]
+    devs = list(getattr(ctx, "_devices", [dev])) or [dev]
+    if is_csv or len(starts) < 2:
+        devs = devs[:1]  # the CSV source parses chunk after chunk on one device; a single block has nothing to shard
+    import threading
+    mlock = threading.Lock()
 
-    def host_blocks():
-        for lo in starts:
-            hi = min(n, lo + block_rows)
-            cols = [c.slice(lo, hi) for c in src.cols] if (lo, hi) != (0, n) else src.cols
-            yield (lambda cols=cols, lo=lo, hi=hi: stage.run_host(dev, cols, hi - lo, first_row_no)), lo, None, None
-
-    def csv_blocks():
-        base = 0
-        col_types = [t if c in used_cols else backend.CSV_SKIP for c, t in enumerate(in_types)]
-        lazy = csv_lazy_columns(prog, used_cols, in_types)
-        for data, skip_header in src.chunks():
-            buf = backend.CsvBuffer(dev, data)
-            parse = buf.parse(col_types, src.delimiter, src.quotechar, skip_header, src.null_values, lazy=lazy)
-            yield (lambda parse=parse: stage.run(parse.block, first_row_no)), base, parse, data
-            base += int(parse.info.n_rows)
-            parse.free()
-            buf.free()
-        src.total_rows = base
-
-    held: List[tuple] = []
+    class Shard:
+        """What one task (= one device's contiguous run of blocks, LocalBackend.cc:679-735) produced."""
+        def __init__(self):
+            self.out_cols: List[List[Column]] = []
+            self.excs: List[np.ndarray] = []
+            self.partials: List[List[int]] = []
+            self.held: List[tuple] = []
+            self.row_no = 0  # rows written + exceptions so far (TransformTask::_outputRowCounter)
 
     def fetch_cols(res, lo, rowmap):
         oc = res.columns()
@@ -400,10 +388,11 @@ def _run_stage(ctx, src: Source, ops: List[Op], exc_counter: Counter, csv_sink: 
             oc[-1].data += lo
         return oc
 
-    for run, lo, parse, data in (csv_blocks() if is_csv else host_blocks()):
-        res = run()
+    def consume(sh: "Shard", res, lo, parse, data):
+        """Take one block's result into the shard (exception records, output columns or partial aggregate)."""
         info = res.info
-        ctx.metrics._add(info)
+        with mlock:
+            ctx.metrics._add(info)
         exc = res.exceptions()
         rowmap = None
         if parse is not None:
@@ -414,8 +403,8 @@ def _run_stage(ctx, src: Source, ops: List[Op], exc_counter: Counter, csv_sink: 
             if pinfo.n_bad:  # block row -> data row
                 rowmap = parse.rowmap().astype(np.int64)
                 raw = data.tobytes()
-                for b in parse.bad_rows():
-                    fallback.append((lo + int(b["row"]), src.line_object(raw[int(b["line_start"]):int(b["line_end"])], False)))
+                for bad in parse.bad_rows():
+                    fallback.append((lo + int(bad["row"]), src.line_object(raw[int(bad["line_start"]):int(bad["line_end"])], False)))
         if len(exc):
             exc = exc.copy()
             if rowmap is not None:
@@ -424,22 +413,94 @@ def _run_stage(ctx, src: Source, ops: List[Op], exc_counter: Counter, csv_sink: 
                 ends = parse.row_ends().astype(np.int64)
                 ends[0] = -1 if ends[0] == 0xFFFFFFFF else ends[0]
                 raw = data.tobytes()
-                for r in exc["row"]:
-                    a = int(ends[r]) + 1
-                    while raw[a] in (10, 13):
-                        a += 1
-                    csv_rows[lo + int(r)] = src.line_object(raw[a:int(ends[r + 1])], True)
+                for r_ in exc["row"]:
+                    a_ = int(ends[r_]) + 1
+                    while raw[a_] in (10, 13):
+                        a_ += 1
+                    csv_rows[lo + int(r_)] = src.line_object(raw[a_:int(ends[r_ + 1])], True)
             exc["row"] += lo
-            exc_all.append(exc)
+            sh.excs.append(exc)
         if prog.endpoint == C["TPLX_EP_MEMORY"]:
-            first_row_no += int(info.n_out_rows) + int(info.n_exceptions)
+            sh.row_no += int(info.n_out_rows) + int(info.n_exceptions)
             if csv_sink is not None:
-                held.append((res, lo, rowmap))  # decide at the end: device CSV writer or column fetch + merge
-                continue
-            out_cols_all.append(fetch_cols(res, lo, rowmap))
+                sh.held.append((res, lo, rowmap))  # decide at the end: device CSV writer or column fetch + merge
+                return
+            sh.out_cols.append(fetch_cols(res, lo, rowmap))
         elif prog.endpoint == C["TPLX_EP_AGGREGATE"]:
-            agg_partials.append(res.aggregate_bits())
+            sh.partials.append(res.aggregate_bits())
         res.free()
+
+    shards: List[Shard] = []
+    agg_combined: Optional[List[int]] = None
+    hash_shares: List[List[Column]] = []
+    if is_csv:
+        sh = Shard()
+        base = 0
+        col_types = [t if c in used_cols else backend.CSV_SKIP for c, t in enumerate(in_types)]
+        lazy = csv_lazy_columns(prog, used_cols, in_types)
+        for data, skip_header in src.chunks():
+            buf = backend.CsvBuffer(dev, data)
+            parse = buf.parse(col_types, src.delimiter, src.quotechar, skip_header, src.null_values, lazy=lazy)
+            consume(sh, stage.run(parse.block, sh.row_no), base, parse, data)
+            base += int(parse.info.n_rows)
+            parse.free()
+            buf.free()
+        src.total_rows = base
+        shards.append(sh)
+    else:
+        # blocks are sharded contiguously over the context's devices (tuplex.gpu.devices): one task per device, its blocks in
+        # order; concatenating the shards in device order preserves the input order (LocalBackend.cc:1104-1152). Map / filter
+        # stages exchange nothing; aggregate endpoints combine through the C ABI's collectives when every device is distinct.
+        from .dist import shard_range
+        blocks = [(lo, min(n, lo + block_rows)) for lo in starts]
+        phys = len(set(devs)) == len(devs) and len(devs) > 1  # distinct physical devices: NCCL communicator over them
+        if phys:
+            ctx._ensure_local_comm(devs)
+
+        def run_shard(k: int) -> Shard:
+            sh = Shard()
+            blo, bhi = shard_range(len(blocks), k, len(devs))
+            for lo, hi in blocks[blo:bhi]:
+                cols = [c.slice(lo, hi) for c in src.cols] if (lo, hi) != (0, n) else src.cols
+                consume(sh, stage.run_host(devs[k], cols, hi - lo, sh.row_no), lo, None, None)
+            if len(devs) > 1 and prog.endpoint == C["TPLX_EP_AGGREGATE"] and phys:
+                # this device's partial = its blocks folded in block order; collective: NCCL all-gather + fold in device order
+                part = None
+                for p in sh.partials:
+                    part = p if part is None else [_acc_bits(a.kind, _acc_combine(a.kind, _acc_value(a.kind, x), _acc_value(a.kind, y)))
+                                                   for a, x, y in zip(prog.accs, part, p)]
+                if part is None:
+                    part = [_acc_identity_bits(a.kind) for a in prog.accs]
+                sh.partials = [stage.agg_finish(devs[k], part)]
+            if len(devs) > 1 and prog.endpoint == C["TPLX_EP_HASH"] and phys:
+                stage.hash_exchange(devs[k])  # collective: afterwards this device's table holds the groups it owns
+            return sh
+
+        if len(devs) == 1:
+            shards = [run_shard(0)]
+        else:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(len(devs)) as ex:
+                shards = list(ex.map(run_shard, range(len(devs))))
+            if prog.endpoint == C["TPLX_EP_AGGREGATE"] and phys:
+                agg_combined = shards[0].partials[0]  # every device holds the same combined bits
+    # one numbering over the whole stage: a shard's row numbers continue where the previous shard stopped
+    out_cols_all: List[List[Column]] = []
+    exc_all: List[np.ndarray] = []
+    agg_partials: List[List[int]] = []
+    held: List[tuple] = []
+    off = 0
+    for sh in shards:
+        for e in sh.excs:
+            if off:
+                e["row_no"] += off
+            exc_all.append(e)
+        off += sh.row_no
+        out_cols_all += sh.out_cols
+        agg_partials += sh.partials
+        held += sh.held
+    if agg_combined is not None:
+        agg_partials = [agg_combined]
     excs = np.concatenate(exc_all) if exc_all else np.zeros(0, dtype=backend.EXC_DTYPE)
 
     # ---- endpoints --------------------------------------------------------------------------------
@@ -518,12 +579,15 @@ def _run_stage(ctx, src: Source, ops: List[Op], exc_counter: Counter, csv_sink: 
         stage.close()
         return [value], [None] * (len(value) if isinstance(value, tuple) else 1)
 
-    # hash endpoint
-    res = stage.hash_finish(dev)
-    cols = res.columns()
-    res.free()
+    # hash endpoint: every distinct device holds the groups it owns after the exchange (a single table otherwise)
     nk = prog.n_keys
-    vals = [c.to_values() for c in cols]
+    vals: List[list] = []
+    for dv in (sorted(set(devs), key=devs.index) if not is_csv else [dev]):
+        res = stage.hash_finish(dv)
+        cols = res.columns()
+        res.free()
+        part_vals = [c.to_values() for c in cols]
+        vals = part_vals if not vals else [a_ + b_ for a_, b_ in zip(vals, part_vals)]
     n_out = len(vals[0]) if vals else 0
     table: Dict[Any, list] = {}
     order: List[Any] = []
@@ -582,6 +646,17 @@ def _acc_value(kind: int, bits: int):
     if kind in (C["TPLX_ACC_SUM_F64"], C["TPLX_ACC_MIN_F64"], C["TPLX_ACC_MAX_F64"]):
         return ir.bits_f64(bits)
     return bits - (1 << 64) if bits >= 1 << 63 else bits
+
+
+def _acc_bits(kind: int, v) -> int:
+    if kind in (C["TPLX_ACC_SUM_F64"], C["TPLX_ACC_MIN_F64"], C["TPLX_ACC_MAX_F64"]):
+        return ir.f64_bits(float(v))
+    return int(v) & ((1 << 64) - 1)
+
+
+def _acc_identity_bits(kind: int) -> int:
+    return {C["TPLX_ACC_SUM_I64"]: 0, C["TPLX_ACC_SUM_F64"]: 0, C["TPLX_ACC_MIN_I64"]: (1 << 63) - 1, C["TPLX_ACC_MAX_I64"]: 1 << 63,
+            C["TPLX_ACC_MIN_F64"]: 0x7FF0000000000000}.get(kind, 0xFFF0000000000000)
 
 
 def _acc_combine(kind: int, a, b):
