@@ -268,6 +268,49 @@ typedef struct tplx_fused_header {
 } tplx_fused_header;
 #define TPLX_MAX_FUSED_PREDS 8
 
+/*
+ * String-scan hint (MEMORY endpoint; used for the prefilter stage of a selective pipeline): when the whole stage is a chain of
+ * filters, each of one of the closed forms below, the planner ALSO states it as a list of terms (carried in the `fused` section
+ * of that stage with TPLX_SCAN_MAGIC). The executor may then evaluate the terms with a dedicated kernel instead of interpreting
+ * the program. An execution hint like the two above: same rows kept, same exception rows (code, operator), evaluated in program
+ * order so that a row raises only in terms it reaches; the oracle ignores it and the parity tests compare both paths.
+ *   CONTAINS    needle in column (column optionally lower()/upper()-ed), optionally negated          SLOWER/SUPPER + SIN (+ BNOT) + FILTER
+ *   FIELD_INT   i = s.find(marker); head = s[: i if i >= 0 else len(s)]; j = head.rfind(sep);
+ *               v = int(head[(0 if j < 0 else j + skip):]);  v <cmp> imm                             SFINDE SSLICE SRFINDK SSLICE S2I ICMP FILTER
+ *               (ValueError of int() -> exception row attributed to operator opidx_val)
+ *   FIXED       fixed-width column <cmp> imm (signed i64 / ordered f64)                              ICMP|FCMP + FILTER
+ */
+#define TPLX_SCAN_MAGIC 0x31435353u /* "SSC1" */
+#define TPLX_MAX_SCAN_TERMS 8
+enum tplx_scan_kind {
+    TPLX_SK_CONTAINS = 0,
+    TPLX_SK_FIELD_INT = 1,
+    TPLX_SK_FIXED = 2,
+};
+enum tplx_scan_flag {
+    TPLX_SCF_CASE_MASK = 3, /* tplx_strflag applied to the column value */
+    TPLX_SCF_NEGATE = 4,    /* CONTAINS: keep the row when the needle is absent */
+    TPLX_SCF_F64 = 8,       /* FIXED: compare as f64 (ordered), else signed i64 */
+};
+typedef struct tplx_scan_term {
+    uint32_t kind;      /* tplx_scan_kind */
+    uint32_t col;       /* input column */
+    uint32_t flags;     /* tplx_scan_flag */
+    uint32_t cmp;       /* tplx_cmp of (value <cmp> imm): FIELD_INT, FIXED */
+    int64_t imm;        /* i64 or f64 bits */
+    uint64_t needle;    /* constant-pool view (offset | length << 32): CONTAINS needle / FIELD_INT marker */
+    uint64_t sep;       /* FIELD_INT: separator (constant-pool view) */
+    int64_t skip;       /* FIELD_INT: added to the separator position */
+    uint32_t opidx_val; /* operator index of the part that can raise (int()) */
+    uint32_t opidx_filter;
+    uint64_t pad;
+} tplx_scan_term;
+typedef struct tplx_scan_header {
+    uint32_t magic;
+    uint32_t n_terms;
+    uint64_t pad;
+} tplx_scan_header;
+
 typedef struct tplx_stage_header {
     uint32_t magic;
     uint32_t version;
@@ -286,7 +329,7 @@ typedef struct tplx_stage_header {
                                  row, used to number exception rows when a prefilter ran); never handed out */
     uint32_t scratch_bytes;   /* per-row scratch for materialised strings */
     uint32_t prefilter_bytes; /* size of the nested prefilter stage descriptor, 0 = none */
-    uint32_t fused_bytes;     /* size of the optional fused-scan section (tplx_fused_header ...), 0 = none */
+    uint32_t fused_bytes;     /* size of the optional closed-form hint: tplx_fused_header ... (AGGREGATE) or tplx_scan_header ... (MEMORY); 0 = none */
 } tplx_stage_header;
 
 #ifdef __cplusplus

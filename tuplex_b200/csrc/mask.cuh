@@ -40,6 +40,8 @@ struct MaskParams {
     uint32_t st_ooff[MASK_MAX_STAGED];     // where its offsets live inside a ring slot
     const DInstr *prog;
     const uint8_t *cpool;
+    uint32_t n_terms;                      // > 0: closed-form evaluation of the stage (string-scan hint), the program is not interpreted
+    tplx_scan_term terms[TPLX_MAX_SCAN_TERMS];
     uint32_t *keep_words, *exc_words;      // n_rows / 32 (rounded up) words each
     uint32_t *exc_codes;                   // n_rows entries, written for exception rows only: code | opidx << 16
     uint8_t *scratch;
@@ -50,6 +52,91 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 
+// ---- K1f: closed-form evaluation of a string-scan hint (include/tplx_ir.h tplx_scan_term) ---------------------------------------
+// The same string primitives as the VM's ops (strops.cuh), called directly: no instruction fetch / decode / register file.
+template <uint32_t HF>
+__device__ __forceinline__ int64_t scan_find(const StrV &h, const StrV &n) {
+    if (n.len == 0) return 0;
+    if (n.len > h.len) return -1;
+    return str_find_impl<HF>(h, n);
+}
+__device__ __forceinline__ bool cmp_i64(uint32_t cmp, int64_t x, int64_t y) {
+    switch (cmp) {
+        case TPLX_CMP_EQ: return x == y;
+        case TPLX_CMP_NE: return x != y;
+        case TPLX_CMP_LT: return x < y;
+        case TPLX_CMP_LE: return x <= y;
+        case TPLX_CMP_GT: return x > y;
+        default: return x >= y;
+    }
+}
+__device__ __forceinline__ bool cmp_f64(uint32_t cmp, double x, double y) {  // ordered predicates (FCMP_O*), != is FCMP_ONE
+    switch (cmp) {
+        case TPLX_CMP_EQ: return x == y;
+        case TPLX_CMP_NE: return (x < y) || (x > y);
+        case TPLX_CMP_LT: return x < y;
+        case TPLX_CMP_LE: return x <= y;
+        case TPLX_CMP_GT: return x > y;
+        default: return x >= y;
+    }
+}
+__device__ __forceinline__ StrV scan_col(const ColIn &ci, uint64_t row) {
+    StrV s;
+    const uint32_t o0 = ci.offsets[row], o1 = ci.offsets[row + 1];
+    s.p = reinterpret_cast<const uint8_t *>(ci.data) + o0;
+    s.len = o1 - o0;
+    s.flags = 0;
+    return s;
+}
+__device__ __forceinline__ StrV scan_const(const uint8_t *cpool, uint64_t enc) {
+    StrV v;
+    v.p = cpool + (uint32_t)enc;
+    v.len = (uint32_t)(enc >> 32);
+    v.flags = 0;
+    return v;
+}
+// evaluates the terms in order for one row; a row raises only in a term it reaches (PipelineBuilder.cc:949)
+__device__ __forceinline__ void scan_eval(const MaskParams &P, const ColIn *__restrict__ cols, uint64_t row, VMThread &t) {
+    for (uint32_t k = 0; k < P.n_terms; ++k) {
+        if (!__any_sync(0xFFFFFFFFu, t.alive)) break;
+        const tplx_scan_term &T = P.terms[k];
+        if (!t.alive) continue;
+        const ColIn &ci = cols[T.col];
+        if (T.kind == TPLX_SK_CONTAINS) {
+            StrV s = scan_col(ci, row);
+            const StrV n = scan_const(P.cpool, T.needle);
+            const uint32_t cf = T.flags & TPLX_SCF_CASE_MASK;
+            s.flags = cf;
+            const int64_t r = cf == TPLX_SF_LOWER ? scan_find<TPLX_SF_LOWER>(s, n) : (cf == TPLX_SF_UPPER ? scan_find<TPLX_SF_UPPER>(s, n) : scan_find<TPLX_SF_NONE>(s, n));
+            t.alive = (r >= 0) != ((T.flags & TPLX_SCF_NEGATE) != 0);
+        } else if (T.kind == TPLX_SK_FIELD_INT) {
+            const StrV s = scan_col(ci, row);
+            const int64_t i = scan_find<TPLX_SF_NONE>(s, scan_const(P.cpool, T.needle));
+            StrV head = s;
+            head.len = i < 0 ? s.len : (uint32_t)i;                                   // s[:stop]
+            const StrV sep = scan_const(P.cpool, T.sep);
+            int64_t j = -1;
+            if (sep.len <= head.len) j = sep.len == 0 ? (int64_t)head.len : str_rfind_impl<TPLX_SF_NONE>(head, sep);
+            const int64_t st = slice_index(j < 0 ? 0 : j + T.skip, (int64_t)head.len);  // head[start:] with Python's clamping
+            StrV f;
+            f.p = head.p + st;
+            f.len = (uint32_t)((int64_t)head.len - st);
+            f.flags = 0;
+            int64_t v;
+            if (!str_to_i64(f, &v)) {
+                t.exc_code = TPLX_EC_VALUEERROR;
+                t.exc_op = T.opidx_val;
+                t.alive = false;
+            } else t.alive = cmp_i64(T.cmp, v, T.imm);
+        } else {
+            const uint64_t raw = reinterpret_cast<const uint64_t *>(ci.data)[row];
+            t.alive = (T.flags & TPLX_SCF_F64) ? cmp_f64(T.cmp, __longlong_as_double((long long)raw), __longlong_as_double((long long)T.imm))
+                                               : cmp_i64(T.cmp, (int64_t)raw, T.imm);
+        }
+    }
+}
+
+template <bool SCAN>
 __global__ void __launch_bounds__(NT) stage_mask_kernel(const MaskParams *__restrict__ Pg) {
     extern __shared__ __align__(16) uint8_t smem[];
     const MaskParams &P = *Pg;
@@ -63,8 +150,9 @@ __global__ void __launch_bounds__(NT) stage_mask_kernel(const MaskParams *__rest
     uint32_t *info = reinterpret_cast<uint32_t *>(smem + P.smem_info_off) + warp * MASK_RING * 2 * MASK_MAX_STAGED;
     uint8_t *ring = smem + P.smem_ring_off + (size_t)warp * MASK_RING * P.slot_bytes;
 
-    for (uint32_t i = tid; i < P.n_instr * (sizeof(DInstr) / 16); i += NT)
-        reinterpret_cast<uint4 *>(s_prog)[i] = reinterpret_cast<const uint4 *>(P.prog)[i];
+    if (!SCAN)
+        for (uint32_t i = tid; i < P.n_instr * (sizeof(DInstr) / 16); i += NT)
+            reinterpret_cast<uint4 *>(s_prog)[i] = reinterpret_cast<const uint4 *>(P.prog)[i];
     for (uint32_t i = lane; i < P.n_in * (sizeof(ColIn) / 8); i += 32)
         reinterpret_cast<uint64_t *>(s_wcols)[i] = reinterpret_cast<const uint64_t *>(P.in)[i];
     if (lane == 0 && ns) {
@@ -138,7 +226,8 @@ __global__ void __launch_bounds__(NT) stage_mask_kernel(const MaskParams *__rest
             t.alive = row < P.n_rows;
             t.exc_code = 0;
             t.scr_used = 0;
-            VM<NT>::run(s_prog, 0, P.n_instr, s_regs, s_wcols, row, row, P.cpool, t);
+            if (SCAN) scan_eval(P, s_wcols, row, t);
+            else VM<NT>::run(s_prog, 0, P.n_instr, s_regs, s_wcols, row, row, P.cpool, t);
             const bool exc = t.exc_code != 0;
             const uint32_t kb = __ballot_sync(0xFFFFFFFFu, t.alive);
             const uint32_t eb = __ballot_sync(0xFFFFFFFFu, exc);

@@ -107,7 +107,8 @@ extern "C" int32_t tplx_gpu_init(const int32_t *devices, int32_t n) {
         CU(cudaFuncSetAttribute(stage_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d->smem_optin));
         CU(cudaFuncSetAttribute(stage_agg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d->smem_optin));
         CU(cudaFuncSetAttribute(stage_hash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d->smem_optin));
-        CU(cudaFuncSetAttribute(stage_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d->smem_optin));
+        CU(cudaFuncSetAttribute(stage_mask_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, d->smem_optin));
+        CU(cudaFuncSetAttribute(stage_mask_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, d->smem_optin));
         // extra execution lanes on the same GPU (chain d -> alt -> alt ...): TPLX_LANES lanes in all. Measured on the
         // Zillow bench: 2 lanes 6.18 G rows/s resident / 653 M rows/s end to end; 3 lanes 6.28 G / 625 M; 4 lanes as 3.
         // The end-to-end number is the headline, so the default stays 2.
@@ -199,6 +200,7 @@ struct tplx_stage {
     bool prefilter_enabled = true;    // switched off at run time when it turns out not to be selective
     uint32_t hidden = 0;              // trailing executor-internal output columns
     bool vec_ok = false;              // fixed-width values and vector-VM ops only: eligible for K1v (vecvm.cuh)
+    std::vector<tplx_scan_term> scan; // string-scan hint (closed form of a pure filter chain), empty = none
     bool has_fused = false;           // closed-form scan-aggregate hint present and valid
     FusedParams fused{};
     std::mutex mu;
@@ -307,7 +309,26 @@ extern "C" int32_t tplx_gpu_stage_create(const void *desc, uint64_t desc_bytes, 
             return bad("stage descriptor: prefilter must be a row-index MEMORY stage over the same input schema");
         off += h.prefilter_bytes;
     }
-    if (h.fused_bytes) {
+    if (h.fused_bytes && h.endpoint == TPLX_EP_MEMORY) {
+        // string-scan hint: the stage as a list of closed-form filter terms (execution hint; validated here)
+        tplx_scan_header sh;
+        if (!need(h.fused_bytes) || h.fused_bytes < sizeof(sh)) return bad("stage descriptor: bad scan section");
+        memcpy(&sh, p + off, sizeof(sh));
+        if (sh.magic != TPLX_SCAN_MAGIC || sh.n_terms == 0 || sh.n_terms > TPLX_MAX_SCAN_TERMS ||
+            h.fused_bytes != sizeof(sh) + sh.n_terms * sizeof(tplx_scan_term))
+            return bad("stage descriptor: malformed scan section");
+        s->scan.resize(sh.n_terms);
+        memcpy(s->scan.data(), p + off + sizeof(sh), sh.n_terms * sizeof(tplx_scan_term));
+        auto view_ok = [&](uint64_t enc) { return (enc & 0xFFFFFFFFull) + (enc >> 32) <= h.const_bytes; };
+        for (const tplx_scan_term &t : s->scan) {
+            bool ok = t.col < h.n_in_cols && t.kind <= TPLX_SK_FIXED && t.cmp <= TPLX_CMP_GE && (!h.n_ops || (t.opidx_val < h.n_ops && t.opidx_filter < h.n_ops));
+            if (ok && t.kind == TPLX_SK_FIXED) ok = s->in_types[t.col] != TPLX_T_STR;
+            if (ok && t.kind != TPLX_SK_FIXED) ok = s->in_types[t.col] == TPLX_T_STR && view_ok(t.needle) && (t.flags & TPLX_SCF_CASE_MASK) <= TPLX_SF_UPPER;
+            if (ok && t.kind == TPLX_SK_FIELD_INT) ok = view_ok(t.sep);
+            if (!ok) return bad("stage descriptor: scan term references bad columns or constants");
+        }
+        off += h.fused_bytes;
+    } else if (h.fused_bytes) {
         // closed-form scan-aggregate hint (execution hint; validated, and ignored when it does not fit)
         if (!need(h.fused_bytes) || h.fused_bytes < sizeof(tplx_fused_header) || h.endpoint != TPLX_EP_AGGREGATE)
             return bad("stage descriptor: bad fused section");
@@ -1124,6 +1145,14 @@ static int32_t run_mask(tplx_stage *ps, StageDev *psd, const tplx_block *b, tplx
     if (P.n_instr && ps->instrs.back().op == TPLX_OP_LDROW && ps->instrs.back().guard == TPLX_NOSLOT) P.n_instr -= 1;
     P.n_in = (uint32_t)ps->in_types.size();
     P.n_slots = std::max<uint32_t>(ps->hdr.n_slots, 1);
+    // K1f: the planner stated the stage in closed form (string-scan hint) -> evaluate the terms directly, nothing is interpreted
+    const bool scan = !ps->scan.empty() && !(getenv("TPLX_NO_SCAN") && atoi(getenv("TPLX_NO_SCAN")));
+    if (scan) {
+        P.n_terms = (uint32_t)ps->scan.size();
+        memcpy(P.terms, ps->scan.data(), ps->scan.size() * sizeof(tplx_scan_term));
+        P.n_slots = 0;  // no register file
+        P.n_instr = 0;
+    }
     P.MR = getenv("TPLX_MASK_MR") ? (uint32_t)std::max(1, std::min(4, atoi(getenv("TPLX_MASK_MR")))) : 1;
     const uint32_t TR = 32 * P.MR;
     P.n_tiles = (uint32_t)((n + TR - 1) / TR);
@@ -1134,7 +1163,7 @@ static int32_t run_mask(tplx_stage *ps, StageDev *psd, const tplx_block *b, tplx
     // string columns the program loads are staged through the warps' shared-memory rings (TPLX_MASK_STAGE=0: plain loads)
     const bool want_stage = !(getenv("TPLX_MASK_STAGE") && atoi(getenv("TPLX_MASK_STAGE")) == 0);
     std::vector<uint32_t> cand;
-    for (uint32_t i = 0; i < P.n_instr && want_stage; ++i) {
+    for (uint32_t i = 0; i < ps->instrs.size() && want_stage; ++i) {
         const tplx_instr &in = ps->instrs[i];
         if (in.op != TPLX_OP_LDCOL || in.flags != TPLX_T_STR) continue;
         const uint32_t c = (uint32_t)in.imm;
@@ -1179,7 +1208,8 @@ static int32_t run_mask(tplx_stage *ps, StageDev *psd, const tplx_block *b, tplx
     }
     if (smem_total > (uint32_t)d->smem_optin) return fail(TPLX_E_UNSUPPORTED, "mask stage needs more shared memory than one SM has");
     int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stage_mask_kernel, NT, smem_total));
+    if (scan) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stage_mask_kernel<true>, NT, smem_total));
+    else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stage_mask_kernel<false>, NT, smem_total));
     if (occ < 1) return fail(TPLX_E_UNSUPPORTED, "mask kernel cannot be resident");
     const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>((P.n_tiles + MASK_WARPS - 1) / MASK_WARPS, (uint32_t)(occ * d->prop.multiProcessorCount)));
     P.scratch_per_thread = ps->materialises ? std::max<uint32_t>(ps->hdr.scratch_bytes, 64) : 0;
@@ -1203,7 +1233,8 @@ static int32_t run_mask(tplx_stage *ps, StageDev *psd, const tplx_block *b, tplx
     rc = dalloc(ra, &dP, 1);
     if (rc) return rc;
     CU(cudaMemcpyAsync(dP, &P, sizeof(P), cudaMemcpyHostToDevice, d->stream));
-    stage_mask_kernel<<<grid, NT, smem_total, d->stream>>>(dP);
+    if (scan) stage_mask_kernel<true><<<grid, NT, smem_total, d->stream>>>(dP);
+    else stage_mask_kernel<false><<<grid, NT, smem_total, d->stream>>>(dP);
     CU(cudaGetLastError());
     mask_count_kernel<<<nb, CMP_NT, 0, d->stream>>>(P.keep_words, P.exc_words, n_words, part);
     mask_scan_kernel<<<1, CMP_NT, 0, d->stream>>>(part, nb, totals);

@@ -450,9 +450,56 @@ class StageCompiler:
         self.guard = None
         regs = [self.reg(v) for v in used_vals]
         self._dce(regs)
-        self._fuse(regs)
+        self._fuse(regs)   # idioms first: they are recognised in the guarded form the if-conversion emits
+        self._cse(regs)
+        self._dce(regs)
+        if getattr(self, "_want_scan_hint", False):
+            self.prog.fused = _match_string_scan(self)  # closed form of a pure filter chain (None when it is not one)
         slots = self._regalloc(regs)
         return slots
+
+    def _cse(self, live_out: List[int]):
+        """Common-subexpression elimination on the single-assignment vreg program (what LLVM's GVN does for the reference,
+        LLVMOptimizer.cc:119-191). If-conversion of early returns recomputes the same path conditions (`not done`, `a and not done`)
+        for every statement; two passes:
+          1. a cheap, non-raising instruction whose operands are defined for every row loses its guard (its result is then defined
+             for every row too; rows outside the guard never look at it);
+          2. identical unguarded pure instructions share one result."""
+        ins = self.prog.instrs
+        OP = lambda k: C["TPLX_OP_" + k]
+        ndef: Dict[int, int] = {}
+        for i in ins:
+            if i.dst != NOSLOT:
+                ndef[i.dst] = ndef.get(i.dst, 0) + 1
+        cheap = {OP(k) for k in ("BNOT", "BAND", "BOR", "ICMP", "FCMP", "IADD", "ISUB", "IMUL", "INEG", "IAND", "IOR", "IXOR", "IABS", "FADD", "FSUB",
+                                 "FMUL", "FNEG", "FABS", "I2F", "SEL", "SLEN", "SLOWER", "SUPPER", "STRUTH", "SSLICE", "SEQ", "LDI", "LDS")}
+        pure = cheap | {OP(k) for k in ("SFIND", "SRFIND", "SIN", "SSTARTS", "SENDS", "SSTRIP", "ISHL", "ISHR", "F2I", "SFINDE", "SRFINDK", "LDROW")}
+        everywhere = set()  # vregs that hold a defined value for every row
+        for i in ins:
+            ops = [r for r in (i.a, i.b, i.c) if r != NOSLOT]
+            single = i.dst != NOSLOT and ndef.get(i.dst, 0) == 1
+            if i.guard != NOSLOT and single and i.op in cheap and i.guard in everywhere and all(r in everywhere for r in ops):
+                i.guard = NOSLOT
+            if i.guard == NOSLOT and single and all(r in everywhere for r in ops):
+                everywhere.add(i.dst)
+        seen: Dict[tuple, int] = {}
+        repl: Dict[int, int] = {}
+        out = []
+        keep = set(live_out)
+        for i in ins:
+            for f in ("a", "b", "c", "guard"):
+                v = getattr(i, f)
+                if v in repl:
+                    setattr(i, f, repl[v])
+            if (i.guard == NOSLOT and i.dst != NOSLOT and ndef.get(i.dst, 0) == 1 and i.op in pure and i.dst not in keep
+                    and all(r == NOSLOT or ndef.get(r, 0) == 1 for r in (i.a, i.b, i.c))):
+                key = (i.op, i.flags, i.a, i.b, i.c, i.imm, i.imm2, self.vreg_width[i.dst])
+                if key in seen:
+                    repl[i.dst] = seen[key]
+                    continue
+                seen[key] = i.dst
+            out.append(i)
+        self.prog.instrs[:] = out
 
     def _fuse(self, live_out: List[int]):
         """Peephole fusion on the (single-assignment) vreg program: two idioms that every 'split at a marker' UDF
@@ -540,8 +587,9 @@ class StageCompiler:
         keep.reverse()
         self.prog.instrs[:] = keep
 
-    def finish_memory(self, prefilter: bool = True) -> Program:
+    def finish_memory(self, prefilter: bool = True, scan_hint: bool = False) -> Program:
         self.prog.endpoint = C["TPLX_EP_MEMORY"]
+        self._want_scan_hint = scan_hint
         n_user = len(self.row)
         k = self._choose_split() if prefilter else 0
         if k:
@@ -555,7 +603,7 @@ class StageCompiler:
             d = pre.new_vreg(T_I64)
             pre.emit(C["TPLX_OP_LDROW"], d)
             pre.row, pre.names = [Val(T_I64, d)], ["__row"]
-            self.prog.prefilter = pre.finish_memory(prefilter=False)
+            self.prog.prefilter = pre.finish_memory(prefilter=False, scan_hint=True)
             self.begin_op(self.oplog[-1][1][-1] if self.oplog else 0)
             d = self.new_vreg(T_I64)
             self.emit(C["TPLX_OP_LDROW"], d)
@@ -743,6 +791,78 @@ class StageCompiler:
         return [assign[r] for r in live_out]
 
 
+def _match_string_scan(sc: "StageCompiler") -> Optional[bytes]:
+    """Recognise a row-index stage (the prefilter of a selective pipeline) that is nothing but a chain of filters of the closed
+    forms of include/tplx_ir.h (tplx_scan_term: CONTAINS / FIELD_INT / FIXED) and state it as a string-scan hint. Works on the
+    vreg program after dead-code elimination and idiom fusion; every instruction has to be explained by a term, otherwise None."""
+    OP = lambda k: C["TPLX_OP_" + k]
+    AC, BC, CC = C["TPLX_F_A_CONST"], C["TPLX_F_B_CONST"], C["TPLX_F_C_CONST"]
+    sym: Dict[int, tuple] = {}
+    terms: List[dict] = []
+    ins = sc.prog.instrs
+    mirror = {C["TPLX_CMP_LT"]: C["TPLX_CMP_GT"], C["TPLX_CMP_GT"]: C["TPLX_CMP_LT"], C["TPLX_CMP_LE"]: C["TPLX_CMP_GE"],
+              C["TPLX_CMP_GE"]: C["TPLX_CMP_LE"], C["TPLX_CMP_EQ"]: C["TPLX_CMP_EQ"], C["TPLX_CMP_NE"]: C["TPLX_CMP_NE"]}
+    for pc, i in enumerate(ins):
+        if i.guard != NOSLOT:
+            return None
+        a, b, c_ = sym.get(i.a), sym.get(i.b), sym.get(i.c)
+        fl = i.flags
+        if i.op == OP("LDCOL"):
+            sym[i.dst] = ("col", int(i.imm), i.flags, 0)
+        elif i.op in (OP("SLOWER"), OP("SUPPER")) and a and a[0] == "col" and a[2] == T_STR and a[3] == 0 and not (fl & AC):
+            sym[i.dst] = ("col", a[1], T_STR, C["TPLX_SF_LOWER"] if i.op == OP("SLOWER") else C["TPLX_SF_UPPER"])
+        elif i.op == OP("SFINDE") and a and a[0] == "col" and a[2] == T_STR and a[3] == 0 and (fl & BC) and not (fl & AC):
+            sym[i.dst] = ("finde", a[1], int(i.imm))
+        elif (i.op == OP("SSLICE") and a and a[0] == "col" and a[2] == T_STR and a[3] == 0 and (fl & 3) == C["TPLX_SL_HAS_END"]
+              and not (fl & (AC | BC | CC)) and c_ and c_[0] == "finde" and c_[1] == a[1]):
+            sym[i.dst] = ("head", a[1], c_[2])
+        elif i.op == OP("SRFINDK") and a and a[0] == "head" and (fl & BC):
+            sym[i.dst] = ("rfk", a[1], a[2], int(i.imm), int(i.imm2))
+        elif (i.op == OP("SSLICE") and a and a[0] == "head" and (fl & 3) == C["TPLX_SL_HAS_START"] and not (fl & (AC | BC | CC))
+              and b and b[0] == "rfk" and b[1:3] == a[1:3]):
+            sym[i.dst] = ("field", a[1], a[2], b[3], b[4])
+        elif i.op == OP("S2I") and a and a[0] == "field" and not (fl & AC):
+            sym[i.dst] = ("fieldint",) + a[1:] + (i.opidx,)
+        elif i.op == OP("ICMP") and (fl & (AC | BC)) in (AC, BC):
+            v = b if (fl & AC) else a
+            k = int(i.imm2 if (fl & AC) else i.imm)
+            cmp_ = mirror[fl & 7] if (fl & AC) else (fl & 7)
+            if v and v[0] == "fieldint":
+                sym[i.dst] = ("pred", dict(kind=C["TPLX_SK_FIELD_INT"], col=v[1], flags=0, cmp=cmp_, imm=k, needle=v[2], sep=v[3], skip=v[4],
+                                           opidx_val=v[5]))
+            elif v and v[0] == "col" and v[2] in (T_I64, T_BOOL):
+                sym[i.dst] = ("pred", dict(kind=C["TPLX_SK_FIXED"], col=v[1], flags=0, cmp=cmp_, imm=k))
+            else:
+                return None
+        elif i.op == OP("FCMP") and (fl & (AC | BC)) in (AC, BC):
+            v = b if (fl & AC) else a
+            k = int(i.imm2 if (fl & AC) else i.imm)
+            if not (v and v[0] == "col" and v[2] == T_F64):
+                return None
+            sym[i.dst] = ("pred", dict(kind=C["TPLX_SK_FIXED"], col=v[1], flags=C["TPLX_SCF_F64"], cmp=mirror[fl & 7] if (fl & AC) else (fl & 7), imm=k))
+        elif i.op == OP("SIN") and (fl & AC) and not (fl & BC) and b and b[0] == "col" and b[2] == T_STR:
+            sym[i.dst] = ("pred", dict(kind=C["TPLX_SK_CONTAINS"], col=b[1], flags=b[3], needle=int(i.imm2)))
+        elif i.op == OP("BNOT") and a and a[0] == "pred" and a[1]["kind"] == C["TPLX_SK_CONTAINS"] and not (fl & AC):
+            t = dict(a[1])
+            t["flags"] ^= C["TPLX_SCF_NEGATE"]
+            sym[i.dst] = ("pred", t)
+        elif i.op == OP("FILTER") and a and a[0] == "pred":
+            t = dict(a[1])
+            t["opidx_filter"] = i.opidx
+            terms.append(t)
+        elif i.op == OP("LDROW") and pc == len(ins) - 1:
+            pass
+        else:
+            return None
+    if not terms or len(terms) > C["TPLX_MAX_SCAN_TERMS"]:
+        return None
+    # every value that can raise must feed a filter: an int() whose result nobody tests would be lost by the closed form
+    n_field = sum(1 for i in ins if i.op == OP("S2I"))
+    if n_field != sum(1 for t in terms if t["kind"] == C["TPLX_SK_FIELD_INT"]):
+        return None
+    return ir.pack_scan_terms(terms)
+
+
 def _match_fused_scan_aggregate(sc: "StageCompiler", agg_func, combine_func, init) -> Optional[bytes]:
     """Recognise the closed form `filters of (column <op> constant) ranges -> sum of const | col | col*col`
     (include/tplx_ir.h tplx_fused_header). Returns the serialized hint or None. Works on a scratch compiler so the
@@ -925,7 +1045,9 @@ class _FuncCompiler:
     def _set_guard(self):
         g = self.path
         if not (self.sc.is_const(self.ret_done) and not self.ret_done.const):
-            g = self.sc.b_and(g, self.sc.b_not(self.ret_done)) if g is not None else self.sc.b_not(self.ret_done)
+            # the guard of the next statement is a value every row must have: computed outside any guard (an instruction that is
+            # skipped leaves its destination undefined, and an undefined guard would let rows run or skip the statement at random)
+            g = self._with_unguarded(lambda: self.sc.b_and(g, self.sc.b_not(self.ret_done)) if g is not None else self.sc.b_not(self.ret_done))
         if g is None:
             self.sc.guard = None
         elif self.sc.is_const(g):

@@ -143,6 +143,30 @@ def bits_f64(b: int) -> float:
     return struct.unpack("<d", struct.pack("<Q", b & ((1 << 64) - 1)))[0]
 
 
+SCAN_HDR_FMT = "<IIQ"              # tplx_scan_header
+SCAN_TERM_FMT = "<IIIIqQQqIIQ"      # tplx_scan_term (64 bytes)
+assert struct.calcsize(SCAN_TERM_FMT) == 64 and struct.calcsize(SCAN_HDR_FMT) == 16
+
+
+def scan_terms(blob: Optional[bytes]) -> Optional[List[dict]]:
+    """Decode a string-scan hint (tplx_scan_header + terms); None when blob is not one."""
+    if not blob or len(blob) < 16:
+        return None
+    magic, n, _ = struct.unpack_from(SCAN_HDR_FMT, blob, 0)
+    if magic != C["TPLX_SCAN_MAGIC"]:
+        return None
+    keys = ("kind", "col", "flags", "cmp", "imm", "needle", "sep", "skip", "opidx_val", "opidx_filter", "pad")
+    return [dict(zip(keys, struct.unpack_from(SCAN_TERM_FMT, blob, 16 + 64 * i))) for i in range(n)]
+
+
+def pack_scan_terms(terms: List[dict]) -> bytes:
+    out = struct.pack(SCAN_HDR_FMT, C["TPLX_SCAN_MAGIC"], len(terms), 0)
+    for t in terms:
+        out += struct.pack(SCAN_TERM_FMT, t["kind"], t["col"], t["flags"], t.get("cmp", 0), _as_i64(t.get("imm", 0)), t.get("needle", 0),
+                           t.get("sep", 0), _as_i64(t.get("skip", 0)), t.get("opidx_val", 0), t.get("opidx_filter", 0), 0)
+    return out
+
+
 def referenced_inputs(prog: Program) -> List[int]:
     """Input columns a stage actually loads (projection pushdown: the reference keeps only these when it reads a
     file, LogicalOptimizer projection pushdown / `columnsToSerialize`, StageBuilder.cc:1045-1070)."""
@@ -151,7 +175,7 @@ def referenced_inputs(prog: Program) -> List[int]:
     while p is not None:
         used.update(int(i.imm) for i in p.instrs if i.op == C["TPLX_OP_LDCOL"])
         p = p.prefilter
-    if prog.fused:
+    if prog.fused and scan_terms(prog.fused) is None:
         _, n_preds, n_terms, _ = struct.unpack_from("<IIII", prog.fused, 0)
         off = 16
         for _ in range(n_preds):
@@ -177,8 +201,13 @@ def project_inputs(prog: Program, used: List[int]) -> None:
                 i.imm = remap[int(i.imm)]
         p.in_types = [p.in_types[c] for c in used]
         p.in_names = [p.in_names[c] for c in used] if p.in_names else p.in_names
+        terms = scan_terms(p.fused)
+        if terms is not None:  # string-scan hint of a (prefilter) row stage: its terms name input columns too
+            for t in terms:
+                t["col"] = remap[t["col"]]
+            p.fused = pack_scan_terms(terms)
         p = p.prefilter
-    if prog.fused:
+    if prog.fused and scan_terms(prog.fused) is None:
         b = bytearray(prog.fused)
         _, n_preds, n_terms, _ = struct.unpack_from("<IIII", b, 0)
         off = 16
