@@ -8,7 +8,7 @@ from tuplex_b200.ir import T_F64, T_I64, T_STR
 FACTS = ["3 bds , 2 ba , 1,560 sqft", "", "bd", " bd", "x bd, y bd", "1 bd", ",", ", ", "a, 12 bd, b", "12", "no marker here", "7 ba , 9 bd",
          "Studio , 1 ba , 500 sqft", "-- , 2 bds", "4 bds , -- ba", ",,,, 5 bd", "11 bds , 3.5 ba", " ", "9", "a,b", ", 10 bds", "  8 bd", ", -3 bd"]
 TITLES = ["House For Sale", "HOUSE", "house", "Condo for rent", "Apartment", "townhouse sold", "", "hous", "ouse", "Lot/Land", "New HoUsE!",
-          "Foreclosed home", "houSe boat", "x" * 37 + "house", "ho" * 9]
+          "Foreclosed home", "houSe boat", "x" * 19 + "house", "ho" * 9]
 
 
 def make_columns(n, seed):

@@ -365,7 +365,7 @@ def test_mask_stage_ragged_sizes_and_modes(gpu, n, monkeypatch):
     cols, _ = U.make_columns(n, n)
     prog = _idiom_prog(U.number_before_marker, True)
     ora = pyoracle.run_program(prog, cols, n, 11)
-    for env in ({}, {"TPLX_MASK_STAGE": "0"}, {"TPLX_MASK_MR": "2"}, {"TPLX_NO_MASK": "1"}):
+    for env in ({}, {"TPLX_MASK_STAGE": "1"}, {"TPLX_MASK_STAGE": "1", "TPLX_MASK_MR": "2"}, {"TPLX_MASK_MR": "2"}, {"TPLX_NO_MASK": "1"}):
         for k in ("TPLX_MASK_STAGE", "TPLX_MASK_MR", "TPLX_NO_MASK"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
@@ -374,7 +374,14 @@ def test_mask_stage_ragged_sizes_and_modes(gpu, n, monkeypatch):
         assert_result_equals_oracle(res, ora, f"n={n} env={env}")
 
 
-def test_mask_stage_oversized_rows_fall_back_to_global(gpu):
+def test_mask_stage_oversized_rows_fall_back_to_global(gpu, monkeypatch):
+    monkeypatch.setenv("TPLX_MASK_STAGE", "1")
+    _oversized_rows_check()
+    monkeypatch.setenv("TPLX_MASK_STAGE", "0")
+    _oversized_rows_check()
+
+
+def _oversized_rows_check():
     """Tiles whose string bytes exceed the ring slot keep their global pointers: rare very long strings between short ones."""
     rng = np.random.default_rng(5)
     n = 30_000
@@ -460,7 +467,7 @@ def test_string_scan_closed_form_equals_vm_and_oracle(gpu, name, n, monkeypatch)
     assert prog.prefilter is not None and ir.scan_terms(prog.prefilter.fused) is not None
     cols = U.make_columns(n, n)
     ora = pyoracle.run_program(prog, cols, n, 4)
-    for env in ({}, {"TPLX_NO_SCAN": "1"}, {"TPLX_MASK_STAGE": "0"}, {"TPLX_NO_MASK": "1"}):
+    for env in ({}, {"TPLX_NO_SCAN": "1"}, {"TPLX_MASK_STAGE": "1"}, {"TPLX_NO_SCAN": "1", "TPLX_MASK_STAGE": "1"}, {"TPLX_NO_MASK": "1"}):
         for k in ("TPLX_NO_SCAN", "TPLX_MASK_STAGE", "TPLX_NO_MASK"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():

@@ -45,6 +45,8 @@ struct KParams {
     uint32_t n_instr, pad_split, n_slots, n_in, n_out, n_str_out, n_accs, R, n_tiles, scratch_per_thread;
     uint32_t K;            // scan vector width = 2 + n_str_out
     uint32_t smem_regs_off, smem_stage_off, smem_misc_off, smem_cols_off;
+    uint32_t smem_stash_off;  // per string output column: NT byte offsets (one per thread) + NT/32 warp totals
+    uint32_t inplace;         // 1: one row per thread and no staging area — outputs are read from the register file (slot s of local row lr = regs[s][lr])
     uint64_t cap_rows, cap_exc;
     const DInstr *prog;    // pre-decoded program (device format)
     const uint8_t *cpool;
@@ -124,14 +126,30 @@ __device__ __forceinline__ bool bit_test(const uint32_t *bits, uint32_t lr) {
 // K-vector, stable compacted write of the staged outputs, exception records. On entry keep_bits / exc_bits / exc_stage and the
 // staged output values (s_stage + out[c].stage_off, indexed by local row) are complete and a __syncthreads() has been passed.
 struct TileSmem {
-    uint8_t *s_stage, *s_regs;
+    uint8_t *s_stage, *s_regs;  // staging area (or the register file base when P.inplace), this thread's register column
+    uint32_t *s_stash;          // [n_str_out][NT] byte offsets, then [n_str_out][NT/32] warp totals
     uint32_t *keep_bits, *exc_bits, *keep_pre, *exc_pre, *exc_stage;
     uint64_t *s_vals, *s_excl, *s_warp;
 };
 __device__ __forceinline__ void rows_tile_finish(const KParams &P, const TileSmem &S, uint32_t tile, uint64_t base, uint32_t R, uint32_t T,
                                                  uint32_t W, uint32_t K, uint32_t state_stride) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint8_t *s_stage = S.s_stage, *s_regs = S.s_regs;
+    uint8_t *s_stage = S.s_stage;
+    uint32_t *s_stash = S.s_stash, *s_wtot = S.s_stash + P.n_str_out * NT;
+    // staged value of output column oc at local row lr: either the staging area ([lr] / [2 lr], [2 lr + 1]) or, in place, the register
+    // file itself (slot-major: regs[slot][lr])
+    auto fixed_at = [&](const OutCol &oc, uint32_t lr) -> uint64_t {
+        return P.inplace ? reinterpret_cast<const uint64_t *>(s_stage + (size_t)oc.slot * (NT * 8))[lr]
+                         : reinterpret_cast<const uint64_t *>(s_stage + oc.stage_off)[lr];
+    };
+    auto str_ptr_at = [&](const OutCol &oc, uint32_t lr) -> uint64_t {
+        return P.inplace ? reinterpret_cast<const uint64_t *>(s_stage + (size_t)oc.slot * (NT * 8))[lr]
+                         : reinterpret_cast<const uint64_t *>(s_stage + oc.stage_off)[2 * (size_t)lr];
+    };
+    auto str_meta_at = [&](const OutCol &oc, uint32_t lr) -> uint64_t {
+        return P.inplace ? reinterpret_cast<const uint64_t *>(s_stage + (size_t)(oc.slot + 1) * (NT * 8))[lr]
+                         : reinterpret_cast<const uint64_t *>(s_stage + oc.stage_off)[2 * (size_t)lr + 1];
+    };
     uint32_t *keep_bits = S.keep_bits, *exc_bits = S.exc_bits, *keep_pre = S.keep_pre, *exc_pre = S.exc_pre, *exc_stage = S.exc_stage;
     uint64_t *s_vals = S.s_vals, *s_excl = S.s_excl, *s_warp = S.s_warp;
     // ---- per-tile counts: word prefixes (warp 0), string byte totals ----------------------
@@ -160,36 +178,39 @@ __device__ __forceinline__ void rows_tile_finish(const KParams &P, const TileSme
     __syncthreads();
     const bool any_keep = s_vals[0] != 0;
     if (!any_keep && tid < MAX_SCAN - 2) s_vals[2 + tid] = 0;
-    // string bytes per output column: thread owns local rows [tid*R, tid*R+R)
-    // (consecutive rows per thread so that one block scan yields in-order byte offsets)
-    for (uint32_t c = 0; any_keep && c < P.n_out; ++c) {
-        const OutCol &oc = P.out[c];
-        if (oc.strk < 0) continue;
-        const uint64_t *st = reinterpret_cast<const uint64_t *>(s_stage + oc.stage_off);
-        uint32_t mine = 0;
-        for (uint32_t j = 0; j < R; ++j) {
-            uint32_t lr = tid * R + j;
-            if (bit_test(keep_bits, lr)) mine += (uint32_t)st[2 * (size_t)lr + 1];
-        }
-        uint32_t inc = mine;
+    // string bytes per output column: thread owns local rows [tid*R, tid*R+R) (consecutive rows per thread, so that one block scan
+    // yields in-order byte offsets). All columns are scanned between ONE pair of barriers: warp scans first, warp totals next.
+    if (any_keep) {
+        for (uint32_t c = 0; c < P.n_out; ++c) {
+            const OutCol &oc = P.out[c];
+            if (oc.strk < 0) continue;
+            uint32_t mine = 0;
+            for (uint32_t j = 0; j < R; ++j) {
+                const uint32_t lr = tid * R + j;
+                if (bit_test(keep_bits, lr)) mine += (uint32_t)str_meta_at(oc, lr);
+            }
+            uint32_t inc = mine;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t a = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-            if (lane >= (uint32_t)o) inc += a;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                if (lane >= (uint32_t)o) inc += a;
+            }
+            s_stash[(uint32_t)oc.strk * NT + tid] = inc - mine;  // exclusive inside the warp
+            if (lane == 31) s_wtot[(uint32_t)oc.strk * (NT / 32) + warp] = inc;
         }
-        __syncthreads();  // s_warp reuse
-        if (lane == 31) s_warp[warp] = inc;
         __syncthreads();
-        uint32_t wofs = 0, tot = 0;
-        for (uint32_t w = 0; w < NT / 32; ++w) {
-            uint32_t v = (uint32_t)s_warp[w];
-            if (w < warp) wofs += v;
-            tot += v;
+        for (uint32_t c = 0; c < P.n_out; ++c) {
+            const OutCol &oc = P.out[c];
+            if (oc.strk < 0) continue;
+            uint32_t wofs = 0, tot = 0;
+            for (uint32_t w = 0; w < NT / 32; ++w) {
+                const uint32_t v = s_wtot[(uint32_t)oc.strk * (NT / 32) + w];
+                if (w < warp) wofs += v;
+                tot += v;
+            }
+            s_stash[(uint32_t)oc.strk * NT + tid] += wofs;  // this thread's exclusive byte offset inside the tile
+            if (tid == 0) s_vals[2 + oc.strk] = tot;
         }
-        // stash this thread's exclusive byte offset in the (now free) register file slot area:
-        // regs are dead after evaluation, reuse slot 0..n_str_out-1 of this thread
-        VM<NT>::R(s_regs, (uint32_t)oc.strk * VM<NT>::SLOT_BYTES) = (uint64_t)(wofs + inc - mine);
-        if (tid == 0) s_vals[2 + oc.strk] = tot;
     }
     __syncthreads();
 
@@ -247,11 +268,9 @@ __device__ __forceinline__ void rows_tile_finish(const KParams &P, const TileSme
         for (uint32_t c = 0; c < P.n_out; ++c) {
             const OutCol &oc = P.out[c];
             if (oc.strk < 0) {
-                const uint64_t *st = reinterpret_cast<const uint64_t *>(s_stage + oc.stage_off);
                 for (uint32_t lr = tid; lr < T; lr += NT)
-                    if (bit_test(keep_bits, lr)) oc.data[pre_keep + bit_rank(keep_bits, keep_pre, lr)] = st[lr];
+                    if (bit_test(keep_bits, lr)) oc.data[pre_keep + bit_rank(keep_bits, keep_pre, lr)] = fixed_at(oc, lr);
             } else {
-                const uint64_t *st = reinterpret_cast<const uint64_t *>(s_stage + oc.stage_off);
                 const uint64_t pre_b = s_excl[2 + oc.strk];
                 const uint64_t tile_b = s_vals[2 + oc.strk];
                 const bool fit = pre_b + tile_b <= oc.cap_bytes && pre_b + tile_b <= 0xFFFFFFFFull;
@@ -259,13 +278,13 @@ __device__ __forceinline__ void rows_tile_finish(const KParams &P, const TileSme
                     if (tid == 0) atomicOr(&P.counters[1], 2u);
                     continue;
                 }
-                uint64_t off = pre_b + VM<NT>::R(s_regs, (uint32_t)oc.strk * VM<NT>::SLOT_BYTES);
+                uint64_t off = pre_b + s_stash[(uint32_t)oc.strk * NT + tid];
                 for (uint32_t j = 0; j < R; ++j) {
                     const uint32_t lr = tid * R + j;
                     if (!bit_test(keep_bits, lr)) continue;
                     StrV sv;
-                    sv.p = reinterpret_cast<const uint8_t *>(st[2 * (size_t)lr]);
-                    const uint64_t m = st[2 * (size_t)lr + 1];
+                    sv.p = reinterpret_cast<const uint8_t *>(str_ptr_at(oc, lr));
+                    const uint64_t m = str_meta_at(oc, lr);
                     sv.len = (uint32_t)m;
                     sv.flags = (uint32_t)(m >> 32);
                     oc.offsets[pre_keep + bit_rank(keep_bits, keep_pre, lr)] = (uint32_t)off;
@@ -312,7 +331,8 @@ __global__ void __launch_bounds__(NT) stage_rows_kernel(const KParams *__restric
     DInstr *s_prog = reinterpret_cast<DInstr *>(smem);
     ColIn *s_cols = reinterpret_cast<ColIn *>(smem + P.smem_cols_off);
     uint8_t *s_regs = smem + P.smem_regs_off + tid * 8;  // this thread's register column
-    uint8_t *s_stage = smem + P.smem_stage_off;
+    uint8_t *s_stage = P.inplace ? smem + P.smem_regs_off : smem + P.smem_stage_off;
+    uint32_t *s_stash = reinterpret_cast<uint32_t *>(smem + P.smem_stash_off);
     uint32_t *keep_bits = reinterpret_cast<uint32_t *>(smem + P.smem_misc_off);
     uint32_t *exc_bits = keep_bits + W;
     uint32_t *keep_pre = exc_bits + W;
@@ -374,7 +394,7 @@ __global__ void __launch_bounds__(NT) stage_rows_kernel(const KParams *__restric
             const uint32_t kb = __ballot_sync(0xFFFFFFFFu, t.alive);
             const uint32_t eb = __ballot_sync(0xFFFFFFFFu, exc);
             if (lane == 0) { keep_bits[lr >> 5] = kb; exc_bits[lr >> 5] = eb; }
-            if (t.alive) stage_row(lr);
+            if (t.alive && !P.inplace) stage_row(lr);
             if (exc) {
                 exc_stage[lr] = t.exc_code | (t.exc_op << 16);
 
@@ -382,8 +402,8 @@ __global__ void __launch_bounds__(NT) stage_rows_kernel(const KParams *__restric
         }
         __syncthreads();
 
-        rows_tile_finish(P, TileSmem{s_stage, s_regs, keep_bits, exc_bits, keep_pre, exc_pre, exc_stage, s_vals, s_excl, s_warp}, tile, base, R, T,
-                         W, K, state_stride);
+        rows_tile_finish(P, TileSmem{s_stage, s_regs, s_stash, keep_bits, exc_bits, keep_pre, exc_pre, exc_stage, s_vals, s_excl, s_warp}, tile, base,
+                         R, T, W, K, state_stride);
     }
 }
 

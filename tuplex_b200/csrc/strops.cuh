@@ -150,35 +150,57 @@ TPLX_HD bool match_at(const StrV &h, uint32_t pos, const StrV &n, uint32_t from)
     return true;
 }
 
-// strstr semantics: first occurrence or -1; empty needle -> 0.
-// SWAR filter on the first (and, when present, second) needle character, 4 haystack positions per step.
-// The haystack is streamed through three rolling aligned words (one new aligned load per step); the case flag is
-// a template parameter so the loop body carries no per-word flag tests.
+// 0x80 in every byte lane where BOTH x0 and x1 are zero (x0, x1 = word ^ splat(char)): one zero-byte test for a 2-character filter
+TPLX_HD uint32_t both_zero4(uint32_t x0, uint32_t x1) {
+    const uint32_t x = x0 | x1;
+    const uint32_t t = ((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x;
+    return ~t & 0x80808080u;
+}
+template <uint32_t HFLAGS>
+TPLX_HD uint32_t case4_t(uint32_t w) {
+    return HFLAGS == TPLX_SF_LOWER ? lower4(w) : (HFLAGS == TPLX_SF_UPPER ? upper4(w) : w);
+}
+template <uint32_t HFLAGS>
+TPLX_HD uint8_t sch_t(const uint8_t *p, uint32_t i) {
+    uint8_t c = p[i];
+    if (HFLAGS == TPLX_SF_LOWER) c += ((uint8_t)(c - 'A') < 26u) ? 32 : 0;
+    if (HFLAGS == TPLX_SF_UPPER) c -= ((uint8_t)(c - 'a') < 26u) ? 32 : 0;
+    return c;
+}
+
+// strstr semantics: first occurrence or -1 (callers handle the empty needle and needle longer than haystack).
+// SWAR filter on the first (and, when present, second) needle character, 4 haystack positions per step. One aligned load per step:
+// string word k (characters 4k..4k+3) = funnel(aw[k], aw[k+1]); the character after it — needed for the 2-character test of position
+// 4k+3 — is the byte at the string's phase inside aw[k+1], so no third word is touched. Steps whose four positions are all admissible run
+// without masking; the last, partial step masks once. The case flag is a template parameter (no per-word flag tests).
 template <uint32_t HFLAGS>
 TPLX_HD int64_t str_find_impl(const StrV &h, const StrV &n) {
     const uint32_t last = h.len - n.len;  // last admissible start
-    const uint32_t c0 = sch(n, 0);
+    const uint32_t c0 = sch(n, 0) * 0x01010101u;
     const bool two = n.len >= 2;
-    const uint32_t c1 = two ? sch(n, 1) : 0;
+    const uint32_t c1 = (two ? sch(n, 1) : 0) * 0x01010101u;
     const uintptr_t addr = (uintptr_t)h.p;
     const uint32_t *aw = (const uint32_t *)(addr & ~(uintptr_t)3);
     const uint32_t sh = (uint32_t)(addr & 3) * 8;
     const uint32_t nwords = (uint32_t)(((addr & 3) + h.len + 3) >> 2);  // aligned words holding string bytes (>= 1)
+    const uint32_t kfull = (last + 1) >> 2;                             // steps k < kfull: positions 4k..4k+3 are all <= last
     uint32_t a0 = aw[0];
-    uint32_t a1 = nwords > 1 ? aw[1] : 0u;
-    uint32_t cur = funnel_r(a0, a1, sh);
-    if (HFLAGS == TPLX_SF_LOWER) cur = lower4(cur);
-    if (HFLAGS == TPLX_SF_UPPER) cur = upper4(cur);
-    for (uint32_t k = 0; 4 * k <= last; ++k) {
-        // string word k+1 (only its first character is ever needed, for the 2-character test of position 4k+3)
-        const uint32_t a2 = (k + 2 < nwords) ? aw[k + 2] : 0u;
-        uint32_t nxt = funnel_r(a1, a2, sh);
-        if (HFLAGS == TPLX_SF_LOWER) nxt = lower4(nxt);
-        if (HFLAGS == TPLX_SF_UPPER) nxt = upper4(nxt);
-        uint32_t m = eq_mask4(cur, c0);
-        if (two) m &= eq_mask4((cur >> 8) | (nxt << 24), c1);
-        const uint32_t valid = last - 4 * k;  // positions 0..valid of this word are admissible
-        if (valid < 3) m &= low_mask(valid + 1);
+    uint32_t k = 0;
+    for (;; ++k) {
+        const bool full = k < kfull;
+        if (!full && 4 * k > last) break;
+        // aw[k+1] holds string bytes whenever it is needed: for sh != 0 it completes string word k; for a 2-character needle it holds
+        // character 4k+4 <= last + 1 < h.len. (1-character needle with sh == 0: not needed, and it may lie outside the string.)
+        const uint32_t a1 = (k + 1 < nwords) ? aw[k + 1] : 0u;
+        const uint32_t cur = case4_t<HFLAGS>(funnel_r(a0, a1, sh));
+        uint32_t m;
+        if (two) {
+            const uint32_t nx = case4_t<HFLAGS>(a1 >> sh);  // low byte = character 4k+4
+            m = both_zero4(cur ^ c0, ((cur >> 8) | (nx << 24)) ^ c1);
+        } else {
+            m = eq_mask4(cur, c0 & 0xFFu);
+        }
+        if (!full) m &= low_mask(last - 4 * k + 1);  // positions 0..last-4k of this word are admissible
         while (m) {
 #ifdef __CUDA_ARCH__
             const uint32_t bit = __ffs(m) - 1;
@@ -186,11 +208,12 @@ TPLX_HD int64_t str_find_impl(const StrV &h, const StrV &n) {
             const uint32_t bit = (uint32_t)__builtin_ctz(m);
 #endif
             const uint32_t pos = 4 * k + (bit >> 3);
-            if (match_at(h, pos, n, two ? 2 : 1)) return (int64_t)pos;
+            bool ok = true;
+            for (uint32_t j = two ? 2 : 1; ok && j < n.len; ++j) ok = sch_t<HFLAGS>(h.p, pos + j) == sch(n, j);
+            if (ok) return (int64_t)pos;
             m &= m - 1;
         }
-        cur = nxt;
-        a1 = a2;
+        a0 = a1;
     }
     return -1;
 }

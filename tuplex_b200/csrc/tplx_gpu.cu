@@ -592,10 +592,14 @@ extern "C" int32_t tplx_gpu_result_free(tplx_result *r) {
 // shared-memory layout; must mirror stage_rows_kernel / stage_agg_kernel
 struct Layout {
     uint32_t cols_off, regs_off, stage_off, misc_off, total;
+    uint32_t stash_off = 0;
+    bool inplace = false;
     std::vector<uint32_t> col_stage_off;
 };
-static Layout make_layout(const tplx_stage *s, uint32_t R, bool rows_ep) {
+// inplace (rows endpoint, R == 1): no staging area, the write phase reads the outputs from the register file
+static Layout make_layout(const tplx_stage *s, uint32_t R, bool rows_ep, bool inplace = false) {
     Layout L;
+    L.inplace = inplace && rows_ep && R == 1;
     const uint32_t T = R * NT, W = T / 32;
     size_t off = align_up(std::max<size_t>(s->instrs.size(), 1) * sizeof(DInstr), 16);
     L.cols_off = (uint32_t)off;
@@ -608,11 +612,14 @@ static Layout make_layout(const tplx_stage *s, uint32_t R, bool rows_ep) {
         size_t so = 0;
         for (auto &oc : s->out_cols) {
             L.col_stage_off.push_back((uint32_t)so);
-            so += (size_t)T * (oc.type == TPLX_T_STR ? 16 : 8);
+            if (!L.inplace) so += (size_t)T * (oc.type == TPLX_T_STR ? 16 : 8);
         }
         off = align_up(off + so, 16);
         L.misc_off = (uint32_t)off;
         off += (size_t)(4 * W + 2 + T) * 4 + (size_t)(2 * MAX_SCAN + NT / 32 + 1) * 8 + 16;
+        off = align_up(off, 16);
+        L.stash_off = (uint32_t)off;
+        off += (size_t)s->n_str_out * (NT + NT / 32) * 4;
     } else {
         L.misc_off = (uint32_t)off;
         off += (size_t)(NT / 32) * std::max<size_t>(s->accs.size(), 1) * 8;
@@ -813,6 +820,8 @@ static int32_t fill_common(KParams &P, tplx_stage *s, StageDev *sd, const tplx_b
     P.smem_regs_off = L.regs_off;
     P.smem_stage_off = L.stage_off;
     P.smem_misc_off = L.misc_off;
+    P.smem_stash_off = L.stash_off;
+    P.inplace = L.inplace ? 1u : 0u;
     P.prog = sd->prog;
     P.cpool = sd->cpool;
     P.opids = sd->opids;
@@ -998,18 +1007,20 @@ static int32_t run_rows(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_
     const uint32_t env_R = getenv("TPLX_TILE_R") ? (uint32_t)atoi(getenv("TPLX_TILE_R")) : 0;
     uint32_t smem_budget = (uint32_t)(d->prop.sharedMemPerMultiprocessor / occ_regs) - 1024;
     uint32_t R = env_R ? env_R : 16;
+    const bool allow_inplace = !(getenv("TPLX_NO_INPLACE") && atoi(getenv("TPLX_NO_INPLACE")));
     Layout L = make_layout(s, R, true);
     while (R > 1 && L.total > smem_budget) {
         R /= 2;
-        L = make_layout(s, R, true);
+        L = make_layout(s, R, true, allow_inplace);  // one row per thread: no staging area, outputs are read from the register file
     }
-    if (L.total > smem_budget) {  // even one row per thread does not fit the budget: give up occupancy instead
+    if (L.total > smem_budget && !(L.inplace && L.total <= (uint32_t)d->smem_optin)) {
+        // even one row per thread does not fit the budget: give up occupancy instead
         smem_budget = (uint32_t)std::min<int>(d->smem_optin, 113 * 1024);
         R = env_R ? env_R : 4;
         L = make_layout(s, R, true);
         while (R > 1 && L.total > smem_budget) {
             R /= 2;
-            L = make_layout(s, R, true);
+            L = make_layout(s, R, true, allow_inplace);
         }
     }
     if (L.total > (uint32_t)d->smem_optin) return fail(TPLX_E_UNSUPPORTED, "stage needs more shared memory than one SM has");
@@ -1160,8 +1171,10 @@ static int32_t run_mask(tplx_stage *ps, StageDev *psd, const tplx_block *b, tplx
     P.prog = psd->prog;
     P.cpool = psd->cpool;
     for (size_t c = 0; c < b->cols.size(); ++c) P.in[c] = b->cols[c];
-    // string columns the program loads are staged through the warps' shared-memory rings (TPLX_MASK_STAGE=0: plain loads)
-    const bool want_stage = !(getenv("TPLX_MASK_STAGE") && atoi(getenv("TPLX_MASK_STAGE")) == 0);
+    // TPLX_MASK_STAGE=1: the string columns the program loads are staged through the warps' shared-memory rings (TMA bulk copies).
+    // Measured on B200 (profiles/r02_zillow.md): the kernel is issue-bound, not latency-bound — staging raises issue utilisation
+    // (62 % -> 71 %) but its per-tile bookkeeping adds 27 % instructions, so plain coalesced loads through L1 are the default.
+    const bool want_stage = getenv("TPLX_MASK_STAGE") && atoi(getenv("TPLX_MASK_STAGE")) != 0;
     std::vector<uint32_t> cand;
     for (uint32_t i = 0; i < ps->instrs.size() && want_stage; ++i) {
         const tplx_instr &in = ps->instrs[i];

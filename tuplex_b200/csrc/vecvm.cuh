@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(NT) stage_rows_vec_kernel(const KParams *__res
             }
         }
         __syncthreads();
-        rows_tile_finish(P, TileSmem{s_regs, nullptr, keep_bits, exc_bits, keep_pre, exc_pre, exc_stage, s_vals, s_excl, s_warp}, tile, base, 2 * J, T, W,
+        rows_tile_finish(P, TileSmem{s_regs, nullptr, nullptr, keep_bits, exc_bits, keep_pre, exc_pre, exc_stage, s_vals, s_excl, s_warp}, tile, base, 2 * J, T, W,
                          K, state_stride);
     }
 }

@@ -101,6 +101,7 @@ struct VM {
     // columns flagged compact (gather.cuh) are indexed by w.
     static __device__ void run(const DInstr *__restrict__ prog, uint32_t pc0, uint32_t pc1, uint8_t *__restrict__ rb,
                                const ColIn *__restrict__ cols, uint64_t row, uint64_t w, const uint8_t *__restrict__ cpool, VMThread &t) {
+        bool check_alive = false;
         for (uint32_t pc = pc0; pc < pc1; ++pc) {
             // uniform fetch (broadcast from shared memory)
             const uint4 w0 = *reinterpret_cast<const uint4 *>(&prog[pc]);
@@ -110,8 +111,14 @@ struct VM {
             const uint32_t opidx = w0.x >> 16;
             const uint32_t dst = w0.y, a = w0.z, b = w0.w, c = w1.x, guard = w1.y;
             bool act = t.alive;
-            if (guard != NOOFF) act = act && (R(rb, guard) != 0);
-            if (!__any_sync(0xFFFFFFFFu, act)) continue;  // whole warp idle for this op
+            if (guard != NOOFF) {
+                act = act && (R(rb, guard) != 0);
+                if (!__any_sync(0xFFFFFFFFu, act)) continue;  // untaken branch of an if-converted UDF: whole warp skips the op
+            } else if (check_alive) {
+                // the previous instruction was a FILTER: when it emptied the warp nothing that follows can execute
+                if (!__any_sync(0xFFFFFFFFu, act)) return;
+            }
+            check_alive = op == TPLX_OP_FILTER;  // warp-uniform
             if (!act) continue;
             const int64_t imm = prog[pc].imm;
             // operand fetch (constant operands come from the immediates: a <- imm2, b <- imm, c <- imm2)
