@@ -57,3 +57,100 @@ def test_cpp_gpu_backend_execute(gpu, tmp_path):
     bad.write_bytes(prog.serialize()[:-16])
     r2 = subprocess.run([exe, str(bad), "0,3", str(psize), prefix] + part_files, capture_output=True, text=True, timeout=120)
     assert r2.returncode == 1 and "stage descriptor" in r2.stderr
+
+
+def _decode_partition(part: bytes, types):
+    """rows of a reference-format partition (Partition.h:130-139 + Serializer.cc:1016-1117): int64 numRows, then per row one 8-byte slot
+    per field (var-len: offset from the slot | size << 32), the 8-byte var-len total when the schema has strings, the payload."""
+    import struct
+    n = struct.unpack_from("<q", part, 0)[0]
+    p = 8
+    has_var = any(t == T_STR for t in types)
+    rows = []
+    for _ in range(n):
+        vals = []
+        for f, t in enumerate(types):
+            slot = p + 8 * f
+            raw = struct.unpack_from("<Q", part, slot)[0]
+            if t == T_STR:
+                off, size = raw & 0xFFFFFFFF, raw >> 32
+                vals.append(part[slot + off: slot + off + size - 1].decode())
+            elif t == 1:
+                vals.append(struct.unpack_from("<d", part, slot)[0])
+            else:
+                vals.append(struct.unpack_from("<q", part, slot)[0])
+        p += 8 * len(types)
+        if has_var:
+            p += 8 + struct.unpack_from("<q", part, p)[0]
+        rows.append(tuple(vals))
+    return rows
+
+
+def _run_host(tmp_path, prog, cols, n, types, psize, devices=None):
+    in_parts = pyoracle.to_partitions(cols, n, psize)
+    desc = tmp_path / "stage.bin"
+    desc.write_bytes(prog.serialize())
+    files = []
+    for i, p in enumerate(in_parts):
+        f = tmp_path / f"in{i}.bin"
+        f.write_bytes(p)
+        files.append(str(f))
+    exe = os.path.join(ROOT, "tuplex_b200", "lib", "tplx_host_run")
+    prefix = str(tmp_path / ("res" + (devices or "").replace(",", "_")))
+    cmd = [exe, str(desc), ",".join(str(t) for t in types), str(psize), prefix] + (["--devices", devices] if devices else []) + files
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    return json.loads(r.stdout.strip().splitlines()[-1]), prefix, len(in_parts)
+
+
+def test_cpp_host_tasks_aggregate_and_hash(gpu, tmp_path):
+    """GpuBackend::execute beyond one memory task: several tasks (here on one GPU: --devices 0,0,0), exception row numbers stitched
+    across tasks, the resolve hook, the aggregate endpoint (Q6 on the reference's lineitem fixture -> gtest golden) and the hash
+    endpoint (AggregateTest.cc:249-364 goldens) — all through the C++ host over the C ABI."""
+    import struct
+    from tuplex_b200 import workloads, ir
+    # ---- memory endpoint, 3 tasks: rows and exception records equal the single-task oracle run
+    rng = np.random.default_rng(3)
+    n = 30_000
+    a = rng.integers(-20, 20, n, dtype=np.int64)
+    s = ["id%d,%d" % (v, v * v) for v in a]
+    cols = [Column(T_I64, a), Column.from_values(s, T_STR)]
+    sc = frontend.StageCompiler([T_I64, T_STR], ["a", "s"])
+    sc.add_with_column("q", lambda x: 1000 // x['a'], 100001)
+    sc.add_filter(lambda x: x['q'] % 3 != 1, 100002)
+    prog = sc.finish_memory()
+    psize = 64 << 10
+    info, prefix, n_in = _run_host(tmp_path, prog, cols, n, [T_I64, T_STR], psize, "0,0,0")
+    ora = pyoracle.run_program(prog, cols, n)
+    assert info["tasks"] == 3 and info["out_rows"] == ora.n_out and info["exceptions"] == len(ora.exceptions) > 0
+    assert info["exceptions_handed_to_resolve"] == info["exceptions"]
+    out_types = [T_I64, T_STR, T_I64]
+    got_rows = []
+    for i in range(info["out_partitions"]):
+        got_rows += _decode_partition(open(f"{prefix}.out{i}", "rb").read(), out_types)
+    want = list(zip(*[ora.values(c) for c in range(3)]))
+    assert got_rows == want
+    assert open(prefix + ".exc", "rb").read() == pyoracle.exception_partition(cols, ora.exceptions)
+    # ---- aggregate endpoint: Q6 over the reference's SF0.01 fixture
+    lcols = workloads.load_lineitem_fixture()
+    ln = len(lcols[0].data)
+    qp = workloads.q6_program()
+    info, prefix, _ = _run_host(tmp_path, qp, lcols, ln, [0, 1, 1, 0], 256 << 10)
+    (bits,) = struct.unpack("<q", open(prefix + ".agg", "rb").read())
+    assert info["endpoint"] == 1 and bits & ((1 << 64) - 1) == pyoracle.run_program(qp, lcols, ln).acc_tree[0]
+    assert abs(ir.bits_f64(bits) - 1193053.2252999984) <= 1e-4   # gtest golden (TPCH.cc:85-97)
+    info2, prefix2, n_parts = _run_host(tmp_path, qp, lcols, ln, [0, 1, 1, 0], 256 << 10, "0,0")
+    (bits2,) = struct.unpack("<q", open(prefix2 + ".agg", "rb").read())
+    assert info2["tasks"] == 2 and abs(ir.bits_f64(bits2) - 1193053.2252999984) <= 1e-4
+    # ---- hash endpoint: AggregateTest.cc goldens (scaled x2500), two tasks into one device table
+    base = [("abc", 1), ("abc", -2), ("xyz", 4), ("abc", -2), ("xyz", 3), ("xyz", 3)]   # sums: abc -3, xyz 10
+    rows = base * 2500
+    kcols = [Column.from_values([r[0] for r in rows], T_STR), Column(T_I64, np.array([r[1] for r in rows], dtype=np.int64))]
+    hs = frontend.StageCompiler([T_STR, T_I64], ["k", "v"])
+    hp = hs.finish_hash(["k"], lambda a, x: a + x[1], lambda a, b: a + b, 0, 100001)
+    for devs in (None, "0,0"):
+        info, prefix, _ = _run_host(tmp_path, hp, kcols, len(rows), [T_STR, T_I64], 16 << 10, devs)
+        got = []
+        for i in range(info["hash_partitions"]):
+            got += _decode_partition(open(f"{prefix}.hash{i}", "rb").read(), [T_STR, T_I64])
+        assert sorted(got) == [("abc", -7500), ("xyz", 25000)] and info["out_rows"] == 2 and info["endpoint"] == 2

@@ -177,3 +177,34 @@ def test_context_over_two_devices(gpu):
     byk = lambda c: c.parallelize(data, columns=["a", "b", "s"]).aggregateByKey(lambda x, y: x + y, lambda acc, r: acc + r["a"], 0, ["s"]).collect()
     assert sorted(byk(two)) == sorted(byk(one)) and len(byk(one)) == 100
     assert sorted(two.parallelize([r[2] for r in data]).unique().collect()) == sorted({r[2] for r in data})
+
+
+def test_cpp_host_two_devices(gpu, tmp_path):
+    """C++ GpuBackend over two GPUs (--devices 0,1): tasks on both devices, tplx_gpu_agg_finish / tplx_gpu_stage_hash_exchange through
+    the backend's NCCL communicator."""
+    import struct
+    import numpy as np
+    from tuplex_b200 import backend, frontend, ir, workloads
+    from tuplex_b200.backend import Column
+    from tuplex_b200.ir import T_I64, T_STR
+    from oracle import pyoracle
+    from test_gpu_cpp_host import _decode_partition, _run_host
+    if backend.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    lcols = workloads.load_lineitem_fixture()
+    ln = len(lcols[0].data)
+    qp = workloads.q6_program()
+    info, prefix, _ = _run_host(tmp_path, qp, lcols, ln, [0, 1, 1, 0], 256 << 10, "0,1")
+    (bits,) = struct.unpack("<q", open(prefix + ".agg", "rb").read())
+    assert info["tasks"] == 2 and abs(ir.bits_f64(bits) - 1193053.2252999984) <= 1e-4
+    rows = [("k%03d" % (i % 300), i % 7 - 3) for i in range(90_000)]
+    kcols = [Column.from_values([r[0] for r in rows], T_STR), Column(T_I64, np.array([r[1] for r in rows], dtype=np.int64))]
+    hp = frontend.StageCompiler([T_STR, T_I64], ["k", "v"]).finish_hash(["k"], lambda a, x: a + x[1], lambda a, b: a + b, 0, 100001)
+    info, prefix, _ = _run_host(tmp_path, hp, kcols, len(rows), [T_STR, T_I64], 64 << 10, "0,1")
+    got = []
+    for i in range(info["hash_partitions"]):
+        got += _decode_partition(open(f"{prefix}.hash{i}", "rb").read(), [T_STR, T_I64])
+    want = {}
+    for k, v in rows:
+        want[k] = want.get(k, 0) + v
+    assert dict(got) == want and len(got) == 300

@@ -3,9 +3,13 @@
 // partitions), files out (output partitions, exception partition). Plays the part of TransformStage::execute ->
 // backend()->execute(this) (tuplex/core/src/physical/TransformStage.cc:610-700).
 //
-//   tplx_host_run <descriptor.bin> <coltypes: e.g. 0,3,1> <partition_size> <out_prefix> <part0.bin> [part1.bin ...]
+//   tplx_host_run <descriptor.bin> <coltypes: e.g. 0,3,1> <partition_size> <out_prefix> [--devices 0,1] <part0.bin> [part1.bin ...]
+// --devices: one task per entry (the same device may repeat: several tasks on one GPU). Outputs: <prefix>.out<i> (memory endpoint),
+// <prefix>.exc, <prefix>.agg (aggregate endpoint: raw 8-byte values), <prefix>.hash<i> (hash endpoint: groups as rows).
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <mutex>
 #include <fstream>
 #include <iostream>
 #include <sstream>
@@ -34,13 +38,35 @@ int main(int argc, char **argv) {
         for (std::string tok; std::getline(ss, tok, ',');) st.inputColumnTypes.push_back((uint8_t)std::atoi(tok.c_str()));
         st.partitionSize = std::strtoull(argv[3], nullptr, 10);
         const std::string prefix = argv[4];
-        for (int i = 5; i < argc; ++i) st.inputPartitions.push_back(slurp(argv[i]));
-        tuplex_b200::GpuBackend backend({0});
+        std::vector<int32_t> devices{0};
+        int first = 5;
+        if (argc > 6 && std::string(argv[5]) == "--devices") {
+            devices.clear();
+            std::stringstream ds(argv[6]);
+            for (std::string tok; std::getline(ds, tok, ',');) devices.push_back(std::atoi(tok.c_str()));
+            first = 7;
+        }
+        for (int i = first; i < argc; ++i) st.inputPartitions.push_back(slurp(argv[i]));
+        tuplex_b200::GpuBackend backend(devices);
+        unsigned long long handed = 0;
+        std::mutex mu;
+        backend.setExceptionHandler([&](uint32_t, const std::vector<uint8_t> &part) {  // the resolve hook: count what a ResolveTask would get
+            long long n = 0;
+            std::memcpy(&n, part.data(), 8);
+            std::lock_guard<std::mutex> lk(mu);
+            handed += (unsigned long long)n;
+        });
         backend.execute(st);
         for (size_t p = 0; p < st.outputPartitions.size(); ++p) dump(prefix + ".out" + std::to_string(p), st.outputPartitions[p]);
+        for (size_t p = 0; p < st.hashPartitions.size(); ++p) dump(prefix + ".hash" + std::to_string(p), st.hashPartitions[p]);
         dump(prefix + ".exc", st.exceptionPartition);
-        std::printf("{\"out_rows\": %llu, \"exceptions\": %llu, \"out_partitions\": %zu, \"kernel_ms\": %.3f}\n",
-                    (unsigned long long)st.numOutputRows, (unsigned long long)st.numExceptionRows, st.outputPartitions.size(), st.kernelMs);
+        std::vector<uint8_t> agg(st.aggregate.size() * 8);
+        if (!agg.empty()) std::memcpy(agg.data(), st.aggregate.data(), agg.size());
+        dump(prefix + ".agg", agg);
+        std::printf("{\"out_rows\": %llu, \"exceptions\": %llu, \"out_partitions\": %zu, \"hash_partitions\": %zu, \"n_aggregate\": %zu, "
+                    "\"tasks\": %u, \"endpoint\": %u, \"exceptions_handed_to_resolve\": %llu, \"kernel_ms\": %.3f}\n",
+                    (unsigned long long)st.numOutputRows, (unsigned long long)st.numExceptionRows, st.outputPartitions.size(), st.hashPartitions.size(),
+                    st.aggregate.size(), st.tasks, (unsigned)st.endpoint(), handed, st.kernelMs);
     } catch (const std::exception &e) {
         std::fprintf(stderr, "error: %s\n", e.what());  // stage-level failure (LocalBackend throws std::runtime_error too)
         return 1;
