@@ -39,6 +39,7 @@ def parse_args():
                     help="the K-step timed region is repeated (each repeat bracketed by barrier + synchronize) until this much time has "
                          "been measured; the reported time is the median repeat")
     ap.add_argument("--no-pageable", action="store_true", help="skip the pageable-host-memory end-to-end variant")
+    ap.add_argument("--no-extras", action="store_true", help="default workload only: skip the brief c1 / aggregateByKey measurements")
     return ap.parse_args()
 
 
@@ -254,7 +255,7 @@ def build_workload(args):
                     desc=f"parallelize([1..{total}]).map(x*x).filter(x%2==0)")
     total = args.rows or 100_000_000
     nkeys = args.keys or max(1000, total // 100)
-    blocks = [(pin_cols(W.gen_keyed(total, nkeys, seed=42)), total)]
+    blocks = [(pin_cols(W.gen_keyed(total, nkeys, seed=42 + int(os.environ.get("RANK", "0")))), total)]  # every rank its own shard of rows
     return dict(name="aggbykey_str", prog=W.keyed_program(), blocks=blocks, rows=total, in_bytes=total * 20, keep=keep, nkeys=nkeys,
                 desc=f"aggregateByKey string key, {total} rows, {nkeys} distinct keys")
 
@@ -744,6 +745,18 @@ def main():
     hc = host_cores()
     keys = ["zillow", "q6"] if args.workload == "both" else [args.workload]
     parts = {k: measure(args, k, rank, world, local, dist, hc) for k in keys}
+    extras = {}
+    if args.workload == "both" and not args.no_extras:
+        # the other two configurations of BASELINE.json, measured briefly in the same run (device-resident value + roofline + e2e):
+        # config 0 (fixed-width map/filter through the vector kernel K1v) and one shard of config 5 (aggregateByKey, string keys;
+        # under torchrun every rank aggregates its shard and the tables are exchanged on the device)
+        xa = argparse.Namespace(**vars(args))
+        xa.steps, xa.min_region_s, xa.no_pageable, xa.no_cpu_baseline = max(3, min(args.steps, 5)), 0.3, True, True
+        xa.rows = 0
+        extras["c1"] = measure(xa, "c1", rank, world, local, dist, hc)
+        xb = argparse.Namespace(**vars(xa))
+        xb.rows, xb.keys = 125_000_000, 10_000_000
+        extras["aggbykey"] = measure(xb, "aggbykey", rank, world, local, dist, hc)
     if rank == 0:
         k0 = keys[0]
         cfg = static_config(args, k0)
@@ -756,6 +769,8 @@ def main():
         if args.workload == "both":
             line["q6"] = parts["q6"]
             line["gpu_launches"] += parts["q6"]["gpu_launches"]
+            for k, v in extras.items():
+                line[k] = v
         line["host"] = hc
         print(json.dumps(line))
     if dist is not None:

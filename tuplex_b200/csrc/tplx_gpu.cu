@@ -917,7 +917,7 @@ static int32_t run_rows_vec(tplx_stage *s, StageDev *sd, const tplx_block *b, in
     uint64_t *tile_state = nullptr, *totals = nullptr;
     uint32_t *counters = nullptr;
     KParams *dP = nullptr;
-    const size_t state_words = (size_t)P.n_tiles * (1 + 2 * P.K);
+    const size_t state_words = (size_t)P.n_tiles;  // one packed word per tile (vec_tile_finish)
     int32_t rc = dalloc(r, &tile_state, state_words);
     if (rc) return rc;
     rc = dalloc(r, &totals, MAX_SCAN);
@@ -990,7 +990,7 @@ static int32_t run_rows(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_
             }
         return TPLX_OK;
     }
-    if (s->vec_ok && !rowlist && !cols_override && !getenv("TPLX_NO_VEC")) {
+    if (s->vec_ok && !rowlist && !cols_override && !getenv("TPLX_NO_VEC") && b->n_rows < (1ull << 31)) {
         bool ok = true;
         for (size_t c = 0; c < b->cols.size(); ++c)
             ok = ok && !(b->cols[c].type & COL_COMPACT) && (c >= b->mapped.size() || !b->mapped[c]) && (((uintptr_t)b->cols[c].data & 15) == 0);

@@ -244,6 +244,111 @@ struct VecVM {
     }
 };
 
+// ---- tile tail of the vector kernel: block-wide decoupled look-back + dense write (fixed-width outputs only) -------------------
+// The scalar kernel's look-back (rows_tile_finish: one warp, a 32-tile window per round, K values behind a status flag and a fence)
+// is fine for heavy tiles; a fixed-width tile is evaluated in ~1-2 us, and then the speed at which inclusive prefixes propagate
+// (32 tiles per L2 round trip) bounds the whole kernel (measured: 59 G rows/s on C1). Here a tile's scan state is ONE 64-bit word
+//   [status:2 | rows kept:31 | exception rows:31]   status 1 = this tile's counts, 2 = inclusive prefix
+// written with a single relaxed store (no fence: status and values travel together), and ALL 256 threads look back at once: thread t
+// polls tile - 1 - t, the block adds the counts up to the nearest inclusive word — 256 tiles per round trip.
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t *p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void vec_tile_finish(const KParams &P, uint32_t tile, uint64_t base, uint32_t T, uint32_t W, uint8_t *s_regs,
+                                                uint32_t *keep_bits, uint32_t *exc_bits, uint32_t *keep_pre, uint32_t *exc_pre,
+                                                uint32_t *exc_stage, uint64_t *s_vals, uint64_t *s_scr) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // word prefixes of the two bitmaps (warp 0)
+    if (warp == 0) {
+        uint32_t ck = 0, ce = 0;
+        for (uint32_t w0 = 0; w0 < W; w0 += 32) {
+            const uint32_t w = w0 + lane;
+            const uint32_t pk = w < W ? __popc(keep_bits[w]) : 0, pe = w < W ? __popc(exc_bits[w]) : 0;
+            uint32_t ik = pk, ie = pe;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, ik, o), b = __shfl_up_sync(0xFFFFFFFFu, ie, o);
+                if (lane >= (uint32_t)o) { ik += a; ie += b; }
+            }
+            if (w < W) { keep_pre[w] = ck + ik - pk; exc_pre[w] = ce + ie - pe; }
+            ck += __shfl_sync(0xFFFFFFFFu, ik, 31);
+            ce += __shfl_sync(0xFFFFFFFFu, ie, 31);
+        }
+        if (lane == 0) {
+            s_vals[0] = ck;
+            s_vals[1] = ce;
+            // publish this tile's counts (tile 0: they are its inclusive prefix)
+            st_cg_u64(P.tile_state + tile, ((uint64_t)(tile == 0 ? 2u : 1u) << 62) | ((uint64_t)ck << 31) | (uint64_t)ce);
+        }
+    }
+    __syncthreads();
+    const uint32_t n_keep = (uint32_t)s_vals[0], n_exc = (uint32_t)s_vals[1];
+    // ---- look-back: 256 predecessors per round ----
+    uint64_t pre_keep = 0, pre_exc = 0;
+    if (tile > 0) {
+        int64_t p = (int64_t)tile - 1;
+        while (true) {
+            const int64_t q = p - (int64_t)tid;
+            uint64_t wd = (uint64_t)2 << 62;  // tiles before the first count as an inclusive prefix of zero
+            if (q >= 0) do { wd = ld_relaxed_u64(P.tile_state + q); } while ((wd >> 62) == 0);
+            const bool incl = (wd >> 62) == 2;
+            const uint32_t im = __ballot_sync(0xFFFFFFFFu, incl);
+            const uint32_t first = im ? (uint32_t)(__ffs(im) - 1) : 32u;  // nearest inclusive word inside this warp's 32 tiles
+            uint64_t k = lane <= first ? (wd >> 31) & 0x7FFFFFFFull : 0, e = lane <= first ? wd & 0x7FFFFFFFull : 0;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                k += __shfl_xor_sync(0xFFFFFFFFu, k, o);
+                e += __shfl_xor_sync(0xFFFFFFFFu, e, o);
+            }
+            if (lane == 0) {
+                s_scr[warp * 2] = (k << 32) | e;      // both < 2^31 * 32: fit 32 bits each? counts are < 2^31 in total, so yes
+                s_scr[warp * 2 + 1] = im ? 1 : 0;
+            }
+            __syncthreads();
+            bool done = false;
+            for (uint32_t w = 0; w < NT / 32 && !done; ++w) {  // warps cover tile-1-32w .. : nearest first
+                pre_keep += s_scr[w * 2] >> 32;
+                pre_exc += s_scr[w * 2] & 0xFFFFFFFFull;
+                done = s_scr[w * 2 + 1] != 0;
+            }
+            __syncthreads();
+            if (done) break;
+            p -= NT;
+        }
+        if (tid == 0) st_cg_u64(P.tile_state + tile, ((uint64_t)2 << 62) | ((pre_keep + n_keep) << 31) | (pre_exc + n_exc));
+    }
+    if (tid == 0 && tile == P.n_tiles - 1) {
+        P.totals[0] = pre_keep + n_keep;
+        P.totals[1] = pre_exc + n_exc;
+    }
+    // ---- write: fixed-width outputs straight from the register file (a slot is indexed by the local row) ----
+    if (n_keep) {
+        for (uint32_t c = 0; c < P.n_out; ++c) {
+            const OutCol &oc = P.out[c];
+            const uint64_t *st = reinterpret_cast<const uint64_t *>(s_regs + oc.stage_off);
+            for (uint32_t lr = tid; lr < T; lr += NT)
+                if (bit_test(keep_bits, lr)) oc.data[pre_keep + bit_rank(keep_bits, keep_pre, lr)] = st[lr];
+        }
+    }
+    if (n_exc) {
+        if (pre_exc + n_exc <= P.cap_exc) {
+            for (uint32_t lr = tid; lr < T; lr += NT) {
+                if (!bit_test(exc_bits, lr)) continue;
+                const uint32_t ke = bit_rank(exc_bits, exc_pre, lr), kk = bit_rank(keep_bits, keep_pre, lr);
+                tplx_exception_rec rec;
+                rec.row = (int64_t)(base + lr);
+                rec.row_no = P.first_row_no + (int64_t)(pre_keep + pre_exc + kk + ke);  // rows written + exceptions so far (TransformTask.cc:764,885)
+                const uint32_t es = exc_stage[lr];
+                rec.code = es & 0xFFFF;
+                rec.op_id = P.opids[es >> 16];
+                P.exc[pre_exc + ke] = rec;
+            }
+        } else if (tid == 0) atomicOr(&P.counters[1], 4u);
+    }
+}
+
 // K1v kernel: persistent CTAs, ticketed tiles of T = 2J * 256 rows, VecVM evaluation, shared tail (rows_tile_finish).
 // Shared memory: prog | cols | regs (n_slots x T x 8 B; output columns are staged in place) | misc (bitmaps, scan scratch).
 template <int J>
@@ -302,8 +407,7 @@ __global__ void __launch_bounds__(NT) stage_rows_vec_kernel(const KParams *__res
             }
         }
         __syncthreads();
-        rows_tile_finish(P, TileSmem{s_regs, nullptr, nullptr, keep_bits, exc_bits, keep_pre, exc_pre, exc_stage, s_vals, s_excl, s_warp}, tile, base, 2 * J, T, W,
-                         K, state_stride);
+        vec_tile_finish(P, tile, base, T, W, s_regs, keep_bits, exc_bits, keep_pre, exc_pre, exc_stage, s_vals, s_excl);
     }
 }
 

@@ -635,7 +635,7 @@ def _run_stage(ctx, src: Source, ops: List[Op], exc_counter: Counter, csv_sink: 
             if key not in table:
                 table[key] = []
                 order.append(key)
-    order.sort(key=lambda k: tuple((0, x) if not isinstance(x, str) else (1, x) for x in k))
+    order.sort(key=_key_order)
     rows = [tuple(list(k) + table[k]) if (len(k) + len(table[k])) != 1 else k[0] for k in order]
     names = list(prog.out_names) + [None] * len(prog.accs)
     stage.close()
@@ -646,6 +646,12 @@ def _acc_value(kind: int, bits: int):
     if kind in (C["TPLX_ACC_SUM_F64"], C["TPLX_ACC_MIN_F64"], C["TPLX_ACC_MAX_F64"]):
         return ir.bits_f64(bits)
     return bits - (1 << 64) if bits >= 1 << 63 else bits
+
+
+def _key_order(k):
+    """Deterministic order of result groups with mixed key types (None / numbers / strings, e.g. rows from the interpreter path)."""
+    return tuple((0, 0) if x is None else ((1, x) if isinstance(x, (int, float)) and not isinstance(x, bool) else
+                                           ((2, int(x)) if isinstance(x, bool) else (3, str(x)))) for x in k)
 
 
 def _acc_bits(kind: int, v) -> int:
@@ -749,7 +755,7 @@ def _run_stage_python(ctx, src: Source, ops: List[Op], exc_counter: Counter):
         key = tuple(r[k] for k in end.columns)
         table[key] = agg(table.get(key, init), r if len(r) != 1 else r[0])
     rows = []
-    for key in sorted(table, key=lambda k: tuple((0, x) if not isinstance(x, str) else (1, x) for x in k)):
+    for key in sorted(table, key=_key_order):
         v = comb(init, table[key])  # combine at least once per group (LocalBackend.cc:2148-2217)
         rows.append(tuple(list(key) + (list(v) if isinstance(v, tuple) else [v])))
     knames = [k if isinstance(k, str) else names[k] for k in end.columns]
