@@ -360,7 +360,8 @@ def test_unique_keeps_rows_from_the_interpreter_path(ctx, tmp_path):
     ds = ctx.parallelize([(6, 3), (5, 0), (8, 4), (7, 0), (4, 2)]).map(lambda a, b: a // b).resolve(ZeroDivisionError, lambda a, b: -1)
     assert sorted(ds.unique().collect()) == [-1, 2]
     p = tmp_path / "u.csv"
-    p.write_text("a,b\n1,x\n2,y\n,z\n1,x\nn/a,w\n2,y\n")
+    # 40 well-formed rows (two distinct), one row with a null cell, one with an unparsable cell: the normal case of column a is i64
+    p.write_text("a,b\n" + "1,x\n2,y\n" * 10 + ",z\n" + "1,x\n2,y\n" * 5 + "n/a,w\n" + "2,y\n1,x\n" * 5)
     rows = ctx.csv(str(p)).unique().collect()
     assert sorted(rows, key=repr) == sorted([(1, "x"), (2, "y"), (None, "z"), ("n/a", "w")], key=repr)
 

@@ -55,13 +55,10 @@ TPLX_HD uint32_t upper4(uint32_t w) {
 TPLX_HD uint32_t case4(uint32_t w, uint32_t flags) {
     return flags == TPLX_SF_LOWER ? lower4(w) : (flags == TPLX_SF_UPPER ? upper4(w) : w);
 }
-TPLX_HD uint8_t case1(uint8_t c, uint32_t flags) {
-    if (flags == TPLX_SF_LOWER) {
-        if ((uint8_t)(c - 'A') < 26u) c += 32;
-    } else if (flags == TPLX_SF_UPPER) {
-        if ((uint8_t)(c - 'a') < 26u) c -= 32;
-    }
-    return c;
+TPLX_HD uint8_t case1(uint8_t c, uint32_t flags) {  // branch-free (selects): it sits in the inner loops of byte-wise fallbacks
+    const uint8_t lo = (flags == TPLX_SF_LOWER && (uint8_t)(c - 'A') < 26u) ? 32 : 0;
+    const uint8_t up = (flags == TPLX_SF_UPPER && (uint8_t)(c - 'a') < 26u) ? 32 : 0;
+    return (uint8_t)(c + lo - up);
 }
 // 0x80 in every byte lane of w that equals c (exact, no false positives)
 TPLX_HD uint32_t eq_mask4(uint32_t w, uint32_t c) {
@@ -184,13 +181,14 @@ TPLX_HD int64_t str_find_impl(const StrV &h, const StrV &n) {
     const uint32_t sh = (uint32_t)(addr & 3) * 8;
     const uint32_t nwords = (uint32_t)(((addr & 3) + h.len + 3) >> 2);  // aligned words holding string bytes (>= 1)
     const uint32_t kfull = (last + 1) >> 2;                             // steps k < kfull: positions 4k..4k+3 are all <= last
+    const uint32_t rem = (last + 1) & 3;                                // admissible positions of the partial step kfull
+    const uint32_t nsteps = kfull + (rem ? 1 : 0);
+    const uint32_t tail_mask = (1u << (8 * rem)) - 1u;                  // rem in 1..3
+    const bool plain_needle = n.flags == TPLX_SF_NONE;
     uint32_t a0 = aw[0];
-    uint32_t k = 0;
-    for (;; ++k) {
-        const bool full = k < kfull;
-        if (!full && 4 * k > last) break;
-        // aw[k+1] holds string bytes whenever it is needed: for sh != 0 it completes string word k; for a 2-character needle it holds
-        // character 4k+4 <= last + 1 < h.len. (1-character needle with sh == 0: not needed, and it may lie outside the string.)
+    for (uint32_t k = 0; k < nsteps; ++k) {
+        // aw[k+1] holds string bytes whenever it is used: for sh != 0 it completes string word k; for a 2-character needle it holds
+        // character 4k+4 <= last + 1 < h.len (full step). The bounds test only matters for the partial step / a 1-character needle.
         const uint32_t a1 = (k + 1 < nwords) ? aw[k + 1] : 0u;
         const uint32_t cur = case4_t<HFLAGS>(funnel_r(a0, a1, sh));
         uint32_t m;
@@ -198,9 +196,9 @@ TPLX_HD int64_t str_find_impl(const StrV &h, const StrV &n) {
             const uint32_t nx = case4_t<HFLAGS>(a1 >> sh);  // low byte = character 4k+4
             m = both_zero4(cur ^ c0, ((cur >> 8) | (nx << 24)) ^ c1);
         } else {
-            m = eq_mask4(cur, c0 & 0xFFu);
+            m = both_zero4(cur ^ c0, 0u);
         }
-        if (!full) m &= low_mask(last - 4 * k + 1);  // positions 0..last-4k of this word are admissible
+        if (k >= kfull) m &= tail_mask;
         while (m) {
 #ifdef __CUDA_ARCH__
             const uint32_t bit = __ffs(m) - 1;
@@ -209,7 +207,8 @@ TPLX_HD int64_t str_find_impl(const StrV &h, const StrV &n) {
 #endif
             const uint32_t pos = 4 * k + (bit >> 3);
             bool ok = true;
-            for (uint32_t j = two ? 2 : 1; ok && j < n.len; ++j) ok = sch_t<HFLAGS>(h.p, pos + j) == sch(n, j);
+            if (plain_needle) for (uint32_t j = two ? 2 : 1; ok && j < n.len; ++j) ok = sch_t<HFLAGS>(h.p, pos + j) == n.p[j];
+            else for (uint32_t j = two ? 2 : 1; ok && j < n.len; ++j) ok = sch_t<HFLAGS>(h.p, pos + j) == sch(n, j);
             if (ok) return (int64_t)pos;
             m &= m - 1;
         }

@@ -1224,6 +1224,8 @@ static int32_t run_mask(tplx_stage *ps, StageDev *psd, const tplx_block *b, tplx
     if (scan) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stage_mask_kernel<true>, NT, smem_total));
     else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stage_mask_kernel<false>, NT, smem_total));
     if (occ < 1) return fail(TPLX_E_UNSUPPORTED, "mask kernel cannot be resident");
+    // TPLX_MASK_OCC caps the resident CTAs per SM: leaving registers free lets the dense launch of another block (other lane) co-reside
+    if (getenv("TPLX_MASK_OCC")) occ = std::max(1, std::min(occ, atoi(getenv("TPLX_MASK_OCC"))));
     const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>((P.n_tiles + MASK_WARPS - 1) / MASK_WARPS, (uint32_t)(occ * d->prop.multiProcessorCount)));
     P.scratch_per_thread = ps->materialises ? std::max<uint32_t>(ps->hdr.scratch_bytes, 64) : 0;
     int32_t rc = ensure_scratch(d, (size_t)grid * NT * P.scratch_per_thread);

@@ -387,23 +387,36 @@ __global__ void __launch_bounds__(NT) stage_rows_vec_kernel(const KParams *__res
         const uint64_t base = (uint64_t)tile * T;
 
         typename VecVM<J>::State st;
-        st.alive = 0;
         st.exc = 0;
+        if (base + T <= P.n_rows) st.alive = (1u << (2 * J)) - 1u;  // full tile (uniform test): every row starts alive
+        else {
+            st.alive = 0;
 #pragma unroll
-        for (uint32_t v = 0; v < 2 * J; ++v)
-            if (base + VecVM<J>::lrow(v >> 1, v & 1) < P.n_rows) st.alive |= 1u << v;
+            for (uint32_t v = 0; v < 2 * J; ++v)
+                if (base + VecVM<J>::lrow(v >> 1, v & 1) < P.n_rows) st.alive |= 1u << v;
+        }
         VecVM<J>::run(s_prog, P.n_instr, s_regs + tid * 16, s_cols, base, P.n_rows, st, exc_stage);
-        // bitmaps indexed by local row: rows (2 tid, 2 tid + 1) of slab j -> word j * 16 + tid / 16, bits 2 (tid % 16) + {0, 1}
+        // bitmaps indexed by local row: thread t holds rows (2t, 2t+1) of slab j, so bit i of a bitmap word comes from lane i / 2
+        // (+ 16 for the word's upper half of the warp), even / odd row by the parity of i: one extra ballot interleaves the two masks
+        const bool any_exc = __any_sync(0xFFFFFFFFu, st.exc != 0);
 #pragma unroll
         for (uint32_t j = 0; j < J; ++j) {
             const uint32_t ke = __ballot_sync(0xFFFFFFFFu, (st.alive >> (2 * j)) & 1u), ko = __ballot_sync(0xFFFFFFFFu, (st.alive >> (2 * j + 1)) & 1u);
-            const uint32_t ee = __ballot_sync(0xFFFFFFFFu, (st.exc >> (2 * j)) & 1u), eo = __ballot_sync(0xFFFFFFFFu, (st.exc >> (2 * j + 1)) & 1u);
+            const uint32_t pick = (lane & 1) ? ko : ke, sh = lane >> 1;
+            const uint32_t w0 = __ballot_sync(0xFFFFFFFFu, (pick >> sh) & 1u), w1 = __ballot_sync(0xFFFFFFFFu, (pick >> (16 + sh)) & 1u);
+            uint32_t e0 = 0, e1 = 0;
+            if (any_exc) {
+                const uint32_t ee = __ballot_sync(0xFFFFFFFFu, (st.exc >> (2 * j)) & 1u), eo = __ballot_sync(0xFFFFFFFFu, (st.exc >> (2 * j + 1)) & 1u);
+                const uint32_t pe = (lane & 1) ? eo : ee;
+                e0 = __ballot_sync(0xFFFFFFFFu, (pe >> sh) & 1u);
+                e1 = __ballot_sync(0xFFFFFFFFu, (pe >> (16 + sh)) & 1u);
+            }
             if (lane == 0) {
                 const uint32_t w = j * (2 * NT / 32) + 2 * warp;
-                keep_bits[w] = spread16(ke) | (spread16(ko) << 1);
-                keep_bits[w + 1] = spread16(ke >> 16) | (spread16(ko >> 16) << 1);
-                exc_bits[w] = spread16(ee) | (spread16(eo) << 1);
-                exc_bits[w + 1] = spread16(ee >> 16) | (spread16(eo >> 16) << 1);
+                keep_bits[w] = w0;
+                keep_bits[w + 1] = w1;
+                exc_bits[w] = e0;
+                exc_bits[w + 1] = e1;
             }
         }
         __syncthreads();

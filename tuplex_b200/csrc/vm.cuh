@@ -346,6 +346,24 @@ struct VM {
                         WS(rb, dst, o, pos, 0);
                         break;
                     }
+                    if (f.len == 1 && s.flags == TPLX_SF_NONE && f.flags == TPLX_SF_NONE && r.flags == TPLX_SF_NONE) {
+                        // single-character needle on a plain string (the common `.replace(',', '')`): two byte loops without case mapping
+                        const uint8_t ch = f.p[0];
+                        uint32_t cnt = 0;
+                        for (uint32_t q = 0; q < s.len; ++q) cnt += s.p[q] == ch;
+                        if (cnt == 0) { WS(rb, dst, s.p, s.len, 0); break; }  // nothing to replace: the input itself (same bytes as a copy)
+                        const uint32_t n1 = s.len + cnt * r.len - cnt;
+                        uint8_t *o1 = scratch_alloc(t, n1 ? n1 : 1, opidx);
+                        if (!o1) break;
+                        uint32_t w = 0;
+                        for (uint32_t q = 0; q < s.len; ++q) {
+                            const uint8_t b0 = s.p[q];
+                            if (b0 == ch) for (uint32_t j = 0; j < r.len; ++j) o1[w++] = r.p[j];
+                            else o1[w++] = b0;
+                        }
+                        WS(rb, dst, o1, n1, 0);
+                        break;
+                    }
                     // count pass
                     uint32_t count = 0, i = 0;
                     while (i + f.len <= s.len) {
