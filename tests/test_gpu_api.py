@@ -412,7 +412,9 @@ def test_sharded_execution_over_two_tasks_matches_one(gpu):
     def pipe2(c):
         return c.parallelize(data, columns=["a", "b", "s"]).map(lambda x: (x["a"] % x["b"], x["s"]))
     d1, d2 = pipe2(one), pipe2(two)
-    assert d1.collect() == d2.collect() and d1.exception_counts == d2.exception_counts and sum(d1.exception_counts.values()) > 1000
+    assert d1.collect() == d2.collect()
+    by_type = lambda ds: sorted((k[1], v) for k, v in ds.exception_counts.items())  # (the operator ids of two separately built plans differ)
+    assert by_type(d1) == by_type(d2) and sum(d1.exception_counts.values()) > 1000
     # aggregate (i64: exact whatever the association) and aggregateByKey / unique over the shards
     agg = lambda c: c.parallelize(data, columns=["a", "b", "s"]).aggregate(lambda x, y: x + y, lambda acc, r: acc + r["a"] * r["b"], 0).collect()
     assert agg(one) == agg(two) == agg(three) == [sum(a * b for a, b, _ in data)]

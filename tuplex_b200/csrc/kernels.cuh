@@ -322,9 +322,8 @@ __device__ __forceinline__ void rows_tile_finish(const KParams &P, const TileSme
 // =============================================================================================
 // Shared memory map (byte offsets from KParams): prog | cols | regs | staging | misc
 // misc: keep_bits[W] exc_bits[W] keep_pre[W+1] exc_pre[W+1] exc_stage[T] scan scratch
-__global__ void __launch_bounds__(NT) stage_rows_kernel(const KParams *__restrict__ Pg) {
+__global__ void __launch_bounds__(NT) stage_rows_kernel(const __grid_constant__ KParams P) {  // parameters in the constant bank
     extern __shared__ __align__(16) uint8_t smem[];
-    const KParams &P = *Pg;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t R = P.R, T = R * NT, W = T / 32, K = P.K;
 

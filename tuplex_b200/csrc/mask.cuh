@@ -80,8 +80,13 @@ __device__ __forceinline__ bool cmp_f64(uint32_t cmp, double x, double y) {  // 
         default: return x >= y;
     }
 }
+template <bool GLOBAL_ONLY>
 __device__ __forceinline__ StrV scan_col(const ColIn &ci, uint64_t row) {
     StrV s;
+    if (GLOBAL_ONLY) {  // nothing is staged: the column lives in global memory, so the string primitives can use LDG instead of generic LD
+        __builtin_assume(__isGlobal(ci.data));
+        __builtin_assume(__isGlobal(ci.offsets));
+    }
     const uint32_t o0 = ci.offsets[row], o1 = ci.offsets[row + 1];
     s.p = reinterpret_cast<const uint8_t *>(ci.data) + o0;
     s.len = o1 - o0;
@@ -96,6 +101,7 @@ __device__ __forceinline__ StrV scan_const(const uint8_t *cpool, uint64_t enc) {
     return v;
 }
 // evaluates the terms in order for one row; a row raises only in a term it reaches (PipelineBuilder.cc:949)
+template <bool GLOBAL_ONLY>
 __device__ __forceinline__ void scan_eval(const MaskParams &P, const ColIn *__restrict__ cols, uint64_t row, VMThread &t) {
     for (uint32_t k = 0; k < P.n_terms; ++k) {
         if (!__any_sync(0xFFFFFFFFu, t.alive)) break;
@@ -103,14 +109,14 @@ __device__ __forceinline__ void scan_eval(const MaskParams &P, const ColIn *__re
         if (!t.alive) continue;
         const ColIn &ci = cols[T.col];
         if (T.kind == TPLX_SK_CONTAINS) {
-            StrV s = scan_col(ci, row);
+            StrV s = scan_col<GLOBAL_ONLY>(ci, row);
             const StrV n = scan_const(P.cpool, T.needle);
             const uint32_t cf = T.flags & TPLX_SCF_CASE_MASK;
             s.flags = cf;
             const int64_t r = cf == TPLX_SF_LOWER ? scan_find<TPLX_SF_LOWER>(s, n) : (cf == TPLX_SF_UPPER ? scan_find<TPLX_SF_UPPER>(s, n) : scan_find<TPLX_SF_NONE>(s, n));
             t.alive = (r >= 0) != ((T.flags & TPLX_SCF_NEGATE) != 0);
         } else if (T.kind == TPLX_SK_FIELD_INT) {
-            const StrV s = scan_col(ci, row);
+            const StrV s = scan_col<GLOBAL_ONLY>(ci, row);
             const int64_t i = scan_find<TPLX_SF_NONE>(s, scan_const(P.cpool, T.needle));
             StrV head = s;
             head.len = i < 0 ? s.len : (uint32_t)i;                                   // s[:stop]
@@ -136,10 +142,11 @@ __device__ __forceinline__ void scan_eval(const MaskParams &P, const ColIn *__re
     }
 }
 
+// The parameter block travels by value in the kernel's constant bank (__grid_constant__): every P.field below is a constant-bank
+// operand instead of a global load through a pointer (terms, column table, offsets — read in the per-row loops).
 template <bool SCAN>
-__global__ void __launch_bounds__(NT) stage_mask_kernel(const MaskParams *__restrict__ Pg) {
+__global__ void __launch_bounds__(NT) stage_mask_kernel(const __grid_constant__ MaskParams P) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const MaskParams &P = *Pg;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t MR = P.MR, TR = 32 * MR, ns = P.n_staged;
 
@@ -226,7 +233,7 @@ __global__ void __launch_bounds__(NT) stage_mask_kernel(const MaskParams *__rest
             t.alive = row < P.n_rows;
             t.exc_code = 0;
             t.scr_used = 0;
-            if (SCAN) scan_eval(P, s_wcols, row, t);
+            if (SCAN) { if (ns) scan_eval<false>(P, s_wcols, row, t); else scan_eval<true>(P, s_wcols, row, t); }
             else VM<NT>::run(s_prog, 0, P.n_instr, s_regs, s_wcols, row, row, P.cpool, t);
             const bool exc = t.exc_code != 0;
             const uint32_t kb = __ballot_sync(0xFFFFFFFFu, t.alive);

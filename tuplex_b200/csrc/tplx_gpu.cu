@@ -846,9 +846,9 @@ static int32_t dalloc(tplx_result *r, T **p, size_t count) {
 // K1v (vecvm.cuh): fixed-width stages, vector-at-a-time. Outputs are fixed width, so capacities are exact (n rows) and the only
 // retry is for exception records.
 template <int J>
-static int32_t launch_rows_vec(uint32_t grid, uint32_t smem, cudaStream_t st, const KParams *dP) {
+static int32_t launch_rows_vec(uint32_t grid, uint32_t smem, cudaStream_t st, const KParams &P) {
     CU(cudaFuncSetAttribute(stage_rows_vec_kernel<J>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    stage_rows_vec_kernel<J><<<grid, NT, smem, st>>>(dP);
+    stage_rows_vec_kernel<J><<<grid, NT, smem, st>>>(P);
     return TPLX_OK;
 }
 static int32_t run_rows_vec(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_t first_row_no, tplx_result *r) {
@@ -947,8 +947,7 @@ static int32_t run_rows_vec(tplx_stage *s, StageDev *sd, const tplx_block *b, in
         CU(cudaMemsetAsync(tile_state, 0, state_words * 8, d->stream));
         CU(cudaMemsetAsync(counters, 0, 16, d->stream));
         CU(cudaMemsetAsync(totals, 0, MAX_SCAN * 8, d->stream));
-        CU(cudaMemcpyAsync(dP, &P, sizeof(P), cudaMemcpyHostToDevice, d->stream));
-        rc = Jsel == 4 ? launch_rows_vec<4>(grid, smem, d->stream, dP) : launch_rows_vec<2>(grid, smem, d->stream, dP);
+        rc = Jsel == 4 ? launch_rows_vec<4>(grid, smem, d->stream, P) : launch_rows_vec<2>(grid, smem, d->stream, P);
         if (rc) return rc;
         CU(cudaGetLastError());
         r->launches += 1;
@@ -1099,9 +1098,8 @@ static int32_t run_rows(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_
         CU(cudaMemsetAsync(tile_state, 0, state_words * 8, d->stream));
         CU(cudaMemsetAsync(counters, 0, 16, d->stream));
         CU(cudaMemsetAsync(totals, 0, MAX_SCAN * 8, d->stream));
-        CU(cudaMemcpyAsync(dP, &P, sizeof(P), cudaMemcpyHostToDevice, d->stream));
         CU(cudaEventRecord(r->evk0, d->stream));
-        stage_rows_kernel<<<grid, NT, L.total, d->stream>>>(dP);
+        stage_rows_kernel<<<grid, NT, L.total, d->stream>>>(P);
         CU(cudaGetLastError());
         CU(cudaEventRecord(r->evk1, d->stream));
         r->launches += 1;
@@ -1234,7 +1232,6 @@ static int32_t run_mask(tplx_stage *ps, StageDev *psd, const tplx_block *b, tplx
     const uint32_t n_words = P.n_tiles * P.MR;
     const uint32_t nb = (n_words + CMP_NT - 1) / CMP_NT;
     uint64_t *part = nullptr, *totals = nullptr;
-    MaskParams *dP = nullptr;
     rc = dalloc(ra, &P.keep_words, n_words);
     if (rc) return rc;
     rc = dalloc(ra, &P.exc_words, n_words);
@@ -1245,11 +1242,8 @@ static int32_t run_mask(tplx_stage *ps, StageDev *psd, const tplx_block *b, tplx
     if (rc) return rc;
     rc = dalloc(ra, &totals, 2);
     if (rc) return rc;
-    rc = dalloc(ra, &dP, 1);
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(dP, &P, sizeof(P), cudaMemcpyHostToDevice, d->stream));
-    if (scan) stage_mask_kernel<true><<<grid, NT, smem_total, d->stream>>>(dP);
-    else stage_mask_kernel<false><<<grid, NT, smem_total, d->stream>>>(dP);
+    if (scan) stage_mask_kernel<true><<<grid, NT, smem_total, d->stream>>>(P);
+    else stage_mask_kernel<false><<<grid, NT, smem_total, d->stream>>>(P);
     CU(cudaGetLastError());
     mask_count_kernel<<<nb, CMP_NT, 0, d->stream>>>(P.keep_words, P.exc_words, n_words, part);
     mask_scan_kernel<<<1, CMP_NT, 0, d->stream>>>(part, nb, totals);

@@ -352,9 +352,8 @@ __device__ __forceinline__ void vec_tile_finish(const KParams &P, uint32_t tile,
 // K1v kernel: persistent CTAs, ticketed tiles of T = 2J * 256 rows, VecVM evaluation, shared tail (rows_tile_finish).
 // Shared memory: prog | cols | regs (n_slots x T x 8 B; output columns are staged in place) | misc (bitmaps, scan scratch).
 template <int J>
-__global__ void __launch_bounds__(NT) stage_rows_vec_kernel(const KParams *__restrict__ Pg) {
+__global__ void __launch_bounds__(NT) stage_rows_vec_kernel(const __grid_constant__ KParams P) {  // parameters in the constant bank
     extern __shared__ __align__(16) uint8_t smem[];
-    const KParams &P = *Pg;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr uint32_t T = VecVM<J>::T, W = T / 32;
     const uint32_t K = P.K;
