@@ -476,3 +476,36 @@ def test_string_scan_closed_form_equals_vm_and_oracle(gpu, name, n, monkeypatch)
         assert_result_equals_oracle(res, ora, f"{name} n={n} env={env}")
     if n > 1000 and name in ("zillow", "fixed_then_field", "field_eq_nan"):
         assert len(ora.exceptions) > 0
+
+
+def test_prefiltered_stage_without_host_round_trip(gpu, monkeypatch):
+    """From the second block of a stage on, the dense launch is sized from the previous block's selectivity and reads the survivor count
+    on the device (no host round trip between the two launches). Blocks with the same / far more survivors / far more exception rows
+    than the estimate (retry paths), an empty block and a block without survivors must all equal the oracle; TPLX_SYNC_PREFILTER=1 (the
+    round-trip path) must give the same."""
+    import scan_udfs as U
+    sc = frontend.StageCompiler(U.TYPES, U.NAMES)
+    U._h_zillow(sc)
+    U.heavy_tail(sc, 100100)
+    prog = sc.finish_memory()
+    rng = np.random.default_rng(77)
+
+    def block(n, p_house, p_bad):
+        f = [("x bd, y bd" if rng.random() < p_bad else U.FACTS[0]) for _ in range(n)]
+        t = [("house" if rng.random() < p_house else "condo") for _ in range(n)]
+        return [Column.from_values(f, T_STR), Column.from_values(t, T_STR), Column(T_I64, rng.integers(0, 9, n).astype(np.int64)),
+                Column(T_F64, rng.normal(0, 1, n))]
+    blocks = [(40_000, 0.02, 0.001), (40_000, 0.02, 0.001), (40_000, 0.6, 0.001), (40_000, 0.02, 0.3), (0, 0, 0), (30_000, 0.0, 0.0),
+              (50_000, 0.05, 0.01)]
+    data = [(block(*b), b[0]) for b in blocks]
+    for env in ({}, {"TPLX_SYNC_PREFILTER": "1"}):
+        monkeypatch.delenv("TPLX_SYNC_PREFILTER", raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        st = backend.Stage(prog)
+        for i, (cols, n) in enumerate(data):
+            res = st.run_host(0, cols, n, 5)
+            ora = pyoracle.run_program(prog, cols, n, 5)
+            assert_result_equals_oracle(res, ora, f"block {i} env={env}")
+            res.free()
+        st.close()

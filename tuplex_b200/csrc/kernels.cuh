@@ -59,7 +59,9 @@ struct KParams {
     uint64_t *tile_partials;  // aggregate: n_tiles * n_accs
     uint64_t *agg_out;        // aggregate: n_accs
     const uint64_t *rowlist;  // optional: evaluate these input rows only (output of a prefilter stage), ascending
-    uint64_t n_work;          // rows to evaluate: n_rows, or the length of rowlist
+    uint64_t n_work;          // rows to evaluate: n_rows, or the length of rowlist (its CAPACITY when n_work_dev is set)
+    const uint64_t *n_work_dev;  // optional: the actual length of rowlist lives on the device (written by an earlier kernel of the
+                                 // same stream): the host sized everything from an estimate and never waited for the count
     ColIn in[TPLX_MAX_COLS];
     OutCol out[TPLX_MAX_COLS];
     AccP accs[TPLX_MAX_ACCS];
@@ -132,7 +134,7 @@ struct TileSmem {
     uint64_t *s_vals, *s_excl, *s_warp;
 };
 __device__ __forceinline__ void rows_tile_finish(const KParams &P, const TileSmem &S, uint32_t tile, uint64_t base, uint32_t R, uint32_t T,
-                                                 uint32_t W, uint32_t K, uint32_t state_stride) {
+                                                 uint32_t W, uint32_t K, uint32_t state_stride, uint32_t n_tiles) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint8_t *s_stage = S.s_stage;
     uint32_t *s_stash = S.s_stash, *s_wtot = S.s_stash + P.n_str_out * NT;
@@ -254,7 +256,7 @@ __device__ __forceinline__ void rows_tile_finish(const KParams &P, const TileSme
         }
         if (lane < K) {
             s_excl[lane] = excl;
-            if (tile == P.n_tiles - 1) P.totals[lane] = excl + myval;
+            if (tile == n_tiles - 1) P.totals[lane] = excl + myval;
         }
     }
     __syncthreads();
@@ -291,10 +293,10 @@ __device__ __forceinline__ void rows_tile_finish(const KParams &P, const TileSme
                     str_copy(oc.bytes + off, sv);
                     off += sv.len;
                 }
-                if (tile == P.n_tiles - 1 && tid == 0) oc.offsets[pre_keep + n_keep] = (uint32_t)(pre_b + tile_b);
+                if (tile == n_tiles - 1 && tid == 0) oc.offsets[pre_keep + n_keep] = (uint32_t)(pre_b + tile_b);
             }
         }
-    } else if (tile == P.n_tiles - 1 && rows_fit && tid == 0) {
+    } else if (tile == n_tiles - 1 && rows_fit && tid == 0) {
         for (uint32_t c = 0; c < P.n_out; ++c)
             if (P.out[c].strk >= 0) P.out[c].offsets[pre_keep] = (uint32_t)s_excl[2 + P.out[c].strk];
     }
@@ -353,6 +355,19 @@ __global__ void __launch_bounds__(NT) stage_rows_kernel(const __grid_constant__ 
     t.scratch = P.scratch + ((size_t)blockIdx.x * NT + tid) * (size_t)P.scratch_per_thread;
 
     const uint32_t state_stride = 1 + 2 * K;
+    // work size: known to the host, or (dense launch behind a prefilter that was not waited for) read from the device and clamped to
+    // the capacity everything was sized for; a count beyond the capacity raises flag 8 and the host redoes the launch
+    uint64_t n_work = P.n_work;
+    uint32_t n_tiles = P.n_tiles;
+    if (P.n_work_dev) {
+        const uint64_t actual = *P.n_work_dev;
+        if (actual > P.n_work && blockIdx.x == 0 && tid == 0) atomicOr(&P.counters[1], 8u);
+        n_work = actual < P.n_work ? actual : P.n_work;
+        n_tiles = (uint32_t)((n_work + T - 1) / T);
+        if (n_tiles == 0 && blockIdx.x == 0 && tid == 0)
+            for (uint32_t c = 0; c < P.n_out; ++c)
+                if (P.out[c].strk >= 0) P.out[c].offsets[0] = 0;
+    }
 
     while (true) {
         __syncthreads();
@@ -363,7 +378,7 @@ __global__ void __launch_bounds__(NT) stage_rows_kernel(const __grid_constant__ 
         for (uint32_t i = tid; i < 2 * W; i += NT) keep_bits[i] = 0;  // keep_bits and exc_bits
         __syncthreads();
         const uint32_t tile = s_ctl[0];
-        if (tile >= P.n_tiles) break;
+        if (tile >= n_tiles) break;
         const uint64_t base = (uint64_t)tile * T;  // position in the work list (== input row without a rowlist)
         t.scr_used = 0;
 
@@ -384,7 +399,7 @@ __global__ void __launch_bounds__(NT) stage_rows_kernel(const __grid_constant__ 
         for (uint32_t s = 0; s < R; ++s) {
             const uint32_t lr = s * NT + tid;
             const uint64_t w = base + lr;
-            const bool valid = w < P.n_work;
+            const bool valid = w < n_work;
             const uint64_t row = P.rowlist ? (valid ? P.rowlist[w] : 0) : w;
             t.alive = valid;
             t.exc_code = 0;
@@ -402,7 +417,7 @@ __global__ void __launch_bounds__(NT) stage_rows_kernel(const __grid_constant__ 
         __syncthreads();
 
         rows_tile_finish(P, TileSmem{s_stage, s_regs, s_stash, keep_bits, exc_bits, keep_pre, exc_pre, exc_stage, s_vals, s_excl, s_warp}, tile, base,
-                         R, T, W, K, state_stride);
+                         R, T, W, K, state_stride, n_tiles);
     }
 }
 

@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(CMP_NT) mask_scan_kernel(uint64_t *__restrict_
 __global__ void __launch_bounds__(CMP_NT) mask_expand_kernel(const uint32_t *__restrict__ keep, const uint32_t *__restrict__ exc, uint32_t n_words,
                                                              const uint64_t *__restrict__ part, uint64_t *__restrict__ rowlist,
                                                              const uint32_t *__restrict__ exc_codes, const int64_t *__restrict__ opids,
-                                                             tplx_exception_rec *__restrict__ exc_out) {
+                                                             tplx_exception_rec *__restrict__ exc_out, uint64_t cap_exc) {
     __shared__ uint32_t s_w[66];
     const uint32_t w = blockIdx.x * CMP_NT + threadIdx.x;
     uint32_t kw = w < n_words ? keep[w] : 0, ew = w < n_words ? exc[w] : 0;
@@ -331,7 +331,8 @@ __global__ void __launch_bounds__(CMP_NT) mask_expand_kernel(const uint32_t *__r
         rec.row_no = 0;  // numbered by the caller once the dense launch's rows are known
         rec.code = es & 0xFFFF;
         rec.op_id = opids[es >> 16];
-        exc_out[eo++] = rec;
+        if (eo < cap_exc) exc_out[eo] = rec;  // beyond the estimated capacity: the host sees totals[1] > cap and expands again
+        ++eo;
     }
 }
 

@@ -60,6 +60,7 @@ struct Device {
     int smem_optin = 0;
     uint8_t *scratch = nullptr;
     size_t scratch_bytes = 0;
+    uint64_t *pinned = nullptr;  // small page-locked buffer: counts fetched with stream-ordered copies that never block the host
     std::mutex mu;
     Device *alt = nullptr;  // second execution lane on the same GPU (own streams + scratch): lets the kernels of two
                             // blocks overlap (e.g. the latency-bound dense launch of one with the prefilter of the next)
@@ -99,6 +100,7 @@ extern "C" int32_t tplx_gpu_init(const int32_t *devices, int32_t n) {
         CU(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&d->d2h_stream, cudaStreamNonBlocking));
+        CU(cudaHostAlloc(&d->pinned, 64 * 8, cudaHostAllocDefault));
         CU(cudaDeviceGetAttribute(&d->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, id));
         cudaMemPool_t pool;
         CU(cudaDeviceGetDefaultMemPool(&pool, id));
@@ -123,6 +125,7 @@ extern "C" int32_t tplx_gpu_init(const int32_t *devices, int32_t n) {
             CU(cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking));
             CU(cudaStreamCreateWithFlags(&a->copy_stream, cudaStreamNonBlocking));
             CU(cudaStreamCreateWithFlags(&a->d2h_stream, cudaStreamNonBlocking));
+            CU(cudaHostAlloc(&a->pinned, 64 * 8, cudaHostAllocDefault));
             tail->alt = a;
             tail = a;
         }
@@ -198,6 +201,7 @@ struct tplx_stage {
     double est_exc_per_row = 0.0;
     tplx_stage *prefilter = nullptr;  // nested selective stage (row index output), may be null
     bool prefilter_enabled = true;    // switched off at run time when it turns out not to be selective
+    double est_surv_ratio = -1.0;     // survivors / rows of the last block (prefilter stage): sizes the next block's dense launch
     uint32_t hidden = 0;              // trailing executor-internal output columns
     bool vec_ok = false;              // fixed-width values and vector-VM ops only: eligible for K1v (vecvm.cuh)
     std::vector<tplx_scan_term> scan; // string-scan hint (closed form of a pure filter chain), empty = none
@@ -573,6 +577,9 @@ struct tplx_result {
     uint32_t launches = 0;
     bool owns_block = false;
     tplx_block *owned_block = nullptr;
+    // mask stage temporaries (run_mask), needed when the exception records have to be expanded again with the exact capacity
+    uint32_t *mask_keep = nullptr, *mask_exc = nullptr, *mask_codes = nullptr, mask_words = 0;
+    uint64_t *mask_part = nullptr;
 };
 
 extern "C" int32_t tplx_gpu_result_free(tplx_result *r) {
@@ -640,11 +647,13 @@ static int32_t ensure_scratch(Device *d, size_t bytes) {
 }
 
 static int32_t run_rows(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_t first_row_no, tplx_result *r,
-                        const uint64_t *rowlist, uint64_t n_list, const std::vector<ColIn> *cols_override = nullptr);
+                        const uint64_t *rowlist, uint64_t n_list, const std::vector<ColIn> *cols_override = nullptr,
+                        const uint64_t *n_work_dev = nullptr);
+constexpr int32_t TPLX_INTERNAL_RETRY = 1;  // run_rows with n_work_dev: the device-side count exceeded the estimated capacity
 static int32_t device_scan(Device *d, const uint64_t *in, uint64_t *out, uint64_t n, bool write_total);
 static int32_t device_scan_batched(Device *d, uint64_t *arrays, uint64_t stride, uint32_t K, uint64_t n);
 static int32_t run_rows_prefiltered(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_t first_row_no, tplx_result *r);
-static int32_t run_mask(tplx_stage *ps, StageDev *psd, const tplx_block *b, tplx_result *ra);
+static int32_t run_mask(tplx_stage *ps, StageDev *psd, const tplx_block *b, tplx_result *ra, bool no_wait, uint64_t **totals_dev, uint64_t *cap_exc_out);
 static int32_t run_agg(tplx_stage *s, StageDev *sd, const tplx_block *b, tplx_result *r);
 static int32_t run_hash(tplx_stage *s, StageDev *sd, const tplx_block *b, tplx_result *r);
 
@@ -969,8 +978,10 @@ static int32_t run_rows_vec(tplx_stage *s, StageDev *sd, const tplx_block *b, in
     return TPLX_OK;
 }
 
+// n_work_dev != nullptr: n_list is only the CAPACITY of the survivor list (an estimate); the real length is read on the device.
+// Returns TPLX_INTERNAL_RETRY when the real length turned out larger (nothing usable was produced).
 static int32_t run_rows(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_t first_row_no, tplx_result *r,
-                        const uint64_t *rowlist, uint64_t n_list, const std::vector<ColIn> *cols_override) {
+                        const uint64_t *rowlist, uint64_t n_list, const std::vector<ColIn> *cols_override, const uint64_t *n_work_dev) {
     Device *d = r->dev;  // execution lane chosen by tplx_gpu_stage_run
     const uint64_t n = rowlist ? n_list : b->n_rows;  // rows to evaluate
     r->hidden = s->hidden;
@@ -1032,6 +1043,7 @@ static int32_t run_rows(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_
         for (size_t c = 0; c < cols_override->size(); ++c) P.in[c] = (*cols_override)[c];
     P.rowlist = rowlist;
     P.n_work = n;
+    P.n_work_dev = n_work_dev;
     P.n_tiles = (uint32_t)((n + (uint64_t)R * NT - 1) / ((uint64_t)R * NT));
     const uint32_t grid = std::min<uint32_t>(P.n_tiles, (uint32_t)(occ * d->prop.multiProcessorCount));
     P.first_row_no = first_row_no;
@@ -1110,13 +1122,16 @@ static int32_t run_rows(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_
         CU(cudaStreamSynchronize(d->stream));
         r->n_out = h_tot[0];
         r->n_exc = h_tot[1];
+        // rows really evaluated (the device-side count when the host only had an estimate): the base of the per-row estimates
+        const uint64_t n_act = n_work_dev ? std::max<uint64_t>(1, std::min<uint64_t>(d->pinned[0], n)) : n;
         si = 0;
         for (size_t c = 0; c < s->out_cols.size(); ++c)
             if (s->out_cols[c].type == TPLX_T_STR) {
                 r->str_bytes[c] = h_tot[2 + si++];
-                s->est_bytes_per_row[c] = (double)r->str_bytes[c] / (double)n;
+                s->est_bytes_per_row[c] = (double)r->str_bytes[c] / (double)n_act;
             }
-        s->est_exc_per_row = (double)r->n_exc / (double)n;
+        s->est_exc_per_row = (double)r->n_exc / (double)n_act;
+        if (h_cnt[1] & 8u) return TPLX_INTERNAL_RETRY;  // more survivors than the estimate everything was sized for
         if (h_cnt[1] == 0) break;
         if (attempt == 2) return fail(TPLX_E_OVERFLOW, "output capacity retry failed");
         for (size_t c = 0; c < s->out_cols.size(); ++c)
@@ -1134,7 +1149,10 @@ static int32_t run_rows(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_
 
 // K1m (mask.cuh): the prefilter stage as a pure map -> bitmaps -> ascending survivor list + exception records.
 // Fills ra like run_rows would for a row-index stage: ra->out[0].data = survivor list, ra->n_out, ra->exc, ra->n_exc.
-static int32_t run_mask(tplx_stage *ps, StageDev *psd, const tplx_block *b, tplx_result *ra) {
+// no_wait: nothing here blocks the host — the survivor list gets the worst-case capacity (n rows), the exception records an
+// estimated one (*cap_exc_out), the counts stay on the device (*totals_dev: [0] survivors, [1] exception rows) and are also copied
+// into the lane's page-locked buffer in stream order; the caller reads them after its own synchronisation.
+static int32_t run_mask(tplx_stage *ps, StageDev *psd, const tplx_block *b, tplx_result *ra, bool no_wait, uint64_t **totals_dev, uint64_t *cap_exc_out) {
     Device *d = ra->dev;
     const uint64_t n = b->n_rows;
     ra->out.assign(1, OutCol{});
@@ -1248,17 +1266,38 @@ static int32_t run_mask(tplx_stage *ps, StageDev *psd, const tplx_block *b, tplx
     mask_count_kernel<<<nb, CMP_NT, 0, d->stream>>>(P.keep_words, P.exc_words, n_words, part);
     mask_scan_kernel<<<1, CMP_NT, 0, d->stream>>>(part, nb, totals);
     CU(cudaGetLastError());
-    uint64_t h_tot[2] = {0, 0};
-    CU(cudaMemcpyAsync(h_tot, totals, 16, cudaMemcpyDeviceToHost, d->stream));
-    CU(cudaStreamSynchronize(d->stream));
-    ra->n_out = h_tot[0];
-    ra->n_exc = h_tot[1];
-    rc = dalloc(ra, &ra->out[0].data, ra->n_out);
-    if (rc) return rc;
-    rc = dalloc(ra, &ra->exc, ra->n_exc);
-    if (rc) return rc;
-    mask_expand_kernel<<<nb, CMP_NT, 0, d->stream>>>(P.keep_words, P.exc_words, n_words, part, ra->out[0].data, P.exc_codes, psd->opids, ra->exc);
-    CU(cudaGetLastError());
+    if (totals_dev) *totals_dev = totals;
+    if (no_wait) {
+        const uint64_t cap_exc = std::max<uint64_t>(4096, (uint64_t)(ps->est_exc_per_row * 1.5 * (double)n) + n / 64);
+        if (cap_exc_out) *cap_exc_out = cap_exc;
+        rc = dalloc(ra, &ra->out[0].data, n);  // worst case: every row survives
+        if (rc) return rc;
+        rc = dalloc(ra, &ra->exc, cap_exc);
+        if (rc) return rc;
+        mask_expand_kernel<<<nb, CMP_NT, 0, d->stream>>>(P.keep_words, P.exc_words, n_words, part, ra->out[0].data, P.exc_codes, psd->opids, ra->exc, cap_exc);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(d->pinned, totals, 16, cudaMemcpyDeviceToHost, d->stream));
+        ra->n_out = ra->n_exc = 0;  // filled in by the caller once the stream has been synchronised
+    } else {
+        uint64_t h_tot[2] = {0, 0};
+        CU(cudaMemcpyAsync(h_tot, totals, 16, cudaMemcpyDeviceToHost, d->stream));
+        CU(cudaStreamSynchronize(d->stream));
+        ra->n_out = h_tot[0];
+        ra->n_exc = h_tot[1];
+        if (cap_exc_out) *cap_exc_out = ra->n_exc;
+        rc = dalloc(ra, &ra->out[0].data, ra->n_out);
+        if (rc) return rc;
+        rc = dalloc(ra, &ra->exc, ra->n_exc);
+        if (rc) return rc;
+        mask_expand_kernel<<<nb, CMP_NT, 0, d->stream>>>(P.keep_words, P.exc_words, n_words, part, ra->out[0].data, P.exc_codes, psd->opids, ra->exc, ra->n_exc);
+        CU(cudaGetLastError());
+    }
+    // kept for a later re-expansion (exception capacity exceeded in no_wait mode)
+    ra->mask_keep = P.keep_words;
+    ra->mask_exc = P.exc_words;
+    ra->mask_codes = P.exc_codes;
+    ra->mask_part = part;
+    ra->mask_words = n_words;
     CU(cudaEventRecord(ra->evk1, d->stream));
     ra->launches += 4;
     return TPLX_OK;
@@ -1290,19 +1329,54 @@ static int32_t run_rows_prefiltered(tplx_stage *s, StageDev *sd, const tplx_bloc
         ~OnExit() { f(); }
     } ra_guard{drop_ra};
     const bool use_mask = !(getenv("TPLX_NO_MASK") && atoi(getenv("TPLX_NO_MASK")));
-    rc = use_mask ? run_mask(ps, psd, b, &ra) : run_rows(ps, psd, b, 0, &ra, nullptr, 0);
+    bool any_mapped = false;
+    for (uint8_t m : b->mapped) any_mapped = any_mapped || m;
+    // Steady state without a host round trip between the two launches: once a block has shown the selectivity, the dense launch of
+    // the next block is sized from it (x1.3 + slack) and reads the real survivor count on the device; the host synchronises once,
+    // at the end. (Blocks with late columns in host memory size their gather from the exact count and keep the round trip.)
+    const bool no_wait = use_mask && !any_mapped && ps->est_surv_ratio >= 0.0 && b->n_rows > 0 && !(getenv("TPLX_SYNC_PREFILTER") && atoi(getenv("TPLX_SYNC_PREFILTER")));
+    uint64_t *totals_dev = nullptr, cap_exc_a = 0;
+    rc = use_mask ? run_mask(ps, psd, b, &ra, no_wait, &totals_dev, &cap_exc_a) : run_rows(ps, psd, b, 0, &ra, nullptr, 0);
     if (rc) { drop_ra(); return rc; }
     // the prefilter's kernel interval is timed lazily (result_info): no host synchronisation for it here
     r->extra_ev.emplace_back(ra.evk0, ra.evk1);
     ra.evk0 = ra.evk1 = nullptr;
     float msa = 0;
+    if (no_wait) {
+        const uint64_t cap = std::min<uint64_t>(b->n_rows, (uint64_t)(ps->est_surv_ratio * 1.3 * (double)b->n_rows) + 65536);
+        rc = run_rows(s, sd, b, first_row_no, r, ra.out[0].data, cap, nullptr, totals_dev);  // synchronises the stream at its end
+        if (rc != TPLX_OK && rc != TPLX_INTERNAL_RETRY) { drop_ra(); return rc; }
+        ra.n_out = d->pinned[0];
+        ra.n_exc = d->pinned[1];
+        ps->est_surv_ratio = (double)ra.n_out / (double)b->n_rows;
+        ps->est_exc_per_row = (double)ra.n_exc / (double)b->n_rows;
+        if (ra.n_exc > cap_exc_a) {  // more prefilter exceptions than estimated: expand them again with the exact capacity
+            int32_t rc2 = dalloc(&ra, &ra.exc, ra.n_exc);
+            if (rc2) { drop_ra(); return rc2; }
+            const uint32_t nb = (ra.mask_words + CMP_NT - 1) / CMP_NT;
+            uint64_t *dummy = nullptr;
+            rc2 = dalloc(&ra, &dummy, ra.n_out + 1);
+            if (rc2) { drop_ra(); return rc2; }
+            mask_expand_kernel<<<nb, CMP_NT, 0, d->stream>>>(ra.mask_keep, ra.mask_exc, ra.mask_words, ra.mask_part, dummy, ra.mask_codes, psd->opids, ra.exc, ra.n_exc);
+            CU(cudaGetLastError());
+        }
+        if (rc == TPLX_INTERNAL_RETRY) {  // more survivors than the estimate: the dense launch again, sized exactly
+            for (void *p : r->owned) cudaFreeAsync(p, d->stream);
+            r->owned.clear();
+            r->launches = 0;
+            rc = run_rows(s, sd, b, first_row_no, r, ra.out[0].data, ra.n_out, nullptr);
+            if (rc) { drop_ra(); return rc; }
+        }
+        r->launches += ra.launches;
+    }
     const uint64_t n_surv = ra.n_out;
+    if (!no_wait) {
+        if (b->n_rows) { ps->est_surv_ratio = (double)n_surv / (double)b->n_rows; if (use_mask) ps->est_exc_per_row = (double)ra.n_exc / (double)b->n_rows; }
+    }
     if (b->n_rows >= (1u << 16) && n_surv * 2 > b->n_rows) s->prefilter_enabled = false;  // not selective: stop using it
     // late columns that still live in host memory: bring over the surviving rows only (gather.cuh)
     std::vector<ColIn> dense_cols;
     float msg = 0;
-    bool any_mapped = false;
-    for (uint8_t m : b->mapped) any_mapped = any_mapped || m;
     if (any_mapped && n_surv) {
         struct EvPair {  // released on every exit path
             cudaEvent_t a = nullptr, b = nullptr;
@@ -1375,18 +1449,23 @@ static int32_t run_rows_prefiltered(tplx_stage *s, StageDev *sd, const tplx_bloc
         CU(cudaEventElapsedTime(&msg, g0, g1));
         r->launches += 2 + 3 * G.n_cols;
     }
-    rc = run_rows(s, sd, b, first_row_no, r, ra.out[0].data, n_surv, dense_cols.empty() ? nullptr : &dense_cols);
-    if (rc) { drop_ra(); return rc; }
+    if (!no_wait) {
+        rc = run_rows(s, sd, b, first_row_no, r, ra.out[0].data, n_surv, dense_cols.empty() ? nullptr : &dense_cols);
+        if (rc) { drop_ra(); return rc; }
+        r->launches += ra.launches;
+    }
     r->kernel_ms_extra = msa + msg;
-    r->launches += ra.launches;
     const uint64_t na = ra.n_exc, nb = r->n_exc;
     if (na) {
+        // stream-ordered copies: the lane's stream is non-blocking, so a plain cudaMemcpy would not wait for the kernels that wrote
+        // these records (with no surviving row the dense launch — and its synchronisation — never happens)
         std::vector<tplx_exception_rec> ea(na), eb(nb), merged;
-        CU(cudaMemcpy(ea.data(), ra.exc, na * sizeof(tplx_exception_rec), cudaMemcpyDeviceToHost));
-        if (nb) CU(cudaMemcpy(eb.data(), r->exc, nb * sizeof(tplx_exception_rec), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpyAsync(ea.data(), ra.exc, na * sizeof(tplx_exception_rec), cudaMemcpyDeviceToHost, d->stream));
+        if (nb) CU(cudaMemcpyAsync(eb.data(), r->exc, nb * sizeof(tplx_exception_rec), cudaMemcpyDeviceToHost, d->stream));
         // input row index of every output row (hidden last column), ascending
         std::vector<int64_t> out_rows(r->n_out);
-        if (r->n_out) CU(cudaMemcpy(out_rows.data(), r->out.back().data, r->n_out * 8, cudaMemcpyDeviceToHost));
+        if (r->n_out) CU(cudaMemcpyAsync(out_rows.data(), r->out.back().data, r->n_out * 8, cudaMemcpyDeviceToHost, d->stream));
+        CU(cudaStreamSynchronize(d->stream));
         // B numbered its exceptions within its own stream: rows written before + index among B's exceptions
         for (uint64_t i = 0; i < nb; ++i) eb[i].row_no = eb[i].row_no - first_row_no - (int64_t)i;  // = rows written before
         for (uint64_t i = 0; i < na; ++i)
@@ -1398,7 +1477,8 @@ static int32_t run_rows_prefiltered(tplx_stage *s, StageDev *sd, const tplx_bloc
         tplx_exception_rec *dm = nullptr;
         rc = dalloc(r, &dm, merged.size());
         if (rc) { drop_ra(); return rc; }
-        CU(cudaMemcpy(dm, merged.data(), merged.size() * sizeof(tplx_exception_rec), cudaMemcpyHostToDevice));
+        CU(cudaMemcpyAsync(dm, merged.data(), merged.size() * sizeof(tplx_exception_rec), cudaMemcpyHostToDevice, d->stream));
+        CU(cudaStreamSynchronize(d->stream));  // `merged` is a local
         r->exc = dm;
         r->n_exc = merged.size();
     }
