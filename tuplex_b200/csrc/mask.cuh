@@ -144,8 +144,9 @@ __device__ __forceinline__ void scan_eval(const MaskParams &P, const ColIn *__re
 
 // The parameter block travels by value in the kernel's constant bank (__grid_constant__): every P.field below is a constant-bank
 // operand instead of a global load through a pointer (terms, column table, offsets — read in the per-row loops).
-template <bool SCAN>
-__global__ void __launch_bounds__(NT) stage_mask_kernel(const __grid_constant__ MaskParams P) {
+// MINB: resident CTAs per SM the register allocation must allow (4 = 64 registers, 5 = 48, 6 = 40).
+template <bool SCAN, int MINB = 4>
+__global__ void __launch_bounds__(NT, MINB) stage_mask_kernel(const __grid_constant__ MaskParams P) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t MR = P.MR, TR = 32 * MR, ns = P.n_staged;

@@ -110,7 +110,9 @@ extern "C" int32_t tplx_gpu_init(const int32_t *devices, int32_t n) {
         CU(cudaFuncSetAttribute(stage_agg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d->smem_optin));
         CU(cudaFuncSetAttribute(stage_hash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d->smem_optin));
         CU(cudaFuncSetAttribute(stage_mask_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, d->smem_optin));
-        CU(cudaFuncSetAttribute(stage_mask_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, d->smem_optin));
+        CU(cudaFuncSetAttribute(stage_mask_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, d->smem_optin));
+        CU(cudaFuncSetAttribute(stage_mask_kernel<true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, d->smem_optin));
+        CU(cudaFuncSetAttribute(stage_mask_kernel<true, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, d->smem_optin));
         // extra execution lanes on the same GPU (chain d -> alt -> alt ...): TPLX_LANES lanes in all. Measured on the
         // Zillow bench: 2 lanes 6.18 G rows/s resident / 653 M rows/s end to end; 3 lanes 6.28 G / 625 M; 4 lanes as 3.
         // The end-to-end number is the headline, so the default stays 2.
@@ -1152,6 +1154,9 @@ static int32_t run_rows(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_
 // no_wait: nothing here blocks the host — the survivor list gets the worst-case capacity (n rows), the exception records an
 // estimated one (*cap_exc_out), the counts stay on the device (*totals_dev: [0] survivors, [1] exception rows) and are also copied
 // into the lane's page-locked buffer in stream order; the caller reads them after its own synchronisation.
+#ifndef TPLX_MASK_MINB_DEFAULT
+#define TPLX_MASK_MINB_DEFAULT 4
+#endif
 static int32_t run_mask(tplx_stage *ps, StageDev *psd, const tplx_block *b, tplx_result *ra, bool no_wait, uint64_t **totals_dev, uint64_t *cap_exc_out) {
     Device *d = ra->dev;
     const uint64_t n = b->n_rows;
@@ -1237,7 +1242,11 @@ static int32_t run_mask(tplx_stage *ps, StageDev *psd, const tplx_block *b, tplx
     }
     if (smem_total > (uint32_t)d->smem_optin) return fail(TPLX_E_UNSUPPORTED, "mask stage needs more shared memory than one SM has");
     int occ = 0;
-    if (scan) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stage_mask_kernel<true>, NT, smem_total));
+    // closed-form kernel: register budget per thread traded for resident warps (TPLX_MASK_MINB = 4 | 5 | 6 CTAs per SM)
+    const int minb = getenv("TPLX_MASK_MINB") ? atoi(getenv("TPLX_MASK_MINB")) : TPLX_MASK_MINB_DEFAULT;
+    if (scan && minb == 6) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stage_mask_kernel<true, 6>, NT, smem_total));
+    else if (scan && minb == 5) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stage_mask_kernel<true, 5>, NT, smem_total));
+    else if (scan) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stage_mask_kernel<true, 4>, NT, smem_total));
     else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stage_mask_kernel<false>, NT, smem_total));
     if (occ < 1) return fail(TPLX_E_UNSUPPORTED, "mask kernel cannot be resident");
     // TPLX_MASK_OCC caps the resident CTAs per SM: leaving registers free lets the dense launch of another block (other lane) co-reside
@@ -1260,7 +1269,9 @@ static int32_t run_mask(tplx_stage *ps, StageDev *psd, const tplx_block *b, tplx
     if (rc) return rc;
     rc = dalloc(ra, &totals, 2);
     if (rc) return rc;
-    if (scan) stage_mask_kernel<true><<<grid, NT, smem_total, d->stream>>>(P);
+    if (scan && minb == 6) stage_mask_kernel<true, 6><<<grid, NT, smem_total, d->stream>>>(P);
+    else if (scan && minb == 5) stage_mask_kernel<true, 5><<<grid, NT, smem_total, d->stream>>>(P);
+    else if (scan) stage_mask_kernel<true, 4><<<grid, NT, smem_total, d->stream>>>(P);
     else stage_mask_kernel<false><<<grid, NT, smem_total, d->stream>>>(P);
     CU(cudaGetLastError());
     mask_count_kernel<<<nb, CMP_NT, 0, d->stream>>>(P.keep_words, P.exc_words, n_words, part);
