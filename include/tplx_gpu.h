@@ -91,6 +91,22 @@ int32_t tplx_gpu_device_info(int32_t device, char *name_buf, int32_t buf_len, in
  * (TransformStage.cc:763-914): validates the program and sizes launch configuration. */
 int32_t tplx_gpu_stage_create(const void *desc, uint64_t desc_bytes, tplx_stage **out);
 int32_t tplx_gpu_stage_destroy(tplx_stage *stage);
+/* Diagnostic (needs no device): the micro-op program the fixed-width row kernel (K1v) would run for this stage — the planner's
+ * accumulator chains, fused compare/filter and dense slot numbers — so that the plan can be checked against the op program on
+ * the host. n_uops = 0: the stage is not eligible for K1v. out may be NULL (sizes only); out_slots gets the dense slot of every
+ * output column (cap_out entries at most). The reference has no counterpart (LLVM does this inside the JIT, LLVMOptimizer.cc). */
+typedef struct tplx_vec_uop {
+    uint32_t vop;    /* micro-op (tuplex_b200/csrc/vecvm.cuh: VOp) */
+    uint32_t xflags; /* planner flags (VFlag): 1 a<-acc, 2 b<-acc, 4 result not stored, 8 filters, 16 a masked by imm2 */
+    uint8_t flags;   /* tplx_instr.flags (constant-operand bits) */
+    uint8_t pad0;
+    uint16_t opidx;
+    uint16_t dst, a, b, c, guard; /* dense slots, TPLX_NOSLOT = none / not in the register file */
+    uint16_t pad1;
+    int64_t imm, imm2;
+} tplx_vec_uop;
+int32_t tplx_gpu_stage_vec_plan(const tplx_stage *stage, tplx_vec_uop *out, uint32_t cap, uint32_t *n_uops, uint32_t *n_slots,
+                                uint16_t *out_slots, uint32_t cap_out);
 
 /* ---- input blocks ----------------------------------------------------------------------- */
 /* Upload a host column block to `device` (pinned or pageable host memory). */

@@ -77,6 +77,7 @@ def lib():
         "tplx_gpu_device_info": ([i32, ct.c_char_p, i32, P(i32), P(u64)], i32),
         "tplx_gpu_stage_create": ([vp, u64, P(vp)], i32),
         "tplx_gpu_stage_destroy": ([vp], i32),
+        "tplx_gpu_stage_vec_plan": ([vp, vp, u32, P(u32), P(u32), vp, u32], i32),
         "tplx_gpu_block_upload": ([i32, P(CColumn), u32, u64, P(vp)], i32),
         "tplx_gpu_block_wrap_device": ([i32, P(CColumn), u32, u64, P(vp)], i32),
         "tplx_gpu_block_from_partitions": ([i32, P(vp), P(u64), u32, P(ct.c_uint8), u32, P(vp)], i32),
@@ -265,6 +266,24 @@ class Stage:
         self._h = ct.c_void_p()
         buf = ct.create_string_buffer(blob, len(blob))
         _check(lib().tplx_gpu_stage_create(buf, len(blob), ct.byref(self._h)), "tplx_gpu_stage_create")
+
+    def vec_plan(self):
+        """(micro-ops, n_slots, output slots) of the fixed-width row kernel for this stage, or None when it is not eligible
+        (tplx_gpu_stage_vec_plan; no device needed). Micro-ops are dicts with the fields of tplx_vec_uop."""
+        n, ns = ct.c_uint32(), ct.c_uint32()
+        _check(lib().tplx_gpu_stage_vec_plan(self._h, None, 0, ct.byref(n), ct.byref(ns), None, 0), "tplx_gpu_stage_vec_plan")
+        if n.value == 0:
+            return None
+        dt = np.dtype([("vop", "<u4"), ("xflags", "<u4"), ("flags", "u1"), ("pad0", "u1"), ("opidx", "<u2"), ("dst", "<u2"), ("a", "<u2"),
+                       ("b", "<u2"), ("c", "<u2"), ("guard", "<u2"), ("pad1", "<u2"), ("imm", "<i8"), ("imm2", "<i8")])
+        assert dt.itemsize == 40
+        buf = np.zeros(n.value, dt)
+        n_out = len(self.program.out_cols)
+        outs = np.zeros(max(n_out, 1), np.uint16)
+        _check(lib().tplx_gpu_stage_vec_plan(self._h, buf.ctypes.data, n.value, ct.byref(n), ct.byref(ns), outs.ctypes.data, n_out),
+               "tplx_gpu_stage_vec_plan")
+        uops = [{k: int(r[k]) for k in dt.names if not k.startswith("pad")} for r in buf]
+        return uops, ns.value, [int(x) for x in outs[:n_out]]
 
     def close(self):
         if self._h:

@@ -45,7 +45,7 @@ struct KParams {
     uint32_t n_instr, pad_split, n_slots, n_in, n_out, n_str_out, n_accs, R, n_tiles, scratch_per_thread;
     uint32_t K;            // scan vector width = 2 + n_str_out
     uint32_t smem_regs_off, smem_stage_off, smem_misc_off, smem_cols_off;
-    uint32_t smem_stash_off;  // per string output column: NT byte offsets (one per thread) + NT/32 warp totals
+    uint32_t smem_stash_off;  // per string output column: NT/32 warp totals of the byte scan
     uint32_t inplace;         // 1: one row per thread and no staging area — outputs are read from the register file (slot s of local row lr = regs[s][lr])
     uint64_t cap_rows, cap_exc;
     const DInstr *prog;    // pre-decoded program (device format)
@@ -129,15 +129,16 @@ __device__ __forceinline__ bool bit_test(const uint32_t *bits, uint32_t lr) {
 // staged output values (s_stage + out[c].stage_off, indexed by local row) are complete and a __syncthreads() has been passed.
 struct TileSmem {
     uint8_t *s_stage, *s_regs;  // staging area (or the register file base when P.inplace), this thread's register column
-    uint32_t *s_stash;          // [n_str_out][NT] byte offsets, then [n_str_out][NT/32] warp totals
+    uint32_t *s_stash;          // [n_str_out][NT/32] warp totals of the string byte scan
     uint32_t *keep_bits, *exc_bits, *keep_pre, *exc_pre, *exc_stage;
-    uint64_t *s_vals, *s_excl, *s_warp;
+    uint32_t exc_stride;        // exc_stage[lr * exc_stride]: 1, or 2 when the codes live in slot 0 of the raising row (in place)
+    uint64_t *s_vals, *s_excl;
 };
 __device__ __forceinline__ void rows_tile_finish(const KParams &P, const TileSmem &S, uint32_t tile, uint64_t base, uint32_t R, uint32_t T,
                                                  uint32_t W, uint32_t K, uint32_t state_stride, uint32_t n_tiles) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint8_t *s_stage = S.s_stage;
-    uint32_t *s_stash = S.s_stash, *s_wtot = S.s_stash + P.n_str_out * NT;
+    uint32_t *s_wtot = S.s_stash;
     // staged value of output column oc at local row lr: either the staging area ([lr] / [2 lr], [2 lr + 1]) or, in place, the register
     // file itself (slot-major: regs[slot][lr])
     auto fixed_at = [&](const OutCol &oc, uint32_t lr) -> uint64_t {
@@ -153,7 +154,7 @@ __device__ __forceinline__ void rows_tile_finish(const KParams &P, const TileSme
                          : reinterpret_cast<const uint64_t *>(s_stage + oc.stage_off)[2 * (size_t)lr + 1];
     };
     uint32_t *keep_bits = S.keep_bits, *exc_bits = S.exc_bits, *keep_pre = S.keep_pre, *exc_pre = S.exc_pre, *exc_stage = S.exc_stage;
-    uint64_t *s_vals = S.s_vals, *s_excl = S.s_excl, *s_warp = S.s_warp;
+    uint64_t *s_vals = S.s_vals, *s_excl = S.s_excl;
     // ---- per-tile counts: word prefixes (warp 0), string byte totals ----------------------
     if (warp == 0) {
         uint32_t ck = 0, ce = 0;
@@ -181,37 +182,35 @@ __device__ __forceinline__ void rows_tile_finish(const KParams &P, const TileSme
     const bool any_keep = s_vals[0] != 0;
     if (!any_keep && tid < MAX_SCAN - 2) s_vals[2 + tid] = 0;
     // string bytes per output column: thread owns local rows [tid*R, tid*R+R) (consecutive rows per thread, so that one block scan
-    // yields in-order byte offsets). All columns are scanned between ONE pair of barriers: warp scans first, warp totals next.
+    // yields in-order byte offsets). All columns are scanned between ONE pair of barriers; only the warp totals go through shared
+    // memory — a thread's own exclusive offset is recomputed (one more warp scan) when the column is written.
+    auto warp_scan_bytes = [&](const OutCol &oc, uint32_t &mine) -> uint32_t {  // inclusive scan of the thread's kept bytes over the warp
+        mine = 0;
+        for (uint32_t j = 0; j < R; ++j) {
+            const uint32_t lr = tid * R + j;
+            if (bit_test(keep_bits, lr)) mine += (uint32_t)str_meta_at(oc, lr);
+        }
+        uint32_t inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+            if (lane >= (uint32_t)o) inc += a;
+        }
+        return inc;
+    };
     if (any_keep) {
         for (uint32_t c = 0; c < P.n_out; ++c) {
             const OutCol &oc = P.out[c];
             if (oc.strk < 0) continue;
-            uint32_t mine = 0;
-            for (uint32_t j = 0; j < R; ++j) {
-                const uint32_t lr = tid * R + j;
-                if (bit_test(keep_bits, lr)) mine += (uint32_t)str_meta_at(oc, lr);
-            }
-            uint32_t inc = mine;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-                if (lane >= (uint32_t)o) inc += a;
-            }
-            s_stash[(uint32_t)oc.strk * NT + tid] = inc - mine;  // exclusive inside the warp
+            uint32_t mine;
+            const uint32_t inc = warp_scan_bytes(oc, mine);
             if (lane == 31) s_wtot[(uint32_t)oc.strk * (NT / 32) + warp] = inc;
         }
         __syncthreads();
-        for (uint32_t c = 0; c < P.n_out; ++c) {
-            const OutCol &oc = P.out[c];
-            if (oc.strk < 0) continue;
-            uint32_t wofs = 0, tot = 0;
-            for (uint32_t w = 0; w < NT / 32; ++w) {
-                const uint32_t v = s_wtot[(uint32_t)oc.strk * (NT / 32) + w];
-                if (w < warp) wofs += v;
-                tot += v;
-            }
-            s_stash[(uint32_t)oc.strk * NT + tid] += wofs;  // this thread's exclusive byte offset inside the tile
-            if (tid == 0) s_vals[2 + oc.strk] = tot;
+        if (tid < P.n_str_out) {
+            uint32_t tot = 0;
+            for (uint32_t w = 0; w < NT / 32; ++w) tot += s_wtot[tid * (NT / 32) + w];
+            s_vals[2 + tid] = tot;
         }
     }
     __syncthreads();
@@ -280,7 +279,10 @@ __device__ __forceinline__ void rows_tile_finish(const KParams &P, const TileSme
                     if (tid == 0) atomicOr(&P.counters[1], 2u);
                     continue;
                 }
-                uint64_t off = pre_b + s_stash[(uint32_t)oc.strk * NT + tid];
+                uint32_t mine, wofs = 0;
+                const uint32_t inc = warp_scan_bytes(oc, mine);
+                for (uint32_t w = 0; w < warp; ++w) wofs += s_wtot[(uint32_t)oc.strk * (NT / 32) + w];
+                uint64_t off = pre_b + wofs + (inc - mine);  // this thread's exclusive byte offset
                 for (uint32_t j = 0; j < R; ++j) {
                     const uint32_t lr = tid * R + j;
                     if (!bit_test(keep_bits, lr)) continue;
@@ -310,7 +312,7 @@ __device__ __forceinline__ void rows_tile_finish(const KParams &P, const TileSme
                 rec.row = (int64_t)(P.rowlist ? P.rowlist[base + lr] : base + lr);
                 // _outputRowCounter semantics: rows written + exceptions so far (TransformTask.cc:764,885)
                 rec.row_no = P.first_row_no + (int64_t)(pre_keep + pre_exc + kk + ke);
-                const uint32_t es = exc_stage[lr];
+                const uint32_t es = exc_stage[lr * S.exc_stride];
                 rec.code = es & 0xFFFF;
                 rec.op_id = P.opids[es >> 16];
                 P.exc[pre_exc + ke] = rec;
@@ -338,11 +340,13 @@ __global__ void __launch_bounds__(NT) stage_rows_kernel(const __grid_constant__ 
     uint32_t *exc_bits = keep_bits + W;
     uint32_t *keep_pre = exc_bits + W;
     uint32_t *exc_pre = keep_pre + W + 1;
-    uint32_t *exc_stage = exc_pre + W + 1;
-    uint64_t *s_vals = reinterpret_cast<uint64_t *>(exc_stage + T);  // K tile values
+    // code | operator of a raising row: its own array, or (in place) slot 0 of that row in the register file — the row is not kept,
+    // nobody reads its values any more
+    uint32_t *exc_stage = P.inplace ? reinterpret_cast<uint32_t *>(smem + P.smem_regs_off) : exc_pre + W + 1;
+    const uint32_t exc_stride = P.inplace ? 2u : 1u;
+    uint64_t *s_vals = reinterpret_cast<uint64_t *>(exc_pre + W + 1 + (P.inplace ? 0u : T));  // K tile values
     uint64_t *s_excl = s_vals + MAX_SCAN;                                                    // K exclusive prefixes
-    uint64_t *s_warp = s_excl + MAX_SCAN;                                                    // NT/32 scan scratch
-    uint32_t *s_ctl = reinterpret_cast<uint32_t *>(s_warp + NT / 32 + 1);                     // [0] tile
+    uint32_t *s_ctl = reinterpret_cast<uint32_t *>(s_excl + MAX_SCAN);                        // [0] tile
 
     // one-time: program + column table into shared memory
     for (uint32_t i = tid; i < P.n_instr * (sizeof(DInstr) / 16); i += NT)
@@ -410,13 +414,13 @@ __global__ void __launch_bounds__(NT) stage_rows_kernel(const __grid_constant__ 
             if (lane == 0) { keep_bits[lr >> 5] = kb; exc_bits[lr >> 5] = eb; }
             if (t.alive && !P.inplace) stage_row(lr);
             if (exc) {
-                exc_stage[lr] = t.exc_code | (t.exc_op << 16);
+                exc_stage[lr * exc_stride] = t.exc_code | (t.exc_op << 16);
 
             }
         }
         __syncthreads();
 
-        rows_tile_finish(P, TileSmem{s_stage, s_regs, s_stash, keep_bits, exc_bits, keep_pre, exc_pre, exc_stage, s_vals, s_excl, s_warp}, tile, base,
+        rows_tile_finish(P, TileSmem{s_stage, s_regs, s_stash, keep_bits, exc_bits, keep_pre, exc_pre, exc_stage, exc_stride, s_vals, s_excl}, tile, base,
                          R, T, W, K, state_stride, n_tiles);
     }
 }

@@ -177,6 +177,188 @@ extern "C" int32_t tplx_gpu_device_info(int32_t device, char *name_buf, int32_t 
 // ---------------------------------------------------------------------------------------------
 // stage
 // ---------------------------------------------------------------------------------------------
+// ---- K1v planner: IR ops of a fixed-width stage -> vector micro-ops (vecvm.cuh) --------------------------------------------------
+// Straight-line liveness over slots decides what never has to touch the shared-memory register file:
+//   * x % 2^k feeding only an integer compare        -> the compare masks its operand (VX_A_MASK), the modulo disappears;
+//   * a boolean op feeding only the next FILTER       -> the op filters (VX_FILTER), the FILTER disappears;
+//   * producer immediately followed by its consumer   -> the operand comes from the accumulator (VX_A_ACC / VX_B_ACC);
+//   * a result that no later micro-op reads from its slot and that is no output column -> not stored (VX_NOSTORE);
+//   * the slots still in use are renumbered densely (fewer slots = more resident CTAs).
+// Only unguarded ops take part (a guarded op merges with the old destination and may be skipped by the warp); ops that can
+// raise keep operands and result in slots (they run row by row). Semantics per row are untouched: the same single integer /
+// IEEE operations in the same order.
+struct VecIns {
+    tplx_instr in;
+    uint32_t vop = V_NOP, xf = 0;
+};
+struct VecPlan {
+    std::vector<VecIns> ins;
+    std::vector<uint16_t> slot_map;  // IR slot -> dense slot (TPLX_NOSLOT = unused)
+    uint32_t n_slots = 1;
+};
+static bool vop_raising(uint32_t v) { return v == V_IFLOORDIV || v == V_IMOD || v == V_FDIV || v == V_FMOD || v == V_FFLOORDIV; }
+static bool vop_pred(uint32_t v) { return v == V_BAND || v == V_BOR || v == V_BNOT || (v >= V_ICMP_EQ && v <= V_FCMP_GE); }
+static bool vop_icmp(uint32_t v) { return v >= V_ICMP_EQ && v <= V_ICMP_GE; }
+// operands read: bit 0 = a, bit 1 = b, bit 2 = c (before constant flags)
+static uint32_t vop_reads(uint32_t v) {
+    switch (v) {
+        case V_NOP: case V_LDCOL: case V_LDI: case V_LDROW: case V_RAISE: return 0;
+        case V_MOV: case V_INEG: case V_IABS: case V_FNEG: case V_FABS: case V_I2F: case V_F2I: case V_BNOT: case V_ISHRK: case V_IANDK: case V_FILTER: return 1;
+        case V_SEL: return 7;
+        default: return 3;
+    }
+}
+static bool vop_has_dst(uint32_t v) { return v != V_NOP && v != V_FILTER && v != V_RAISE; }
+static VecPlan vec_plan(const std::vector<tplx_instr> &prog, const std::vector<tplx_outcol> &outs, uint32_t n_slots_ir) {
+    VecPlan pl;
+    for (const tplx_instr &in : prog) {
+        VecIns v;
+        v.in = in;
+        switch (in.op) {
+            case TPLX_OP_LDCOL: v.vop = V_LDCOL; break;
+            case TPLX_OP_LDI: v.vop = V_LDI; break;
+            case TPLX_OP_LDROW: v.vop = V_LDROW; break;
+            case TPLX_OP_MOV: v.vop = V_MOV; break;
+            case TPLX_OP_SEL: v.vop = V_SEL; break;
+            case TPLX_OP_IADD: v.vop = V_IADD; break;
+            case TPLX_OP_ISUB: v.vop = V_ISUB; break;
+            case TPLX_OP_IMUL: v.vop = V_IMUL; break;
+            case TPLX_OP_INEG: v.vop = V_INEG; break;
+            case TPLX_OP_IAND: v.vop = V_IAND; break;
+            case TPLX_OP_IOR: v.vop = V_IOR; break;
+            case TPLX_OP_IXOR: v.vop = V_IXOR; break;
+            case TPLX_OP_ISHL: v.vop = V_ISHL; break;
+            case TPLX_OP_ISHR: v.vop = V_ISHR; break;
+            case TPLX_OP_IABS: v.vop = V_IABS; break;
+            case TPLX_OP_FADD: v.vop = V_FADD; break;
+            case TPLX_OP_FSUB: v.vop = V_FSUB; break;
+            case TPLX_OP_FMUL: v.vop = V_FMUL; break;
+            case TPLX_OP_FNEG: v.vop = V_FNEG; break;
+            case TPLX_OP_FABS: v.vop = V_FABS; break;
+            case TPLX_OP_I2F: v.vop = V_I2F; break;
+            case TPLX_OP_F2I: v.vop = V_F2I; break;
+            case TPLX_OP_BAND: v.vop = V_BAND; break;
+            case TPLX_OP_BOR: v.vop = V_BOR; break;
+            case TPLX_OP_BNOT: v.vop = V_BNOT; break;
+            case TPLX_OP_ICMP: v.vop = V_ICMP_EQ + std::min<uint32_t>(in.flags & 7, 5); break;
+            case TPLX_OP_FCMP: v.vop = V_FCMP_EQ + std::min<uint32_t>(in.flags & 7, 5); break;
+            case TPLX_OP_IFLOORDIV: v.vop = V_IFLOORDIV; break;
+            case TPLX_OP_IMOD: v.vop = V_IMOD; break;
+            case TPLX_OP_FDIV: v.vop = V_FDIV; break;
+            case TPLX_OP_FMOD: v.vop = V_FMOD; break;
+            case TPLX_OP_FFLOORDIV: v.vop = V_FFLOORDIV; break;
+            case TPLX_OP_FILTER: v.vop = V_FILTER; break;
+            case TPLX_OP_RAISE: v.vop = V_RAISE; break;
+            default: v.vop = V_NOP; break;
+        }
+        if (v.vop == V_NOP) continue;
+        if ((v.vop == V_IMOD || v.vop == V_IFLOORDIV) && (in.flags & TPLX_F_B_CONST) && in.imm > 0 && (in.imm & (in.imm - 1)) == 0) {
+            // constant power-of-two divisor: x % 2^k == x & (2^k - 1), x // 2^k == x >> k under floored semantics; cannot raise
+            int k = 0;
+            while ((1ll << k) != in.imm) ++k;
+            v.in.imm = v.vop == V_IMOD ? in.imm - 1 : k;
+            v.vop = v.vop == V_IMOD ? V_IANDK : V_ISHRK;
+        }
+        pl.ins.push_back(v);
+    }
+    auto unguarded = [](const VecIns &v) { return v.in.guard == TPLX_NOSLOT; };
+    auto reads_slot = [](const VecIns &v, int which) -> int {  // slot read through operand `which` from the register file, or -1
+        const uint32_t m = vop_reads(v.vop);
+        if (!((m >> which) & 1u)) return -1;
+        const uint32_t cf = which == 0 ? TPLX_F_A_CONST : (which == 1 ? TPLX_F_B_CONST : TPLX_F_C_CONST);
+        if (v.in.flags & cf) return -1;
+        if (which == 0 && (v.xf & VX_A_ACC)) return -1;
+        if (which == 1 && (v.xf & VX_B_ACC)) return -1;
+        const uint16_t sl = which == 0 ? v.in.a : (which == 1 ? v.in.b : v.in.c);
+        return sl == TPLX_NOSLOT ? -1 : (int)sl;
+    };
+    // is the value instruction i left in slot d read from the slot after position `from` (or an output)?
+    auto slot_live_after = [&](size_t from, uint16_t d) {
+        for (size_t k = from; k < pl.ins.size(); ++k) {
+            const VecIns &v = pl.ins[k];
+            for (int w = 0; w < 3; ++w)
+                if (reads_slot(v, w) == (int)d) return true;
+            if (v.in.guard == d) return true;
+            if (vop_has_dst(v.vop) && v.in.dst == d) {
+                if (unguarded(v) && !vop_raising(v.vop)) return false;  // fully overwritten (a raising op writes its active rows only)
+                return true;                                            // partial write: the old value shows through
+            }
+        }
+        for (const tplx_outcol &oc : outs)
+            if (oc.slot == d) return true;
+        return false;
+    };
+    // (a) x % 2^k feeding only the next integer compare
+    for (size_t i = 0; i + 1 < pl.ins.size(); ++i) {
+        VecIns &m = pl.ins[i], &c = pl.ins[i + 1];
+        if (m.vop != V_IANDK || !unguarded(m) || !unguarded(c) || !vop_icmp(c.vop) || (m.in.flags & TPLX_F_A_CONST) || (c.in.flags & TPLX_F_A_CONST)) continue;
+        if (c.in.a != m.in.dst || (!(c.in.flags & TPLX_F_B_CONST) && c.in.b == m.in.dst)) continue;
+        if (c.in.dst != m.in.dst && slot_live_after(i + 2, m.in.dst)) continue;
+        c.in.a = m.in.a;
+        c.in.imm2 = m.in.imm;
+        c.xf |= VX_A_MASK;
+        pl.ins.erase(pl.ins.begin() + (long)i);
+    }
+    // (b) boolean op feeding only the next FILTER
+    for (size_t i = 0; i + 1 < pl.ins.size(); ++i) {
+        VecIns &c = pl.ins[i], &f = pl.ins[i + 1];
+        if (!vop_pred(c.vop) || f.vop != V_FILTER || !unguarded(c) || !unguarded(f) || (f.in.flags & TPLX_F_A_CONST) || f.in.a != c.in.dst) continue;
+        c.xf |= VX_FILTER;
+        pl.ins.erase(pl.ins.begin() + (long)i + 1);
+    }
+    // (c) accumulator operands
+    for (size_t i = 0; i + 1 < pl.ins.size(); ++i) {
+        const VecIns &pr = pl.ins[i];
+        VecIns &co = pl.ins[i + 1];
+        if (!unguarded(pr) || !unguarded(co) || !vop_has_dst(pr.vop) || vop_raising(pr.vop) || vop_raising(co.vop) || co.vop == V_RAISE) continue;
+        const uint32_t m = vop_reads(co.vop);
+        if ((m & 1u) && !(co.in.flags & TPLX_F_A_CONST) && co.in.a == pr.in.dst) co.xf |= VX_A_ACC;
+        if ((m & 2u) && !(co.in.flags & TPLX_F_B_CONST) && co.in.b == pr.in.dst) co.xf |= VX_B_ACC;
+    }
+    // (d) results nobody reads from their slot
+    for (size_t i = 0; i < pl.ins.size(); ++i) {
+        VecIns &v = pl.ins[i];
+        if (!unguarded(v) || !vop_has_dst(v.vop) || vop_raising(v.vop) || v.in.dst == TPLX_NOSLOT) continue;
+        if (!slot_live_after(i + 1, v.in.dst)) v.xf |= VX_NOSTORE;
+    }
+    // (e) dense slot numbers for what is still touched
+    pl.slot_map.assign(std::max<uint32_t>(n_slots_ir, 1), TPLX_NOSLOT);
+    uint32_t next = 0;
+    auto touch = [&](uint16_t sl) {
+        if (sl != TPLX_NOSLOT && sl < pl.slot_map.size() && pl.slot_map[sl] == TPLX_NOSLOT) pl.slot_map[sl] = (uint16_t)next++;
+    };
+    for (const VecIns &v : pl.ins) {
+        for (int w = 0; w < 3; ++w) {
+            const int sl = reads_slot(v, w);
+            if (sl >= 0) touch((uint16_t)sl);
+        }
+        touch(v.in.guard);
+        if (vop_has_dst(v.vop) && !(v.xf & VX_NOSTORE)) touch(v.in.dst);
+    }
+    for (const tplx_outcol &oc : outs) touch(oc.slot);
+    pl.n_slots = std::max<uint32_t>(next, 1);
+    return pl;
+}
+// device format of the plan for tiles of T rows (slot stride T * 8 bytes)
+static std::vector<DInstr> vec_encode(const VecPlan &pl, uint32_t T) {
+    std::vector<DInstr> out;
+    auto off = [&](uint16_t sl) { return sl == TPLX_NOSLOT || pl.slot_map[sl] == TPLX_NOSLOT ? NOOFF : (uint32_t)pl.slot_map[sl] * T * 8u; };
+    for (const VecIns &v : pl.ins) {
+        DInstr d{};
+        d.op_flags = v.vop | ((uint32_t)v.in.flags << 8) | ((uint32_t)v.in.opidx << 16);
+        d.dst = (v.xf & VX_NOSTORE) ? NOOFF : off(v.in.dst);
+        d.a = off(v.in.a);
+        d.b = off(v.in.b);
+        d.c = off(v.in.c);
+        d.guard = off(v.in.guard);
+        d.pad0 = v.xf;
+        d.imm = v.in.imm;
+        d.imm2 = v.in.imm2;
+        out.push_back(d);
+    }
+    return out;
+}
+
 struct StageDev {
     Device *dev = nullptr;
     DInstr *prog = nullptr;  // pre-decoded program
@@ -206,6 +388,7 @@ struct tplx_stage {
     double est_surv_ratio = -1.0;     // survivors / rows of the last block (prefilter stage): sizes the next block's dense launch
     uint32_t hidden = 0;              // trailing executor-internal output columns
     bool vec_ok = false;              // fixed-width values and vector-VM ops only: eligible for K1v (vecvm.cuh)
+    VecPlan vplan;                    // K1v micro-op program (accumulator chains, fused compare/filter), built when vec_ok
     std::vector<tplx_scan_term> scan; // string-scan hint (closed form of a pure filter chain), empty = none
     bool has_fused = false;           // closed-form scan-aggregate hint present and valid
     FusedParams fused{};
@@ -392,13 +575,14 @@ extern "C" int32_t tplx_gpu_stage_create(const void *desc, uint64_t desc_bytes, 
         }
         if ((in.op == TPLX_OP_SEL || in.op == TPLX_OP_MOV) && (in.flags & 3) != 1) s->vec_ok = false;
     }
+    if (s->vec_ok) s->vplan = vec_plan(s->instrs, s->out_cols, h.n_slots);
     *out = s;
     return TPLX_OK;
 }
 
 // tplx_instr -> device format: slot numbers become byte offsets into a thread's register column
-// (slot_bytes = NT * 8 for the scalar VM; T * 8 for the vector VM, which also gets strength-reduced micro-ops)
-static std::vector<DInstr> predecode(const std::vector<tplx_instr> &ins, uint32_t slot_bytes = NT * 8, bool vec = false) {
+// (the vector kernel has its own planner: vec_plan / vec_encode)
+static std::vector<DInstr> predecode(const std::vector<tplx_instr> &ins, uint32_t slot_bytes = NT * 8) {
     std::vector<DInstr> out(ins.size());
     auto off = [slot_bytes](uint16_t slot) { return slot == TPLX_NOSLOT ? NOOFF : (uint32_t)slot * slot_bytes; };
     for (size_t i = 0; i < ins.size(); ++i) {
@@ -412,14 +596,6 @@ static std::vector<DInstr> predecode(const std::vector<tplx_instr> &ins, uint32_
         d.guard = off(in.guard);
         d.imm = in.imm;
         d.imm2 = in.imm2;
-        if (vec && (in.op == TPLX_OP_IMOD || in.op == TPLX_OP_IFLOORDIV) && (in.flags & TPLX_F_B_CONST) && in.imm > 0 && (in.imm & (in.imm - 1)) == 0) {
-            // constant power-of-two divisor: x % 2^k == x & (2^k - 1), x // 2^k == x >> k under floored semantics; cannot raise
-            int k = 0;
-            while ((1ll << k) != in.imm) ++k;
-            const uint32_t uop = in.op == TPLX_OP_IMOD ? UOP_IAND_MOD : UOP_ISHR_FLOORDIV;
-            d.op_flags = uop | ((uint32_t)in.flags << 8) | ((uint32_t)in.opidx << 16);
-            d.imm = in.op == TPLX_OP_IMOD ? in.imm - 1 : k;
-        }
         out[i] = d;
     }
     return out;
@@ -443,6 +619,34 @@ static int32_t stage_dev(tplx_stage *s, Device *d, StageDev **out) {
     CU(cudaMemcpy(sd.opids, s->opids.data(), s->opids.size() * 8, cudaMemcpyHostToDevice));
     s->devs.push_back(sd);
     *out = &s->devs.back();
+    return TPLX_OK;
+}
+
+extern "C" int32_t tplx_gpu_stage_vec_plan(const tplx_stage *s, tplx_vec_uop *out, uint32_t cap, uint32_t *n_uops, uint32_t *n_slots,
+                                           uint16_t *out_slots, uint32_t cap_out) {
+    if (!s || !n_uops) return fail(TPLX_E_BADARG, "stage_vec_plan: bad arguments");
+    *n_uops = s->vec_ok ? (uint32_t)s->vplan.ins.size() : 0;
+    if (n_slots) *n_slots = s->vec_ok ? s->vplan.n_slots : 0;
+    if (!s->vec_ok) return TPLX_OK;
+    const VecPlan &pl = s->vplan;
+    auto dense = [&](uint16_t sl) { return sl == TPLX_NOSLOT || sl >= pl.slot_map.size() ? (uint16_t)TPLX_NOSLOT : pl.slot_map[sl]; };
+    for (uint32_t i = 0; out && i < cap && i < pl.ins.size(); ++i) {
+        const VecIns &v = pl.ins[i];
+        tplx_vec_uop u{};
+        u.vop = v.vop;
+        u.xflags = v.xf;
+        u.flags = v.in.flags;
+        u.opidx = v.in.opidx;
+        u.dst = (v.xf & VX_NOSTORE) ? (uint16_t)TPLX_NOSLOT : dense(v.in.dst);
+        u.a = dense(v.in.a);
+        u.b = dense(v.in.b);
+        u.c = dense(v.in.c);
+        u.guard = dense(v.in.guard);
+        u.imm = v.in.imm;
+        u.imm2 = v.in.imm2;
+        out[i] = u;
+    }
+    for (uint32_t c = 0; out_slots && c < cap_out && c < s->out_cols.size(); ++c) out_slots[c] = dense(s->out_cols[c].slot);
     return TPLX_OK;
 }
 
@@ -625,10 +829,11 @@ static Layout make_layout(const tplx_stage *s, uint32_t R, bool rows_ep, bool in
         }
         off = align_up(off + so, 16);
         L.misc_off = (uint32_t)off;
-        off += (size_t)(4 * W + 2 + T) * 4 + (size_t)(2 * MAX_SCAN + NT / 32 + 1) * 8 + 16;
+        // bitmaps + word prefixes, codes of raising rows (in place: kept in slot 0 of the row), scan values, ticket
+        off += (size_t)(4 * W + 2 + (L.inplace ? 0 : T)) * 4 + (size_t)(2 * MAX_SCAN) * 8 + 16;
         off = align_up(off, 16);
         L.stash_off = (uint32_t)off;
-        off += (size_t)s->n_str_out * (NT + NT / 32) * 4;
+        off += (size_t)s->n_str_out * (NT / 32) * 4;
     } else {
         L.misc_off = (uint32_t)off;
         off += (size_t)(NT / 32) * std::max<size_t>(s->accs.size(), 1) * 8;
@@ -865,20 +1070,20 @@ static int32_t launch_rows_vec(uint32_t grid, uint32_t smem, cudaStream_t st, co
 static int32_t run_rows_vec(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_t first_row_no, tplx_result *r) {
     Device *d = r->dev;
     const uint64_t n = b->n_rows;
-    const uint32_t ns = std::max<uint32_t>(s->hdr.n_slots, 1);
+    const uint32_t ns = s->vplan.n_slots;
+    const size_t n_uops = s->vplan.ins.size();
     // J = 4 (2048-row tiles, 8 rows per thread per dispatch) when the register file leaves room for >= 3 CTAs per SM, else J = 2
     int Jsel = 0;
     uint32_t smem = 0, T = 0, cols_off = 0, regs_off = 0, misc_off = 0;
     for (int J : {4, 2}) {
         T = 2u * J * NT;
-        const uint32_t W = T / 32;
-        size_t off = align_up(std::max<size_t>(s->instrs.size(), 1) * sizeof(DInstr), 16);
+        size_t off = align_up(std::max<size_t>(n_uops, 1) * sizeof(DInstr), 16);
         cols_off = (uint32_t)off;
         off = align_up(off + std::max<size_t>(s->in_types.size(), 1) * sizeof(ColIn), 16);
         regs_off = (uint32_t)off;
         off = align_up(off + (size_t)ns * T * 8, 16);
         misc_off = (uint32_t)off;
-        off += (size_t)(4 * W + 2 + T) * 4 + (size_t)(2 * MAX_SCAN + NT / 32 + 1) * 8 + 16;
+        off += 32 * 4 + (size_t)T * 4 + (size_t)(2 * (NT / 32)) * 8 + 16;  // s_cnt, exc_stage, look-back scratch, ticket
         smem = (uint32_t)align_up(off, 16);
         if (smem <= 72 * 1024 || (J == 2 && smem <= (uint32_t)d->smem_optin)) { Jsel = J; break; }
     }
@@ -887,7 +1092,7 @@ static int32_t run_rows_vec(tplx_stage *s, StageDev *sd, const tplx_block *b, in
     if (!sd->prog_vec[ji]) {
         std::lock_guard<std::mutex> lk(s->mu);
         if (!sd->prog_vec[ji]) {
-            std::vector<DInstr> dec = predecode(s->instrs, T * 8, true);
+            std::vector<DInstr> dec = vec_encode(s->vplan, T);
             DInstr *p = nullptr;
             CU(cudaMalloc(&p, std::max<size_t>(dec.size() * sizeof(DInstr), 16)));
             CU(cudaMemcpy(p, dec.data(), dec.size() * sizeof(DInstr), cudaMemcpyHostToDevice));
@@ -903,6 +1108,8 @@ static int32_t run_rows_vec(tplx_stage *s, StageDev *sd, const tplx_block *b, in
     KParams P;
     fill_common(P, s, sd, b, L, 2 * Jsel);
     P.prog = sd->prog_vec[ji];
+    P.n_instr = (uint32_t)n_uops;
+    P.n_slots = ns;
     P.n_tiles = (uint32_t)((n + T - 1) / T);
     P.first_row_no = first_row_no;
     int occ = 0;
@@ -945,7 +1152,7 @@ static int32_t run_rows_vec(tplx_stage *s, StageDev *sd, const tplx_block *b, in
         oc.slot = s->out_cols[c].slot;
         oc.type = s->out_cols[c].type;
         oc.strk = -1;
-        oc.stage_off = (uint32_t)s->out_cols[c].slot * T * 8;
+        oc.stage_off = (uint32_t)s->vplan.slot_map[s->out_cols[c].slot] * T * 8;
         rc = dalloc(r, &oc.data, n);
         if (rc) return rc;
     }
@@ -1039,6 +1246,22 @@ static int32_t run_rows(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stage_rows_kernel, NT, L.total));
     if (occ < 1) return fail(TPLX_E_UNSUPPORTED, "stage kernel cannot be resident");
+    // String stages read their input bytes through L1 again and again (every string op walks the bytes): shared memory must not
+    // take the whole 256 KB of the SM. Measured on the Zillow dense launch (B200): 3 CTAs/SM + 60 KB L1 0.413 ms, 4 CTAs/SM + 28 KB L1
+    // 0.54 ms, 2 CTAs/SM + 124 KB L1 0.53 ms. So the carve-out is capped at 196 KB (85 % of 228) and occupancy counted against it.
+    int carve = s->has_str ? 85 : -1;
+    if (getenv("TPLX_DENSE_CARVEOUT")) carve = atoi(getenv("TPLX_DENSE_CARVEOUT"));
+    CU(cudaFuncSetAttribute(stage_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    if (carve > 0 && carve < 100) {
+        static const int steps_kb[] = {8, 16, 32, 64, 100, 132, 164, 196, 228};
+        int cfg = 228;
+        for (int kb : steps_kb)
+            if (kb * 100 >= carve * 228) { cfg = kb; break; }
+        occ = std::max(1, std::min(occ, (int)((size_t)cfg * 1024 / ((size_t)L.total + 1024))));
+    }
+    if (getenv("TPLX_DENSE_OCC") && atoi(getenv("TPLX_DENSE_OCC")) > 0) occ = std::min(occ, atoi(getenv("TPLX_DENSE_OCC")));
+    if (getenv("TPLX_TRACE"))
+        fprintf(stderr, "[tplx] rows kernel: R %u, shared memory %u B (%s), %d CTAs/SM\n", R, L.total, L.inplace ? "in place" : "staged", occ);
     KParams P;
     fill_common(P, s, sd, b, L, R);
     if (cols_override)

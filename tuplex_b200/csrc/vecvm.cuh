@@ -3,13 +3,18 @@
 // (tuplex/core/src/physical/TuplexSourceTaskBuilder.cc:104-215 + PipelineBuilder.cc:565-700 for fixed-width rows).
 //
 // Same op program, same per-row semantics as vm.cuh (every op is the same single integer / IEEE operation), evaluated
-// VECTOR-AT-A-TIME: a thread owns V = 2J rows of a tile; one instruction dispatch (uniform fetch + decode) is followed by 2J
+// VECTOR-AT-A-TIME: a thread owns V = 2J rows of a tile; one instruction dispatch (uniform fetch + jump table) is followed by 2J
 // row operations, so the interpretive overhead per row shrinks by 2J. B200 mapping:
 //   * inputs: coalesced 128-bit global loads (LDG.E.128: thread t reads rows 2t, 2t+1 of every 512-row slab of the tile);
-//   * register file in shared memory as regs[slot][local row] — one conflict-free LDS.128 / STS.128 moves two rows;
-//     because a slot is indexed by the local row it IS the staging array of an output column (no copy before the write);
-//   * filter mask -> warp ballots -> bitmaps -> rows_tile_finish (decoupled look-back scan + dense coalesced write), shared
-//     with the scalar kernel.
+//   * ACCUMULATOR CHAINS: the host's vector planner (vec_plan in tplx_gpu.cu) finds the straight-line producer -> consumer pairs of
+//     the program; the consumer takes the value from the thread's registers (the accumulator = result of the previous micro-op)
+//     and a result nobody else reads is never stored. compare + filter and (x mod 2^k) + compare are single micro-ops.
+//     C1 (x*x, x % 2 == 0) runs as LDCOL -> IMUL -> masked-compare-filter: one LDG.128 and one STS.128 per two rows;
+//   * what does have to live across micro-ops sits in shared memory as regs[slot][local row] — one conflict-free LDS.128 /
+//     STS.128 moves two rows, and because a slot is indexed by the local row it IS the staging array of an output column;
+//   * compaction by the OWNER of a row: two ballots per 512-row slab give every thread the rank of its rows inside the warp,
+//     one 32-entry scan of (slab, warp) counts gives the rank inside the tile, a block-wide packed look-back (below) the
+//     rank in the output — the thread then stores its own rows (dense, ascending addresses across the warp). No bitmaps.
 // Strings never enter this kernel (the host selects it only for programs without string values).
 #pragma once
 #include <stdint.h>
@@ -17,19 +22,24 @@
 
 namespace tplx {
 
-// internal micro-ops produced by the pre-decoder (never part of the IR): strength-reduced forms with a constant power-of-two
-// divisor; floored semantics make both exact for every dividend:  x // 2^k == x >> k (arithmetic),  x % 2^k == x & (2^k - 1)
-constexpr uint32_t UOP_ISHR_FLOORDIV = 200;  // imm = k
-constexpr uint32_t UOP_IAND_MOD = 201;       // imm = 2^k - 1
-
-__device__ __forceinline__ uint32_t spread16(uint32_t x) {  // bit i -> bit 2i
-    x &= 0xFFFFu;
-    x = (x | (x << 8)) & 0x00FF00FFu;
-    x = (x | (x << 4)) & 0x0F0F0F0Fu;
-    x = (x | (x << 2)) & 0x33333333u;
-    x = (x | (x << 1)) & 0x55555555u;
-    return x;
-}
+// Vector micro-ops: produced by the host's planner from the IR ops, never part of the IR. Dense numbering (jump-table dispatch).
+// V_ISHRK / V_IANDK: strength-reduced x // 2^k, x % 2^k (floored semantics make both exact for every dividend).
+enum VOp : uint32_t {
+    V_NOP = 0, V_LDCOL, V_LDI, V_LDROW, V_MOV, V_SEL,
+    V_IADD, V_ISUB, V_IMUL, V_INEG, V_IAND, V_IOR, V_IXOR, V_ISHL, V_ISHR, V_ISHRK, V_IANDK, V_IABS,
+    V_FADD, V_FSUB, V_FMUL, V_FNEG, V_FABS, V_I2F, V_F2I, V_BAND, V_BOR, V_BNOT,
+    V_ICMP_EQ, V_ICMP_NE, V_ICMP_LT, V_ICMP_LE, V_ICMP_GT, V_ICMP_GE,
+    V_FCMP_EQ, V_FCMP_NE, V_FCMP_LT, V_FCMP_LE, V_FCMP_GT, V_FCMP_GE,
+    V_IFLOORDIV, V_IMOD, V_FDIV, V_FMOD, V_FFLOORDIV, V_FILTER, V_RAISE, V_COUNT
+};
+// planner flags of a micro-op (DInstr.pad0)
+enum VFlag : uint32_t {
+    VX_A_ACC = 1,    // operand a = the accumulator (result of the previous micro-op) instead of a slot
+    VX_B_ACC = 2,    // operand b likewise
+    VX_NOSTORE = 4,  // nobody reads the result from its slot: keep it in the accumulator only
+    VX_FILTER = 8,   // boolean result: rows with 0 leave the pipeline (the FILTER that followed, fused)
+    VX_A_MASK = 16,  // integer compares: a <- a & imm2 first (the x % 2^k that preceded, fused)
+};
 
 template <int J>
 struct VecVM {
@@ -57,30 +67,34 @@ struct VecVM {
         exc_stage[lr] = code | (opidx << 16);
     }
 
-    // rb = regs base + tid * 16. tile_row0 = first input row of the tile. Rows >= n_rows are inactive from the start.
+    // rb = regs base + tid * 16. tile_row0 = first input row of the tile; full = the tile has T rows (uniform).
     static __device__ void run(const DInstr *__restrict__ prog, uint32_t n_instr, uint8_t *__restrict__ rb, const ColIn *__restrict__ cols,
-                               uint64_t tile_row0, uint64_t n_rows, State &st, uint32_t *__restrict__ exc_stage) {
+                               uint64_t tile_row0, uint64_t n_rows, bool full, State &st, uint32_t *__restrict__ exc_stage) {
+        ulonglong2 acc[J];
+#pragma unroll
+        for (uint32_t j = 0; j < J; ++j) acc[j] = make_ulonglong2(0, 0);
         for (uint32_t pc = 0; pc < n_instr; ++pc) {
             const uint4 w0 = *reinterpret_cast<const uint4 *>(&prog[pc]);
-            const uint2 w1 = *reinterpret_cast<const uint2 *>(&prog[pc].c);
+            const uint4 w1 = *reinterpret_cast<const uint4 *>(&prog[pc].c);
+            const ulonglong2 w2 = *reinterpret_cast<const ulonglong2 *>(&prog[pc].imm);
             const uint32_t op = w0.x & 0xFF, flags = (w0.x >> 8) & 0xFF, opidx = w0.x >> 16;
-            const uint32_t dst = w0.y, a = w0.z, b = w0.w, c = w1.x, guard = w1.y;
-            const uint64_t imm = (uint64_t)prog[pc].imm, imm2 = (uint64_t)prog[pc].imm2;
+            const uint32_t dst = w0.y, a = w0.z, b = w0.w, c = w1.x, guard = w1.y, xf = w1.z;
+            const uint64_t imm = w2.x, imm2 = w2.y;
             uint32_t act = st.alive;  // rows this instruction executes for
-            if (guard != NOOFF) {
+            const bool guarded = guard != NOOFF;
+            if (guarded) {
 #pragma unroll
                 for (uint32_t j = 0; j < J; ++j) {
                     const ulonglong2 g = ld2(rb, guard, j);
                     if (g.x == 0) act &= ~(1u << (2 * j));
                     if (g.y == 0) act &= ~(2u << (2 * j));
                 }
+                if (!__any_sync(0xFFFFFFFFu, act != 0)) continue;  // untaken branch: the warp skips the op
             }
-            if (!__any_sync(0xFFFFFFFFu, act != 0)) continue;
-            const bool guarded = guard != NOOFF;
-            // operands: constants ride in the immediates (a <- imm2, b <- imm, c <- imm2)
-#define LDA(j) ((flags & TPLX_F_A_CONST) ? make_ulonglong2(imm2, imm2) : ld2(rb, a, j))
-#define LDB(j) ((flags & TPLX_F_B_CONST) ? make_ulonglong2(imm, imm) : ld2(rb, b, j))
-            // store: unguarded ops write both rows unconditionally (a row that is not alive never reaches an output);
+            // operands: the accumulator, a constant riding in the immediates (a <- imm2, b <- imm, c <- imm2), or a slot
+#define LDA(j) ((xf & VX_A_ACC) ? acc[j] : ((flags & TPLX_F_A_CONST) ? make_ulonglong2(imm2, imm2) : ld2(rb, a, j)))
+#define LDB(j) ((xf & VX_B_ACC) ? acc[j] : ((flags & TPLX_F_B_CONST) ? make_ulonglong2(imm, imm) : ld2(rb, b, j)))
+            // result: unguarded ops produce both rows unconditionally (a row that is not alive never reaches an output);
             // guarded ops must leave the destination of rows outside the guard untouched (phi of an if-converted branch)
 #define STD(j, R0, R1)                                                                     \
     do {                                                                                   \
@@ -90,7 +104,8 @@ struct VecVM {
             if (!((act >> (2 * (j))) & 1u)) _r.x = _o.x;                                   \
             if (!((act >> (2 * (j) + 1)) & 1u)) _r.y = _o.y;                               \
         }                                                                                  \
-        st2(rb, dst, j, _r);                                                               \
+        acc[j] = _r;                                                                       \
+        if (!(xf & VX_NOSTORE)) st2(rb, dst, j, _r);                                       \
     } while (0)
 #define BIN(EXPR)                                                                          \
     _Pragma("unroll") for (uint32_t j = 0; j < J; ++j) {                                   \
@@ -110,9 +125,27 @@ struct VecVM {
         STD(j, r0, r1);                                                                    \
     }                                                                                      \
     break
+            // boolean results: optionally the filter itself (planner: unguarded only, so act == alive)
+#define PRED(MASKED, EXPR)                                                                 \
+    {                                                                                      \
+        const uint64_t msk = (MASKED) && (xf & VX_A_MASK) ? imm2 : ~0ull;                  \
+        _Pragma("unroll") for (uint32_t j = 0; j < J; ++j) {                               \
+            const ulonglong2 A = LDA(j), B = LDB(j);                                       \
+            uint64_t r0, r1;                                                               \
+            { const uint64_t x = A.x & msk, y = B.x; (void)y; r0 = (uint64_t)(EXPR); }     \
+            { const uint64_t x = A.y & msk, y = B.y; (void)y; r1 = (uint64_t)(EXPR); }     \
+            STD(j, r0, r1);                                                                \
+            if (xf & VX_FILTER) {                                                          \
+                if (!r0) st.alive &= ~(1u << (2 * j));                                     \
+                if (!r1) st.alive &= ~(2u << (2 * j));                                     \
+            }                                                                              \
+        }                                                                                  \
+        if ((xf & VX_FILTER) && !__any_sync(0xFFFFFFFFu, st.alive != 0)) return;           \
+    }                                                                                      \
+    break
 #define F(x) __longlong_as_double((long long)(x))
 #define U(d) ((uint64_t)__double_as_longlong(d))
-            // ops that can raise: evaluated row by row for the active rows only
+            // ops that can raise: evaluated row by row for the active rows only, operands and result in slots
 #define RAISING(...)                                                                       \
     _Pragma("unroll") for (uint32_t v = 0; v < V; ++v) {                                   \
         if (!((act >> v) & 1u)) continue;                                                  \
@@ -127,84 +160,79 @@ struct VecVM {
     }                                                                                      \
     break
             switch (op) {
-                case TPLX_OP_LDCOL: {
-                    const ColIn &ci = cols[imm];
-                    const uint64_t *src = reinterpret_cast<const uint64_t *>(ci.data);
+                case V_LDCOL: {
+                    const uint64_t *src = reinterpret_cast<const uint64_t *>(cols[imm].data);
+#ifdef __CUDA_ARCH__
+                    __builtin_assume(__isGlobal(src));
+#endif
 #pragma unroll
                     for (uint32_t j = 0; j < J; ++j) {
                         const uint64_t row = tile_row0 + lrow(j, 0);
                         ulonglong2 v = make_ulonglong2(0, 0);
-                        if (row + 1 < n_rows) v = *reinterpret_cast<const ulonglong2 *>(src + row);  // 16-byte aligned: row is even, base is
+                        if (full || row + 1 < n_rows) v = *reinterpret_cast<const ulonglong2 *>(src + row);  // 16-byte aligned: row is even, base is
                         else if (row < n_rows) v.x = src[row];
                         STD(j, v.x, v.y);
                     }
                     break;
                 }
-                case TPLX_OP_LDI:
+                case V_LDI:
 #pragma unroll
                     for (uint32_t j = 0; j < J; ++j) STD(j, imm, imm);
                     break;
-                case TPLX_OP_LDROW:
+                case V_LDROW:
 #pragma unroll
                     for (uint32_t j = 0; j < J; ++j) {
                         const uint64_t row = tile_row0 + lrow(j, 0);
                         STD(j, row, row + 1);
                     }
                     break;
-                case TPLX_OP_MOV: UNA(x);
-                case TPLX_OP_SEL:
+                case V_MOV: UNA(x);
+                case V_SEL:
 #pragma unroll
                     for (uint32_t j = 0; j < J; ++j) {
                         const ulonglong2 A = LDA(j), B = LDB(j), Cn = ld2(rb, c, j);
                         STD(j, Cn.x ? A.x : B.x, Cn.y ? A.y : B.y);
                     }
                     break;
-                case TPLX_OP_IADD: BIN(x + y);
-                case TPLX_OP_ISUB: BIN(x - y);
-                case TPLX_OP_IMUL: BIN(x * y);
-                case TPLX_OP_INEG: UNA((uint64_t)0 - x);
-                case TPLX_OP_IAND: BIN(x & y);
-                case TPLX_OP_IOR: BIN(x | y);
-                case TPLX_OP_IXOR: BIN(x ^ y);
-                case TPLX_OP_ISHL: BIN(x << (y & 63));
-                case TPLX_OP_ISHR: BIN((uint64_t)((int64_t)x >> (y & 63)));
-                case UOP_ISHR_FLOORDIV: UNA((uint64_t)((int64_t)x >> (imm & 63)));
-                case UOP_IAND_MOD: UNA(x & imm);
-                case TPLX_OP_IABS: UNA((int64_t)x < 0 ? (uint64_t)0 - x : x);
-                case TPLX_OP_FADD: BIN(U(__dadd_rn(F(x), F(y))));
-                case TPLX_OP_FSUB: BIN(U(__dsub_rn(F(x), F(y))));
-                case TPLX_OP_FMUL: BIN(U(__dmul_rn(F(x), F(y))));
-                case TPLX_OP_FNEG: UNA(x ^ 0x8000000000000000ull);
-                case TPLX_OP_FABS: UNA(x & 0x7FFFFFFFFFFFFFFFull);
-                case TPLX_OP_I2F: UNA(U((double)(int64_t)x));
-                case TPLX_OP_F2I: UNA((uint64_t)(int64_t)F(x));
-                case TPLX_OP_BAND: BIN((uint64_t)((x != 0) & (y != 0)));
-                case TPLX_OP_BOR: BIN((uint64_t)((x != 0) | (y != 0)));
-                case TPLX_OP_BNOT: UNA((uint64_t)(x == 0));
-                case TPLX_OP_ICMP:
-                    switch (flags & 7) {
-                        case TPLX_CMP_EQ: BIN((uint64_t)(x == y));
-                        case TPLX_CMP_NE: BIN((uint64_t)(x != y));
-                        case TPLX_CMP_LT: BIN((uint64_t)((int64_t)x < (int64_t)y));
-                        case TPLX_CMP_LE: BIN((uint64_t)((int64_t)x <= (int64_t)y));
-                        case TPLX_CMP_GT: BIN((uint64_t)((int64_t)x > (int64_t)y));
-                        default: BIN((uint64_t)((int64_t)x >= (int64_t)y));
-                    }
-                    break;
-                case TPLX_OP_FCMP:
-                    switch (flags & 7) {  // ordered predicates: false when either side is NaN
-                        case TPLX_CMP_EQ: BIN((uint64_t)(F(x) == F(y)));
-                        case TPLX_CMP_NE: BIN((uint64_t)((F(x) < F(y)) || (F(x) > F(y))));
-                        case TPLX_CMP_LT: BIN((uint64_t)(F(x) < F(y)));
-                        case TPLX_CMP_LE: BIN((uint64_t)(F(x) <= F(y)));
-                        case TPLX_CMP_GT: BIN((uint64_t)(F(x) > F(y)));
-                        default: BIN((uint64_t)(F(x) >= F(y)));
-                    }
-                    break;
-                case TPLX_OP_IFLOORDIV: RAISING({ if ((int64_t)y == 0) bad = true; else r = (uint64_t)floordiv_i64((int64_t)x, (int64_t)y); });
-                case TPLX_OP_IMOD: RAISING({ if ((int64_t)y == 0) bad = true; else r = (uint64_t)floormod_i64((int64_t)x, (int64_t)y); });
-                case TPLX_OP_FDIV: RAISING({ if (F(y) == 0.0) bad = true; else r = U(__ddiv_rn(F(x), F(y))); });
-                case TPLX_OP_FMOD: RAISING({
+                case V_IADD: BIN(x + y);
+                case V_ISUB: BIN(x - y);
+                case V_IMUL: BIN(x * y);
+                case V_INEG: UNA((uint64_t)0 - x);
+                case V_IAND: BIN(x & y);
+                case V_IOR: BIN(x | y);
+                case V_IXOR: BIN(x ^ y);
+                case V_ISHL: BIN(x << (y & 63));
+                case V_ISHR: BIN((uint64_t)((int64_t)x >> (y & 63)));
+                case V_ISHRK: UNA((uint64_t)((int64_t)x >> (imm & 63)));
+                case V_IANDK: UNA(x & imm);
+                case V_IABS: UNA((int64_t)x < 0 ? (uint64_t)0 - x : x);
+                case V_FADD: BIN(U(__dadd_rn(F(x), F(y))));
+                case V_FSUB: BIN(U(__dsub_rn(F(x), F(y))));
+                case V_FMUL: BIN(U(__dmul_rn(F(x), F(y))));
+                case V_FNEG: UNA(x ^ 0x8000000000000000ull);
+                case V_FABS: UNA(x & 0x7FFFFFFFFFFFFFFFull);
+                case V_I2F: UNA(U((double)(int64_t)x));
+                case V_F2I: UNA((uint64_t)(int64_t)F(x));
+                case V_BAND: PRED(false, (x != 0) & (y != 0));
+                case V_BOR: PRED(false, (x != 0) | (y != 0));
+                case V_BNOT: PRED(false, x == 0);
+                case V_ICMP_EQ: PRED(true, x == y);
+                case V_ICMP_NE: PRED(true, x != y);
+                case V_ICMP_LT: PRED(true, (int64_t)x < (int64_t)y);
+                case V_ICMP_LE: PRED(true, (int64_t)x <= (int64_t)y);
+                case V_ICMP_GT: PRED(true, (int64_t)x > (int64_t)y);
+                case V_ICMP_GE: PRED(true, (int64_t)x >= (int64_t)y);
+                // ordered predicates: false when either side is NaN
+                case V_FCMP_EQ: PRED(false, F(x) == F(y));
+                case V_FCMP_NE: PRED(false, (F(x) < F(y)) || (F(x) > F(y)));
+                case V_FCMP_LT: PRED(false, F(x) < F(y));
+                case V_FCMP_LE: PRED(false, F(x) <= F(y));
+                case V_FCMP_GT: PRED(false, F(x) > F(y));
+                case V_FCMP_GE: PRED(false, F(x) >= F(y));
+                case V_IFLOORDIV: RAISING({ if ((int64_t)y == 0) bad = true; else r = (uint64_t)floordiv_i64((int64_t)x, (int64_t)y); });
+                case V_IMOD: RAISING({ if ((int64_t)y == 0) bad = true; else r = (uint64_t)floormod_i64((int64_t)x, (int64_t)y); });
+                case V_FDIV: RAISING({ if (F(y) == 0.0) bad = true; else r = U(__ddiv_rn(F(x), F(y))); });
+                case V_FMOD: RAISING({
                     if (F(y) == 0.0) bad = true;
                     else {
                         double m = fmod(F(x), F(y));  // == LLVM frem, exact
@@ -212,20 +240,21 @@ struct VecVM {
                         r = U(m);
                     }
                 });
-                case TPLX_OP_FFLOORDIV: RAISING({
+                case V_FFLOORDIV: RAISING({
                     const int64_t xi = (int64_t)F(x), yi = (int64_t)F(y);
                     if (F(y) == 0.0 || yi == 0) bad = true;
                     else r = U((double)floordiv_i64(xi, yi));
                 });
-                case TPLX_OP_FILTER:
+                case V_FILTER:
 #pragma unroll
                     for (uint32_t j = 0; j < J; ++j) {
-                        const ulonglong2 A = ld2(rb, a, j);
+                        const ulonglong2 A = LDA(j);
                         if (A.x == 0) st.alive &= ~(act & (1u << (2 * j)));
                         if (A.y == 0) st.alive &= ~(act & (2u << (2 * j)));
                     }
+                    if (!__any_sync(0xFFFFFFFFu, st.alive != 0)) return;  // the warp is empty: nothing that follows can execute
                     break;
-                case TPLX_OP_RAISE:
+                case V_RAISE:
 #pragma unroll
                     for (uint32_t v = 0; v < V; ++v)
                         if ((act >> v) & 1u) raise_row(st, v, (uint32_t)imm, opidx, exc_stage, lrow(v >> 1, v & 1));
@@ -237,6 +266,7 @@ struct VecVM {
 #undef STD
 #undef BIN
 #undef UNA
+#undef PRED
 #undef F
 #undef U
 #undef RAISING
@@ -244,7 +274,7 @@ struct VecVM {
     }
 };
 
-// ---- tile tail of the vector kernel: block-wide decoupled look-back + dense write (fixed-width outputs only) -------------------
+// ---- tile tail: ranks by the owner, block-wide decoupled look-back, dense write (fixed-width outputs only) ---------------------
 // The scalar kernel's look-back (rows_tile_finish: one warp, a 32-tile window per round, K values behind a status flag and a fence)
 // is fine for heavy tiles; a fixed-width tile is evaluated in ~1-2 us, and then the speed at which inclusive prefixes propagate
 // (32 tiles per L2 round trip) bounds the whole kernel (measured: 59 G rows/s on C1). Here a tile's scan state is ONE 64-bit word
@@ -256,126 +286,31 @@ __device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t *p) {
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void vec_tile_finish(const KParams &P, uint32_t tile, uint64_t base, uint32_t T, uint32_t W, uint8_t *s_regs,
-                                                uint32_t *keep_bits, uint32_t *exc_bits, uint32_t *keep_pre, uint32_t *exc_pre,
-                                                uint32_t *exc_stage, uint64_t *s_vals, uint64_t *s_scr) {
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // word prefixes of the two bitmaps (warp 0)
-    if (warp == 0) {
-        uint32_t ck = 0, ce = 0;
-        for (uint32_t w0 = 0; w0 < W; w0 += 32) {
-            const uint32_t w = w0 + lane;
-            const uint32_t pk = w < W ? __popc(keep_bits[w]) : 0, pe = w < W ? __popc(exc_bits[w]) : 0;
-            uint32_t ik = pk, ie = pe;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, ik, o), b = __shfl_up_sync(0xFFFFFFFFu, ie, o);
-                if (lane >= (uint32_t)o) { ik += a; ie += b; }
-            }
-            if (w < W) { keep_pre[w] = ck + ik - pk; exc_pre[w] = ce + ie - pe; }
-            ck += __shfl_sync(0xFFFFFFFFu, ik, 31);
-            ce += __shfl_sync(0xFFFFFFFFu, ie, 31);
-        }
-        if (lane == 0) {
-            s_vals[0] = ck;
-            s_vals[1] = ce;
-            // publish this tile's counts (tile 0: they are its inclusive prefix)
-            st_cg_u64(P.tile_state + tile, ((uint64_t)(tile == 0 ? 2u : 1u) << 62) | ((uint64_t)ck << 31) | (uint64_t)ce);
-        }
-    }
-    __syncthreads();
-    const uint32_t n_keep = (uint32_t)s_vals[0], n_exc = (uint32_t)s_vals[1];
-    // ---- look-back: 256 predecessors per round ----
-    uint64_t pre_keep = 0, pre_exc = 0;
-    if (tile > 0) {
-        int64_t p = (int64_t)tile - 1;
-        while (true) {
-            const int64_t q = p - (int64_t)tid;
-            uint64_t wd = (uint64_t)2 << 62;  // tiles before the first count as an inclusive prefix of zero
-            if (q >= 0) do { wd = ld_relaxed_u64(P.tile_state + q); } while ((wd >> 62) == 0);
-            const bool incl = (wd >> 62) == 2;
-            const uint32_t im = __ballot_sync(0xFFFFFFFFu, incl);
-            const uint32_t first = im ? (uint32_t)(__ffs(im) - 1) : 32u;  // nearest inclusive word inside this warp's 32 tiles
-            uint64_t k = lane <= first ? (wd >> 31) & 0x7FFFFFFFull : 0, e = lane <= first ? wd & 0x7FFFFFFFull : 0;
-#pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                k += __shfl_xor_sync(0xFFFFFFFFu, k, o);
-                e += __shfl_xor_sync(0xFFFFFFFFu, e, o);
-            }
-            if (lane == 0) {
-                s_scr[warp * 2] = (k << 32) | e;      // both < 2^31 * 32: fit 32 bits each? counts are < 2^31 in total, so yes
-                s_scr[warp * 2 + 1] = im ? 1 : 0;
-            }
-            __syncthreads();
-            bool done = false;
-            for (uint32_t w = 0; w < NT / 32 && !done; ++w) {  // warps cover tile-1-32w .. : nearest first
-                pre_keep += s_scr[w * 2] >> 32;
-                pre_exc += s_scr[w * 2] & 0xFFFFFFFFull;
-                done = s_scr[w * 2 + 1] != 0;
-            }
-            __syncthreads();
-            if (done) break;
-            p -= NT;
-        }
-        if (tid == 0) st_cg_u64(P.tile_state + tile, ((uint64_t)2 << 62) | ((pre_keep + n_keep) << 31) | (pre_exc + n_exc));
-    }
-    if (tid == 0 && tile == P.n_tiles - 1) {
-        P.totals[0] = pre_keep + n_keep;
-        P.totals[1] = pre_exc + n_exc;
-    }
-    // ---- write: fixed-width outputs straight from the register file (a slot is indexed by the local row) ----
-    if (n_keep) {
-        for (uint32_t c = 0; c < P.n_out; ++c) {
-            const OutCol &oc = P.out[c];
-            const uint64_t *st = reinterpret_cast<const uint64_t *>(s_regs + oc.stage_off);
-            for (uint32_t lr = tid; lr < T; lr += NT)
-                if (bit_test(keep_bits, lr)) oc.data[pre_keep + bit_rank(keep_bits, keep_pre, lr)] = st[lr];
-        }
-    }
-    if (n_exc) {
-        if (pre_exc + n_exc <= P.cap_exc) {
-            for (uint32_t lr = tid; lr < T; lr += NT) {
-                if (!bit_test(exc_bits, lr)) continue;
-                const uint32_t ke = bit_rank(exc_bits, exc_pre, lr), kk = bit_rank(keep_bits, keep_pre, lr);
-                tplx_exception_rec rec;
-                rec.row = (int64_t)(base + lr);
-                rec.row_no = P.first_row_no + (int64_t)(pre_keep + pre_exc + kk + ke);  // rows written + exceptions so far (TransformTask.cc:764,885)
-                const uint32_t es = exc_stage[lr];
-                rec.code = es & 0xFFFF;
-                rec.op_id = P.opids[es >> 16];
-                P.exc[pre_exc + ke] = rec;
-            }
-        } else if (tid == 0) atomicOr(&P.counters[1], 4u);
-    }
-}
 
-// K1v kernel: persistent CTAs, ticketed tiles of T = 2J * 256 rows, VecVM evaluation, shared tail (rows_tile_finish).
-// Shared memory: prog | cols | regs (n_slots x T x 8 B; output columns are staged in place) | misc (bitmaps, scan scratch).
+// K1v kernel: persistent CTAs, ticketed tiles of T = 2J * 256 rows.
+// Shared memory: prog | cols | regs (n_slots x T x 8 B; output columns are staged in place) | misc: s_cnt[8J] exc_stage[T] scan scratch.
+// Row order inside a tile: slab j (512 rows), warp w (64 rows), lane (2 rows). s_cnt[j * 8 + w] = kept | raised << 16 of that group.
 template <int J>
-__global__ void __launch_bounds__(NT) stage_rows_vec_kernel(const __grid_constant__ KParams P) {  // parameters in the constant bank
+__global__ void __launch_bounds__(NT, 4) stage_rows_vec_kernel(const __grid_constant__ KParams P) {  // parameters in the constant bank
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr uint32_t T = VecVM<J>::T, W = T / 32;
-    const uint32_t K = P.K;
+    constexpr uint32_t T = VecVM<J>::T, G = 8 * J;  // G = (slab, warp) groups per tile (<= 32)
+    static_assert(G <= 32, "one scan lane per (slab, warp) group");
 
     DInstr *s_prog = reinterpret_cast<DInstr *>(smem);
     ColIn *s_cols = reinterpret_cast<ColIn *>(smem + P.smem_cols_off);
     uint8_t *s_regs = smem + P.smem_regs_off;
-    uint32_t *keep_bits = reinterpret_cast<uint32_t *>(smem + P.smem_misc_off);
-    uint32_t *exc_bits = keep_bits + W;
-    uint32_t *keep_pre = exc_bits + W;
-    uint32_t *exc_pre = keep_pre + W + 1;
-    uint32_t *exc_stage = exc_pre + W + 1;
-    uint64_t *s_vals = reinterpret_cast<uint64_t *>(exc_stage + T);
-    uint64_t *s_excl = s_vals + MAX_SCAN;
-    uint64_t *s_warp = s_excl + MAX_SCAN;
-    uint32_t *s_ctl = reinterpret_cast<uint32_t *>(s_warp + NT / 32 + 1);
+    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(smem + P.smem_misc_off);
+    uint32_t *exc_stage = s_cnt + 32;
+    uint64_t *s_scr = reinterpret_cast<uint64_t *>(exc_stage + T);  // look-back scratch: 2 words per warp
+    uint32_t *s_ctl = reinterpret_cast<uint32_t *>(s_scr + 2 * (NT / 32));
 
     for (uint32_t i = tid; i < P.n_instr * (sizeof(DInstr) / 16); i += NT)
         reinterpret_cast<uint4 *>(s_prog)[i] = reinterpret_cast<const uint4 *>(P.prog)[i];
     for (uint32_t i = tid; i < P.n_in * (sizeof(ColIn) / 8); i += NT)
         reinterpret_cast<uint64_t *>(s_cols)[i] = reinterpret_cast<const uint64_t *>(P.in)[i];
-    const uint32_t state_stride = 1 + 2 * K;
+    uint8_t *rb = s_regs + tid * 16;
+    const uint32_t lt = (1u << lane) - 1u;
 
     while (true) {
         __syncthreads();
@@ -384,42 +319,123 @@ __global__ void __launch_bounds__(NT) stage_rows_vec_kernel(const __grid_constan
         const uint32_t tile = s_ctl[0];
         if (tile >= P.n_tiles) break;
         const uint64_t base = (uint64_t)tile * T;
+        const bool full = base + T <= P.n_rows;  // uniform
 
         typename VecVM<J>::State st;
         st.exc = 0;
-        if (base + T <= P.n_rows) st.alive = (1u << (2 * J)) - 1u;  // full tile (uniform test): every row starts alive
+        if (full) st.alive = (1u << (2 * J)) - 1u;  // every row starts alive
         else {
             st.alive = 0;
 #pragma unroll
             for (uint32_t v = 0; v < 2 * J; ++v)
                 if (base + VecVM<J>::lrow(v >> 1, v & 1) < P.n_rows) st.alive |= 1u << v;
         }
-        VecVM<J>::run(s_prog, P.n_instr, s_regs + tid * 16, s_cols, base, P.n_rows, st, exc_stage);
-        // bitmaps indexed by local row: thread t holds rows (2t, 2t+1) of slab j, so bit i of a bitmap word comes from lane i / 2
-        // (+ 16 for the word's upper half of the warp), even / odd row by the parity of i: one extra ballot interleaves the two masks
-        const bool any_exc = __any_sync(0xFFFFFFFFu, st.exc != 0);
+        VecVM<J>::run(s_prog, P.n_instr, rb, s_cols, base, P.n_rows, full, st, exc_stage);
+
+        // ---- counts per (slab, warp) group ----
+        const bool warp_exc = __any_sync(0xFFFFFFFFu, st.exc != 0);
 #pragma unroll
         for (uint32_t j = 0; j < J; ++j) {
             const uint32_t ke = __ballot_sync(0xFFFFFFFFu, (st.alive >> (2 * j)) & 1u), ko = __ballot_sync(0xFFFFFFFFu, (st.alive >> (2 * j + 1)) & 1u);
-            const uint32_t pick = (lane & 1) ? ko : ke, sh = lane >> 1;
-            const uint32_t w0 = __ballot_sync(0xFFFFFFFFu, (pick >> sh) & 1u), w1 = __ballot_sync(0xFFFFFFFFu, (pick >> (16 + sh)) & 1u);
-            uint32_t e0 = 0, e1 = 0;
-            if (any_exc) {
+            uint32_t cnt = __popc(ke) + __popc(ko);
+            if (warp_exc) {
                 const uint32_t ee = __ballot_sync(0xFFFFFFFFu, (st.exc >> (2 * j)) & 1u), eo = __ballot_sync(0xFFFFFFFFu, (st.exc >> (2 * j + 1)) & 1u);
-                const uint32_t pe = (lane & 1) ? eo : ee;
-                e0 = __ballot_sync(0xFFFFFFFFu, (pe >> sh) & 1u);
-                e1 = __ballot_sync(0xFFFFFFFFu, (pe >> (16 + sh)) & 1u);
+                cnt |= (__popc(ee) + __popc(eo)) << 16;
             }
-            if (lane == 0) {
-                const uint32_t w = j * (2 * NT / 32) + 2 * warp;
-                keep_bits[w] = w0;
-                keep_bits[w + 1] = w1;
-                exc_bits[w] = e0;
-                exc_bits[w + 1] = e1;
-            }
+            if (lane == 0) s_cnt[j * 8 + warp] = cnt;
         }
         __syncthreads();
-        vec_tile_finish(P, tile, base, T, W, s_regs, keep_bits, exc_bits, keep_pre, exc_pre, exc_stage, s_vals, s_excl);
+        // every warp scans the G group counts (kept in the low half, raised in the high half: both <= T = 2048)
+        uint32_t gi = lane < G ? s_cnt[lane] : 0;
+        const uint32_t gmine = gi;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, gi, o);
+            if (lane >= (uint32_t)o) gi += u;
+        }
+        const uint32_t gtot = __shfl_sync(0xFFFFFFFFu, gi, 31);
+        const uint32_t gex = gi - gmine;  // exclusive prefix of group `lane`
+        const uint32_t n_keep = gtot & 0xFFFFu, n_exc = gtot >> 16;
+        if (tid == 0)  // publish this tile's counts (tile 0: they are its inclusive prefix)
+            st_cg_u64(P.tile_state + tile, ((uint64_t)(tile == 0 ? 2u : 1u) << 62) | ((uint64_t)n_keep << 31) | (uint64_t)n_exc);
+
+        // ---- look-back: 256 predecessors per round ----
+        uint64_t pre_keep = 0, pre_exc = 0;
+        if (tile > 0) {
+            int64_t p = (int64_t)tile - 1;
+            while (true) {
+                const int64_t q = p - (int64_t)tid;
+                uint64_t wd = (uint64_t)2 << 62;  // tiles before the first count as an inclusive prefix of zero
+                if (q >= 0) do { wd = ld_relaxed_u64(P.tile_state + q); } while ((wd >> 62) == 0);
+                const bool incl = (wd >> 62) == 2;
+                const uint32_t im = __ballot_sync(0xFFFFFFFFu, incl);
+                const uint32_t first = im ? (uint32_t)(__ffs(im) - 1) : 32u;  // nearest inclusive word inside this warp's 32 tiles
+                uint64_t k = lane <= first ? (wd >> 31) & 0x7FFFFFFFull : 0, e = lane <= first ? wd & 0x7FFFFFFFull : 0;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                    k += __shfl_xor_sync(0xFFFFFFFFu, k, o);
+                    e += __shfl_xor_sync(0xFFFFFFFFu, e, o);
+                }
+                if (lane == 0) {
+                    s_scr[warp * 2] = (k << 32) | e;  // counts are < 2^31 in total: 32 bits each
+                    s_scr[warp * 2 + 1] = im ? 1 : 0;
+                }
+                __syncthreads();
+                bool done = false;
+                for (uint32_t w = 0; w < NT / 32 && !done; ++w) {  // warps cover tile-1-32w .. : nearest first
+                    pre_keep += s_scr[w * 2] >> 32;
+                    pre_exc += s_scr[w * 2] & 0xFFFFFFFFull;
+                    done = s_scr[w * 2 + 1] != 0;
+                }
+                __syncthreads();
+                if (done) break;
+                p -= NT;
+            }
+            if (tid == 0) st_cg_u64(P.tile_state + tile, ((uint64_t)2 << 62) | ((pre_keep + n_keep) << 31) | (pre_exc + n_exc));
+        }
+        if (tid == 0 && tile == P.n_tiles - 1) {
+            P.totals[0] = pre_keep + n_keep;
+            P.totals[1] = pre_exc + n_exc;
+        }
+
+        // ---- write: every thread stores its own rows, straight from its column of the register file ----
+        const bool exc_fit = pre_exc + n_exc <= P.cap_exc;
+        if (n_exc && !exc_fit && tid == 0) atomicOr(&P.counters[1], 4u);
+#pragma unroll
+        for (uint32_t j = 0; j < J; ++j) {
+            const uint32_t a0 = (st.alive >> (2 * j)) & 1u, a1 = (st.alive >> (2 * j + 1)) & 1u;
+            const uint32_t ke = __ballot_sync(0xFFFFFFFFu, a0), ko = __ballot_sync(0xFFFFFFFFu, a1);
+            const uint32_t gpre = __shfl_sync(0xFFFFFFFFu, gex, j * 8 + warp);
+            const uint32_t kk = (gpre & 0xFFFFu) + __popc(ke & lt) + __popc(ko & lt);  // kept rows of the tile before this thread's even row
+            if (a0 | a1) {
+                const uint64_t at = pre_keep + kk;
+                for (uint32_t c = 0; c < P.n_out; ++c) {
+                    const OutCol &oc = P.out[c];
+                    uint64_t *od = oc.data;
+                    __builtin_assume(__isGlobal(od));
+                    const ulonglong2 v = VecVM<J>::ld2(rb, oc.stage_off, j);
+                    if (a0) od[at] = v.x;
+                    if (a1) od[at + a0] = v.y;
+                }
+            }
+            if (n_exc && exc_fit) {  // uniform
+                const uint32_t x0 = (st.exc >> (2 * j)) & 1u, x1 = (st.exc >> (2 * j + 1)) & 1u;
+                const uint32_t ee = __ballot_sync(0xFFFFFFFFu, x0), eo = __ballot_sync(0xFFFFFFFFu, x1);
+                const uint32_t ek = (gpre >> 16) + __popc(ee & lt) + __popc(eo & lt);
+                for (uint32_t b = 0; b < 2; ++b) {
+                    if (!(b ? x1 : x0)) continue;
+                    const uint32_t lr = VecVM<J>::lrow(j, b);
+                    const uint32_t ke_ = ek + (b ? x0 : 0), kk_ = kk + (b ? a0 : 0);
+                    tplx_exception_rec rec;
+                    rec.row = (int64_t)(base + lr);
+                    rec.row_no = P.first_row_no + (int64_t)(pre_keep + pre_exc + kk_ + ke_);  // rows written + exceptions so far (TransformTask.cc:764,885)
+                    const uint32_t es = exc_stage[lr];
+                    rec.code = es & 0xFFFF;
+                    rec.op_id = P.opids[es >> 16];
+                    P.exc[pre_exc + ke_] = rec;
+                }
+            }
+        }
     }
 }
 
