@@ -45,6 +45,8 @@ def _f2i(d):
     return int(d) & M64 if math.isfinite(d) else 0
 
 
+READS = {"V_NOP": 0, "V_LDCOL": 0, "V_LDI": 0, "V_LDROW": 0, "V_RAISE": 0, "V_MOV": 1, "V_INEG": 1, "V_IABS": 1, "V_FNEG": 1, "V_FABS": 1,
+         "V_I2F": 1, "V_F2I": 1, "V_BNOT": 1, "V_ISHRK": 1, "V_IANDK": 1, "V_FILTER": 1, "V_SEL": 7}  # default: a and b
 RAISING = {"V_IFLOORDIV", "V_IMOD", "V_FDIV", "V_FMOD", "V_FFLOORDIV"}
 
 
@@ -58,8 +60,14 @@ def run_row(uops, cols, row, row_index):
         guarded = uo["guard"] != NOSLOT
         if guarded and slots.get(uo["guard"], 0) == 0:
             continue
-        A = acc if xf & X_A_ACC else ((uo["imm2"] & M64) if fl & A_CONST else slots.get(uo["a"], 0))
+        # the accumulator is operand a's home: an a that is not already there is loaded into it first (vecvm.cuh, VX_LOAD_A), so a
+        # b taken from the accumulator is only meaningful together with a from the accumulator (x op x)
+        if READS.get(name, 3) & 1 and not (xf & X_A_ACC):
+            acc = (uo["imm2"] & M64) if fl & A_CONST else slots.get(uo["a"], 0)
+        A = acc
         B = acc if xf & X_B_ACC else ((uo["imm"] & M64) if fl & B_CONST else slots.get(uo["b"], 0))
+        if xf & X_B_ACC:
+            assert xf & X_A_ACC, "b from the accumulator needs a from the accumulator"
         if name in RAISING:
             assert not (xf & (X_A_ACC | X_B_ACC | X_NOSTORE)), "raising micro-ops keep operands and result in slots"
         if name == "V_LDCOL":
@@ -155,8 +163,7 @@ def run_row(uops, cols, row, row_index):
             return ("exc", uo["imm"] & 0xFFFF, uo["opidx"])
         else:
             raise AssertionError(f"unknown micro-op {name}")
-        if not guarded:
-            acc = r
+        acc = r
         if not (xf & X_NOSTORE):
             assert uo["dst"] != NOSLOT
             slots[uo["dst"]] = r

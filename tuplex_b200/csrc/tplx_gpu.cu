@@ -312,8 +312,38 @@ static VecPlan vec_plan(const std::vector<tplx_instr> &prog, const std::vector<t
         VecIns &co = pl.ins[i + 1];
         if (!unguarded(pr) || !unguarded(co) || !vop_has_dst(pr.vop) || vop_raising(pr.vop) || vop_raising(co.vop) || co.vop == V_RAISE) continue;
         const uint32_t m = vop_reads(co.vop);
-        if ((m & 1u) && !(co.in.flags & TPLX_F_A_CONST) && co.in.a == pr.in.dst) co.xf |= VX_A_ACC;
-        if ((m & 2u) && !(co.in.flags & TPLX_F_B_CONST) && co.in.b == pr.in.dst) co.xf |= VX_B_ACC;
+        const bool a_is = (m & 1u) && !(co.in.flags & TPLX_F_A_CONST) && co.in.a == pr.in.dst;
+        const bool b_is = (m & 2u) && !(co.in.flags & TPLX_F_B_CONST) && co.in.b == pr.in.dst;
+        if (a_is) {
+            co.xf |= VX_A_ACC;
+            if (b_is) co.xf |= VX_B_ACC;  // x op x
+        } else if (b_is && co.vop != V_SEL && !(co.xf & VX_A_MASK)) {
+            // the accumulator is operand a's home (loading a overwrites it): commute, or flip the comparison, so that the chained
+            // value becomes a; ops that are neither (x - acc, x << acc) read the stored slot instead
+            uint32_t sw = V_NOP;
+            switch (co.vop) {
+                case V_IADD: case V_IMUL: case V_IAND: case V_IOR: case V_IXOR: case V_FADD: case V_FMUL: case V_BAND: case V_BOR:
+                case V_ICMP_EQ: case V_ICMP_NE: case V_FCMP_EQ: case V_FCMP_NE: sw = co.vop; break;
+                case V_ICMP_LT: sw = V_ICMP_GT; break;
+                case V_ICMP_GT: sw = V_ICMP_LT; break;
+                case V_ICMP_LE: sw = V_ICMP_GE; break;
+                case V_ICMP_GE: sw = V_ICMP_LE; break;
+                case V_FCMP_LT: sw = V_FCMP_GT; break;
+                case V_FCMP_GT: sw = V_FCMP_LT; break;
+                case V_FCMP_LE: sw = V_FCMP_GE; break;
+                case V_FCMP_GE: sw = V_FCMP_LE; break;
+                default: break;
+            }
+            if (sw != V_NOP) {
+                co.vop = sw;
+                std::swap(co.in.a, co.in.b);
+                std::swap(co.in.imm, co.in.imm2);
+                const uint8_t fl = co.in.flags;
+                co.in.flags = (uint8_t)((fl & ~(TPLX_F_A_CONST | TPLX_F_B_CONST)) | ((fl & TPLX_F_A_CONST) ? TPLX_F_B_CONST : 0) |
+                                        ((fl & TPLX_F_B_CONST) ? TPLX_F_A_CONST : 0));
+                co.xf |= VX_A_ACC;
+            }
+        }
     }
     // (d) results nobody reads from their slot
     for (size_t i = 0; i < pl.ins.size(); ++i) {
@@ -339,21 +369,35 @@ static VecPlan vec_plan(const std::vector<tplx_instr> &prog, const std::vector<t
     pl.n_slots = std::max<uint32_t>(next, 1);
     return pl;
 }
-// device format of the plan for tiles of T rows (slot stride T * 8 bytes)
-static std::vector<DInstr> vec_encode(const VecPlan &pl, uint32_t T) {
-    std::vector<DInstr> out;
+// device format of the plan (VInstr, vecvm.cuh) for tiles of T rows: the program sits at the start of shared memory, the register
+// file at regs_off with a slot stride of T * 8 bytes
+static std::vector<VInstr> vec_encode(const VecPlan &pl, uint32_t T, uint32_t regs_off) {
+    std::vector<VInstr> out;
     auto off = [&](uint16_t sl) { return sl == TPLX_NOSLOT || pl.slot_map[sl] == TPLX_NOSLOT ? NOOFF : (uint32_t)pl.slot_map[sl] * T * 8u; };
-    for (const VecIns &v : pl.ins) {
-        DInstr d{};
-        d.op_flags = v.vop | ((uint32_t)v.in.flags << 8) | ((uint32_t)v.in.opidx << 16);
+    for (size_t i = 0; i < pl.ins.size(); ++i) {
+        const VecIns &v = pl.ins[i];
+        VInstr d{};
+        uint32_t xf = v.xf;
+        const uint32_t rd = vop_reads(v.vop), self = (uint32_t)(i * sizeof(VInstr));
+        if (rd & 1u) {
+            if (!(xf & VX_A_ACC)) {
+                xf |= VX_LOAD_A;
+                if (v.in.flags & TPLX_F_A_CONST) d.pa = self + (uint32_t)offsetof(VInstr, ka);
+                else { d.pa = regs_off + off(v.in.a); xf |= VX_A_THREAD; }
+            }
+        }
+        if ((rd & 2u) && !(xf & VX_B_ACC)) {
+            if (v.in.flags & TPLX_F_B_CONST) d.pb = self + (uint32_t)offsetof(VInstr, kb);
+            else { d.pb = regs_off + off(v.in.b); xf |= VX_B_THREAD; }
+        }
+        if (rd & 4u) d.pc = off(v.in.c);
+        if (vop_has_dst(v.vop)) xf |= VX_RESULT;
+        d.op_opidx = v.vop | ((uint32_t)v.in.opidx << 16);
+        d.xf = xf;
         d.dst = (v.xf & VX_NOSTORE) ? NOOFF : off(v.in.dst);
-        d.a = off(v.in.a);
-        d.b = off(v.in.b);
-        d.c = off(v.in.c);
         d.guard = off(v.in.guard);
-        d.pad0 = v.xf;
-        d.imm = v.in.imm;
-        d.imm2 = v.in.imm2;
+        d.kb[0] = d.kb[1] = (uint64_t)v.in.imm;
+        d.ka[0] = d.ka[1] = (uint64_t)v.in.imm2;
         out.push_back(d);
     }
     return out;
@@ -1077,7 +1121,7 @@ static int32_t run_rows_vec(tplx_stage *s, StageDev *sd, const tplx_block *b, in
     uint32_t smem = 0, T = 0, cols_off = 0, regs_off = 0, misc_off = 0;
     for (int J : {4, 2}) {
         T = 2u * J * NT;
-        size_t off = align_up(std::max<size_t>(n_uops, 1) * sizeof(DInstr), 16);
+        size_t off = align_up(std::max<size_t>(n_uops, 1) * sizeof(VInstr), 16);
         cols_off = (uint32_t)off;
         off = align_up(off + std::max<size_t>(s->in_types.size(), 1) * sizeof(ColIn), 16);
         regs_off = (uint32_t)off;
@@ -1092,11 +1136,11 @@ static int32_t run_rows_vec(tplx_stage *s, StageDev *sd, const tplx_block *b, in
     if (!sd->prog_vec[ji]) {
         std::lock_guard<std::mutex> lk(s->mu);
         if (!sd->prog_vec[ji]) {
-            std::vector<DInstr> dec = vec_encode(s->vplan, T);
-            DInstr *p = nullptr;
-            CU(cudaMalloc(&p, std::max<size_t>(dec.size() * sizeof(DInstr), 16)));
-            CU(cudaMemcpy(p, dec.data(), dec.size() * sizeof(DInstr), cudaMemcpyHostToDevice));
-            sd->prog_vec[ji] = p;
+            std::vector<VInstr> dec = vec_encode(s->vplan, T, regs_off);
+            VInstr *p = nullptr;
+            CU(cudaMalloc(&p, std::max<size_t>(dec.size() * sizeof(VInstr), 16)));
+            CU(cudaMemcpy(p, dec.data(), dec.size() * sizeof(VInstr), cudaMemcpyHostToDevice));
+            sd->prog_vec[ji] = reinterpret_cast<DInstr *>(p);
         }
     }
     Layout L;
@@ -1110,6 +1154,7 @@ static int32_t run_rows_vec(tplx_stage *s, StageDev *sd, const tplx_block *b, in
     P.prog = sd->prog_vec[ji];
     P.n_instr = (uint32_t)n_uops;
     P.n_slots = ns;
+
     P.n_tiles = (uint32_t)((n + T - 1) / T);
     P.first_row_no = first_row_no;
     int occ = 0;

@@ -22,7 +22,7 @@
 
 namespace tplx {
 
-// Vector micro-ops: produced by the host's planner from the IR ops, never part of the IR. Dense numbering (jump-table dispatch).
+// Vector micro-ops: produced by the host's planner from the IR ops, never part of the IR. Dense numbering.
 // V_ISHRK / V_IANDK: strength-reduced x // 2^k, x % 2^k (floored semantics make both exact for every dividend).
 enum VOp : uint32_t {
     V_NOP = 0, V_LDCOL, V_LDI, V_LDROW, V_MOV, V_SEL,
@@ -32,14 +32,34 @@ enum VOp : uint32_t {
     V_FCMP_EQ, V_FCMP_NE, V_FCMP_LT, V_FCMP_LE, V_FCMP_GT, V_FCMP_GE,
     V_IFLOORDIV, V_IMOD, V_FDIV, V_FMOD, V_FFLOORDIV, V_FILTER, V_RAISE, V_COUNT
 };
-// planner flags of a micro-op (DInstr.pad0)
+// planner flags of a micro-op
 enum VFlag : uint32_t {
-    VX_A_ACC = 1,    // operand a = the accumulator (result of the previous micro-op) instead of a slot
-    VX_B_ACC = 2,    // operand b likewise
-    VX_NOSTORE = 4,  // nobody reads the result from its slot: keep it in the accumulator only
-    VX_FILTER = 8,   // boolean result: rows with 0 leave the pipeline (the FILTER that followed, fused)
-    VX_A_MASK = 16,  // integer compares: a <- a & imm2 first (the x % 2^k that preceded, fused)
+    VX_A_ACC = 1,     // operand a = the accumulator (result of the previous micro-op) instead of a slot
+    VX_B_ACC = 2,     // operand b likewise (only together with VX_A_ACC: loading a would overwrite the accumulator)
+    VX_NOSTORE = 4,   // nobody reads the result from its slot: keep it in the accumulator only
+    VX_FILTER = 8,    // boolean result: rows with 0 leave the pipeline (the FILTER that followed, fused)
+    VX_A_MASK = 16,   // integer compares: a <- a & imm2 first (the x % 2^k that preceded, fused)
+    // set by the encoder (vec_encode), not by the planner:
+    VX_LOAD_A = 32,   // the op reads a and it is not in the accumulator: load it first
+    VX_RESULT = 64,   // the op produces a value (everything but FILTER / RAISE)
+    VX_A_THREAD = 128,  // operand a is a slot (per-thread address, stride SLAB); clear = a constant pair inside the instruction
+    VX_B_THREAD = 256,  // operand b likewise
 };
+
+// Device format of a micro-op: operands are ADDRESSES, so that a slot and a constant are read by the same 128-bit shared-memory
+// load (a constant is a pair [v, v] inside the instruction itself, read by all lanes at once: stride 0, no per-thread offset).
+struct __align__(16) VInstr {
+    uint32_t op_opidx;  // vop | opidx << 16
+    uint32_t xf;        // VFlag bits
+    uint32_t dst;       // byte offset of the destination slot from the start of the register file, NOOFF = none
+    uint32_t guard;     // likewise, NOOFF = unguarded
+    uint32_t pa, pb;    // operands a, b: byte offset from the start of shared memory (slot: its first row; constant: the pair below)
+    uint32_t pc;        // operand c (SEL condition): byte offset of its slot from the start of the register file
+    uint32_t pad;
+    uint64_t kb[2];     // [imm, imm]: constant b; scalar immediates (column index, shift count, exception code)
+    uint64_t ka[2];     // [imm2, imm2]: constant a, or the mask of VX_A_MASK
+};
+static_assert(sizeof(VInstr) == 64, "VInstr layout");
 
 template <int J>
 struct VecVM {
@@ -67,19 +87,19 @@ struct VecVM {
         exc_stage[lr] = code | (opidx << 16);
     }
 
-    // rb = regs base + tid * 16. tile_row0 = first input row of the tile; full = the tile has T rows (uniform).
-    static __device__ void run(const DInstr *__restrict__ prog, uint32_t n_instr, uint8_t *__restrict__ rb, const ColIn *__restrict__ cols,
-                               uint64_t tile_row0, uint64_t n_rows, bool full, State &st, uint32_t *__restrict__ exc_stage) {
-        ulonglong2 acc[J];
+    // smem = start of shared memory (operand addresses), rb = register file + tid * 16. tile_row0 = first input row of the tile;
+    // full = the tile has T rows (uniform).
+    static __device__ void run(const VInstr *__restrict__ prog, uint32_t n_instr, const uint8_t *__restrict__ smem, uint8_t *__restrict__ rb,
+                               const ColIn *__restrict__ cols, uint64_t tile_row0, uint64_t n_rows, bool full, State &st,
+                               uint32_t *__restrict__ exc_stage) {
+        const uint32_t tid16 = threadIdx.x * 16;
+        ulonglong2 acc[J];  // the accumulator: operand a on entry to an op, its result on exit
 #pragma unroll
         for (uint32_t j = 0; j < J; ++j) acc[j] = make_ulonglong2(0, 0);
         for (uint32_t pc = 0; pc < n_instr; ++pc) {
             const uint4 w0 = *reinterpret_cast<const uint4 *>(&prog[pc]);
-            const uint4 w1 = *reinterpret_cast<const uint4 *>(&prog[pc].c);
-            const ulonglong2 w2 = *reinterpret_cast<const ulonglong2 *>(&prog[pc].imm);
-            const uint32_t op = w0.x & 0xFF, flags = (w0.x >> 8) & 0xFF, opidx = w0.x >> 16;
-            const uint32_t dst = w0.y, a = w0.z, b = w0.w, c = w1.x, guard = w1.y, xf = w1.z;
-            const uint64_t imm = w2.x, imm2 = w2.y;
+            const uint4 w1 = *reinterpret_cast<const uint4 *>(&prog[pc].pa);
+            const uint32_t op = w0.x & 0xFFFF, opidx = w0.x >> 16, xf = w0.y, dst = w0.z, guard = w0.w;
             uint32_t act = st.alive;  // rows this instruction executes for
             const bool guarded = guard != NOOFF;
             if (guarded) {
@@ -91,77 +111,65 @@ struct VecVM {
                 }
                 if (!__any_sync(0xFFFFFFFFu, act != 0)) continue;  // untaken branch: the warp skips the op
             }
-            // operands: the accumulator, a constant riding in the immediates (a <- imm2, b <- imm, c <- imm2), or a slot
-#define LDA(j) ((xf & VX_A_ACC) ? acc[j] : ((flags & TPLX_F_A_CONST) ? make_ulonglong2(imm2, imm2) : ld2(rb, a, j)))
-#define LDB(j) ((xf & VX_B_ACC) ? acc[j] : ((flags & TPLX_F_B_CONST) ? make_ulonglong2(imm, imm) : ld2(rb, b, j)))
-            // result: unguarded ops produce both rows unconditionally (a row that is not alive never reaches an output);
-            // guarded ops must leave the destination of rows outside the guard untouched (phi of an if-converted branch)
-#define STD(j, R0, R1)                                                                     \
-    do {                                                                                   \
-        ulonglong2 _r = make_ulonglong2((R0), (R1));                                       \
-        if (guarded) {                                                                     \
-            const ulonglong2 _o = ld2(rb, dst, j);                                         \
-            if (!((act >> (2 * (j))) & 1u)) _r.x = _o.x;                                   \
-            if (!((act >> (2 * (j) + 1)) & 1u)) _r.y = _o.y;                               \
-        }                                                                                  \
-        acc[j] = _r;                                                                       \
-        if (!(xf & VX_NOSTORE)) st2(rb, dst, j, _r);                                       \
-    } while (0)
+            if (xf & VX_LOAD_A) {
+                const uint8_t *pA = smem + w1.x + ((xf & VX_A_THREAD) ? tid16 : 0u);
+                const uint32_t sA = (xf & VX_A_THREAD) ? SLAB : 0u;
+#pragma unroll
+                for (uint32_t j = 0; j < J; ++j) acc[j] = *reinterpret_cast<const ulonglong2 *>(pA + j * sA);
+            }
+            const uint8_t *pB = smem + w1.y + ((xf & VX_B_THREAD) ? tid16 : 0u);
+            const uint32_t sB = (xf & VX_B_THREAD) ? SLAB : 0u;
+#define LB(j) (*reinterpret_cast<const ulonglong2 *>(pB + (j) * sB))
+            // binary op on (accumulator, b): b is the accumulator itself (x * x), or one 128-bit load per two rows
 #define BIN(EXPR)                                                                          \
-    _Pragma("unroll") for (uint32_t j = 0; j < J; ++j) {                                   \
-        const ulonglong2 A = LDA(j), B = LDB(j);                                           \
-        uint64_t r0, r1;                                                                   \
-        { const uint64_t x = A.x, y = B.x; r0 = (EXPR); }                                  \
-        { const uint64_t x = A.y, y = B.y; r1 = (EXPR); }                                  \
-        STD(j, r0, r1);                                                                    \
+    if (xf & VX_B_ACC) {                                                                   \
+        _Pragma("unroll") for (uint32_t j = 0; j < J; ++j) {                               \
+            { const uint64_t x = acc[j].x, y = x; acc[j].x = (uint64_t)(EXPR); }           \
+            { const uint64_t x = acc[j].y, y = x; acc[j].y = (uint64_t)(EXPR); }           \
+        }                                                                                  \
+    } else {                                                                               \
+        _Pragma("unroll") for (uint32_t j = 0; j < J; ++j) {                               \
+            const ulonglong2 B = LB(j);                                                    \
+            { const uint64_t x = acc[j].x, y = B.x; acc[j].x = (uint64_t)(EXPR); }         \
+            { const uint64_t x = acc[j].y, y = B.y; acc[j].y = (uint64_t)(EXPR); }         \
+        }                                                                                  \
     }                                                                                      \
     break
 #define UNA(EXPR)                                                                          \
     _Pragma("unroll") for (uint32_t j = 0; j < J; ++j) {                                   \
-        const ulonglong2 A = LDA(j);                                                       \
-        uint64_t r0, r1;                                                                   \
-        { const uint64_t x = A.x; r0 = (EXPR); }                                           \
-        { const uint64_t x = A.y; r1 = (EXPR); }                                           \
-        STD(j, r0, r1);                                                                    \
+        { const uint64_t x = acc[j].x; acc[j].x = (uint64_t)(EXPR); }                      \
+        { const uint64_t x = acc[j].y; acc[j].y = (uint64_t)(EXPR); }                      \
     }                                                                                      \
     break
-            // boolean results: optionally the filter itself (planner: unguarded only, so act == alive)
-#define PRED(MASKED, EXPR)                                                                 \
+            // integer compares: optionally on (a & mask) — the x % 2^k that preceded
+#define ICMP(EXPR)                                                                         \
     {                                                                                      \
-        const uint64_t msk = (MASKED) && (xf & VX_A_MASK) ? imm2 : ~0ull;                  \
+        const uint64_t msk = (xf & VX_A_MASK) ? prog[pc].ka[0] : ~0ull;                    \
         _Pragma("unroll") for (uint32_t j = 0; j < J; ++j) {                               \
-            const ulonglong2 A = LDA(j), B = LDB(j);                                       \
-            uint64_t r0, r1;                                                               \
-            { const uint64_t x = A.x & msk, y = B.x; (void)y; r0 = (uint64_t)(EXPR); }     \
-            { const uint64_t x = A.y & msk, y = B.y; (void)y; r1 = (uint64_t)(EXPR); }     \
-            STD(j, r0, r1);                                                                \
-            if (xf & VX_FILTER) {                                                          \
-                if (!r0) st.alive &= ~(1u << (2 * j));                                     \
-                if (!r1) st.alive &= ~(2u << (2 * j));                                     \
-            }                                                                              \
+            const ulonglong2 B = (xf & VX_B_ACC) ? acc[j] : LB(j);                         \
+            { const int64_t x = (int64_t)(acc[j].x & msk), y = (int64_t)B.x; acc[j].x = (uint64_t)(EXPR); } \
+            { const int64_t x = (int64_t)(acc[j].y & msk), y = (int64_t)B.y; acc[j].y = (uint64_t)(EXPR); } \
         }                                                                                  \
-        if ((xf & VX_FILTER) && !__any_sync(0xFFFFFFFFu, st.alive != 0)) return;           \
     }                                                                                      \
     break
 #define F(x) __longlong_as_double((long long)(x))
 #define U(d) ((uint64_t)__double_as_longlong(d))
-            // ops that can raise: evaluated row by row for the active rows only, operands and result in slots
+            // ops that can raise: row by row for the active rows only; a raising row leaves the pipeline
 #define RAISING(...)                                                                       \
     _Pragma("unroll") for (uint32_t v = 0; v < V; ++v) {                                   \
         if (!((act >> v) & 1u)) continue;                                                  \
-        const uint32_t off8 = (v >> 1) * SLAB + (v & 1) * 8;                               \
-        const uint64_t x = (flags & TPLX_F_A_CONST) ? imm2 : *reinterpret_cast<const uint64_t *>(rb + a + off8); \
-        const uint64_t y = (flags & TPLX_F_B_CONST) ? imm : *reinterpret_cast<const uint64_t *>(rb + b + off8);  \
-        uint64_t r;                                                                        \
+        const ulonglong2 Bv = LB(v >> 1);                                                  \
+        const uint64_t x = (v & 1) ? acc[v >> 1].y : acc[v >> 1].x, y = (v & 1) ? Bv.y : Bv.x; \
+        uint64_t r = 0;                                                                    \
         bool bad = false;                                                                  \
         __VA_ARGS__;                                                                       \
         if (bad) raise_row(st, v, TPLX_EC_ZERODIVISIONERROR, opidx, exc_stage, lrow(v >> 1, v & 1)); \
-        else *reinterpret_cast<uint64_t *>(rb + dst + off8) = r;                           \
+        if (v & 1) acc[v >> 1].y = r; else acc[v >> 1].x = r;                              \
     }                                                                                      \
     break
             switch (op) {
                 case V_LDCOL: {
-                    const uint64_t *src = reinterpret_cast<const uint64_t *>(cols[imm].data);
+                    const uint64_t *src = reinterpret_cast<const uint64_t *>(cols[prog[pc].kb[0]].data);
 #ifdef __CUDA_ARCH__
                     __builtin_assume(__isGlobal(src));
 #endif
@@ -171,27 +179,30 @@ struct VecVM {
                         ulonglong2 v = make_ulonglong2(0, 0);
                         if (full || row + 1 < n_rows) v = *reinterpret_cast<const ulonglong2 *>(src + row);  // 16-byte aligned: row is even, base is
                         else if (row < n_rows) v.x = src[row];
-                        STD(j, v.x, v.y);
+                        acc[j] = v;
                     }
                     break;
                 }
-                case V_LDI:
+                case V_LDI: {
+                    const uint64_t imm = prog[pc].kb[0];
 #pragma unroll
-                    for (uint32_t j = 0; j < J; ++j) STD(j, imm, imm);
+                    for (uint32_t j = 0; j < J; ++j) acc[j] = make_ulonglong2(imm, imm);
                     break;
+                }
                 case V_LDROW:
 #pragma unroll
                     for (uint32_t j = 0; j < J; ++j) {
                         const uint64_t row = tile_row0 + lrow(j, 0);
-                        STD(j, row, row + 1);
+                        acc[j] = make_ulonglong2(row, row + 1);
                     }
                     break;
-                case V_MOV: UNA(x);
+                case V_MOV: break;  // a is already in the accumulator
                 case V_SEL:
 #pragma unroll
                     for (uint32_t j = 0; j < J; ++j) {
-                        const ulonglong2 A = LDA(j), B = LDB(j), Cn = ld2(rb, c, j);
-                        STD(j, Cn.x ? A.x : B.x, Cn.y ? A.y : B.y);
+                        const ulonglong2 B = (xf & VX_B_ACC) ? acc[j] : LB(j), Cn = ld2(rb, w1.z, j);
+                        if (!Cn.x) acc[j].x = B.x;
+                        if (!Cn.y) acc[j].y = B.y;
                     }
                     break;
                 case V_IADD: BIN(x + y);
@@ -203,8 +214,8 @@ struct VecVM {
                 case V_IXOR: BIN(x ^ y);
                 case V_ISHL: BIN(x << (y & 63));
                 case V_ISHR: BIN((uint64_t)((int64_t)x >> (y & 63)));
-                case V_ISHRK: UNA((uint64_t)((int64_t)x >> (imm & 63)));
-                case V_IANDK: UNA(x & imm);
+                case V_ISHRK: { const uint32_t k = (uint32_t)prog[pc].kb[0] & 63; UNA((uint64_t)((int64_t)x >> k)); }
+                case V_IANDK: { const uint64_t m = prog[pc].kb[0]; UNA(x & m); }
                 case V_IABS: UNA((int64_t)x < 0 ? (uint64_t)0 - x : x);
                 case V_FADD: BIN(U(__dadd_rn(F(x), F(y))));
                 case V_FSUB: BIN(U(__dsub_rn(F(x), F(y))));
@@ -213,22 +224,22 @@ struct VecVM {
                 case V_FABS: UNA(x & 0x7FFFFFFFFFFFFFFFull);
                 case V_I2F: UNA(U((double)(int64_t)x));
                 case V_F2I: UNA((uint64_t)(int64_t)F(x));
-                case V_BAND: PRED(false, (x != 0) & (y != 0));
-                case V_BOR: PRED(false, (x != 0) | (y != 0));
-                case V_BNOT: PRED(false, x == 0);
-                case V_ICMP_EQ: PRED(true, x == y);
-                case V_ICMP_NE: PRED(true, x != y);
-                case V_ICMP_LT: PRED(true, (int64_t)x < (int64_t)y);
-                case V_ICMP_LE: PRED(true, (int64_t)x <= (int64_t)y);
-                case V_ICMP_GT: PRED(true, (int64_t)x > (int64_t)y);
-                case V_ICMP_GE: PRED(true, (int64_t)x >= (int64_t)y);
+                case V_BAND: BIN((x != 0) & (y != 0));
+                case V_BOR: BIN((x != 0) | (y != 0));
+                case V_BNOT: UNA(x == 0);
+                case V_ICMP_EQ: ICMP(x == y);
+                case V_ICMP_NE: ICMP(x != y);
+                case V_ICMP_LT: ICMP(x < y);
+                case V_ICMP_LE: ICMP(x <= y);
+                case V_ICMP_GT: ICMP(x > y);
+                case V_ICMP_GE: ICMP(x >= y);
                 // ordered predicates: false when either side is NaN
-                case V_FCMP_EQ: PRED(false, F(x) == F(y));
-                case V_FCMP_NE: PRED(false, (F(x) < F(y)) || (F(x) > F(y)));
-                case V_FCMP_LT: PRED(false, F(x) < F(y));
-                case V_FCMP_LE: PRED(false, F(x) <= F(y));
-                case V_FCMP_GT: PRED(false, F(x) > F(y));
-                case V_FCMP_GE: PRED(false, F(x) >= F(y));
+                case V_FCMP_EQ: BIN(F(x) == F(y));
+                case V_FCMP_NE: BIN((F(x) < F(y)) || (F(x) > F(y)));
+                case V_FCMP_LT: BIN(F(x) < F(y));
+                case V_FCMP_LE: BIN(F(x) <= F(y));
+                case V_FCMP_GT: BIN(F(x) > F(y));
+                case V_FCMP_GE: BIN(F(x) >= F(y));
                 case V_IFLOORDIV: RAISING({ if ((int64_t)y == 0) bad = true; else r = (uint64_t)floordiv_i64((int64_t)x, (int64_t)y); });
                 case V_IMOD: RAISING({ if ((int64_t)y == 0) bad = true; else r = (uint64_t)floormod_i64((int64_t)x, (int64_t)y); });
                 case V_FDIV: RAISING({ if (F(y) == 0.0) bad = true; else r = U(__ddiv_rn(F(x), F(y))); });
@@ -248,28 +259,50 @@ struct VecVM {
                 case V_FILTER:
 #pragma unroll
                     for (uint32_t j = 0; j < J; ++j) {
-                        const ulonglong2 A = LDA(j);
-                        if (A.x == 0) st.alive &= ~(act & (1u << (2 * j)));
-                        if (A.y == 0) st.alive &= ~(act & (2u << (2 * j)));
+                        if (acc[j].x == 0) st.alive &= ~(act & (1u << (2 * j)));
+                        if (acc[j].y == 0) st.alive &= ~(act & (2u << (2 * j)));
                     }
                     if (!__any_sync(0xFFFFFFFFu, st.alive != 0)) return;  // the warp is empty: nothing that follows can execute
                     break;
-                case V_RAISE:
+                case V_RAISE: {
+                    const uint32_t code = (uint32_t)prog[pc].kb[0];
 #pragma unroll
                     for (uint32_t v = 0; v < V; ++v)
-                        if ((act >> v) & 1u) raise_row(st, v, (uint32_t)imm, opidx, exc_stage, lrow(v >> 1, v & 1));
+                        if ((act >> v) & 1u) raise_row(st, v, code, opidx, exc_stage, lrow(v >> 1, v & 1));
                     break;
+                }
                 default: break;
             }
-#undef LDA
-#undef LDB
-#undef STD
+#undef LB
 #undef BIN
 #undef UNA
-#undef PRED
+#undef ICMP
 #undef F
 #undef U
 #undef RAISING
+            // ---- result: merge under a guard, store unless nobody reads the slot, filter ----
+            if (xf & VX_RESULT) {
+                if (guarded) {  // rows outside the guard keep the old destination (phi of an if-converted branch)
+#pragma unroll
+                    for (uint32_t j = 0; j < J; ++j) {
+                        const ulonglong2 o = ld2(rb, dst, j);
+                        if (!((act >> (2 * j)) & 1u)) acc[j].x = o.x;
+                        if (!((act >> (2 * j + 1)) & 1u)) acc[j].y = o.y;
+                    }
+                }
+                if (!(xf & VX_NOSTORE)) {
+#pragma unroll
+                    for (uint32_t j = 0; j < J; ++j) st2(rb, dst, j, acc[j]);
+                }
+                if (xf & VX_FILTER) {  // unguarded (planner): act == alive
+#pragma unroll
+                    for (uint32_t j = 0; j < J; ++j) {
+                        if (acc[j].x == 0) st.alive &= ~(1u << (2 * j));
+                        if (acc[j].y == 0) st.alive &= ~(2u << (2 * j));
+                    }
+                    if (!__any_sync(0xFFFFFFFFu, st.alive != 0)) return;
+                }
+            }
         }
     }
 };
@@ -288,7 +321,8 @@ __device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t *p) {
 }
 
 // K1v kernel: persistent CTAs, ticketed tiles of T = 2J * 256 rows.
-// Shared memory: prog | cols | regs (n_slots x T x 8 B; output columns are staged in place) | misc: s_cnt[8J] exc_stage[T] scan scratch.
+// Shared memory: prog (VInstr) | cols | regs (n_slots x T x 8 B; output columns are staged in place) | misc: s_cnt[8J] exc_stage[T]
+// scan scratch, tickets.
 // Row order inside a tile: slab j (512 rows), warp w (64 rows), lane (2 rows). s_cnt[j * 8 + w] = kept | raised << 16 of that group.
 template <int J>
 __global__ void __launch_bounds__(NT, 4) stage_rows_vec_kernel(const __grid_constant__ KParams P) {  // parameters in the constant bank
@@ -297,23 +331,25 @@ __global__ void __launch_bounds__(NT, 4) stage_rows_vec_kernel(const __grid_cons
     constexpr uint32_t T = VecVM<J>::T, G = 8 * J;  // G = (slab, warp) groups per tile (<= 32)
     static_assert(G <= 32, "one scan lane per (slab, warp) group");
 
-    DInstr *s_prog = reinterpret_cast<DInstr *>(smem);
+    VInstr *s_prog = reinterpret_cast<VInstr *>(smem);
     ColIn *s_cols = reinterpret_cast<ColIn *>(smem + P.smem_cols_off);
     uint8_t *s_regs = smem + P.smem_regs_off;
     uint32_t *s_cnt = reinterpret_cast<uint32_t *>(smem + P.smem_misc_off);
     uint32_t *exc_stage = s_cnt + 32;
     uint64_t *s_scr = reinterpret_cast<uint64_t *>(exc_stage + T);  // look-back scratch: 2 words per warp
-    uint32_t *s_ctl = reinterpret_cast<uint32_t *>(s_scr + 2 * (NT / 32));
+    uint32_t *s_ctl = reinterpret_cast<uint32_t *>(s_scr + 2 * (NT / 32));  // [0] ticket
 
-    for (uint32_t i = tid; i < P.n_instr * (sizeof(DInstr) / 16); i += NT)
+    for (uint32_t i = tid; i < P.n_instr * (sizeof(VInstr) / 16); i += NT)
         reinterpret_cast<uint4 *>(s_prog)[i] = reinterpret_cast<const uint4 *>(P.prog)[i];
     for (uint32_t i = tid; i < P.n_in * (sizeof(ColIn) / 8); i += NT)
         reinterpret_cast<uint64_t *>(s_cols)[i] = reinterpret_cast<const uint64_t *>(P.in)[i];
     uint8_t *rb = s_regs + tid * 16;
     const uint32_t lt = (1u << lane) - 1u;
 
+    // Tickets are taken when the tile starts, not ahead of time: a ticket held while its owner still works on the previous tile
+    // stalls the look-back of every later tile (measured: 103 -> 77 G rows/s on C1 with one ticket of lookahead).
     while (true) {
-        __syncthreads();
+        __syncthreads();  // s_cnt, the ticket and the look-back scratch are rewritten below
         if (tid == 0) s_ctl[0] = atomicAdd(&P.counters[0], 1u);
         __syncthreads();
         const uint32_t tile = s_ctl[0];
@@ -330,7 +366,7 @@ __global__ void __launch_bounds__(NT, 4) stage_rows_vec_kernel(const __grid_cons
             for (uint32_t v = 0; v < 2 * J; ++v)
                 if (base + VecVM<J>::lrow(v >> 1, v & 1) < P.n_rows) st.alive |= 1u << v;
         }
-        VecVM<J>::run(s_prog, P.n_instr, rb, s_cols, base, P.n_rows, full, st, exc_stage);
+        VecVM<J>::run(s_prog, P.n_instr, smem, rb, s_cols, base, P.n_rows, full, st, exc_stage);
 
         // ---- counts per (slab, warp) group ----
         const bool warp_exc = __any_sync(0xFFFFFFFFu, st.exc != 0);
