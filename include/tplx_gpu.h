@@ -73,6 +73,9 @@ typedef struct tplx_result_info {
     uint32_t kernel_launches;
     uint32_t zero_copy_cols; /* run_host: input columns read in place from page-locked host memory (late materialisation) */
     uint64_t h2d_bytes;      /* run_host: bytes of input explicitly copied host->device */
+    uint32_t specialised_launches; /* of kernel_launches: kernels the stage specialiser compiled for this stage (csrc/jit.inl);
+                                      0 = the interpreting kernels ran */
+    uint32_t pad_info;
 } tplx_result_info;
 
 /* ---- process / devices ------------------------------------------------------------------ */
@@ -91,6 +94,16 @@ int32_t tplx_gpu_device_info(int32_t device, char *name_buf, int32_t buf_len, in
  * (TransformStage.cc:763-914): validates the program and sizes launch configuration. */
 int32_t tplx_gpu_stage_create(const void *desc, uint64_t desc_bytes, tplx_stage **out);
 int32_t tplx_gpu_stage_destroy(tplx_stage *stage);
+/* The stage specialiser (csrc/jit.inl) — this library's counterpart of the reference's per-stage code generation + JIT
+ * (StageBuilder.cc:602-1143, TransformStage::compile TransformStage.cc:763-914): for a stage that sees large blocks the op program
+ * is printed as a straight-line CUDA row function and the library's own kernel source is compiled around it at run time (NVRTC,
+ * sm_100a) and launched instead of the interpreting kernel — same parameters, same tiles / scans / exception records.
+ * Controlled by TPLX_JIT (0 off, 1 = stages with blocks of >= TPLX_JIT_MIN_ROWS rows [default], 2 = always); when NVRTC is not
+ * installed the interpreting kernels run. This entry point is the diagnostic view of it and needs no device: the generated row
+ * function of `kind` (1 = K1 rows, 2 / 3 = K1v with 8 / 4 rows per thread, 4 = K3 aggregate, 5 = K1m mask, 6 = K4 hash) as text,
+ * and, with compile != 0, the size of the cubin NVRTC produced for it (0 + the compiler log when it failed / NVRTC is absent). */
+int32_t tplx_gpu_stage_specialise(tplx_stage *stage, int32_t kind, int32_t compile, char *src, uint64_t src_cap, uint64_t *src_len,
+                                  uint64_t *cubin_bytes, char *log, uint64_t log_cap);
 /* Diagnostic (needs no device): the micro-op program the fixed-width row kernel (K1v) would run for this stage — the planner's
  * accumulator chains, fused compare/filter and dense slot numbers — so that the plan can be checked against the op program on
  * the host. n_uops = 0: the stage is not eligible for K1v. out may be NULL (sizes only); out_slots gets the dense slot of every

@@ -37,7 +37,8 @@ class CExceptionRec(ct.Structure):
 class CResultInfo(ct.Structure):
     _fields_ = [("n_in_rows", ct.c_uint64), ("n_out_rows", ct.c_uint64), ("n_exceptions", ct.c_uint64),
                 ("out_str_bytes", ct.c_uint64 * MAX_COLS), ("kernel_ms", ct.c_double), ("total_ms", ct.c_double),
-                ("kernel_launches", ct.c_uint32), ("zero_copy_cols", ct.c_uint32), ("h2d_bytes", ct.c_uint64)]
+                ("kernel_launches", ct.c_uint32), ("zero_copy_cols", ct.c_uint32), ("h2d_bytes", ct.c_uint64),
+                ("specialised_launches", ct.c_uint32), ("pad_info", ct.c_uint32)]
 
 
 class CCsvDesc(ct.Structure):
@@ -78,6 +79,7 @@ def lib():
         "tplx_gpu_stage_create": ([vp, u64, P(vp)], i32),
         "tplx_gpu_stage_destroy": ([vp], i32),
         "tplx_gpu_stage_vec_plan": ([vp, vp, u32, P(u32), P(u32), vp, u32], i32),
+        "tplx_gpu_stage_specialise": ([vp, i32, i32, ct.c_char_p, u64, P(u64), P(u64), ct.c_char_p, u64], i32),
         "tplx_gpu_block_upload": ([i32, P(CColumn), u32, u64, P(vp)], i32),
         "tplx_gpu_block_wrap_device": ([i32, P(CColumn), u32, u64, P(vp)], i32),
         "tplx_gpu_block_from_partitions": ([i32, P(vp), P(u64), u32, P(ct.c_uint8), u32, P(vp)], i32),
@@ -284,6 +286,16 @@ class Stage:
                "tplx_gpu_stage_vec_plan")
         uops = [{k: int(r[k]) for k in dt.names if not k.startswith("pad")} for r in buf]
         return uops, ns.value, [int(x) for x in outs[:n_out]]
+
+    def specialise(self, kind: int, compile: bool = True):
+        """(generated CUDA row function, cubin size, compiler log) of the stage specialiser for kernel `kind`
+        (tplx_gpu_stage_specialise; needs no device). cubin size 0 = NVRTC absent or the compile failed (see the log)."""
+        n, nb = ct.c_uint64(), ct.c_uint64()
+        src = ct.create_string_buffer(1 << 20)
+        log = ct.create_string_buffer(1 << 16)
+        _check(lib().tplx_gpu_stage_specialise(self._h, kind, 1 if compile else 0, src, len(src), ct.byref(n), ct.byref(nb), log, len(log)),
+               "tplx_gpu_stage_specialise")
+        return src.value.decode(), int(nb.value), log.value.decode(errors="replace")
 
     def close(self):
         if self._h:

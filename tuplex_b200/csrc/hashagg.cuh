@@ -181,6 +181,7 @@ __device__ __forceinline__ void atomic_acc_global(uint32_t kind, uint64_t *p, ui
     }
 }
 
+#ifndef TPLX_JIT
 // fill accumulator arrays with identities
 __global__ void hash_init_accs(HashTableDev T, uint32_t n_accs, const AccP *accs_dev_unused, uint32_t k0, uint32_t kind) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -410,5 +411,7 @@ static inline void hash_table_destroy(HashTable *t) {
     cudaFree(t->d.counters);
     delete t;
 }
+
+#endif  // !TPLX_JIT
 
 }  // namespace tplx

@@ -321,12 +321,31 @@ __device__ __forceinline__ void rows_tile_finish(const KParams &P, const TileSme
     }
 }
 
+// ---- stage specialiser (jit.inl) ----------------------------------------------------------------------------------------------
+// When this header is compiled at run time by NVRTC (TPLX_JIT), "jit_row.cuh" is the op program of ONE stage printed as a
+// straight-line function (jit_run / jit_row_fixed) and exactly one kernel of the library is compiled around it, as
+// `tplx_jit_kernel`: TPLX_JIT_KIND 1 = K1 rows, 2 / 3 = K1v (J = 4 / 2), 4 = K3 aggregate, 5 = K1m mask, 6 = K4 hash.
+// The register file of a specialised kernel is COMPACT: it holds the live-out slots only (outputs, accumulator inputs), in the
+// order the host's jit::liveout() numbered them; KParams carries those compact slot numbers.
+#ifdef TPLX_JIT
+__device__ __forceinline__ void jit_touch(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#include "jit_row.cuh"
+#define TPLX_VM_RUN(prog, n_instr, regs, cols, row, w, cpool, t) jit_run(regs, cols, row, w, cpool, t)
+#else
+#define TPLX_VM_RUN(prog, n_instr, regs, cols, row, w, cpool, t) VM<NT>::run(prog, 0, n_instr, regs, cols, row, w, cpool, t)
+#endif
+
 // =============================================================================================
 // K1: rows in -> rows out
 // =============================================================================================
 // Shared memory map (byte offsets from KParams): prog | cols | regs | staging | misc
 // misc: keep_bits[W] exc_bits[W] keep_pre[W+1] exc_pre[W+1] exc_stage[T] scan scratch
+#if !defined(TPLX_JIT) || TPLX_JIT_KIND == 1
+#ifdef TPLX_JIT
+extern "C" __global__ void __launch_bounds__(NT, TPLX_JIT_MINB) tplx_jit_kernel(const __grid_constant__ KParams P) {
+#else
 __global__ void __launch_bounds__(NT) stage_rows_kernel(const __grid_constant__ KParams P) {  // parameters in the constant bank
+#endif
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t R = P.R, T = R * NT, W = T / 32, K = P.K;
@@ -407,7 +426,10 @@ __global__ void __launch_bounds__(NT) stage_rows_kernel(const __grid_constant__ 
             const uint64_t row = P.rowlist ? (valid ? P.rowlist[w] : 0) : w;
             t.alive = valid;
             t.exc_code = 0;
-            VM<NT>::run(s_prog, 0, P.n_instr, s_regs, s_cols, row, w, P.cpool, t);
+#ifdef TPLX_JIT
+            if (P.rowlist && valid && !P.pad_split) jit_prefetch(s_cols, row, w);  // pad_split = 1: switched off (TPLX_JIT_PREFETCH=0)
+#endif
+            TPLX_VM_RUN(s_prog, P.n_instr, s_regs, s_cols, row, w, P.cpool, t);
             const bool exc = t.exc_code != 0;
             const uint32_t kb = __ballot_sync(0xFFFFFFFFu, t.alive);
             const uint32_t eb = __ballot_sync(0xFFFFFFFFu, exc);
@@ -424,13 +446,19 @@ __global__ void __launch_bounds__(NT) stage_rows_kernel(const __grid_constant__ 
                          R, T, W, K, state_stride, n_tiles);
     }
 }
+#endif  // K1
 
 // =============================================================================================
 // K3: rows in -> aggregate (fixed reduction tree; see DESIGN.md "reduction tree")
 //   thread t of a tile folds local rows t, t+NT, ... in order from the identity,
 //   warp tree via shfl_down 16,8,4,2,1, warps combined sequentially -> tile partial.
 // =============================================================================================
+#if !defined(TPLX_JIT) || TPLX_JIT_KIND == 4
+#ifdef TPLX_JIT
+extern "C" __global__ void __launch_bounds__(NT, TPLX_JIT_MINB) tplx_jit_kernel(const KParams *__restrict__ Pg) {
+#else
 __global__ void __launch_bounds__(NT) stage_agg_kernel(const KParams *__restrict__ Pg) {
+#endif
     extern __shared__ __align__(16) uint8_t smem[];
     const KParams &P = *Pg;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -462,7 +490,7 @@ __global__ void __launch_bounds__(NT) stage_agg_kernel(const KParams *__restrict
             t.alive = row < P.n_rows;
             t.exc_code = 0;
             t.scr_used = 0;
-            VM<NT>::run(s_prog, 0, P.n_instr, s_regs, s_cols, row, row, P.cpool, t);
+            TPLX_VM_RUN(s_prog, P.n_instr, s_regs, s_cols, row, row, P.cpool, t);
             if (t.alive) {
 #pragma unroll
                 for (uint32_t k = 0; k < TPLX_MAX_ACCS; ++k)
@@ -503,6 +531,9 @@ __global__ void __launch_bounds__(NT) stage_agg_kernel(const KParams *__restrict
     }
 }
 
+#endif  // K3
+
+#ifndef TPLX_JIT
 // thread t folds tile partials t, t+FIN_NT, ... in order; warp tree; warps sequential; then init (+) total
 __global__ void __launch_bounds__(FIN_NT) agg_finalize_kernel(const KParams *__restrict__ Pg) {
     __shared__ uint64_t s_w[FIN_NT / 32];
@@ -529,5 +560,6 @@ __global__ void __launch_bounds__(FIN_NT) agg_finalize_kernel(const KParams *__r
         __syncthreads();
     }
 }
+#endif  // !TPLX_JIT
 
 }  // namespace tplx

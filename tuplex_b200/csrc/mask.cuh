@@ -145,8 +145,15 @@ __device__ __forceinline__ void scan_eval(const MaskParams &P, const ColIn *__re
 // The parameter block travels by value in the kernel's constant bank (__grid_constant__): every P.field below is a constant-bank
 // operand instead of a global load through a pointer (terms, column table, offsets — read in the per-row loops).
 // MINB: resident CTAs per SM the register allocation must allow (4 = 64 registers, 5 = 48, 6 = 40).
+#if !defined(TPLX_JIT) || TPLX_JIT_KIND == 5
+#ifdef TPLX_JIT
+// specialised K1m (stage specialiser, jit.inl): the prefilter program as straight-line code, no register file at all (the bitmaps carry the result)
+extern "C" __global__ void __launch_bounds__(NT, TPLX_JIT_MINB) tplx_jit_kernel(const __grid_constant__ MaskParams P) {
+    constexpr bool SCAN = false;
+#else
 template <bool SCAN, int MINB = 4>
 __global__ void __launch_bounds__(NT, MINB) stage_mask_kernel(const __grid_constant__ MaskParams P) {
+#endif
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t MR = P.MR, TR = 32 * MR, ns = P.n_staged;
@@ -235,7 +242,7 @@ __global__ void __launch_bounds__(NT, MINB) stage_mask_kernel(const __grid_const
             t.exc_code = 0;
             t.scr_used = 0;
             if (SCAN) { if (ns) scan_eval<false>(P, s_wcols, row, t); else scan_eval<true>(P, s_wcols, row, t); }
-            else VM<NT>::run(s_prog, 0, P.n_instr, s_regs, s_wcols, row, row, P.cpool, t);
+            else TPLX_VM_RUN(s_prog, P.n_instr, s_regs, s_wcols, row, row, P.cpool, t);
             const bool exc = t.exc_code != 0;
             const uint32_t kb = __ballot_sync(0xFFFFFFFFu, t.alive);
             const uint32_t eb = __ballot_sync(0xFFFFFFFFu, exc);
@@ -248,6 +255,9 @@ __global__ void __launch_bounds__(NT, MINB) stage_mask_kernel(const __grid_const
         __syncwarp();  // every lane is done with this ring slot
     }
 }
+#endif  // K1m
+
+#ifndef TPLX_JIT
 
 // ---------------------------------------------------------------------------------------------------------
 // bitmaps -> ascending survivor list + exception records (three small launches; the bitmaps are n_rows / 8 bytes)
@@ -336,5 +346,7 @@ __global__ void __launch_bounds__(CMP_NT) mask_expand_kernel(const uint32_t *__r
         ++eo;
     }
 }
+
+#endif  // !TPLX_JIT
 
 }  // namespace tplx

@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -27,6 +28,7 @@
 #include "mask.cuh"
 #include "vecvm.cuh"
 #include "csv.cuh"
+#include "jit.inl"
 
 using namespace tplx;
 
@@ -410,6 +412,7 @@ struct StageDev {
     uint8_t *cpool = nullptr;
     int64_t *opids = nullptr;
     HashTable *ht = nullptr;  // HASH endpoint
+    std::map<int, jit::Loaded> jit_fn;  // specialised kernels of this stage on this device, by jit::Kind
 };
 
 struct tplx_stage {
@@ -436,6 +439,10 @@ struct tplx_stage {
     std::vector<tplx_scan_term> scan; // string-scan hint (closed form of a pure filter chain), empty = none
     bool has_fused = false;           // closed-form scan-aggregate hint present and valid
     FusedParams fused{};
+    // stage specialiser (jit.inl): live-out slots (the compact register file of the specialised kernels), one binary per kernel kind
+    jit::LiveOut jit_live;
+    std::map<int, std::shared_ptr<jit::Binary>> jit_bin;
+    bool jit_hot = false;             // a block large enough to pay for the compile has been seen
     std::mutex mu;
 };
 
@@ -620,6 +627,7 @@ extern "C" int32_t tplx_gpu_stage_create(const void *desc, uint64_t desc_bytes, 
         if ((in.op == TPLX_OP_SEL || in.op == TPLX_OP_MOV) && (in.flags & 3) != 1) s->vec_ok = false;
     }
     if (s->vec_ok) s->vplan = vec_plan(s->instrs, s->out_cols, h.n_slots);
+    s->jit_live = jit::liveout(s->out_cols, s->accs, h.n_slots);
     *out = s;
     return TPLX_OK;
 }
@@ -643,6 +651,84 @@ static std::vector<DInstr> predecode(const std::vector<tplx_instr> &ins, uint32_
         out[i] = d;
     }
     return out;
+}
+
+// ---- stage specialiser: compile (once per stage and kernel kind) and load (once per device) -------------------------------------
+static std::shared_ptr<jit::Binary> jit_binary(tplx_stage *s, int kind, int minb) {  // s->mu held
+    auto it = s->jit_bin.find(kind);
+    if (it != s->jit_bin.end()) return it->second;
+    auto bin = std::make_shared<jit::Binary>();
+    jit::compile(*bin, jit::generate(s->hdr, s->instrs, s->in_types, s->jit_live, kind), kind, minb);
+    if (getenv("TPLX_TRACE") || (bin->failed && getenv("TPLX_JIT_VERBOSE")))
+        fprintf(stderr, "[tplx] specialiser: kind %d, %zu instructions -> %zu B cubin in %.0f ms%s%s\n", kind, s->instrs.size(), bin->cubin.size(), bin->compile_ms,
+                bin->failed ? " FAILED: " : "", bin->failed ? bin->log.c_str() : "");
+    if (const char *dir = getenv("TPLX_JIT_DUMP")) {  // evidence / debugging: the generated row function and the cubin
+        const std::string base = std::string(dir) + "/tplx_jit_k" + std::to_string(kind) + "_" + std::to_string(s->instrs.size()) + "ins";
+        if (FILE *f = fopen((base + ".cuh").c_str(), "w")) { fwrite(bin->source.data(), 1, bin->source.size(), f); fclose(f); }
+        if (!bin->failed)
+            if (FILE *f = fopen((base + ".cubin").c_str(), "wb")) { fwrite(bin->cubin.data(), 1, bin->cubin.size(), f); fclose(f); }
+    }
+    s->jit_bin[kind] = bin;
+    return bin;
+}
+// resident CTAs per SM the specialised kernel's register allocation must allow (measured on B200, profiles/r02_jit.md)
+static int jit_minb(const tplx_stage *s, int kind) {
+    auto env = [](const char *n, int dflt) { const char *e = getenv(n); return e && atoi(e) > 0 ? atoi(e) : dflt; };
+    switch (kind) {
+        case jit::K_VEC4: case jit::K_VEC4P: return env("TPLX_JIT_MINB_VEC", 6);
+        case jit::K_VEC2: return env("TPLX_JIT_MINB_VEC", 3);
+        case jit::K_MASK: return env("TPLX_JIT_MINB_MASK", 4);
+        default: return env("TPLX_JIT_MINB", 3);
+    }
+}
+static bool jit_wanted(tplx_stage *s, uint64_t block_rows) {
+    const int m = jit::mode();
+    if (m <= 0 || s->instrs.empty()) return false;
+    if (m >= 2 || block_rows >= jit::min_rows()) s->jit_hot = true;
+    return s->jit_hot;
+}
+// nullptr: not available (NVRTC / driver entry points missing, compile or load failed) — the interpreting kernel runs instead
+static jit::Loaded *jit_get(tplx_stage *s, StageDev *sd, int kind, int minb) {
+    std::lock_guard<std::mutex> lk(s->mu);
+    auto it = sd->jit_fn.find(kind);
+    if (it != sd->jit_fn.end()) return it->second.failed ? nullptr : &it->second;
+    jit::Loaded ld;
+    jit::CuDrv *cu = jit::cudrv_api();
+    std::shared_ptr<jit::Binary> bin = jit_binary(s, kind, minb);
+    if (!cu || bin->failed) ld.failed = true;
+    if (!ld.failed) {
+        cudaSetDevice(sd->dev->id);
+        cudaFree(0);  // the runtime's primary context is current on this thread
+        int rc = cu->ModuleLoadData(&ld.mod, bin->cubin.data());
+        if (!rc) rc = cu->ModuleGetFunction(&ld.fn, ld.mod, "tplx_jit_kernel");
+        if (!rc) rc = cu->FuncSetAttribute(ld.fn, jit::CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, sd->dev->smem_optin);
+        if (!rc) cu->FuncGetAttribute(&ld.regs, jit::CU_FUNC_ATTRIBUTE_NUM_REGS, ld.fn);
+        if (rc) {
+            const char *msg = nullptr;
+            cu->GetErrorString(rc, &msg);
+            if (getenv("TPLX_TRACE") || getenv("TPLX_JIT_VERBOSE")) fprintf(stderr, "[tplx] specialiser: loading kind %d failed: %s\n", kind, msg ? msg : "?");
+            ld.failed = true;
+        } else if (getenv("TPLX_TRACE"))
+            fprintf(stderr, "[tplx] specialiser: kind %d loaded on device %d, %d registers/thread\n", kind, sd->dev->id, ld.regs);
+    }
+    auto &slot = sd->jit_fn[kind];
+    slot = ld;
+    return slot.failed ? nullptr : &slot;
+}
+static int32_t jit_launch(jit::Loaded *jf, uint32_t grid, uint32_t smem, cudaStream_t st, const void *params) {
+    void *args[] = {const_cast<void *>(params)};
+    const int rc = jit::cudrv_api()->LaunchKernel(jf->fn, grid, 1, 1, NT, 1, 1, smem, (void *)st, args, nullptr);
+    if (rc) {
+        const char *msg = nullptr;
+        jit::cudrv_api()->GetErrorString(rc, &msg);
+        return fail(TPLX_E_CUDA, std::string("specialised kernel launch: ") + (msg ? msg : "?"));
+    }
+    return TPLX_OK;
+}
+static int jit_occupancy(jit::Loaded *jf, uint32_t smem) {
+    int occ = 0;
+    if (jit::cudrv_api()->OccupancyMaxActiveBlocksPerMultiprocessor(&occ, jf->fn, NT, smem)) occ = 0;
+    return occ;
 }
 
 static int32_t stage_dev(tplx_stage *s, Device *d, StageDev **out) {
@@ -694,6 +780,35 @@ extern "C" int32_t tplx_gpu_stage_vec_plan(const tplx_stage *s, tplx_vec_uop *ou
     return TPLX_OK;
 }
 
+extern "C" int32_t tplx_gpu_stage_specialise(tplx_stage *s, int32_t kind, int32_t compile, char *src, uint64_t src_cap, uint64_t *src_len,
+                                             uint64_t *cubin_bytes, char *log, uint64_t log_cap) {
+    if (!s || kind < jit::K_ROWS || kind > jit::K_VEC4P || kind == jit::K_HASH) return fail(TPLX_E_BADARG, "stage_specialise: bad arguments");
+    if ((kind == jit::K_VEC4 || kind == jit::K_VEC2 || kind == jit::K_VEC4P) && !s->vec_ok) return fail(TPLX_E_UNSUPPORTED, "stage_specialise: not a fixed-width MEMORY stage");
+    std::string text;
+    size_t nb = 0;
+    std::string lg;
+    if (compile) {
+        std::lock_guard<std::mutex> lk(s->mu);
+        std::shared_ptr<jit::Binary> bin = jit_binary(s, kind, jit_minb(s, kind));
+        text = bin->source;
+        nb = bin->failed ? 0 : bin->cubin.size();
+        lg = bin->log;
+    } else text = jit::generate(s->hdr, s->instrs, s->in_types, s->jit_live, kind);
+    if (src_len) *src_len = text.size();
+    if (src && src_cap) {
+        const size_t n = std::min<size_t>(text.size(), src_cap - 1);
+        memcpy(src, text.data(), n);
+        src[n] = 0;
+    }
+    if (cubin_bytes) *cubin_bytes = nb;
+    if (log && log_cap) {
+        const size_t n = std::min<size_t>(lg.size(), log_cap - 1);
+        memcpy(log, lg.data(), n);
+        log[n] = 0;
+    }
+    return TPLX_OK;
+}
+
 extern "C" int32_t tplx_gpu_stage_destroy(tplx_stage *s) {
     if (!s) return TPLX_OK;
     for (auto &sd : s->devs) {
@@ -705,6 +820,8 @@ extern "C" int32_t tplx_gpu_stage_destroy(tplx_stage *s) {
         cudaFree(sd.cpool);
         cudaFree(sd.opids);
         if (sd.ht) hash_table_destroy(sd.ht);
+        for (auto &kv : sd.jit_fn)
+            if (kv.second.mod) jit::cudrv_api()->ModuleUnload(kv.second.mod);
     }
     if (s->prefilter) tplx_gpu_stage_destroy(s->prefilter);
     delete s;
@@ -825,6 +942,7 @@ struct tplx_result {
     uint64_t h2d_bytes = 0;       // explicit host->device copies of inputs (run_host)
     uint32_t zero_copy_cols = 0;  // input columns read in place from page-locked host memory
     uint32_t launches = 0;
+    uint32_t jit_launches = 0;  // of those: kernels produced by the stage specialiser
     bool owns_block = false;
     tplx_block *owned_block = nullptr;
     // mask stage temporaries (run_mask), needed when the exception records have to be expanded again with the exact capacity
@@ -854,15 +972,16 @@ struct Layout {
     std::vector<uint32_t> col_stage_off;
 };
 // inplace (rows endpoint, R == 1): no staging area, the write phase reads the outputs from the register file
-static Layout make_layout(const tplx_stage *s, uint32_t R, bool rows_ep, bool inplace = false) {
+// jit: layout of the specialised kernel — no program in shared memory, the register file holds the live-out slots only
+static Layout make_layout(const tplx_stage *s, uint32_t R, bool rows_ep, bool inplace = false, bool jit = false) {
     Layout L;
     L.inplace = inplace && rows_ep && R == 1;
     const uint32_t T = R * NT, W = T / 32;
-    size_t off = align_up(std::max<size_t>(s->instrs.size(), 1) * sizeof(DInstr), 16);
+    size_t off = jit ? 16 : align_up(std::max<size_t>(s->instrs.size(), 1) * sizeof(DInstr), 16);
     L.cols_off = (uint32_t)off;
     off = align_up(off + std::max<size_t>(s->in_types.size(), 1) * sizeof(ColIn), 16);
     L.regs_off = (uint32_t)off;
-    uint32_t nslots = std::max<uint32_t>(std::max<uint32_t>(s->hdr.n_slots, s->n_str_out), 1);
+    uint32_t nslots = std::max<uint32_t>(std::max<uint32_t>(jit ? (uint32_t)s->jit_live.slots.size() : s->hdr.n_slots, s->n_str_out), 1);
     off = align_up(off + (size_t)nslots * NT * 8, 16);
     L.stage_off = (uint32_t)off;
     if (rows_ep) {
@@ -1131,9 +1250,30 @@ static int32_t run_rows_vec(tplx_stage *s, StageDev *sd, const tplx_block *b, in
         smem = (uint32_t)align_up(off, 16);
         if (smem <= 72 * 1024 || (J == 2 && smem <= (uint32_t)d->smem_optin)) { Jsel = J; break; }
     }
+    // specialised K1v (jit.inl): the register file holds the live-out slots only; J = 4 (8 rows per thread) when that fits, else J = 2
+    jit::Loaded *jf = nullptr;
+    if (jit_wanted(s, n)) {
+        const uint32_t nl = std::max<uint32_t>((uint32_t)s->jit_live.slots.size(), 1);
+        for (int J : {4, 2}) {
+            const uint32_t Tj = 2u * J * NT;
+            size_t off = 16;
+            const uint32_t c_off = (uint32_t)off;
+            off = align_up(off + std::max<size_t>(s->in_types.size(), 1) * sizeof(ColIn), 16);
+            const uint32_t r_off = (uint32_t)off;
+            off = align_up(off + (size_t)nl * Tj * 8, 16);
+            const uint32_t m_off = (uint32_t)off;
+            off += 32 * 4 + (size_t)Tj * 4 + (size_t)(2 * (NT / 32)) * 8 + 16;
+            if (align_up(off, 16) > (J == 4 ? 56u * 1024 : 100u * 1024)) continue;
+            const bool pipe = J == 4 && getenv("TPLX_JIT_VEC_PIPE") && atoi(getenv("TPLX_JIT_VEC_PIPE"));
+            const int kind = J == 4 ? (pipe ? jit::K_VEC4P : jit::K_VEC4) : jit::K_VEC2;
+            jf = jit_get(s, sd, kind, jit_minb(s, kind));
+            if (jf) { Jsel = J; T = Tj; cols_off = c_off; regs_off = r_off; misc_off = m_off; smem = (uint32_t)align_up(off, 16); }
+            break;
+        }
+    }
     if (!Jsel) return TPLX_E_UNSUPPORTED;
     const int ji = Jsel == 4 ? 1 : 0;
-    if (!sd->prog_vec[ji]) {
+    if (!jf && !sd->prog_vec[ji]) {
         std::lock_guard<std::mutex> lk(s->mu);
         if (!sd->prog_vec[ji]) {
             std::vector<VInstr> dec = vec_encode(s->vplan, T, regs_off);
@@ -1152,13 +1292,14 @@ static int32_t run_rows_vec(tplx_stage *s, StageDev *sd, const tplx_block *b, in
     KParams P;
     fill_common(P, s, sd, b, L, 2 * Jsel);
     P.prog = sd->prog_vec[ji];
-    P.n_instr = (uint32_t)n_uops;
-    P.n_slots = ns;
+    P.n_instr = jf ? 0u : (uint32_t)n_uops;
+    P.n_slots = jf ? (uint32_t)s->jit_live.slots.size() : ns;
 
     P.n_tiles = (uint32_t)((n + T - 1) / T);
     P.first_row_no = first_row_no;
     int occ = 0;
-    if (Jsel == 4) {
+    if (jf) occ = jit_occupancy(jf, smem);
+    else if (Jsel == 4) {
         CU(cudaFuncSetAttribute(stage_rows_vec_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stage_rows_vec_kernel<4>, NT, smem));
     } else {
@@ -1197,7 +1338,7 @@ static int32_t run_rows_vec(tplx_stage *s, StageDev *sd, const tplx_block *b, in
         oc.slot = s->out_cols[c].slot;
         oc.type = s->out_cols[c].type;
         oc.strk = -1;
-        oc.stage_off = (uint32_t)s->vplan.slot_map[s->out_cols[c].slot] * T * 8;
+        oc.stage_off = (jf ? (uint32_t)s->jit_live.map[s->out_cols[c].slot] : (uint32_t)s->vplan.slot_map[s->out_cols[c].slot]) * T * 8;
         rc = dalloc(r, &oc.data, n);
         if (rc) return rc;
     }
@@ -1210,8 +1351,9 @@ static int32_t run_rows_vec(tplx_stage *s, StageDev *sd, const tplx_block *b, in
         CU(cudaMemsetAsync(tile_state, 0, state_words * 8, d->stream));
         CU(cudaMemsetAsync(counters, 0, 16, d->stream));
         CU(cudaMemsetAsync(totals, 0, MAX_SCAN * 8, d->stream));
-        rc = Jsel == 4 ? launch_rows_vec<4>(grid, smem, d->stream, P) : launch_rows_vec<2>(grid, smem, d->stream, P);
+        rc = jf ? jit_launch(jf, grid, smem, d->stream, &P) : Jsel == 4 ? launch_rows_vec<4>(grid, smem, d->stream, P) : launch_rows_vec<2>(grid, smem, d->stream, P);
         if (rc) return rc;
+        if (jf) r->jit_launches += 1;
         CU(cudaGetLastError());
         r->launches += 1;
         uint64_t h_tot[MAX_SCAN];
@@ -1265,38 +1407,46 @@ static int32_t run_rows(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_
     }
     // tile shape: the largest tile (fewest barrier / look-back episodes, best load balance inside the CTA) that does
     // not cost occupancy: the register-limited number of resident CTAs divides the SM's shared memory into budgets
+    // specialised K1 (jit.inl): same kernel source around the generated row function, compact register file
+    jit::Loaded *jf = nullptr;
+    if (jit_wanted(s, b->n_rows)) {
+        jf = jit_get(s, sd, jit::K_ROWS, jit_minb(s, jit::K_ROWS));
+    }
     int occ_regs = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_regs, stage_rows_kernel, NT, 0));
+    if (jf) occ_regs = jit_occupancy(jf, 0);
+    else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_regs, stage_rows_kernel, NT, 0));
     occ_regs = std::max(occ_regs, 1);
     const uint32_t env_R = getenv("TPLX_TILE_R") ? (uint32_t)atoi(getenv("TPLX_TILE_R")) : 0;
     uint32_t smem_budget = (uint32_t)(d->prop.sharedMemPerMultiprocessor / occ_regs) - 1024;
     uint32_t R = env_R ? env_R : 16;
     const bool allow_inplace = !(getenv("TPLX_NO_INPLACE") && atoi(getenv("TPLX_NO_INPLACE")));
-    Layout L = make_layout(s, R, true);
+    Layout L = make_layout(s, R, true, false, jf != nullptr);
     while (R > 1 && L.total > smem_budget) {
         R /= 2;
-        L = make_layout(s, R, true, allow_inplace);  // one row per thread: no staging area, outputs are read from the register file
+        L = make_layout(s, R, true, allow_inplace, jf != nullptr);  // one row per thread: no staging area, outputs are read from the register file
     }
     if (L.total > smem_budget && !(L.inplace && L.total <= (uint32_t)d->smem_optin)) {
         // even one row per thread does not fit the budget: give up occupancy instead
         smem_budget = (uint32_t)std::min<int>(d->smem_optin, 113 * 1024);
         R = env_R ? env_R : 4;
-        L = make_layout(s, R, true);
+        L = make_layout(s, R, true, false, jf != nullptr);
         while (R > 1 && L.total > smem_budget) {
             R /= 2;
-            L = make_layout(s, R, true, allow_inplace);
+            L = make_layout(s, R, true, allow_inplace, jf != nullptr);
         }
     }
     if (L.total > (uint32_t)d->smem_optin) return fail(TPLX_E_UNSUPPORTED, "stage needs more shared memory than one SM has");
     int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stage_rows_kernel, NT, L.total));
+    if (jf) occ = jit_occupancy(jf, L.total);
+    else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stage_rows_kernel, NT, L.total));
     if (occ < 1) return fail(TPLX_E_UNSUPPORTED, "stage kernel cannot be resident");
     // String stages read their input bytes through L1 again and again (every string op walks the bytes): shared memory must not
     // take the whole 256 KB of the SM. Measured on the Zillow dense launch (B200): 3 CTAs/SM + 60 KB L1 0.413 ms, 4 CTAs/SM + 28 KB L1
     // 0.54 ms, 2 CTAs/SM + 124 KB L1 0.53 ms. So the carve-out is capped at 196 KB (85 % of 228) and occupancy counted against it.
     int carve = s->has_str ? 85 : -1;
     if (getenv("TPLX_DENSE_CARVEOUT")) carve = atoi(getenv("TPLX_DENSE_CARVEOUT"));
-    CU(cudaFuncSetAttribute(stage_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    if (jf) jit::cudrv_api()->FuncSetAttribute(jf->fn, jit::CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, carve);
+    else CU(cudaFuncSetAttribute(stage_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     if (carve > 0 && carve < 100) {
         static const int steps_kb[] = {8, 16, 32, 64, 100, 132, 164, 196, 228};
         int cfg = 228;
@@ -1306,9 +1456,14 @@ static int32_t run_rows(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_
     }
     if (getenv("TPLX_DENSE_OCC") && atoi(getenv("TPLX_DENSE_OCC")) > 0) occ = std::min(occ, atoi(getenv("TPLX_DENSE_OCC")));
     if (getenv("TPLX_TRACE"))
-        fprintf(stderr, "[tplx] rows kernel: R %u, shared memory %u B (%s), %d CTAs/SM\n", R, L.total, L.inplace ? "in place" : "staged", occ);
+        fprintf(stderr, "[tplx] rows kernel%s: R %u, shared memory %u B (%s), %d CTAs/SM\n", jf ? " (specialised)" : "", R, L.total, L.inplace ? "in place" : "staged", occ);
     KParams P;
     fill_common(P, s, sd, b, L, R);
+    if (jf) {
+        P.n_instr = 0;
+        P.n_slots = (uint32_t)s->jit_live.slots.size();
+        P.pad_split = (getenv("TPLX_JIT_PREFETCH") && !atoi(getenv("TPLX_JIT_PREFETCH"))) ? 1u : 0u;
+    }
     if (cols_override)
         for (size_t c = 0; c < cols_override->size(); ++c) P.in[c] = (*cols_override)[c];
     P.rowlist = rowlist;
@@ -1356,7 +1511,7 @@ static int32_t run_rows(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_
         int si = 0;
         for (size_t c = 0; c < s->out_cols.size(); ++c) {
             OutCol &oc = P.out[c];
-            oc.slot = s->out_cols[c].slot;
+            oc.slot = jf ? (uint32_t)s->jit_live.map[s->out_cols[c].slot] : s->out_cols[c].slot;
             oc.type = s->out_cols[c].type;
             oc.stage_off = L.col_stage_off[c];
             if (oc.type == TPLX_T_STR) {
@@ -1381,7 +1536,11 @@ static int32_t run_rows(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_
         CU(cudaMemsetAsync(counters, 0, 16, d->stream));
         CU(cudaMemsetAsync(totals, 0, MAX_SCAN * 8, d->stream));
         CU(cudaEventRecord(r->evk0, d->stream));
-        stage_rows_kernel<<<grid, NT, L.total, d->stream>>>(P);
+        if (jf) {
+            rc = jit_launch(jf, grid, L.total, d->stream, &P);
+            if (rc) return rc;
+            r->jit_launches += 1;
+        } else stage_rows_kernel<<<grid, NT, L.total, d->stream>>>(P);
         CU(cudaGetLastError());
         CU(cudaEventRecord(r->evk1, d->stream));
         r->launches += 1;
@@ -1446,7 +1605,17 @@ static int32_t run_mask(tplx_stage *ps, StageDev *psd, const tplx_block *b, tplx
     P.n_in = (uint32_t)ps->in_types.size();
     P.n_slots = std::max<uint32_t>(ps->hdr.n_slots, 1);
     // K1f: the planner stated the stage in closed form (string-scan hint) -> evaluate the terms directly, nothing is interpreted
-    const bool scan = !ps->scan.empty() && !(getenv("TPLX_NO_SCAN") && atoi(getenv("TPLX_NO_SCAN")));
+    bool scan = !ps->scan.empty() && !(getenv("TPLX_NO_SCAN") && atoi(getenv("TPLX_NO_SCAN")));
+    // specialised K1m (jit.inl): for prefilters without a closed form (TPLX_JIT_MASK=1: also instead of the closed form, to compare)
+    jit::Loaded *jf = nullptr;
+    if ((!scan || (getenv("TPLX_JIT_MASK") && atoi(getenv("TPLX_JIT_MASK")))) && jit_wanted(ps, n)) {
+        jf = jit_get(ps, psd, jit::K_MASK, jit_minb(ps, jit::K_MASK));
+        if (jf) {
+            scan = false;
+            P.n_slots = 0;  // no register file: nothing is live out of a prefilter program
+            P.n_instr = 0;
+        }
+    }
     if (scan) {
         P.n_terms = (uint32_t)ps->scan.size();
         memcpy(P.terms, ps->scan.data(), ps->scan.size() * sizeof(tplx_scan_term));
@@ -1512,7 +1681,8 @@ static int32_t run_mask(tplx_stage *ps, StageDev *psd, const tplx_block *b, tplx
     int occ = 0;
     // closed-form kernel: register budget per thread traded for resident warps (TPLX_MASK_MINB = 4 | 5 | 6 CTAs per SM)
     const int minb = getenv("TPLX_MASK_MINB") ? atoi(getenv("TPLX_MASK_MINB")) : TPLX_MASK_MINB_DEFAULT;
-    if (scan && minb == 6) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stage_mask_kernel<true, 6>, NT, smem_total));
+    if (jf) occ = jit_occupancy(jf, smem_total);
+    else if (scan && minb == 6) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stage_mask_kernel<true, 6>, NT, smem_total));
     else if (scan && minb == 5) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stage_mask_kernel<true, 5>, NT, smem_total));
     else if (scan) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stage_mask_kernel<true, 4>, NT, smem_total));
     else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stage_mask_kernel<false>, NT, smem_total));
@@ -1537,7 +1707,11 @@ static int32_t run_mask(tplx_stage *ps, StageDev *psd, const tplx_block *b, tplx
     if (rc) return rc;
     rc = dalloc(ra, &totals, 2);
     if (rc) return rc;
-    if (scan && minb == 6) stage_mask_kernel<true, 6><<<grid, NT, smem_total, d->stream>>>(P);
+    if (jf) {
+        rc = jit_launch(jf, grid, smem_total, d->stream, &P);
+        if (rc) return rc;
+        ra->jit_launches += 1;
+    } else if (scan && minb == 6) stage_mask_kernel<true, 6><<<grid, NT, smem_total, d->stream>>>(P);
     else if (scan && minb == 5) stage_mask_kernel<true, 5><<<grid, NT, smem_total, d->stream>>>(P);
     else if (scan) stage_mask_kernel<true, 4><<<grid, NT, smem_total, d->stream>>>(P);
     else stage_mask_kernel<false><<<grid, NT, smem_total, d->stream>>>(P);
@@ -1647,6 +1821,7 @@ static int32_t run_rows_prefiltered(tplx_stage *s, StageDev *sd, const tplx_bloc
             if (rc) { drop_ra(); return rc; }
         }
         r->launches += ra.launches;
+        r->jit_launches += ra.jit_launches;
     }
     const uint64_t n_surv = ra.n_out;
     if (!no_wait) {
@@ -1732,6 +1907,7 @@ static int32_t run_rows_prefiltered(tplx_stage *s, StageDev *sd, const tplx_bloc
         rc = run_rows(s, sd, b, first_row_no, r, ra.out[0].data, n_surv, dense_cols.empty() ? nullptr : &dense_cols);
         if (rc) { drop_ra(); return rc; }
         r->launches += ra.launches;
+        r->jit_launches += ra.jit_launches;
     }
     r->kernel_ms_extra = msa + msg;
     const uint64_t na = ra.n_exc, nb = r->n_exc;
@@ -1891,13 +2067,23 @@ static int32_t run_agg(tplx_stage *s, StageDev *sd, const tplx_block *b, tplx_re
     Device *d = r->dev;
     const uint64_t n = b->n_rows;
     const uint32_t R = 16;
-    Layout L = make_layout(s, R, false);
+    // specialised K3 (jit.inl) for stages without a closed-form hint: compact register file = the accumulator inputs
+    jit::Loaded *jf = nullptr;
+    if (!(s->has_fused && !getenv("TPLX_NO_FUSED")) && jit_wanted(s, n))
+        jf = jit_get(s, sd, jit::K_AGG, jit_minb(s, jit::K_AGG));
+    Layout L = make_layout(s, R, false, false, jf != nullptr);
     if (L.total > (uint32_t)d->smem_optin) return fail(TPLX_E_UNSUPPORTED, "stage needs more shared memory than one SM has");
     int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stage_agg_kernel, NT, L.total));
+    if (jf) occ = jit_occupancy(jf, L.total);
+    else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stage_agg_kernel, NT, L.total));
     if (occ < 1) return fail(TPLX_E_UNSUPPORTED, "stage kernel cannot be resident");
     KParams P;
     fill_common(P, s, sd, b, L, R);
+    if (jf) {
+        P.n_instr = 0;
+        P.n_slots = (uint32_t)s->jit_live.slots.size();
+        for (size_t k = 0; k < s->accs.size(); ++k) P.accs[k].slot = (uint32_t)s->jit_live.map[s->accs[k].slot];
+    }
     const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(P.n_tiles, (uint32_t)(occ * d->prop.multiProcessorCount)));
     P.scratch_per_thread = s->materialises ? std::max<uint32_t>(s->hdr.scratch_bytes, 64) : 0;
     int32_t rc = ensure_scratch(d, (size_t)grid * NT * P.scratch_per_thread);
@@ -1926,6 +2112,12 @@ static int32_t run_agg(tplx_stage *s, StageDev *sd, const tplx_block *b, tplx_re
         if (P.n_tiles && s->has_fused && !getenv("TPLX_NO_FUSED")) {
             int32_t frc = launch_fused(s, d, dP, P, r);
             if (frc) return frc;
+        } else if (P.n_tiles && jf) {
+            const KParams *dPc = dP;
+            rc = jit_launch(jf, grid, L.total, d->stream, &dPc);
+            if (rc) return rc;
+            r->launches += 1;
+            r->jit_launches += 1;
         } else if (P.n_tiles) {
             stage_agg_kernel<<<grid, NT, L.total, d->stream>>>(dP);
             CU(cudaGetLastError());
@@ -1984,6 +2176,7 @@ extern "C" int32_t tplx_gpu_result_info(tplx_result *r, tplx_result_info *info) 
     info->kernel_ms = r->kernel_ms;
     info->total_ms = r->total_ms;
     info->kernel_launches = r->launches;
+    info->specialised_launches = r->jit_launches;
     info->zero_copy_cols = r->zero_copy_cols;
     info->h2d_bytes = r->h2d_bytes;
     return TPLX_OK;

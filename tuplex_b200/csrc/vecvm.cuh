@@ -324,8 +324,62 @@ __device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t *p) {
 // Shared memory: prog (VInstr) | cols | regs (n_slots x T x 8 B; output columns are staged in place) | misc: s_cnt[8J] exc_stage[T]
 // scan scratch, tickets.
 // Row order inside a tile: slab j (512 rows), warp w (64 rows), lane (2 rows). s_cnt[j * 8 + w] = kept | raised << 16 of that group.
+#ifdef TPLX_JIT
+// Specialised evaluation (stage specialiser, jit.inl): per two-row group one LDG.128 per used input column, the generated
+// straight-line row function for each of the two rows (slots in registers), one STS.128 per live-out slot into the compact
+// register file the tile tail reads. Same State / exc_stage protocol as VecVM::run.
+template <int J>
+__device__ __forceinline__ void jit_load_vec(ulonglong2 (&vin)[J][JIT_NIN], const ColIn *__restrict__ cols, uint64_t tile_row0, uint64_t n_rows, bool full) {
+#pragma unroll
+    for (uint32_t k = 0; k < JIT_NIN; ++k) {
+        const uint64_t *src = reinterpret_cast<const uint64_t *>(cols[jit_incol(k)].data);
+        __builtin_assume(__isGlobal(src));
+#pragma unroll
+        for (uint32_t j = 0; j < J; ++j) {
+            const uint64_t row = tile_row0 + VecVM<J>::lrow(j, 0);
+            ulonglong2 v = make_ulonglong2(0, 0);
+            if (full || row + 1 < n_rows) v = *reinterpret_cast<const ulonglong2 *>(src + row);  // 16-byte aligned: row is even, base is
+            else if (row < n_rows) v.x = src[row];
+            vin[j][k] = v;
+        }
+    }
+}
+template <int J>
+__device__ __forceinline__ void jit_eval_vec(const ulonglong2 (&vin)[J][JIT_NIN], uint8_t *__restrict__ rb, uint64_t tile_row0, typename VecVM<J>::State &st,
+                                             uint32_t *__restrict__ exc_stage) {
+#pragma unroll
+    for (uint32_t j = 0; j < J; ++j) {
+        const uint64_t row = tile_row0 + VecVM<J>::lrow(j, 0);
+        uint64_t in0[JIT_NIN], in1[JIT_NIN], o0[JIT_NLIVE], o1[JIT_NLIVE];
+#pragma unroll
+        for (uint32_t k = 0; k < JIT_NIN; ++k) { in0[k] = vin[j][k].x; in1[k] = vin[j][k].y; }
+#pragma unroll
+        for (uint32_t k = 0; k < JIT_NLIVE; ++k) { o0[k] = 0; o1[k] = 0; }
+        bool a0 = (st.alive >> (2 * j)) & 1u, a1 = (st.alive >> (2 * j + 1)) & 1u;
+        uint32_t e0 = 0, e1 = 0;
+        if (a0) jit_row_fixed(row, in0, a0, e0, o0);
+        if (a1) jit_row_fixed(row + 1, in1, a1, e1, o1);
+        if (!a0) st.alive &= ~(1u << (2 * j));
+        if (!a1) st.alive &= ~(2u << (2 * j));
+        if (e0) VecVM<J>::raise_row(st, 2 * j, e0 & 0xFFFFu, e0 >> 16, exc_stage, VecVM<J>::lrow(j, 0));
+        if (e1) VecVM<J>::raise_row(st, 2 * j + 1, e1 & 0xFFFFu, e1 >> 16, exc_stage, VecVM<J>::lrow(j, 1));
+#pragma unroll
+        for (uint32_t k = 0; k < JIT_NLIVE; ++k) VecVM<J>::st2(rb, k * VecVM<J>::SLOT_BYTES, j, make_ulonglong2(o0[k], o1[k]));
+    }
+}
+#endif
+
+#if !defined(TPLX_JIT) || TPLX_JIT_KIND == 2 || TPLX_JIT_KIND == 3 || TPLX_JIT_KIND == 7
+#ifdef TPLX_JIT
+// TPLX_JIT_KIND 7 = J 4 with the PIPELINED tile loop: the next ticket is taken as soon as this tile's counts are published and the
+// next tile's input is loaded (LDG.128 into registers) while this tile waits for its predecessors and writes.
+#define TPLX_JIT_PIPE (TPLX_JIT_KIND == 7)
+extern "C" __global__ void __launch_bounds__(NT, TPLX_JIT_MINB) tplx_jit_kernel(const __grid_constant__ KParams P) {
+    constexpr int J = TPLX_JIT_KIND == 3 ? 2 : 4;
+#else
 template <int J>
 __global__ void __launch_bounds__(NT, 4) stage_rows_vec_kernel(const __grid_constant__ KParams P) {  // parameters in the constant bank
+#endif
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr uint32_t T = VecVM<J>::T, G = 8 * J;  // G = (slab, warp) groups per tile (<= 32)
@@ -348,12 +402,21 @@ __global__ void __launch_bounds__(NT, 4) stage_rows_vec_kernel(const __grid_cons
 
     // Tickets are taken when the tile starts, not ahead of time: a ticket held while its owner still works on the previous tile
     // stalls the look-back of every later tile (measured: 103 -> 77 G rows/s on C1 with one ticket of lookahead).
+#if defined(TPLX_JIT) && TPLX_JIT_PIPE
+    ulonglong2 vin[J][JIT_NIN];
+    if (tid == 0) s_ctl[0] = atomicAdd(&P.counters[0], 1u);
+    __syncthreads();
+    uint32_t tile = s_ctl[0];
+    if (tile < P.n_tiles) jit_load_vec<J>(vin, s_cols, (uint64_t)tile * T, P.n_rows, (uint64_t)tile * T + T <= P.n_rows);
+    while (tile < P.n_tiles) {
+#else
     while (true) {
         __syncthreads();  // s_cnt, the ticket and the look-back scratch are rewritten below
         if (tid == 0) s_ctl[0] = atomicAdd(&P.counters[0], 1u);
         __syncthreads();
         const uint32_t tile = s_ctl[0];
         if (tile >= P.n_tiles) break;
+#endif
         const uint64_t base = (uint64_t)tile * T;
         const bool full = base + T <= P.n_rows;  // uniform
 
@@ -366,7 +429,17 @@ __global__ void __launch_bounds__(NT, 4) stage_rows_vec_kernel(const __grid_cons
             for (uint32_t v = 0; v < 2 * J; ++v)
                 if (base + VecVM<J>::lrow(v >> 1, v & 1) < P.n_rows) st.alive |= 1u << v;
         }
+#if defined(TPLX_JIT) && TPLX_JIT_PIPE
+        jit_eval_vec<J>(vin, rb, base, st, exc_stage);
+#elif defined(TPLX_JIT)
+        {
+            ulonglong2 vin[J][JIT_NIN];
+            jit_load_vec<J>(vin, s_cols, base, P.n_rows, full);
+            jit_eval_vec<J>(vin, rb, base, st, exc_stage);
+        }
+#else
         VecVM<J>::run(s_prog, P.n_instr, smem, rb, s_cols, base, P.n_rows, full, st, exc_stage);
+#endif
 
         // ---- counts per (slab, warp) group ----
         const bool warp_exc = __any_sync(0xFFFFFFFFu, st.exc != 0);
@@ -395,6 +468,13 @@ __global__ void __launch_bounds__(NT, 4) stage_rows_vec_kernel(const __grid_cons
         if (tid == 0)  // publish this tile's counts (tile 0: they are its inclusive prefix)
             st_cg_u64(P.tile_state + tile, ((uint64_t)(tile == 0 ? 2u : 1u) << 62) | ((uint64_t)n_keep << 31) | (uint64_t)n_exc);
 
+#if defined(TPLX_JIT) && TPLX_JIT_PIPE
+        // the counts are out: take the next ticket now and start loading that tile — the loads fly while this tile looks back and writes
+        if (tid == 0) s_ctl[1] = atomicAdd(&P.counters[0], 1u);
+        __syncthreads();
+        const uint32_t next_tile = s_ctl[1];
+        if (next_tile < P.n_tiles) jit_load_vec<J>(vin, s_cols, (uint64_t)next_tile * T, P.n_rows, (uint64_t)next_tile * T + T <= P.n_rows);
+#endif
         // ---- look-back: 256 predecessors per round ----
         uint64_t pre_keep = 0, pre_exc = 0;
         if (tile > 0) {
@@ -472,7 +552,11 @@ __global__ void __launch_bounds__(NT, 4) stage_rows_vec_kernel(const __grid_cons
                 }
             }
         }
+#if defined(TPLX_JIT) && TPLX_JIT_PIPE
+        tile = next_tile;
+#endif
     }
 }
+#endif  // K1v
 
 }  // namespace tplx

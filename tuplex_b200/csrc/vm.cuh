@@ -70,6 +70,183 @@ __device__ __forceinline__ void raise_exc(VMThread &t, uint32_t code, uint32_t o
     t.alive = false;
 }
 
+// ---- op bodies shared by the interpreter (VM::run below) and the stage specialiser's generated code (jit.inl): one
+// implementation of every non-trivial op, written on plain values (StrV views, integers), not on the register file ---------------
+#ifdef TPLX_JIT
+#define TPLX_OPFN_HEAVY __device__ __noinline__   // generated code may use an op several times: one out-of-line copy
+#else
+#define TPLX_OPFN_HEAVY __device__ __forceinline__
+#endif
+__device__ __forceinline__ bool op_icmp(uint32_t pred, int64_t x, int64_t y) {
+    switch (pred) {
+        case TPLX_CMP_EQ: return x == y;
+        case TPLX_CMP_NE: return x != y;
+        case TPLX_CMP_LT: return x < y;
+        case TPLX_CMP_LE: return x <= y;
+        case TPLX_CMP_GT: return x > y;
+        default: return x >= y;
+    }
+}
+__device__ __forceinline__ bool op_fcmp(uint32_t pred, double x, double y) {  // ordered predicates: false if either is NaN
+    switch (pred) {
+        case TPLX_CMP_EQ: return x == y;
+        case TPLX_CMP_NE: return (x < y) || (x > y);  // FCMP_ONE
+        case TPLX_CMP_LT: return x < y;
+        case TPLX_CMP_LE: return x <= y;
+        case TPLX_CMP_GT: return x > y;
+        default: return x >= y;
+    }
+}
+__device__ __forceinline__ double op_fmod(double x, double y) {  // y != 0
+    double r = fmod(x, y);  // == LLVM frem, exact
+    if (r != 0.0 && ((r < 0.0) != (y < 0.0))) r = __dadd_rn(r, y);
+    return r;
+}
+__device__ __forceinline__ StrV mk_strv(const uint8_t *p, uint32_t len, uint32_t flags) {
+    StrV v;
+    v.p = p;
+    v.len = len;
+    v.flags = flags;
+    return v;
+}
+__device__ __forceinline__ bool op_sstarts(const StrV &s, const StrV &p) {
+    bool r = p.len <= s.len;
+    for (uint32_t i = 0; r && i < p.len; ++i) r = sch(s, i) == sch(p, i);
+    return r;
+}
+__device__ __forceinline__ bool op_sends(const StrV &s, const StrV &p) {
+    bool r = p.len <= s.len;
+    for (uint32_t i = 0; r && i < p.len; ++i) r = sch(s, s.len - p.len + i) == sch(p, i);
+    return r;
+}
+__device__ __forceinline__ StrV op_sslice(const StrV &s, uint32_t flags, int64_t b, int64_t c) {
+    const int64_t len = s.len;
+    const int64_t st = (flags & TPLX_SL_HAS_START) ? slice_index(b, len) : 0;
+    const int64_t en = (flags & TPLX_SL_HAS_END) ? slice_index(c, len) : len;
+    if (st < en) return mk_strv(s.p + st, (uint32_t)(en - st), s.flags);
+    return mk_strv(s.p, 0, 0);
+}
+__device__ __forceinline__ bool op_sindex(const StrV &s, int64_t idx, StrV *out) {  // false = IndexError
+    if (idx < 0) idx += s.len;
+    if (idx < 0 || idx >= (int64_t)s.len) return false;
+    *out = mk_strv(s.p + idx, 1, s.flags);
+    return true;
+}
+__device__ __forceinline__ StrV op_sstrip(const StrV &s, uint32_t flags) {
+    uint32_t i = 0, e = s.len;
+    if (flags & 1) while (i < e && is_pyspace(s.p[i])) ++i;
+    if (flags & 2) while (e > i && is_pyspace(s.p[e - 1])) --e;
+    return mk_strv(s.p + i, e - i, s.flags);
+}
+// the materialising ops return false when the per-row scratch arena is exhausted (the row has been marked by scratch_alloc)
+__device__ __forceinline__ bool op_sconcat(VMThread &t, const StrV &x, const StrV &y, uint32_t opidx, StrV *out) {
+    // empty operand returns the other side unchanged (BlockGeneratorVisitor.cc:381-436)
+    if (x.len == 0) { *out = y; return true; }
+    if (y.len == 0) { *out = x; return true; }
+    uint8_t *o = scratch_alloc(t, x.len + y.len, opidx);
+    if (!o) return false;
+    str_copy(o, x);
+    str_copy(o + x.len, y);
+    *out = mk_strv(o, x.len + y.len, 0);
+    return true;
+}
+TPLX_OPFN_HEAVY bool op_sreplace(VMThread &t, const StrV &s, const StrV &f, const StrV &r, uint32_t opidx, StrV *out) {
+    // runtime/src/Runtime.cc:401-540
+    if (s.len == 0 || (f.len == 0 && r.len == 0)) { *out = s; return true; }
+    if (f.len == 0) {
+        uint32_t n = (r.len + 1) * s.len + r.len;
+        uint8_t *o = scratch_alloc(t, n, opidx);
+        if (!o) return false;
+        uint32_t pos = 0;
+        for (uint32_t i = 0; i < s.len; ++i) {
+            for (uint32_t j = 0; j < r.len; ++j) o[pos++] = sch(r, j);
+            o[pos++] = sch(s, i);
+        }
+        for (uint32_t j = 0; j < r.len; ++j) o[pos++] = sch(r, j);
+        *out = mk_strv(o, pos, 0);
+        return true;
+    }
+    if (f.len == 1 && s.flags == TPLX_SF_NONE && f.flags == TPLX_SF_NONE && r.flags == TPLX_SF_NONE) {
+        // single-character needle on a plain string (the common `.replace(',', '')`): two byte loops without case mapping
+        const uint8_t ch = f.p[0];
+        uint32_t cnt = 0;
+        for (uint32_t q = 0; q < s.len; ++q) cnt += s.p[q] == ch;
+        if (cnt == 0) { *out = mk_strv(s.p, s.len, 0); return true; }  // nothing to replace: the input itself (same bytes as a copy)
+        const uint32_t n1 = s.len + cnt * r.len - cnt;
+        uint8_t *o1 = scratch_alloc(t, n1 ? n1 : 1, opidx);
+        if (!o1) return false;
+        uint32_t w = 0;
+        for (uint32_t q = 0; q < s.len; ++q) {
+            const uint8_t b0 = s.p[q];
+            if (b0 == ch) for (uint32_t j = 0; j < r.len; ++j) o1[w++] = r.p[j];
+            else o1[w++] = b0;
+        }
+        *out = mk_strv(o1, n1, 0);
+        return true;
+    }
+    // count pass
+    uint32_t count = 0, i = 0;
+    while (i + f.len <= s.len) {
+        uint32_t j = 0;
+        while (j < f.len && sch(s, i + j) == sch(f, j)) ++j;
+        if (j == f.len) { ++count; i += f.len; } else ++i;
+    }
+    uint32_t n = s.len + count * r.len - count * f.len;
+    uint8_t *o = scratch_alloc(t, n ? n : 1, opidx);
+    if (!o) return false;
+    uint32_t pos = 0;
+    i = 0;
+    while (i < s.len) {
+        bool m = false;
+        if (i + f.len <= s.len) {
+            uint32_t j = 0;
+            while (j < f.len && sch(s, i + j) == sch(f, j)) ++j;
+            m = (j == f.len);
+        }
+        if (m) {
+            for (uint32_t j = 0; j < r.len; ++j) o[pos++] = sch(r, j);
+            i += f.len;
+        } else o[pos++] = sch(s, i++);
+    }
+    *out = mk_strv(o, pos, 0);
+    return true;
+}
+TPLX_OPFN_HEAVY bool op_sfmtd(VMThread &t, uint32_t flags, uint64_t raw, uint32_t width, uint32_t opidx, StrV *out) {
+    // '%[0]<w>d' % v: snprintf with C's %d, which consumes an int (BlockGeneratorVisitor.cc:675-775);
+    // flags bit1: '{:0<w>}'.format(v) / f-strings go through fmt and keep all 64 bits (Runtime.cc:544-607)
+    const int64_t v = (flags & 2) ? (int64_t)raw : (int64_t)(int32_t)(int64_t)raw;
+    uint64_t mag = v < 0 ? (uint64_t)0 - (uint64_t)v : (uint64_t)v;
+    uint32_t nd = 1;
+    for (uint64_t q = mag; q >= 10; q /= 10) ++nd;
+    uint32_t body = nd + (v < 0 ? 1 : 0);
+    uint32_t total = body > width ? body : width;
+    uint8_t *o = scratch_alloc(t, total, opidx);
+    if (!o) return false;
+    uint32_t padn = total - body, pos = 0;
+    if (flags & 1) {
+        if (v < 0) o[pos++] = '-';
+        for (uint32_t i = 0; i < padn; ++i) o[pos++] = '0';
+    } else {
+        for (uint32_t i = 0; i < padn; ++i) o[pos++] = ' ';
+        if (v < 0) o[pos++] = '-';
+    }
+    for (uint32_t i = 0; i < nd; ++i) { o[pos + nd - 1 - i] = (uint8_t)('0' + mag % 10); mag /= 10; }
+    *out = mk_strv(o, total, 0);
+    return true;
+}
+TPLX_OPFN_HEAVY bool op_i2s(VMThread &t, int64_t v, uint32_t opidx, StrV *out) {
+    uint64_t mag = v < 0 ? (uint64_t)0 - (uint64_t)v : (uint64_t)v;
+    uint32_t nd = 1;
+    for (uint64_t q = mag; q >= 10; q /= 10) ++nd;
+    uint32_t total = nd + (v < 0 ? 1 : 0);
+    uint8_t *o = scratch_alloc(t, total, opidx);
+    if (!o) return false;
+    if (v < 0) o[0] = '-';
+    for (uint32_t i = 0; i < nd; ++i) { o[total - 1 - i] = (uint8_t)('0' + mag % 10); mag /= 10; }
+    *out = mk_strv(o, total, 0);
+    return true;
+}
+
 template <int NT>
 struct VM {
     static constexpr uint32_t SLOT_BYTES = NT * 8;  // distance between consecutive slots of one thread
@@ -203,9 +380,7 @@ struct VM {
                 case TPLX_OP_FMOD: {
                     double x = FA(), y = FB();
                     if (y == 0.0) { raise_exc(t, TPLX_EC_ZERODIVISIONERROR, opidx); break; }
-                    double r = fmod(x, y);  // == LLVM frem, exact
-                    if (r != 0.0 && ((r < 0.0) != (y < 0.0))) r = __dadd_rn(r, y);
-                    WF(r);
+                    WF(op_fmod(x, y));
                     break;
                 }
                 case TPLX_OP_FNEG: R(rb, dst) = IA() ^ 0x8000000000000000ull; break;
@@ -220,34 +395,8 @@ struct VM {
                 }
                 case TPLX_OP_I2F: WF((double)(int64_t)IA()); break;
                 case TPLX_OP_F2I: R(rb, dst) = (uint64_t)(int64_t)FA(); break;
-                case TPLX_OP_ICMP: {
-                    int64_t x = (int64_t)IA(), y = (int64_t)IB();
-                    bool r;
-                    switch (flags & 7) {
-                        case TPLX_CMP_EQ: r = x == y; break;
-                        case TPLX_CMP_NE: r = x != y; break;
-                        case TPLX_CMP_LT: r = x < y; break;
-                        case TPLX_CMP_LE: r = x <= y; break;
-                        case TPLX_CMP_GT: r = x > y; break;
-                        default: r = x >= y; break;
-                    }
-                    R(rb, dst) = r;
-                    break;
-                }
-                case TPLX_OP_FCMP: {
-                    double x = FA(), y = FB();
-                    bool r;
-                    switch (flags & 7) {  // ordered predicates: false if either is NaN
-                        case TPLX_CMP_EQ: r = x == y; break;
-                        case TPLX_CMP_NE: r = (x < y) || (x > y); break;  // FCMP_ONE
-                        case TPLX_CMP_LT: r = x < y; break;
-                        case TPLX_CMP_LE: r = x <= y; break;
-                        case TPLX_CMP_GT: r = x > y; break;
-                        default: r = x >= y; break;
-                    }
-                    R(rb, dst) = r;
-                    break;
-                }
+                case TPLX_OP_ICMP: R(rb, dst) = op_icmp(flags & 7, (int64_t)IA(), (int64_t)IB()); break;
+                case TPLX_OP_FCMP: R(rb, dst) = op_fcmp(flags & 7, FA(), FB()); break;
                 case TPLX_OP_BAND: R(rb, dst) = (IA() != 0) & (IB() != 0); break;
                 case TPLX_OP_BOR: R(rb, dst) = (IA() != 0) | (IB() != 0); break;
                 case TPLX_OP_BNOT: R(rb, dst) = (IA() == 0); break;
@@ -268,35 +417,17 @@ struct VM {
                 case TPLX_OP_SIN: R(rb, dst) = str_find(SB(), SA()) >= 0; break;
                 case TPLX_OP_SEQ: R(rb, dst) = (uint64_t)(str_eq(SA(), SB()) != (bool)(flags & 1)); break;
                 case TPLX_OP_STRUTH: R(rb, dst) = SA().len != 0; break;
-                case TPLX_OP_SSTARTS: {
-                    StrV s = SA(), p = SB();
-                    bool r = p.len <= s.len;
-                    for (uint32_t i = 0; r && i < p.len; ++i) r = sch(s, i) == sch(p, i);
-                    R(rb, dst) = r;
-                    break;
-                }
-                case TPLX_OP_SENDS: {
-                    StrV s = SA(), p = SB();
-                    bool r = p.len <= s.len;
-                    for (uint32_t i = 0; r && i < p.len; ++i) r = sch(s, s.len - p.len + i) == sch(p, i);
-                    R(rb, dst) = r;
-                    break;
-                }
+                case TPLX_OP_SSTARTS: R(rb, dst) = op_sstarts(SA(), SB()); break;
+                case TPLX_OP_SENDS: R(rb, dst) = op_sends(SA(), SB()); break;
                 case TPLX_OP_SSLICE: {
-                    StrV s = SA();
-                    int64_t len = s.len;
-                    int64_t st = (flags & TPLX_SL_HAS_START) ? slice_index((int64_t)IB(), len) : 0;
-                    int64_t en = (flags & TPLX_SL_HAS_END) ? slice_index((int64_t)IC(), len) : len;
-                    if (st < en) WS(rb, dst, s.p + st, (uint32_t)(en - st), s.flags);
-                    else WS(rb, dst, s.p, 0, 0);
+                    const StrV o = op_sslice(SA(), flags, (flags & TPLX_SL_HAS_START) ? (int64_t)IB() : 0, (flags & TPLX_SL_HAS_END) ? (int64_t)IC() : 0);
+                    WS(rb, dst, o.p, o.len, o.flags);
                     break;
                 }
                 case TPLX_OP_SINDEX: {
-                    StrV s = SA();
-                    int64_t idx = (int64_t)IB();
-                    if (idx < 0) idx += s.len;
-                    if (idx < 0 || idx >= (int64_t)s.len) { raise_exc(t, TPLX_EC_INDEXERROR, opidx); break; }
-                    WS(rb, dst, s.p + idx, 1, s.flags);
+                    StrV o;
+                    if (!op_sindex(SA(), (int64_t)IB(), &o)) { raise_exc(t, TPLX_EC_INDEXERROR, opidx); break; }
+                    WS(rb, dst, o.p, o.len, o.flags);
                     break;
                 }
                 case TPLX_OP_SLOWER: {
@@ -310,122 +441,32 @@ struct VM {
                     break;
                 }
                 case TPLX_OP_SSTRIP: {
-                    StrV s = SA();
-                    uint32_t i = 0, e = s.len;
-                    if (flags & 1) while (i < e && is_pyspace(s.p[i])) ++i;
-                    if (flags & 2) while (e > i && is_pyspace(s.p[e - 1])) --e;
-                    WS(rb, dst, s.p + i, e - i, s.flags);
+                    const StrV o = op_sstrip(SA(), flags);
+                    WS(rb, dst, o.p, o.len, o.flags);
                     break;
                 }
                 case TPLX_OP_SCONCAT: {
-                    // empty operand returns the other side unchanged (BlockGeneratorVisitor.cc:381-436)
-                    StrV x = SA(), y = SB();
-                    if (x.len == 0) { WS(rb, dst, y.p, y.len, y.flags); break; }
-                    if (y.len == 0) { WS(rb, dst, x.p, x.len, x.flags); break; }
-                    uint8_t *o = scratch_alloc(t, x.len + y.len, opidx);
-                    if (!o) break;
-                    str_copy(o, x);
-                    str_copy(o + x.len, y);
-                    WS(rb, dst, o, x.len + y.len, 0);
+                    StrV o;
+                    if (!op_sconcat(t, SA(), SB(), opidx, &o)) break;
+                    WS(rb, dst, o.p, o.len, o.flags);
                     break;
                 }
                 case TPLX_OP_SREPLACE: {
-                    // runtime/src/Runtime.cc:401-540
-                    StrV s = SA(), f = SB(), r = SC();
-                    if (s.len == 0 || (f.len == 0 && r.len == 0)) { WS(rb, dst, s.p, s.len, s.flags); break; }
-                    if (f.len == 0) {
-                        uint32_t n = (r.len + 1) * s.len + r.len;
-                        uint8_t *o = scratch_alloc(t, n, opidx);
-                        if (!o) break;
-                        uint32_t pos = 0;
-                        for (uint32_t i = 0; i < s.len; ++i) {
-                            for (uint32_t j = 0; j < r.len; ++j) o[pos++] = sch(r, j);
-                            o[pos++] = sch(s, i);
-                        }
-                        for (uint32_t j = 0; j < r.len; ++j) o[pos++] = sch(r, j);
-                        WS(rb, dst, o, pos, 0);
-                        break;
-                    }
-                    if (f.len == 1 && s.flags == TPLX_SF_NONE && f.flags == TPLX_SF_NONE && r.flags == TPLX_SF_NONE) {
-                        // single-character needle on a plain string (the common `.replace(',', '')`): two byte loops without case mapping
-                        const uint8_t ch = f.p[0];
-                        uint32_t cnt = 0;
-                        for (uint32_t q = 0; q < s.len; ++q) cnt += s.p[q] == ch;
-                        if (cnt == 0) { WS(rb, dst, s.p, s.len, 0); break; }  // nothing to replace: the input itself (same bytes as a copy)
-                        const uint32_t n1 = s.len + cnt * r.len - cnt;
-                        uint8_t *o1 = scratch_alloc(t, n1 ? n1 : 1, opidx);
-                        if (!o1) break;
-                        uint32_t w = 0;
-                        for (uint32_t q = 0; q < s.len; ++q) {
-                            const uint8_t b0 = s.p[q];
-                            if (b0 == ch) for (uint32_t j = 0; j < r.len; ++j) o1[w++] = r.p[j];
-                            else o1[w++] = b0;
-                        }
-                        WS(rb, dst, o1, n1, 0);
-                        break;
-                    }
-                    // count pass
-                    uint32_t count = 0, i = 0;
-                    while (i + f.len <= s.len) {
-                        uint32_t j = 0;
-                        while (j < f.len && sch(s, i + j) == sch(f, j)) ++j;
-                        if (j == f.len) { ++count; i += f.len; } else ++i;
-                    }
-                    uint32_t n = s.len + count * r.len - count * f.len;
-                    uint8_t *o = scratch_alloc(t, n ? n : 1, opidx);
-                    if (!o) break;
-                    uint32_t pos = 0;
-                    i = 0;
-                    while (i < s.len) {
-                        bool m = false;
-                        if (i + f.len <= s.len) {
-                            uint32_t j = 0;
-                            while (j < f.len && sch(s, i + j) == sch(f, j)) ++j;
-                            m = (j == f.len);
-                        }
-                        if (m) {
-                            for (uint32_t j = 0; j < r.len; ++j) o[pos++] = sch(r, j);
-                            i += f.len;
-                        } else o[pos++] = sch(s, i++);
-                    }
-                    WS(rb, dst, o, pos, 0);
+                    StrV o;
+                    if (!op_sreplace(t, SA(), SB(), SC(), opidx, &o)) break;
+                    WS(rb, dst, o.p, o.len, o.flags);
                     break;
                 }
                 case TPLX_OP_SFMTD: {
-                    // '%[0]<w>d' % v: snprintf with C's %d, which consumes an int (BlockGeneratorVisitor.cc:675-775);
-                    // flags bit1: '{:0<w>}'.format(v) / f-strings go through fmt and keep all 64 bits (Runtime.cc:544-607)
-                    const int64_t v = (flags & 2) ? (int64_t)R(rb, a) : (int64_t)(int32_t)(int64_t)R(rb, a);
-                    uint32_t width = (uint32_t)imm;
-                    uint64_t mag = v < 0 ? (uint64_t)0 - (uint64_t)v : (uint64_t)v;
-                    uint32_t nd = 1;
-                    for (uint64_t q = mag; q >= 10; q /= 10) ++nd;
-                    uint32_t body = nd + (v < 0 ? 1 : 0);
-                    uint32_t total = body > width ? body : width;
-                    uint8_t *o = scratch_alloc(t, total, opidx);
-                    if (!o) break;
-                    uint32_t padn = total - body, pos = 0;
-                    if (flags & 1) {
-                        if (v < 0) o[pos++] = '-';
-                        for (uint32_t i = 0; i < padn; ++i) o[pos++] = '0';
-                    } else {
-                        for (uint32_t i = 0; i < padn; ++i) o[pos++] = ' ';
-                        if (v < 0) o[pos++] = '-';
-                    }
-                    for (uint32_t i = 0; i < nd; ++i) { o[pos + nd - 1 - i] = (uint8_t)('0' + mag % 10); mag /= 10; }
-                    WS(rb, dst, o, total, 0);
+                    StrV o;
+                    if (!op_sfmtd(t, flags, R(rb, a), (uint32_t)imm, opidx, &o)) break;
+                    WS(rb, dst, o.p, o.len, o.flags);
                     break;
                 }
                 case TPLX_OP_I2S: {
-                    int64_t v = (int64_t)R(rb, a);
-                    uint64_t mag = v < 0 ? (uint64_t)0 - (uint64_t)v : (uint64_t)v;
-                    uint32_t nd = 1;
-                    for (uint64_t q = mag; q >= 10; q /= 10) ++nd;
-                    uint32_t total = nd + (v < 0 ? 1 : 0);
-                    uint8_t *o = scratch_alloc(t, total, opidx);
-                    if (!o) break;
-                    if (v < 0) o[0] = '-';
-                    for (uint32_t i = 0; i < nd; ++i) { o[total - 1 - i] = (uint8_t)('0' + mag % 10); mag /= 10; }
-                    WS(rb, dst, o, total, 0);
+                    StrV o;
+                    if (!op_i2s(t, (int64_t)R(rb, a), opidx, &o)) break;
+                    WS(rb, dst, o.p, o.len, o.flags);
                     break;
                 }
                 case TPLX_OP_S2I: {
