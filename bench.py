@@ -19,6 +19,10 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# Steady-state measurement: the stage specialiser (csrc/jit.inl) compiles a stage once per process; by default that happens on a
+# background thread while the interpreting kernels keep working. Here the first warm-up step waits for it, so that every timed step
+# runs the same kernels (TPLX_JIT=0 measures the interpreting kernels).
+os.environ.setdefault("TPLX_JIT_SYNC", "1")
 
 import numpy as np  # noqa: E402
 
@@ -513,6 +517,7 @@ def measure(args, wl_key, rank, world, local, dist, hc):
         for p in partials:
             tot = tot + p
         if dist is not None:  # the one collective of the path, inside the C ABI: ncclAllGather + fold in rank order
+            stats["local_partial"] = tot
             tot = ir.bits_f64(st.agg_finish(local, [ir.f64_bits(tot)])[0])
         return tot
 
@@ -529,16 +534,18 @@ def measure(args, wl_key, rank, world, local, dist, hc):
             r = st.run(b, 0)   # every block is its own task (row numbers per task), so blocks need not run in sequence
             inf = r.info
             out = (inf.kernel_ms, inf.kernel_launches, int(inf.n_out_rows),
-                   ir.bits_f64(r.aggregate_bits()[0]) if ep == ir.C["TPLX_EP_AGGREGATE"] else None)
+                   ir.bits_f64(r.aggregate_bits()[0]) if ep == ir.C["TPLX_EP_AGGREGATE"] else None, int(inf.specialised_launches))
             r.free()
             return out
         # row stages: blocks in flight on the GPU's execution lanes (the latency-bound dense launch of one block overlaps the
         # prefilter of the next). Aggregate scans are DRAM-bound (nothing to overlap) and hash stages share one table per
         # device: those run one block at a time.
         runner = pool.map if ep == ir.C["TPLX_EP_MEMORY"] else map
-        for km, kl, no, part in runner(one_resident, dev_blocks):
+        spec = 0
+        for km, kl, no, part, sl in runner(one_resident, dev_blocks):
             kms += km
             launches += kl
+            spec += sl
             n_out += no
             if part is not None:
                 partials.append(part)
@@ -552,7 +559,7 @@ def measure(args, wl_key, rank, world, local, dist, hc):
             kms += fin.info.kernel_ms
             launches += fin.info.kernel_launches
             fin.free()
-        stats.update(kernel_ms=kms, launches=launches, n_out=n_out)
+        stats.update(kernel_ms=kms, launches=launches, n_out=n_out, specialised=spec)
 
     def step_e2e(blocks):
         d2h = 0
@@ -680,6 +687,9 @@ def measure(args, wl_key, rank, world, local, dist, hc):
                  "tpch_q6": "fused_scan_agg_tma_kernel", "aggbykey_str": "stage_hash_kernel",
                  "c1_map_filter": "stage_rows_vec_kernel<4> (K1v)"}.get(
             wl["name"], {0: "stage_rows_kernel", 1: "stage_agg_kernel", 2: "stage_hash_kernel"}[ep])
+        if stats.get("specialised", 0):  # the stage specialiser's build of the same kernel source ran (tplx_jit_kernel)
+            kname = kname.replace("stage_rows_kernel (dense", "stage_rows_kernel specialised for this stage at run time (NVRTC, tplx_jit_kernel; dense") \
+                         .replace("stage_rows_vec_kernel<4> (K1v)", "stage_rows_vec_kernel<4> (K1v) specialised for this stage at run time (NVRTC, tplx_jit_kernel)")
         line = {
             "value": rows_all / (dt / args.steps), "unit": "rows/s", "ms_per_step": ms_step,
             "timed_region": {"repeats": len(reps), "seconds_measured": spent, "reported": "median repeat of K steps, max over ranks",
@@ -693,6 +703,7 @@ def measure(args, wl_key, rank, world, local, dist, hc):
                             "columns the prefilter reads; zero_copy_cols input columns stay in host memory and are read over PCIe for "
                             "surviving rows only (late materialisation); every output column and the exception records are fetched"},
             "gpu_launches": launches,
+            "specialised_launches_per_step": stats.get("specialised", 0),  # of the step's launches: kernels the stage specialiser (csrc/jit.inl) compiled for this stage at run time
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(wl, n_launch), "peak_source": peak_src, "algorithmic_bytes_per_row": alg_bytes / wl["rows"],
                          "kernel_ms_per_launch": k_ms_per_launch, "kernel_share_of_step": k_ms_step / ms_step,
@@ -706,6 +717,19 @@ def measure(args, wl_key, rank, world, local, dist, hc):
             line["checks"]["result"] = repr(stats["result"])
             line["checks"]["collective"] = ("tplx_gpu_agg_finish: ncclAllGather of the per-GPU partial + fold in rank order on the device"
                                             if world > 1 else None)
+    if dist is not None and "local_partial" in stats:
+        # self-test of the collective under the launcher (every rank takes part): the device-side fold must equal, bit for bit, the
+        # same fold of the ranks' partials done on the host after a torch.distributed all_gather
+        import torch as _t
+        mine = _t.tensor([stats["local_partial"]], dtype=_t.float64, device="cuda")
+        allp = [_t.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allp, mine)
+        exp = 0.0
+        for t_ in allp:
+            exp = exp + float(t_.item())
+        got = st.agg_finish(local, [ir.f64_bits(stats["local_partial"])])[0]
+        if rank == 0:
+            line["checks"]["collective_parity"] = bool(ir.f64_bits(exp) == got)
         if not args.no_cpu_baseline and world == 1:  # the CPU arm is reported at N = 1 only
             line["cpu_baseline"] = cpu_arm(args, wl_key, wl, hc)
     # free this workload's device and pinned memory before the next one is built

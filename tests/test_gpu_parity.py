@@ -509,3 +509,62 @@ def test_prefiltered_stage_without_host_round_trip(gpu, monkeypatch):
             assert_result_equals_oracle(res, ora, f"block {i} env={env}")
             res.free()
         st.close()
+
+
+def _keyed_with_ids(n, n_keys, seed, zipf):
+    """workloads.gen_keyed, but the key ids are kept so that the expected groups come from numpy alone."""
+    rng = np.random.default_rng(seed)
+    ids = (np.minimum(rng.zipf(1.2, n) - 1, n_keys - 1) if zipf else rng.integers(0, n_keys, n)).astype(np.int64)
+    digits = np.zeros((n, 8), dtype=np.uint8)
+    digits[:, 0] = ord("k")
+    x = ids.copy()
+    for p in range(7, 0, -1):
+        digits[:, p] = ord("0") + (x % 10)
+        x //= 10
+    offs = (np.arange(n + 1, dtype=np.int64) * 8).astype(np.uint32)
+    return ids, Column(T_STR, digits.reshape(-1), offs)
+
+
+def _ids_of_key_column(col):
+    assert np.array_equal(np.diff(col.offsets.astype(np.int64)), np.full(len(col.offsets) - 1, 8))
+    d = col.data.reshape(-1, 8)
+    assert (d[:, 0] == ord("k")).all()
+    ids = np.zeros(len(d), dtype=np.int64)
+    for p in range(1, 8):
+        ids = ids * 10 + (d[:, p].astype(np.int64) - ord("0"))
+    return ids
+
+
+@pytest.mark.parametrize("zipf", [False, True])
+def test_hash_aggregate_10m_keys(gpu, zipf):
+    """BASELINE config 5 at its key count (10 M distinct string keys; uniform and Zipf-distributed rows), one GPU's shard cut to
+    20 M rows: i64 sums per key exact, f64 sums per key (atomics, order not fixed) within n_k * eps * sum|x| of numpy's sequential
+    sums. Expected groups are computed by numpy from the generator's ids (independent of the oracle and of the device)."""
+    n, n_keys = 20_000_000, 10_000_000
+    ids, keycol = _keyed_with_ids(n, n_keys, 77, zipf)
+    rng = np.random.default_rng(78)
+    vi = rng.integers(-1000, 1000, n, dtype=np.int64)
+    vf = rng.integers(-100000, 100000, n).astype(np.float64) / 64.0 + 0.1
+    sc = frontend.StageCompiler([T_STR, T_I64, T_F64], ["key", "v", "f"])
+    prog = sc.finish_hash(["key"], lambda a, x: (a[0] + x[1], a[1] + x[2]), lambda a, b: (a[0] + b[0], a[1] + b[1]), (0, 0.0), 100001)
+    st = backend.Stage(prog)
+    st.hash_reserve(0, n_keys)
+    half = n // 2  # two blocks into one table, like two partitions of one task
+    for lo, hi in ((0, half), (half, n)):
+        cols = [Column(T_STR, keycol.data[lo * 8:hi * 8], (keycol.offsets[lo:hi + 1].astype(np.int64) - lo * 8).astype(np.uint32)),
+                Column(T_I64, vi[lo:hi]), Column(T_F64, vf[lo:hi])]
+        st.run_host(0, cols, hi - lo).info
+    fin = st.hash_finish(0)
+    got_ids = _ids_of_key_column(fin.column(0))
+    present = np.unique(ids)
+    assert len(got_ids) == len(present) and np.array_equal(np.sort(got_ids), present)
+    want_i = np.zeros(n_keys, dtype=np.int64)
+    np.add.at(want_i, ids, vi)
+    assert np.array_equal(fin.column(1).data.view(np.int64), want_i[got_ids])
+    want_f = np.bincount(ids, weights=vf, minlength=n_keys)
+    abs_f = np.bincount(ids, weights=np.abs(vf), minlength=n_keys)
+    cnt = np.bincount(ids, minlength=n_keys)
+    got_f = fin.column(2).data.view(np.float64)
+    bound = cnt[got_ids] * np.finfo(np.float64).eps * abs_f[got_ids] + 1e-300
+    assert (np.abs(got_f - want_f[got_ids]) <= bound).all()
+    st.close()

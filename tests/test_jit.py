@@ -16,7 +16,7 @@ from oracle import pyoracle
 from fuzz_udfs import COLS, TYPES, Gen, apply_ops, make_columns
 from helpers import assert_result_equals_oracle
 
-K_ROWS, K_VEC4, K_VEC2, K_AGG, K_MASK, K_HASH = 1, 2, 3, 4, 5, 6
+K_ROWS, K_VEC4, K_VEC2, K_AGG, K_MASK = 1, 2, 3, 4, 5
 
 
 class jit_mode:
@@ -209,3 +209,72 @@ def test_random_pipelines_specialised_match_oracle(gpu, seed):
             if compared >= 5:
                 break
     assert compared >= 3
+
+
+@pytest.mark.gpu
+def test_tiered_execution_background_compile(gpu):
+    """Default policy: the first blocks of a hot stage run on the interpreting kernel while NVRTC compiles on a background thread;
+    later blocks run the specialised kernel. Every block gives the same result."""
+    import time
+    n = 200_000
+    x = np.arange(1, n + 1, dtype=np.int64)
+    cols = [backend.Column(ir.T_I64, x)]
+    prog = W.c1_program()
+    ora = pyoracle.run_program(prog, cols, n)
+    old = {k: os.environ.get(k) for k in ("TPLX_JIT", "TPLX_JIT_MIN_ROWS", "TPLX_JIT_SYNC")}
+    os.environ.update(TPLX_JIT="1", TPLX_JIT_MIN_ROWS="1000", TPLX_JIT_SYNC="0")
+    try:
+        st = backend.Stage(prog)
+        seen = []
+        t0 = time.time()
+        while time.time() - t0 < 60:
+            res = st.run_host(0, cols, n)
+            assert_result_equals_oracle(res, ora, "tiered")
+            seen.append(int(res.info.specialised_launches))
+            res.free()
+            if seen[-1]:
+                break
+            time.sleep(0.05)
+        assert seen[-1] > 0, "the specialised kernel never took over"
+        assert seen[0] == 0, "the first block waited for the compiler"
+        st.close()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 8191, 8192, 8193, 100_003, 3_000_001])
+@pytest.mark.parametrize("wide", [4, 2, 0])
+def test_wide_tile_kernel_with_exceptions(gpu, n, wide):
+    """K1w (B sub-batches of 2048 rows per ticket) vs the oracle: ragged tiles, ZeroDivisionError rows (their codes live in slot 0 of
+    the raising row), a filter, one and two output columns; TPLX_JIT_WIDE = 4 / 2 / 0 selects B = 4, B = 2 or K1v's 2048-row tiles."""
+    rng = np.random.default_rng(n + wide)
+    a = rng.integers(-10_000, 10_000, n)
+    cols = [backend.Column(ir.T_I64, a)]
+    old = os.environ.get("TPLX_JIT_WIDE")
+    os.environ["TPLX_JIT_WIDE"] = str(wide)
+    try:
+        for two in (False, True):
+            sc = frontend.StageCompiler([ir.T_I64], ["a"])
+            sc.add_map(lambda x: x // (x % 7), 100001)       # x % 7 == 0 raises
+            sc.add_filter(lambda x: x % 3 != 1, 100002)
+            if two:
+                sc.add_map(lambda x: (x, x * 2 + 1), 100003)
+            prog = sc.finish_memory(prefilter=False)
+            ora = pyoracle.run_program(prog, cols, n, first_row_no=5)
+            with jit_mode(2):
+                st = backend.Stage(prog)
+                res = st.run_host(0, cols, n, first_row_no=5)
+                assert_result_equals_oracle(res, ora, f"n={n} wide={wide} two={two}")
+                assert int(res.info.specialised_launches) > 0
+                res.free()
+                st.close()
+    finally:
+        if old is None:
+            os.environ.pop("TPLX_JIT_WIDE", None)
+        else:
+            os.environ["TPLX_JIT_WIDE"] = old

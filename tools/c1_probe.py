@@ -1,5 +1,6 @@
 """Kernel-time probe: C1 (map x*x, filter even) over one device-resident block of 100M i64 rows through K1v."""
 import sys, os
+os.environ.setdefault("TPLX_JIT_SYNC", "1")  # steady state: wait for the stage specialiser at the first block
 sys.path.insert(0, '/root/repo')
 import numpy as np
 from tuplex_b200 import backend, workloads as W

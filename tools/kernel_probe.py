@@ -1,5 +1,6 @@
 """Kernel-time probe: Zillow stage over one device-resident block; prints CUDA-event kernel ms (prefilter+dense)."""
 import sys, os
+os.environ.setdefault("TPLX_JIT_SYNC", "1")  # steady state: wait for the stage specialiser at the first block
 sys.path.insert(0, '/root/repo')
 import numpy as np
 from tuplex_b200 import backend, workloads as W

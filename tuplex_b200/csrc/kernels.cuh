@@ -324,7 +324,7 @@ __device__ __forceinline__ void rows_tile_finish(const KParams &P, const TileSme
 // ---- stage specialiser (jit.inl) ----------------------------------------------------------------------------------------------
 // When this header is compiled at run time by NVRTC (TPLX_JIT), "jit_row.cuh" is the op program of ONE stage printed as a
 // straight-line function (jit_run / jit_row_fixed) and exactly one kernel of the library is compiled around it, as
-// `tplx_jit_kernel`: TPLX_JIT_KIND 1 = K1 rows, 2 / 3 = K1v (J = 4 / 2), 4 = K3 aggregate, 5 = K1m mask, 6 = K4 hash.
+// `tplx_jit_kernel`: TPLX_JIT_KIND 1 = K1 rows, 2 / 3 = K1v (J = 4 / 2), 4 = K3 aggregate, 5 = K1m mask (K4, the hash aggregate, is table-bound and stays interpreted).
 // The register file of a specialised kernel is COMPACT: it holds the live-out slots only (outputs, accumulator inputs), in the
 // order the host's jit::liveout() numbered them; KParams carries those compact slot numbers.
 #ifdef TPLX_JIT

@@ -654,28 +654,40 @@ static std::vector<DInstr> predecode(const std::vector<tplx_instr> &ins, uint32_
 }
 
 // ---- stage specialiser: compile (once per stage and kernel kind) and load (once per device) -------------------------------------
-static std::shared_ptr<jit::Binary> jit_binary(tplx_stage *s, int kind, int minb) {  // s->mu held
-    auto it = s->jit_bin.find(kind);
-    if (it != s->jit_bin.end()) return it->second;
-    auto bin = std::make_shared<jit::Binary>();
-    jit::compile(*bin, jit::generate(s->hdr, s->instrs, s->in_types, s->jit_live, kind), kind, minb);
+static void jit_compile_job(std::shared_ptr<jit::Binary> bin, std::string src, int kind, int minb, size_t n_instr) {
+    jit::compile(*bin, src, kind, minb);
     if (getenv("TPLX_TRACE") || (bin->failed && getenv("TPLX_JIT_VERBOSE")))
-        fprintf(stderr, "[tplx] specialiser: kind %d, %zu instructions -> %zu B cubin in %.0f ms%s%s\n", kind, s->instrs.size(), bin->cubin.size(), bin->compile_ms,
+        fprintf(stderr, "[tplx] specialiser: kind %d, %zu instructions -> %zu B cubin in %.0f ms%s%s\n", kind, n_instr, bin->cubin.size(), bin->compile_ms,
                 bin->failed ? " FAILED: " : "", bin->failed ? bin->log.c_str() : "");
     if (const char *dir = getenv("TPLX_JIT_DUMP")) {  // evidence / debugging: the generated row function and the cubin
-        const std::string base = std::string(dir) + "/tplx_jit_k" + std::to_string(kind) + "_" + std::to_string(s->instrs.size()) + "ins";
+        const std::string base = std::string(dir) + "/tplx_jit_k" + std::to_string(kind) + "_" + std::to_string(n_instr) + "ins";
         if (FILE *f = fopen((base + ".cuh").c_str(), "w")) { fwrite(bin->source.data(), 1, bin->source.size(), f); fclose(f); }
         if (!bin->failed)
             if (FILE *f = fopen((base + ".cubin").c_str(), "wb")) { fwrite(bin->cubin.data(), 1, bin->cubin.size(), f); fclose(f); }
     }
+    bin->ready.store(1, std::memory_order_release);
+}
+// wait = false: the compile runs on a background thread and the returned binary may not be ready yet (ready == 0)
+static std::shared_ptr<jit::Binary> jit_binary(tplx_stage *s, int kind, int minb, bool wait) {  // s->mu held
+    auto it = s->jit_bin.find(kind);
+    if (it != s->jit_bin.end()) {
+        if (wait && !it->second->ready.load(std::memory_order_acquire) && it->second->worker.joinable()) it->second->worker.join();
+        return it->second;
+    }
+    auto bin = std::make_shared<jit::Binary>();
     s->jit_bin[kind] = bin;
+    std::string src = jit::generate(s->hdr, s->instrs, s->in_types, s->jit_live, kind);
+    if (wait) jit_compile_job(bin, std::move(src), kind, minb, s->instrs.size());
+    else bin->worker = std::thread(jit_compile_job, bin, std::move(src), kind, minb, s->instrs.size());
     return bin;
 }
 // resident CTAs per SM the specialised kernel's register allocation must allow (measured on B200, profiles/r02_jit.md)
 static int jit_minb(const tplx_stage *s, int kind) {
     auto env = [](const char *n, int dflt) { const char *e = getenv(n); return e && atoi(e) > 0 ? atoi(e) : dflt; };
     switch (kind) {
-        case jit::K_VEC4: case jit::K_VEC4P: return env("TPLX_JIT_MINB_VEC", 6);
+        case jit::K_VEC4: return env("TPLX_JIT_MINB_VEC", 8);
+        case jit::K_WIDE4: return env("TPLX_JIT_MINB_WIDE", 3);
+        case jit::K_WIDE2: return env("TPLX_JIT_MINB_WIDE", 4);
         case jit::K_VEC2: return env("TPLX_JIT_MINB_VEC", 3);
         case jit::K_MASK: return env("TPLX_JIT_MINB_MASK", 4);
         default: return env("TPLX_JIT_MINB", 3);
@@ -694,7 +706,8 @@ static jit::Loaded *jit_get(tplx_stage *s, StageDev *sd, int kind, int minb) {
     if (it != sd->jit_fn.end()) return it->second.failed ? nullptr : &it->second;
     jit::Loaded ld;
     jit::CuDrv *cu = jit::cudrv_api();
-    std::shared_ptr<jit::Binary> bin = jit_binary(s, kind, minb);
+    std::shared_ptr<jit::Binary> bin = jit_binary(s, kind, minb, jit::synchronous());
+    if (!bin->ready.load(std::memory_order_acquire)) return nullptr;  // still compiling: this block runs on the interpreting kernel
     if (!cu || bin->failed) ld.failed = true;
     if (!ld.failed) {
         cudaSetDevice(sd->dev->id);
@@ -714,6 +727,11 @@ static jit::Loaded *jit_get(tplx_stage *s, StageDev *sd, int kind, int minb) {
     auto &slot = sd->jit_fn[kind];
     slot = ld;
     return slot.failed ? nullptr : &slot;
+}
+static bool jit_pending(tplx_stage *s, int kind) {  // a background compile of this kind is still running
+    std::lock_guard<std::mutex> lk(s->mu);
+    auto it = s->jit_bin.find(kind);
+    return it != s->jit_bin.end() && !it->second->ready.load(std::memory_order_acquire);
 }
 static int32_t jit_launch(jit::Loaded *jf, uint32_t grid, uint32_t smem, cudaStream_t st, const void *params) {
     void *args[] = {const_cast<void *>(params)};
@@ -782,14 +800,14 @@ extern "C" int32_t tplx_gpu_stage_vec_plan(const tplx_stage *s, tplx_vec_uop *ou
 
 extern "C" int32_t tplx_gpu_stage_specialise(tplx_stage *s, int32_t kind, int32_t compile, char *src, uint64_t src_cap, uint64_t *src_len,
                                              uint64_t *cubin_bytes, char *log, uint64_t log_cap) {
-    if (!s || kind < jit::K_ROWS || kind > jit::K_VEC4P || kind == jit::K_HASH) return fail(TPLX_E_BADARG, "stage_specialise: bad arguments");
-    if ((kind == jit::K_VEC4 || kind == jit::K_VEC2 || kind == jit::K_VEC4P) && !s->vec_ok) return fail(TPLX_E_UNSUPPORTED, "stage_specialise: not a fixed-width MEMORY stage");
+    if (!s || kind < jit::K_ROWS || kind > jit::K_WIDE2) return fail(TPLX_E_BADARG, "stage_specialise: bad arguments");
+    if ((kind == jit::K_VEC4 || kind == jit::K_VEC2 || kind == jit::K_WIDE4 || kind == jit::K_WIDE2) && !s->vec_ok) return fail(TPLX_E_UNSUPPORTED, "stage_specialise: not a fixed-width MEMORY stage");
     std::string text;
     size_t nb = 0;
     std::string lg;
     if (compile) {
         std::lock_guard<std::mutex> lk(s->mu);
-        std::shared_ptr<jit::Binary> bin = jit_binary(s, kind, jit_minb(s, kind));
+        std::shared_ptr<jit::Binary> bin = jit_binary(s, kind, jit_minb(s, kind), true);
         text = bin->source;
         nb = bin->failed ? 0 : bin->cubin.size();
         lg = bin->log;
@@ -824,6 +842,8 @@ extern "C" int32_t tplx_gpu_stage_destroy(tplx_stage *s) {
             if (kv.second.mod) jit::cudrv_api()->ModuleUnload(kv.second.mod);
     }
     if (s->prefilter) tplx_gpu_stage_destroy(s->prefilter);
+    for (auto &kv : s->jit_bin)
+        if (kv.second->worker.joinable()) kv.second->worker.join();
     delete s;
     return TPLX_OK;
 }
@@ -1246,7 +1266,7 @@ static int32_t run_rows_vec(tplx_stage *s, StageDev *sd, const tplx_block *b, in
         regs_off = (uint32_t)off;
         off = align_up(off + (size_t)ns * T * 8, 16);
         misc_off = (uint32_t)off;
-        off += 32 * 4 + (size_t)T * 4 + (size_t)(2 * (NT / 32)) * 8 + 16;  // s_cnt, exc_stage, look-back scratch, ticket
+        off += 32 * 4 + (size_t)T * 4 + (size_t)(4 * (NT / 32)) * 8 + 16;  // s_cnt, exc_stage, look-back scratch, ticket
         smem = (uint32_t)align_up(off, 16);
         if (smem <= 72 * 1024 || (J == 2 && smem <= (uint32_t)d->smem_optin)) { Jsel = J; break; }
     }
@@ -1254,7 +1274,30 @@ static int32_t run_rows_vec(tplx_stage *s, StageDev *sd, const tplx_block *b, in
     jit::Loaded *jf = nullptr;
     if (jit_wanted(s, n)) {
         const uint32_t nl = std::max<uint32_t>((uint32_t)s->jit_live.slots.size(), 1);
+        const int forceJ = getenv("TPLX_JIT_VEC_J") ? atoi(getenv("TPLX_JIT_VEC_J")) : 0;  // experiments: tile size at equal occupancy
+        // K1w (wide tiles: B sub-batches of 2048 rows per ticket) when the live-out slots of B sub-batches fit the shared memory of
+        // 3 (B = 4) / 4 (B = 2) resident CTAs; TPLX_JIT_WIDE=0 keeps K1v's 2048-row tiles
+        const int wide_max = getenv("TPLX_JIT_WIDE") ? atoi(getenv("TPLX_JIT_WIDE")) : 4;
+        bool wide_pending = false;
+        for (int Bw : {4, 2}) {
+            if (jf || forceJ || Bw > wide_max) continue;
+            const uint32_t Tw = (uint32_t)Bw * 2048u;
+            size_t off = 16;
+            const uint32_t c_off = (uint32_t)off;
+            off = align_up(off + std::max<size_t>(s->in_types.size(), 1) * sizeof(ColIn), 16);
+            const uint32_t r_off = (uint32_t)off;
+            off = align_up(off + (size_t)nl * Tw * 8, 16);
+            const uint32_t m_off = (uint32_t)off;
+            off += (size_t)Bw * 32 * 4 + (size_t)(4 * (NT / 32)) * 8 + 16;
+            if (align_up(off, 16) > (Bw == 4 ? 74u * 1024 : 55u * 1024)) continue;
+            const int kind = Bw == 4 ? jit::K_WIDE4 : jit::K_WIDE2;
+            jf = jit_get(s, sd, kind, jit_minb(s, kind));
+            if (jf) { Jsel = 4; T = Tw; cols_off = c_off; regs_off = r_off; misc_off = m_off; smem = (uint32_t)align_up(off, 16); }
+            else if (jit_pending(s, kind)) { wide_pending = true; break; }  // still compiling: interpreter meanwhile, no second compile
+        }
         for (int J : {4, 2}) {
+            if (jf || wide_pending) break;
+            if (forceJ && J != forceJ) continue;
             const uint32_t Tj = 2u * J * NT;
             size_t off = 16;
             const uint32_t c_off = (uint32_t)off;
@@ -1262,10 +1305,9 @@ static int32_t run_rows_vec(tplx_stage *s, StageDev *sd, const tplx_block *b, in
             const uint32_t r_off = (uint32_t)off;
             off = align_up(off + (size_t)nl * Tj * 8, 16);
             const uint32_t m_off = (uint32_t)off;
-            off += 32 * 4 + (size_t)Tj * 4 + (size_t)(2 * (NT / 32)) * 8 + 16;
+            off += 32 * 4 + (size_t)Tj * 4 + (size_t)(4 * (NT / 32)) * 8 + 16;
             if (align_up(off, 16) > (J == 4 ? 56u * 1024 : 100u * 1024)) continue;
-            const bool pipe = J == 4 && getenv("TPLX_JIT_VEC_PIPE") && atoi(getenv("TPLX_JIT_VEC_PIPE"));
-            const int kind = J == 4 ? (pipe ? jit::K_VEC4P : jit::K_VEC4) : jit::K_VEC2;
+            const int kind = J == 4 ? jit::K_VEC4 : jit::K_VEC2;
             jf = jit_get(s, sd, kind, jit_minb(s, kind));
             if (jf) { Jsel = J; T = Tj; cols_off = c_off; regs_off = r_off; misc_off = m_off; smem = (uint32_t)align_up(off, 16); }
             break;
@@ -1462,7 +1504,9 @@ static int32_t run_rows(tplx_stage *s, StageDev *sd, const tplx_block *b, int64_
     if (jf) {
         P.n_instr = 0;
         P.n_slots = (uint32_t)s->jit_live.slots.size();
-        P.pad_split = (getenv("TPLX_JIT_PREFETCH") && !atoi(getenv("TPLX_JIT_PREFETCH"))) ? 1u : 0u;
+        // dense-launch prefetch (jit_prefetch): measured on the Zillow dense launch it doubles the DRAM reads (whole 128-byte lines for
+        // cells that need one or two sectors: 433 vs 226 MB per block) and costs 6 %: off unless TPLX_JIT_PREFETCH=1
+        P.pad_split = (getenv("TPLX_JIT_PREFETCH") && atoi(getenv("TPLX_JIT_PREFETCH"))) ? 0u : 1u;
     }
     if (cols_override)
         for (size_t c = 0; c < cols_override->size(); ++c) P.in[c] = (*cols_override)[c];

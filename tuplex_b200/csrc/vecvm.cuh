@@ -320,6 +320,45 @@ __device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t *p) {
     return v;
 }
 
+// Block-wide decoupled look-back of a tile (all NT threads call it): on return pre_keep / pre_exc = rows kept / raised by every earlier
+// tile, and this tile's inclusive prefix has been published. s_scr: 4 * NT/32 words of shared memory (double-buffered per round).
+__device__ __forceinline__ void vec_lookback(const KParams &P, uint32_t tile, uint32_t n_keep, uint32_t n_exc, uint64_t *s_scr, uint64_t &pre_keep,
+                                             uint64_t &pre_exc) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tile > 0) {
+        int64_t p = (int64_t)tile - 1;
+        for (uint32_t round = 0;; ++round) {
+            uint64_t *scr = s_scr + (round & 1u) * (2 * (NT / 32));  // double-buffered: one barrier per round
+            const int64_t q = p - (int64_t)tid;
+            uint64_t wd = (uint64_t)2 << 62;  // tiles before the first count as an inclusive prefix of zero
+            if (q >= 0) do { wd = ld_relaxed_u64(P.tile_state + q); } while ((wd >> 62) == 0);
+            const bool incl = (wd >> 62) == 2;
+            const uint32_t im = __ballot_sync(0xFFFFFFFFu, incl);
+            const uint32_t first = im ? (uint32_t)(__ffs(im) - 1) : 32u;  // nearest inclusive word inside this warp's 32 tiles
+            uint64_t k = lane <= first ? (wd >> 31) & 0x7FFFFFFFull : 0, e = lane <= first ? wd & 0x7FFFFFFFull : 0;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                k += __shfl_xor_sync(0xFFFFFFFFu, k, o);
+                e += __shfl_xor_sync(0xFFFFFFFFu, e, o);
+            }
+            if (lane == 0) {
+                scr[warp * 2] = (k << 32) | e;  // counts are < 2^31 in total: 32 bits each
+                scr[warp * 2 + 1] = im ? 1 : 0;
+            }
+            __syncthreads();
+            bool done = false;
+            for (uint32_t w = 0; w < NT / 32 && !done; ++w) {  // warps cover tile-1-32w .. : nearest first
+                pre_keep += scr[w * 2] >> 32;
+                pre_exc += scr[w * 2] & 0xFFFFFFFFull;
+                done = scr[w * 2 + 1] != 0;
+            }
+            if (done) break;
+            p -= NT;
+        }
+        if (tid == 0) st_cg_u64(P.tile_state + tile, ((uint64_t)2 << 62) | ((pre_keep + n_keep) << 31) | (pre_exc + n_exc));
+    }
+}
+
 // K1v kernel: persistent CTAs, ticketed tiles of T = 2J * 256 rows.
 // Shared memory: prog (VInstr) | cols | regs (n_slots x T x 8 B; output columns are staged in place) | misc: s_cnt[8J] exc_stage[T]
 // scan scratch, tickets.
@@ -369,11 +408,190 @@ __device__ __forceinline__ void jit_eval_vec(const ulonglong2 (&vin)[J][JIT_NIN]
 }
 #endif
 
-#if !defined(TPLX_JIT) || TPLX_JIT_KIND == 2 || TPLX_JIT_KIND == 3 || TPLX_JIT_KIND == 7
+#if defined(TPLX_JIT) && (TPLX_JIT_KIND == 6 || TPLX_JIT_KIND == 7)
+// ---- K1w: the specialised fixed-width row kernel with WIDE tiles ---------------------------------------------------------------------
+// Measured on C1 (profiles/r02_jit.md): with the interpretation gone, K1v is bound by the latency chain of a tile — ticket, LDG,
+// counts, look-back over every earlier tile still in flight, stores — of which the look-back waits for the SLOWEST load among all
+// predecessors (in-order retirement over a window of ~1000 tiles): ~10-14 us per 2048-row tile however few instructions the tile takes.
+// Only resident warps hide that, and a specialised row function leaves registers and shared memory to spare. So a CTA takes B = 4 (or 2)
+// sub-batches of 2048 rows per ticket: one ticket, one count barrier, ONE look-back and one inclusive-prefix publication per 8192 rows,
+// 64 KB of loads per CTA between two waits; the sub-batches are evaluated back to back (the LDG.128s of sub-batch b + 1 are issued before
+// sub-batch b is evaluated when the registers allow), their live-out slots staged side by side in the compact register file
+// (regs[slot][b][local row]), exception codes of raising rows in slot 0 of that row (a raising row is not written).
+// Same row order, same packed tile-state word, same output as K1v with tiles four times the size.
+extern "C" __global__ void __launch_bounds__(NT, TPLX_JIT_MINB) tplx_jit_kernel(const __grid_constant__ KParams P) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr int J = 4, B = TPLX_JIT_KIND == 6 ? 4 : 2;
+    using VV = VecVM<J>;
+    constexpr uint32_t TS = VV::T, T = B * TS, SLOT_W = T * 8;  // rows per sub-batch / per tile, bytes of one slot of the wide register file
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    ColIn *s_cols = reinterpret_cast<ColIn *>(smem + P.smem_cols_off);
+    uint8_t *s_regs = smem + P.smem_regs_off;
+    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(smem + P.smem_misc_off);  // [B][32]: kept | raised << 16 per (sub-batch, slab, warp)
+    uint64_t *s_scr = reinterpret_cast<uint64_t *>(s_cnt + B * 32);
+    uint32_t *s_ctl = reinterpret_cast<uint32_t *>(s_scr + 4 * (NT / 32));
+
+    for (uint32_t i = tid; i < P.n_in * (sizeof(ColIn) / 8); i += NT)
+        reinterpret_cast<uint64_t *>(s_cols)[i] = reinterpret_cast<const uint64_t *>(P.in)[i];
+    uint8_t *rb = s_regs + tid * 16;
+    const uint32_t lt = (1u << lane) - 1u;
+    auto code_at = [&](uint32_t b, uint32_t lr) -> uint32_t * {  // code | opidx << 16 of a raising row: the low word of its slot 0
+        return reinterpret_cast<uint32_t *>(s_regs + ((size_t)b * TS + lr) * 8);
+    };
+
+    if (tid == 0) s_ctl[0] = atomicAdd(&P.counters[0], 1u);
+    while (true) {
+        __syncthreads();  // the ticket is visible; s_cnt and the look-back scratch of the previous tile are no longer read
+        const uint32_t tile = s_ctl[0];
+        if (tile >= P.n_tiles) break;
+        const uint64_t base = (uint64_t)tile * T;
+
+        // ---- evaluate the B sub-batches ----
+        uint32_t alive[B], excb[B];
+        auto eval = [&](uint32_t b, const ulonglong2 (&vin)[J][JIT_NIN]) {
+            const uint64_t sb = base + (uint64_t)b * TS;
+            uint32_t al = 0, ex = 0;
+            uint32_t ec[2 * J];
+#pragma unroll
+            for (uint32_t j = 0; j < J; ++j) {
+                const uint64_t row = sb + VV::lrow(j, 0);
+                uint64_t in0[JIT_NIN], in1[JIT_NIN], o0[JIT_NLIVE], o1[JIT_NLIVE];
+#pragma unroll
+                for (uint32_t k = 0; k < JIT_NIN; ++k) { in0[k] = vin[j][k].x; in1[k] = vin[j][k].y; }
+#pragma unroll
+                for (uint32_t k = 0; k < JIT_NLIVE; ++k) { o0[k] = 0; o1[k] = 0; }
+                bool a0 = row < P.n_rows, a1 = row + 1 < P.n_rows;
+                uint32_t e0 = 0, e1 = 0;
+                if (a0) jit_row_fixed(row, in0, a0, e0, o0);
+                if (a1) jit_row_fixed(row + 1, in1, a1, e1, o1);
+                al |= (a0 ? 1u : 0u) << (2 * j) | (a1 ? 2u : 0u) << (2 * j);
+                ex |= (e0 ? 1u : 0u) << (2 * j) | (e1 ? 2u : 0u) << (2 * j);
+                ec[2 * j] = e0;
+                ec[2 * j + 1] = e1;
+#pragma unroll
+                for (uint32_t k = 0; k < JIT_NLIVE; ++k)
+                    *reinterpret_cast<ulonglong2 *>(rb + k * SLOT_W + b * (TS * 8) + j * VV::SLAB) = make_ulonglong2(o0[k], o1[k]);
+            }
+            if (ex) {  // after the stores: the code takes the place of the (unwritten) row's slot 0
+#pragma unroll
+                for (uint32_t v = 0; v < 2 * J; ++v)
+                    if ((ex >> v) & 1u) *code_at(b, VV::lrow(v >> 1, v & 1)) = ec[v];
+            }
+            alive[b] = al;
+            excb[b] = ex;
+        };
+        if constexpr (JIT_NIN <= 2) {  // two sub-batches of input in registers: the next one is in flight while this one is evaluated
+            ulonglong2 va[J][JIT_NIN], vb[J][JIT_NIN];
+            jit_load_vec<J>(va, s_cols, base, P.n_rows, base + TS <= P.n_rows);
+#pragma unroll
+            for (uint32_t b = 0; b < B; b += 2) {
+                jit_load_vec<J>(vb, s_cols, base + (uint64_t)(b + 1) * TS, P.n_rows, base + (uint64_t)(b + 2) * TS <= P.n_rows);
+                eval(b, va);
+                if (b + 2 < B) jit_load_vec<J>(va, s_cols, base + (uint64_t)(b + 2) * TS, P.n_rows, base + (uint64_t)(b + 3) * TS <= P.n_rows);
+                eval(b + 1, vb);
+            }
+        } else {
+#pragma unroll
+            for (uint32_t b = 0; b < B; ++b) {
+                ulonglong2 va[J][JIT_NIN];
+                jit_load_vec<J>(va, s_cols, base + (uint64_t)b * TS, P.n_rows, base + (uint64_t)(b + 1) * TS <= P.n_rows);
+                eval(b, va);
+            }
+        }
+
+        // ---- counts per (sub-batch, slab, warp) group ----
+        uint32_t any_exc = 0;
+#pragma unroll
+        for (uint32_t b = 0; b < B; ++b) any_exc |= excb[b];
+        const bool warp_exc = __any_sync(0xFFFFFFFFu, any_exc != 0);
+#pragma unroll
+        for (uint32_t b = 0; b < B; ++b) {
+#pragma unroll
+            for (uint32_t j = 0; j < J; ++j) {
+                const uint32_t ke = __ballot_sync(0xFFFFFFFFu, (alive[b] >> (2 * j)) & 1u), ko = __ballot_sync(0xFFFFFFFFu, (alive[b] >> (2 * j + 1)) & 1u);
+                uint32_t cnt = __popc(ke) + __popc(ko);
+                if (warp_exc) {
+                    const uint32_t ee = __ballot_sync(0xFFFFFFFFu, (excb[b] >> (2 * j)) & 1u), eo = __ballot_sync(0xFFFFFFFFu, (excb[b] >> (2 * j + 1)) & 1u);
+                    cnt |= (__popc(ee) + __popc(eo)) << 16;
+                }
+                if (lane == 0) s_cnt[b * 32 + j * 8 + warp] = cnt;
+            }
+        }
+        __syncthreads();
+        // every warp scans the B x 32 group counts (kept in the low half, raised in the high half: both <= T = 8192 < 2^16)
+        uint32_t gex[B], run = 0;
+#pragma unroll
+        for (uint32_t b = 0; b < B; ++b) {
+            uint32_t gi = s_cnt[b * 32 + lane];
+            const uint32_t gmine = gi;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, gi, o);
+                if (lane >= (uint32_t)o) gi += u;
+            }
+            gex[b] = run + gi - gmine;  // exclusive prefix of group (b, lane) inside the tile
+            run += __shfl_sync(0xFFFFFFFFu, gi, 31);
+        }
+        const uint32_t n_keep = run & 0xFFFFu, n_exc = run >> 16;
+        if (tid == 0)  // publish this tile's counts (tile 0: they are its inclusive prefix)
+            st_cg_u64(P.tile_state + tile, ((uint64_t)(tile == 0 ? 2u : 1u) << 62) | ((uint64_t)n_keep << 31) | (uint64_t)n_exc);
+
+        uint64_t pre_keep = 0, pre_exc = 0;
+        vec_lookback(P, tile, n_keep, n_exc, s_scr, pre_keep, pre_exc);
+        if (tid == 0 && tile == P.n_tiles - 1) {
+            P.totals[0] = pre_keep + n_keep;
+            P.totals[1] = pre_exc + n_exc;
+        }
+
+        // ---- write: every thread stores its own rows, straight from its column of the register file ----
+        const bool exc_fit = pre_exc + n_exc <= P.cap_exc;
+        if (n_exc && !exc_fit && tid == 0) atomicOr(&P.counters[1], 4u);
+#pragma unroll
+        for (uint32_t b = 0; b < B; ++b) {
+#pragma unroll
+            for (uint32_t j = 0; j < J; ++j) {
+                const uint32_t a0 = (alive[b] >> (2 * j)) & 1u, a1 = (alive[b] >> (2 * j + 1)) & 1u;
+                const uint32_t ke = __ballot_sync(0xFFFFFFFFu, a0), ko = __ballot_sync(0xFFFFFFFFu, a1);
+                const uint32_t gpre = __shfl_sync(0xFFFFFFFFu, gex[b], j * 8 + warp);
+                const uint32_t kk = (gpre & 0xFFFFu) + __popc(ke & lt) + __popc(ko & lt);  // kept rows of the tile before this thread's even row
+                if (a0 | a1) {
+                    const uint64_t at = pre_keep + kk;
+                    for (uint32_t c = 0; c < P.n_out; ++c) {
+                        const OutCol &oc = P.out[c];
+                        uint64_t *od = oc.data;
+                        __builtin_assume(__isGlobal(od));
+                        const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(rb + oc.stage_off + b * (TS * 8) + j * VV::SLAB);
+                        if (a0) od[at] = v.x;
+                        if (a1) od[at + a0] = v.y;
+                    }
+                }
+                if (n_exc && exc_fit) {  // uniform
+                    const uint32_t x0 = (excb[b] >> (2 * j)) & 1u, x1 = (excb[b] >> (2 * j + 1)) & 1u;
+                    const uint32_t ee = __ballot_sync(0xFFFFFFFFu, x0), eo = __ballot_sync(0xFFFFFFFFu, x1);
+                    const uint32_t ek = (gpre >> 16) + __popc(ee & lt) + __popc(eo & lt);
+                    for (uint32_t h = 0; h < 2; ++h) {
+                        if (!(h ? x1 : x0)) continue;
+                        const uint32_t lr = VV::lrow(j, h);
+                        const uint32_t ke_ = ek + (h ? x0 : 0), kk_ = kk + (h ? a0 : 0);
+                        tplx_exception_rec rec;
+                        rec.row = (int64_t)(base + (uint64_t)b * TS + lr);
+                        rec.row_no = P.first_row_no + (int64_t)(pre_keep + pre_exc + kk_ + ke_);  // rows written + exceptions so far (TransformTask.cc:764,885)
+                        const uint32_t es = *code_at(b, lr);
+                        rec.code = es & 0xFFFF;
+                        rec.op_id = P.opids[es >> 16];
+                        P.exc[pre_exc + ke_] = rec;
+                    }
+                }
+            }
+        }
+        if (tid == 0) s_ctl[0] = atomicAdd(&P.counters[0], 1u);  // every thread read the old ticket before the counts barrier of this tile
+    }
+}
+#endif  // K1w
+
+#if !defined(TPLX_JIT) || TPLX_JIT_KIND == 2 || TPLX_JIT_KIND == 3
 #ifdef TPLX_JIT
-// TPLX_JIT_KIND 7 = J 4 with the PIPELINED tile loop: the next ticket is taken as soon as this tile's counts are published and the
-// next tile's input is loaded (LDG.128 into registers) while this tile waits for its predecessors and writes.
-#define TPLX_JIT_PIPE (TPLX_JIT_KIND == 7)
 extern "C" __global__ void __launch_bounds__(NT, TPLX_JIT_MINB) tplx_jit_kernel(const __grid_constant__ KParams P) {
     constexpr int J = TPLX_JIT_KIND == 3 ? 2 : 4;
 #else
@@ -390,8 +608,8 @@ __global__ void __launch_bounds__(NT, 4) stage_rows_vec_kernel(const __grid_cons
     uint8_t *s_regs = smem + P.smem_regs_off;
     uint32_t *s_cnt = reinterpret_cast<uint32_t *>(smem + P.smem_misc_off);
     uint32_t *exc_stage = s_cnt + 32;
-    uint64_t *s_scr = reinterpret_cast<uint64_t *>(exc_stage + T);  // look-back scratch: 2 words per warp
-    uint32_t *s_ctl = reinterpret_cast<uint32_t *>(s_scr + 2 * (NT / 32));  // [0] ticket
+    uint64_t *s_scr = reinterpret_cast<uint64_t *>(exc_stage + T);  // look-back scratch: 2 words per warp, double-buffered
+    uint32_t *s_ctl = reinterpret_cast<uint32_t *>(s_scr + 4 * (NT / 32));  // [0] ticket
 
     for (uint32_t i = tid; i < P.n_instr * (sizeof(VInstr) / 16); i += NT)
         reinterpret_cast<uint4 *>(s_prog)[i] = reinterpret_cast<const uint4 *>(P.prog)[i];
@@ -401,22 +619,14 @@ __global__ void __launch_bounds__(NT, 4) stage_rows_vec_kernel(const __grid_cons
     const uint32_t lt = (1u << lane) - 1u;
 
     // Tickets are taken when the tile starts, not ahead of time: a ticket held while its owner still works on the previous tile
-    // stalls the look-back of every later tile (measured: 103 -> 77 G rows/s on C1 with one ticket of lookahead).
-#if defined(TPLX_JIT) && TPLX_JIT_PIPE
-    ulonglong2 vin[J][JIT_NIN];
+    // stalls the look-back of every later tile (measured: 103 -> 77 G rows/s on C1 with one ticket of lookahead; loading the next
+    // tile's input under the look-back of this one: 149 -> 112 G rows/s). Thread 0 takes the next ticket when IT has finished the
+    // tile (its atomic overlaps the other warps' stores) and one barrier at the top of the loop publishes it.
     if (tid == 0) s_ctl[0] = atomicAdd(&P.counters[0], 1u);
-    __syncthreads();
-    uint32_t tile = s_ctl[0];
-    if (tile < P.n_tiles) jit_load_vec<J>(vin, s_cols, (uint64_t)tile * T, P.n_rows, (uint64_t)tile * T + T <= P.n_rows);
-    while (tile < P.n_tiles) {
-#else
     while (true) {
-        __syncthreads();  // s_cnt, the ticket and the look-back scratch are rewritten below
-        if (tid == 0) s_ctl[0] = atomicAdd(&P.counters[0], 1u);
-        __syncthreads();
+        __syncthreads();  // the ticket is visible; s_cnt and the look-back scratch of the previous tile are no longer read
         const uint32_t tile = s_ctl[0];
         if (tile >= P.n_tiles) break;
-#endif
         const uint64_t base = (uint64_t)tile * T;
         const bool full = base + T <= P.n_rows;  // uniform
 
@@ -429,9 +639,7 @@ __global__ void __launch_bounds__(NT, 4) stage_rows_vec_kernel(const __grid_cons
             for (uint32_t v = 0; v < 2 * J; ++v)
                 if (base + VecVM<J>::lrow(v >> 1, v & 1) < P.n_rows) st.alive |= 1u << v;
         }
-#if defined(TPLX_JIT) && TPLX_JIT_PIPE
-        jit_eval_vec<J>(vin, rb, base, st, exc_stage);
-#elif defined(TPLX_JIT)
+#if defined(TPLX_JIT)
         {
             ulonglong2 vin[J][JIT_NIN];
             jit_load_vec<J>(vin, s_cols, base, P.n_rows, full);
@@ -468,47 +676,9 @@ __global__ void __launch_bounds__(NT, 4) stage_rows_vec_kernel(const __grid_cons
         if (tid == 0)  // publish this tile's counts (tile 0: they are its inclusive prefix)
             st_cg_u64(P.tile_state + tile, ((uint64_t)(tile == 0 ? 2u : 1u) << 62) | ((uint64_t)n_keep << 31) | (uint64_t)n_exc);
 
-#if defined(TPLX_JIT) && TPLX_JIT_PIPE
-        // the counts are out: take the next ticket now and start loading that tile — the loads fly while this tile looks back and writes
-        if (tid == 0) s_ctl[1] = atomicAdd(&P.counters[0], 1u);
-        __syncthreads();
-        const uint32_t next_tile = s_ctl[1];
-        if (next_tile < P.n_tiles) jit_load_vec<J>(vin, s_cols, (uint64_t)next_tile * T, P.n_rows, (uint64_t)next_tile * T + T <= P.n_rows);
-#endif
         // ---- look-back: 256 predecessors per round ----
         uint64_t pre_keep = 0, pre_exc = 0;
-        if (tile > 0) {
-            int64_t p = (int64_t)tile - 1;
-            while (true) {
-                const int64_t q = p - (int64_t)tid;
-                uint64_t wd = (uint64_t)2 << 62;  // tiles before the first count as an inclusive prefix of zero
-                if (q >= 0) do { wd = ld_relaxed_u64(P.tile_state + q); } while ((wd >> 62) == 0);
-                const bool incl = (wd >> 62) == 2;
-                const uint32_t im = __ballot_sync(0xFFFFFFFFu, incl);
-                const uint32_t first = im ? (uint32_t)(__ffs(im) - 1) : 32u;  // nearest inclusive word inside this warp's 32 tiles
-                uint64_t k = lane <= first ? (wd >> 31) & 0x7FFFFFFFull : 0, e = lane <= first ? wd & 0x7FFFFFFFull : 0;
-#pragma unroll
-                for (int o = 16; o; o >>= 1) {
-                    k += __shfl_xor_sync(0xFFFFFFFFu, k, o);
-                    e += __shfl_xor_sync(0xFFFFFFFFu, e, o);
-                }
-                if (lane == 0) {
-                    s_scr[warp * 2] = (k << 32) | e;  // counts are < 2^31 in total: 32 bits each
-                    s_scr[warp * 2 + 1] = im ? 1 : 0;
-                }
-                __syncthreads();
-                bool done = false;
-                for (uint32_t w = 0; w < NT / 32 && !done; ++w) {  // warps cover tile-1-32w .. : nearest first
-                    pre_keep += s_scr[w * 2] >> 32;
-                    pre_exc += s_scr[w * 2] & 0xFFFFFFFFull;
-                    done = s_scr[w * 2 + 1] != 0;
-                }
-                __syncthreads();
-                if (done) break;
-                p -= NT;
-            }
-            if (tid == 0) st_cg_u64(P.tile_state + tile, ((uint64_t)2 << 62) | ((pre_keep + n_keep) << 31) | (pre_exc + n_exc));
-        }
+        vec_lookback(P, tile, n_keep, n_exc, s_scr, pre_keep, pre_exc);
         if (tid == 0 && tile == P.n_tiles - 1) {
             P.totals[0] = pre_keep + n_keep;
             P.totals[1] = pre_exc + n_exc;
@@ -552,9 +722,7 @@ __global__ void __launch_bounds__(NT, 4) stage_rows_vec_kernel(const __grid_cons
                 }
             }
         }
-#if defined(TPLX_JIT) && TPLX_JIT_PIPE
-        tile = next_tile;
-#endif
+        if (tid == 0) s_ctl[0] = atomicAdd(&P.counters[0], 1u);  // every thread read the old ticket before the counts barrier of this tile
     }
 }
 #endif  // K1v
