@@ -689,7 +689,8 @@ def measure(args, wl_key, rank, world, local, dist, hc):
             wl["name"], {0: "stage_rows_kernel", 1: "stage_agg_kernel", 2: "stage_hash_kernel"}[ep])
         if stats.get("specialised", 0):  # the stage specialiser's build of the same kernel source ran (tplx_jit_kernel)
             kname = kname.replace("stage_rows_kernel (dense", "stage_rows_kernel specialised for this stage at run time (NVRTC, tplx_jit_kernel; dense") \
-                         .replace("stage_rows_vec_kernel<4> (K1v)", "stage_rows_vec_kernel<4> (K1v) specialised for this stage at run time (NVRTC, tplx_jit_kernel)")
+                         .replace("stage_rows_vec_kernel<4> (K1v)", "tplx_jit_kernel = K1r (vecvm.cuh), the fixed-width row kernel specialised for this stage at run time "
+                                                                    "(NVRTC): fates + counts in pass 1, outputs in pass 2 from L2, nothing staged")
         line = {
             "value": rows_all / (dt / args.steps), "unit": "rows/s", "ms_per_step": ms_step,
             "timed_region": {"repeats": len(reps), "seconds_measured": spent, "reported": "median repeat of K steps, max over ranks",

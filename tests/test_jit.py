@@ -247,16 +247,18 @@ def test_tiered_execution_background_compile(gpu):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n", [1, 8191, 8192, 8193, 100_003, 3_000_001])
-@pytest.mark.parametrize("wide", [4, 2, 0])
-def test_wide_tile_kernel_with_exceptions(gpu, n, wide):
-    """K1w (B sub-batches of 2048 rows per ticket) vs the oracle: ragged tiles, ZeroDivisionError rows (their codes live in slot 0 of
-    the raising row), a filter, one and two output columns; TPLX_JIT_WIDE = 4 / 2 / 0 selects B = 4, B = 2 or K1v's 2048-row tiles."""
-    rng = np.random.default_rng(n + wide)
+@pytest.mark.parametrize("n", [1, 8191, 8192, 8193, 16385, 100_003, 3_000_001])
+@pytest.mark.parametrize("kernel", ["re2", "re4", "re8", "wide4", "wide2", "k1v"])
+def test_wide_tile_kernels_with_exceptions(gpu, n, kernel):
+    """The specialised fixed-width kernels with tiles wider than K1v's 2048 rows vs the oracle — K1r (nothing staged, the tile is
+    evaluated again from L2 once its offset is known; 2 / 4 / 8 sub-batches of 2048 rows per ticket, two tiles in flight per CTA) and K1w (live-out slots of 4 / 2
+    sub-batches staged in shared memory) — on ragged tiles, with ZeroDivisionError rows, a filter, one and two output columns."""
+    rng = np.random.default_rng(n)
     a = rng.integers(-10_000, 10_000, n)
     cols = [backend.Column(ir.T_I64, a)]
-    old = os.environ.get("TPLX_JIT_WIDE")
-    os.environ["TPLX_JIT_WIDE"] = str(wide)
+    env = {"re2": ("2", "0"), "re4": ("4", "0"), "re8": ("8", "0"), "wide4": ("0", "4"), "wide2": ("0", "2"), "k1v": ("0", "0")}[kernel]
+    old = {k: os.environ.get(k) for k in ("TPLX_JIT_RE", "TPLX_JIT_WIDE")}
+    os.environ["TPLX_JIT_RE"], os.environ["TPLX_JIT_WIDE"] = env
     try:
         for two in (False, True):
             sc = frontend.StageCompiler([ir.T_I64], ["a"])
@@ -269,12 +271,13 @@ def test_wide_tile_kernel_with_exceptions(gpu, n, wide):
             with jit_mode(2):
                 st = backend.Stage(prog)
                 res = st.run_host(0, cols, n, first_row_no=5)
-                assert_result_equals_oracle(res, ora, f"n={n} wide={wide} two={two}")
+                assert_result_equals_oracle(res, ora, f"n={n} kernel={kernel} two={two}")
                 assert int(res.info.specialised_launches) > 0
                 res.free()
                 st.close()
     finally:
-        if old is None:
-            os.environ.pop("TPLX_JIT_WIDE", None)
-        else:
-            os.environ["TPLX_JIT_WIDE"] = old
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v

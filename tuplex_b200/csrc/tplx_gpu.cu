@@ -676,7 +676,7 @@ static std::shared_ptr<jit::Binary> jit_binary(tplx_stage *s, int kind, int minb
     }
     auto bin = std::make_shared<jit::Binary>();
     s->jit_bin[kind] = bin;
-    std::string src = jit::generate(s->hdr, s->instrs, s->in_types, s->jit_live, kind);
+    std::string src = jit::generate(s->hdr, s->instrs, s->in_types, s->jit_live, s->out_cols, kind);
     if (wait) jit_compile_job(bin, std::move(src), kind, minb, s->instrs.size());
     else bin->worker = std::thread(jit_compile_job, bin, std::move(src), kind, minb, s->instrs.size());
     return bin;
@@ -688,6 +688,7 @@ static int jit_minb(const tplx_stage *s, int kind) {
         case jit::K_VEC4: return env("TPLX_JIT_MINB_VEC", 8);
         case jit::K_WIDE4: return env("TPLX_JIT_MINB_WIDE", 3);
         case jit::K_WIDE2: return env("TPLX_JIT_MINB_WIDE", 4);
+        case jit::K_RE4: case jit::K_RE8: case jit::K_RE2: case jit::K_RE1: return env("TPLX_JIT_MINB_RE", 6);
         case jit::K_VEC2: return env("TPLX_JIT_MINB_VEC", 3);
         case jit::K_MASK: return env("TPLX_JIT_MINB_MASK", 4);
         default: return env("TPLX_JIT_MINB", 3);
@@ -800,8 +801,8 @@ extern "C" int32_t tplx_gpu_stage_vec_plan(const tplx_stage *s, tplx_vec_uop *ou
 
 extern "C" int32_t tplx_gpu_stage_specialise(tplx_stage *s, int32_t kind, int32_t compile, char *src, uint64_t src_cap, uint64_t *src_len,
                                              uint64_t *cubin_bytes, char *log, uint64_t log_cap) {
-    if (!s || kind < jit::K_ROWS || kind > jit::K_WIDE2) return fail(TPLX_E_BADARG, "stage_specialise: bad arguments");
-    if ((kind == jit::K_VEC4 || kind == jit::K_VEC2 || kind == jit::K_WIDE4 || kind == jit::K_WIDE2) && !s->vec_ok) return fail(TPLX_E_UNSUPPORTED, "stage_specialise: not a fixed-width MEMORY stage");
+    if (!s || kind < jit::K_ROWS || kind > jit::K_RE1) return fail(TPLX_E_BADARG, "stage_specialise: bad arguments");
+    if ((kind == jit::K_VEC4 || kind == jit::K_VEC2 || kind >= jit::K_WIDE4) && !s->vec_ok) return fail(TPLX_E_UNSUPPORTED, "stage_specialise: not a fixed-width MEMORY stage");
     std::string text;
     size_t nb = 0;
     std::string lg;
@@ -811,7 +812,7 @@ extern "C" int32_t tplx_gpu_stage_specialise(tplx_stage *s, int32_t kind, int32_
         text = bin->source;
         nb = bin->failed ? 0 : bin->cubin.size();
         lg = bin->log;
-    } else text = jit::generate(s->hdr, s->instrs, s->in_types, s->jit_live, kind);
+    } else text = jit::generate(s->hdr, s->instrs, s->in_types, s->jit_live, s->out_cols, kind);
     if (src_len) *src_len = text.size();
     if (src && src_cap) {
         const size_t n = std::min<size_t>(text.size(), src_cap - 1);
@@ -1275,12 +1276,28 @@ static int32_t run_rows_vec(tplx_stage *s, StageDev *sd, const tplx_block *b, in
     if (jit_wanted(s, n)) {
         const uint32_t nl = std::max<uint32_t>((uint32_t)s->jit_live.slots.size(), 1);
         const int forceJ = getenv("TPLX_JIT_VEC_J") ? atoi(getenv("TPLX_JIT_VEC_J")) : 0;  // experiments: tile size at equal occupancy
+        bool wide_pending = false;
         // K1w (wide tiles: B sub-batches of 2048 rows per ticket) when the live-out slots of B sub-batches fit the shared memory of
         // 3 (B = 4) / 4 (B = 2) resident CTAs; TPLX_JIT_WIDE=0 keeps K1v's 2048-row tiles
         const int wide_max = getenv("TPLX_JIT_WIDE") ? atoi(getenv("TPLX_JIT_WIDE")) : 4;
-        bool wide_pending = false;
+        // K1r (nothing staged, the tile is evaluated again from L2 once its offset is known) for programs of a few operations
+        const int re_b = getenv("TPLX_JIT_RE") ? atoi(getenv("TPLX_JIT_RE")) : 2;
+        const size_t re_max = getenv("TPLX_JIT_RE_MAX_INSTR") ? (size_t)atoi(getenv("TPLX_JIT_RE_MAX_INSTR")) : 16;
+        if (!forceJ && (re_b == 4 || re_b == 8 || re_b == 2 || re_b == 1) && s->instrs.size() <= re_max) {
+            const uint32_t Tw = (uint32_t)re_b * 2048u;
+            size_t off = 16;
+            const uint32_t c_off = (uint32_t)off;
+            off = align_up(off + std::max<size_t>(s->in_types.size(), 1) * sizeof(ColIn), 16);
+            const uint32_t r_off = (uint32_t)off;  // no register file
+            const uint32_t m_off = (uint32_t)off;
+            off += (size_t)re_b * 32 * 4 + (size_t)(4 * (NT / 32)) * 8 + 16;
+            const int kind = re_b == 4 ? jit::K_RE4 : (re_b == 8 ? jit::K_RE8 : (re_b == 2 ? jit::K_RE2 : jit::K_RE1));
+            jf = jit_get(s, sd, kind, jit_minb(s, kind));
+            if (jf) { Jsel = 4; T = Tw; cols_off = c_off; regs_off = r_off; misc_off = m_off; smem = (uint32_t)align_up(off, 16); }
+            else if (jit_pending(s, kind)) wide_pending = true;
+        }
         for (int Bw : {4, 2}) {
-            if (jf || forceJ || Bw > wide_max) continue;
+            if (jf || wide_pending || forceJ || Bw > wide_max) continue;
             const uint32_t Tw = (uint32_t)Bw * 2048u;
             size_t off = 16;
             const uint32_t c_off = (uint32_t)off;
@@ -1385,6 +1402,11 @@ static int32_t run_rows_vec(tplx_stage *s, StageDev *sd, const tplx_block *b, in
         if (rc) return rc;
     }
     P.cap_rows = n;
+    if (jf && getenv("TPLX_JIT_TIMES")) {  // diagnostic build of K1w: per-tile phase clocks
+        rc = dalloc(r, &P.tile_partials, (size_t)P.n_tiles * 8);
+        if (rc) return rc;
+        CU(cudaMemsetAsync(P.tile_partials, 0, (size_t)P.n_tiles * 64, d->stream));
+    }
     uint64_t cap_exc = std::max<uint64_t>(4096, (uint64_t)(s->est_exc_per_row * 1.5 * (double)n) + n / 64);
     for (int attempt = 0; attempt < 2; ++attempt) {
         P.cap_exc = cap_exc;
@@ -1411,6 +1433,11 @@ static int32_t run_rows_vec(tplx_stage *s, StageDev *sd, const tplx_block *b, in
         cap_exc = r->n_exc + 16;
     }
     CU(cudaEventRecord(r->evk1, d->stream));
+    if (P.tile_partials && getenv("TPLX_JIT_TIMES")) {
+        std::vector<uint64_t> h((size_t)P.n_tiles * 8);
+        CU(cudaMemcpy(h.data(), P.tile_partials, h.size() * 8, cudaMemcpyDeviceToHost));
+        if (FILE *f = fopen(getenv("TPLX_JIT_TIMES"), "wb")) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
+    }
     for (size_t c = 0; c < s->out_cols.size(); ++c) r->out[c] = P.out[c];
     r->exc = P.exc;
     return TPLX_OK;

@@ -408,6 +408,12 @@ __device__ __forceinline__ void jit_eval_vec(const ulonglong2 (&vin)[J][JIT_NIN]
 }
 #endif
 
+#ifdef TPLX_JIT_TIMES
+#define TPLX_TQ(i) tq[i] = clock64()
+#else
+#define TPLX_TQ(i)
+#endif
+
 #if defined(TPLX_JIT) && (TPLX_JIT_KIND == 6 || TPLX_JIT_KIND == 7)
 // ---- K1w: the specialised fixed-width row kernel with WIDE tiles ---------------------------------------------------------------------
 // Measured on C1 (profiles/r02_jit.md): with the interpretation gone, K1v is bound by the latency chain of a tile — ticket, LDG,
@@ -446,6 +452,10 @@ extern "C" __global__ void __launch_bounds__(NT, TPLX_JIT_MINB) tplx_jit_kernel(
         const uint32_t tile = s_ctl[0];
         if (tile >= P.n_tiles) break;
         const uint64_t base = (uint64_t)tile * T;
+#ifdef TPLX_JIT_TIMES  // diagnostic build (TPLX_JIT_TIMES=<file>): thread 0's clock at the phase boundaries of every tile
+        long long tq[6];
+        tq[0] = clock64();
+#endif
 
         // ---- evaluate the B sub-batches ----
         uint32_t alive[B], excb[B];
@@ -500,6 +510,7 @@ extern "C" __global__ void __launch_bounds__(NT, TPLX_JIT_MINB) tplx_jit_kernel(
             }
         }
 
+        TPLX_TQ(1);
         // ---- counts per (sub-batch, slab, warp) group ----
         uint32_t any_exc = 0;
 #pragma unroll
@@ -537,8 +548,10 @@ extern "C" __global__ void __launch_bounds__(NT, TPLX_JIT_MINB) tplx_jit_kernel(
         if (tid == 0)  // publish this tile's counts (tile 0: they are its inclusive prefix)
             st_cg_u64(P.tile_state + tile, ((uint64_t)(tile == 0 ? 2u : 1u) << 62) | ((uint64_t)n_keep << 31) | (uint64_t)n_exc);
 
+        TPLX_TQ(2);
         uint64_t pre_keep = 0, pre_exc = 0;
         vec_lookback(P, tile, n_keep, n_exc, s_scr, pre_keep, pre_exc);
+        TPLX_TQ(3);
         if (tid == 0 && tile == P.n_tiles - 1) {
             P.totals[0] = pre_keep + n_keep;
             P.totals[1] = pre_exc + n_exc;
@@ -585,10 +598,213 @@ extern "C" __global__ void __launch_bounds__(NT, TPLX_JIT_MINB) tplx_jit_kernel(
                 }
             }
         }
+        TPLX_TQ(4);
         if (tid == 0) s_ctl[0] = atomicAdd(&P.counters[0], 1u);  // every thread read the old ticket before the counts barrier of this tile
+#ifdef TPLX_JIT_TIMES
+        if (tid == 0 && P.tile_partials) {
+            tq[5] = clock64();
+            uint32_t smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            for (int i = 0; i < 6; ++i) P.tile_partials[(size_t)tile * 8 + i] = (uint64_t)tq[i];
+            P.tile_partials[(size_t)tile * 8 + 6] = smid;
+            P.tile_partials[(size_t)tile * 8 + 7] = blockIdx.x;
+        }
+#endif
     }
 }
 #endif  // K1w
+
+#if defined(TPLX_JIT) && (TPLX_JIT_KIND >= 8 && TPLX_JIT_KIND <= 11)
+// ---- K1r: the specialised fixed-width row kernel that stages NOTHING: L2 is the staging buffer ----------------------------------------
+// Per-tile phase clocks of K1w on C1 (tools/tile_times.py, profiles/r02_jit.md): load + evaluate 5.4 us, counts 1.0 us, look-back 5.5 us
+// (= waiting for the slowest load among the ~1000 tiles in flight: in-order retirement), stores 3.0 us. Rows sit in shared memory from
+// their evaluation to their store, ~12 us, and shared memory bounds the rows in flight (148 x 227 KB / 8 B = 4 M rows): throughput =
+// rows in flight / latency = what was measured. Short of making DRAM latency deterministic, the way out is to hold rows in flight
+// somewhere bigger: the 126 MB L2. K1r evaluates a tile TWICE:
+//   pass 1: LDG.128 the inputs, run the row function for the row's FATE only (kept / filtered / raised: two bits per row in registers),
+//           count, publish — nothing is staged;
+//   pass 2: once the tile's offset is known, LDG.128 the same inputs again (read a few microseconds ago: L2 hits, ncu: DRAM reads
+//           1.15 x algorithmic), run the row function again and store the outputs of the kept rows straight from registers.
+// DRAM traffic stays algorithmic (one read, one write), the second read costs L2 bandwidth and the second evaluation instructions — a
+// trade for programs of a few operations (the planner picks K1r for those, K1w otherwise). No shared memory beyond the counts, so a
+// CTA can keep TWO tiles in flight for the price of ten registers: the look-back of tile A (the wait for the slowest of its predecessors)
+// is done after pass 1 of the CTA's next tile B has been issued and B's counts are published — the wait overlaps real work, and no
+// ticket is ever held without its counts being produced as fast as the CTA can.
+extern "C" __global__ void __launch_bounds__(NT, TPLX_JIT_MINB) tplx_jit_kernel(const __grid_constant__ KParams P) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr int J = 4, B = TPLX_JIT_KIND == 8 ? 4 : (TPLX_JIT_KIND == 9 ? 8 : (TPLX_JIT_KIND == 10 ? 2 : 1));
+    using VV = VecVM<J>;
+    constexpr uint32_t TS = VV::T, T = B * TS;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    ColIn *s_cols = reinterpret_cast<ColIn *>(smem + P.smem_cols_off);
+    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(smem + P.smem_misc_off);  // [B][32]: kept | raised << 16 per (sub-batch, slab, warp)
+    uint64_t *s_scr = reinterpret_cast<uint64_t *>(s_cnt + B * 32);
+    uint32_t *s_ctl = reinterpret_cast<uint32_t *>(s_scr + 4 * (NT / 32));
+
+    for (uint32_t i = tid; i < P.n_in * (sizeof(ColIn) / 8); i += NT)
+        reinterpret_cast<uint64_t *>(s_cols)[i] = reinterpret_cast<const uint64_t *>(P.in)[i];
+    const uint32_t lt = (1u << lane) - 1u;
+
+    struct Tile {            // what a thread keeps of a tile between its two passes
+        uint32_t tile;       // ticket
+        uint64_t alive, excm;  // bit b * 8 + v: row v of this thread in sub-batch b is kept / raised
+        uint32_t gex[B];     // exclusive prefix (kept | raised << 16) of group (b, lane) inside the tile
+        uint32_t n_keep, n_exc;
+    };
+
+    // pass 1 + counts + publication of tile t.tile (all threads; one barrier)
+    auto first_pass = [&](Tile &t) {
+        const uint64_t base = (uint64_t)t.tile * T;
+        uint64_t alive = 0, excm = 0;
+#pragma unroll
+        for (uint32_t b = 0; b < B; ++b) {
+            ulonglong2 vin[J][JIT_NIN];
+            const uint64_t sb = base + (uint64_t)b * TS;
+            jit_load_vec<J>(vin, s_cols, sb, P.n_rows, sb + TS <= P.n_rows);
+#pragma unroll
+            for (uint32_t j = 0; j < J; ++j) {
+                const uint64_t row = sb + VV::lrow(j, 0);
+                uint64_t in0[JIT_NIN], in1[JIT_NIN], o0[JIT_NLIVE], o1[JIT_NLIVE];
+#pragma unroll
+                for (uint32_t k = 0; k < JIT_NIN; ++k) { in0[k] = vin[j][k].x; in1[k] = vin[j][k].y; }
+                bool a0 = row < P.n_rows, a1 = row + 1 < P.n_rows;
+                uint32_t e0 = 0, e1 = 0;
+                if (a0) jit_row_fixed(row, in0, a0, e0, o0);
+                if (a1) jit_row_fixed(row + 1, in1, a1, e1, o1);
+                alive |= (uint64_t)((a0 ? 1u : 0u) | (a1 ? 2u : 0u)) << (b * 8 + 2 * j);
+                excm |= (uint64_t)((e0 ? 1u : 0u) | (e1 ? 2u : 0u)) << (b * 8 + 2 * j);
+            }
+        }
+        const bool warp_exc = __any_sync(0xFFFFFFFFu, excm != 0);
+#pragma unroll
+        for (uint32_t b = 0; b < B; ++b) {
+#pragma unroll
+            for (uint32_t j = 0; j < J; ++j) {
+                const uint32_t sh = b * 8 + 2 * j;
+                const uint32_t ke = __ballot_sync(0xFFFFFFFFu, (alive >> sh) & 1u), ko = __ballot_sync(0xFFFFFFFFu, (alive >> (sh + 1)) & 1u);
+                uint32_t cnt = __popc(ke) + __popc(ko);
+                if (warp_exc) {
+                    const uint32_t ee = __ballot_sync(0xFFFFFFFFu, (excm >> sh) & 1u), eo = __ballot_sync(0xFFFFFFFFu, (excm >> (sh + 1)) & 1u);
+                    cnt |= (__popc(ee) + __popc(eo)) << 16;
+                }
+                if (lane == 0) s_cnt[b * 32 + j * 8 + warp] = cnt;
+            }
+        }
+        __syncthreads();
+        uint32_t run = 0;  // kept in the low half, raised in the high half: both <= T = 16384 < 2^16
+#pragma unroll
+        for (uint32_t b = 0; b < B; ++b) {
+            uint32_t gi = s_cnt[b * 32 + lane];
+            const uint32_t gmine = gi;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, gi, o);
+                if (lane >= (uint32_t)o) gi += u;
+            }
+            t.gex[b] = run + gi - gmine;
+            run += __shfl_sync(0xFFFFFFFFu, gi, 31);
+        }
+        t.alive = alive;
+        t.excm = excm;
+        t.n_keep = run & 0xFFFFu;
+        t.n_exc = run >> 16;
+        if (tid == 0)
+            st_cg_u64(P.tile_state + t.tile, ((uint64_t)(t.tile == 0 ? 2u : 1u) << 62) | ((uint64_t)t.n_keep << 31) | (uint64_t)t.n_exc);
+    };
+
+    // look-back + pass 2 of a tile whose counts were published earlier
+    auto second_pass = [&](const Tile &t) {
+        const uint64_t base = (uint64_t)t.tile * T;
+        uint64_t pre_keep = 0, pre_exc = 0;
+        vec_lookback(P, t.tile, t.n_keep, t.n_exc, s_scr, pre_keep, pre_exc);
+        if (tid == 0 && t.tile == P.n_tiles - 1) {
+            P.totals[0] = pre_keep + t.n_keep;
+            P.totals[1] = pre_exc + t.n_exc;
+        }
+        const bool exc_fit = pre_exc + t.n_exc <= P.cap_exc;
+        if (t.n_exc && !exc_fit && tid == 0) atomicOr(&P.counters[1], 4u);
+        if (!(t.n_keep || (t.n_exc && exc_fit))) return;  // uniform
+#pragma unroll
+        for (uint32_t b = 0; b < B; ++b) {
+            if (!__any_sync(0xFFFFFFFFu, ((t.alive | t.excm) >> (b * 8)) & 0xFFu)) continue;  // nothing of this warp's rows in the sub-batch
+            ulonglong2 vin[J][JIT_NIN];
+            const uint64_t sb = base + (uint64_t)b * TS;
+            jit_load_vec<J>(vin, s_cols, sb, P.n_rows, sb + TS <= P.n_rows);
+#pragma unroll
+            for (uint32_t j = 0; j < J; ++j) {
+                const uint32_t sh = b * 8 + 2 * j;
+                const uint32_t a0 = (uint32_t)(t.alive >> sh) & 1u, a1 = (uint32_t)(t.alive >> (sh + 1)) & 1u;
+                const uint32_t x0 = (uint32_t)(t.excm >> sh) & 1u, x1 = (uint32_t)(t.excm >> (sh + 1)) & 1u;
+                const uint64_t row = sb + VV::lrow(j, 0);
+                uint64_t in0[JIT_NIN], in1[JIT_NIN], o0[JIT_NLIVE], o1[JIT_NLIVE];
+#pragma unroll
+                for (uint32_t k = 0; k < JIT_NIN; ++k) { in0[k] = vin[j][k].x; in1[k] = vin[j][k].y; }
+#pragma unroll
+                for (uint32_t k = 0; k < JIT_NLIVE; ++k) { o0[k] = 0; o1[k] = 0; }
+                bool r0 = true, r1 = true;
+                uint32_t e0 = 0, e1 = 0;
+                if (a0 | x0) jit_row_fixed(row, in0, r0, e0, o0);      // same inputs, same function: same fate as in pass 1
+                if (a1 | x1) jit_row_fixed(row + 1, in1, r1, e1, o1);
+                const uint32_t ke = __ballot_sync(0xFFFFFFFFu, a0), ko = __ballot_sync(0xFFFFFFFFu, a1);
+                const uint32_t gpre = __shfl_sync(0xFFFFFFFFu, t.gex[b], j * 8 + warp);
+                const uint32_t kk = (gpre & 0xFFFFu) + __popc(ke & lt) + __popc(ko & lt);
+                if (a0 | a1) {
+                    const uint64_t at = pre_keep + kk;
+#pragma unroll
+                    for (uint32_t c = 0; c < JIT_NOUT; ++c) {
+                        if (c >= P.n_out) break;
+                        uint64_t *od = P.out[c].data;
+                        __builtin_assume(__isGlobal(od));
+                        if (a0) od[at] = o0[jit_outslot(c)];
+                        if (a1) od[at + a0] = o1[jit_outslot(c)];
+                    }
+                }
+                if (t.n_exc && exc_fit) {  // uniform
+                    const uint32_t ee = __ballot_sync(0xFFFFFFFFu, x0), eo = __ballot_sync(0xFFFFFFFFu, x1);
+                    const uint32_t ek = (gpre >> 16) + __popc(ee & lt) + __popc(eo & lt);
+                    for (uint32_t h = 0; h < 2; ++h) {
+                        if (!(h ? x1 : x0)) continue;
+                        const uint32_t ke_ = ek + (h ? x0 : 0), kk_ = kk + (h ? a0 : 0);
+                        tplx_exception_rec rec;
+                        rec.row = (int64_t)(sb + VV::lrow(j, h));
+                        rec.row_no = P.first_row_no + (int64_t)(pre_keep + pre_exc + kk_ + ke_);  // rows written + exceptions so far (TransformTask.cc:764,885)
+                        const uint32_t es = h ? e1 : e0;
+                        rec.code = es & 0xFFFF;
+                        rec.op_id = P.opids[es >> 16];
+                        P.exc[pre_exc + ke_] = rec;
+                    }
+                }
+            }
+        }
+    };
+
+    // Two tiles in flight per CTA: pass 1 of the new ticket first (its counts are what every successor waits for), then the
+    // look-back + pass 2 of the previous one. TPLX_JIT_DEFER 0: one tile at a time.
+#ifndef TPLX_JIT_DEFER
+#define TPLX_JIT_DEFER 1
+#endif
+    Tile cur, prev;
+    bool have_prev = false;
+    if (tid == 0) s_ctl[0] = atomicAdd(&P.counters[0], 1u);
+    while (true) {
+        __syncthreads();  // the ticket is visible; s_cnt and the look-back scratch are free again
+        cur.tile = s_ctl[0];
+        const bool have = cur.tile < P.n_tiles;  // uniform
+        if (have) first_pass(cur);
+        if (TPLX_JIT_DEFER) {
+            if (have_prev) second_pass(prev);
+            if (!have) break;
+            prev = cur;
+            have_prev = true;
+        } else {
+            if (!have) break;
+            second_pass(cur);
+        }
+        if (tid == 0) s_ctl[0] = atomicAdd(&P.counters[0], 1u);  // every thread has read the old ticket (barrier of first_pass)
+    }
+}
+#endif  // K1r
 
 #if !defined(TPLX_JIT) || TPLX_JIT_KIND == 2 || TPLX_JIT_KIND == 3
 #ifdef TPLX_JIT
