@@ -45,13 +45,16 @@ typedef struct tplx_block tplx_block;   /* a device-resident column block (input
 typedef struct tplx_result tplx_result; /* outputs of one block through a stage */
 
 /* One input column of a column block. Fixed-width types: `data` = n_rows 8-byte values.
- * TPLX_T_STR: `data` = concatenated bytes (no terminators), `offsets` = n_rows+1 uint32. */
+ * TPLX_T_STR: `data` = concatenated bytes (no terminators), `offsets` = n_rows+1 uint32.
+ * Option[T] columns (utils/include/TypeSystem.h; per-row bitmap in the row format, Serializer.cc:1041-1059) carry a validity
+ * bitmap: `valid` = (n_rows + 31) / 32 words, bit (r & 31) of word r >> 5 set = row r holds a value; NULL = no row is None. */
 typedef struct tplx_column {
     uint8_t type; /* tplx_type */
     uint8_t pad[7];
     const void *data;
     const uint32_t *offsets;
     uint64_t data_bytes;
+    const uint32_t *valid;
 } tplx_column;
 
 /* Exception record as produced by the device (fixed width); tplx_gpu_result_exception_partition
@@ -197,6 +200,33 @@ int32_t tplx_gpu_stage_hash_merge(tplx_stage *stage, const tplx_block *packed);
 int32_t tplx_gpu_stage_hash_export_raw(tplx_stage *stage, int32_t device, tplx_result **out);
 /* Drop the device's table (start a new job on the same stage). */
 int32_t tplx_gpu_stage_hash_reset(tplx_stage *stage, int32_t device);
+
+/* ---- hash join (K8): build + probe between two column blocks ----------------------------------- */
+/* Replaces the reference's pair of stages around a JoinOperator: the build stage that appends every row of the smaller side
+ * to the bucket of its key (writeRowToHashTable, core/src/physical/TransformTask.cc:769-842; HashJoinStage.cc) and the probe
+ * inside the row pipeline of the other side (addHashJoinProbe + createInnerJoinBucketLoop / createLeftJoinBucketLoop,
+ * core/src/physical/PipelineBuilder.cc:2110-2523). Output rows: probe rows in input order, the matches of one probe row in
+ * build-row order (bucket order = insertion order); key types i64 / bool / str; a None key matches None keys (null bucket,
+ * test/core/JoinTest.cc:21-133). Column order of the result as in JoinOperator::inferSchema (core/src/logical/JoinOperator.cc:163-184):
+ * | left non-key columns | key | right non-key columns |. Map / filter stages on either side are ordinary tplx_stage runs whose
+ * result columns are wrapped with tplx_gpu_block_wrap_device; the probe shards over devices like any row stage (the table is
+ * built once per device: broadcast join, no exchange). */
+typedef struct tplx_join tplx_join;
+enum tplx_join_flags {
+    TPLX_JOIN_LEFT_OUTER = 1,  /* leftJoin: a probe row without a match is emitted once, build columns None (:2214-2328) */
+    TPLX_JOIN_BUILD_FIRST = 2, /* the build side is the LEFT dataset (JoinOperator::buildRight() false): its columns come first */
+};
+/* Build the table over column key_col of a device-resident block. The block is borrowed until tplx_gpu_join_destroy. */
+int32_t tplx_gpu_join_build(const tplx_block *build, uint32_t key_col, tplx_join **out);
+int32_t tplx_gpu_join_info(const tplx_join *join, uint64_t *n_rows, uint64_t *n_null_rows, double *build_ms, uint32_t *kernel_launches);
+/* Probe with a device-resident block on the same device. The result's columns are fetched with the tplx_gpu_result_* calls;
+ * nullable output columns (left join, Option inputs) also carry a validity bitmap. */
+int32_t tplx_gpu_join_probe(tplx_join *join, const tplx_block *probe, uint32_t key_col, uint32_t flags, tplx_result **out);
+int32_t tplx_gpu_join_destroy(tplx_join *join);
+/* Validity of output column `col`: *nullable = 1 and (n_out_rows + 31) / 32 words (bit set = value present) when the column
+ * can hold None, else *nullable = 0 and `words` untouched. words may be NULL (query only). */
+int32_t tplx_gpu_result_fetch_validity(tplx_result *res, uint32_t col, uint32_t *words, uint32_t *nullable);
+int32_t tplx_gpu_result_device_validity(tplx_result *res, uint32_t col, const uint32_t **words);
 
 /* ---- multi-GPU: the one exchange step of the path ------------------------------------------- */
 /* One rank per (process, device) over NCCL (NVLink 5 / NVSwitch). Map / filter stages shard over ranks without any

@@ -309,3 +309,85 @@ def csv_write(cols, n_rows: int, delimiter=",", quotechar='"') -> bytes:
     buf = np.empty(need, dtype=np.uint8)
     L.csv_oracle_write(arr, len(cols), n_rows, delimiter.encode(), quotechar.encode(), buf.ctypes.data if need else None)
     return buf.tobytes()
+
+
+# ---- hash join (join_oracle.c) ----------------------------------------------------------------------------------------------
+class _JCol(ct.Structure):
+    _fields_ = [("type", ct.c_uint8), ("pad", ct.c_uint8 * 7), ("data", ct.c_void_p), ("offsets", ct.c_void_p), ("valid", ct.c_void_p)]
+
+
+def _jcol(col):
+    """col: object with .type, .data, .offsets and optionally .valid (uint32 words, bit set = present)."""
+    jc = _JCol()
+    keep = []
+    d = np.ascontiguousarray(col.data)
+    keep.append(d)
+    jc.type = col.type
+    jc.data = d.ctypes.data
+    if col.type == T_STR:
+        o = np.ascontiguousarray(col.offsets, dtype=np.uint32)
+        keep.append(o)
+        jc.offsets = o.ctypes.data
+    v = getattr(col, "valid", None)
+    if v is not None:
+        v = np.ascontiguousarray(v, dtype=np.uint32)
+        keep.append(v)
+        jc.valid = v.ctypes.data
+    return jc, keep
+
+
+def join_pairs(build_key, n_build: int, probe_key, n_probe: int, left_outer: bool = False):
+    """(probe rows, build rows) of the join's output in the reference's order; build row -1 = left join without a match."""
+    L = lib()
+    L.tplx_oracle_join.restype = ct.c_uint64
+    L.tplx_oracle_join.argtypes = [ct.POINTER(_JCol), ct.c_uint64, ct.POINTER(_JCol), ct.c_uint64, ct.c_int, ct.c_void_p, ct.c_void_p, ct.c_uint64]
+    b, kb = _jcol(build_key)
+    p, kp = _jcol(probe_key)
+    n = L.tplx_oracle_join(ct.byref(b), n_build, ct.byref(p), n_probe, int(left_outer), None, None, 0)
+    op = np.empty(n, np.int64)
+    ob = np.empty(n, np.int64)
+    L.tplx_oracle_join(ct.byref(b), n_build, ct.byref(p), n_probe, int(left_outer), op.ctypes.data if n else None, ob.ctypes.data if n else None, n)
+    return op, ob
+
+
+def join_rows(left_rows: Sequence[tuple], left_key: int, right_rows: Sequence[tuple], right_key: int, key_type: int, left_outer: bool = False,
+              build_right: bool = True) -> List[tuple]:
+    """The join of two lists of python tuples through the C oracle (None keys allowed): the rows the reference's collect() returns,
+    | left non-key | key | right non-key | (JoinOperator.cc:163-184), ordered by the probe side."""
+    class _K:
+        pass
+
+    def keycol(rows, k):
+        c = _K()
+        c.type = key_type
+        vals = [r[k] for r in rows]
+        valid = np.zeros((len(vals) + 31) // 32, np.uint32)
+        for i, v in enumerate(vals):
+            if v is not None:
+                valid[i >> 5] |= np.uint32(1 << (i & 31))
+        c.valid = valid if any(v is None for v in vals) else None
+        if key_type == T_STR:
+            enc = [(v or "").encode() for v in vals]
+            c.offsets = np.zeros(len(enc) + 1, np.uint32)
+            np.cumsum([len(e) for e in enc], out=c.offsets[1:])
+            c.data = np.frombuffer(b"".join(enc) + b"\0", np.uint8).copy()
+        else:
+            c.offsets = None
+            c.data = np.array([int(v or 0) for v in vals], np.int64)
+        return c
+
+    if build_right:
+        op, ob = join_pairs(keycol(right_rows, right_key), len(right_rows), keycol(left_rows, left_key), len(left_rows), left_outer)
+        li, ri = op, ob
+    else:
+        assert not left_outer
+        op, ob = join_pairs(keycol(left_rows, left_key), len(left_rows), keycol(right_rows, right_key), len(right_rows), False)
+        li, ri = ob, op
+    n_right = len(right_rows[0]) if right_rows else 0
+    out = []
+    for l, r in zip(li.tolist(), ri.tolist()):
+        lrow = left_rows[l]
+        rrow = right_rows[r] if r >= 0 else (None,) * n_right
+        key = lrow[left_key] if build_right else right_rows[r][right_key]
+        out.append(tuple(v for i, v in enumerate(lrow) if i != left_key) + (key,) + tuple(v for i, v in enumerate(rrow) if i != right_key))
+    return out

@@ -17,10 +17,10 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
   python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-pageable --no-extras --min-region-s 0 > $O/r02_launches_bench.log 2>&1
 # one full capture per flagship kernel
 export PROBE_CYCLES=${PROBE_CYCLES:-400}
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:stage_mask -s 3 -c 1 -f -o $O/r02_scan python tools/kernel_probe.py > $O/ncu_a.log 2>&1
+[ "${SKIP_OLD:-0}" = "1" ] || timeout 300 ncu --set full --clock-control none --import-source on -k regex:stage_mask -s 3 -c 1 -f -o $O/r02_scan python tools/kernel_probe.py > $O/ncu_a.log 2>&1
 # the dense launch and the C1 kernel are the stage specialiser's builds (tplx_jit_kernel) by default; TPLX_JIT=0 = their interpreting twins
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:tplx_jit_kernel -s 3 -c 1 -f -o $O/r02_dense python tools/kernel_probe.py > $O/ncu_b.log 2>&1
 PROBE_ROWS=50000000 timeout 300 ncu --set full --clock-control none --import-source on -k regex:tplx_jit_kernel -s 2 -c 1 -f -o $O/r02_vec python tools/c1_probe.py > $O/ncu_c.log 2>&1
 ls -la $O/*.ncu-rep
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:fused_scan_agg_tma -s 1 -c 1 -f -o $O/r02_q6 python bench.py --workload q6 --rows 100000000 --steps 1 --warmup 1 --no-cpu-baseline --no-pageable --min-region-s 0 > $O/ncu_d.log 2>&1
+[ "${SKIP_OLD:-0}" = "1" ] || timeout 300 ncu --set full --clock-control none --import-source on -k regex:fused_scan_agg_tma -s 1 -c 1 -f -o $O/r02_q6 python bench.py --workload q6 --rows 100000000 --steps 1 --warmup 1 --no-cpu-baseline --no-pageable --min-region-s 0 > $O/ncu_d.log 2>&1
 ls -la $O/*.ncu-rep

@@ -27,7 +27,7 @@ class GpuBackendError(RuntimeError):
 
 class CColumn(ct.Structure):
     _fields_ = [("type", ct.c_uint8), ("pad", ct.c_uint8 * 7), ("data", ct.c_void_p), ("offsets", ct.c_void_p),
-                ("data_bytes", ct.c_uint64)]
+                ("data_bytes", ct.c_uint64), ("valid", ct.c_void_p)]
 
 
 class CExceptionRec(ct.Structure):
@@ -102,6 +102,12 @@ def lib():
         "tplx_gpu_stage_hash_export_raw": ([vp, i32, P(vp)], i32),
         "tplx_gpu_stage_hash_merge": ([vp, vp], i32),
         "tplx_gpu_stage_hash_reset": ([vp, i32], i32),
+        "tplx_gpu_join_build": ([vp, u32, P(vp)], i32),
+        "tplx_gpu_join_info": ([vp, P(u64), P(u64), P(ct.c_double), P(u32)], i32),
+        "tplx_gpu_join_probe": ([vp, vp, u32, u32, P(vp)], i32),
+        "tplx_gpu_join_destroy": ([vp], i32),
+        "tplx_gpu_result_fetch_validity": ([vp, u32, vp, P(u32)], i32),
+        "tplx_gpu_result_device_validity": ([vp, u32, P(vp)], i32),
         "tplx_gpu_comm_unique_id": ([vp], i32),
         "tplx_gpu_comm_init": ([i32, i32, i32, vp], i32),
         "tplx_gpu_comm_init_local": ([P(i32), i32], i32),
@@ -187,6 +193,18 @@ def comm_destroy(device: int):
 # ------------------------------------------------------------------------------------------------
 # host column blocks
 # ------------------------------------------------------------------------------------------------
+def pack_valid(present: np.ndarray) -> np.ndarray:
+    """bool per row -> validity words (bit (r & 31) of word r >> 5)."""
+    n = len(present)
+    bits = np.zeros(((n + 31) // 32) * 32, dtype=np.uint8)
+    bits[:n] = present
+    return np.packbits(bits.reshape(-1, 32), axis=1, bitorder="little").view("<u4").reshape(-1).copy()
+
+
+def unpack_valid(words: np.ndarray, n: int) -> np.ndarray:
+    return np.unpackbits(np.ascontiguousarray(words, dtype="<u4").view(np.uint8), bitorder="little")[:n].astype(bool)
+
+
 @dataclass
 class Column:
     """One column of a column block on the host. Fixed width: `data` is an 8-byte numpy array
@@ -194,12 +212,20 @@ class Column:
     type: int
     data: np.ndarray
     offsets: Optional[np.ndarray] = None
+    valid: Optional[np.ndarray] = None  # Option[T] column: uint32 words, bit (r & 31) of word r >> 5 set = row r holds a value; None = no Nones
 
     def __len__(self):
         return len(self.offsets) - 1 if self.type == T_STR else len(self.data)
 
     @staticmethod
     def from_values(values: Sequence, t: int) -> "Column":
+        """Values of one type; None entries make the column an Option[T] column (validity bitmap, placeholder value 0 / '')."""
+        valid = None
+        if any(v is None for v in values):
+            present = np.fromiter((v is not None for v in values), dtype=bool, count=len(values))
+            valid = pack_valid(present)
+            fill = "" if t == T_STR else 0
+            values = [fill if v is None else v for v in values]
         if t == T_STR:
             enc = [v.encode("utf-8") for v in values]
             lens = np.fromiter((len(b) for b in enc), dtype=np.int64, count=len(enc))
@@ -208,10 +234,14 @@ class Column:
             if lens.sum() > 0xFFFFFFFF:
                 raise GpuBackendError("string column exceeds 4 GiB; use smaller blocks")
             data = np.frombuffer(b"".join(enc), dtype=np.uint8).copy() if enc else np.zeros(0, np.uint8)
-            return Column(T_STR, data, offsets)
+            return Column(T_STR, data, offsets, valid)
         if t == T_F64:
-            return Column(T_F64, np.asarray(values, dtype=np.float64))
-        return Column(t, np.asarray(values, dtype=np.int64))
+            return Column(T_F64, np.asarray(values, dtype=np.float64), None, valid)
+        return Column(t, np.asarray(values, dtype=np.int64), None, valid)
+
+    def present(self) -> Optional[np.ndarray]:
+        """bool per row (True = holds a value), or None for a column without Nones."""
+        return None if self.valid is None else unpack_valid(self.valid, len(self))
 
     def to_values(self) -> list:
         if self.type == T_STR:
@@ -219,22 +249,28 @@ class Column:
             o = self.offsets
             # device string ops are byte based (ASCII case mapping, byte slices): a slice may cut a multi-byte sequence. Decode like
             # csvsource._text does, so that such a cell becomes a row value instead of failing the whole collect()
-            return [raw[o[i]:o[i + 1]].decode("utf-8", "replace") for i in range(len(o) - 1)]
-        if self.type == T_BOOL:
-            return [bool(v) for v in self.data.tolist()]
-        return self.data.tolist()
+            vals = [raw[o[i]:o[i + 1]].decode("utf-8", "replace") for i in range(len(o) - 1)]
+        elif self.type == T_BOOL:
+            vals = [bool(v) for v in self.data.tolist()]
+        else:
+            vals = self.data.tolist()
+        if self.valid is not None:
+            vals = [v if ok else None for v, ok in zip(vals, self.present().tolist())]
+        return vals
 
     def slice(self, lo: int, hi: int) -> "Column":
+        valid = None if self.valid is None else pack_valid(self.present()[lo:hi])
         if self.type == T_STR:
             o = self.offsets[lo:hi + 1]
-            return Column(T_STR, self.data[int(o[0]):int(o[-1])], (o - o[0]).astype(np.uint32))
-        return Column(self.type, self.data[lo:hi])
+            return Column(T_STR, self.data[int(o[0]):int(o[-1])], (o - o[0]).astype(np.uint32), valid)
+        return Column(self.type, self.data[lo:hi], None, valid)
 
     def take(self, idx: np.ndarray) -> "Column":
         if self.type == T_STR:
             vals = self.to_values()
             return Column.from_values([vals[i] for i in idx.tolist()], T_STR)
-        return Column(self.type, self.data[idx])
+        valid = None if self.valid is None else pack_valid(self.present()[idx])
+        return Column(self.type, self.data[idx], None, valid)
 
     def nbytes(self) -> int:
         return int(self.data.nbytes + (self.offsets.nbytes if self.offsets is not None else 0))
@@ -256,6 +292,12 @@ def _ccols(cols: Sequence[Column]):
         else:
             arr[i].offsets = None
             arr[i].data_bytes = d.nbytes
+        if c.valid is not None:
+            v = np.ascontiguousarray(c.valid, dtype=np.uint32)
+            keep.append(v)
+            arr[i].valid = v.ctypes.data
+        else:
+            arr[i].valid = None
     return arr, keep
 
 
@@ -412,12 +454,13 @@ class Block:
 
 
 class Result:
-    def __init__(self, h, stage: Stage, block: Optional[Block], hash_result: bool = False):
+    def __init__(self, h, stage: Optional[Stage], block: Optional[Block], hash_result: bool = False, types: Optional[List[int]] = None):
         self._h = h
         self.stage = stage
         self.block = block  # keep the input alive for exception gather
         self._info = None
         self.hash_result = hash_result
+        self._types = types  # results that do not come from a stage (join probe): the output column types
 
     @property
     def info(self) -> CResultInfo:
@@ -428,6 +471,8 @@ class Result:
         return self._info
 
     def out_types(self) -> List[int]:
+        if self._types is not None:
+            return list(self._types)
         p = self.stage.program
         if self.hash_result:
             f = {ir.C["TPLX_ACC_SUM_F64"], ir.C["TPLX_ACC_MIN_F64"], ir.C["TPLX_ACC_MAX_F64"]}
@@ -442,11 +487,25 @@ class Result:
             data = np.empty(max(nb, 1), dtype=np.uint8)
             offsets = np.empty(n + 1, dtype=np.uint32)
             _check(lib().tplx_gpu_result_fetch_column(self._h, c, data.ctypes.data, offsets.ctypes.data), "result_fetch_column")
-            return Column(T_STR, data[:nb], offsets)
+            return Column(T_STR, data[:nb], offsets, self.validity(c))
         data = np.empty(n, dtype=np.float64 if t == T_F64 else np.int64)
         if n:
             _check(lib().tplx_gpu_result_fetch_column(self._h, c, data.ctypes.data, None), "result_fetch_column")
-        return Column(t, data)
+        return Column(t, data, None, self.validity(c))
+
+    def validity(self, c: int) -> Optional[np.ndarray]:
+        """Validity words of a nullable output column (tplx_gpu_result_fetch_validity), None for a column that cannot hold None."""
+        nullable = ct.c_uint32()
+        _check(lib().tplx_gpu_result_fetch_validity(self._h, c, None, ct.byref(nullable)), "result_fetch_validity")
+        if not nullable.value:
+            return None
+        n = int(self.info.n_out_rows)
+        words = np.zeros((n + 31) // 32, dtype=np.uint32)
+        if n:
+            _check(lib().tplx_gpu_result_fetch_validity(self._h, c, words.ctypes.data, ct.byref(nullable)), "result_fetch_validity")
+            if n & 31:
+                words[-1] &= np.uint32((1 << (n & 31)) - 1)
+        return words
 
     def columns(self) -> List[Column]:
         return [self.column(c) for c in range(len(self.out_types()))]
@@ -505,6 +564,54 @@ class Result:
     def free(self):
         if self._h:
             lib().tplx_gpu_result_free(self._h)
+            self._h = ct.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------------------------
+# hash join (K8): build once, probe block after block
+# ------------------------------------------------------------------------------------------------
+JOIN_LEFT_OUTER = ir.C["TPLX_JOIN_LEFT_OUTER"]
+JOIN_BUILD_FIRST = ir.C["TPLX_JOIN_BUILD_FIRST"]
+
+
+class Join:
+    """Device hash table over one key column of the build side (tplx_gpu_join_build); replaces the reference's build stage with a
+    hash-table endpoint (TransformTask.cc:769-842). probe() = the hash-join probe of the row pipeline (PipelineBuilder.cc:2110-2523)."""
+
+    def __init__(self, build: Block, build_types: Sequence[int], key_col: int):
+        self.build = build  # borrowed by the table: keep it alive
+        self.build_types = list(build_types)
+        self.key_col = key_col
+        self._h = ct.c_void_p()
+        _check(lib().tplx_gpu_join_build(build._h, key_col, ct.byref(self._h)), "tplx_gpu_join_build")
+
+    @property
+    def info(self):
+        n, nn, ms, kl = ct.c_uint64(), ct.c_uint64(), ct.c_double(), ct.c_uint32()
+        _check(lib().tplx_gpu_join_info(self._h, ct.byref(n), ct.byref(nn), ct.byref(ms), ct.byref(kl)), "tplx_gpu_join_info")
+        return {"n_rows": n.value, "n_null_rows": nn.value, "build_ms": ms.value, "kernel_launches": kl.value}
+
+    def out_types(self, probe_types: Sequence[int], probe_key: int, build_first: bool) -> List[int]:
+        pt = [t for i, t in enumerate(probe_types) if i != probe_key]
+        bt = [t for i, t in enumerate(self.build_types) if i != self.key_col]
+        kt = [probe_types[probe_key]]
+        return bt + kt + pt if build_first else pt + kt + bt
+
+    def probe(self, probe: Block, probe_types: Sequence[int], probe_key: int, left_outer: bool = False, build_first: bool = False) -> Result:
+        h = ct.c_void_p()
+        flags = (JOIN_LEFT_OUTER if left_outer else 0) | (JOIN_BUILD_FIRST if build_first else 0)
+        _check(lib().tplx_gpu_join_probe(self._h, probe._h, probe_key, flags, ct.byref(h)), "tplx_gpu_join_probe")
+        return Result(h, None, probe, types=self.out_types(probe_types, probe_key, build_first))
+
+    def free(self):
+        if self._h:
+            lib().tplx_gpu_join_destroy(self._h)
             self._h = ct.c_void_p()
 
     def __del__(self):

@@ -110,7 +110,10 @@ class Context:
     def _dataset_from_rows(self, rows, names) -> DataSet:
         return DataSet(self, self._source_from_rows(rows, names))
 
-    def _source_from_rows(self, rows: Sequence, names: Optional[List[Optional[str]]], infer: bool = True) -> Source:
+    def _source_from_rows(self, rows: Sequence, names: Optional[List[Optional[str]]], infer: bool = True, option: bool = False) -> Source:
+        """option: None values stay in the normal case as Option[T] columns (validity bitmap) instead of making the row a fallback
+        row — the form the hash join consumes (None keys go to the null bucket, nullable payload columns are gathered with their
+        bitmaps); row stages still take rows with None on the interpreter path."""
         n = len(rows)
         fast = self._homogeneous_source(rows, names)
         if fast is not None:
@@ -145,7 +148,7 @@ class Context:
             ok = (len(r) if isinstance(r, tuple) else -1) == arity
             if ok:
                 vals = r if arity != -1 else (r,)
-                ok = all(_kind(v) == t for v, t in zip(vals, col_types))
+                ok = all(_kind(v) == t or (option and v is None) for v, t in zip(vals, col_types))
             if ok:
                 for c, v in enumerate(vals):
                     normal_vals[c].append(v)

@@ -28,6 +28,7 @@
 #include "mask.cuh"
 #include "vecvm.cuh"
 #include "csv.cuh"
+#include "join.cuh"
 #include "jit.inl"
 
 using namespace tplx;
@@ -862,6 +863,7 @@ struct tplx_block {
     std::vector<uint8_t> mapped;       // per column: 1 = read in place from page-locked host memory (run_host);
                                        // 2 = lazy CSV column: data = CSV text, offsets = (uint64) cell references (K6)
     uint8_t csv_quote = '"';
+    std::vector<const uint32_t *> valid;  // per column: validity bitmap of an Option[T] column (bit r & 31 of word r >> 5 set = present), or nullptr
 };
 
 extern "C" int32_t tplx_gpu_block_upload(int32_t device, const tplx_column *cols, uint32_t n_cols, uint64_t n_rows,
@@ -891,6 +893,16 @@ extern "C" int32_t tplx_gpu_block_upload(int32_t device, const tplx_column *cols
         }
         b->cols.push_back(ci);
         b->data_bytes.push_back(nb);
+        const uint32_t *vd = nullptr;
+        if (cols[c].valid) {  // Option[T] column (Serializer.cc:1041-1059 keeps the same information as a per-row bitmap)
+            void *vp = nullptr;
+            const size_t vb = (n_rows + 31) / 32 * 4;
+            CU(cudaMallocAsync(&vp, vb + 16, d->copy_stream));
+            b->owned.push_back(vp);
+            if (vb) CU(cudaMemcpyAsync(vp, cols[c].valid, vb, cudaMemcpyHostToDevice, d->copy_stream));
+            vd = static_cast<const uint32_t *>(vp);
+        }
+        b->valid.push_back(vd);
     }
     CU(cudaEventCreateWithFlags(&b->ready, cudaEventDisableTiming));
     CU(cudaEventRecord(b->ready, d->copy_stream));
@@ -913,6 +925,7 @@ extern "C" int32_t tplx_gpu_block_wrap_device(int32_t device, const tplx_column 
         ci.offsets = cols[c].offsets;
         b->cols.push_back(ci);
         b->data_bytes.push_back(cols[c].type == TPLX_T_STR ? cols[c].data_bytes : n_rows * 8);
+        b->valid.push_back(cols[c].valid);
     }
     *out = b;
     return TPLX_OK;
@@ -952,6 +965,7 @@ struct tplx_result {
     std::vector<OutCol> out;
     std::vector<uint8_t> out_types;
     std::vector<uint64_t> str_bytes;
+    std::vector<uint32_t *> out_valid;  // per output column: validity bitmap of a nullable column, or nullptr (may be shorter than out)
     tplx_exception_rec *exc = nullptr;
     uint64_t *agg_out = nullptr;
     uint32_t n_accs = 0;
@@ -2301,3 +2315,4 @@ extern "C" int32_t tplx_gpu_result_fetch_aggregate(tplx_result *r, int64_t *acc_
 #include "tplx_gpu_hash.inl"
 #include "tplx_gpu_csv.inl"
 #include "tplx_gpu_comm.inl"
+#include "tplx_gpu_join.inl"

@@ -48,17 +48,90 @@ class Source:
         self.total_rows = total_rows
 
 
+class JoinSpec:
+    """A JoinOperator of the logical plan (tuplex/core/src/logical/JoinOperator.cc): two upstream datasets, the key column on each
+    side, inner or left, and the prefixes / suffixes applied to the column names of each side."""
+
+    def __init__(self, left: "DataSet", right: "DataSet", left_col: str, right_col: str, kind: str, left_prefix: str, left_suffix: str,
+                 right_prefix: str, right_suffix: str):
+        self.left, self.right = left, right
+        self.left_col, self.right_col = left_col, right_col
+        self.kind = kind  # "inner" | "left"
+        self.left_prefix, self.left_suffix = left_prefix, left_suffix
+        self.right_prefix, self.right_suffix = right_prefix, right_suffix
+
+    def key_indices(self, lnames, rnames):
+        if self.left_col not in lnames:
+            raise ValueError(f"column '{self.left_col}' not found in left dataset for join.")  # JoinOperator.cc:99-102
+        if self.right_col not in rnames:
+            raise ValueError(f"column '{self.right_col}' not found in right dataset for join.")
+        return lnames.index(self.left_col), rnames.index(self.right_col)
+
+    def names(self, lnames, rnames):
+        """| left columns except the key | key (left name) | right columns except the key |  (JoinOperator.cc:163-184)"""
+        li, ri = self.key_indices(lnames, rnames)
+        deco = lambda n, p, s: None if n is None else p + n + s  # noqa: E731
+        return ([deco(n, self.left_prefix, self.left_suffix) for i, n in enumerate(lnames) if i != li] +
+                [deco(lnames[li], self.left_prefix, self.left_suffix)] +
+                [deco(n, self.right_prefix, self.right_suffix) for i, n in enumerate(rnames) if i != ri])
+
+    def build_right(self) -> bool:
+        """JoinOperator::buildRight (core/include/logical/JoinOperator.h:62-69): a left join always builds on the right side,
+        an inner join on the side with the smaller cost."""
+        return self.kind == "left" or self.left._cost() >= self.right._cost()
+
+
 class DataSet:
-    def __init__(self, ctx, source: Optional[Source], ops: Sequence[Op] = (), parent: Optional["DataSet"] = None):
+    def __init__(self, ctx, source: Optional[Source], ops: Sequence[Op] = (), parent: Optional["DataSet"] = None,
+                 join: Optional[JoinSpec] = None):
         self._ctx = ctx
         self._source = source
         self._ops: List[Op] = list(ops)
         self._parent = parent  # upstream DataSet whose result is this one's source (after an aggregate)
+        self._join = join      # this dataset's source is the join of two upstream datasets
         self._last_exceptions: Counter = Counter()
 
     # ---- lazy operators ---------------------------------------------------------------------------
     def _with(self, op: Op) -> "DataSet":
-        return DataSet(self._ctx, self._source, self._ops + [op], self._parent)
+        return DataSet(self._ctx, self._source, self._ops + [op], self._parent, self._join)
+
+    def join(self, dsRight: "DataSet", leftKeyColumn: str, rightKeyColumn: str, prefixes=None, suffixes=None) -> "DataSet":
+        """(inner) join with another dataset on one key column per side (python/tuplex/dataset.py:384-440)."""
+        return self._make_join(dsRight, leftKeyColumn, rightKeyColumn, prefixes, suffixes, "inner")
+
+    def leftJoin(self, dsRight: "DataSet", leftKeyColumn: str, rightKeyColumn: str, prefixes=None, suffixes=None) -> "DataSet":
+        """left (outer) join: rows of this dataset without a partner keep None in the right columns (python/tuplex/dataset.py:442-498)."""
+        return self._make_join(dsRight, leftKeyColumn, rightKeyColumn, prefixes, suffixes, "left")
+
+    def _make_join(self, dsRight, leftKeyColumn, rightKeyColumn, prefixes, suffixes, kind):
+        if not isinstance(dsRight, DataSet):
+            raise TypeError("dsRight must be a DataSet")
+        lp = ls = rp = rs = ""
+        if prefixes:
+            prefixes = tuple(prefixes)
+            assert len(prefixes) == 2, "prefixes must be a sequence of 2 elements!"
+            lp, rp = prefixes[0] or "", prefixes[1] or ""
+        if suffixes:
+            suffixes = tuple(suffixes)
+            assert len(suffixes) == 2, "suffixes must be a sequence of 2 elements!"
+            ls, rs = suffixes[0] or "", suffixes[1] or ""
+        spec = JoinSpec(self, dsRight, leftKeyColumn, rightKeyColumn, kind, lp, ls, rp, rs)
+        spec.names(self._plan_names()[1], dsRight._plan_names()[1])  # unknown key columns are reported when the join is declared
+        return DataSet(self._ctx, None, [], None, spec)
+
+    def _cost(self) -> int:
+        """LogicalOperator::cost (core/include/logical/LogicalOperator.h:197-204): sources report their row count
+        (ParallelizeOperator.cc:121-129, FileInputOperator.cc:533-536), every other operator the sum over its parents."""
+        if self._join is not None:
+            return self._join.left._cost() + self._join.right._cost()
+        if self._parent is not None:
+            return self._parent._cost()
+        src = self._source
+        if src is None:
+            return 0
+        if hasattr(src, "chunks"):  # CSV source: data rows = line ends of the files (the reference estimates from a sample)
+            return int(sum(int(np.count_nonzero(a == 10)) for a in getattr(src, "files", [])))
+        return int(src.total_rows)
 
     def map(self, ftor):
         return self._with(Op("map", ftor))
@@ -83,7 +156,7 @@ class DataSet:
     def resolve(self, eclass, ftor):
         if not self._ops:
             raise ValueError("resolve() needs a preceding operator")
-        ds = DataSet(self._ctx, self._source, self._ops, self._parent)
+        ds = DataSet(self._ctx, self._source, self._ops, self._parent, self._join)
         ds._ops[-1] = _clone_op(ds._ops[-1])  # the parent DataSet (and its other branches) keep the operator without this resolver
         ds._ops[-1].resolvers.append((eclass, ftor))
         return ds
@@ -91,7 +164,7 @@ class DataSet:
     def ignore(self, eclass):
         if not self._ops:
             raise ValueError("ignore() needs a preceding operator")
-        ds = DataSet(self._ctx, self._source, self._ops, self._parent)
+        ds = DataSet(self._ctx, self._source, self._ops, self._parent, self._join)
         ds._ops[-1] = _clone_op(ds._ops[-1])
         ds._ops[-1].ignores.append(eclass)
         return ds
@@ -164,7 +237,9 @@ class DataSet:
     def _plan_names(self):
         """Column names from the logical plan alone (the reference derives them without executing,
         python/tuplex/dataset.py:720-735): operators are replayed over names only."""
-        if self._parent is not None:
+        if self._join is not None:
+            names = self._join.names(self._join.left._plan_names()[1], self._join.right._plan_names()[1])
+        elif self._parent is not None:
             _, names = self._parent._plan_names()
             names = list(names)
         else:
@@ -218,7 +293,13 @@ class DataSet:
     def _execute(self, dry: bool = False, sink: Optional[str] = None):
         """Split the operator chain into stages and run them. Returns (python rows, column names)."""
         src = self._source
-        if self._parent is not None:
+        self._last_exceptions = Counter()
+        if self._join is not None:
+            rows, names = _run_join(self._ctx, self._join, self._last_exceptions)
+            if not self._ops:
+                return rows, names
+            src = self._ctx._source_from_rows(rows, names)
+        elif self._parent is not None:
             rows, names = self._parent._execute()
             src = self._ctx._source_from_rows(rows, names)
         stages: List[List[Op]] = [[]]
@@ -229,7 +310,6 @@ class DataSet:
         if not stages[-1] and len(stages) > 1:
             stages.pop()
         rows = names = None
-        self._last_exceptions = Counter()
         for si, ops in enumerate(stages):
             if si > 0:
                 src = self._ctx._source_from_rows(rows, names)
@@ -289,6 +369,207 @@ def _csv_cell(v, null_value=None) -> str:
 def _row_of(cols: List[Column], values_cache: List[list], i: int):
     vals = tuple(values_cache[c][i] for c in range(len(cols)))
     return vals if len(vals) != 1 else vals[0]
+
+
+def _rows_as_tuples(rows):
+    return [r if isinstance(r, tuple) else (r,) for r in rows]
+
+
+def _run_join(ctx, spec: JoinSpec, exc_counter: Counter):
+    """A JoinOperator between two executed datasets: HashJoinStage of the reference (core/src/physical/HashJoinStage.cc; build stage
+    with a hash-table endpoint + probe inside the other side's pipeline, PipelineBuilder.cc:2110-2523) on the GPU (K8,
+    tplx_gpu_join_build / tplx_gpu_join_probe). Rows outside the normal case of either side (fallback rows) are joined on the
+    interpreter path and merged by (probe row, build row), which is the order the normal case produces."""
+    lrows, lnames = spec.left._execute()
+    rrows, rnames = spec.right._execute()
+    exc_counter.update(spec.left._last_exceptions)
+    exc_counter.update(spec.right._last_exceptions)
+    lnames = list(lnames) if lnames else []
+    rnames = list(rnames) if rnames else []
+    li, ri = spec.key_indices(lnames, rnames)
+    names = spec.names(lnames, rnames)
+    build_right = spec.build_right()
+    left_outer = spec.kind == "left"
+    lsrc = ctx._source_from_rows(lrows, lnames, option=True)
+    rsrc = ctx._source_from_rows(rrows, rnames, option=True)
+    n_left_cols, n_right_cols = len(lnames), len(rnames)
+
+    def python_join():
+        """Interpreter path of the whole join (key types the device does not hash, empty sides)."""
+        L, R = _rows_as_tuples(lrows), _rows_as_tuples(rrows)
+        return _py_join_pairs(L, li, R, ri, left_outer, build_right, n_right_cols), names
+
+    if not lrows or not rrows or len(lsrc.cols) != n_left_cols or len(rsrc.cols) != n_right_cols:
+        return python_join()
+    lk, rk = lsrc.cols[li], rsrc.cols[ri]
+    if lk.type != rk.type:  # a side whose keys are all None takes the other side's key type (NULLVALUE vs Option[T], JoinOperator.cc:121-131)
+        if rk.valid is not None and not rk.present().any():
+            rsrc.cols[ri] = rk = Column.from_values([None] * len(rk), lk.type)
+        elif lk.valid is not None and not lk.present().any():
+            lsrc.cols[li] = lk = Column.from_values([None] * len(lk), rk.type)
+        else:
+            raise TypeError(f"can't perform join, left column '{spec.left_col}' type {ir.TYPE_NAMES[lk.type]} is not the same as right column "
+                            f"'{spec.right_col}' type {ir.TYPE_NAMES[rk.type]}")
+    if lk.type == T_F64 or len(names) > C["TPLX_MAX_COLS"] - 2:
+        return python_join()
+
+    need_idx = bool(lsrc.fallback or rsrc.fallback)
+    lcols, rcols = list(lsrc.cols), list(rsrc.cols)
+    if need_idx:  # original row numbers travel as one more payload column per side: the merge below orders by them
+        lcols.append(Column(T_I64, lsrc.orig_index if lsrc.orig_index is not None else np.arange(lsrc.n_rows, dtype=np.int64)))
+        rcols.append(Column(T_I64, rsrc.orig_index if rsrc.orig_index is not None else np.arange(rsrc.n_rows, dtype=np.int64)))
+    probe_cols, build_cols, pk, bk = (lcols, rcols, li, ri) if build_right else (rcols, lcols, ri, li)
+    n_probe, n_build = (lsrc.n_rows, rsrc.n_rows) if build_right else (rsrc.n_rows, lsrc.n_rows)
+    devs = list(getattr(ctx, "_devices", [ctx._device])) or [ctx._device]
+    block_rows = ctx._block_rows
+    blocks = [(lo, min(n_probe, lo + block_rows)) for lo in range(0, n_probe, block_rows)] or [(0, 0)]
+    if len(set(devs)) != len(devs) or len(blocks) < 2:
+        devs = devs[:1]
+    backend.init(sorted(set(devs)))
+    from .dist import shard_range
+    import threading
+    mlock = threading.Lock()
+
+    def run_shard(k: int):
+        """One task per device: the table is built once per device (broadcast of the small side), the device's contiguous run of
+        probe blocks goes through it in order; no exchange between devices."""
+        dev = devs[k]
+        bb = backend.Block.upload(dev, build_cols, n_build)
+        jn = backend.Join(bb, [c.type for c in build_cols], bk)
+        outs = []
+        blo, bhi = shard_range(len(blocks), k, len(devs))
+        for lo, hi in blocks[blo:bhi]:
+            cols = [c.slice(lo, hi) for c in probe_cols] if (lo, hi) != (0, n_probe) else probe_cols
+            pb = backend.Block.upload(dev, cols, hi - lo)
+            res = jn.probe(pb, [c.type for c in probe_cols], pk, left_outer=left_outer, build_first=not build_right)
+            info = res.info
+            with mlock:
+                ctx.metrics._add(info)
+                ctx.metrics.join_probe_rows = getattr(ctx.metrics, "join_probe_rows", 0) + (hi - lo)
+            outs.append(res.columns())
+            res.free()
+            pb.free()
+        with mlock:
+            ctx.metrics.join_build_ms = getattr(ctx.metrics, "join_build_ms", 0.0) + jn.info["build_ms"]
+        jn.free()
+        bb.free()
+        return outs
+
+    if len(devs) == 1:
+        shard_outs = [run_shard(0)]
+    else:
+        shard_outs: List[Any] = [None] * len(devs)
+        errs: List[BaseException] = []
+
+        def work(k):
+            try:
+                shard_outs[k] = run_shard(k)
+            except BaseException as e:  # noqa: BLE001
+                errs.append(e)
+        ths = [threading.Thread(target=work, args=(k,)) for k in range(len(devs))]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        if errs:
+            raise errs[0]
+    col_vals: Optional[List[list]] = None
+    for outs in shard_outs:
+        for oc in outs:
+            vals = [c.to_values() for c in oc]
+            if col_vals is None:
+                col_vals = vals
+            else:
+                for a, b in zip(col_vals, vals):
+                    a.extend(b)
+    col_vals = col_vals or []
+    n_out = len(col_vals[0]) if col_vals else 0
+    if not need_idx:
+        rows = list(zip(*col_vals)) if len(col_vals) > 1 else list(col_vals[0]) if col_vals else []
+        return rows, names
+    # ---- interpreter path for the fallback rows of either side, merged in (probe row, build row) order ----
+    # device layout with the index columns: first side's non-key columns (its index last), key, second side's non-key columns (index last)
+    n_first = (n_left_cols if build_right else n_left_cols)  # left columns always come first
+    left_idx_pos = n_first - 1                    # left non-key columns are n_left_cols - 1 payloads + the index column
+    right_idx_pos = len(col_vals) - 1
+    lidx, ridx = col_vals[left_idx_pos], col_vals[right_idx_pos]
+    keep = [i for i in range(len(col_vals)) if i not in (left_idx_pos, right_idx_pos)]
+    gpu_rows = [tuple(col_vals[c][i] for c in keep) for i in range(n_out)]
+    L, R = _rows_as_tuples(lrows), _rows_as_tuples(rrows)
+    lfall = {i for i, _ in lsrc.fallback}
+    rfall = {i for i, _ in rsrc.fallback}
+    extra = _py_join_index_pairs(L, li, R, ri, lfall, rfall)
+    merged = {}
+    for row, l, r in zip(gpu_rows, lidx, ridx):
+        merged[(l, -1 if r is None else r)] = row
+    for l, r in extra:
+        merged[(l, r)] = _join_row(L[l], li, R[r], ri, n_right_cols)
+    if left_outer:  # a left row is emitted with None only when nothing matched it on either path
+        matched = {l for (l, r) in merged if r >= 0}
+        for key in [k for k in merged if k[1] < 0 and k[0] in matched]:
+            del merged[key]
+        for l in lfall - matched:
+            if len(L[l]) > li:
+                merged[(l, -1)] = _join_row(L[l], li, None, ri, n_right_cols)
+    order = sorted(merged, key=(lambda k: (k[0], k[1])) if build_right else (lambda k: (k[1], k[0])))
+    rows = [merged[k] for k in order]
+    if len(names) == 1:
+        rows = [r[0] for r in rows]
+    return rows, names
+
+
+def _join_row(lrow, li, rrow, ri, n_right_cols):
+    rr = rrow if rrow is not None else (None,) * n_right_cols
+    return tuple(v for i, v in enumerate(lrow) if i != li) + (lrow[li],) + tuple(v for i, v in enumerate(rr) if i != ri)
+
+
+def _key_of(v):
+    return (type(v).__name__, v)  # 1, 1.0 and True are different keys (the reference joins equal TYPES only)
+
+
+def _py_join_index_pairs(L, li, R, ri, lfall, rfall):
+    """(left row, right row) pairs in which at least one side is a fallback row."""
+    pairs = []
+    if lfall:
+        table: Dict[Any, List[int]] = {}
+        for j, r in enumerate(R):
+            if len(r) > ri:
+                table.setdefault(_key_of(r[ri]), []).append(j)
+        for l in sorted(lfall):
+            if len(L[l]) > li:
+                pairs += [(l, j) for j in table.get(_key_of(L[l][li]), [])]
+    if rfall:
+        table = {}
+        for j in sorted(rfall):
+            if len(R[j]) > ri:
+                table.setdefault(_key_of(R[j][ri]), []).append(j)
+        for l, row in enumerate(L):
+            if l not in lfall and len(row) > li:
+                pairs += [(l, j) for j in table.get(_key_of(row[li]), [])]
+    return pairs
+
+
+def _py_join_pairs(L, li, R, ri, left_outer, build_right, n_right_cols):
+    """The whole join on the interpreter path (same order rules as the device path)."""
+    out = []
+    if build_right:
+        table: Dict[Any, List[int]] = {}
+        for j, r in enumerate(R):
+            table.setdefault(_key_of(r[ri]), []).append(j)
+        for l in L:
+            ms = table.get(_key_of(l[li]), [])
+            out += [_join_row(l, li, R[j], ri, n_right_cols) for j in ms]
+            if not ms and left_outer:
+                out.append(_join_row(l, li, None, ri, n_right_cols))
+    else:
+        table = {}
+        for i, l in enumerate(L):
+            table.setdefault(_key_of(l[li]), []).append(i)
+        for r in R:
+            out += [_join_row(L[i], li, r, ri, n_right_cols) for i in table.get(_key_of(r[ri]), [])]
+    if out and len(out[0]) == 1:
+        out = [r[0] for r in out]
+    return out
 
 
 def _run_stage(ctx, src: Source, ops: List[Op], exc_counter: Counter, csv_sink: Optional[list] = None):

@@ -26,7 +26,7 @@ def _parse_header(path: str) -> Dict[str, int]:
 
 
 C = _parse_header(_HDR)
-C.update({k: v for k, v in _parse_header(os.path.join(os.path.dirname(_HDR), "tplx_gpu.h")).items() if k == "TPLX_COMM_ID_BYTES"})
+C.update({k: v for k, v in _parse_header(os.path.join(os.path.dirname(_HDR), "tplx_gpu.h")).items() if k == "TPLX_COMM_ID_BYTES" or k.startswith("TPLX_JOIN_")})
 globals().update(C)  # TPLX_OP_*, TPLX_T_*, ... become module attributes
 
 T_I64, T_F64, T_BOOL, T_STR = C["TPLX_T_I64"], C["TPLX_T_F64"], C["TPLX_T_BOOL"], C["TPLX_T_STR"]
