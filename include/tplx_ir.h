@@ -24,11 +24,15 @@ extern "C" {
 #endif
 
 #define TPLX_IR_MAGIC 0x58504C54u /* "TPLX" */
-#define TPLX_IR_VERSION 7u
+#define TPLX_IR_VERSION 8u
 #define TPLX_NOSLOT 0xFFFFu
 #define TPLX_MAX_COLS 64
 #define TPLX_MAX_ACCS 16
 #define TPLX_MAX_KEYS 8
+/* in_types entry of an "is None" companion input column: TPLX_T_NULLOF | c says "bool column, 1 where Option[T] input column c
+ * holds None" (c < TPLX_MAX_COLS). Companions follow the physical columns; the executor fills them from column c's validity
+ * bitmap (tplx_column.valid), the caller passes only the physical columns. To the op program a companion is a TPLX_T_BOOL column. */
+#define TPLX_T_NULLOF 0x80u
 
 /* column / value types (python::Type subset on the normal-case path, utils/include/TypeSystem.h) */
 enum tplx_type {
@@ -194,9 +198,10 @@ typedef struct tplx_instr {
 } tplx_instr;
 
 typedef struct tplx_outcol {
-    uint16_t slot; /* value slot at program end */
-    uint8_t type;  /* tplx_type */
-    uint8_t pad;
+    uint16_t slot;   /* value slot at program end */
+    uint8_t type;    /* tplx_type */
+    uint8_t null_of; /* 0, or 1 + k: this (hidden, TPLX_T_BOOL) column is 1 where output column k — an Option[T] column — holds None;
+                        the executor turns it into column k's validity bitmap (tplx_gpu_result_fetch_validity) */
 } tplx_outcol;
 
 typedef struct tplx_acc {

@@ -602,6 +602,10 @@ int tplx_oracle_run(const void *desc, uint64_t desc_bytes, const tplx_ocol *cols
     res->n_accs = na;
     const int is_hash = S.h.endpoint == TPLX_EP_HASH;
     res->n_cols = is_hash ? S.h.n_keys + na : (uint64_t)(S.h.n_out_cols - S.h.hidden_out_cols);
+    /* Option[T] outputs: the hidden `is None` companions (tplx_outcol.null_of) sit right behind the visible columns and are
+     * reported too, so that a test can fold them back into None values */
+    if (!is_hash)
+        for (uint64_t c = res->n_cols; c < S.h.n_out_cols && S.out_cols[c].null_of; ++c) res->n_cols = c + 1;
     for (uint64_t c = 0; c < S.h.n_out_cols && c < res->n_cols; ++c) res->col_types[c] = S.out_cols[c].type;
     if (is_hash)
         for (uint32_t k = 0; k < na; ++k) {

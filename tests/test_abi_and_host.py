@@ -72,10 +72,14 @@ def test_frontend_lowering_shapes():
 
 
 def test_parallelize_majority_type_and_fallback_rows():
-    ctx = Context()
+    ctx = Context({"tuplex.gpu.optionColumns": False})  # rows with None leave the normal case
     src = ctx._source_from_rows([1, 2, None, 4], None)
     assert [c.type for c in src.cols] == [T_I64] and src.n_rows == 3
     assert src.fallback == [(2, None)] and src.orig_index.tolist() == [0, 1, 3]
+    ctx = Context()  # default: None stays in the normal case, the column becomes Option[i64] (validity bitmap)
+    src = ctx._source_from_rows([1, 2, None, 4], None)
+    assert [c.type for c in src.cols] == [T_I64] and src.n_rows == 4 and not src.fallback
+    assert src.cols[0].valid.tolist() == [0b1011] and src.cols[0].to_values() == [1, 2, None, 4]
     src = ctx._source_from_rows([(1, "a"), (2, "b"), (3.5, "c"), ("x", "d")], ["n", "s"])
     assert [c.type for c in src.cols] == [T_I64, T_STR] and src.n_rows == 2 and len(src.fallback) == 2
 

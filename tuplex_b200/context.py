@@ -28,6 +28,9 @@ _DEFAULTS = {
     "tuplex.optimizer.mergeExceptionsInOrder": "true",
     "tuplex.gpu.devices": "0",
     "tuplex.gpu.blockRows": str(16 << 20),
+    # None values stay in the normal case as Option[T] columns (validity bitmaps; the device code tests the flag like the
+    # reference's null-aware normal case, StageBuilder.cc:644-672); false: rows holding None take the interpreter path
+    "tuplex.gpu.optionColumns": "true",
     "tuplex.webui.enable": "false",
 }
 
@@ -110,10 +113,12 @@ class Context:
     def _dataset_from_rows(self, rows, names) -> DataSet:
         return DataSet(self, self._source_from_rows(rows, names))
 
-    def _source_from_rows(self, rows: Sequence, names: Optional[List[Optional[str]]], infer: bool = True, option: bool = False) -> Source:
+    def _source_from_rows(self, rows: Sequence, names: Optional[List[Optional[str]]], infer: bool = True, option: Optional[bool] = None) -> Source:
         """option: None values stay in the normal case as Option[T] columns (validity bitmap) instead of making the row a fallback
         row — the form the hash join consumes (None keys go to the null bucket, nullable payload columns are gathered with their
         bitmaps); row stages still take rows with None on the interpreter path."""
+        if option is None:
+            option = self._options.get("tuplex.gpu.optionColumns", "true") == "true"
         n = len(rows)
         fast = self._homogeneous_source(rows, names)
         if fast is not None:

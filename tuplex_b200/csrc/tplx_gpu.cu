@@ -29,6 +29,7 @@
 #include "vecvm.cuh"
 #include "csv.cuh"
 #include "join.cuh"
+#include "option.cuh"
 #include "jit.inl"
 
 using namespace tplx;
@@ -418,7 +419,9 @@ struct StageDev {
 
 struct tplx_stage {
     tplx_stage_header hdr{};
-    std::vector<uint8_t> in_types;
+    std::vector<uint8_t> in_types;    // per input column of the program; "is None" companions appear as TPLX_T_BOOL
+    std::vector<int32_t> in_null_of;  // per input column: -1, or the Option[T] column this one is the companion of
+    uint32_t n_companions = 0;        // trailing companion columns (the caller's blocks hold in_types.size() - n_companions columns)
     std::vector<tplx_outcol> out_cols;
     std::vector<tplx_acc> accs;
     std::vector<int64_t> opids;
@@ -471,6 +474,18 @@ extern "C" int32_t tplx_gpu_stage_create(const void *desc, uint64_t desc_bytes, 
     size_t n = align_up(h.n_in_cols, 8);
     if (!need(n)) return bad("stage descriptor truncated (in_types)");
     s->in_types.assign(p + off, p + off + h.n_in_cols);
+    s->in_null_of.assign(h.n_in_cols, -1);
+    for (uint32_t c = 0; c < h.n_in_cols; ++c)
+        if (s->in_types[c] & TPLX_T_NULLOF) {  // "is None" companion of an Option[T] column: a bool column the executor fills
+            s->in_null_of[c] = s->in_types[c] & 0x7F;
+            s->in_types[c] = TPLX_T_BOOL;
+            ++s->n_companions;
+        }
+    for (uint32_t c = 0; c < h.n_in_cols; ++c) {
+        const bool comp = s->in_null_of[c] >= 0;
+        if (comp != (c >= h.n_in_cols - s->n_companions) || (comp && (uint32_t)s->in_null_of[c] >= h.n_in_cols - s->n_companions))
+            return bad("stage descriptor: companion columns must follow the physical columns and name one of them");
+    }
     off += n;
     n = align_up(h.n_out_cols * sizeof(tplx_outcol), 8);
     if (!need(n)) return bad("stage descriptor truncated (out_cols)");
@@ -539,6 +554,12 @@ extern "C" int32_t tplx_gpu_stage_create(const void *desc, uint64_t desc_bytes, 
         if (in.op == TPLX_OP_LDS) s->has_str = true;
     }
     if (h.hidden_out_cols > h.n_out_cols) return bad("stage descriptor: hidden_out_cols out of range");
+    for (uint32_t k = 0; k < h.n_out_cols; ++k) {
+        const tplx_outcol &oc = s->out_cols[k];
+        if (!oc.null_of) continue;
+        if (h.endpoint != TPLX_EP_MEMORY || oc.type != TPLX_T_BOOL || k < h.n_out_cols - h.hidden_out_cols || oc.null_of > h.n_out_cols - h.hidden_out_cols)
+            return bad("stage descriptor: an `is None` companion must be a hidden bool column of a visible output column");
+    }
     s->hidden = h.hidden_out_cols;
     if (h.prefilter_bytes) {
         if (!need(h.prefilter_bytes) || h.endpoint != TPLX_EP_MEMORY) return bad("stage descriptor: bad prefilter section");
@@ -980,6 +1001,7 @@ struct tplx_result {
     uint32_t jit_launches = 0;  // of those: kernels produced by the stage specialiser
     bool owns_block = false;
     tplx_block *owned_block = nullptr;
+    tplx_block *expanded_block = nullptr;  // the input block plus the `is None` companions of its Option[T] columns (tplx_gpu_stage_run)
     // mask stage temporaries (run_mask), needed when the exception records have to be expanded again with the exact capacity
     uint32_t *mask_keep = nullptr, *mask_exc = nullptr, *mask_codes = nullptr, mask_words = 0;
     uint64_t *mask_part = nullptr;
@@ -994,6 +1016,7 @@ extern "C" int32_t tplx_gpu_result_free(tplx_result *r) {
     if (r->evk0) cudaEventDestroy(r->evk0);
     if (r->evk1) cudaEventDestroy(r->evk1);
     for (auto &e : r->extra_ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    if (r->expanded_block) tplx_gpu_block_free(r->expanded_block);
     if (r->owned_block) tplx_gpu_block_free(r->owned_block);
     delete r;
     return TPLX_OK;
@@ -1062,7 +1085,78 @@ static int32_t run_mask(tplx_stage *ps, StageDev *psd, const tplx_block *b, tplx
 static int32_t run_agg(tplx_stage *s, StageDev *sd, const tplx_block *b, tplx_result *r);
 static int32_t run_hash(tplx_stage *s, StageDev *sd, const tplx_block *b, tplx_result *r);
 
+static int32_t stage_run_impl(tplx_stage *s, const tplx_block *b, int64_t first_row_no, tplx_result **out);
+template <typename T>
+static int32_t dalloc(tplx_result *r, T **p, size_t count);
+
+// Option[T] columns on the way in and out of a stage (option.cuh): companions of the input columns are expanded from the block's
+// validity bitmaps, companions of the output columns are packed into the result's validity bitmaps.
 extern "C" int32_t tplx_gpu_stage_run(tplx_stage *s, const tplx_block *b, int64_t first_row_no, tplx_result **out) {
+    if (!s || !b || !out) return fail(TPLX_E_BADARG, "stage_run: bad arguments");
+    tplx_block *x = nullptr;
+    if (s->n_companions && b->cols.size() + s->n_companions == s->in_types.size()) {
+        for (uint8_t m : b->mapped)
+            if (m) return fail(TPLX_E_UNSUPPORTED, "stage_run: a stage with Option[T] inputs needs device-resident block columns");
+        Device *d = b->dev;
+        CU(cudaSetDevice(d->id));
+        x = new tplx_block();
+        x->dev = d;
+        x->n_rows = b->n_rows;
+        x->cols = b->cols;
+        x->data_bytes = b->data_bytes;
+        x->valid = b->valid;
+        x->csv_quote = b->csv_quote;
+        if (b->ready) CU(cudaStreamWaitEvent(d->copy_stream, b->ready, 0));
+        const uint64_t n = b->n_rows;
+        for (size_t j = b->cols.size(); j < s->in_types.size(); ++j) {
+            const uint32_t c = (uint32_t)s->in_null_of[j];
+            void *buf = nullptr;
+            CU(cudaMallocAsync(&buf, n * 8 + 16, d->copy_stream));
+            x->owned.push_back(buf);
+            const uint32_t *v = c < b->valid.size() ? b->valid[c] : nullptr;
+            if (v && n) valid_expand_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, d->copy_stream>>>(v, n, static_cast<uint64_t *>(buf));
+            else CU(cudaMemsetAsync(buf, 0, n * 8 + 16, d->copy_stream));  // a column without a bitmap holds no None
+            ColIn ci{};
+            ci.type = TPLX_T_BOOL;
+            ci.data = buf;
+            x->cols.push_back(ci);
+            x->data_bytes.push_back(n * 8);
+            x->valid.push_back(nullptr);
+        }
+        CU(cudaGetLastError());
+        CU(cudaEventCreateWithFlags(&x->ready, cudaEventDisableTiming));
+        CU(cudaEventRecord(x->ready, d->copy_stream));
+    }
+    int32_t rc = stage_run_impl(s, x ? x : b, first_row_no, out);
+    if (rc) {
+        if (x) tplx_gpu_block_free(x);
+        return rc;
+    }
+    tplx_result *r = *out;
+    if (x) r->expanded_block = x;  // the expanded block lives as long as the result (exception rows are gathered from it)
+    bool any = false;
+    for (const tplx_outcol &oc : s->out_cols) any = any || oc.null_of;
+    if (any && s->hdr.endpoint == TPLX_EP_MEMORY) {
+        Device *d = r->dev;
+        CU(cudaSetDevice(d->id));
+        r->out_valid.assign(r->out.size(), nullptr);
+        for (size_t k = 0; k < s->out_cols.size() && k < r->out.size(); ++k) {
+            if (!s->out_cols[k].null_of) continue;
+            uint32_t *w = nullptr;
+            int32_t rc2 = dalloc(r, &w, (r->n_out + 31) / 32 + 1);
+            if (rc2) return rc2;
+            if (r->n_out) valid_pack_kernel<<<(uint32_t)((r->n_out + 255) / 256), 256, 0, d->stream>>>(r->out[k].data, r->n_out, w);
+            r->out_valid[s->out_cols[k].null_of - 1] = w;
+            r->launches += 1;
+        }
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(r->ev1, d->stream));
+        CU(cudaStreamSynchronize(d->stream));
+    }
+    return TPLX_OK;
+}
+
+static int32_t stage_run_impl(tplx_stage *s, const tplx_block *b, int64_t first_row_no, tplx_result **out) {
     if (!s || !b || !out) return fail(TPLX_E_BADARG, "stage_run: bad arguments");
     if (b->cols.size() != s->in_types.size()) return fail(TPLX_E_BADARG, "stage_run: block column count != stage input schema");
     for (size_t c = 0; c < b->cols.size(); ++c)
@@ -1143,7 +1237,7 @@ extern "C" int32_t tplx_gpu_stage_run_host(tplx_stage *s, int32_t device, const 
     int32_t rc = TPLX_OK;
     uint64_t h2d = 0;
     uint32_t zc = 0;
-    if (s && s->prefilter && s->prefilter_enabled && s->hdr.endpoint == TPLX_EP_MEMORY && cols && n_cols == s->in_types.size()) {
+    if (s && s->prefilter && s->prefilter_enabled && s->hdr.endpoint == TPLX_EP_MEMORY && cols && n_cols == s->in_types.size() && !s->n_companions) {
         // Late materialisation across PCIe: only the columns the prefilter reads are copied to HBM. The other
         // columns are needed for surviving rows only; when they lie in page-locked host memory the dense launch
         // reads exactly those rows through the mapped address (zero-copy), otherwise they are copied like before.

@@ -268,7 +268,7 @@ class DataSet:
         fall back to reading the UDF's return expression."""
         if self._parent is None and self._source is not None and len(self._source.cols) == len(names):
             try:
-                sc = StageCompiler([c.type for c in self._source.cols], self._source.names)
+                sc = StageCompiler([c.type for c in self._source.cols], self._source.names, _option_cols(self._source.cols))
                 for o in self._ops:
                     if o.kind == "map":
                         sc.add_map(o.udf, o.id)
@@ -369,6 +369,11 @@ def _csv_cell(v, null_value=None) -> str:
 def _row_of(cols: List[Column], values_cache: List[list], i: int):
     vals = tuple(values_cache[c][i] for c in range(len(cols)))
     return vals if len(vals) != 1 else vals[0]
+
+
+def _option_cols(cols) -> List[int]:
+    """Input columns that hold None values (Option[T]): the stage reads their validity bitmaps through companion columns."""
+    return [c for c, col in enumerate(cols) if getattr(col, "valid", None) is not None]
 
 
 def _rows_as_tuples(rows):
@@ -582,7 +587,7 @@ def _run_stage(ctx, src: Source, ops: List[Op], exc_counter: Counter, csv_sink: 
         return _run_stage_python(ctx, Source([], [], 0, None, [], 0), ops, exc_counter)
     prog = None
     try:
-        sc = StageCompiler(in_types, src.names)
+        sc = StageCompiler(in_types, src.names, _option_cols(src.cols))
         for op in row_ops:
             if op.resolvers or op.ignores:
                 pass  # resolvers only act on the slow path
@@ -789,7 +794,7 @@ def _run_stage(ctx, src: Source, ops: List[Op], exc_counter: Counter, csv_sink: 
         ncols = len(prog.out_cols) - prog.hidden_out_cols
         if csv_sink is not None:
             # CSV sink: when no row took the interpreter path the rows are formatted on the device (K7) in block order
-            ok = not len(excs) and not fallback
+            ok = not len(excs) and not fallback and not any(prog.out_null_of)  # the device writer prints values, not None cells
             if ok:
                 for res, _, _ in held:
                     txt = res.csv_bytes(n_cols=ncols - (1 if need_rowidx else 0))

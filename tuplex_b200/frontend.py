@@ -121,6 +121,7 @@ class Val:
     vreg: Optional[int] = None
     const: Any = None
     sel: Any = None  # (cond, a, b) when this value is cond ? a : b
+    null: Any = None  # Option[T] value: bool Val "this row's value is None" (None = the value can never be None)
 
     @property
     def is_const(self):
@@ -150,6 +151,24 @@ def const_val(v) -> Val:
     return Val(_py_type_of(v), None, v)
 
 
+T_NONE = -1  # static type of the literal None (python::Type::NULLVALUE): a value that is None for every row
+
+
+def none_val() -> Val:
+    return Val(T_NONE, None, None, None, const_val(True))
+
+
+def is_none_literal(v) -> bool:
+    return isinstance(v, Val) and v.type == T_NONE
+
+
+def plain(v: Val) -> Val:
+    """The same value without its None flag (callers have dealt with the None rows)."""
+    if v.null is None:
+        return v
+    return Val(v.type, v.vreg, v.const, v.sel)
+
+
 # ------------------------------------------------------------------------------------------------
 # the stage compiler
 # ------------------------------------------------------------------------------------------------
@@ -161,8 +180,18 @@ class StageCompiler:
     addAggregate :2525, buildWithHashmapWriter :1108).
     """
 
-    def __init__(self, in_types: Sequence[int], in_names: Sequence[Optional[str]]):
-        self.prog = Program(list(in_types), list(in_names))
+    def __init__(self, in_types: Sequence[int], in_names: Sequence[Optional[str]], option_cols: Sequence[int] = ()):
+        """option_cols: input columns of type Option[T] (normal case with None values, utils/include/TypeSystem.h; the reference keeps
+        a per-row bitmap for them, Serializer.cc:1041-1059). Each gets an "is None" companion input column of type bool behind the
+        physical columns (descriptor: in_types entry TPLX_T_NULLOF | column); the executor expands the column's validity bitmap into
+        it. UDF code sees a value with a None flag: `is None` / `== None` tests read the flag, any other use of a None value raises
+        TypeError for that row (it is resolved on the interpreter path), values flow to the output with their flag."""
+        in_types, in_names = list(in_types), list(in_names)
+        self.phys_types, self.phys_names = list(in_types), list(in_names)
+        self.option_cols = sorted(set(int(c) for c in option_cols))
+        null_of = {len(in_types) + k: c for k, c in enumerate(self.option_cols)}
+        self.prog = Program(in_types + [T_BOOL] * len(null_of), in_names + [None] * len(null_of))
+        self.prog.null_of = dict(null_of)
         self.vreg_width: List[int] = []
         self.row: List[Val] = []
         self.names: List[Optional[str]] = list(in_names)
@@ -171,8 +200,12 @@ class StageCompiler:
         self.guard: Optional[int] = None  # vreg of current guard
         self.filters: List[Tuple[int, int]] = []  # (pc after the FILTER instruction, number of logged operators incl. it)
         self.oplog: List[Tuple[str, tuple]] = []  # operators in order, so that a prefix can be replayed (prefilter stage)
+        comp = {c: j for j, c in null_of.items()}
         for c, t in enumerate(in_types):
-            self.row.append(Val(t, None, ("col", c)))  # lazily loaded column reference
+            v = Val(t, None, ("col", c))  # lazily loaded column reference
+            if c in comp:
+                v.null = Val(T_BOOL, None, ("col", comp[c]))
+            self.row.append(v)
 
     # ---- emission helpers ----------------------------------------------------------------------
     def new_vreg(self, t: int) -> int:
@@ -293,6 +326,10 @@ class StageCompiler:
         """Python truth value test (LLVMEnvironment::truthValueTest; filter: PipelineBuilder.cc:671-686)."""
         if isinstance(v, TupleVal):
             return const_val(len(v.elems) > 0)
+        if v.null is not None:  # None is false; a value is tested as usual
+            if v.type == T_NONE:
+                return const_val(False)
+            return self.b_and(self.b_not(v.null), self.truth(plain(v)))
         if self.is_const(v):
             return const_val(bool(v.const))
         if v.type == T_BOOL:
@@ -332,6 +369,20 @@ class StageCompiler:
             return TupleVal([self.select(cond, x, y) for x, y in zip(a.elems, b.elems)], a.names or b.names)
         if self.is_const(cond):
             return a if cond.const else b
+        if a.null is not None or b.null is not None:
+            # Option[T]: select the values and the None flags separately (upCastReturnType, BlockGeneratorVisitor.cc:4055-4075)
+            if a.type == T_NONE and b.type == T_NONE:
+                return a
+            zero = {T_STR: "", T_F64: 0.0, T_BOOL: False}
+            na = a.null if a.null is not None else const_val(False)
+            nb = b.null if b.null is not None else const_val(False)
+            va = plain(a) if a.type != T_NONE else const_val(zero.get(b.type, 0))
+            vb = plain(b) if b.type != T_NONE else const_val(zero.get(a.type, 0))
+            out = self.select(cond, va, vb)
+            null = self.select(cond, na, nb)
+            if self.is_const(null) and not null.const:
+                return out
+            return Val(out.type, out.vreg, out.const, out.sel, null)
         a, b = self.unify(a, b)
         if a.type == T_BOOL:
             # boolean selects with constant arms are plain logic
@@ -596,7 +647,7 @@ class StageCompiler:
             # selective pipeline: a prefilter stage finds the surviving rows, this stage then runs densely over
             # them. The hidden trailing column (input row index of each output row) lets the executor number
             # exception rows across the two launches.
-            pre = StageCompiler(self.prog.in_types, self.prog.in_names)
+            pre = StageCompiler(self.phys_types, self.phys_names, self.option_cols)
             for name, a in self.oplog[:k]:
                 getattr(pre, name)(*a)
             pre.begin_op(self.oplog[k - 1][1][-1])
@@ -610,8 +661,24 @@ class StageCompiler:
             self.row.append(Val(T_I64, d))
             self.names.append("__row")
             self.prog.hidden_out_cols = 1
-        slots = self._finish(self.row)
-        self.prog.out_cols = [(s, v.type) for s, v in zip(slots, self.row)]
+        # Option[T] outputs: the value column plus a hidden bool "is None" companion (descriptor: tplx_outcol.null_of); the executor
+        # packs the companion into the result's validity bitmap. Companions sit behind the visible columns, before "__row".
+        outs, null_of = [], []
+        for i, v in enumerate(self.row[:n_user]):
+            if v.type == T_NONE:
+                raise UnsupportedUDF("a column that is None for every row is not a normal-case column")
+            outs.append(plain(v))
+            null_of.append(0)
+        comps = [(i, v.null) for i, v in enumerate(self.row[:n_user]) if v.null is not None and not (self.is_const(v.null) and not v.null.const)]
+        for i, nv in comps:
+            outs.append(nv)
+            null_of.append(i + 1)
+        outs += self.row[n_user:]
+        null_of += [0] * (len(self.row) - n_user)
+        self.prog.hidden_out_cols += len(comps)
+        slots = self._finish(outs)
+        self.prog.out_cols = [(s, v.type) for s, v in zip(slots, outs)]
+        self.prog.out_null_of = null_of
         self.prog.out_names = list(self.names[:n_user])
         if k:
             self.row.pop()
@@ -649,6 +716,8 @@ class StageCompiler:
         self.begin_op(op_id)
         kidx = [self.col_index(k) for k in key_cols]
         for i in kidx:
+            if self.row[i].null is not None:
+                raise UnsupportedUDF("Option[T] key column (null bucket) takes the interpreter path")
             if self.row[i].type not in (T_I64, T_STR, T_BOOL):
                 raise UnsupportedUDF("f64 keys are not supported (reference: PipelineBuilder.cc:1175-1177)")
         accs = self._lower_aggregate(agg_func, combine_func, init) if agg_func is not None else []
@@ -1163,7 +1232,7 @@ class _FuncCompiler:
         sc = self.sc
         if isinstance(e, ast.Constant):
             if e.value is None:
-                raise UnsupportedUDF("None in normal-case code")
+                return none_val()
             return const_val(e.value)
         if isinstance(e, ast.Name):
             if e.id in self.env:
@@ -1186,13 +1255,14 @@ class _FuncCompiler:
             return TupleVal([self.expr(v) for v in e.values], [k.value for k in e.keys])
         if isinstance(e, ast.JoinedStr):
             return self.format_pieces([("lit", p.value) if isinstance(p, ast.Constant) else
-                                       ("val", self.expr(p.value), self._spec_of(p)) for p in e.values])
+                                       ("val", self.need(self.expr(p.value)), self._spec_of(p)) for p in e.values])
         if isinstance(e, ast.BinOp):
             return self.binop(e.op, self.expr(e.left), self.expr(e.right))
         if isinstance(e, ast.UnaryOp):
             v = self.expr(e.operand)
             if isinstance(e.op, ast.Not):
                 return sc.b_not(sc.truth(v))
+            v = self.need(v)
             if isinstance(v, TupleVal) or v.type == T_STR:
                 raise UnsupportedUDF("unary operator on non-number")
             if isinstance(e.op, ast.USub):
@@ -1248,6 +1318,7 @@ class _FuncCompiler:
         sc = self.sc
         if isinstance(l, TupleVal) or isinstance(r, TupleVal):
             raise UnsupportedUDF("tuple arithmetic")
+        l, r = self.need(l), self.need(r)
         if l.type == T_STR or r.type == T_STR:
             if isinstance(op, ast.Add) and l.type == T_STR and r.type == T_STR:
                 if sc.is_const(l) and sc.is_const(r):
@@ -1313,6 +1384,17 @@ class _FuncCompiler:
             return sc.op2(C["TPLX_OP_FDIV"], T_F64, const_val(1.0), p if is_f else sc.to_f64(p))
         # base == 0 -> the constant 0 / 0.0 (for -0.0 too: FCmpOEQ(-0.0, 0.0) holds)
         return sc.select(is_zero, zero, p) if is_f else p
+
+    def need(self, v):
+        """A value about to be USED (arithmetic, call argument, index ...): for an Option[T] value the rows that hold None raise
+        TypeError here — on the executed path only, like every exception (PipelineBuilder.cc:949) — and take the interpreter path,
+        where CPython decides what `None + 1` or `str(None)` means; the other rows go on with the plain T value."""
+        if isinstance(v, TupleVal) or v.null is None:
+            return v
+        if v.type == T_NONE:
+            raise UnsupportedUDF("the literal None used as a value")
+        self.raise_if(v.null, C["TPLX_EC_TYPEERROR"])
+        return plain(v)
 
     def raise_if(self, cond: Val, code: int):
         """Raise `code` for the rows where cond holds (on the executed path only)."""
@@ -1493,6 +1575,12 @@ class _FuncCompiler:
             return sc.b_not(acc) if isinstance(op, ast.NotIn) else acc
         if isinstance(l, TupleVal) or isinstance(r, TupleVal):
             raise UnsupportedUDF("tuple comparison")
+        if l.null is not None or r.null is not None:
+            if isinstance(op, (ast.Eq, ast.NotEq, ast.Is, ast.IsNot)):
+                return self.compare_option(op, l, r)
+            l, r = self.need(l), self.need(r)  # ordering / containment with None: TypeError for those rows
+        elif isinstance(op, (ast.Is, ast.IsNot)):
+            raise UnsupportedUDF("`is` between values that are never None")
         if isinstance(op, (ast.In, ast.NotIn)):
             if l.type != T_STR or r.type != T_STR:
                 raise UnsupportedUDF("`in` is supported for str in str")
@@ -1524,6 +1612,25 @@ class _FuncCompiler:
         if l.type == T_F64 or r.type == T_F64:
             return sc.op2(C["TPLX_OP_FCMP"], T_BOOL, sc.to_f64(l), sc.to_f64(r), flags=pred)
         return sc.op2(C["TPLX_OP_ICMP"], T_BOOL, sc.to_i64(l), sc.to_i64(r), flags=pred)
+
+    def compare_option(self, op, l: Val, r: Val):
+        """== / != / is / is not with Option[T] or None operands (BlockGeneratorVisitor.cc:1030-1150): None equals only None; two
+        present values compare as their base types; no row raises."""
+        sc = self.sc
+        eq = isinstance(op, (ast.Eq, ast.Is))
+        ln = l.null if l.null is not None else const_val(False)
+        rn = r.null if r.null is not None else const_val(False)
+        if l.type == T_NONE or r.type == T_NONE:
+            res = sc.b_and(ln, rn) if (l.type == T_NONE and r.type == T_NONE) else (rn if l.type == T_NONE else ln)
+            # `x is None`: true exactly for the None rows of x (the other side is None for every row)
+            return res if eq else sc.b_not(res)
+        if isinstance(op, (ast.Is, ast.IsNot)):
+            raise UnsupportedUDF("`is` between two values")
+        both_null = sc.b_and(ln, rn)
+        any_null = sc.b_or(ln, rn)
+        same = self.compare1(ast.Eq(), plain(l), plain(r))  # compares never raise: evaluated for every row, used where both are present
+        res = sc.b_or(both_null, sc.b_and(sc.b_not(any_null), same))
+        return res if eq else sc.b_not(res)
 
     def _fold_eq_through_select(self, v, k: str):
         """(cond ? 'a' : 'b') == 'k'  ->  logic over cond when every leaf is a constant (else None)."""
@@ -1567,8 +1674,8 @@ class _FuncCompiler:
                 st = self.expr(sl.step)
                 if not (sc.is_const(st) and st.const == 1):
                     raise UnsupportedUDF("slice stride other than 1")
-            lo = self.expr(sl.lower) if sl.lower is not None else None
-            hi = self.expr(sl.upper) if sl.upper is not None else None
+            lo = self.need(self.expr(sl.lower)) if sl.lower is not None else None
+            hi = self.need(self.expr(sl.upper)) if sl.upper is not None else None
             for v in (lo, hi):
                 if v is not None and (isinstance(v, TupleVal) or v.type not in (T_I64, T_BOOL)):
                     raise UnsupportedUDF("slice bounds must be integers")
@@ -1579,7 +1686,7 @@ class _FuncCompiler:
             sc.emit_vals(C["TPLX_OP_SSLICE"], d, base, sc.to_i64(lo) if lo is not None else None,
                          sc.to_i64(hi) if hi is not None else None, flags=flags)
             return Val(T_STR, d)
-        idx = self.expr(e.slice)
+        idx = self.need(self.expr(e.slice))
         if isinstance(idx, TupleVal) or idx.type not in (T_I64, T_BOOL):
             # single string column addressed by name
             if sc.is_const(idx) and isinstance(idx.const, str) and idx.const in sc.names and len(sc.row) == 1:
@@ -1595,6 +1702,8 @@ class _FuncCompiler:
         if isinstance(e.func, ast.Name):
             name = e.func.id
             args = [self.expr(a) for a in e.args]
+            if name != "bool":  # bool(None) is False; every other builtin raises TypeError on None
+                args = [self.need(a) for a in args]
             if any(isinstance(a, TupleVal) for a in args):
                 if name == "len" and len(args) == 1:
                     return const_val(len(args[0].elems))
@@ -1637,11 +1746,11 @@ class _FuncCompiler:
                 return sc.select(c, y, x)  # Python: min(x, y) returns y only if y < x
             raise UnsupportedUDF(f"call to {name}()")
         if isinstance(e.func, ast.Attribute):
-            obj = self.expr(e.func.value)
+            obj = self.need(self.expr(e.func.value))
             if isinstance(obj, TupleVal) or obj.type != T_STR:
                 raise UnsupportedUDF("method call on non-string")
             m = e.func.attr
-            args = [self.expr(a) for a in e.args]
+            args = [self.need(self.expr(a)) for a in e.args]
             if any(isinstance(a, TupleVal) for a in args):
                 raise UnsupportedUDF("tuple argument")
 

@@ -84,6 +84,8 @@ class Program:
     n_slots: int = 0
     endpoint: int = 0
     hidden_out_cols: int = 0
+    null_of: Dict[int, int] = field(default_factory=dict)   # input column j is the "is None" companion of Option[T] input column null_of[j]
+    out_null_of: List[int] = field(default_factory=list)    # per output column: 0, or 1 + the output column it is the "is None" companion of
     prefilter: Optional["Program"] = None  # selective leading part, output = surviving row indices
     fused: Optional[bytes] = None  # serialized tplx_fused_header section (closed-form scan-aggregate hint)
     scratch_bytes: int = 256
@@ -105,8 +107,9 @@ class Program:
             return b + b"\0" * ((-len(b)) % 8)
 
         body = b""
-        body += pad8(bytes(self.in_types))
-        body += pad8(b"".join(struct.pack("<HBB", s, t, 0) for s, t in self.out_cols))
+        body += pad8(bytes((C["TPLX_T_NULLOF"] | self.null_of[j]) if j in self.null_of else t for j, t in enumerate(self.in_types)))
+        nof = list(self.out_null_of) + [0] * (len(self.out_cols) - len(self.out_null_of))
+        body += pad8(b"".join(struct.pack("<HBB", s, t, nof[k]) for k, (s, t) in enumerate(self.out_cols)))
         body += b"".join(struct.pack("<BBHIq", a.kind, 0, a.slot, 0, _as_i64(a.init_bits)) for a in self.accs)
         body += b"".join(struct.pack("<q", o) for o in self.opids)
         body += b"".join(i.pack() for i in self.instrs)
