@@ -485,6 +485,94 @@ def reference_line(args):
 
 
 # ------------------------------------------------------------------------------------------------------
+def measure_join(args, rank, world, local, dist):
+    """K8 (csrc/join.cuh): a flights-like broadcast join, measured briefly next to the headline workloads. Probe side = 50 M rows
+    (i64 key, i64 payload) resident in HBM, build side = a 1 M-row dimension table (i64 key, i64 payload, 8-byte string), inner join,
+    90 % of the probe rows find exactly one partner. A step = one probe of the whole block (count, scan, emit, gather of every output
+    column); the table is built once outside the timed region (its time is reported). value = probe rows / s over all ranks."""
+    import time
+    import torch
+    from tuplex_b200 import backend, ir
+    from tuplex_b200.backend import Column
+    n_probe, n_build = 50_000_000, 1_000_000
+    rng = np.random.default_rng(42 + rank)
+    bkeys = rng.permutation(n_build).astype(np.int64) * 2 + 1
+    names = np.frombuffer(b"".join(b"%08d" % i for i in range(n_build)), dtype=np.uint8).copy()
+    build = [Column(ir.T_I64, bkeys), Column(ir.T_I64, rng.integers(0, 1 << 40, n_build)),
+             Column(ir.T_STR, names, (np.arange(n_build + 1, dtype=np.uint64) * 8).astype(np.uint32))]
+    pkeys = bkeys[rng.integers(0, n_build, n_probe)]
+    miss = rng.random(n_probe) < 0.1
+    pkeys[miss] = pkeys[miss] + 1  # even keys never match
+    probe = [Column(ir.T_I64, pkeys), Column(ir.T_I64, rng.integers(0, 1 << 40, n_probe))]
+    bb = backend.Block.upload(local, build, n_build)
+    pb = backend.Block.upload(local, probe, n_probe)
+    jn = backend.Join(bb, [c.type for c in build], 0)
+    ptypes = [c.type for c in probe]
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    steps = max(3, min(args.steps, 5))
+    kms, n_out, out_bytes, launches = [], 0, 0, 0
+    for _ in range(3):
+        jn.probe(pb, ptypes, 0).free()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        res = jn.probe(pb, ptypes, 0)
+        info = res.info
+        kms.append(float(info.kernel_ms))
+        n_out, launches = int(info.n_out_rows), int(info.kernel_launches)
+        out_bytes = n_out * 8 * 3 + int(sum(info.out_str_bytes[:4])) + (n_out + 1) * 4
+        res.free()
+    sync_all()
+    dt = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    # end to end: pageable host columns in, every output column out (Block.upload + probe + fetch), one step
+    sync_all()
+    t1 = time.perf_counter()
+    pb2 = backend.Block.upload(local, probe, n_probe)
+    res = jn.probe(pb2, ptypes, 0)
+    cols = res.columns()
+    e2e_s = time.perf_counter() - t1
+    d2h = sum(c.nbytes() for c in cols)
+    res.free()
+    pb2.free()
+    binfo = jn.info
+    jn.free()
+    pb.free()
+    bb.free()
+    if rank != 0:
+        return None
+    peak, peak_src = peaks()
+    alg = n_probe * 16 + out_bytes  # probe columns read once + output columns written once (table traffic not counted)
+    km = float(np.median(kms))
+    out = {"workload": "join_broadcast", "description": "inner hash join, 50 M probe rows (i64 key, i64) x 1 M-row table (i64 key, i64, str8), 90 % hit rate; "
+           "K8 build + probe (csrc/join.cuh) through tplx_gpu_join_build / tplx_gpu_join_probe", "rows_per_gpu": n_probe, "build_rows": n_build,
+           "value": n_probe * world * steps / dt, "unit": "rows/s", "ms_per_step": dt / steps * 1e3, "steps": steps, "out_rows_per_gpu": n_out,
+           "build_ms": binfo["build_ms"], "gpu_launches": launches * steps,
+           "roofline": {"bound": "hbm", "kernel": "join_probe_count/emit + join_gather_* (K8)", "achieved": alg / (km * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": alg / (km * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_row": alg / n_probe,
+                        "kernel_ms_per_launch": km},
+           "e2e": {"value": n_probe / e2e_s, "unit": "rows/s", "h2d_bytes_per_step": n_probe * 16, "d2h_bytes_per_step": int(d2h), "steps": 1,
+                   "inputs_prepinned": False}}
+    if not args.no_cpu_baseline:
+        # CPU arm: the join oracle (oracle/join_oracle.c, one thread) on a bounded sample of the same probe rows
+        from oracle import pyoracle
+        ns = 5_000_000
+        t2 = time.perf_counter()
+        op, _ = pyoracle.join_pairs(build[0], n_build, Column(ir.T_I64, pkeys[:ns]), ns, False)
+        cs = time.perf_counter() - t2
+        out["cpu_baseline"] = {"value": ns / cs, "unit": "rows/s", "cores": 1, "kind": "port",
+                               "sample": f"{ns} probe rows against the same {n_build}-row table, index pairs only (oracle/join_oracle.c)", "out_rows": int(len(op))}
+    return out
+
+
 def measure(args, wl_key, rank, world, local, dist, hc):
     """Device-resident `value`, `roofline`, end-to-end `e2e` (page-locked and pageable host inputs) and the CPU arm of one workload.
     Returns the fields of its JSON object (rank 0) or None."""
@@ -784,6 +872,9 @@ def main():
         xb = argparse.Namespace(**vars(xa))
         xb.rows, xb.keys = 125_000_000, 10_000_000
         extras["aggbykey"] = measure(xb, "aggbykey", rank, world, local, dist, hc)
+        xj = argparse.Namespace(**vars(xa))
+        xj.no_cpu_baseline = args.no_cpu_baseline
+        extras["join"] = measure_join(xj, rank, world, local, dist)
     if rank == 0:
         k0 = keys[0]
         cfg = static_config(args, k0)
