@@ -303,3 +303,19 @@ def test_context_join_with_fallback_rows_and_blocks(gpu):
     # inner join that builds on the left side (probe = right rows)
     small = c.parallelize(L[:300], columns=["k", "v"])
     assert small.join(dr, "k", "k").collect() == dataset._py_join_pairs(L[:300], 0, R, 0, False, False, 2)
+
+
+@pytest.mark.gpu
+def test_context_join_sharded_over_tasks(gpu):
+    """tuplex.gpu.devices lists the device twice: two tasks, each builds its own table and probes its contiguous run of blocks
+    (broadcast join, no exchange); the concatenation in task order equals the single-task result."""
+    import tuplex_b200 as tuplex
+    rng = np.random.default_rng(33)
+    L = [(int(k), "l%d" % i, float(i)) for i, k in enumerate(rng.integers(0, 500, 9000))]
+    R = [(int(k), "r%d" % i) for i, k in enumerate(rng.integers(0, 600, 1200))]
+    one = tuplex.Context({"tuplex.gpu.blockRows": 1000})
+    two = tuplex.Context({"tuplex.gpu.blockRows": 1000, "tuplex.gpu.devices": "0,0"})
+    for ctx_ in (one, two):
+        dl, dr = ctx_.parallelize(L, columns=["k", "v", "f"]), ctx_.parallelize(R, columns=["k", "w"])
+        assert dl.leftJoin(dr, "k", "k").collect() == po.join_rows(L, 0, R, 0, T_I64, left_outer=True)
+        assert dl.join(dr, "k", "k", prefixes=("l_", "r_")).columns == ["l_v", "l_f", "l_k", "r_w"]

@@ -428,8 +428,8 @@ def _run_join(ctx, spec: JoinSpec, exc_counter: Counter):
     devs = list(getattr(ctx, "_devices", [ctx._device])) or [ctx._device]
     block_rows = ctx._block_rows
     blocks = [(lo, min(n_probe, lo + block_rows)) for lo in range(0, n_probe, block_rows)] or [(0, 0)]
-    if len(set(devs)) != len(devs) or len(blocks) < 2:
-        devs = devs[:1]
+    if len(blocks) < 2:
+        devs = devs[:1]  # a single probe block has nothing to shard
     backend.init(sorted(set(devs)))
     from .dist import shard_range
     import threading
