@@ -228,6 +228,17 @@ int32_t tplx_gpu_join_destroy(tplx_join *join);
 int32_t tplx_gpu_result_fetch_validity(tplx_result *res, uint32_t col, uint32_t *words, uint32_t *nullable);
 int32_t tplx_gpu_result_device_validity(tplx_result *res, uint32_t col, const uint32_t **words);
 
+/* ---- in-order merge of resolved rows (K9) --------------------------------------------------------- */
+/* Replaces ResolveTask::executeInOrder (core/src/physical/ResolveTask.cc:878-1258, emitNormalRows :300-375) for rows the resolve path
+ * produced in the stage's normal-case OUTPUT schema: every resolved row returns to the slot of the task's output stream its exception
+ * record occupied (row_no, TransformTask.cc:764,885); exceptions that stay unresolved leave their slot empty. `res` is the stage result
+ * of one block run with `first_row_no`; `resolved` is a device-resident block with the stage's visible output columns (validity bitmaps
+ * for Option columns), one row per resolved exception, ordered by `resolved_row_nos` (strictly ascending, each the row_no of one of
+ * res's exception records). The merged rows come back as a new result (columns + validity, no exception records) that the
+ * partition / CSV writers accept like any stage result. */
+int32_t tplx_gpu_result_merge_resolved(tplx_result *res, const tplx_block *resolved, const int64_t *resolved_row_nos, int64_t first_row_no,
+                                       tplx_result **out);
+
 /* ---- multi-GPU: the one exchange step of the path ------------------------------------------- */
 /* One rank per (process, device) over NCCL (NVLink 5 / NVSwitch). Map / filter stages shard over ranks without any
  * communication (one task per partition group, LocalBackend.cc:679-735); only aggregate endpoints exchange data:

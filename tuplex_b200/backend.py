@@ -108,6 +108,7 @@ def lib():
         "tplx_gpu_join_destroy": ([vp], i32),
         "tplx_gpu_result_fetch_validity": ([vp, u32, vp, P(u32)], i32),
         "tplx_gpu_result_device_validity": ([vp, u32, P(vp)], i32),
+        "tplx_gpu_result_merge_resolved": ([vp, vp, P(i64), i64, P(vp)], i32),
         "tplx_gpu_comm_unique_id": ([vp], i32),
         "tplx_gpu_comm_init": ([i32, i32, i32, vp], i32),
         "tplx_gpu_comm_init_local": ([P(i32), i32], i32),
@@ -552,6 +553,14 @@ class Result:
             _check(lib().tplx_gpu_result_csv(self._h, n_cols, ord(delimiter), ord(quotechar), buf.ctypes.data, need.value, ct.byref(need)),
                    "tplx_gpu_result_csv")
         return buf.tobytes()
+
+    def merge_resolved(self, resolved: "Block", row_nos: Sequence[int], first_row_no: int = 0) -> "Result":
+        """In-order merge of resolved rows on the device (K9, tplx_gpu_result_merge_resolved; ResolveTask::executeInOrder):
+        `resolved` holds the stage's visible output columns, one row per resolved exception, ordered by row number."""
+        arr = (ct.c_int64 * max(len(row_nos), 1))(*[int(v) for v in row_nos])
+        h = ct.c_void_p()
+        _check(lib().tplx_gpu_result_merge_resolved(self._h, resolved._h, arr, first_row_no, ct.byref(h)), "tplx_gpu_result_merge_resolved")
+        return Result(h, None, resolved, types=self.out_types())
 
     def exception_partition(self) -> bytes:
         need = ct.c_uint64()

@@ -30,6 +30,7 @@
 #include "csv.cuh"
 #include "join.cuh"
 #include "option.cuh"
+#include "merge.cuh"
 #include "jit.inl"
 
 using namespace tplx;
@@ -2410,3 +2411,4 @@ extern "C" int32_t tplx_gpu_result_fetch_aggregate(tplx_result *r, int64_t *acc_
 #include "tplx_gpu_csv.inl"
 #include "tplx_gpu_comm.inl"
 #include "tplx_gpu_join.inl"
+#include "tplx_gpu_merge.inl"

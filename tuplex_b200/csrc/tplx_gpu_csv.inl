@@ -347,6 +347,8 @@ extern "C" int32_t tplx_gpu_csv_result_free(tplx_csv_result *r) {
 extern "C" int32_t tplx_gpu_result_csv(tplx_result *r, uint32_t n_cols, uint8_t delimiter, uint8_t quotechar, uint8_t *buf,
                                        uint64_t buf_bytes, uint64_t *bytes_needed) {
     if (!r || !bytes_needed || r->agg_out) return fail(TPLX_E_BADARG, "result_csv: needs a row result");
+    for (size_t c = 0; c + r->hidden < r->out.size() && c < r->out_valid.size() && (n_cols == 0 || c < n_cols); ++c)
+        if (r->out_valid[c]) return fail(TPLX_E_UNSUPPORTED, "result_csv: Option[T] column (None cells): use the host row writer");
     Device *d = r->dev;
     CsvSinkCols C{};
     C.n_cols = (uint32_t)(r->out.size() - r->hidden);

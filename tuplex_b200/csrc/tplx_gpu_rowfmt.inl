@@ -168,6 +168,8 @@ extern "C" int32_t tplx_gpu_result_partitions(tplx_result *r, uint64_t partition
                                               uint64_t *bytes_needed, uint64_t *part_offsets, uint32_t max_parts,
                                               uint32_t *n_parts) {
     if (!r || !bytes_needed || !n_parts || partition_bytes <= 8) return fail(TPLX_E_BADARG, "result_partitions: bad arguments");
+    for (size_t c = 0; c + r->hidden < r->out.size() && c < r->out_valid.size(); ++c)
+        if (r->out_valid[c]) return fail(TPLX_E_UNSUPPORTED, "result_partitions: Option[T] output columns need the row bitmap (Serializer.cc:1041-1059): not built");
     if (r->agg_out) {
         // aggregate result: one row with one slot per accumulator (LocalBackend.cc:1180-1207)
         uint64_t need = 8 + 8ull * r->n_accs;

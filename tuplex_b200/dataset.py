@@ -707,9 +707,10 @@ def _run_stage(ctx, src: Source, ops: List[Op], exc_counter: Counter, csv_sink: 
             exc["row"] += lo
             sh.excs.append(exc)
         if prog.endpoint == C["TPLX_EP_MEMORY"]:
+            frn = sh.row_no  # the block ran with this first_row_no
             sh.row_no += int(info.n_out_rows) + int(info.n_exceptions)
             if csv_sink is not None:
-                sh.held.append((res, lo, rowmap))  # decide at the end: device CSV writer or column fetch + merge
+                sh.held.append((res, lo, rowmap, frn, getattr(sh, "dev", dev)))  # decide at the end: device CSV writer or column fetch + merge
                 return
             sh.out_cols.append(fetch_cols(res, lo, rowmap))
         elif prog.endpoint == C["TPLX_EP_AGGREGATE"]:
@@ -745,6 +746,7 @@ def _run_stage(ctx, src: Source, ops: List[Op], exc_counter: Counter, csv_sink: 
 
         def run_shard(k: int) -> Shard:
             sh = Shard()
+            sh.dev = devs[k]
             blo, bhi = shard_range(len(blocks), k, len(devs))
             for lo, hi in blocks[blo:bhi]:
                 cols = [c.slice(lo, hi) for c in src.cols] if (lo, hi) != (0, n) else src.cols
@@ -796,19 +798,26 @@ def _run_stage(ctx, src: Source, ops: List[Op], exc_counter: Counter, csv_sink: 
             # CSV sink: when no row took the interpreter path the rows are formatted on the device (K7) in block order
             ok = not len(excs) and not fallback and not any(prog.out_null_of)  # the device writer prints values, not None cells
             if ok:
-                for res, _, _ in held:
+                for res, *_ in held:
                     txt = res.csv_bytes(n_cols=ncols - (1 if need_rowidx else 0))
                     if txt is None:  # f64 output column: host formatter
                         ok = False
                         break
                     csv_sink.append(txt)
+            elif len(excs) and not fallback and not is_csv and not need_rowidx and not any(prog.out_null_of):
+                # exception rows: resolve them in CPython, put the resolved rows back into their slots ON THE DEVICE (K9,
+                # ResolveTask::executeInOrder) and keep the device row writer
+                chunks = _device_merge_csv(held, row_ops, src, input_row, [t for _, t in prog.out_cols[:ncols]], exc_counter)
+                if chunks is not None:
+                    csv_sink.extend(chunks)
+                    ok = True
             if ok:
-                for res, _, _ in held:
+                for res, *_ in held:
                     res.free()
                 stage.close()
                 return None, out_names
             del csv_sink[:]
-            for res, lo_, rowmap_ in held:
+            for res, lo_, rowmap_, *_ in held:
                 out_cols_all.append(fetch_cols(res, lo_, rowmap_))
                 res.free()
         merged_vals = [sum((oc[c].to_values() for oc in out_cols_all), []) for c in range(ncols)]
@@ -971,6 +980,57 @@ def _py_fold(row_ops, end: Op, value, obj, names, exc_counter):
     except Exception as ex:  # noqa: BLE001
         exc_counter[(getattr(ex, "tplx_op", end.id), type(ex).__name__)] += 1
         return value
+
+
+def _fits_type(v, t: int) -> bool:
+    if t == T_STR:
+        return isinstance(v, str)
+    if t == T_F64:
+        return isinstance(v, float)
+    if t == T_BOOL:
+        return isinstance(v, bool)
+    return isinstance(v, int) and not isinstance(v, bool) and -(1 << 63) <= v < (1 << 63)
+
+
+def _device_merge_csv(held, row_ops, src, input_row, out_types, exc_counter: Counter) -> Optional[List[bytes]]:
+    """CSV text of every held block result with its resolved exception rows merged in order on the device
+    (tplx_gpu_result_merge_resolved + tplx_gpu_result_csv). None when a resolved row does not fit the stage's output schema
+    (the host path then merges and formats); exception counts are only taken over on success."""
+    ncols = len(out_types)
+    chunks: List[bytes] = []
+    counts: Counter = Counter()
+    for res, lo, _rowmap, frn, dev in held:
+        ex = res.exceptions()
+        if not len(ex):
+            txt = res.csv_bytes(n_cols=ncols)
+            if txt is None:
+                return None
+            chunks.append(txt)
+            continue
+        rows, nos = [], []
+        for e in ex[np.argsort(ex["row_no"], kind="stable")]:
+            try:
+                val, _ = pyexec.run_row(row_ops, input_row(lo + int(e["row"])), src.names)
+            except Dropped:
+                continue
+            except Exception as err:  # noqa: BLE001 — stays an exception
+                counts[(getattr(err, "tplx_op", int(e["op_id"])), type(err).__name__)] += 1
+                continue
+            vt = val if isinstance(val, tuple) else (val,)
+            if len(vt) != ncols or not all(_fits_type(v, t) for v, t in zip(vt, out_types)):
+                return None
+            rows.append(vt)
+            nos.append(int(e["row_no"]))
+        blk = backend.Block.upload(dev, [Column.from_values([r[c] for r in rows], out_types[c]) for c in range(ncols)], len(rows))
+        merged = res.merge_resolved(blk, nos, frn)
+        txt = merged.csv_bytes(n_cols=ncols)
+        merged.free()
+        blk.free()
+        if txt is None:
+            return None
+        chunks.append(txt)
+    exc_counter.update(counts)
+    return chunks
 
 
 def _merge_by_rowno(normal_rows: list, excs: np.ndarray, resolved: List[Tuple[int, int, Any]]) -> list:
