@@ -33,6 +33,9 @@ extern "C" {
  * holds None" (c < TPLX_MAX_COLS). Companions follow the physical columns; the executor fills them from column c's validity
  * bitmap (tplx_column.valid), the caller passes only the physical columns. To the op program a companion is a TPLX_T_BOOL column. */
 #define TPLX_T_NULLOF 0x80u
+/* flag on a column type where a SCHEMA is given as bytes (tplx_gpu_block_from_partitions col_types): the field is Option[T]
+ * and takes part in the row bitmap (Serializer.cc:1041-1059) */
+#define TPLX_T_OPTION 0x40u
 
 /* column / value types (python::Type subset on the normal-case path, utils/include/TypeSystem.h) */
 enum tplx_type {

@@ -25,7 +25,7 @@ T_I64, T_F64, T_BOOL, T_STR = 0, 1, 2, 3
 
 class OCol(ct.Structure):
     _fields_ = [("type", ct.c_uint8), ("pad", ct.c_uint8 * 7), ("data", ct.c_void_p), ("offsets", ct.c_void_p),
-                ("data_bytes", ct.c_uint64)]
+                ("data_bytes", ct.c_uint64), ("valid", ct.c_void_p)]
 
 
 class OExc(ct.Structure):
@@ -93,6 +93,11 @@ def _ocols(cols):
             arr[i].data_bytes = int(o[-1]) if len(o) else 0
         else:
             arr[i].data_bytes = d.nbytes
+        v = getattr(c, "valid", None)
+        if v is not None:  # Option[T] column (row formats: bitmap; the op program reads companions instead)
+            v = np.ascontiguousarray(v, dtype=np.uint32)
+            keep.append(v)
+            arr[i].valid = v.ctypes.data
     return arr, keep
 
 

@@ -197,6 +197,7 @@ typedef struct tplx_ocol {
     const void *data;        /* fixed: 8-byte values; str: bytes */
     const uint32_t *offsets; /* str: n+1 */
     uint64_t data_bytes;
+    const uint32_t *valid;   /* Option[T] column: bit (r & 31) of word r >> 5 set = value present; NULL = not an Option column */
 } tplx_ocol;
 
 typedef struct tplx_oexc {
@@ -782,23 +783,47 @@ void tplx_oracle_free(tplx_oresult *r) {
 /* ------------------------------------------------------------------------------------------- */
 /* row / partition / exception byte formats                                                     */
 /* ------------------------------------------------------------------------------------------- */
+static int o_present(const tplx_ocol *c, uint64_t i) { return !c->valid || ((c->valid[i >> 5] >> (i & 31)) & 1u); }
+static uint64_t o_bitmap_bytes(const tplx_ocol *cols, uint32_t n_cols) { /* calcBitmapSize, Serializer.cc:29-41 */
+    uint32_t n_opt = 0;
+    for (uint32_t c = 0; c < n_cols; ++c) n_opt += cols[c].valid != NULL;
+    return (uint64_t)((n_opt + 63) / 64) * 8;
+}
 static uint64_t o_row_size(const tplx_ocol *cols, uint32_t n_cols, uint64_t i) {
-    uint64_t sz = 8ull * n_cols, var = 0;
+    uint64_t sz = 8ull * n_cols + o_bitmap_bytes(cols, n_cols), var = 0;
     int has = 0;
     for (uint32_t c = 0; c < n_cols; ++c)
         if (cols[c].type == TPLX_T_STR) {
             has = 1;
-            var += (uint64_t)(cols[c].offsets[i + 1] - cols[c].offsets[i]) + 1;
+            if (o_present(&cols[c], i)) var += (uint64_t)(cols[c].offsets[i + 1] - cols[c].offsets[i]) + 1;
         }
     return sz + (has ? 8 + var : 0);
 }
-/* Serializer::serialize (utils/src/Serializer.cc:1016-1117) for the non-Option normal case */
+/* Serializer::serialize (utils/src/Serializer.cc:1016-1117): bitmap of the Option fields (bit k = the k-th Option field is None,
+ * :1041-1059), one 8-byte slot per field, total var-len bytes, var-len payload. A None string keeps its slot (offset of the next
+ * var field, size 0) and contributes no bytes (appendWithoutInference(option<string>), :313-338); a None number has a zero slot. */
 static uint64_t o_write_row(const tplx_ocol *cols, uint32_t n_cols, uint64_t i, uint8_t *dst) {
+    const uint64_t bm = o_bitmap_bytes(cols, n_cols);
+    if (bm) {
+        memset(dst, 0, bm);
+        uint32_t k = 0;
+        for (uint32_t c = 0; c < n_cols; ++c) {
+            if (!cols[c].valid) continue;
+            if (!o_present(&cols[c], i)) dst[k / 8] |= (uint8_t)(1u << (k % 8)); /* little endian int64 words */
+            ++k;
+        }
+        dst += bm;
+    }
     uint64_t var_off = 8ull * n_cols + 8, total = 0;
     int has = 0;
     for (uint32_t c = 0; c < n_cols; ++c) {
         if (cols[c].type == TPLX_T_STR) {
             has = 1;
+            if (!o_present(&cols[c], i)) {
+                int64_t info = (int64_t)((var_off - 8ull * c) & 0xFFFFFFFFull);
+                memcpy(dst + 8ull * c, &info, 8);
+                continue;
+            }
             uint32_t o0 = cols[c].offsets[i], len = cols[c].offsets[i + 1] - o0;
             int64_t info = (int64_t)((var_off - 8ull * c) & 0xFFFFFFFFull) | ((int64_t)(len + 1) << 32);
             memcpy(dst + 8ull * c, &info, 8);
@@ -806,10 +831,12 @@ static uint64_t o_write_row(const tplx_ocol *cols, uint32_t n_cols, uint64_t i, 
             dst[var_off + len] = 0;
             var_off += len + 1;
             total += len + 1;
+        } else if (!o_present(&cols[c], i)) {
+            memset(dst + 8ull * c, 0, 8);
         } else memcpy(dst + 8ull * c, (const int64_t *)cols[c].data + i, 8);
     }
     if (has) memcpy(dst + 8ull * n_cols, &total, 8);
-    return 8ull * n_cols + (has ? 8 + total : 0);
+    return bm + 8ull * n_cols + (has ? 8 + total : 0);
 }
 
 /* rows [0,n) of a column block -> partitions, split like rowToMemorySink (TransformTask.h:47-92).

@@ -167,3 +167,78 @@ def test_context_none_goldens(gpu):
     c2 = tuplex.Context({"tuplex.gpu.optionColumns": False})
     assert c2.parallelize([1, 2, None, 4]).map(lambda x: (x, x * x)).collect() == [(1, 1), (2, 4), (4, 16)]
     assert c2.parallelize([1, None]).map(lambda x: x == None).collect() == [False, True]  # noqa: E711
+
+
+# ---- Option[T] fields in the reference's row format (K5, Serializer.cc:1016-1117) ---------------------------------------------
+def _opt_cols(vals, types, option):
+    cols = []
+    for c, (v, t) in enumerate(zip(vals, types)):
+        col = Column.from_values(v, t)
+        if c in option and col.valid is None:  # statically Option[T] although this block holds no None
+            col.valid = backend.pack_valid(np.ones(len(v), bool))
+        cols.append(col)
+    return cols
+
+
+def test_oracle_row_bytes_with_option_fields_hand_derived(built):
+    """(a: Option[i64] = None, s: str = 'ab', t: Option[str] = None, u: Option[str] = 'x', k: i64 = 7), bytes derived by hand from
+    Serializer::serialize: bitmap word (bit k = k-th Option field is None) | 5 slots | var-len total | payload; a None string keeps the
+    offset of the next var field with size 0 (appendWithoutInference(option<string>), Serializer.cc:313-338)."""
+    import struct
+    cols = _opt_cols([[None], ["ab"], [None], ["x"], [7]], [T_I64, T_STR, T_STR, T_STR, T_I64], {0, 2, 3})
+    (part,) = pyoracle.to_partitions(cols, 1, 1 << 20)
+    row = struct.pack("<q", 0b011)                    # a and t are None, u is present
+    row += struct.pack("<q", 0)                       # a
+    row += struct.pack("<q", 40 | (3 << 32))          # s: payload at slot address + 40, 'ab\\0'
+    row += struct.pack("<q", 35)                      # t: None, size 0, where the next var field starts (51 - 16)
+    row += struct.pack("<q", 27 | (2 << 32))          # u: 'x\\0' at 51 - 24
+    row += struct.pack("<q", 7)                       # k
+    row += struct.pack("<q", 5) + b"ab\0x\0"          # var-len total + payload
+    assert part == struct.pack("<q", 1) + row and len(row) == 61
+
+
+@pytest.mark.gpu
+def test_gpu_row_format_with_option_fields(gpu):
+    """K5 both ways and the exception partition with Option fields: byte-identical to the oracle."""
+    n = 5000
+    vals = _data(n, 99)
+    cols = _opt_cols(vals, TYPES, set(OPTION))
+    parts = pyoracle.to_partitions(cols, n, 64 << 10)
+    assert len(parts) > 2
+    # partitions -> column block (bitmaps -> validity) -> a pass-through stage -> columns + validity back
+    blk = backend.Block.from_partitions(0, parts, TYPES, OPTION)
+    sc = frontend.StageCompiler(TYPES, NAMES, OPTION)
+    sc.add_map(lambda x: (x["a"], x["b"], x["c"], x["s"]), 100001)
+    st = backend.Stage(sc.finish_memory())
+    res = st.run(blk)
+    got = [c.to_values() for c in res.columns()]
+    assert got == vals
+    # result -> partitions (validity -> bitmaps)
+    assert res.partitions(64 << 10) == parts
+    res.free()
+    st.close()
+    # exception rows keep their Option fields: the original input row with its bitmap
+    sc = frontend.StageCompiler(TYPES, NAMES, OPTION)
+    sc.add_map(lambda x: x["a"] + x["b"], 100001)
+    prog = sc.finish_memory()
+    st = backend.Stage(prog)
+    res = st.run(blk)
+    ora = pyoracle.run_program(prog, _expanded(cols, prog), n)
+    exc = res.exceptions()
+    assert len(exc) == sum(v is None for v in vals[0]) and np.array_equal(exc["row"], ora.exceptions["row"])
+    assert res.exception_partition() == pyoracle.exception_partition(cols, ora.exceptions)
+    res.free()
+    st.close()
+    blk.free()
+    # a left join's nullable columns serialise with the bitmap as well
+    left = [Column.from_values([1, 2, 3, 4], T_I64), Column.from_values(["a", "b", "c", "d"], T_STR)]
+    right = [Column.from_values([2, 4], T_I64), Column.from_values(["two", "four"], T_STR), Column.from_values([20, 40], T_I64)]
+    lb, rb = backend.Block.upload(0, left, 4), backend.Block.upload(0, right, 2)
+    jn = backend.Join(rb, [T_I64, T_STR, T_I64], 0)
+    jr = jn.probe(lb, [T_I64, T_STR], 0, left_outer=True)
+    want = _opt_cols([["a", "b", "c", "d"], [1, 2, 3, 4], [None, "two", None, "four"], [None, 20, None, 40]], [T_STR, T_I64, T_STR, T_I64], {2, 3})
+    assert jr.partitions(1 << 20) == pyoracle.to_partitions(want, 4, 1 << 20)
+    jr.free()
+    jn.free()
+    lb.free()
+    rb.free()

@@ -428,8 +428,10 @@ class Block:
         return Block(h, n_rows, device)
 
     @staticmethod
-    def from_partitions(device: int, partitions: Sequence[bytes], col_types: Sequence[int]) -> "Block":
+    def from_partitions(device: int, partitions: Sequence[bytes], col_types: Sequence[int], option_cols: Sequence[int] = ()) -> "Block":
+        """option_cols: Option[T] fields of the schema (they take part in the row bitmap, Serializer.cc:1041-1059)."""
         init([device])
+        col_types = [t | (ir.C["TPLX_T_OPTION"] if c in set(option_cols) else 0) for c, t in enumerate(col_types)]
         n = len(partitions)
         bufs = [np.frombuffer(p, dtype=np.uint8) for p in partitions]
         ptrs = (ct.c_void_p * max(n, 1))(*[b.ctypes.data for b in bufs])

@@ -116,19 +116,36 @@ struct RowFmtCols {
     uint64_t *data[TPLX_MAX_COLS];      // fixed width values / (partitions->columns) destination
     uint32_t *offsets[TPLX_MAX_COLS];   // string offsets (n+1)
     uint8_t *bytes[TPLX_MAX_COLS];      // string bytes
+    // Option[T] fields (Serializer.cc:1041-1059): the row starts with a bitmap of ceil(n_opt / 64) 8-byte words, bit k set = the k-th
+    // Option field of the row is None; a None string field has size 0 and no bytes (appendWithoutInference(option<string>), :313-338)
+    uint32_t n_opt, bitmap_bytes;
+    int8_t optk[TPLX_MAX_COLS];         // index among the Option fields, -1 = not an Option field
+    uint32_t *valid[TPLX_MAX_COLS];     // column block side: validity words (bit set = value present)
 };
+
+__device__ __forceinline__ bool rf_present(const RowFmtCols &C, uint32_t c, uint64_t i) {
+    return C.optk[c] < 0 || !C.valid[c] || ((C.valid[c][i >> 5] >> (i & 31)) & 1u);
+}
 
 // ---- partitions -> columns ----------------------------------------------------------------------
 // pass 1: fixed-width fields + string lengths (as uint64 for the scan)
 __global__ void rows_to_cols_pass1(const uint8_t *__restrict__ rows, const uint64_t *__restrict__ row_off, uint64_t n,
                                    RowFmtCols C, uint64_t *__restrict__ lens /* [n_str][n+1] */) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint8_t *slots = rows + row_off[i];
+    const bool active = i < n;
+    const uint8_t *bm = active ? rows + row_off[i] : rows;
+    const uint8_t *slots = bm + C.bitmap_bytes;
     for (uint32_t c = 0; c < C.n_cols; ++c) {
+        bool isnull = false;
+        if (C.optk[c] >= 0) {  // whole warps take this branch together: one validity word per warp and Option column
+            if (active) isnull = (ld64u(bm + 8 * (size_t)(C.optk[c] >> 6)) >> (C.optk[c] & 63)) & 1ull;
+            const uint32_t w = __ballot_sync(0xFFFFFFFFu, active && !isnull);
+            if ((threadIdx.x & 31) == 0 && (i >> 5) < ((n + 31) >> 5)) C.valid[c][i >> 5] = w;
+        }
+        if (!active) continue;
         uint64_t v = ld64u(slots + 8 * (size_t)c);
-        if (C.types[c] == TPLX_T_STR) lens[(size_t)C.strk[c] * (n + 1) + i] = (v >> 32) ? (v >> 32) - 1 : 0;  // drop the NUL
-        else C.data[c][i] = v;
+        if (C.types[c] == TPLX_T_STR) lens[(size_t)C.strk[c] * (n + 1) + i] = (!isnull && (v >> 32)) ? (v >> 32) - 1 : 0;  // drop the NUL
+        else C.data[c][i] = isnull ? 0 : v;
     }
 }
 // pass 2: string bytes (lens now holds exclusive byte offsets)
@@ -141,7 +158,7 @@ __global__ void rows_to_cols_pass2(const uint8_t *__restrict__ rows, const uint6
         const uint64_t o = lens[(size_t)C.strk[c] * (n + 1) + i];
         C.offsets[c][i] = (uint32_t)o;
         if (i == n) continue;
-        const uint8_t *slot = rows + row_off[i] + 8 * (size_t)c;
+        const uint8_t *slot = rows + row_off[i] + C.bitmap_bytes + 8 * (size_t)c;
         const uint64_t v = ld64u(slot);
         const uint8_t *src = slot + (uint32_t)v;
         const uint32_t len = (v >> 32) ? (uint32_t)(v >> 32) - 1 : 0;
@@ -153,17 +170,30 @@ __global__ void rows_to_cols_pass2(const uint8_t *__restrict__ rows, const uint6
 // ---- columns -> rows ------------------------------------------------------------------------------
 // serialized size of row i of a column block
 __device__ __forceinline__ uint64_t row_size(const RowFmtCols &C, uint64_t i) {
-    uint64_t sz = 8ull * C.n_cols;
+    uint64_t sz = 8ull * C.n_cols + C.bitmap_bytes;
     if (C.n_str) {
         sz += 8;
         for (uint32_t c = 0; c < C.n_cols; ++c)
-            if (C.types[c] == TPLX_T_STR) sz += (uint64_t)(C.offsets[c][i + 1] - C.offsets[c][i]) + 1;
+            if (C.types[c] == TPLX_T_STR && rf_present(C, c, i)) sz += (uint64_t)(C.offsets[c][i + 1] - C.offsets[c][i]) + 1;
     }
     return sz;
 }
 __device__ __forceinline__ void write_row(const RowFmtCols &C, uint64_t i, uint8_t *dst) {
+    if (C.bitmap_bytes) {  // bit k = the k-th Option field is None
+        for (uint32_t w = 0; w < C.bitmap_bytes / 8; ++w) {
+            uint64_t bits = 0;
+            for (uint32_t c = 0; c < C.n_cols; ++c)
+                if (C.optk[c] >= 0 && (uint32_t)(C.optk[c] >> 6) == w && !rf_present(C, c, i)) bits |= 1ull << (C.optk[c] & 63);
+            st64u(dst + 8 * (size_t)w, bits);
+        }
+        dst += C.bitmap_bytes;
+    }
     uint64_t var = 8ull * C.n_cols + 8, total = 0;
     for (uint32_t c = 0; c < C.n_cols; ++c) {
+        if (!rf_present(C, c, i)) {  // None: a zero slot; a string field still records where the next one starts, with size 0
+            st64u(dst + 8 * (size_t)c, C.types[c] == TPLX_T_STR ? ((var - 8ull * c) & 0xFFFFFFFFull) : 0ull);
+            continue;
+        }
         if (C.types[c] == TPLX_T_STR) {
             const uint32_t o0 = C.offsets[c][i], len = C.offsets[c][i + 1] - o0;
             const uint64_t rel = var - 8ull * c;

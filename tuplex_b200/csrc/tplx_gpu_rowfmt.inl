@@ -32,18 +32,18 @@ static int32_t device_scan_batched(Device *d, uint64_t *arrays, uint64_t stride,
 // itself (fixed slots + optional var-len total), so this is inherently sequential per partition
 // (Deserializer::inferLength, Serializer.cc:1227-1284); it touches 8-16 bytes per row.
 static bool walk_partition(const uint8_t *part, uint64_t bytes, uint32_t n_cols, bool has_var, uint64_t base,
-                           std::vector<uint64_t> &row_off) {
+                           std::vector<uint64_t> &row_off, uint32_t bitmap_bytes = 0) {
     if (bytes < 8) return false;
     int64_t n_rows;
     memcpy(&n_rows, part, 8);
     if (n_rows < 0) return false;
     uint64_t pos = 8;
     for (int64_t r = 0; r < n_rows; ++r) {
-        uint64_t fixed = 8ull * n_cols + (has_var ? 8 : 0);
+        uint64_t fixed = bitmap_bytes + 8ull * n_cols + (has_var ? 8 : 0);
         if (pos + fixed > bytes) return false;
         row_off.push_back(base + pos);
         uint64_t var = 0;
-        if (has_var) memcpy(&var, part + pos + 8ull * n_cols, 8);
+        if (has_var) memcpy(&var, part + pos + bitmap_bytes + 8ull * n_cols, 8);
         pos += fixed + var;
         if (pos > bytes) return false;
     }
@@ -61,9 +61,11 @@ extern "C" int32_t tplx_gpu_block_from_partitions(int32_t device, const uint8_t 
     RowFmtCols C{};
     C.n_cols = n_cols;
     for (uint32_t c = 0; c < n_cols; ++c) {
-        C.types[c] = col_types[c];
-        C.strk[c] = col_types[c] == TPLX_T_STR ? (int8_t)C.n_str++ : (int8_t)-1;
+        C.types[c] = col_types[c] & 0x3F;
+        C.strk[c] = C.types[c] == TPLX_T_STR ? (int8_t)C.n_str++ : (int8_t)-1;
+        C.optk[c] = (col_types[c] & TPLX_T_OPTION) ? (int8_t)C.n_opt++ : (int8_t)-1;  // Option[T] field: bit optk of the row bitmap
     }
+    C.bitmap_bytes = (C.n_opt + 63) / 64 * 8;
     // 1. upload raw partition bytes (async) while the host walks row starts
     uint64_t total = 0;
     std::vector<uint64_t> pbase(n_partitions);
@@ -77,7 +79,7 @@ extern "C" int32_t tplx_gpu_block_from_partitions(int32_t device, const uint8_t 
         CU(cudaMemcpyAsync(raw + pbase[p], partitions[p], partition_bytes[p], cudaMemcpyHostToDevice, d->stream));
     std::vector<uint64_t> row_off;
     for (uint32_t p = 0; p < n_partitions; ++p)
-        if (!walk_partition(partitions[p], partition_bytes[p], n_cols, C.n_str > 0, pbase[p], row_off)) {
+        if (!walk_partition(partitions[p], partition_bytes[p], n_cols, C.n_str > 0, pbase[p], row_off, C.bitmap_bytes)) {
             cudaFreeAsync(raw, d->stream);
             return fail(TPLX_E_BADARG, "block_from_partitions: malformed partition");
         }
@@ -104,6 +106,13 @@ extern "C" int32_t tplx_gpu_block_from_partitions(int32_t device, const uint8_t 
             b->owned.push_back(v);
             C.data[c] = static_cast<uint64_t *>(v);
         }
+    }
+    for (uint32_t c = 0; c < n_cols; ++c) {
+        if (C.optk[c] < 0) continue;
+        void *v = nullptr;
+        CU(cudaMallocAsync(&v, (n + 31) / 32 * 4 + 16, d->stream));
+        b->owned.push_back(v);
+        C.valid[c] = static_cast<uint32_t *>(v);
     }
     const uint32_t nb = (uint32_t)((n + RF_NT) / RF_NT);
     if (n) rows_to_cols_pass1<<<nb, RF_NT, 0, d->stream>>>(raw, d_row_off, n, C, lens);
@@ -139,6 +148,7 @@ extern "C" int32_t tplx_gpu_block_from_partitions(int32_t device, const uint8_t 
             b->data_bytes.push_back(n * 8);
         }
         b->cols.push_back(ci);
+        b->valid.push_back(C.optk[c] >= 0 ? C.valid[c] : nullptr);
     }
     CU(cudaFreeAsync(raw, d->stream));
     CU(cudaFreeAsync(d_row_off, d->stream));
@@ -161,15 +171,19 @@ static void result_rowfmt(const tplx_result *r, RowFmtCols &C) {
             C.strk[c] = -1;
             C.data[c] = r->out[c].data;
         }
+        C.optk[c] = -1;
+        if (c < r->out_valid.size() && r->out_valid[c]) {  // Option[T] output column: takes part in the row bitmap
+            C.optk[c] = (int8_t)C.n_opt++;
+            C.valid[c] = r->out_valid[c];
+        }
     }
+    C.bitmap_bytes = (C.n_opt + 63) / 64 * 8;
 }
 
 extern "C" int32_t tplx_gpu_result_partitions(tplx_result *r, uint64_t partition_bytes, uint8_t *buf, uint64_t buf_bytes,
                                               uint64_t *bytes_needed, uint64_t *part_offsets, uint32_t max_parts,
                                               uint32_t *n_parts) {
     if (!r || !bytes_needed || !n_parts || partition_bytes <= 8) return fail(TPLX_E_BADARG, "result_partitions: bad arguments");
-    for (size_t c = 0; c + r->hidden < r->out.size() && c < r->out_valid.size(); ++c)
-        if (r->out_valid[c]) return fail(TPLX_E_UNSUPPORTED, "result_partitions: Option[T] output columns need the row bitmap (Serializer.cc:1041-1059): not built");
     if (r->agg_out) {
         // aggregate result: one row with one slot per accumulator (LocalBackend.cc:1180-1207)
         uint64_t need = 8 + 8ull * r->n_accs;
@@ -249,7 +263,9 @@ extern "C" int32_t tplx_gpu_result_exception_partition(tplx_result *r, uint8_t *
     const tplx_block *b = r->block;
     RowFmtCols C;
     memset(&C, 0, sizeof(C));
-    C.n_cols = (uint32_t)b->cols.size();
+    // the ORIGINAL input row in the normal-case input schema: the physical columns (not the `is None` companions the executor
+    // appended for the op program); Option[T] input columns carry their bit in the row bitmap
+    C.n_cols = (uint32_t)b->cols.size() - (r->stage ? r->stage->n_companions : 0);
     for (uint32_t c = 0; c < C.n_cols; ++c) {
         C.types[c] = (uint8_t)b->cols[c].type;
         if (C.types[c] == TPLX_T_STR) {
@@ -260,7 +276,13 @@ extern "C" int32_t tplx_gpu_result_exception_partition(tplx_result *r, uint8_t *
             C.strk[c] = -1;
             C.data[c] = static_cast<uint64_t *>(const_cast<void *>(b->cols[c].data));
         }
+        C.optk[c] = -1;
+        if (c < b->valid.size() && b->valid[c]) {
+            C.optk[c] = (int8_t)C.n_opt++;
+            C.valid[c] = const_cast<uint32_t *>(b->valid[c]);
+        }
     }
+    C.bitmap_bytes = (C.n_opt + 63) / 64 * 8;
     const uint64_t ne = r->n_exc;
     if (ne == 0) {
         *bytes_needed = 8;
