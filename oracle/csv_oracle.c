@@ -426,6 +426,7 @@ typedef struct {
     const void *data;
     const uint32_t *offsets;
     uint64_t data_bytes;
+    const uint32_t *valid; /* same layout as tplx_ocol (tplx_oracle.c); the CSV sink writes non-Option columns only */
 } sink_col;
 
 /* returns bytes written; out may be NULL to size */
