@@ -154,3 +154,43 @@ def test_cpp_host_tasks_aggregate_and_hash(gpu, tmp_path):
         for i in range(info["hash_partitions"]):
             got += _decode_partition(open(f"{prefix}.hash{i}", "rb").read(), [T_STR, T_I64])
         assert sorted(got) == [("abc", -7500), ("xyz", 25000)] and info["out_rows"] == 2 and info["endpoint"] == 2
+
+
+def test_cpp_host_hash_join(gpu, tmp_path):
+    """GpuBackend::execute(GpuHashJoinStage&): reference-format partitions of both sides in, joined rows out as partitions (Option
+    fields of a left join with their row bitmap), two tasks on one device; byte-identical to the oracle's rows serialised by the oracle."""
+    from tuplex_b200 import backend
+    rng = np.random.default_rng(12)
+    n_probe, n_build = 30_000, 900
+    pk = rng.integers(0, 1200, n_probe)
+    probe = [Column(T_I64, pk.astype(np.int64)), Column.from_values(["p%d" % i for i in range(n_probe)], T_STR)]
+    bk = rng.integers(0, 1200, n_build)
+    build = [Column.from_values(["name-%d" % v for v in bk.tolist()], T_STR), Column(T_I64, bk.astype(np.int64)), Column(T_I64, np.arange(n_build, dtype=np.int64) * 10)]
+    psize = 64 << 10
+    pparts, bparts = pyoracle.to_partitions(probe, n_probe, psize), pyoracle.to_partitions(build, n_build, psize)
+    files = []
+    for tag, parts in (("b", bparts), ("p", pparts)):
+        for i, p in enumerate(parts):
+            f = tmp_path / f"{tag}{i}.bin"
+            f.write_bytes(p)
+            files.append(str(f))
+    exe = os.path.join(ROOT, "tuplex_b200", "lib", "tplx_host_run")
+    for left_outer in (False, True):
+        op, ob = pyoracle.join_pairs(build[1], n_build, probe[0], n_probe, left_outer)
+        pvals, bvals = [c.to_values() for c in probe], [c.to_values() for c in build]
+        take = lambda vals, idx: [None if i < 0 else vals[i] for i in idx.tolist()]  # noqa: E731
+        want_vals = [take(pvals[1], op), take(pvals[0], op), take(bvals[0], ob), take(bvals[2], ob)]   # | probe non-key | key | build non-key |
+        want_cols = [Column.from_values(v, t) for v, t in zip(want_vals, [T_STR, T_I64, T_STR, T_I64])]
+        if left_outer:
+            for c in want_cols[2:]:  # Option[T] columns of a left join even where this run has no None
+                if c.valid is None:
+                    c.valid = backend.pack_valid(np.ones(len(op), bool))
+        prefix = str(tmp_path / f"join{int(left_outer)}")
+        cmd = [exe, "--join", "0,3", "0", "3,0,0", "1", str(1 if left_outer else 0), str(psize), prefix, "0,0", str(len(bparts))] + files
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        info = json.loads(r.stdout.strip().splitlines()[-1])
+        assert info["out_rows"] == len(op) and info["tasks"] == 2
+        got = b"".join(open(f"{prefix}.out{i}", "rb").read()[8:] for i in range(info["out_partitions"]))
+        want = b"".join(p[8:] for p in pyoracle.to_partitions(want_cols, len(op), psize))
+        assert got == want   # same rows, same bytes (partition boundaries differ: two tasks)

@@ -43,11 +43,23 @@ def test_c1_row_function_text_and_cubin():
     st = backend.Stage(W.c1_program())
     src, nb, log = st.specialise(K_VEC4)
     # x * x ; x % 2 == 0 as straight-line code on named slots: no fetch, no dispatch, constants inline
-    assert "r1 = r0 * r0;" in src and "floormod_i64((int64_t)r1, y_)" in src and "0x2ull" in src
+    # (% by the constant 2 is a mask on this path: the strength reduction the vector kernel's pre-decode does as well)
+    assert "r1 = r0 * r0;" in src and "& 0x1ull;" in src and "floormod_i64" not in src
     assert "jit_row_fixed" in src and "out[0] = r1;" in src
     assert nb > 0, f"NVRTC produced no cubin: {log}"
     src1, nb1, log1 = st.specialise(K_ROWS)
     assert "jit_run(" in src1 and nb1 > 0, log1
+    st.close()
+
+
+def test_constant_power_of_two_divisors_are_strength_reduced():
+    sc = frontend.StageCompiler([ir.T_I64], ["a"])
+    sc.add_map(lambda x: (x["a"] // 8, x["a"] % 16, x["a"] // 6, x["a"] % 3, x["a"] % 1), 100001)
+    st = backend.Stage(sc.finish_memory())
+    src, nb, log = st.specialise(K_VEC4)
+    assert nb > 0, log
+    assert ">> 3);" in src and "& 0xfull;" in src and "& 0x0ull;" in src     # 2^k: shift / mask, no zero test
+    assert src.count("floordiv_i64(") == 1 and src.count("floormod_i64(") == 1   # 6 and 3 keep the general form
     st.close()
 
 
@@ -145,6 +157,31 @@ def test_fixed_width_exceptions_and_branches(gpu):
             assert (int(res.info.specialised_launches) > 0) == (mode == 2)
             res.free()
             st.close()
+
+
+@pytest.mark.gpu
+def test_strength_reduced_divisions_on_negative_values(gpu):
+    """x // 2^k and x % 2^k as shift / mask must keep Python's floor semantics for negative x (specialised == interpreted == oracle)."""
+    n = 200_003
+    rng = np.random.default_rng(17)
+    a = rng.integers(-(1 << 40), 1 << 40, n)
+    a[:4] = [-(1 << 63), (1 << 63) - 1, -1, 0]
+    cols = [backend.Column(ir.T_I64, a)]
+    sc = frontend.StageCompiler([ir.T_I64], ["a"])
+    sc.add_map(lambda x: (x["a"] // 8, x["a"] % 16, x["a"] // 1, x["a"] % 1, x["a"] // 4096, x["a"] % 2), 100001)
+    sc.add_filter(lambda a, b, c, d, e, f: f == 1 or b > 3, 100002)
+    prog = sc.finish_memory(prefilter=False)
+    ora = pyoracle.run_program(prog, cols, n)
+    for mode in (2, 0):
+        with jit_mode(mode):
+            st = backend.Stage(prog)
+            res = st.run_host(0, cols, n)
+            assert_result_equals_oracle(res, ora, f"TPLX_JIT={mode}")
+            res.free()
+            st.close()
+    want = [(int(v) // 8, int(v) % 16, int(v), 0, int(v) // 4096, int(v) % 2) for v in a.tolist()]
+    want = [w for w in want if w[5] == 1 or w[1] > 3]
+    assert list(zip(*[ora.values(c) for c in range(6)])) == want  # and the oracle is CPython's floor semantics
 
 
 @pytest.mark.gpu

@@ -233,4 +233,77 @@ void GpuBackend::execute(GpuTransformStage &st) {
     tplx_gpu_stage_destroy(stage);
 }
 
+void GpuBackend::execute(GpuHashJoinStage &st) {
+    const uint32_t T = (uint32_t)_devices.size();
+    const uint32_t np = (uint32_t)st.probePartitions.size();
+    st.tasks = T;
+    struct Task {
+        std::vector<std::vector<uint8_t>> out;
+        uint64_t n_out = 0;
+        double kernel_ms = 0, build_ms = 0;
+        std::exception_ptr error;
+    };
+    std::vector<Task> tasks(T);
+    const uint32_t flags = (st.leftOuter ? TPLX_JOIN_LEFT_OUTER : 0) | (st.buildFirst ? TPLX_JOIN_BUILD_FIRST : 0);
+    auto run_task = [&](uint32_t t) {
+        Task &tk = tasks[t];
+        tplx_block *bb = nullptr, *pb = nullptr;
+        tplx_join *jn = nullptr;
+        tplx_result *res = nullptr;
+        try {
+            std::vector<const uint8_t *> ptrs;
+            std::vector<uint64_t> sizes;
+            for (auto &p : st.buildPartitions) {
+                ptrs.push_back(p.data());
+                sizes.push_back(p.size());
+            }
+            check(tplx_gpu_block_from_partitions(_devices[t], ptrs.data(), sizes.data(), (uint32_t)ptrs.size(), st.buildColumnTypes.data(),
+                                                 (uint32_t)st.buildColumnTypes.size(), &bb), "tplx_gpu_block_from_partitions(build)");
+            check(tplx_gpu_join_build(bb, st.buildKey, &jn), "tplx_gpu_join_build");
+            check(tplx_gpu_join_info(jn, nullptr, nullptr, &tk.build_ms, nullptr), "tplx_gpu_join_info");
+            const uint32_t base = np / T, rem = np % T;
+            const uint32_t lo = t * base + std::min(t, rem), hi = lo + base + (t < rem ? 1 : 0);
+            ptrs.clear();
+            sizes.clear();
+            for (uint32_t p = lo; p < hi; ++p) {
+                ptrs.push_back(st.probePartitions[p].data());
+                sizes.push_back(st.probePartitions[p].size());
+            }
+            if (!ptrs.empty()) {
+                check(tplx_gpu_block_from_partitions(_devices[t], ptrs.data(), sizes.data(), (uint32_t)ptrs.size(), st.probeColumnTypes.data(),
+                                                     (uint32_t)st.probeColumnTypes.size(), &pb), "tplx_gpu_block_from_partitions(probe)");
+                check(tplx_gpu_join_probe(jn, pb, st.probeKey, flags, &res), "tplx_gpu_join_probe");
+                tplx_result_info info;
+                check(tplx_gpu_result_info(res, &info), "tplx_gpu_result_info");
+                tk.n_out = info.n_out_rows;
+                tk.kernel_ms = info.kernel_ms;
+                tk.out = fetch_partitions(res, st.partitionSize, "tplx_gpu_result_partitions(join)");
+            }
+        } catch (...) {
+            tk.error = std::current_exception();
+        }
+        if (res) tplx_gpu_result_free(res);
+        if (jn) tplx_gpu_join_destroy(jn);
+        if (pb) tplx_gpu_block_free(pb);
+        if (bb) tplx_gpu_block_free(bb);
+    };
+    if (T == 1) run_task(0);
+    else {
+        std::vector<std::thread> th;
+        for (uint32_t t = 0; t < T; ++t) th.emplace_back(run_task, t);
+        for (auto &x : th) x.join();
+    }
+    for (auto &tk : tasks)
+        if (tk.error) std::rethrow_exception(tk.error);
+    st.outputPartitions.clear();
+    st.numOutputRows = 0;
+    st.kernelMs = st.buildMs = 0;
+    for (auto &tk : tasks) {
+        for (auto &p : tk.out) st.outputPartitions.push_back(std::move(p));
+        st.numOutputRows += tk.n_out;
+        st.kernelMs += tk.kernel_ms;
+        st.buildMs += tk.build_ms;
+    }
+}
+
 }  // namespace tuplex_b200

@@ -50,6 +50,22 @@ struct GpuTransformStage {
     uint8_t endpoint() const;  // tplx_endpoint read from the descriptor header
 };
 
+// a JoinOperator between two executed stages (HashJoinStage, tuplex/core/include/physical/HashJoinStage.h): the build side's rows
+// and the probe side's rows as reference-format partitions, key column per side, result as partitions
+struct GpuHashJoinStage {
+    std::vector<uint8_t> probeColumnTypes, buildColumnTypes;  // tplx_type per column, | TPLX_T_OPTION for Option[T] fields
+    std::vector<std::vector<uint8_t>> probePartitions, buildPartitions;
+    uint32_t probeKey = 0, buildKey = 0;
+    bool leftOuter = false;   // JoinType::LEFT: unmatched probe rows are emitted with None build columns
+    bool buildFirst = false;  // the build side is the LEFT dataset (JoinOperator::buildRight() == false): its columns come first
+    uint64_t partitionSize = 32ull << 20;
+    // ---- result ----
+    std::vector<std::vector<uint8_t>> outputPartitions;  // | left non-key | key | right non-key | rows, probe order
+    uint64_t numOutputRows = 0;
+    double kernelMs = 0, buildMs = 0;
+    uint32_t tasks = 0;
+};
+
 class GpuBackend {
 public:
     // devices: one task per entry. Distinct devices get an NCCL communicator (tplx_gpu_comm_init_local); the same device may be
@@ -58,6 +74,10 @@ public:
     ~GpuBackend();
     // IBackend::execute(PhysicalStage*): run the normal case of one stage over all its input partitions
     void execute(GpuTransformStage &stage);
+    // HashJoinStage::execute's job on the GPU (K8): every task builds the table on its device from all build partitions
+    // (broadcast of the small side, like the reference hands one hash map to every task through init_stage_f, CodeDefs.h:94) and
+    // probes its contiguous run of probe partitions; outputs are concatenated in task order = probe order
+    void execute(GpuHashJoinStage &stage);
     // called once per task that produced exception rows, with that task's exception partition (row numbers local to the task),
     // from the task's thread — the hook where the reference schedules its ResolveTask
     void setExceptionHandler(std::function<void(uint32_t task, const std::vector<uint8_t> &exceptionPartition)> fn) { _onExceptions = std::move(fn); }

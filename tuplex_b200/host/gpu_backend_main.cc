@@ -26,7 +26,48 @@ static void dump(const std::string &path, const std::vector<uint8_t> &b) {
     f.write(reinterpret_cast<const char *>(b.data()), (std::streamsize)b.size());
 }
 
+// tplx_host_run --join <probe coltypes> <probe key> <build coltypes> <build key> <flags: 1 left outer, 2 build first> <partition_size>
+//               <out_prefix> <devices: 0 or 0,1,..> <n_build_parts> <build part files...> <probe part files...>
+static int main_join(int argc, char **argv) {
+    if (argc < 12) {
+        std::fprintf(stderr, "usage: %s --join <probe types> <probe key> <build types> <build key> <flags> <partition_size> <out_prefix> <devices> <n_build> <files...>\n", argv[0]);
+        return 2;
+    }
+    try {
+        tuplex_b200::GpuHashJoinStage st;
+        auto types = [](const char *a) {
+            std::vector<uint8_t> v;
+            std::stringstream ss(a);
+            for (std::string tok; std::getline(ss, tok, ',');) v.push_back((uint8_t)std::atoi(tok.c_str()));
+            return v;
+        };
+        st.probeColumnTypes = types(argv[2]);
+        st.probeKey = (uint32_t)std::atoi(argv[3]);
+        st.buildColumnTypes = types(argv[4]);
+        st.buildKey = (uint32_t)std::atoi(argv[5]);
+        const int flags = std::atoi(argv[6]);
+        st.leftOuter = flags & 1;
+        st.buildFirst = flags & 2;
+        st.partitionSize = std::strtoull(argv[7], nullptr, 10);
+        const std::string prefix = argv[8];
+        std::vector<int32_t> devices;
+        for (uint8_t d : types(argv[9])) devices.push_back(d);
+        const int nb = std::atoi(argv[10]);
+        for (int i = 11; i < argc; ++i) (i < 11 + nb ? st.buildPartitions : st.probePartitions).push_back(slurp(argv[i]));
+        tuplex_b200::GpuBackend backend(devices);
+        backend.execute(st);
+        for (size_t p = 0; p < st.outputPartitions.size(); ++p) dump(prefix + ".out" + std::to_string(p), st.outputPartitions[p]);
+        std::printf("{\"out_rows\": %llu, \"out_partitions\": %zu, \"tasks\": %u, \"kernel_ms\": %.3f, \"build_ms\": %.3f}\n",
+                    (unsigned long long)st.numOutputRows, st.outputPartitions.size(), st.tasks, st.kernelMs, st.buildMs);
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "error: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}
+
 int main(int argc, char **argv) {
+    if (argc > 1 && std::string(argv[1]) == "--join") return main_join(argc, argv);
     if (argc < 6) {
         std::fprintf(stderr, "usage: %s <descriptor.bin> <coltypes> <partition_size> <out_prefix> <part.bin>...\n", argv[0]);
         return 2;
