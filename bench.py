@@ -91,13 +91,17 @@ class Clocks:
                 "samples": len(self.samples)}
 
 
+STAGE_KERNEL_SOURCES = ("strops.cuh", "csvops.cuh", "vm.cuh", "kernels.cuh", "vecvm.cuh", "fused.cuh", "mask.cuh", "jit.inl")
+
+
 def kernel_source_hash():
-    """sha256 over the CUDA sources: the key that ties profiles/traffic.json (DRAM bytes from an `ncu --set full` capture) to the
-    code it was captured from."""
+    """sha256 over the sources of the stage kernels the headline workloads launch (row / mask / vector / fused kernels, the VM, the string
+    primitives, the specialiser): the key that ties profiles/traffic.json (DRAM bytes from an `ncu --set full` capture, tools/make_traffic.py)
+    to the code it was captured from. Sources of other kernels (CSV, join, merge, hash) do not enter it."""
     import hashlib
     h = hashlib.sha256()
     d = os.path.join(ROOT, "tuplex_b200", "csrc")
-    for f in sorted(os.listdir(d)):
+    for f in STAGE_KERNEL_SOURCES:
         h.update(f.encode())
         h.update(open(os.path.join(d, f), "rb").read())
     return h.hexdigest()[:16]
@@ -874,7 +878,10 @@ def main():
         extras["aggbykey"] = measure(xb, "aggbykey", rank, world, local, dist, hc)
         xj = argparse.Namespace(**vars(xa))
         xj.no_cpu_baseline = args.no_cpu_baseline
-        extras["join"] = measure_join(xj, rank, world, local, dist)
+        try:
+            extras["join"] = measure_join(xj, rank, world, local, dist)
+        except Exception as e:  # noqa: BLE001 — an extra must never take the headline line down with it
+            extras["join"] = {"workload": "join_broadcast", "error": repr(e)[:300]}
     if rank == 0:
         k0 = keys[0]
         cfg = static_config(args, k0)
