@@ -37,3 +37,19 @@ def test_resolve_and_ignore_leave_the_parent_plan_alone():
     assert a._ops[-1].id == b._ops[-1].id == c._ops[-1].id  # same operator: exception counts are keyed by its id
     d = b.resolve(ValueError, lambda r: -2)
     assert len(b._ops[-1].resolvers) == 1 and len(d._ops[-1].resolvers) == 2
+
+
+def test_types_and_text_source(tmp_path):
+    """DataSet.types from the plan (python/tuplex/dataset.py:374-382) and Context.text (python/tuplex/context.py:367-387), no device."""
+    import typing
+    import tuplex_b200 as tuplex
+    c = tuplex.Context()
+    ds = c.parallelize([(1, "a", None), (2, "b", 3.5)], columns=["i", "s", "f"])
+    assert ds.types == [int, str, typing.Optional[float]]
+    assert ds.map(lambda x: (x["i"] * 2, x["s"].upper(), x["f"] is None)).types == [int, str, bool]
+    assert ds.withColumn("g", lambda x: None if x["i"] > 1 else x["s"]).types == [int, str, typing.Optional[float], typing.Optional[str]]
+    p = tmp_path / "t.txt"
+    p.write_text("hello\nNULL\n\nworld\r\n")
+    t = c.text(str(p), null_values=["NULL"])
+    assert t._source.cols[0].to_values() == ["hello", None, "", "world"] and t.types == [typing.Optional[str]]
+    assert c.text(str(p))._source.cols[0].to_values() == ["hello", "NULL", "", "world"]

@@ -200,6 +200,25 @@ class Context:
             return None  # ints beyond 64 bits take the general path (fallback rows)
         return Source(cols, names, n, None, [], n)
 
+    def text(self, pattern, null_values=None) -> DataSet:
+        """tuplex.Context.text (python/tuplex/context.py:367-387): every line of the files is one row of type str; lines equal to a
+        null value become None (the column is then Option[str])."""
+        null_values = list(null_values or [])
+        lines: List[Optional[str]] = []
+        for fn in sorted(f for p in pattern.split(",") for f in (glob.glob(p) or [p])):
+            try:
+                with open(fn, "r", encoding="utf-8", errors="replace", newline="") as fp:
+                    data = fp.read()
+            except OSError:
+                self._log(f"text: no such file {fn!r}")
+                continue
+            part = data.split("\n")
+            if part and part[-1] == "":
+                part.pop()  # the newline that ends the last line does not start another one
+            lines.extend(ln[:-1] if ln.endswith("\r") else ln for ln in part)
+        rows = [None if ln in null_values else ln for ln in lines]
+        return DataSet(self, self._source_from_rows(rows, None))
+
     def csv(self, pattern, columns=None, header=None, delimiter=None, quotechar='"', null_values=[''], type_hints={}) -> DataSet:
         """tuplex.Context.csv (python/tuplex/context.py:203-290). Planning (delimiter, header, normal-case types) looks at
         a sample of the first file on the host, like the reference's CSVStatistic; the rows themselves are parsed on

@@ -230,6 +230,45 @@ class DataSet:
         return names
 
     @property
+    def types(self):
+        """Output schema as a list of `typing` types (python/tuplex/dataset.py:374-382), from the plan alone where the operators
+        compile for the device (Option[T] columns -> typing.Optional[T]); datasets behind a join / an interpreter-path stage are
+        typed from their first rows."""
+        import typing
+        py = {T_I64: int, T_F64: float, T_BOOL: bool, T_STR: str}
+        if self._join is None and self._parent is None and self._source is not None and not hasattr(self._source, "chunks"):
+            try:
+                sc = StageCompiler([c.type for c in self._source.cols], self._source.names, _option_cols(self._source.cols))
+                for o in self._ops:
+                    if o.kind == "map":
+                        sc.add_map(o.udf, o.id)
+                    elif o.kind == "filter":
+                        sc.add_filter(o.udf, o.id)
+                    elif o.kind == "withColumn":
+                        sc.add_with_column(o.column, o.udf, o.id)
+                    elif o.kind == "mapColumn":
+                        sc.add_map_column(o.column, o.udf, o.id)
+                    elif o.kind == "selectColumns":
+                        sc.add_select(o.columns, o.id)
+                    elif o.kind == "renameColumn":
+                        sc.add_rename(o.column, o.extra, o.id)
+                    else:
+                        raise UnsupportedUDF("endpoint")
+                return [typing.Optional[py[v.type]] if v.null is not None else py[v.type] for v in sc.row]
+            except (UnsupportedUDF, KeyError):
+                pass
+        rows = self.take(64)
+        if not rows:
+            return None
+        tup = [r if isinstance(r, tuple) else (r,) for r in rows]
+        out = []
+        for c in range(len(tup[0])):
+            ts = {type(r[c]) for r in tup if len(r) > c and r[c] is not None}
+            t = ts.pop() if len(ts) == 1 else typing.Any
+            out.append(typing.Optional[t] if any(len(r) > c and r[c] is None for r in tup) else t)
+        return out
+
+    @property
     def exception_counts(self):
         return dict(self._last_exceptions)
 
