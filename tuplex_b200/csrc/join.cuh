@@ -34,6 +34,7 @@ namespace tplx {
 constexpr uint32_t JOIN_NONE = 0xFFFFFFFFu;
 constexpr uint32_t JOIN_NT = 256;
 constexpr uint32_t JOIN_SMALL = 32;  // groups up to this size are ordered by one thread
+constexpr uint32_t JOIN_STR_LANES = 8;  // lanes that copy one output string
 
 struct JoinKey {            // a key column (build or probe side)
     const void *data;       // 8-byte values, or string bytes
@@ -251,7 +252,7 @@ __global__ void __launch_bounds__(JOIN_NT) join_gather_valid_kernel(const uint32
     const uint32_t w = __ballot_sync(0xFFFFFFFFu, ok);
     if ((threadIdx.x & 31) == 0 && (i >> 5) < ((n + 31) >> 5)) dst_words[i >> 5] = w;
 }
-// strings: lengths (then an exclusive scan), then one warp per output row copies the bytes
+// strings: lengths (then an exclusive scan), then JOIN_STR_LANES lanes per output row copy the bytes
 __global__ void __launch_bounds__(JOIN_NT) join_str_len_kernel(const uint32_t *__restrict__ src_off, const uint32_t *__restrict__ idx, uint64_t n,
                                                                uint64_t *__restrict__ lens) {
     const uint64_t i = (uint64_t)blockIdx.x * JOIN_NT + threadIdx.x;
@@ -262,16 +263,19 @@ __global__ void __launch_bounds__(JOIN_NT) join_str_len_kernel(const uint32_t *_
 __global__ void __launch_bounds__(JOIN_NT) join_str_copy_kernel(const uint8_t *__restrict__ src, const uint32_t *__restrict__ src_off,
                                                                 const uint32_t *__restrict__ idx, uint64_t n, const uint64_t *__restrict__ pos,
                                                                 uint32_t *__restrict__ dst_off, uint8_t *__restrict__ dst) {
-    const uint64_t i = ((uint64_t)blockIdx.x * JOIN_NT + threadIdx.x) >> 5;
-    const uint32_t lane = threadIdx.x & 31;
+    // JOIN_STR_LANES lanes per output row: the strings of this path are short (codes, names: 8 B in the bench's table), a whole warp per
+    // row spent 3.1 G warp-instructions on 45 M rows (ncu, profiles/r02_ncu_kernels.md); 8 lanes keep one byte per lane and row in flight
+    const uint64_t t = (uint64_t)blockIdx.x * JOIN_NT + threadIdx.x;
+    const uint64_t i = t / JOIN_STR_LANES;
+    const uint32_t sub = (uint32_t)(t % JOIN_STR_LANES);
     if (i > n) return;
     const uint64_t d0 = pos[i];
-    if (lane == 0) dst_off[i] = (uint32_t)d0;  // entry n = total
+    if (sub == 0) dst_off[i] = (uint32_t)d0;  // entry n = total
     if (i == n) return;
     const uint32_t r = idx[i];
     if (r == JOIN_NONE) return;
     const uint32_t s0 = src_off[r], len = src_off[r + 1] - s0;
-    for (uint32_t k = lane; k < len; k += 32) dst[d0 + k] = src[s0 + k];
+    for (uint32_t k = sub; k < len; k += JOIN_STR_LANES) dst[d0 + k] = src[s0 + k];
 }
 
 }  // namespace tplx

@@ -61,12 +61,14 @@ __global__ void __launch_bounds__(256) merge_str_len_kernel(const uint32_t *__re
     lens[i] = o[r + 1] - o[r];
 }
 
-// one warp per output row
+// MERGE_STR_LANES lanes per output row (short strings: see join_str_copy_kernel)
+constexpr uint32_t MERGE_STR_LANES = 8;
 __global__ void __launch_bounds__(256) merge_str_copy_kernel(const uint8_t *__restrict__ da, const uint32_t *__restrict__ oa, const uint8_t *__restrict__ db,
                                                              const uint32_t *__restrict__ ob, const uint32_t *__restrict__ sel, uint64_t n,
                                                              const uint64_t *__restrict__ pos, uint32_t *__restrict__ dst_off, uint8_t *__restrict__ dst) {
-    const uint64_t i = ((uint64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
-    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    const uint64_t i = t / MERGE_STR_LANES;
+    const uint32_t lane = (uint32_t)(t % MERGE_STR_LANES);
     if (i > n) return;
     const uint64_t d0 = pos[i];
     if (lane == 0) dst_off[i] = (uint32_t)d0;  // entry n = total
@@ -75,7 +77,7 @@ __global__ void __launch_bounds__(256) merge_str_copy_kernel(const uint8_t *__re
     const uint8_t *src = (s & MERGE_B) ? db : da;
     const uint32_t *o = (s & MERGE_B) ? ob : oa;
     const uint32_t s0 = o[r], len = o[r + 1] - s0;
-    for (uint32_t k = lane; k < len; k += 32) dst[d0 + k] = src[s0 + k];
+    for (uint32_t k = lane; k < len; k += MERGE_STR_LANES) dst[d0 + k] = src[s0 + k];
 }
 
 }  // namespace tplx

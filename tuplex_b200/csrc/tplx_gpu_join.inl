@@ -150,7 +150,7 @@ static int32_t join_gather_column(tplx_result *r, size_t oc, const tplx_block *s
         if (tot > 0xFFFFFFFFull) { cudaFreeAsync(lens, d->stream); return fail(TPLX_E_OVERFLOW, "join_probe: an output string column exceeds 4 GiB; probe smaller blocks"); }
         if ((rc = dalloc(r, &r->out[oc].offsets, n_out + 1))) return rc;
         if ((rc = dalloc(r, &r->out[oc].bytes, (size_t)align_up(tot, 16) + 16))) return rc;
-        const uint32_t nw = (uint32_t)(((n_out + 1) * 32 + JOIN_NT - 1) / JOIN_NT);
+        const uint32_t nw = (uint32_t)(((n_out + 1) * JOIN_STR_LANES + JOIN_NT - 1) / JOIN_NT);
         join_str_copy_kernel<<<nw, JOIN_NT, 0, d->stream>>>(reinterpret_cast<const uint8_t *>(src->cols[c].data), src->cols[c].offsets, idx, n_out, lens,
                                                             r->out[oc].offsets, r->out[oc].bytes);
         CU(cudaFreeAsync(lens, d->stream));

@@ -77,7 +77,7 @@ extern "C" int32_t tplx_gpu_result_merge_resolved(tplx_result *res, const tplx_b
             if (tot > 0xFFFFFFFFull) { cudaFreeAsync(lens, d->stream); return fail(TPLX_E_OVERFLOW, "result_merge_resolved: a string column exceeds 4 GiB"); }
             if ((rc = dalloc(r, &r->out[c].offsets, n + 1))) return rc;
             if ((rc = dalloc(r, &r->out[c].bytes, (size_t)align_up(tot, 16) + 16))) return rc;
-            const uint32_t nw = (uint32_t)(((n + 1) * 32 + 255) / 256);
+            const uint32_t nw = (uint32_t)(((n + 1) * MERGE_STR_LANES + 255) / 256);
             merge_str_copy_kernel<<<nw, 256, 0, d->stream>>>(res->out[c].bytes, res->out[c].offsets, reinterpret_cast<const uint8_t *>(resolved->cols[c].data),
                                                             resolved->cols[c].offsets, sel, n, lens, r->out[c].offsets, r->out[c].bytes);
             CU(cudaFreeAsync(lens, d->stream));
