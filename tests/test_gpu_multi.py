@@ -177,6 +177,11 @@ def test_context_over_two_devices(gpu):
     byk = lambda c: c.parallelize(data, columns=["a", "b", "s"]).aggregateByKey(lambda x, y: x + y, lambda acc, r: acc + r["a"], 0, ["s"]).collect()
     assert sorted(byk(two)) == sorted(byk(one)) and len(byk(one)) == 100
     assert sorted(two.parallelize([r[2] for r in data]).unique().collect()) == sorted({r[2] for r in data})
+    # K8: the build side is broadcast to both devices (one table each), the probe blocks are sharded; concatenation = probe order
+    dim = [("w%d" % k, k * 10, None if k % 7 == 0 else float(k)) for k in range(0, 120, 2)]
+    jn = lambda c: (c.parallelize(data, columns=["a", "b", "s"]).leftJoin(c.parallelize(dim, columns=["w", "v", "f"]), "s", "w", prefixes=(None, "d_"))
+                     .filter(lambda x: x["d_v"] is None or x["d_v"] % 20 == 0).collect())
+    assert jn(two) == jn(one) and len(jn(one)) > 1000
 
 
 def test_cpp_host_two_devices(gpu, tmp_path):
