@@ -396,3 +396,16 @@ def join_rows(left_rows: Sequence[tuple], left_key: int, right_rows: Sequence[tu
         key = lrow[left_key] if build_right else right_rows[r][right_key]
         out.append(tuple(v for i, v in enumerate(lrow) if i != left_key) + (key,) + tuple(v for i, v in enumerate(rrow) if i != right_key))
     return out
+
+
+# ---- in-order merge of resolved rows (merge_oracle.c) ------------------------------------------------------------------------
+def merge_sources(n_norm: int, exc_row_nos: Sequence[int], resolved: Sequence[bool]) -> np.ndarray:
+    """Source of every row of the merged output stream: j >= 0 = normal row j, ~m = the m-th resolved exception (ResolveTask::executeInOrder)."""
+    L = lib()
+    L.tplx_oracle_merge.restype = ct.c_uint64
+    L.tplx_oracle_merge.argtypes = [ct.c_uint64, ct.c_void_p, ct.c_void_p, ct.c_uint64, ct.c_void_p]
+    nos = np.ascontiguousarray(exc_row_nos, dtype=np.int64)
+    res = np.ascontiguousarray(resolved, dtype=np.uint8)
+    out = np.empty(n_norm + len(nos) + 1, np.int64)
+    n = L.tplx_oracle_merge(n_norm, nos.ctypes.data, res.ctypes.data, len(nos), out.ctypes.data)
+    return out[:n].copy()

@@ -16,6 +16,31 @@ def _stage():
     return sc.finish_memory()
 
 
+def test_merge_closed_form_equals_reference_walk():
+    """K9's closed form (normal row j -> j + #{m : a_m <= j}, resolved row m -> a_m + m, a_m = row number - exceptions before it) and the
+    host restatement `_merge_by_rowno` against the oracle's literal walk of ResolveTask::executeInOrder (oracle/merge_oracle.c)."""
+    from oracle import pyoracle
+    rng = np.random.default_rng(2)
+    for trial in range(200):
+        n_norm, n_exc = int(rng.integers(0, 60)), int(rng.integers(0, 25))
+        # a task's output stream: n_norm + n_exc slots, the exceptions sit at random distinct slots
+        slots = np.sort(rng.choice(n_norm + n_exc, n_exc, replace=False)) if n_exc else np.zeros(0, np.int64)
+        resolved = rng.random(n_exc) < 0.6
+        want = pyoracle.merge_sources(n_norm, slots, resolved)
+        a = np.array([int(slots[k]) - k for k in range(n_exc) if resolved[k]], np.int64)
+        closed = np.empty(n_norm + len(a), np.int64)
+        for j in range(n_norm):
+            closed[j + int(np.searchsorted(a, j, side="right"))] = j
+        for m, am in enumerate(a.tolist()):
+            closed[am + m] = ~m
+        assert closed.tolist() == want.tolist()
+        exc = np.zeros(n_exc, dtype=backend.EXC_DTYPE)
+        exc["row_no"] = slots
+        res_rows = [(0, int(slots[k]), "R%d" % m) for m, k in enumerate([k for k in range(n_exc) if resolved[k]])]
+        host = _merge_by_rowno(["n%d" % j for j in range(n_norm)], exc, res_rows)
+        assert host == ["n%d" % v if v >= 0 else "R%d" % ~v for v in want.tolist()]
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("first_row_no", [0, 1000])
 def test_device_merge_equals_host_merge(gpu, first_row_no):
