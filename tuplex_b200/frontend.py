@@ -59,10 +59,19 @@ def _code_signature(code: types.CodeType):
 
 def get_udf_ast(func) -> Tuple[List[str], Union[ast.expr, List[ast.stmt]], Dict[str, Any]]:
     """Return (argument names, body, resolvable globals/closure) for a lambda or def."""
-    if isinstance(func, str):  # source string, like the reference's UDF("lambda x: ...") in C++ tests
-        node = ast.parse(func.strip(), mode="eval").body
+    if isinstance(func, str):  # source string, like the reference's UDF("lambda x: ...") / UDF("def f(x):\n ...") in C++ tests
+        src = func.strip()
+        if src.startswith("def "):
+            import textwrap
+            mod = ast.parse(textwrap.dedent(func).strip().expandtabs(4))
+            fns = [n for n in mod.body if isinstance(n, ast.FunctionDef)]
+            if len(fns) != 1:
+                raise UnsupportedUDF("UDF string must hold one function")
+            _check_args(fns[0].args)
+            return [a.arg for a in fns[0].args.args], fns[0].body, {}
+        node = ast.parse(src, mode="eval").body
         if not isinstance(node, ast.Lambda):
-            raise UnsupportedUDF("UDF string must be a lambda")
+            raise UnsupportedUDF("UDF string must be a lambda or a def")
         return [a.arg for a in node.args.args], node.body, {}
     if not isinstance(func, types.FunctionType):
         raise UnsupportedUDF(f"not a plain Python function: {func!r}")
@@ -1722,7 +1731,14 @@ class _FuncCompiler:
             if name == "float" and len(args) == 1 and not sc.is_const(args[0]):
                 return sc.op1(C["TPLX_OP_S2F"], T_F64, args[0])  # fast_atod semantics (FunctionRegistry.cc createFloatCast)
             if name == "bool" and len(args) == 1:
-                return sc.truth(args[0])
+                a = args[0]
+                if isinstance(a, Val) and a.type == T_F64 and not sc.is_const(a):
+                    # bool(f64) is NOT the truth test of `if x:`: createBoolCast compares with FCMP_OEQ and negates (FunctionRegistry.cc:396-399),
+                    # so bool(nan) is True like in Python, while `if nan:` is false in the reference (truthValueTest, FCMP_ONE,
+                    # LLVMEnvironment.cc:922-927; gtest golden UseCaseFunctionsTest.cc:183-197)
+                    v = sc.b_not(sc.op2(C["TPLX_OP_FCMP"], T_BOOL, plain(a), const_val(0.0), flags=C["TPLX_CMP_EQ"]))
+                    return v if a.null is None else sc.b_and(sc.b_not(a.null), v)
+                return sc.truth(a)
             if name == "len" and len(args) == 1 and args[0].type == T_STR:
                 return const_val(len(args[0].const)) if sc.is_const(args[0]) else sc.op1(C["TPLX_OP_SLEN"], T_I64, args[0])
             if name == "str" and len(args) == 1:

@@ -72,11 +72,31 @@ class Dropped(Exception):
     pass
 
 
+_SRC_CACHE: dict = {}
+
+
+def udf_from_source(src: str):
+    """A UDF given as source text (the reference's UDF("lambda x: ...") / UDF("def f(x): ...")): compiled once."""
+    fn = _SRC_CACHE.get(src)
+    if fn is None:
+        text = src.strip()
+        if text.startswith("def "):
+            import textwrap
+            ns: dict = {}
+            exec(textwrap.dedent(src).strip().expandtabs(4), ns)  # noqa: S102 — user code, like any UDF
+            fns = [v for k, v in ns.items() if callable(v) and not k.startswith("__")]
+            fn = fns[-1]
+        else:
+            fn = eval(text)  # noqa: S307
+        _SRC_CACHE[src] = fn
+    return fn
+
+
 def _call(udf, value, names):
     """Call a UDF with Tuplex's argument convention: one column -> the value itself, many -> a Row;
     a multi-parameter lambda unpacks the row."""
     if isinstance(udf, str):
-        udf = eval(udf)  # UDF given as source string
+        udf = udf_from_source(udf)
     if isinstance(value, tuple):
         n = udf.__code__.co_argcount
         if n > 1 and n == len(value):
@@ -132,7 +152,7 @@ def run_row(ops: Sequence[Op], value, names: List[Optional[str]]):
             elif op.kind == "mapColumn":
                 vals = list(value) if isinstance(value, tuple) else [value]
                 i = names.index(op.column) if isinstance(op.column, str) else op.column
-                vals[i] = _apply_with_resolvers(op, lambda f: (eval(f) if isinstance(f, str) else f)(vals[i]))
+                vals[i] = _apply_with_resolvers(op, lambda f: (udf_from_source(f) if isinstance(f, str) else f)(vals[i]))
                 value = tuple(vals) if len(vals) != 1 else vals[0]
             elif op.kind == "selectColumns":
                 vals = list(value) if isinstance(value, tuple) else [value]
