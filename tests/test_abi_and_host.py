@@ -185,3 +185,21 @@ def test_csv_missing_file_gives_empty_dataset():
     assert ds.collect() == []
     ds.show()
     assert any("no such file" in m for m in ctx._messages)
+
+
+def test_cpp_host_join_fails_loudly_without_a_device(built, tmp_path):
+    """tplx_host_run --join (GpuBackend::execute(GpuHashJoinStage&)) has no CPU path either: without a device it exits non-zero with the
+    library's message instead of producing rows."""
+    import subprocess
+    from oracle import pyoracle
+    if backend.device_count() > 0:
+        pytest.skip("a GPU is visible")
+    cols = [backend.Column(T_I64, np.arange(4, dtype=np.int64))]
+    (part,) = pyoracle.to_partitions(cols, 4, 1 << 16)
+    f = tmp_path / "p.bin"
+    f.write_bytes(part)
+    exe = os.path.join(ROOT, "tuplex_b200", "lib", "tplx_host_run")
+    r = subprocess.run([exe, "--join", "0", "0", "0", "0", "0", str(1 << 16), str(tmp_path / "out"), "0", "1", str(f), str(f)],
+                       capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0 and "error" in r.stderr.lower()
+    assert not (tmp_path / "out.out0").exists()
