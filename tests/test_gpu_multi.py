@@ -177,11 +177,29 @@ def test_context_over_two_devices(gpu):
     byk = lambda c: c.parallelize(data, columns=["a", "b", "s"]).aggregateByKey(lambda x, y: x + y, lambda acc, r: acc + r["a"], 0, ["s"]).collect()
     assert sorted(byk(two)) == sorted(byk(one)) and len(byk(one)) == 100
     assert sorted(two.parallelize([r[2] for r in data]).unique().collect()) == sorted({r[2] for r in data})
-    # K8: the build side is broadcast to both devices (one table each), the probe blocks are sharded; concatenation = probe order
+
+
+def test_context_join_over_two_devices(gpu):
+    """K8 with tuplex.gpu.devices='0,1': the build side is broadcast (one table per device), the probe blocks are sharded contiguously,
+    the concatenation in device order is the probe order — equal to the one-device result."""
+    import random
+    import tuplex_b200
+    from tuplex_b200 import backend
+    if backend.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    rng = random.Random(9)
+    data = [(rng.randint(-50, 50), rng.randint(0, 6), "w%d" % rng.randint(0, 99)) for _ in range(60_000)]
     dim = [("w%d" % k, k * 10, None if k % 7 == 0 else float(k)) for k in range(0, 120, 2)]
-    jn = lambda c: (c.parallelize(data, columns=["a", "b", "s"]).leftJoin(c.parallelize(dim, columns=["w", "v", "f"]), "s", "w", prefixes=(None, "d_"))
-                     .filter(lambda x: x["d_v"] is None or x["d_v"] % 20 == 0).collect())
-    assert jn(two) == jn(one) and len(jn(one)) > 1000
+    one = tuplex_b200.Context({"tuplex.gpu.blockRows": 7000})
+    two = tuplex_b200.Context({"tuplex.gpu.blockRows": 7000, "tuplex.gpu.devices": "0,1"})
+
+    def run(c):
+        left = c.parallelize(data, columns=["a", "b", "s"])
+        right = c.parallelize(dim, columns=["w", "v", "f"])
+        return left.leftJoin(right, "s", "w", prefixes=(None, "d_")).collect()
+    got1, got2 = run(one), run(two)
+    assert got2 == got1 and len(got1) == len(data)
+    assert sum(1 for r in got1 if r[3] is None) == sum(1 for r in data if int(r[2][1:]) % 2 == 1 or int(r[2][1:]) >= 120)
 
 
 def test_cpp_host_two_devices(gpu, tmp_path):
